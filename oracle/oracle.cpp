@@ -1,0 +1,1452 @@
+// oracle.cpp - CPU ORACLE for the g2o LM/GN hot path.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+//
+// A from-scratch, Eigen-free restatement of the reference's CPU path, in the reference's operation
+// order (edges in internalId order, upper-triangular block Hessian, column-major blocks), linked
+// against the reference's own vendored CSparse (oracle/_ref/libg2o_csparse_ref.so) for cs_amd,
+// cs_symperm/etree/post/counts, and csparse_extension::cs_cholsolsymb.
+//
+// Every function cites the reference file:line it restates.  Paths are relative to
+// /root/reference/g2o unless they start with EXTERNAL/.
+//
+// Parity pinning status: pinned by BASELINE.md section 2 known answers (block-AMD permutation hashes and
+// nnz(L) for the four in-tree datasets, tests/test_oracle.py); CHOLMOD flavour: "parity unpinned".
+#include "oracle.h"
+
+#include <algorithm>
+#include <array>
+#include <cassert>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <time.h>
+#include <tr1/unordered_map>
+#include <vector>
+
+#ifndef NCOMPLEX
+#define NCOMPLEX
+#endif
+#include <cs.h>  // reference header, found via -I$(REF)/EXTERNAL/csparse at oracle build time
+
+// solvers/csparse/csparse_helper.h:41-42 (compiled from the reference into libg2o_csparse_ref.so)
+namespace g2o { namespace csparse_extension {
+int cs_cholsolsymb(const cs* A, double* b, const css* S, double* workspace, int* work);
+} }
+
+namespace {
+
+// stuff/timeutil.h:107 get_monotonic_time
+inline double now() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+// stuff/misc.h:94-106
+inline double normalize_theta(double theta) {
+  if (theta >= -M_PI && theta < M_PI) return theta;
+  double multiplier = floor(theta / (2 * M_PI));
+  theta = theta - multiplier * 2 * M_PI;
+  if (theta >= M_PI) theta -= 2 * M_PI;
+  if (theta < -M_PI) theta += 2 * M_PI;
+  return theta;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiny column-major dense helpers (stand-ins for the Eigen fixed-size expressions)
+// ---------------------------------------------------------------------------------------------
+// C(RxC) = A(RxK) * B(KxC)
+template <int R, int K, int C>
+inline void mm(const double* A, const double* B, double* Cm) {
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < R; ++r) {
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += A[r + k * R] * B[k + c * K];
+      Cm[r + c * R] = s;
+    }
+}
+// C(RxC) = A^T (A is KxR) * B (KxC)
+template <int R, int K, int C>
+inline void mtm(const double* A, const double* B, double* Cm) {
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < R; ++r) {
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += A[k + r * K] * B[k + c * K];
+      Cm[r + c * R] = s;
+    }
+}
+// C(RxC) = A (RxK) * B^T (B is CxK)
+template <int R, int K, int C>
+inline void mmt(const double* A, const double* B, double* Cm) {
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < R; ++r) {
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += A[r + k * R] * B[c + k * C];
+      Cm[r + c * R] = s;
+    }
+}
+
+// Eigen Quaterniond::toRotationMatrix (Eigen/src/Geometry/Quaternion.h); q = (x,y,z,w); R col-major
+inline void quat_to_R(const double* q, double* R) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[3] = txy - twz;       R[6] = txz + twy;
+  R[1] = txy + twz;       R[4] = 1 - (txx + tzz); R[7] = tyz - twx;
+  R[2] = txz - twy;       R[5] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+// Eigen Quaterniond(Matrix3d) (restated in-tree at types/slam3d/test_mat2quat_jacobian.cpp:42-83)
+inline void R_to_quat(const double* R, double* q) {
+  auto m = [&](int r, int c) { return R[r + 3 * c]; };
+  double t = m(0, 0) + m(1, 1) + m(2, 2);
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m(2, 1) - m(1, 2)) * t;
+    q[1] = (m(0, 2) - m(2, 0)) * t;
+    q[2] = (m(1, 0) - m(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (m(k, j) - m(j, k)) * t;
+    q[j] = (m(j, i) + m(i, j)) * t;
+    q[k] = (m(k, i) + m(i, k)) * t;
+  }
+}
+inline void quat_normalize(double* q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+
+// Isometry3d stored as [R col-major 9 | t 3]
+struct Iso { double R[9]; double t[3]; };
+inline Iso iso_inverse(const Iso& a) {  // Eigen Transform::inverse(Isometry): [R^T | -R^T t]
+  Iso r;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.R[i + 3 * j] = a.R[j + 3 * i];
+  for (int i = 0; i < 3; ++i) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += -r.R[i + 3 * k] * a.t[k];
+    r.t[i] = s;
+  }
+  return r;
+}
+inline Iso iso_mul(const Iso& a, const Iso& b) {
+  Iso r;
+  mm<3, 3, 3>(a.R, b.R, r.R);
+  for (int i = 0; i < 3; ++i) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += a.R[i + 3 * k] * b.t[k];
+    r.t[i] = s + a.t[i];
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph objects
+// ---------------------------------------------------------------------------------------------
+constexpr int EST_MAX = 64;  // CAM: t3 q4 K5 | w2n 12 | w2i 12 | dRdx 9 dRdy 9 dRdz 9 = 63
+
+struct Edge;
+struct Vertex {
+  int kind = 0, id = 0, dim = 0;
+  bool fixed = false, marginalized = false;
+  int hessianIndex = -1, colInHessian = -1;
+  int numOplusCalls = 0;
+  double est[EST_MAX];
+  double b[6];
+  double* H = nullptr;  // mapped diagonal block (dim x dim, col-major), base_vertex.h mapHessianMemory
+  std::vector<std::array<double, EST_MAX>> backup;
+  std::vector<Edge*> edges;
+};
+
+struct Edge {
+  int kind = 0, D = 0, internalId = 0;
+  Vertex* v[2] = {nullptr, nullptr};
+  double meas[12];     // SE2 [x y th]; SE3 Iso of Z; P2MC [u v]
+  double invMeas[12];  // cached inverse measurement (edge_se2.h:55-58, edge_se3 setMeasurement)
+  double info[36];     // D x D col-major
+  double err[6];
+  double Ji[36], Jj[36];  // D x Di, D x Dj col-major
+  double* H = nullptr;    // mapped off-diagonal block
+  bool transposed = false;  // _hessianRowMajor (base_binary_edge.hpp:207-218)
+};
+
+inline int vertex_dim(int kind) { return kind == ORC_VERTEX_SE2 ? 3 : kind == ORC_VERTEX_XYZ ? 3 : 6; }
+inline int edge_dim(int kind) { return kind == ORC_EDGE_SE2 ? 3 : kind == ORC_EDGE_SE3 ? 6 : 2; }
+
+// ---- SE2 (types/slam2d/se2.h:41-119) ----
+struct SE2 { double x, y, th; };
+inline SE2 se2_mul(const SE2& a, const SE2& b) {  // se2.h:66-78
+  SE2 r;
+  double c = cos(a.th), s = sin(a.th);
+  r.x = a.x + (c * b.x - s * b.y);
+  r.y = a.y + (s * b.x + c * b.y);
+  r.th = normalize_theta(a.th + b.th);
+  return r;
+}
+inline SE2 se2_inv(const SE2& a) {  // se2.h:86-96
+  SE2 r;
+  r.th = normalize_theta(-a.th);
+  double c = cos(r.th), s = sin(r.th);
+  double tx = a.x * -1., ty = a.y * -1.;
+  r.x = c * tx - s * ty;
+  r.y = s * tx + c * ty;
+  return r;
+}
+
+// ---- SBACam derived quantities (types/sba/sbacam.h:120-181) ----
+// est: t[0..3) q[3..7) K[7..12)=fx fy cx cy baseline | w2n[12..24) | w2i[24..36) | dRdx[36..45) dRdy dRdz
+inline void cam_refresh(double* est) {
+  double R[9];
+  quat_to_R(est + 3, R);
+  double* w2n = est + 12;  // 3x4 col-major
+  // transformW2F (sbacam.h:120-130): m.block<3,3> = R^T ; m.col(3) = -m * [t;1] with col(3) zero
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) w2n[r + 3 * c] = R[c + 3 * r];
+  for (int r = 0; r < 3; ++r) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += w2n[r + 3 * k] * est[k];
+    s += 0.0 * 1.0;
+    w2n[r + 9] = -s;
+  }
+  // setProjection (sbacam.h:159): w2i = Kcam * w2n
+  const double fx = est[7], fy = est[8], cx = est[9], cy = est[10];
+  double* w2i = est + 24;
+  for (int c = 0; c < 4; ++c) {
+    w2i[0 + 3 * c] = fx * w2n[0 + 3 * c] + 0.0 * w2n[1 + 3 * c] + cx * w2n[2 + 3 * c];
+    w2i[1 + 3 * c] = 0.0 * w2n[0 + 3 * c] + fy * w2n[1 + 3 * c] + cy * w2n[2 + 3 * c];
+    w2i[2 + 3 * c] = 0.0 * w2n[0 + 3 * c] + 0.0 * w2n[1 + 3 * c] + 1.0 * w2n[2 + 3 * c];
+  }
+  // setDr (sbacam.h:162-181): dRdx = dRidx * w2n.block<3,3>(0,0) etc.
+  static const double dRidx[9] = {0, 0, 0, 0, 0, -2, 0, 2, 0};   // col-major of [[0,0,0],[0,0,2],[0,-2,0]]
+  static const double dRidy[9] = {0, 0, 2, 0, 0, 0, -2, 0, 0};   // [[0,0,-2],[0,0,0],[2,0,0]]
+  static const double dRidz[9] = {0, -2, 0, 2, 0, 0, 0, 0, 0};   // [[0,2,0],[-2,0,0],[0,0,0]]
+  mm<3, 3, 3>(dRidx, w2n, est + 36);
+  mm<3, 3, 3>(dRidy, w2n, est + 45);
+  mm<3, 3, 3>(dRidz, w2n, est + 54);
+}
+// SE3Quat::normalizeRotation (types/slam3d/se3quat.h:280-285)
+inline void se3quat_normalize_rotation(double* q) {
+  if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] *= -1;
+  quat_normalize(q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-type error / Jacobian / oplus
+// ---------------------------------------------------------------------------------------------
+// types/slam3d/isometry3d_mappings.cpp:38-44, 77-83, 93-99  toVectorMQT
+inline void to_vector_mqt(const Iso& d, double* v) {
+  double q[4];
+  R_to_quat(d.R, q);
+  quat_normalize(q);
+  if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] *= -1;
+  v[0] = d.t[0]; v[1] = d.t[1]; v[2] = d.t[2];
+  v[3] = q[0]; v[4] = q[1]; v[5] = q[2];
+}
+
+void compute_error(Edge* e) {
+  Vertex* v0 = e->v[0];
+  Vertex* v1 = e->v[1];
+  switch (e->kind) {
+    case ORC_EDGE_SE2: {  // types/slam2d/edge_se2.h:46-52
+      SE2 x1{v0->est[0], v0->est[1], v0->est[2]}, x2{v1->est[0], v1->est[1], v1->est[2]};
+      SE2 zi{e->invMeas[0], e->invMeas[1], e->invMeas[2]};
+      SE2 d = se2_mul(zi, se2_mul(se2_inv(x1), x2));
+      e->err[0] = d.x; e->err[1] = d.y; e->err[2] = d.th;
+      break;
+    }
+    case ORC_EDGE_SE3: {  // types/slam3d/edge_se3.cpp:48-53
+      Iso Xi, Xj, Zi;
+      memcpy(&Xi, v0->est, sizeof(Iso)); memcpy(&Xj, v1->est, sizeof(Iso));
+      memcpy(&Zi, e->invMeas, sizeof(Iso));
+      Iso d = iso_mul(iso_mul(Zi, iso_inverse(Xi)), Xj);
+      to_vector_mqt(d, e->err);
+      break;
+    }
+    case ORC_EDGE_P2MC: {  // types/sba/types_sba.h:170-192
+      const double* pt = v0->est;
+      const double* w2i = v1->est + 24;
+      double p[3];
+      for (int r = 0; r < 3; ++r)
+        p[r] = w2i[r] * pt[0] + w2i[r + 3] * pt[1] + w2i[r + 6] * pt[2] + w2i[r + 9] * 1.0;
+      e->err[0] = p[0] / p[2] - e->meas[0];
+      e->err[1] = p[1] / p[2] - e->meas[1];
+      break;
+    }
+  }
+}
+
+// types/slam3d/dquat2mat.cpp:9-59 + dquat2mat_maxima_generated.cpp:1-165.
+// dq (3x9 col-major), columns ordered r00 r10 r20 r01 r11 r21 r02 r12 r22.
+void compute_dq_dR(double* dq, const double* R) {
+  const double r00 = R[0], r10 = R[1], r20 = R[2], r01 = R[3], r11 = R[4], r21 = R[5], r02 = R[6],
+               r12 = R[7], r22 = R[8];
+  for (int i = 0; i < 27; ++i) dq[i] = 0;
+  auto D = [&](int r, int c) -> double& { return dq[r + 3 * c]; };
+  double S, qw;
+  double tr = r00 + r11 + r22;
+  if (tr > 0) {
+    S = sqrt(tr + 1.0) * 2;
+    qw = 0.25 * S;
+    S *= .25;
+    double a1 = 1 / pow(S, 3), a2 = -0.03125 * (r21 - r12) * a1, a3 = 1 / S, a4 = 0.25 * a3,
+           a5 = -0.25 * a3, a6 = 0.03125 * (r20 - r02) * a1, a7 = -0.03125 * (r10 - r01) * a1;
+    D(0, 0) = a2; D(0, 4) = a2; D(0, 5) = a4; D(0, 7) = a5; D(0, 8) = a2;
+    D(1, 0) = a6; D(1, 2) = a5; D(1, 4) = a6; D(1, 6) = a4; D(1, 8) = a6;
+    D(2, 0) = a7; D(2, 1) = a4; D(2, 3) = a5; D(2, 4) = a7; D(2, 8) = a7;
+  } else if ((r00 > r11) & (r00 > r22)) {
+    S = sqrt(1.0 + r00 - r11 - r22) * 2;
+    qw = (r21 - r12) / S;
+    S *= .25;
+    double a1 = 1 / S, a2 = -0.125 * a1, a3 = 1 / pow(S, 3), a4 = r10 + r01, a5 = 0.25 * a1,
+           a6 = 0.03125 * a3 * a4, a7 = r20 + r02, a8 = 0.03125 * a3 * a7;
+    D(0, 0) = 0.125 * a1; D(0, 4) = a2; D(0, 8) = a2;
+    D(1, 0) = -0.03125 * a3 * a4; D(1, 1) = a5; D(1, 3) = a5; D(1, 4) = a6; D(1, 8) = a6;
+    D(2, 0) = -0.03125 * a3 * a7; D(2, 2) = a5; D(2, 4) = a8; D(2, 6) = a5; D(2, 8) = a8;
+  } else if (r11 > r22) {
+    S = sqrt(1.0 + r11 - r00 - r22) * 2;
+    qw = (r02 - r20) / S;
+    S *= .25;
+    double a1 = 1 / pow(S, 3), a2 = r10 + r01, a3 = 0.03125 * a1 * a2, a4 = 1 / S, a5 = 0.25 * a4,
+           a6 = -0.125 * a4, a7 = r21 + r12, a8 = 0.03125 * a1 * a7;
+    D(0, 0) = a3; D(0, 1) = a5; D(0, 3) = a5; D(0, 4) = -0.03125 * a1 * a2; D(0, 8) = a3;
+    D(1, 0) = a6; D(1, 4) = 0.125 * a4; D(1, 8) = a6;
+    D(2, 0) = a8; D(2, 4) = -0.03125 * a1 * a7; D(2, 5) = a5; D(2, 7) = a5; D(2, 8) = a8;
+  } else {
+    S = sqrt(1.0 + r22 - r00 - r11) * 2;
+    qw = (r10 - r01) / S;
+    S *= .25;
+    double a1 = 1 / pow(S, 3), a2 = r20 + r02, a3 = 0.03125 * a1 * a2, a4 = 1 / S, a5 = 0.25 * a4,
+           a6 = r21 + r12, a7 = 0.03125 * a1 * a6, a8 = -0.125 * a4;
+    D(0, 0) = a3; D(0, 2) = a5; D(0, 4) = a3; D(0, 6) = a5; D(0, 8) = -0.03125 * a1 * a2;
+    D(1, 0) = a7; D(1, 4) = a7; D(1, 5) = a5; D(1, 7) = a5; D(1, 8) = -0.03125 * a1 * a6;
+    D(2, 0) = a8; D(2, 4) = a8; D(2, 8) = 0.125 * a4;
+  }
+  if (qw <= 0) for (int i = 0; i < 27; ++i) dq[i] *= -1;
+}
+
+void linearize(Edge* e) {
+  Vertex* v0 = e->v[0];
+  Vertex* v1 = e->v[1];
+  switch (e->kind) {
+    case ORC_EDGE_SE2: {  // types/slam2d/edge_se2.cpp:76-99
+      double thetai = v0->est[2];
+      double dtx = v1->est[0] - v0->est[0], dty = v1->est[1] - v0->est[1];
+      double si = sin(thetai), ci = cos(thetai);
+      double A0[9], B0[9];
+      auto A = [&](int r, int c) -> double& { return A0[r + 3 * c]; };
+      auto B = [&](int r, int c) -> double& { return B0[r + 3 * c]; };
+      A(0, 0) = -ci; A(0, 1) = -si; A(0, 2) = -si * dtx + ci * dty;
+      A(1, 0) = si;  A(1, 1) = -ci; A(1, 2) = -ci * dtx - si * dty;
+      A(2, 0) = 0;   A(2, 1) = 0;   A(2, 2) = -1;
+      B(0, 0) = ci;  B(0, 1) = si;  B(0, 2) = 0;
+      B(1, 0) = -si; B(1, 1) = ci;  B(1, 2) = 0;
+      B(2, 0) = 0;   B(2, 1) = 0;   B(2, 2) = 1;
+      double z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      double c = cos(e->invMeas[2]), s = sin(e->invMeas[2]);
+      z[0] = c; z[3] = -s; z[1] = s; z[4] = c; z[8] = 1.;
+      mm<3, 3, 3>(z, A0, e->Ji);
+      mm<3, 3, 3>(z, B0, e->Jj);
+      break;
+    }
+    case ORC_EDGE_SE3: {  // types/slam3d/edge_se3.cpp:63-75 -> isometry3d_gradients.h:194-265
+      Iso Xi, Xj, Z;
+      memcpy(&Xi, v0->est, sizeof(Iso)); memcpy(&Xj, v1->est, sizeof(Iso));
+      memcpy(&Z, e->meas, sizeof(Iso));
+      const Iso A = iso_inverse(Z);
+      const Iso B = iso_mul(iso_inverse(Xi), Xj);
+      const Iso E = iso_mul(A, B);
+      const double *Re = E.R, *Ra = A.R, *Rb = B.R, *tb = B.t;
+      double dq[27];
+      compute_dq_dR(dq, Re);
+      double* Ji = e->Ji; double* Jj = e->Jj;
+      for (int i = 0; i < 36; ++i) Ji[i] = Jj[i] = 0;
+      auto JI = [&](int r, int c) -> double& { return Ji[r + 6 * c]; };
+      auto JJ = [&](int r, int c) -> double& { return Jj[r + 6 * c]; };
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { JI(r, c) = -Ra[r + 3 * c]; JJ(r, c) = Re[r + 3 * c]; }
+      {  // dte/dqi = Ra * skewT(tb); skewT rows [0,-z,y],[z,0,-x],[-y,x,0] with doubled entries
+        const double x = 2 * tb[0], y = 2 * tb[1], z = 2 * tb[2];
+        double S[9] = {0, z, -y, -z, 0, x, y, -x, 0};  // col-major
+        double T[9];
+        mm<3, 3, 3>(Ra, S, T);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) JI(r, 3 + c) = T[r + 3 * c];
+      }
+      double buf[27];  // M (9x3 col-major): column k = vec(Mk)
+      {  // dre/dqi : skewT(Sxt,Syt,Szt,Rb) isometry3d_gradients.h:71-84
+        const double r11 = 2 * Rb[0], r12 = 2 * Rb[3], r13 = 2 * Rb[6], r21 = 2 * Rb[1], r22 = 2 * Rb[4],
+                     r23 = 2 * Rb[7], r31 = 2 * Rb[2], r32 = 2 * Rb[5], r33 = 2 * Rb[8];
+        // row-major listings from the reference, transposed into col-major storage
+        double Sxt[9] = {0, r31, -r21, 0, r32, -r22, 0, r33, -r23};
+        double Syt[9] = {-r31, 0, r11, -r32, 0, r12, -r33, 0, r13};
+        double Szt[9] = {r21, -r11, 0, r22, -r12, 0, r23, -r13, 0};
+        mm<3, 3, 3>(Ra, Sxt, buf); mm<3, 3, 3>(Ra, Syt, buf + 9); mm<3, 3, 3>(Ra, Szt, buf + 18);
+        double Q[9];
+        mm<3, 9, 3>(dq, buf, Q);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) JI(3 + r, 3 + c) = Q[r + 3 * c];
+      }
+      {  // dre/dqj : skew(Sx,Sy,Sz,I) isometry3d_gradients.h:58-69
+        const double r11 = 2, r12 = 0, r13 = 0, r21 = 0, r22 = 2, r23 = 0, r31 = 0, r32 = 0, r33 = 2;
+        double Sx[9] = {0, -r31, r21, 0, -r32, r22, 0, -r33, r23};
+        double Sy[9] = {r31, 0, -r11, r32, 0, -r12, r33, 0, -r13};
+        double Sz[9] = {-r21, r11, 0, -r22, r12, 0, -r23, r13, 0};
+        mm<3, 3, 3>(Re, Sx, buf); mm<3, 3, 3>(Re, Sy, buf + 9); mm<3, 3, 3>(Re, Sz, buf + 18);
+        double Q[9];
+        mm<3, 9, 3>(dq, buf, Q);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) JJ(3 + r, 3 + c) = Q[r + 3 * c];
+      }
+      break;
+    }
+    case ORC_EDGE_P2MC: {  // types/sba/types_sba.cpp:334-403
+      const double* cam = v1->est;
+      const double* w2n = cam + 12;
+      const double* pt = v0->est;
+      double pc[3];
+      for (int r = 0; r < 3; ++r)
+        pc[r] = w2n[r] * pt[0] + w2n[r + 3] * pt[1] + w2n[r + 6] * pt[2] + w2n[r + 9] * 1.0;
+      double px = pc[0], py = pc[1], pz = pc[2];
+      double ipz2 = 1.0 / (pz * pz);
+      if (std::isnan(ipz2)) { fprintf(stderr, "[SetJac] infinite jac\n"); abort(); }
+      double ipz2fx = ipz2 * cam[7], ipz2fy = ipz2 * cam[8];
+      double pwt[3] = {pt[0] - cam[0], pt[1] - cam[1], pt[2] - cam[2]};
+      double* Jxi = e->Ji;  // 2x3
+      double* Jxj = e->Jj;  // 2x6
+      auto setcol = [&](double* J, int c, const double* dp) {
+        J[0 + 2 * c] = (pz * dp[0] - px * dp[2]) * ipz2fx;
+        J[1 + 2 * c] = (pz * dp[1] - py * dp[2]) * ipz2fy;
+      };
+      double dp[3];
+      mm<3, 3, 1>(cam + 36, pwt, dp); setcol(Jxj, 3, dp);
+      mm<3, 3, 1>(cam + 45, pwt, dp); setcol(Jxj, 4, dp);
+      mm<3, 3, 1>(cam + 54, pwt, dp); setcol(Jxj, 5, dp);
+      for (int k = 0; k < 3; ++k) {
+        for (int r = 0; r < 3; ++r) dp[r] = -w2n[r + 3 * k];
+        setcol(Jxj, k, dp);
+      }
+      for (int k = 0; k < 3; ++k) {
+        for (int r = 0; r < 3; ++r) dp[r] = w2n[r + 3 * k];
+        setcol(Jxi, k, dp);
+      }
+      break;
+    }
+  }
+}
+
+void oplus(Vertex* v, const double* u) {
+  switch (v->kind) {
+    case ORC_VERTEX_SE2: {  // types/slam2d/vertex_se2.h:51-58
+      v->est[0] += u[0]; v->est[1] += u[1];
+      v->est[2] = normalize_theta(v->est[2] + u[2]);
+      break;
+    }
+    case ORC_VERTEX_SE3: {  // types/slam3d/vertex_se3.h:107-116, isometry3d_mappings.cpp:84-91,117-122
+      Iso inc;
+      double w = 1 - (u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);
+      if (w < 0) {
+        for (int i = 0; i < 9; ++i) inc.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      } else {
+        w = sqrt(w);
+        double q[4] = {u[3], u[4], u[5], w};
+        quat_to_R(q, inc.R);
+      }
+      inc.t[0] = u[0]; inc.t[1] = u[1]; inc.t[2] = u[2];
+      Iso cur; memcpy(&cur, v->est, sizeof(Iso));
+      Iso r = iso_mul(cur, inc);
+      if (++v->numOplusCalls > 1000) {  // orthogonalizeAfter, isometry3d_mappings.h:86-91
+        v->numOplusCalls = 0;
+        double E[9], RE[9];
+        mtm<3, 3, 3>(r.R, r.R, E);
+        E[0] -= 1; E[4] -= 1; E[8] -= 1;
+        mm<3, 3, 3>(r.R, E, RE);
+        for (int i = 0; i < 9; ++i) r.R[i] -= 0.5 * RE[i];
+      }
+      memcpy(v->est, &r, sizeof(Iso));
+      break;
+    }
+    case ORC_VERTEX_CAM: {  // types/sba/types_sba.h:93-100, sbacam.h:101-117
+      double* t = v->est; double* q = v->est + 3;
+      t[0] += u[0]; t[1] += u[1]; t[2] += u[2];
+      double qr[4] = {u[3], u[4], u[5], 0};
+      qr[3] = sqrt(1.0 - (u[3] * u[3] + u[4] * u[4] + u[5] * u[5]));
+      // Eigen quaternion product a*b, a=_r, b=qr
+      double a[4] = {q[0], q[1], q[2], q[3]};
+      double r[4];
+      r[3] = a[3] * qr[3] - a[0] * qr[0] - a[1] * qr[1] - a[2] * qr[2];
+      r[0] = a[3] * qr[0] + a[0] * qr[3] + a[1] * qr[2] - a[2] * qr[1];
+      r[1] = a[3] * qr[1] + a[1] * qr[3] + a[2] * qr[0] - a[0] * qr[2];
+      r[2] = a[3] * qr[2] + a[2] * qr[3] + a[0] * qr[1] - a[1] * qr[0];
+      quat_normalize(r);
+      for (int i = 0; i < 4; ++i) q[i] = r[i];
+      cam_refresh(v->est);
+      break;
+    }
+    case ORC_VERTEX_XYZ: {  // types/sba/types_sba.h:151-155
+      v->est[0] += u[0]; v->est[1] += u[1]; v->est[2] += u[2];
+      break;
+    }
+  }
+}
+
+// core/base_binary_edge.hpp:54-120 (no robust kernel: none of the configs sets one)
+template <int D, int Di, int Dj>
+void construct_quadratic_form_t(Edge* e) {
+  Vertex* from = e->v[0];
+  Vertex* to = e->v[1];
+  const double* A = e->Ji;  // D x Di
+  const double* B = e->Jj;  // D x Dj
+  const bool fromNotFixed = !from->fixed, toNotFixed = !to->fixed;
+  if (!(fromNotFixed || toNotFixed)) return;
+  const double* omega = e->info;
+  double omega_r[D];
+  for (int r = 0; r < D; ++r) {
+    double s = 0;
+    for (int k = 0; k < D; ++k) s += omega[r + D * k] * e->err[k];
+    omega_r[r] = -s;
+  }
+  if (fromNotFixed) {
+    double AtO[Di * D];  // Di x D
+    mtm<Di, D, D>(A, omega, AtO);
+    double tb[Di];
+    mtm<Di, D, 1>(A, omega_r, tb);
+    for (int i = 0; i < Di; ++i) from->b[i] += tb[i];
+    double AtOA[Di * Di];
+    mm<Di, D, Di>(AtO, A, AtOA);
+    for (int i = 0; i < Di * Di; ++i) from->H[i] += AtOA[i];
+    if (toNotFixed) {
+      if (e->transposed) {  // _hessianTransposed (Dj x Di) += B^T * AtO^T
+        double T[Dj * Di];
+        for (int c = 0; c < Di; ++c)
+          for (int r = 0; r < Dj; ++r) {
+            double s = 0;
+            for (int k = 0; k < D; ++k) s += B[k + D * r] * AtO[c + Di * k];
+            T[r + Dj * c] = s;
+          }
+        for (int i = 0; i < Dj * Di; ++i) e->H[i] += T[i];
+      } else {  // _hessian (Di x Dj) += AtO * B
+        double T[Di * Dj];
+        mm<Di, D, Dj>(AtO, B, T);
+        for (int i = 0; i < Di * Dj; ++i) e->H[i] += T[i];
+      }
+    }
+  }
+  if (toNotFixed) {
+    double tb[Dj];
+    mtm<Dj, D, 1>(B, omega_r, tb);
+    for (int i = 0; i < Dj; ++i) to->b[i] += tb[i];
+    double BtO[Dj * D];
+    mtm<Dj, D, D>(B, omega, BtO);
+    double BtOB[Dj * Dj];
+    mm<Dj, D, Dj>(BtO, B, BtOB);
+    for (int i = 0; i < Dj * Dj; ++i) to->H[i] += BtOB[i];
+  }
+}
+void construct_quadratic_form(Edge* e) {
+  switch (e->kind) {
+    case ORC_EDGE_SE2: construct_quadratic_form_t<3, 3, 3>(e); break;
+    case ORC_EDGE_SE3: construct_quadratic_form_t<6, 6, 6>(e); break;
+    case ORC_EDGE_P2MC: construct_quadratic_form_t<2, 3, 6>(e); break;
+  }
+}
+// core/base_edge.h:58-61
+inline double edge_chi2(const Edge* e) {
+  const int D = e->D;
+  double s = 0;
+  for (int r = 0; r < D; ++r) {
+    double t = 0;
+    for (int k = 0; k < D; ++k) t += e->info[r + D * k] * e->err[k];
+    s += e->err[r] * t;
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SparseBlockMatrix (core/sparse_block_matrix.h:61-220): per block column a std::map<row, block*>
+// ---------------------------------------------------------------------------------------------
+struct BlockPool {  // bump allocator for the block payloads
+  std::vector<std::unique_ptr<double[]>> chunks;
+  size_t used = 0, cap = 0;
+  double* get(size_t n) {
+    if (used + n > cap) {
+      cap = std::max<size_t>(n, 1 << 20);
+      chunks.emplace_back(new double[cap]);
+      used = 0;
+    }
+    double* p = chunks.back().get() + used;
+    used += n;
+    return p;
+  }
+};
+struct SBM {
+  int rdim = 0, cdim = 0, nrows = 0, ncols = 0;  // uniform block dims; #block rows / cols
+  std::vector<std::map<int, double*>> cols;
+  BlockPool pool;
+  void resize(int nr, int nc, int rd, int cd) { nrows = nr; ncols = nc; rdim = rd; cdim = cd; cols.assign(nc, {}); }
+  double* block(int r, int c, bool alloc) {
+    auto it = cols[c].find(r);
+    if (it != cols[c].end()) return it->second;
+    if (!alloc) return nullptr;
+    double* p = pool.get((size_t)rdim * cdim);
+    for (int i = 0; i < rdim * cdim; ++i) p[i] = 0;
+    cols[c][r] = p;
+    return p;
+  }
+  void clear() {  // sparse_block_matrix.hpp:67-83 (zero every block, keep structure)
+    for (auto& c : cols) for (auto& kv : c) memset(kv.second, 0, sizeof(double) * rdim * cdim);
+  }
+  size_t nonZeroBlocks() const { size_t n = 0; for (auto& c : cols) n += c.size(); return n; }
+};
+struct CCSCol { int row; double* block; };
+
+// ---------------------------------------------------------------------------------------------
+// LinearSolverCSparse (solvers/csparse/linear_solver_csparse.h:70-345)
+// ---------------------------------------------------------------------------------------------
+struct LinearSolverCSparseO {
+  bool blockOrdering = true;
+  css* S = nullptr;
+  cs A{};  // scalar CCS, upper
+  std::vector<int> Ap, Ai; std::vector<double> Ax;
+  std::vector<int> blockPerm;   // P of cs_amd on the block pattern (or scalar P)
+  std::vector<double> work; std::vector<int> iwork;
+  double timeSymbolic = 0, timeNumeric = 0;
+  ~LinearSolverCSparseO() { if (S) cs_sfree(S); }
+  void init() { if (S) { cs_sfree(S); S = nullptr; } }
+
+  // core/sparse_block_matrix_ccs.h:143-199 fillCCS(upperTriangle=true)
+  void fill(const SBM& M, bool onlyValues) {
+    const int d = M.cdim;
+    const int n = M.ncols * d;
+    if (!onlyValues) {
+      size_t nz = 0;
+      for (int c = 0; c < M.ncols; ++c) for (auto& kv : M.cols[c]) nz += (kv.first == c) ? d * (d + 1) / 2 : d * d;
+      Ap.assign(n + 1, 0); Ai.assign(nz, 0); Ax.assign(nz, 0);
+    }
+    int nz = 0;
+    for (int i = 0; i < M.ncols; ++i) {
+      int cstart = i * d;
+      for (int c = 0; c < d; ++c) {
+        if (!onlyValues) Ap[cstart + c] = nz;
+        for (auto& kv : M.cols[i]) {
+          int rstart = kv.first * d;
+          int elems = d;
+          if (rstart == cstart) elems = c + 1;
+          for (int r = 0; r < elems; ++r) {
+            Ax[nz] = kv.second[r + d * c];
+            if (!onlyValues) Ai[nz] = rstart + r;
+            ++nz;
+          }
+        }
+      }
+    }
+    if (!onlyValues) Ap[n] = nz;
+    A.nzmax = (int)Ai.size(); A.m = A.n = n; A.p = Ap.data(); A.i = Ai.data(); A.x = Ax.data(); A.nz = -1;
+  }
+
+  // linear_solver_csparse.h:246-300
+  void computeSymbolic(const SBM& M) {
+    double t = now();
+    const int n = A.n;
+    if (!blockOrdering) {
+      S = cs_schol(1, &A);
+      blockPerm.clear();
+    } else {
+      // core/sparse_block_matrix.hpp:519-545 fillBlockStructure (upper incl. diagonal)
+      std::vector<int> Bp(M.ncols + 1), Bi;
+      for (int c = 0; c < M.ncols; ++c) {
+        Bp[c] = (int)Bi.size();
+        for (auto& kv : M.cols[c]) if (kv.first <= c) Bi.push_back(kv.first);
+      }
+      Bp[M.ncols] = (int)Bi.size();
+      cs aux{};
+      aux.nzmax = (int)Bi.size(); aux.m = aux.n = M.ncols; aux.p = Bp.data(); aux.i = Bi.data(); aux.x = nullptr; aux.nz = -1;
+      int* P = cs_amd(1, &aux);
+      blockPerm.assign(P, P + M.ncols);
+      std::vector<int> scalarPerm(n);
+      size_t idx = 0;
+      for (int i = 0; i < M.ncols; ++i) {
+        int base = P[i] * M.cdim;
+        for (int j = 0; j < M.cdim; ++j) scalarPerm[idx++] = base++;
+      }
+      cs_free(P);
+      S = (css*)cs_calloc(1, sizeof(css));
+      S->pinv = cs_pinv(scalarPerm.data(), n);
+      cs* C = cs_symperm(&A, S->pinv, 0);
+      S->parent = cs_etree(C, 0);
+      int* post = cs_post(S->parent, n);
+      int* c = cs_counts(C, S->parent, post, 0);
+      cs_free(post);
+      cs_spfree(C);
+      S->cp = (int*)cs_malloc(n + 1, sizeof(int));
+      S->unz = S->lnz = cs_cumsum(S->cp, c, n);
+      cs_free(c);
+      if (S->lnz < 0) { cs_sfree(S); S = nullptr; }
+    }
+    timeSymbolic = now() - t;
+  }
+
+  // linear_solver_csparse.h:106-142
+  bool solve(const SBM& M, double* x, const double* b) {
+    fill(M, S != nullptr);
+    if (!S) computeSymbolic(M);
+    if (!S) return false;
+    const int n = A.n;
+    if ((int)work.size() < n) { work.assign(2 * n, 0); iwork.assign(4 * n, 0); }
+    double t = now();
+    if (x != b) memcpy(x, b, n * sizeof(double));
+    int ok = g2o::csparse_extension::cs_cholsolsymb(&A, x, S, work.data(), iwork.data());
+    timeNumeric = now() - t;
+    return ok != 0;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the optimizer: OptimizableGraph + SparseOptimizer + BlockSolver + GN/LM
+// ---------------------------------------------------------------------------------------------
+}  // namespace
+
+struct oracle_graph {
+  typedef std::tr1::unordered_map<int, Vertex*> VertexIDMap;  // core/hyper_graph.h VertexIDMap
+  VertexIDMap vertices;
+  std::vector<std::unique_ptr<Vertex>> vstore;
+  std::vector<std::unique_ptr<Edge>> edges;  // addEdge order = internalId
+  // SparseOptimizer
+  std::vector<Vertex*> activeVertices, ivMap;
+  std::vector<Edge*> activeEdges;
+  // BlockSolver (core/block_solver.h:43-186)
+  bool doSchur = false;
+  int numPoses = 0, numLandmarks = 0, sizePoses = 0, sizeLandmarks = 0, poseDim = 0, landmarkDim = 0;
+  SBM Hpp, Hll, Hpl, Hschur;
+  std::vector<std::vector<CCSCol>> HplCCS;               // per landmark column, ascending pose row
+  std::vector<std::vector<CCSCol>> HschurTransposedCCS;  // per row i1: (i2, block) ascending
+  std::vector<double> DInvSchur;
+  std::vector<double> x, b, coefficients, bschur, diagBackupPose, diagBackupLandmark;
+  LinearSolverCSparseO linearSolver;
+  // LM state (core/optimization_algorithm_levenberg.h)
+  double currentLambda = -1, ni = 2;
+  int levenbergIterations = 0;
+  double timeSchur = 0, timeLinearSolver = 0;
+
+  Vertex* vertex(int id) { auto it = vertices.find(id); return it == vertices.end() ? nullptr : it->second; }
+};
+
+namespace {
+typedef oracle_graph G;
+
+Vertex* add_vertex(G* g, int kind, int id) {
+  if (g->vertex(id)) return nullptr;  // HyperGraph::addVertex fails on duplicate ids
+  g->vstore.emplace_back(new Vertex());
+  Vertex* v = g->vstore.back().get();
+  v->kind = kind; v->id = id; v->dim = vertex_dim(kind);
+  for (int i = 0; i < EST_MAX; ++i) v->est[i] = 0;
+  g->vertices[id] = v;
+  return v;
+}
+
+// per-type read(): payload = numbers after the id
+bool vertex_read(Vertex* v, const double* p, int n) {
+  switch (v->kind) {
+    case ORC_VERTEX_SE2:  // types/slam2d/vertex_se2.cpp:41-47
+      if (n < 3) return false;
+      v->est[0] = p[0]; v->est[1] = p[1]; v->est[2] = p[2];
+      return true;
+    case ORC_VERTEX_SE3: {  // types/slam3d/vertex_se3.cpp:44-51 ; fromVectorQT (no normalisation)
+      if (n < 7) return false;
+      double q[4] = {p[3], p[4], p[5], p[6]};
+      quat_to_R(q, v->est);
+      v->est[9] = p[0]; v->est[10] = p[1]; v->est[11] = p[2];
+      return true;
+    }
+    case ORC_VERTEX_CAM: {  // types/sba/types_sba.cpp:74-112
+      if (n < 7) return false;
+      v->est[0] = p[0]; v->est[1] = p[1]; v->est[2] = p[2];
+      double q[4] = {p[3], p[4], p[5], p[6]};
+      quat_normalize(q);
+      se3quat_normalize_rotation(q);  // SBACam(r,t) -> SE3Quat(q,t) ctor
+      for (int i = 0; i < 4; ++i) v->est[3 + i] = q[i];
+      if (n >= 12) { for (int i = 0; i < 5; ++i) v->est[7 + i] = p[7 + i]; }
+      else { v->est[7] = 300; v->est[8] = 300; v->est[9] = 320; v->est[10] = 320; v->est[11] = 0.1; }
+      cam_refresh(v->est);
+      return true;
+    }
+    case ORC_VERTEX_XYZ:  // types/sba/types_sba.cpp:180-186
+      if (n < 3) return false;
+      v->est[0] = p[0]; v->est[1] = p[1]; v->est[2] = p[2];
+      return true;
+  }
+  return false;
+}
+
+bool edge_read(Edge* e, const double* p, int n) {
+  const int D = e->D;
+  for (int i = 0; i < 36; ++i) e->info[i] = 0;
+  for (int i = 0; i < D; ++i) e->info[i + D * i] = 1;
+  switch (e->kind) {
+    case ORC_EDGE_SE2: {  // types/slam2d/edge_se2.cpp:40-53
+      if (n < 9) return false;
+      e->meas[0] = p[0]; e->meas[1] = p[1]; e->meas[2] = p[2];
+      SE2 zi = se2_inv(SE2{p[0], p[1], p[2]});
+      e->invMeas[0] = zi.x; e->invMeas[1] = zi.y; e->invMeas[2] = zi.th;
+      int k = 3;
+      for (int i = 0; i < 3; ++i) for (int j = i; j < 3; ++j) { e->info[i + 3 * j] = p[k]; e->info[j + 3 * i] = p[k]; ++k; }
+      return true;
+    }
+    case ORC_EDGE_SE3: {  // types/slam3d/edge_se3.cpp:14-36
+      if (n < 7) return false;
+      double q[4] = {p[3], p[4], p[5], p[6]};
+      quat_normalize(q);  // Vector4d::MapType(meas.data()+3).normalize()
+      Iso Z;
+      quat_to_R(q, Z.R);
+      Z.t[0] = p[0]; Z.t[1] = p[1]; Z.t[2] = p[2];
+      memcpy(e->meas, &Z, sizeof(Iso));
+      Iso Zi = iso_inverse(Z);
+      memcpy(e->invMeas, &Zi, sizeof(Iso));
+      int k = 7;
+      for (int i = 0; i < 6 && k < n; ++i) for (int j = i; j < 6 && k < n; ++j) { e->info[i + 6 * j] = p[k]; e->info[j + 6 * i] = p[k]; ++k; }
+      return true;
+    }
+    case ORC_EDGE_P2MC: {  // types/sba/types_sba.cpp:204-213 (information forced to identity)
+      if (n < 2) return false;
+      e->meas[0] = p[0]; e->meas[1] = p[1];
+      return true;
+    }
+  }
+  return false;
+}
+
+// EdgeSE2::initialEstimate / EdgeSE3::initialEstimate for vertices created by load(createEdges=true)
+void initial_estimate_to(Edge* e) {  // to = from * meas
+  if (e->kind == ORC_EDGE_SE2) {
+    SE2 f{e->v[0]->est[0], e->v[0]->est[1], e->v[0]->est[2]};
+    SE2 r = se2_mul(f, SE2{e->meas[0], e->meas[1], e->meas[2]});
+    e->v[1]->est[0] = r.x; e->v[1]->est[1] = r.y; e->v[1]->est[2] = r.th;
+  } else if (e->kind == ORC_EDGE_SE3) {
+    Iso f, z; memcpy(&f, e->v[0]->est, sizeof(Iso)); memcpy(&z, e->meas, sizeof(Iso));
+    Iso r = iso_mul(f, z); memcpy(e->v[1]->est, &r, sizeof(Iso));
+  }
+}
+void initial_estimate_from(Edge* e) {  // from = to * meas^-1
+  if (e->kind == ORC_EDGE_SE2) {
+    SE2 t{e->v[1]->est[0], e->v[1]->est[1], e->v[1]->est[2]};
+    SE2 r = se2_mul(t, SE2{e->invMeas[0], e->invMeas[1], e->invMeas[2]});
+    e->v[0]->est[0] = r.x; e->v[0]->est[1] = r.y; e->v[0]->est[2] = r.th;
+  } else if (e->kind == ORC_EDGE_SE3) {
+    Iso t, z; memcpy(&t, e->v[1]->est, sizeof(Iso)); memcpy(&z, e->meas, sizeof(Iso));
+    Iso r = iso_mul(t, iso_inverse(z)); memcpy(e->v[0]->est, &r, sizeof(Iso));
+  }
+}
+void set_to_origin(Vertex* v) {
+  for (int i = 0; i < EST_MAX; ++i) v->est[i] = 0;
+  if (v->kind == ORC_VERTEX_SE3) { v->est[0] = v->est[4] = v->est[8] = 1; }
+  if (v->kind == ORC_VERTEX_CAM) { v->est[6] = 1; v->est[7] = 1; v->est[8] = 1; v->est[9] = 0.5; v->est[10] = 0.5; cam_refresh(v->est); }
+}
+
+int add_edge(G* g, int kind, int id1, int id2, const double* payload, int n) {
+  // core/optimizable_graph.cpp:454-520 (binary edges, createEdges = true)
+  static const int vk0[3] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_XYZ};
+  static const int vk1[3] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_CAM};
+  Vertex* from = g->vertex(id1);
+  Vertex* to = g->vertex(id2);
+  int doInit = 0;
+  if (!from) { from = add_vertex(g, vk0[kind], id1); set_to_origin(from); doInit = 2; }
+  if (!to) { to = add_vertex(g, vk1[kind], id2); set_to_origin(to); doInit = 1; }
+  if (from->kind != vk0[kind] || to->kind != vk1[kind]) return -1;
+  g->edges.emplace_back(new Edge());
+  Edge* e = g->edges.back().get();
+  e->kind = kind; e->D = edge_dim(kind);
+  e->v[0] = from; e->v[1] = to;
+  e->internalId = (int)g->edges.size() - 1;
+  for (int i = 0; i < 6; ++i) e->err[i] = 0;
+  if (!edge_read(e, payload, n)) { g->edges.pop_back(); return -1; }
+  from->edges.push_back(e);
+  if (to != from) to->edges.push_back(e);
+  if (doInit == 1) initial_estimate_to(e);
+  if (doInit == 2) initial_estimate_from(e);
+  return 0;
+}
+
+// ---- apps/g2o_cli/g2o.cpp:272-320 + core/sparse_optimizer.cpp:116-164 ----
+bool gauge_freedom(G* g) {
+  if (g->vertices.empty()) return false;
+  int maxDim = 0;
+  for (auto& kv : g->vertices) maxDim = std::max(maxDim, kv.second->dim);
+  for (auto& kv : g->vertices) {
+    Vertex* v = kv.second;
+    if (v->dim == maxDim) {
+      if (v->fixed) return false;
+      // unary full-dimension priors: none of the configured edge types is unary
+    }
+  }
+  return true;
+}
+Vertex* find_gauge(G* g) {
+  if (g->vertices.empty()) return nullptr;
+  int maxDim = 0;
+  for (auto& kv : g->vertices) maxDim = std::max(maxDim, kv.second->dim);
+  for (auto& kv : g->vertices) if (kv.second->dim == maxDim) return kv.second;
+  return nullptr;
+}
+
+// ---- core/sparse_optimizer.cpp:199-267, 166-190 ----
+bool initialize_optimization(G* g) {
+  if (g->edges.empty()) return false;
+  for (Vertex* v : g->ivMap) v->hessianIndex = -1;
+  g->ivMap.clear();
+  g->activeVertices.clear();
+  g->activeEdges.clear();
+  std::vector<char> edgeActive(g->edges.size(), 0);
+  for (auto& kv : g->vertices) {
+    Vertex* v = kv.second;
+    int levelEdges = 0;
+    for (Edge* e : v->edges) {
+      bool allFixed = e->v[0]->fixed && e->v[1]->fixed;
+      if (!allFixed) { edgeActive[e->internalId] = 1; levelEdges++; }
+    }
+    if (levelEdges) g->activeVertices.push_back(v);
+  }
+  for (size_t k = 0; k < g->edges.size(); ++k) if (edgeActive[k]) g->activeEdges.push_back(g->edges[k].get());
+  // sortVectorContainers: vertices by id, edges by internalId (already)
+  std::sort(g->activeVertices.begin(), g->activeVertices.end(), [](Vertex* a, Vertex* b) { return a->id < b->id; });
+  // buildIndexMapping
+  if (g->activeVertices.empty()) return false;
+  g->ivMap.resize(g->activeVertices.size());
+  size_t i = 0;
+  for (int k = 0; k < 2; ++k)
+    for (Vertex* v : g->activeVertices) {
+      if (!v->fixed) {
+        if ((int)v->marginalized == k) { v->hessianIndex = (int)i; g->ivMap[i] = v; ++i; }
+      } else {
+        v->hessianIndex = -1;
+      }
+    }
+  g->ivMap.resize(i);
+  return true;
+}
+
+// ---- core/block_solver.hpp:142-295 ----
+bool build_structure(G* g) {
+  g->numPoses = g->numLandmarks = g->sizePoses = g->sizeLandmarks = 0;
+  g->poseDim = g->landmarkDim = 0;
+  for (Vertex* v : g->ivMap) {
+    if (!v->marginalized) { v->colInHessian = g->sizePoses; g->sizePoses += v->dim; ++g->numPoses; g->poseDim = v->dim; }
+    else { v->colInHessian = g->sizeLandmarks; g->sizeLandmarks += v->dim; ++g->numLandmarks; g->landmarkDim = v->dim; }
+  }
+  const int pd = g->poseDim, ld = g->landmarkDim ? g->landmarkDim : 3;
+  g->Hpp = SBM(); g->Hll = SBM(); g->Hpl = SBM(); g->Hschur = SBM();
+  g->Hpp.resize(g->numPoses, g->numPoses, pd, pd);
+  if (g->doSchur) {
+    g->Hschur.resize(g->numPoses, g->numPoses, pd, pd);
+    g->Hll.resize(g->numLandmarks, g->numLandmarks, ld, ld);
+    g->Hpl.resize(g->numPoses, g->numLandmarks, pd, ld);
+  }
+  const int total = g->sizePoses + g->sizeLandmarks;
+  g->x.assign(total, 0); g->b.assign(total, 0);
+  g->coefficients.assign(total, 0); g->bschur.assign(g->sizePoses, 0);
+  int poseIdx = 0, landmarkIdx = 0;
+  for (Vertex* v : g->ivMap) {
+    if (!v->marginalized) { v->H = g->Hpp.block(poseIdx, poseIdx, true); ++poseIdx; }
+    else { v->H = g->Hll.block(landmarkIdx, landmarkIdx, true); ++landmarkIdx; }
+  }
+  std::vector<std::set<int>> schurLookup;  // SparseBlockMatrixHashMap: per column set of rows
+  if (g->doSchur) schurLookup.resize(g->numPoses);
+  for (Edge* e : g->activeEdges) {
+    Vertex* v1 = e->v[0]; Vertex* v2 = e->v[1];
+    int ind1 = v1->hessianIndex, ind2 = v2->hessianIndex;
+    if (ind1 == -1 || ind2 == -1) continue;
+    bool transposedBlock = ind1 > ind2;
+    if (transposedBlock) std::swap(ind1, ind2);
+    if (!v1->marginalized && !v2->marginalized) {
+      e->H = g->Hpp.block(ind1, ind2, true);
+      e->transposed = transposedBlock;
+      if (g->doSchur) schurLookup[ind2].insert(ind1);
+    } else if (v1->marginalized && v2->marginalized) {
+      e->H = g->Hll.block(ind1 - g->numPoses, ind2 - g->numPoses, true);
+      e->transposed = false;
+    } else {
+      if (v1->marginalized) {
+        e->H = g->Hpl.block(v2->hessianIndex, v1->hessianIndex - g->numPoses, true);
+        e->transposed = true;
+      } else {
+        e->H = g->Hpl.block(v1->hessianIndex, v2->hessianIndex - g->numPoses, true);
+        e->transposed = false;
+      }
+    }
+  }
+  if (!g->doSchur) return true;
+  g->DInvSchur.assign((size_t)g->numLandmarks * ld * ld, 0);
+  g->HplCCS.assign(g->numLandmarks, {});
+  for (int c = 0; c < g->numLandmarks; ++c)
+    for (auto& kv : g->Hpl.cols[c]) g->HplCCS[c].push_back(CCSCol{kv.first, kv.second});
+  for (Vertex* v : g->ivMap) {
+    if (!v->marginalized) continue;
+    for (Edge* e1 : v->edges)
+      for (int i = 0; i < 2; ++i) {
+        Vertex* v1 = e1->v[i];
+        if (v1->hessianIndex == -1 || v1 == v) continue;
+        for (Edge* e2 : v->edges)
+          for (int j = 0; j < 2; ++j) {
+            Vertex* v2 = e2->v[j];
+            if (v2->hessianIndex == -1 || v2 == v) continue;
+            int i1 = v1->hessianIndex, i2 = v2->hessianIndex;
+            if (i1 <= i2) schurLookup[i2].insert(i1);
+          }
+      }
+  }
+  for (int c = 0; c < g->numPoses; ++c) for (int r : schurLookup[c]) g->Hschur.block(r, c, true);
+  g->HschurTransposedCCS.assign(g->numPoses, {});
+  for (int c = 0; c < g->numPoses; ++c)
+    for (auto& kv : g->Hschur.cols[c]) g->HschurTransposedCCS[kv.first].push_back(CCSCol{c, kv.second});
+  return true;
+}
+
+// ---- core/sparse_optimizer.cpp:61-114 ----
+double compute_active_errors(G* g) {
+  for (Edge* e : g->activeEdges) compute_error(e);
+  double chi = 0.0;
+  for (Edge* e : g->activeEdges) chi += edge_chi2(e);
+  return chi;
+}
+
+// ---- core/block_solver.hpp:501-560 ----
+void build_system(G* g) {
+  for (Vertex* v : g->ivMap) for (int i = 0; i < 6; ++i) v->b[i] = 0;
+  g->Hpp.clear();
+  if (g->doSchur) { g->Hll.clear(); g->Hpl.clear(); }
+  for (Edge* e : g->activeEdges) { linearize(e); construct_quadratic_form(e); }
+  for (Vertex* v : g->ivMap) {
+    int iBase = v->colInHessian;
+    if (v->marginalized) iBase += g->sizePoses;
+    for (int i = 0; i < v->dim; ++i) g->b[iBase + i] = v->b[i];
+  }
+}
+
+// ---- core/block_solver.hpp:563-604 ----
+void set_lambda(G* g, double lambda, bool backup) {
+  const int pd = g->poseDim, ld = g->landmarkDim;
+  if (backup) { g->diagBackupPose.resize((size_t)g->numPoses * pd); g->diagBackupLandmark.resize((size_t)g->numLandmarks * ld); }
+  for (int i = 0; i < g->numPoses; ++i) {
+    double* blk = g->Hpp.block(i, i, false);
+    for (int k = 0; k < pd; ++k) { if (backup) g->diagBackupPose[(size_t)i * pd + k] = blk[k + pd * k]; blk[k + pd * k] += lambda; }
+  }
+  for (int i = 0; i < g->numLandmarks; ++i) {
+    double* blk = g->Hll.block(i, i, false);
+    for (int k = 0; k < ld; ++k) { if (backup) g->diagBackupLandmark[(size_t)i * ld + k] = blk[k + ld * k]; blk[k + ld * k] += lambda; }
+  }
+}
+void restore_diagonal(G* g) {
+  const int pd = g->poseDim, ld = g->landmarkDim;
+  for (int i = 0; i < g->numPoses; ++i) {
+    double* blk = g->Hpp.block(i, i, false);
+    for (int k = 0; k < pd; ++k) blk[k + pd * k] = g->diagBackupPose[(size_t)i * pd + k];
+  }
+  for (int i = 0; i < g->numLandmarks; ++i) {
+    double* blk = g->Hll.block(i, i, false);
+    for (int k = 0; k < ld; ++k) blk[k + ld * k] = g->diagBackupLandmark[(size_t)i * ld + k];
+  }
+}
+
+// Eigen fixed 3x3 inverse (Eigen/src/LU/Inverse.h compute_inverse<.,.,3>): cofactors / determinant
+inline void inverse3(const double* m, double* r) {
+  auto M = [&](int i, int j) { return m[i + 3 * j]; };
+  auto cof = [&](int i, int j) {
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return M(i1, j1) * M(i2, j2) - M(i1, j2) * M(i2, j1);
+  };
+  double c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+  double det = c0 * M(0, 0) + c1 * M(1, 0) + c2 * M(2, 0);
+  double invdet = 1.0 / det;
+  r[0 + 3 * 0] = c0 * invdet; r[0 + 3 * 1] = c1 * invdet; r[0 + 3 * 2] = c2 * invdet;
+  r[1 + 3 * 0] = cof(0, 1) * invdet; r[1 + 3 * 1] = cof(1, 1) * invdet; r[1 + 3 * 2] = cof(2, 1) * invdet;
+  r[2 + 3 * 0] = cof(0, 2) * invdet; r[2 + 3 * 1] = cof(1, 2) * invdet; r[2 + 3 * 2] = cof(2, 2) * invdet;
+}
+
+// ---- core/block_solver.hpp:354-486 ----
+bool solve(G* g) {
+  if (!g->doSchur) {
+    double t = now();
+    bool ok = g->linearSolver.solve(g->Hpp, g->x.data(), g->b.data());
+    g->timeLinearSolver = now() - t;
+    return ok;
+  }
+  double t = now();
+  const int pd = g->poseDim, ld = g->landmarkDim;
+  assert(pd == 6 && ld == 3);
+  g->Hschur.clear();
+  for (int c = 0; c < g->numPoses; ++c)  // _Hpp->add(_Hschur)
+    for (auto& kv : g->Hpp.cols[c]) {
+      double* d = g->Hschur.block(kv.first, c, false);
+      for (int i = 0; i < pd * pd; ++i) d[i] += kv.second[i];
+    }
+  memset(g->coefficients.data(), 0, g->sizePoses * sizeof(double));
+  for (int l = 0; l < g->numLandmarks; ++l) {
+    const double* D = g->Hll.cols[l].begin()->second;
+    double* Dinv = &g->DInvSchur[(size_t)l * 9];
+    inverse3(D, Dinv);
+    double db0[3], db[3];
+    for (int j = 0; j < 3; ++j) db0[j] = g->b[l * 3 + g->sizePoses + j];
+    mm<3, 3, 1>(Dinv, db0, db);
+    const std::vector<CCSCol>& col = g->HplCCS[l];
+    for (size_t o = 0; o < col.size(); ++o) {
+      int i1 = col[o].row;
+      const double* Bi = col[o].block;  // 6x3
+      double BDinv[18];
+      mm<6, 3, 3>(Bi, Dinv, BDinv);
+      double Bb[6];
+      mm<6, 3, 1>(Bi, db, Bb);
+      for (int k = 0; k < 6; ++k) g->coefficients[i1 * 6 + k] += Bb[k];
+      auto target = g->HschurTransposedCCS[i1].begin();
+      for (size_t in = o; in < col.size(); ++in) {  // lower_bound(i1) == o since rows are unique+sorted
+        int i2 = col[in].row;
+        const double* Bj = col[in].block;
+        while (target->row < i2) ++target;
+        double* H = target->block;
+        double T[36];
+        mmt<6, 3, 6>(BDinv, Bj, T);
+        for (int k = 0; k < 36; ++k) H[k] -= T[k];
+      }
+    }
+  }
+  memcpy(g->bschur.data(), g->b.data(), g->sizePoses * sizeof(double));
+  for (int i = 0; i < g->sizePoses; ++i) g->bschur[i] -= g->coefficients[i];
+  g->timeSchur = now() - t;
+  t = now();
+  bool solvedPoses = g->linearSolver.solve(g->Hschur, g->x.data(), g->bschur.data());
+  g->timeLinearSolver = now() - t;
+  if (!solvedPoses) return false;
+  double* xp = g->x.data();
+  double* cp = g->coefficients.data();
+  double* xl = g->x.data() + g->sizePoses;
+  double* cl = g->coefficients.data() + g->sizePoses;
+  const double* bl = g->b.data() + g->sizePoses;
+  for (int i = 0; i < g->sizePoses; ++i) cp[i] = -xp[i];
+  memcpy(cl, bl, g->sizeLandmarks * sizeof(double));
+  for (int l = 0; l < g->numLandmarks; ++l)  // _HplCCS->rightMultiply(cl, cp): cl += B^T cp
+    for (const CCSCol& rb : g->HplCCS[l]) {
+      double tmp[3];
+      mtm<3, 6, 1>(rb.block, cp + rb.row * 6, tmp);
+      for (int k = 0; k < 3; ++k) cl[l * 3 + k] += tmp[k];
+    }
+  memset(xl, 0, g->sizeLandmarks * sizeof(double));
+  for (int l = 0; l < g->numLandmarks; ++l) {  // _DInvSchur->multiply(xl, cl)
+    double tmp[3];
+    mm<3, 3, 1>(&g->DInvSchur[(size_t)l * 9], cl + l * 3, tmp);
+    for (int k = 0; k < 3; ++k) xl[l * 3 + k] += tmp[k];
+  }
+  return true;
+}
+
+void update(G* g) {  // core/sparse_optimizer.cpp:421-434
+  const double* u = g->x.data();
+  for (Vertex* v : g->ivMap) { oplus(v, u); u += v->dim; }
+}
+void push(G* g) { for (Vertex* v : g->activeVertices) { std::array<double, EST_MAX> a; memcpy(a.data(), v->est, sizeof(v->est)); v->backup.push_back(a); } }
+void pop(G* g) { for (Vertex* v : g->activeVertices) { memcpy(v->est, v->backup.back().data(), sizeof(v->est)); v->backup.pop_back(); } }
+void discard_top(G* g) { for (Vertex* v : g->activeVertices) v->backup.pop_back(); }
+
+bool algorithm_init(G* g) {  // core/optimization_algorithm_with_hessian.cpp:50-73 + block_solver.hpp:606-620
+  bool useSchur = false;
+  for (Vertex* v : g->activeVertices) if (v->marginalized) { useSchur = true; break; }
+  g->doSchur = useSchur;
+  g->linearSolver.init();
+  return true;
+}
+
+double lambda_init(G* g) {  // core/optimization_algorithm_levenberg.cpp:149-163
+  double maxDiagonal = 0.;
+  for (Vertex* v : g->ivMap)
+    for (int j = 0; j < v->dim; ++j) maxDiagonal = std::max(fabs(v->H[j + v->dim * j]), maxDiagonal);
+  return 1e-5 * maxDiagonal;
+}
+double compute_scale(G* g) {  // core/optimization_algorithm_levenberg.cpp:165-172
+  double scale = 0.;
+  for (size_t j = 0; j < g->x.size(); ++j) scale += g->x[j] * (g->currentLambda * g->x[j] + g->b[j]);
+  return scale;
+}
+
+// core/optimization_algorithm_gauss_newton.cpp:50-93
+int solve_gn(G* g, int iteration, oracle_iter_stats* st) {
+  double t = now();
+  compute_active_errors(g);
+  st->time_residuals = now() - t;
+  if (iteration == 0) { if (!build_structure(g)) return -1; }
+  t = now();
+  build_system(g);
+  st->time_quadratic_form = now() - t;
+  t = now();
+  bool ok = solve(g);
+  st->time_linear_solution = now() - t;
+  t = now();
+  update(g);
+  st->time_update = now() - t;
+  return ok ? 1 : -1;
+}
+
+// core/optimization_algorithm_levenberg.cpp:57-147
+int solve_lm(G* g, int iteration, oracle_iter_stats* st) {
+  if (iteration == 0) { if (!build_structure(g)) return -1; }
+  double t = now();
+  double currentChi = compute_active_errors(g);
+  st->time_residuals = now() - t;
+  t = now();
+  double tempChi = currentChi;
+  build_system(g);
+  st->time_quadratic_form = now() - t;
+  if (iteration == 0) { g->currentLambda = lambda_init(g); g->ni = 2; }
+  double rho = 0;
+  int& qmax = g->levenbergIterations;
+  qmax = 0;
+  do {
+    push(g);
+    t = now();
+    set_lambda(g, g->currentLambda, true);
+    bool ok2 = solve(g);
+    st->time_linear_solution += now() - t;
+    st->time_schur += g->timeSchur; st->time_linear_solver += g->timeLinearSolver;
+    t = now();
+    update(g);
+    st->time_update = now() - t;
+    restore_diagonal(g);
+    tempChi = compute_active_errors(g);
+    if (!ok2) tempChi = DBL_MAX;
+    rho = (currentChi - tempChi);
+    double scale = compute_scale(g);
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - pow((2 * rho - 1), 3);
+      alpha = std::min(alpha, 2. / 3.);
+      double scaleFactor = std::max(1. / 3., alpha);
+      g->currentLambda *= scaleFactor;
+      g->ni = 2;
+      currentChi = tempChi;
+      discard_top(g);
+    } else {
+      g->currentLambda *= g->ni;
+      g->ni *= 2;
+      pop(g);
+    }
+    qmax++;
+  } while (rho < 0 && qmax < 10);
+  if (qmax == 10 || rho == 0) return 2;
+  return 1;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C interface
+// =============================================================================================
+extern "C" {
+
+oracle_graph* oracle_new(void) { return new oracle_graph(); }
+void oracle_free(oracle_graph* g) { delete g; }
+
+int oracle_add_vertex(oracle_graph* g, int kind, int id, const double* payload, int n) {
+  Vertex* v = add_vertex(g, kind, id);
+  if (!v) return -1;
+  return vertex_read(v, payload, n) ? 0 : -1;
+}
+int oracle_add_edge(oracle_graph* g, int kind, int id1, int id2, const double* payload, int n) {
+  return add_edge(g, kind, id1, id2, payload, n);
+}
+int oracle_set_fixed(oracle_graph* g, int id, int fixed) {
+  Vertex* v = g->vertex(id);
+  if (!v) return -1;
+  v->fixed = fixed != 0;
+  return 0;
+}
+
+int oracle_load(oracle_graph* g, const char* path) {
+  std::ifstream is(path);
+  if (!is) return -1;
+  std::string line, token;
+  std::vector<double> nums;
+  while (std::getline(is, line)) {
+    std::stringstream ss(line);
+    token.clear();
+    ss >> token;
+    if (token.empty() || token[0] == '#') continue;
+    if (token == "FIX") { int id; while (ss >> id) oracle_set_fixed(g, id, 1); continue; }
+    int vkind = -1, ekind = -1;
+    if (token == "VERTEX_SE2") vkind = ORC_VERTEX_SE2;
+    else if (token == "VERTEX_SE3:QUAT") vkind = ORC_VERTEX_SE3;
+    else if (token == "VERTEX_CAM") vkind = ORC_VERTEX_CAM;
+    else if (token == "VERTEX_XYZ") vkind = ORC_VERTEX_XYZ;
+    else if (token == "EDGE_SE2") ekind = ORC_EDGE_SE2;
+    else if (token == "EDGE_SE3:QUAT") ekind = ORC_EDGE_SE3;
+    else if (token == "EDGE_PROJECT_P2MC") ekind = ORC_EDGE_P2MC;
+    else continue;  // unknown tags are skipped (optimizable_graph.cpp:417-423)
+    nums.clear();
+    if (vkind >= 0) {
+      int id; ss >> id;
+      double d; while (ss >> d) nums.push_back(d);
+      oracle_add_vertex(g, vkind, id, nums.data(), (int)nums.size());
+    } else {
+      int id1, id2; ss >> id1 >> id2;
+      double d; while (ss >> d) nums.push_back(d);
+      oracle_add_edge(g, ekind, id1, id2, nums.data(), (int)nums.size());
+    }
+  }
+  return 0;
+}
+
+int oracle_setup_cli(oracle_graph* g, int requires_marginalize) {
+  if (g->vertices.empty()) return -2;
+  bool gf = gauge_freedom(g);
+  Vertex* gauge = find_gauge(g);
+  int ret = -1;
+  if (gf) {
+    if (!gauge) return -2;
+    gauge->fixed = true;
+    ret = gauge->id;
+  }
+  if (requires_marginalize) {
+    int maxDim = 0, minDim = 1 << 30;
+    for (auto& kv : g->vertices) { maxDim = std::max(maxDim, kv.second->dim); minDim = std::min(minDim, kv.second->dim); }
+    if (maxDim != minDim)
+      for (auto& kv : g->vertices) if (kv.second->dim != maxDim) kv.second->marginalized = true;
+  }
+  return ret;
+}
+int oracle_initialize(oracle_graph* g) { return initialize_optimization(g) ? 0 : -1; }
+void oracle_set_block_ordering(oracle_graph* g, int bo) { g->linearSolver.blockOrdering = bo != 0; }
+
+int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_stats* stats) {
+  if (g->ivMap.empty()) return -1;
+  if (!algorithm_init(g)) return -1;
+  int cj = 0;
+  int result = 1;
+  bool ok = true;
+  for (int i = 0; i < iterations && ok; ++i) {
+    oracle_iter_stats local; memset(&local, 0, sizeof(local));
+    oracle_iter_stats* st = stats ? &stats[i] : &local;
+    memset(st, 0, sizeof(*st));
+    st->iteration = i;
+    double ts = now();
+    g->linearSolver.timeSymbolic = 0;
+    result = (algorithm == ORC_GN) ? solve_gn(g, i, st) : solve_lm(g, i, st);
+    ok = (result == 1);
+    st->time_iteration = now() - ts;   // the hot path proper (without the stats-only chi2 below)
+    st->chi2 = compute_active_errors(g);
+    st->result = result;
+    st->lambda = g->currentLambda;
+    st->levenberg_iterations = g->levenbergIterations;
+    st->time_symbolic = g->linearSolver.timeSymbolic;
+    st->time_numeric = g->linearSolver.timeNumeric;
+    if (algorithm == ORC_GN) { st->time_schur = g->timeSchur; st->time_linear_solver = g->timeLinearSolver; }
+    ++cj;
+  }
+  if (result == -1) return 0;
+  return cj;
+}
+
+int oracle_algorithm_init(oracle_graph* g) { return algorithm_init(g) ? 0 : -1; }
+int oracle_build_structure(oracle_graph* g) { return build_structure(g) ? 0 : -1; }
+double oracle_compute_active_errors(oracle_graph* g) { return compute_active_errors(g); }
+int oracle_build_system(oracle_graph* g) { build_system(g); return 0; }
+double oracle_lambda_init(oracle_graph* g) { return lambda_init(g); }
+int oracle_set_lambda(oracle_graph* g, double lambda, int backup) { g->currentLambda = lambda; set_lambda(g, lambda, backup != 0); return 0; }
+int oracle_restore_diagonal(oracle_graph* g) { restore_diagonal(g); return 0; }
+int oracle_solve(oracle_graph* g) { return solve(g) ? 1 : 0; }
+int oracle_update(oracle_graph* g) { update(g); return 0; }
+int oracle_push(oracle_graph* g) { push(g); return 0; }
+int oracle_pop(oracle_graph* g) { pop(g); return 0; }
+int oracle_discard_top(oracle_graph* g) { discard_top(g); return 0; }
+
+int oracle_dims(oracle_graph* g, int* d) {
+  d[0] = g->numPoses; d[1] = g->numLandmarks; d[2] = g->sizePoses; d[3] = g->sizeLandmarks;
+  d[4] = (int)g->activeEdges.size(); d[5] = (int)g->activeVertices.size(); d[6] = g->poseDim; d[7] = g->landmarkDim;
+  return 0;
+}
+int oracle_get_b(oracle_graph* g, double* b) { memcpy(b, g->b.data(), g->b.size() * sizeof(double)); return (int)g->b.size(); }
+int oracle_get_x(oracle_graph* g, double* x) { memcpy(x, g->x.data(), g->x.size() * sizeof(double)); return (int)g->x.size(); }
+int oracle_get_errors(oracle_graph* g, double* err) {
+  size_t k = 0;
+  for (Edge* e : g->activeEdges) for (int i = 0; i < e->D; ++i) err[k++] = e->err[i];
+  return (int)k;
+}
+static int canonical_estimate(const Vertex* v, double* out) {
+  switch (v->kind) {
+    case ORC_VERTEX_SE2: memcpy(out, v->est, 3 * sizeof(double)); return 3;
+    case ORC_VERTEX_SE3: memcpy(out, v->est, 12 * sizeof(double)); return 12;
+    case ORC_VERTEX_CAM: memcpy(out, v->est, 12 * sizeof(double)); return 12;
+    case ORC_VERTEX_XYZ: memcpy(out, v->est, 3 * sizeof(double)); return 3;
+  }
+  return -1;
+}
+int oracle_get_estimate(oracle_graph* g, int id, double* out) {
+  Vertex* v = g->vertex(id);
+  if (!v) return -1;
+  return canonical_estimate(v, out);
+}
+int oracle_vertex_count(oracle_graph* g) { return (int)g->vertices.size(); }
+int oracle_get_vertices(oracle_graph* g, int* ids, int* kinds, int* hidx, int* flags) {
+  std::vector<Vertex*> vs;
+  for (auto& kv : g->vertices) vs.push_back(kv.second);
+  std::sort(vs.begin(), vs.end(), [](Vertex* a, Vertex* b) { return a->id < b->id; });
+  for (size_t i = 0; i < vs.size(); ++i) {
+    ids[i] = vs[i]->id; kinds[i] = vs[i]->kind; hidx[i] = vs[i]->hessianIndex;
+    flags[i] = (vs[i]->fixed ? 1 : 0) | (vs[i]->marginalized ? 2 : 0);
+  }
+  return (int)vs.size();
+}
+int oracle_edge_count(oracle_graph* g) { return (int)g->edges.size(); }
+int oracle_get_edge(oracle_graph* g, int k, int* kind, int* id1, int* id2, double* meas, double* info) {
+  if (k < 0 || k >= (int)g->edges.size()) return -1;
+  Edge* e = g->edges[k].get();
+  *kind = e->kind; *id1 = e->v[0]->id; *id2 = e->v[1]->id;
+  int nm = e->kind == ORC_EDGE_SE2 ? 3 : e->kind == ORC_EDGE_SE3 ? 12 : 2;
+  memcpy(meas, e->meas, nm * sizeof(double));
+  memcpy(info, e->info, e->D * e->D * sizeof(double));
+  return 0;
+}
+int oracle_get_blocks(oracle_graph* g, int which, int* rows, int* cols, double* values) {
+  SBM* M = which == 0 ? &g->Hpp : which == 1 ? &g->Hll : which == 2 ? &g->Hpl : &g->Hschur;
+  int n = 0;
+  const int sz = M->rdim * M->cdim;
+  for (int c = 0; c < M->ncols; ++c)
+    for (auto& kv : M->cols[c]) {
+      if (rows) { rows[n] = kv.first; cols[n] = c; memcpy(values + (size_t)n * sz, kv.second, sz * sizeof(double)); }
+      ++n;
+    }
+  return n;
+}
+int oracle_get_bschur(oracle_graph* g, double* out) { memcpy(out, g->bschur.data(), g->bschur.size() * sizeof(double)); return (int)g->bschur.size(); }
+int oracle_get_block_perm(oracle_graph* g, int* perm) {
+  auto& P = g->linearSolver.blockPerm;
+  if (perm) memcpy(perm, P.data(), P.size() * sizeof(int));
+  return (int)P.size();
+}
+int64_t oracle_get_lnz(oracle_graph* g) { return g->linearSolver.S ? (int64_t)g->linearSolver.S->lnz : -1; }
+
+int oracle_cs_amd(int n, const int* colptr, const int* rowidx, int* perm) {
+  cs aux{};
+  aux.nzmax = colptr[n]; aux.m = aux.n = n; aux.p = const_cast<int*>(colptr); aux.i = const_cast<int*>(rowidx);
+  aux.x = nullptr; aux.nz = -1;
+  int* P = cs_amd(1, &aux);
+  if (!P) return -1;
+  memcpy(perm, P, n * sizeof(int));
+  cs_free(P);
+  return 0;
+}
+int64_t oracle_scalar_amd_lnz(oracle_graph* g) {
+  SBM& M = g->doSchur ? g->Hschur : g->Hpp;
+  LinearSolverCSparseO ls;
+  ls.fill(M, false);
+  css* S = cs_schol(1, &ls.A);
+  if (!S) return -1;
+  int64_t r = (int64_t)S->lnz;
+  cs_sfree(S);
+  return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+/*
+ * oracle.h - C interface of the CPU ORACLE (TEST INFRASTRUCTURE ONLY).
+ *
+ * The oracle is a from-scratch, Eigen-free restatement of the reference's CPU hot path
+ * (g2o SparseOptimizer -> OptimizationAlgorithm{GaussNewton,Levenberg} -> BlockSolver ->
+ * LinearSolverCSparse) that calls the reference's OWN vendored CSparse (compiled in place into
+ * oracle/_ref/libg2o_csparse_ref.so) for ordering, symbolic analysis and numeric Cholesky.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library.  The product (openslam_g2o_b200/) never links, imports or executes it.
+ *
+ * Parity pinning: the reference ships no golden vectors for this path.  The oracle is
+ * pinned by (1) the known-answer table of BASELINE.md section 2 (block-AMD permutation hash, nnz(L)), which was
+ * produced by the reference's vendored CSparse and which this oracle reproduces through the same
+ * library, and (2) the reference's two self-consistency tests restated in tests/ (analytic vs numeric
+ * Jacobian at 1e-6).  The CHOLMOD flavour of the path is unpinned by the reference (SuiteSparse is not
+ * vendored); parity is claimed against the CSparse flavour ({gn,lm}_fix* solvers).
+ */
+#ifndef G2O_B200_ORACLE_H
+#define G2O_B200_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_graph oracle_graph;
+
+/* vertex / edge kinds (shared numbering with include/g2o_b200.h) */
+enum { ORC_VERTEX_SE2 = 0, ORC_VERTEX_SE3 = 1, ORC_VERTEX_CAM = 2, ORC_VERTEX_XYZ = 3 };
+enum { ORC_EDGE_SE2 = 0, ORC_EDGE_SE3 = 1, ORC_EDGE_P2MC = 2 };
+enum { ORC_GN = 0, ORC_LM = 1 };
+
+/* one record per outer iteration; mirrors the fields of G2OBatchStatistics (core/batch_stats.h:40-77) */
+typedef struct oracle_iter_stats {
+  int iteration;
+  int levenberg_iterations;
+  int result;          /* 1 OK, 2 Terminate, -1 Fail (core/optimization_algorithm.h SolverResult) */
+  int reserved;
+  double chi2;         /* activeRobustChi2 after the iteration */
+  double lambda;       /* _currentLambda after the iteration (LM) */
+  double time_residuals, time_quadratic_form, time_schur, time_symbolic, time_numeric,
+         time_linear_solver, time_linear_solution, time_update, time_iteration;
+} oracle_iter_stats;
+
+oracle_graph* oracle_new(void);
+void oracle_free(oracle_graph* g);
+
+/* OptimizableGraph::load (core/optimizable_graph.cpp:356-569) for the configured tags */
+int oracle_load(oracle_graph* g, const char* path);
+/* programmatic construction; payload = the numbers that follow the ids on the .g2o line */
+int oracle_add_vertex(oracle_graph* g, int kind, int id, const double* payload, int n);
+int oracle_add_edge(oracle_graph* g, int kind, int id1, int id2, const double* payload, int n);
+int oracle_set_fixed(oracle_graph* g, int id, int fixed);
+
+/* apps/g2o_cli/g2o.cpp:272-320: gauge fixing + marginalisation of the low-dimensional vertices.
+ * returns the id of the vertex fixed as gauge, -1 if none was needed, -2 on error. */
+int oracle_setup_cli(oracle_graph* g, int requires_marginalize);
+/* SparseOptimizer::initializeOptimization (core/sparse_optimizer.cpp:199-267) */
+int oracle_initialize(oracle_graph* g);
+/* LinearSolverCSparse::setBlockOrdering (solver_csparse.cpp: fix* -> 1, var -> 0) */
+void oracle_set_block_ordering(oracle_graph* g, int block_ordering);
+
+/* SparseOptimizer::optimize (core/sparse_optimizer.cpp:354-419); returns #iterations done (0 on Fail) */
+int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_stats* stats);
+
+/* ---- step-wise access to the same objects (for fine-grained parity tests) ---- */
+int oracle_algorithm_init(oracle_graph* g);             /* OptimizationAlgorithmWithHessian::init */
+int oracle_build_structure(oracle_graph* g);            /* BlockSolver::buildStructure */
+double oracle_compute_active_errors(oracle_graph* g);   /* computeActiveErrors + activeRobustChi2 */
+int oracle_build_system(oracle_graph* g);               /* BlockSolver::buildSystem */
+double oracle_lambda_init(oracle_graph* g);             /* Levenberg::computeLambdaInit */
+int oracle_set_lambda(oracle_graph* g, double lambda, int backup);
+int oracle_restore_diagonal(oracle_graph* g);
+int oracle_solve(oracle_graph* g);                      /* BlockSolver::solve, 1 ok / 0 not PD */
+int oracle_update(oracle_graph* g);                     /* SparseOptimizer::update(solver.x()) */
+int oracle_push(oracle_graph* g);
+int oracle_pop(oracle_graph* g);
+int oracle_discard_top(oracle_graph* g);
+
+/* dims[0..7] = numPoses, numLandmarks, sizePoses, sizeLandmarks, #activeEdges, #activeVertices,
+ *              poseDim, landmarkDim */
+int oracle_dims(oracle_graph* g, int* dims);
+int oracle_get_b(oracle_graph* g, double* b);           /* length sizePoses+sizeLandmarks */
+int oracle_get_x(oracle_graph* g, double* x);
+int oracle_get_errors(oracle_graph* g, double* err);    /* active edges in order, D doubles each */
+/* canonical estimate layouts: SE2 [x y th]; SE3 [R col-major 9, t 3]; CAM [t3 q(xyzw)4 fx fy cx cy b];
+ * XYZ [x y z].  returns #doubles written or -1 */
+int oracle_get_estimate(oracle_graph* g, int id, double* out);
+int oracle_vertex_count(oracle_graph* g);
+/* all vertices ascending id: ids[], kind[], hessianIndex[], flags (1 fixed | 2 marginalized) */
+int oracle_get_vertices(oracle_graph* g, int* ids, int* kinds, int* hidx, int* flags);
+int oracle_edge_count(oracle_graph* g);                 /* all edges, file order */
+/* canonical edge data: ids of both vertices + measurement + information, see oracle_get_estimate.
+ * meas: SE2 [x y th]; SE3 [R9 t3] of Z; P2MC [u v].  info: full DxD col-major. */
+int oracle_get_edge(oracle_graph* g, int k, int* kind, int* id1, int* id2, double* meas, double* info);
+
+/* Hessian blocks. which: 0 Hpp, 1 Hll, 2 Hpl, 3 Hschur.  First call with rows==NULL returns #blocks.
+ * blocks are listed column by column, ascending row; values column-major, rdim*cdim each. */
+int oracle_get_blocks(oracle_graph* g, int which, int* rows, int* cols, double* values);
+int oracle_get_bschur(oracle_graph* g, double* out);
+/* symbolic results of LinearSolverCSparse::computeSymbolicDecomposition
+ * (solvers/csparse/linear_solver_csparse.h:246-300): block permutation (block ordering) or scalar
+ * permutation, and nnz(L). */
+int oracle_get_block_perm(oracle_graph* g, int* perm);  /* returns length */
+int64_t oracle_get_lnz(oracle_graph* g);
+
+/* standalone ordering known-answer helper: runs the vendored cs_amd(1, pattern) on an upper-triangular
+ * block pattern in CCS form (as fillBlockStructure emits it) */
+int oracle_cs_amd(int n, const int* colptr, const int* rowidx, int* perm);
+/* scalar cs_schol(1, A) lnz of the current linear system (for BASELINE.md "scalar-AMD" column) */
+int64_t oracle_scalar_amd_lnz(oracle_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
