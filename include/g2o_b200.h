@@ -1,0 +1,198 @@
+/*
+ * g2o_b200.h - C-ABI of the B200-native g2o solve path (libg2o_b200.so).
+ *
+ * Plain C: opaque handles, caller-owned buffers, int status returns (0 = ok, >0 = numerical outcome,
+ * <0 = error; b200_last_error() gives the text).  No C++/torch types cross this boundary.
+ * Everything behind it runs as hand-written sm_100a CUDA; there is NO CPU fallback: every compute entry
+ * point fails with B200_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to /root/reference/g2o).
+ *
+ * Data layouts (all double = IEEE f64, all indices 32-bit int, matrices column-major like Eigen):
+ *   vertex estimates  SE2: [x y theta]                              (types/slam2d/vertex_se2.h:64-73)
+ *                     SE3: [R(3x3 col-major) t(3)] = Isometry3d     (types/slam3d/vertex_se3.h, state is R|t)
+ *                     CAM: [t(3) q(x y z w) fx fy cx cy baseline]   (types/sba/sbacam.h:60-98)
+ *                     XYZ: [x y z]                                  (types/sba/types_sba.h:136-156)
+ *   edge measurement  SE2: [x y theta] of Z; SE3: [R t] of Z (12); P2MC: [u v]
+ *   edge information  full D x D column-major (D = 3, 6, 2)
+ */
+#ifndef G2O_B200_H
+#define G2O_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_NOT_POSITIVE_DEFINITE 1   /* LinearSolver::solve returned false (linear_solver.h:59) */
+#define B200_ERR_INVALID (-1)
+#define B200_ERR_NO_DEVICE (-2)
+#define B200_ERR_CUDA (-3)
+#define B200_ERR_UNSUPPORTED (-4)      /* graph uses types outside {SE2,SE3,CAM,XYZ}: no CPU fallback */
+#define B200_ERR_COLLECTIVE (-5)
+
+enum { B200_VERTEX_SE2 = 0, B200_VERTEX_SE3 = 1, B200_VERTEX_CAM = 2, B200_VERTEX_XYZ = 3 };
+enum { B200_EDGE_SE2 = 0, B200_EDGE_SE3 = 1, B200_EDGE_P2MC = 2 };
+enum { B200_GAUSS_NEWTON = 0, B200_LEVENBERG = 1 };
+/* OptimizationAlgorithm::SolverResult (core/optimization_algorithm.h:49) */
+enum { B200_RESULT_TERMINATE = 2, B200_RESULT_OK = 1, B200_RESULT_FAIL = -1 };
+
+typedef struct b200_ctx b200_ctx;
+
+/* POD twin of G2OBatchStatistics (core/batch_stats.h:40-77); times in seconds (CUDA events / monotonic) */
+typedef struct b200_iter_stats {
+  int32_t iteration;
+  int32_t levenberg_iterations;
+  int32_t result;
+  int32_t reserved;
+  double chi2;
+  double lambda;
+  double time_residuals, time_quadratic_form, time_schur, time_symbolic, time_numeric,
+         time_linear_solver, time_linear_solution, time_update, time_iteration;
+} b200_iter_stats;
+
+/* optional collective for landmark-sharded BA: sum-all-reduce `count` doubles living at DEVICE pointer
+ * `dev_ptr`, ordered on CUDA stream `stream` (a cudaStream_t).  The host side supplies it (NCCL through
+ * torch.distributed in the Python harness, ncclAllReduce in a C++ host).  return 0 on success. */
+typedef int (*b200_allreduce_fn)(void* dev_ptr, int64_t count, void* stream, void* user);
+
+/* ------------------------------------------------------------------ lifetime */
+int b200_device_count(void);
+int b200_create(int device, b200_ctx** out);
+void b200_destroy(b200_ctx* ctx);
+const char* b200_last_error(const b200_ctx* ctx);   /* ctx may be NULL: last creation error */
+const char* b200_version(void);
+
+/* ------------------------------------------------------------------ graph ingest
+ * What a Solver adapter extracts in buildStructure() from SparseOptimizer::indexMapping()/activeEdges()
+ * (core/block_solver.hpp:142-295).  One pose kind and at most one landmark kind (XYZ) per context.
+ * hessian_index: g2o's v->hessianIndex() (-1 = fixed);  marginalized: v->marginalized() (may be NULL). */
+int b200_set_vertices(b200_ctx* ctx, int kind, int n, const double* estimates,
+                      const int32_t* hessian_index, const uint8_t* marginalized);
+/* vi/vj index into the vertex array of the kind the edge type expects
+ * (SE2: SE2,SE2; SE3: SE3,SE3; P2MC: vi = XYZ point, vj = CAM).  Order = active edge order (internalId). */
+int b200_set_edges(b200_ctx* ctx, int kind, int n, const int32_t* vi, const int32_t* vj,
+                   const double* measurement, const double* information);
+/* landmark sharding: this context owns the landmarks / edges it was given; cameras are
+ * replicated.  After the local Schur reduction [Hschur | bschur | scalars] is all-reduced through fn. */
+int b200_set_allreduce(b200_ctx* ctx, b200_allreduce_fn fn, void* user, int rank, int world_size);
+/* sharded BA: blocks (rows[i] <= cols[i]) that OTHER shards contribute to the reduced camera matrix, so that
+ * every rank builds the identical Hschur pattern (core/block_solver.hpp:262-288 over the whole graph) */
+int b200_add_schur_pattern(b200_ctx* ctx, int n, const int32_t* rows, const int32_t* cols);
+/* the CUDA stream (cudaStream_t) all work of this context is ordered on; b200_synchronize waits for it */
+void* b200_get_stream(b200_ctx* ctx);
+int b200_synchronize(b200_ctx* ctx);
+
+/* ------------------------------------------------------------------ Level 2: g2o::Solver (core/solver.h:44-149) */
+/* Solver::buildStructure (core/block_solver.hpp:142-295) + LinearSolver symbolic phase
+ * (solvers/csparse/linear_solver_csparse.h:246-300): block pattern, block AMD, supernodal analysis. */
+int b200_build_structure(b200_ctx* ctx);
+/* SparseOptimizer::computeActiveErrors + activeRobustChi2 (core/sparse_optimizer.cpp:61-114) */
+int b200_compute_active_errors(b200_ctx* ctx, double* chi2);
+/* Solver::buildSystem (core/block_solver.hpp:501-560) */
+int b200_build_system(b200_ctx* ctx);
+/* Solver::setLambda / restoreDiagonal (core/block_solver.hpp:563-604) */
+int b200_set_lambda(b200_ctx* ctx, double lambda, int backup);
+int b200_restore_diagonal(b200_ctx* ctx);
+/* Solver::solve (core/block_solver.hpp:354-486): [Schur] + sparse Cholesky + back-substitution.
+ * returns B200_OK or B200_NOT_POSITIVE_DEFINITE. */
+int b200_solve(b200_ctx* ctx);
+/* SparseOptimizer::update(solver->x()) (core/sparse_optimizer.cpp:421-434) */
+int b200_update(b200_ctx* ctx);
+/* SparseOptimizer::push / pop / discardTop (core/sparse_optimizer.cpp:515-553, 599-612) */
+int b200_push(b200_ctx* ctx);
+int b200_pop(b200_ctx* ctx);
+int b200_discard_top(b200_ctx* ctx);
+
+/* ------------------------------------------------------------------ Level 3: g2o::OptimizationAlgorithm
+ * SparseOptimizer::optimize loop over OptimizationAlgorithm{GaussNewton,Levenberg}::solve
+ * (core/sparse_optimizer.cpp:354-419, core/optimization_algorithm_levenberg.cpp:57-147,
+ * core/optimization_algorithm_gauss_newton.cpp:50-93), whole iteration device-resident.
+ * stats may be NULL, else room for max_iterations records.  returns #iterations done (0 on Fail), <0 error */
+int b200_optimize(b200_ctx* ctx, int algorithm, int max_iterations, b200_iter_stats* stats);
+/* one OptimizationAlgorithm::solve(iteration) */
+int b200_algorithm_solve(b200_ctx* ctx, int algorithm, int iteration, b200_iter_stats* stats);
+/* LM properties (core/optimization_algorithm_levenberg.cpp:43-49) */
+int b200_set_lm_params(b200_ctx* ctx, double user_lambda_init, int max_trials_after_failure);
+
+/* ------------------------------------------------------------------ read-back (host mirrors the adapter needs) */
+/* dims[8] = numPoses numLandmarks sizePoses sizeLandmarks numEdges numVertices poseDim landmarkDim */
+int b200_get_dims(b200_ctx* ctx, int32_t* dims);
+int b200_get_x(b200_ctx* ctx, double* x);           /* Solver::x(), length sizePoses+sizeLandmarks */
+int b200_get_b(b200_ctx* ctx, double* b);           /* Solver::b() */
+int b200_get_estimates(b200_ctx* ctx, int kind, double* estimates);  /* same layout/order as set_vertices */
+int b200_get_hessian_diagonal(b200_ctx* ctx, double* diag);          /* v->hessian(j,j), index order */
+/* which: 0 Hpp 1 Hll 2 Hpl 3 Hschur; call with rows==NULL to get the block count.  Blocks are listed
+ * column by column, ascending block row (SparseBlockMatrix order), values column-major. */
+int b200_get_blocks(b200_ctx* ctx, int which, int32_t* rows, int32_t* cols, double* values);
+int b200_get_bschur(b200_ctx* ctx, double* out);
+/* fill-reducing block ordering actually used (bit-exact twin of cs_amd(1, blockPattern),
+ * EXTERNAL/csparse/cs_amd.c:18-364 as called from linear_solver_csparse.h:268) and nnz(L) of the scalar
+ * factor it implies (css::lnz, linear_solver_csparse.h:292-293) */
+int b200_get_block_ordering(b200_ctx* ctx, int32_t* perm);   /* returns #blocks */
+int64_t b200_get_factor_nnz(b200_ctx* ctx);
+/* supernodal schedule facts: out[0..5] = #supernodes, #tasks, #levels, max panel rows, max panel cols,
+ * stored factor doubles */
+int b200_get_factor_info(b200_ctx* ctx, int64_t* out);
+/* kernels launched by this context since creation (bench "gpu_launches") */
+int64_t b200_get_launch_count(b200_ctx* ctx);
+/* seconds of the dominant kernels accumulated with CUDA events when profiling is on */
+int b200_set_profiling(b200_ctx* ctx, int on);
+/* phase id: 0 errors 1 linearize 2 schur 3 factor 4 trisolve 5 update 6 backsub; returns seconds,count */
+int b200_get_phase_time(b200_ctx* ctx, int phase, double* seconds, int64_t* count);
+
+/* ------------------------------------------------------------------ Level 1: g2o::LinearSolver<MatrixType>
+ * (core/linear_solver.h:40-81): solve A x = b for an upper-triangular block-CCS SparseBlockMatrix
+ * (core/sparse_block_matrix.h:61-220) with uniform block size.  Pattern is analysed at the first solve after
+ * b200_ls_init(), like LinearSolverCSparse (linear_solver_csparse.h:106-142). */
+typedef struct b200_linear_solver b200_linear_solver;
+int b200_ls_create(int device, b200_linear_solver** out);
+void b200_ls_destroy(b200_linear_solver* ls);
+int b200_ls_init(b200_linear_solver* ls);            /* LinearSolver::init(): drop the symbolic factor */
+/* colptr[nblocks+1], rowidx[]: upper block pattern incl. diagonal, ascending rows per column
+ * (SparseBlockMatrix::fillBlockStructure, core/sparse_block_matrix.hpp:519-545).
+ * values: blocks in the same order, block_dim^2 doubles each, column-major.  x,b: HOST buffers. */
+int b200_ls_solve(b200_linear_solver* ls, int nblocks, int block_dim, const int32_t* colptr,
+                  const int32_t* rowidx, const double* values, double* x, const double* b);
+int b200_ls_get_block_ordering(b200_linear_solver* ls, int32_t* perm);
+int64_t b200_ls_get_factor_nnz(b200_linear_solver* ls);
+const char* b200_ls_last_error(const b200_linear_solver* ls);
+
+/* ------------------------------------------------------------------ host-only helpers (no GPU needed)
+ * The ordering by itself, for parity checks against cs_amd. */
+int b200_block_amd(int nblocks, const int32_t* colptr, const int32_t* rowidx, int32_t* perm);
+
+/* ------------------------------------------------------------------ standalone host
+ * .g2o text -> SoA ingest without the g2o object graph: OptimizableGraph::load
+ * (core/optimizable_graph.cpp:356-569) for the configured tags, the CLI's gauge + marginalisation
+ * (apps/g2o_cli/g2o.cpp:272-320) and SparseOptimizer::initializeOptimization index mapping
+ * (core/sparse_optimizer.cpp:166-267), then b200_set_vertices/b200_set_edges on ctx. */
+typedef struct b200_graph b200_graph;
+int b200_graph_create(b200_graph** out);
+void b200_graph_destroy(b200_graph* g);
+int b200_graph_load(b200_graph* g, const char* path);
+int b200_graph_add_vertex(b200_graph* g, int kind, int id, const double* payload, int n);
+int b200_graph_add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, int n);
+/* bulk ingest: payload row-major [n x stride] */
+int b200_graph_add_vertices(b200_graph* g, int kind, int n, const int32_t* ids, const double* payload, int stride);
+int b200_graph_add_edges(b200_graph* g, int kind, int n, const int32_t* id1, const int32_t* id2, const double* payload, int stride);
+int b200_graph_set_fixed(b200_graph* g, int id, int fixed);
+/* returns the gauge vertex id fixed (or -1 if none needed) */
+int b200_graph_setup_cli(b200_graph* g, int requires_marginalize);
+int b200_graph_initialize(b200_graph* g);
+/* counts[4] = #vertices by kind; edge_counts[3] */
+int b200_graph_counts(b200_graph* g, int32_t* vertex_counts, int32_t* edge_counts);
+/* upload to a context.  shard/num_shards: landmark sharding (0,1 = everything) */
+int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards);
+/* write estimates from ctx back into the graph; b200_graph_get_estimate returns the canonical layout */
+int b200_graph_download(b200_graph* g, b200_ctx* ctx);
+int b200_graph_get_estimate(b200_graph* g, int id, double* out);
+/* info[4] = kind, hessianIndex, fixed, marginalized */
+int b200_graph_get_vertex_info(b200_graph* g, int id, int32_t* info);
+int b200_graph_save(b200_graph* g, const char* path);   /* OptimizableGraph::save (optimizable_graph.cpp:589-622) */
+const char* b200_graph_last_error(const b200_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

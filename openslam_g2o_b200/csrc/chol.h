@@ -1,0 +1,54 @@
+// chol.h - supernodal left-looking sparse block Cholesky on the GPU (host-side interface).
+//
+// Replaces the numeric phase of the reference's linear solvers for the reduced pose system:
+// LinearSolverCSparse::solve -> cs_cholsolsymb -> cs_chol_workspace + cs_lsolve/cs_ltsolve
+// (solvers/csparse/linear_solver_csparse.h:106-142, solvers/csparse/csparse_helper.cpp:56-143) and
+// LinearSolverCholmod::solve -> cholmod_factorize + cholmod_solve
+// (solvers/cholmod/linear_solver_cholmod.h:115-154).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "common.h"
+#include "symbolic.h"
+
+namespace g2o_b200 {
+
+class CholeskyGpu {
+ public:
+  CholeskyGpu() = default;
+  ~CholeskyGpu();
+  // host: ordering + symbolic analysis; uploads the plan.  colptr/rowidx = upper block pattern.
+  void analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt, cudaStream_t s);
+  bool analyzed() const { return analyzed_; }
+  void reset() { analyzed_ = false; }
+  const SymbolicFactor& symbolic() const { return S_; }
+
+  // numeric factorisation of A + lambda*I (A: device, input block order, d*d col-major per block).
+  // d_lambda may be nullptr (lambda = 0).  Asynchronous on s; the not-positive-definite outcome lands in
+  // the device flag read by status().
+  void factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc);
+  // x = A^-1 b (both device, length nb*d, original ordering).  Asynchronous on s.
+  void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc);
+  int* status_ptr() { return d_status_.p; }  // device int: 0 ok, 1 not positive definite
+  double* factor_values() { return d_L_.p; }
+
+ private:
+  bool analyzed_ = false;
+  SymbolicFactor S_;
+  DevBuf<int> d_sn_col0_, d_sn_ncol_, d_sn_nrow_, d_sn_rowptr_, d_sn_rows_;
+  DevBuf<long long> d_sn_lptr_;
+  DevBuf<int> d_upd_ptr_, d_upd_k_, d_upd_p0_, d_upd_p1_, d_rel_;
+  DevBuf<long long> d_upd_relptr_;
+  DevBuf<int> d_task_ptr_, d_task_sn_;
+  DevBuf<long long> d_a_dst_, d_diag_dst_;
+  DevBuf<int> d_a_ld_, d_diag_ld_, d_perm_;
+  DevBuf<unsigned char> d_a_trans_;
+  DevBuf<double> d_L_, d_y_;
+  DevBuf<int> d_status_;
+  int nblk_ = 0;
+  std::vector<int> level_threads_;  // CTA size per level
+};
+
+}  // namespace g2o_b200

@@ -1,0 +1,86 @@
+// common.h - CUDA error handling and device buffers shared by the .cu translation units
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace g2o_b200 {
+
+struct CudaError {
+  cudaError_t code;
+  const char* what;
+  const char* file;
+  int line;
+};
+
+#define B200_CUDA(expr)                                                         \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) throw ::g2o_b200::CudaError{_e, #expr, __FILE__, __LINE__}; \
+  } while (0)
+
+inline std::string describe(const CudaError& e) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e.code, cudaGetErrorString(e.code), e.file,
+           e.line, e.what);
+  return buf;
+}
+
+// Host-only contexts (b200_create(-1, ..)) run the integer structure phase without a device so that ordering /
+// pattern / sharding logic can be tested on a CPU box; every compute entry point still fails loudly there.
+inline bool& host_only_flag() {
+  static thread_local bool f = false;
+  return f;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;    // elements in use
+  size_t cap = 0;  // elements allocated
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cap = 0;
+  }
+  void alloc(size_t count) {
+    if (host_only_flag()) { n = count; return; }
+    if (count <= cap && p) { n = count; return; }
+    release();
+    const size_t c = count == 0 ? 1 : count;
+    B200_CUDA(cudaMalloc((void**)&p, c * sizeof(T)));
+    cap = c;
+    n = count;
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) {
+    alloc(h.size());
+    if (host_only_flag()) return;
+    if (!h.empty()) B200_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (host_only_flag()) return;
+    if (count) B200_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(cudaStream_t s) {
+    if (host_only_flag()) return;
+    if (p && n) B200_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+// counts every kernel launch of this library (reported as bench "gpu_launches")
+struct LaunchCounter {
+  int64_t n = 0;
+};
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace g2o_b200

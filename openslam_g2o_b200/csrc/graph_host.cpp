@@ -1,0 +1,551 @@
+// graph_host.cpp - standalone host side above the C-ABI: .g2o text <-> SoA arrays without the g2o object graph.
+//
+// Mirrors, for the configured tags only (VERTEX_SE2, EDGE_SE2, VERTEX_SE3:QUAT, EDGE_SE3:QUAT, VERTEX_CAM,
+// VERTEX_XYZ, EDGE_PROJECT_P2MC, FIX):
+//   OptimizableGraph::load                      core/optimizable_graph.cpp:356-569
+//   per-type read()                             types/slam2d/{vertex_se2,edge_se2}.cpp, types/slam3d/{vertex_se3,edge_se3}.cpp,
+//                                               types/sba/types_sba.cpp:74-112,180-186,204-213
+//   g2o CLI gauge + marginalisation             apps/g2o_cli/g2o.cpp:272-320, core/sparse_optimizer.cpp:116-164
+//   SparseOptimizer::initializeOptimization     core/sparse_optimizer.cpp:166-267
+//   OptimizableGraph::save                      core/optimizable_graph.cpp:589-622
+// Host-only, pointer-free after load; everything numeric per iteration happens behind b200_ctx.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <tr1/unordered_map>
+#include <vector>
+
+#include "../../include/g2o_b200.h"
+#include "geometry.cuh"
+
+using namespace g2o_b200;
+
+namespace {
+struct HVertex {
+  int kind = 0, id = 0;
+  bool fixed = false, marginalized = false, active = false;
+  int hidx = -1;
+  int slot = -1;  // index inside the per-kind array handed to the context
+  double est[12];
+};
+struct HEdge {
+  int kind = 0;
+  int v0 = 0, v1 = 0;  // indices into vertices
+  bool active = false;
+  double meas[12];
+  double info[36];
+};
+int vdim(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 6; }
+int vest(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12; }
+int edim(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
+int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
+
+void quat_normalize(double* q) {
+  double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+// Eigen Quaterniond(Matrix3d), for save() (toVectorQT, isometry3d_mappings.cpp:101-108)
+void R_to_quat(const double* R, double* q) {
+  auto m = [&](int r, int c) { return R[r + 3 * c]; };
+  double t = m(0, 0) + m(1, 1) + m(2, 2);
+  if (t > 0) {
+    t = std::sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t;
+    q[0] = (m(2, 1) - m(1, 2)) * t; q[1] = (m(0, 2) - m(2, 0)) * t; q[2] = (m(1, 0) - m(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (m(k, j) - m(j, k)) * t; q[j] = (m(j, i) + m(i, j)) * t; q[k] = (m(k, i) + m(i, k)) * t;
+  }
+}
+}  // namespace
+
+struct b200_graph {
+  std::tr1::unordered_map<int, int> idmap;  // same container family as HyperGraph::VertexIDMap (gauge order!)
+  std::vector<HVertex> vertices;
+  std::vector<HEdge> edges;
+  std::vector<int> active_edges;            // edge indices, internalId order
+  std::vector<int> kind_slots[4];           // per kind: vertex indices handed to the context (ascending id)
+  std::string err;
+  int find(int id) const { auto it = idmap.find(id); return it == idmap.end() ? -1 : it->second; }
+};
+
+namespace {
+
+int add_vertex(b200_graph* g, int kind, int id) {
+  if (g->find(id) >= 0) return -1;  // HyperGraph::addVertex refuses duplicate ids
+  HVertex v;
+  v.kind = kind; v.id = id;
+  for (double& d : v.est) d = 0;
+  g->vertices.push_back(v);
+  g->idmap[id] = (int)g->vertices.size() - 1;
+  return (int)g->vertices.size() - 1;
+}
+void set_to_origin(HVertex& v) {
+  for (double& d : v.est) d = 0;
+  if (v.kind == B200_VERTEX_SE3) v.est[0] = v.est[4] = v.est[8] = 1;
+  if (v.kind == B200_VERTEX_CAM) { v.est[6] = 1; v.est[7] = 1; v.est[8] = 1; v.est[9] = 0.5; v.est[10] = 0.5; }
+}
+bool vertex_read(HVertex& v, const double* p, int n) {
+  switch (v.kind) {
+    case B200_VERTEX_SE2:
+    case B200_VERTEX_XYZ:
+      if (n < 3) return false;
+      v.est[0] = p[0]; v.est[1] = p[1]; v.est[2] = p[2];
+      return true;
+    case B200_VERTEX_SE3: {  // fromVectorQT: quaternion used un-normalised (isometry3d_mappings.cpp:131-136)
+      if (n < 7) return false;
+      const double q[4] = {p[3], p[4], p[5], p[6]};
+      geo::quat_to_R(q, v.est);
+      v.est[9] = p[0]; v.est[10] = p[1]; v.est[11] = p[2];
+      return true;
+    }
+    case B200_VERTEX_CAM: {  // types_sba.cpp:74-112 + SE3Quat::normalizeRotation (se3quat.h:280-285)
+      if (n < 7) return false;
+      v.est[0] = p[0]; v.est[1] = p[1]; v.est[2] = p[2];
+      double q[4] = {p[3], p[4], p[5], p[6]};
+      quat_normalize(q);
+      if (q[3] < 0) for (double& d : q) d *= -1;
+      quat_normalize(q);
+      for (int i = 0; i < 4; ++i) v.est[3 + i] = q[i];
+      if (n >= 12) for (int i = 0; i < 5; ++i) v.est[7 + i] = p[7 + i];
+      else { v.est[7] = 300; v.est[8] = 300; v.est[9] = 320; v.est[10] = 320; v.est[11] = 0.1; }
+      return true;
+    }
+  }
+  return false;
+}
+bool edge_read(HEdge& e, const double* p, int n) {
+  const int D = edim(e.kind);
+  for (double& d : e.info) d = 0;
+  for (int i = 0; i < D; ++i) e.info[i + D * i] = 1;
+  switch (e.kind) {
+    case B200_EDGE_SE2: {
+      if (n < 9) return false;
+      e.meas[0] = p[0]; e.meas[1] = p[1]; e.meas[2] = p[2];
+      int k = 3;
+      for (int i = 0; i < 3; ++i) for (int j = i; j < 3; ++j) { e.info[i + 3 * j] = p[k]; e.info[j + 3 * i] = p[k]; ++k; }
+      return true;
+    }
+    case B200_EDGE_SE3: {  // measurement quaternion IS normalised (edge_se3.cpp:18-20)
+      if (n < 7) return false;
+      double q[4] = {p[3], p[4], p[5], p[6]};
+      quat_normalize(q);
+      geo::quat_to_R(q, e.meas);
+      e.meas[9] = p[0]; e.meas[10] = p[1]; e.meas[11] = p[2];
+      int k = 7;
+      for (int i = 0; i < 6 && k < n; ++i) for (int j = i; j < 6 && k < n; ++j) { e.info[i + 6 * j] = p[k]; e.info[j + 6 * i] = p[k]; ++k; }
+      return true;
+    }
+    case B200_EDGE_P2MC:  // information forced to identity on read (types_sba.cpp:204-213)
+      if (n < 2) return false;
+      e.meas[0] = p[0]; e.meas[1] = p[1];
+      return true;
+  }
+  return false;
+}
+// EdgeSE2/EdgeSE3::initialEstimate for vertices first seen in an edge line (load with createEdges = true)
+void initial_estimate(b200_graph* g, const HEdge& e, bool to_from_from) {
+  HVertex& a = g->vertices[e.v0];
+  HVertex& b = g->vertices[e.v1];
+  if (e.kind == B200_EDGE_SE2) {
+    geo::SE2 z{e.meas[0], e.meas[1], e.meas[2]};
+    if (to_from_from) { geo::SE2 r = geo::se2_mul(geo::SE2{a.est[0], a.est[1], a.est[2]}, z); b.est[0] = r.x; b.est[1] = r.y; b.est[2] = r.th; }
+    else { geo::SE2 r = geo::se2_mul(geo::SE2{b.est[0], b.est[1], b.est[2]}, geo::se2_inv(z)); a.est[0] = r.x; a.est[1] = r.y; a.est[2] = r.th; }
+  } else if (e.kind == B200_EDGE_SE3) {
+    geo::Iso Z, A, B;
+    memcpy(Z.R, e.meas, 72); memcpy(Z.t, e.meas + 9, 24);
+    memcpy(A.R, a.est, 72); memcpy(A.t, a.est + 9, 24);
+    memcpy(B.R, b.est, 72); memcpy(B.t, b.est + 9, 24);
+    if (to_from_from) { geo::Iso r = geo::iso_mul(A, Z); memcpy(b.est, r.R, 72); memcpy(b.est + 9, r.t, 24); }
+    else { geo::Iso r = geo::iso_mul(B, geo::iso_inverse(Z)); memcpy(a.est, r.R, 72); memcpy(a.est + 9, r.t, 24); }
+  }
+}
+int add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, int n) {
+  static const int vk0[3] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_XYZ};
+  static const int vk1[3] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_CAM};
+  int a = g->find(id1), b = g->find(id2);
+  int doInit = 0;
+  if (a < 0) { a = add_vertex(g, vk0[kind], id1); set_to_origin(g->vertices[a]); doInit = 2; }
+  if (b < 0) { b = add_vertex(g, vk1[kind], id2); set_to_origin(g->vertices[b]); doInit = 1; }
+  if (g->vertices[a].kind != vk0[kind] || g->vertices[b].kind != vk1[kind]) { g->err = "edge connects vertices of the wrong type"; return B200_ERR_UNSUPPORTED; }
+  HEdge e;
+  e.kind = kind; e.v0 = a; e.v1 = b;
+  if (!edge_read(e, payload, n)) { g->err = "short edge payload"; return B200_ERR_INVALID; }
+  g->edges.push_back(e);
+  if (doInit == 1) initial_estimate(g, e, true);
+  if (doInit == 2) initial_estimate(g, e, false);
+  return B200_OK;
+}
+
+// tokenizer over an in-memory copy of the file (20M-edge inputs: no iostreams on the hot parse path)
+struct LineParser {
+  const char* p;
+  const char* end;
+  bool next_token(const char*& b, const char*& e) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    if (p >= end || *p == '\n') return false;
+    b = p;
+    while (p < end && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r') ++p;
+    e = p;
+    return true;
+  }
+  void skip_line() {
+    while (p < end && *p != '\n') ++p;
+    if (p < end) ++p;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int b200_graph_create(b200_graph** out) {
+  if (!out) return B200_ERR_INVALID;
+  *out = new b200_graph();
+  return B200_OK;
+}
+void b200_graph_destroy(b200_graph* g) { delete g; }
+const char* b200_graph_last_error(const b200_graph* g) { return g ? g->err.c_str() : ""; }
+
+int b200_graph_add_vertex(b200_graph* g, int kind, int id, const double* payload, int n) {
+  if (!g || kind < 0 || kind > 3) return B200_ERR_INVALID;
+  int v = add_vertex(g, kind, id);
+  if (v < 0) { g->err = "duplicate vertex id"; return B200_ERR_INVALID; }
+  if (!vertex_read(g->vertices[v], payload, n)) { g->err = "short vertex payload"; return B200_ERR_INVALID; }
+  return B200_OK;
+}
+int b200_graph_add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, int n) {
+  if (!g || kind < 0 || kind > 2) return B200_ERR_INVALID;
+  return add_edge(g, kind, id1, id2, payload, n);
+}
+// bulk variants: payload is row-major [n x stride]
+int b200_graph_add_vertices(b200_graph* g, int kind, int n, const int32_t* ids, const double* payload, int stride) {
+  if (!g || kind < 0 || kind > 3 || n < 0 || !ids || !payload) return B200_ERR_INVALID;
+  g->vertices.reserve(g->vertices.size() + n);
+  for (int i = 0; i < n; ++i) {
+    int rc = b200_graph_add_vertex(g, kind, ids[i], payload + (size_t)i * stride, stride);
+    if (rc) return rc;
+  }
+  return B200_OK;
+}
+int b200_graph_add_edges(b200_graph* g, int kind, int n, const int32_t* id1, const int32_t* id2, const double* payload, int stride) {
+  if (!g || kind < 0 || kind > 2 || n < 0 || !id1 || !id2 || !payload) return B200_ERR_INVALID;
+  g->edges.reserve(g->edges.size() + n);
+  for (int i = 0; i < n; ++i) {
+    int rc = add_edge(g, kind, id1[i], id2[i], payload + (size_t)i * stride, stride);
+    if (rc) return rc;
+  }
+  return B200_OK;
+}
+int b200_graph_set_fixed(b200_graph* g, int id, int fixed) {
+  if (!g) return B200_ERR_INVALID;
+  int v = g->find(id);
+  if (v < 0) { g->err = "unable to fix vertex: not found"; return B200_ERR_INVALID; }
+  g->vertices[v].fixed = fixed != 0;
+  return B200_OK;
+}
+
+int b200_graph_load(b200_graph* g, const char* path) {
+  if (!g || !path) return B200_ERR_INVALID;
+  FILE* f = fopen(path, "rb");
+  if (!f) { g->err = std::string("cannot open ") + path; return B200_ERR_INVALID; }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> buf((size_t)sz + 1);
+  size_t rd = fread(buf.data(), 1, (size_t)sz, f);
+  fclose(f);
+  buf[rd] = '\n';
+  LineParser lp{buf.data(), buf.data() + rd + 1};
+  std::vector<double> nums;
+  while (lp.p < lp.end) {
+    const char *tb, *te;
+    if (!lp.next_token(tb, te)) { lp.skip_line(); continue; }
+    std::string tag(tb, te);
+    if (tag[0] == '#') { lp.skip_line(); continue; }
+    if (tag == "FIX") {
+      while (lp.next_token(tb, te)) {
+        int id = (int)strtol(tb, nullptr, 10);
+        int v = g->find(id);
+        if (v >= 0) g->vertices[v].fixed = true;
+      }
+      lp.skip_line();
+      continue;
+    }
+    int vkind = -1, ekind = -1;
+    if (tag == "VERTEX_SE2") vkind = B200_VERTEX_SE2;
+    else if (tag == "VERTEX_SE3:QUAT") vkind = B200_VERTEX_SE3;
+    else if (tag == "VERTEX_CAM") vkind = B200_VERTEX_CAM;
+    else if (tag == "VERTEX_XYZ") vkind = B200_VERTEX_XYZ;
+    else if (tag == "EDGE_SE2") ekind = B200_EDGE_SE2;
+    else if (tag == "EDGE_SE3:QUAT") ekind = B200_EDGE_SE3;
+    else if (tag == "EDGE_PROJECT_P2MC") ekind = B200_EDGE_P2MC;
+    else { lp.skip_line(); continue; }  // unknown tags are skipped (optimizable_graph.cpp:417-423)
+    nums.clear();
+    int ids[2] = {0, 0};
+    const int nid = vkind >= 0 ? 1 : 2;
+    bool ok = true;
+    for (int i = 0; i < nid; ++i) {
+      if (!lp.next_token(tb, te)) { ok = false; break; }
+      ids[i] = (int)strtol(tb, nullptr, 10);
+    }
+    while (ok && lp.next_token(tb, te)) nums.push_back(strtod(tb, nullptr));
+    lp.skip_line();
+    if (!ok) continue;
+    if (vkind >= 0) {
+      int v = add_vertex(g, vkind, ids[0]);
+      if (v >= 0) vertex_read(g->vertices[v], nums.data(), (int)nums.size());
+    } else {
+      int rc = add_edge(g, ekind, ids[0], ids[1], nums.data(), (int)nums.size());
+      if (rc == B200_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  return B200_OK;
+}
+
+int b200_graph_setup_cli(b200_graph* g, int requires_marginalize) {
+  if (!g || g->vertices.empty()) return -2;
+  int maxDim = 0, minDim = 1 << 30;
+  for (const HVertex& v : g->vertices) { maxDim = std::max(maxDim, vdim(v.kind)); minDim = std::min(minDim, vdim(v.kind)); }
+  // gaugeFreedom(): false as soon as a max-dimension vertex is fixed (no unary priors among the configured edges)
+  bool gaugeFreedom = true;
+  for (const HVertex& v : g->vertices) if (vdim(v.kind) == maxDim && v.fixed) { gaugeFreedom = false; break; }
+  int ret = -1;
+  if (gaugeFreedom) {
+    // findGauge(): first max-dimension vertex in VertexIDMap iteration order
+    for (auto it = g->idmap.begin(); it != g->idmap.end(); ++it) {
+      HVertex& v = g->vertices[it->second];
+      if (vdim(v.kind) == maxDim) { v.fixed = true; ret = v.id; break; }
+    }
+  }
+  if (requires_marginalize && maxDim != minDim)
+    for (HVertex& v : g->vertices) if (vdim(v.kind) != maxDim) v.marginalized = true;
+  return ret;
+}
+
+int b200_graph_initialize(b200_graph* g) {
+  if (!g) return B200_ERR_INVALID;
+  if (g->edges.empty()) { g->err = "attempt to initialize an empty graph"; return B200_ERR_INVALID; }
+  for (HVertex& v : g->vertices) { v.active = false; v.hidx = -1; v.slot = -1; }
+  g->active_edges.clear();
+  for (size_t k = 0; k < g->edges.size(); ++k) {
+    HEdge& e = g->edges[k];
+    e.active = !(g->vertices[e.v0].fixed && g->vertices[e.v1].fixed);
+    if (e.active) { g->active_edges.push_back((int)k); g->vertices[e.v0].active = true; g->vertices[e.v1].active = true; }
+  }
+  std::vector<int> act;
+  for (size_t i = 0; i < g->vertices.size(); ++i) if (g->vertices[i].active) act.push_back((int)i);
+  std::sort(act.begin(), act.end(), [&](int a, int b) { return g->vertices[a].id < g->vertices[b].id; });
+  if (act.empty()) { g->err = "no active vertices"; return B200_ERR_INVALID; }
+  int idx = 0;
+  for (int k = 0; k < 2; ++k)
+    for (int i : act) {
+      HVertex& v = g->vertices[i];
+      if (!v.fixed && (int)v.marginalized == k) v.hidx = idx++;
+    }
+  for (int k = 0; k < 4; ++k) g->kind_slots[k].clear();
+  for (int i : act) { HVertex& v = g->vertices[i]; v.slot = (int)g->kind_slots[v.kind].size(); g->kind_slots[v.kind].push_back(i); }
+  return B200_OK;
+}
+
+int b200_graph_counts(b200_graph* g, int32_t* vc, int32_t* ec) {
+  if (!g) return B200_ERR_INVALID;
+  if (vc) { for (int k = 0; k < 4; ++k) vc[k] = 0; for (const HVertex& v : g->vertices) vc[v.kind]++; }
+  if (ec) { for (int k = 0; k < 3; ++k) ec[k] = 0; for (const HEdge& e : g->edges) ec[e.kind]++; }
+  return B200_OK;
+}
+
+int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
+  if (!g || !ctx || num_shards < 1 || shard < 0 || shard >= num_shards) return B200_ERR_INVALID;
+  if (g->active_edges.empty()) { g->err = "call b200_graph_initialize first"; return B200_ERR_INVALID; }
+  const int ekind = g->edges[g->active_edges[0]].kind;
+  for (int k : g->active_edges) if (g->edges[k].kind != ekind) { g->err = "mixed edge types are not supported"; return B200_ERR_UNSUPPORTED; }
+  const bool ba = ekind == B200_EDGE_P2MC;
+  if (num_shards > 1 && !ba) { g->err = "only bundle adjustment shards (pose graphs stay single-GPU)"; return B200_ERR_UNSUPPORTED; }
+  // numPoses = #free non-marginalized vertices
+  int np = 0;
+  for (const HVertex& v : g->vertices) if (v.hidx >= 0 && !v.marginalized) ++np;
+  // ---- landmark sharding: contiguous landmark-index ranges balanced by edge count
+  std::vector<int> lm_shard;  // per XYZ slot
+  std::vector<int> local_slot, local_hidx;
+  if (ba) {
+    const std::vector<int>& ls = g->kind_slots[B200_VERTEX_XYZ];
+    lm_shard.assign(ls.size(), 0);
+    if (num_shards > 1) {
+      std::vector<long long> deg(ls.size(), 0);
+      for (int k : g->active_edges) deg[g->vertices[g->edges[k].v0].slot]++;
+      std::vector<int> order(ls.size());
+      for (size_t i = 0; i < ls.size(); ++i) order[i] = (int)i;
+      std::sort(order.begin(), order.end(), [&](int a, int b) {
+        int ha = g->vertices[ls[a]].hidx, hb = g->vertices[ls[b]].hidx;
+        if ((ha < 0) != (hb < 0)) return hb < 0;  // free landmarks first, by hessian index
+        return ha != hb ? ha < hb : a < b;
+      });
+      long long total = 0;
+      for (long long d : deg) total += d;
+      long long acc = 0;
+      for (int i : order) {
+        int sidx = (int)std::min<long long>(num_shards - 1, acc * num_shards / std::max<long long>(total, 1));
+        if (g->vertices[ls[i]].hidx < 0) sidx = 0;
+        lm_shard[i] = sidx;
+        acc += deg[i];
+      }
+    }
+  }
+  for (int kind = 0; kind < 4; ++kind) {
+    const std::vector<int>& sl = g->kind_slots[kind];
+    if (sl.empty()) continue;
+    const int ne = vest(kind);
+    std::vector<double> est;
+    std::vector<int32_t> hidx;
+    std::vector<uint8_t> marg;
+    if (kind == B200_VERTEX_XYZ && ba) {
+      local_slot.assign(sl.size(), -1);
+      int nloc = 0, nfree = 0;
+      for (size_t i = 0; i < sl.size(); ++i) {
+        if (lm_shard[i] != shard) continue;
+        const HVertex& v = g->vertices[sl[i]];
+        local_slot[i] = nloc++;
+        est.insert(est.end(), v.est, v.est + ne);
+        hidx.push_back(v.hidx >= 0 ? np + nfree++ : -1);
+        marg.push_back(v.marginalized ? 1 : 0);
+      }
+      if (num_shards == 1)  // keep g2o's own numbering when nothing is sharded
+        for (size_t i = 0, q = 0; i < sl.size(); ++i) if (lm_shard[i] == shard) hidx[q++] = g->vertices[sl[i]].hidx;
+    } else {
+      for (int i : sl) {
+        const HVertex& v = g->vertices[i];
+        est.insert(est.end(), v.est, v.est + ne);
+        hidx.push_back(v.hidx);
+        marg.push_back(v.marginalized ? 1 : 0);
+      }
+    }
+    int rc = b200_set_vertices(ctx, kind, (int)hidx.size(), est.data(), hidx.data(), marg.data());
+    if (rc) { g->err = b200_last_error(ctx); return rc; }
+  }
+  {
+    const int D = edim(ekind), nm = emeas(ekind);
+    std::vector<int32_t> vi, vj;
+    std::vector<double> meas, info;
+    std::vector<int32_t> xr, xc;  // Hschur blocks contributed by other shards
+    for (int k : g->active_edges) {
+      const HEdge& e = g->edges[k];
+      int s0 = g->vertices[e.v0].slot, s1 = g->vertices[e.v1].slot;
+      if (ba) {
+        if (lm_shard[s0] != shard) continue;
+        s0 = local_slot[s0];
+      }
+      vi.push_back(s0); vj.push_back(s1);
+      meas.insert(meas.end(), e.meas, e.meas + nm);
+      info.insert(info.end(), e.info, e.info + D * D);
+    }
+    if (ba && num_shards > 1) {
+      // per foreign landmark: the camera pairs it couples
+      std::vector<std::vector<int>> cams(g->kind_slots[B200_VERTEX_XYZ].size());
+      for (int k : g->active_edges) {
+        const HEdge& e = g->edges[k];
+        const HVertex& p = g->vertices[e.v0];
+        const HVertex& c = g->vertices[e.v1];
+        if (lm_shard[p.slot] == shard || p.hidx < 0 || c.hidx < 0) continue;
+        cams[p.slot].push_back(c.hidx);
+      }
+      std::vector<long long> keys;
+      for (auto& cl : cams) {
+        std::sort(cl.begin(), cl.end());
+        cl.erase(std::unique(cl.begin(), cl.end()), cl.end());
+        for (size_t a = 0; a < cl.size(); ++a) for (size_t b = a; b < cl.size(); ++b) keys.push_back(((long long)cl[b] << 32) | cl[a]);
+        if (keys.size() > ((size_t)1 << 24)) { std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end()); }
+      }
+      std::sort(keys.begin(), keys.end());
+      keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+      for (long long kk : keys) { xc.push_back((int)(kk >> 32)); xr.push_back((int)(kk & 0xffffffff)); }
+      int rc = b200_add_schur_pattern(ctx, (int)xr.size(), xr.data(), xc.data());
+      if (rc) return rc;
+    }
+    int rc = b200_set_edges(ctx, ekind, (int)vi.size(), vi.data(), vj.data(), meas.data(), info.data());
+    if (rc) { g->err = b200_last_error(ctx); return rc; }
+  }
+  return B200_OK;
+}
+
+int b200_graph_download(b200_graph* g, b200_ctx* ctx) {
+  if (!g || !ctx) return B200_ERR_INVALID;
+  for (int kind = 0; kind < 4; ++kind) {
+    const std::vector<int>& sl = g->kind_slots[kind];
+    if (sl.empty()) continue;
+    const int ne = vest(kind);
+    std::vector<double> est(sl.size() * ne);
+    int rc = b200_get_estimates(ctx, kind, est.data());
+    if (rc) { g->err = b200_last_error(ctx); return rc; }
+    for (size_t i = 0; i < sl.size(); ++i) memcpy(g->vertices[sl[i]].est, &est[i * ne], ne * sizeof(double));
+  }
+  return B200_OK;
+}
+
+int b200_graph_get_estimate(b200_graph* g, int id, double* out) {
+  if (!g || !out) return B200_ERR_INVALID;
+  int v = g->find(id);
+  if (v < 0) return B200_ERR_INVALID;
+  const int ne = vest(g->vertices[v].kind);
+  memcpy(out, g->vertices[v].est, ne * sizeof(double));
+  return ne;
+}
+
+int b200_graph_get_vertex_info(b200_graph* g, int id, int32_t* out /* kind, hidx, fixed, marginalized */) {
+  if (!g || !out) return B200_ERR_INVALID;
+  int v = g->find(id);
+  if (v < 0) return B200_ERR_INVALID;
+  const HVertex& x = g->vertices[v];
+  out[0] = x.kind; out[1] = x.hidx; out[2] = x.fixed; out[3] = x.marginalized;
+  return B200_OK;
+}
+
+int b200_graph_save(b200_graph* g, const char* path) {
+  if (!g || !path) return B200_ERR_INVALID;
+  FILE* f = fopen(path, "w");
+  if (!f) { g->err = std::string("cannot write ") + path; return B200_ERR_INVALID; }
+  std::vector<int> order(g->vertices.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return g->vertices[a].id < g->vertices[b].id; });
+  static const char* vtag[4] = {"VERTEX_SE2", "VERTEX_SE3:QUAT", "VERTEX_CAM", "VERTEX_XYZ"};
+  static const char* etag[3] = {"EDGE_SE2", "EDGE_SE3:QUAT", "EDGE_PROJECT_P2MC"};
+  for (int i : order) {
+    const HVertex& v = g->vertices[i];
+    fprintf(f, "%s %d", vtag[v.kind], v.id);
+    if (v.kind == B200_VERTEX_SE2 || v.kind == B200_VERTEX_XYZ) fprintf(f, " %.17g %.17g %.17g", v.est[0], v.est[1], v.est[2]);
+    else if (v.kind == B200_VERTEX_SE3) {
+      double q[4];
+      R_to_quat(v.est, q);
+      quat_normalize(q);
+      fprintf(f, " %.17g %.17g %.17g %.17g %.17g %.17g %.17g", v.est[9], v.est[10], v.est[11], q[0], q[1], q[2], q[3]);
+    } else {
+      for (int k = 0; k < 12; ++k) fprintf(f, " %.17g", v.est[k]);
+    }
+    fprintf(f, "\n");
+    if (v.fixed) fprintf(f, "FIX %d\n", v.id);
+  }
+  for (const HEdge& e : g->edges) {
+    fprintf(f, "%s %d %d", etag[e.kind], g->vertices[e.v0].id, g->vertices[e.v1].id);
+    const int D = edim(e.kind);
+    if (e.kind == B200_EDGE_SE2) fprintf(f, " %.17g %.17g %.17g", e.meas[0], e.meas[1], e.meas[2]);
+    else if (e.kind == B200_EDGE_SE3) {
+      double q[4];
+      R_to_quat(e.meas, q);
+      quat_normalize(q);
+      fprintf(f, " %.17g %.17g %.17g %.17g %.17g %.17g %.17g", e.meas[9], e.meas[10], e.meas[11], q[0], q[1], q[2], q[3]);
+    } else fprintf(f, " %.17g %.17g", e.meas[0], e.meas[1]);
+    if (e.kind != B200_EDGE_P2MC)
+      for (int i = 0; i < D; ++i) for (int j = i; j < D; ++j) fprintf(f, " %.17g", e.info[i + D * j]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return B200_OK;
+}
+
+}  // extern "C"

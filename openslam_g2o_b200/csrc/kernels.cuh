@@ -1,0 +1,598 @@
+// kernels.cuh - sm_100a kernels of the per-iteration hot path except the Cholesky (chol.cu):
+//   errors + chi2            (SparseOptimizer::computeActiveErrors/activeRobustChi2, core/sparse_optimizer.cpp:61-114)
+//   linearize + accumulate   (BlockSolver::buildSystem, core/block_solver.hpp:501-560;
+//                             BaseBinaryEdge::constructQuadraticForm, core/base_binary_edge.hpp:54-120)
+//   Schur complement         (BlockSolver::solve, core/block_solver.hpp:367-439)
+//   landmark back-substitution (core/block_solver.hpp:461-481)
+//   oplus update             (SparseOptimizer::update, core/sparse_optimizer.cpp:421-434)
+//   LM scalars               (computeLambdaInit / computeScale, core/optimization_algorithm_levenberg.cpp:149-172)
+//
+// Accumulation is by ordered gather (no atomics): every Hessian block / b segment is written by one
+// thread group that sums its contributions in ascending edge order, so results are run-to-run
+// bit-identical and follow the reference's summation order.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "geometry.cuh"
+
+namespace g2o_b200 {
+namespace k {
+
+using namespace geo;
+
+// ------------------------------------------------------------------ deterministic reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block sum for blockDim.x <= 1024, result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) r += sh[i];
+  }
+  return r;
+}
+// out[0] = sum(partials[0..n)) in a fixed order; single block
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// ------------------------------------------------------------------ pose graphs (SE2 / SE3)
+// edge arrays are SoA: meas[f*E + e], info[f*E + e] (upper triangle, row-major order)
+template <int D>
+__device__ __forceinline__ void load_info(const double* __restrict__ info, int E, int e, double* W /*DxD full*/) {
+  int f = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      const double v = info[(long long)f * E + e];
+      W[i + D * j] = v;
+      W[j + D * i] = v;
+      ++f;
+    }
+}
+template <int D>
+__device__ __forceinline__ double chi2_of(const double* W, const double* e) {
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) t += W[r + D * c] * e[c];
+    s += e[r] * t;
+  }
+  return s;
+}
+
+__device__ __forceinline__ SE2 load_se2(const double* __restrict__ est, int v) {
+  const double4 q = *reinterpret_cast<const double4*>(est + 4ll * v);
+  return SE2{q.x, q.y, q.z};
+}
+__device__ __forceinline__ Iso load_iso(const double* __restrict__ est, int v) {
+  Iso X;
+  const double2* p = reinterpret_cast<const double2*>(est + 12ll * v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { double2 a = p[i]; X.R[2 * i] = a.x; X.R[2 * i + 1] = a.y; }
+  { double2 a = p[4]; X.R[8] = a.x; X.t[0] = a.y; }
+  { double2 a = p[5]; X.t[1] = a.x; X.t[2] = a.y; }
+  return X;
+}
+__device__ __forceinline__ Iso load_iso_soa(const double* __restrict__ meas, int E, int e) {
+  Iso Z;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Z.R[i] = meas[(long long)i * E + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) Z.t[i] = meas[(long long)(9 + i) * E + e];
+  return Z;
+}
+
+// KIND 0 = SE2 (D=3), 1 = SE3 (D=6)
+template <int KIND>
+__global__ void pg_chi2_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v1,
+                               const double* __restrict__ est, const double* __restrict__ meas,
+                               const double* __restrict__ info, double* __restrict__ partials) {
+  constexpr int D = KIND == 0 ? 3 : 6;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0;
+  if (e < E) {
+    double err[D], W[D * D];
+    if (KIND == 0) {
+      const SE2 zi{meas[e], meas[(long long)E + e], meas[2ll * E + e]};
+      se2_error(load_se2(est, v0[e]), load_se2(est, v1[e]), zi, err);
+    } else {
+      se3_error(load_iso(est, v0[e]), load_iso(est, v1[e]), load_iso_soa(meas, E, e), err);
+    }
+    load_info<D>(info, E, e, W);
+    chi = chi2_of<D>(W, err);
+  }
+  chi = block_sum(chi);
+  if (threadIdx.x == 0) partials[blockIdx.x] = chi;
+}
+
+// per edge staging record: [Hii D*D | Hjj D*D | Hij D*D (destination orientation) | bi D | bj D]
+template <int KIND>
+__global__ void __launch_bounds__(128)
+pg_linearize_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v1, const double* __restrict__ est,
+                    const double* __restrict__ meas, const double* __restrict__ info,
+                    const unsigned char* __restrict__ transposed, double* __restrict__ stage) {
+  constexpr int D = KIND == 0 ? 3 : 6;
+  constexpr int STRIDE = 3 * D * D + 2 * D;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double A[D * D], B[D * D], err[D];
+  if (KIND == 0) {
+    const SE2 zi{meas[e], meas[(long long)E + e], meas[2ll * E + e]};
+    const SE2 xi = load_se2(est, v0[e]), xj = load_se2(est, v1[e]);
+    se2_error(xi, xj, zi, err);
+    se2_jacobians(xi, xj, zi, A, B);
+  } else {
+    se3_jacobians(load_iso(est, v0[e]), load_iso(est, v1[e]), load_iso_soa(meas, E, e), A, B, err);
+  }
+  double W[D * D];
+  load_info<D>(info, E, e, W);
+  double omega_r[D];
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) s += W[r + D * c] * err[c];
+    omega_r[r] = -s;
+  }
+  double* out = stage + (long long)e * STRIDE;
+  double T[D * D];  // AtO, then BtO
+  mtm<D, D, D>(A, W, T);
+  {
+    double H[D * D];
+    mm<D, D, D>(T, A, H);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) out[i] = H[i];
+    mm<D, D, D>(T, B, H);  // AtO * B = block (i,j)
+    if (transposed[e]) {
+#pragma unroll
+      for (int c = 0; c < D; ++c)
+#pragma unroll
+        for (int r = 0; r < D; ++r) out[2 * D * D + c + D * r] = H[r + D * c];
+    } else {
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) out[2 * D * D + i] = H[i];
+    }
+  }
+  mtm<D, D, D>(B, W, T);
+  {
+    double H[D * D];
+    mm<D, D, D>(T, B, H);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) out[D * D + i] = H[i];
+  }
+  double bi[D], bj[D];
+  mtm<D, D, 1>(A, omega_r, bi);
+  mtm<D, D, 1>(B, omega_r, bj);
+#pragma unroll
+  for (int i = 0; i < D; ++i) { out[3 * D * D + i] = bi[i]; out[3 * D * D + D + i] = bj[i]; }
+}
+
+// ordered gather: dst[seg*LEN + k] = sum over sources s of stage[(id/5)*STRIDE + field_off[id%5] + k]
+// source ids of a segment are ascending in edge order.  LEN = D*D (Hessian blocks) or D (b).
+template <int D, int LEN>
+__global__ void gather_segments_kernel(int nseg, const int* __restrict__ src_ptr, const int* __restrict__ src_id,
+                                       const double* __restrict__ stage, double* __restrict__ dst) {
+  constexpr int STRIDE = 3 * D * D + 2 * D;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nseg * LEN) return;
+  const int seg = (int)(idx / LEN), kk = (int)(idx - (long long)seg * LEN);
+  double s = 0.0;
+  for (int p = src_ptr[seg]; p < src_ptr[seg + 1]; ++p) {
+    const int id = src_id[p];
+    const int e = id / 5, f = id - e * 5;
+    const int off = f < 3 ? f * D * D : 3 * D * D + (f - 3) * D;
+    s += stage[(long long)e * STRIDE + off + kk];
+  }
+  dst[idx] = s;
+}
+
+// ------------------------------------------------------------------ bundle adjustment (CAM + XYZ, P2MC)
+__global__ void cam_derive_kernel(int n, const double* __restrict__ est, double* __restrict__ der) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double e[12], d[16];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) e[k] = est[12ll * i + k];
+  cam_derive(e, d);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) der[16ll * i + k] = d[k];
+}
+
+__device__ __forceinline__ void load_der(const double* __restrict__ der, int c, double* d) {
+  const double2* p = reinterpret_cast<const double2*>(der + 16ll * c);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { double2 a = __ldg(p + i); d[2 * i] = a.x; d[2 * i + 1] = a.y; }
+}
+
+__global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* __restrict__ e_cam,
+                               const double* __restrict__ pt_est, const double* __restrict__ cam_der,
+                               const double* __restrict__ meas, const double* __restrict__ info,
+                               double* __restrict__ partials) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0;
+  if (e < E) {
+    double der[16];
+    load_der(cam_der, e_cam[e], der);
+    const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * e_pt[e]);
+    const double X[3] = {X4.x, X4.y, X4.z};
+    const double z[2] = {meas[e], meas[(long long)E + e]};
+    double err[2];
+    p2mc_error(der, X, z, err);
+    const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    chi = err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]);
+  }
+  chi = block_sum(chi);
+  if (threadIdx.x == 0) partials[blockIdx.x] = chi;
+}
+
+// one thread per landmark: Hll, b_l and one Hpl block per observation (edges of a landmark are contiguous)
+__global__ void __launch_bounds__(128)
+ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ lm_vertex,
+                           const int* __restrict__ e_cam, const int* __restrict__ e_hpl,
+                           const unsigned char* __restrict__ e_first, const double* __restrict__ pt_est,
+                           const double* __restrict__ cam_est, const double* __restrict__ cam_der,
+                           const double* __restrict__ meas, const double* __restrict__ info, int E,
+                           double* __restrict__ Hll, double* __restrict__ Hpl, double* __restrict__ b_l) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nl) return;
+  const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * lm_vertex[l]);
+  const double X[3] = {X4.x, X4.y, X4.z};
+  double H[9], bl[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) H[i] = 0.0;
+  bl[0] = bl[1] = bl[2] = 0.0;
+  for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+    const int c = e_cam[e];
+    double der[16];
+    load_der(cam_der, c, der);
+    const double ct[3] = {cam_est[12ll * c], cam_est[12ll * c + 1], cam_est[12ll * c + 2]};
+    double Jp[6], Jc[12], err[2];
+    p2mc_jacobians(der, ct, X, Jp, Jc);
+    const double z[2] = {meas[e], meas[(long long)E + e]};
+    p2mc_error(der, X, z, err);
+    const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    // JpW = Jp^T W (3x2), omega_r = -W err
+    double JpW[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      JpW[k] = Jp[2 * k] * w0 + Jp[2 * k + 1] * w1;
+      JpW[k + 3] = Jp[2 * k] * w1 + Jp[2 * k + 1] * w2;
+    }
+    const double or0 = -(w0 * err[0] + w1 * err[1]), or1 = -(w1 * err[0] + w2 * err[1]);
+#pragma unroll
+    for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) H[r + 3 * c2] += JpW[r] * Jp[2 * c2] + JpW[r + 3] * Jp[2 * c2 + 1];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) bl[r] += Jp[2 * r] * or0 + Jp[2 * r + 1] * or1;
+    const int slot = e_hpl[e];
+    if (slot >= 0) {  // Hpl(cam, l) (6x3) += Jc^T W Jp   (the transposed write of base_binary_edge.hpp:81-82)
+      double* dst = Hpl + 18ll * slot;
+      const bool first = e_first[e] != 0;
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double v = Jc[2 * r] * JpW[c2] + Jc[2 * r + 1] * JpW[c2 + 3];
+          dst[r + 6 * c2] = first ? v : dst[r + 6 * c2] + v;
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Hll[9ll * l + i] = H[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) b_l[3ll * l + i] = bl[i];
+}
+
+// one CTA per free camera: Hpp(i,i) and b_i as an ordered tree-sum over the camera's observations
+__global__ void __launch_bounds__(128)
+ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict__ cam_eidx,
+                         const int* __restrict__ pose_vertex, const int* __restrict__ e_pt,
+                         const double* __restrict__ pt_est, const double* __restrict__ cam_est,
+                         const double* __restrict__ cam_der, const double* __restrict__ meas,
+                         const double* __restrict__ info, int E, const int* __restrict__ hpp_diag_block,
+                         double* __restrict__ Hpp, double* __restrict__ b_p) {
+  const int i = blockIdx.x;
+  const int c = pose_vertex[i];
+  double der[16];
+  load_der(cam_der, c, der);
+  const double ct[3] = {cam_est[12ll * c], cam_est[12ll * c + 1], cam_est[12ll * c + 2]};
+  double acc[27];  // 21 upper-triangular entries of Jc^T W Jc (column-wise) + 6 of b
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int p = cam_eptr[i] + threadIdx.x; p < cam_eptr[i + 1]; p += blockDim.x) {
+    const int e = cam_eidx[p];
+    const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * e_pt[e]);
+    const double X[3] = {X4.x, X4.y, X4.z};
+    double Jp[6], Jc[12], err[2];
+    p2mc_jacobians(der, ct, X, Jp, Jc);
+    const double z[2] = {meas[e], meas[(long long)E + e]};
+    p2mc_error(der, X, z, err);
+    const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    double JW[12];  // Jc^T W : 6x2
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      JW[k] = Jc[2 * k] * w0 + Jc[2 * k + 1] * w1;
+      JW[k + 6] = Jc[2 * k] * w1 + Jc[2 * k + 1] * w2;
+    }
+    const double or0 = -(w0 * err[0] + w1 * err[1]), or1 = -(w1 * err[0] + w2 * err[1]);
+    int q = 0;
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc)
+#pragma unroll
+      for (int r = 0; r <= cc; ++r) acc[q++] += JW[r] * Jc[2 * cc] + JW[r + 6] * Jc[2 * cc + 1];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) acc[21 + r] += Jc[2 * r] * or0 + Jc[2 * r + 1] * or1;
+  }
+  __shared__ double sh[4][27];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) sh[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    const int nw = blockDim.x >> 5;
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += sh[w][threadIdx.x];
+    sh[0][threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    const int r = threadIdx.x % 6, cc = threadIdx.x / 6;
+    const int lo = r < cc ? r : cc, hi = r < cc ? cc : r;
+    Hpp[36ll * hpp_diag_block[i] + threadIdx.x] = sh[0][hi * (hi + 1) / 2 + lo];
+  } else if (threadIdx.x < 42) {
+    b_p[6ll * i + (threadIdx.x - 36)] = sh[0][21 + threadIdx.x - 36];
+  }
+}
+
+// ------------------------------------------------------------------ Schur complement
+// S1: per landmark Dinv = (Hll + lambda I)^-1, db = Dinv b_l           (block_solver.hpp:381-395)
+__global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__ Hll, const double* __restrict__ b_l,
+                                              const double* __restrict__ lambda, double* __restrict__ Dinv,
+                                              double* __restrict__ db) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nl) return;
+  const double lam = *lambda;
+  double D[9], Di[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) D[i] = Hll[9ll * l + i];
+  D[0] += lam; D[4] += lam; D[8] += lam;
+  inverse3(D, Di);
+  const double b0 = b_l[3ll * l], b1 = b_l[3ll * l + 1], b2 = b_l[3ll * l + 2];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Dinv[9ll * l + i] = Di[i];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) db[3ll * l + r] = Di[r] * b0 + Di[r + 3] * b1 + Di[r + 6] * b2;
+}
+
+// S2: one warp per block (i1,i2) of Hschur:
+//   Hschur(i1,i2) = hpp_scale*(Hpp(i1,i2) + [i1==i2] lambda I) - sum_l (Hpl(i1,l) Dinv_l) Hpl(i2,l)^T
+//   bschur_i1     = hpp_scale*b_i1 - sum_l Hpl(i1,l) db_l        (diagonal targets only)
+// contributions of a target are stored in ascending landmark order (block_solver.hpp:397-439).
+// hpp_scale is 1 on a single GPU; with landmark sharding only rank 0 adds the (already reduced) Hpp term.
+__global__ void __launch_bounds__(128)
+schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __restrict__ t_col,
+                    const int* __restrict__ t_hpp, const int* __restrict__ sc_ptr, const int* __restrict__ sc_lm,
+                    const int* __restrict__ sc_a, const int* __restrict__ sc_b, const double* __restrict__ Hpp,
+                    const double* __restrict__ Hpl, const double* __restrict__ Dinv, const double* __restrict__ db,
+                    const double* __restrict__ b_p, const double* __restrict__ lambda, double hpp_scale,
+                    double* __restrict__ Hschur, double* __restrict__ bschur) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= ntarget) return;
+  const int i1 = t_row[t], i2 = t_col[t];
+  const bool diag = i1 == i2;
+  double acc[36], cacc[6];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
+  for (int c = sc_ptr[t] + lane; c < sc_ptr[t + 1]; c += 32) {
+    const int l = sc_lm[c];
+    const double* Ba = Hpl + 18ll * sc_a[c];
+    const double* Bb = Hpl + 18ll * sc_b[c];
+    double Di[9], A[18], T[18];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Di[k] = Dinv[9ll * l + k];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) A[k] = Ba[k];
+    mm<6, 3, 3>(A, Di, T);  // BDinv
+    if (diag) {
+      const double d0 = db[3ll * l], d1 = db[3ll * l + 1], d2 = db[3ll * l + 2];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) cacc[r] += A[r] * d0 + A[r + 6] * d1 + A[r + 12] * d2;
+    }
+#pragma unroll
+    for (int k = 0; k < 18; ++k) A[k] = Bb[k];
+#pragma unroll
+    for (int c2 = 0; c2 < 6; ++c2)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[r + 6 * c2] += T[r] * A[c2] + T[r + 6] * A[c2 + 6] + T[r + 12] * A[c2 + 12];
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
+  const int hb = t_hpp[t];
+  const double lam = diag ? *lambda : 0.0;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) {
+    if (lane == (k & 31)) {
+      double base = 0.0;
+      if (hb >= 0 && hpp_scale != 0.0) base = hpp_scale * (Hpp[36ll * hb + k] + ((k % 7 == 0) ? lam : 0.0));
+      Hschur[36ll * t + k] = base - acc[k];
+    }
+  }
+  if (diag) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cacc[k] = warp_sum(cacc[k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (lane == k) bschur[6ll * i1 + k] = hpp_scale * b_p[6ll * i1 + k] - cacc[k];
+  }
+}
+
+// landmark back-substitution: x_l = Dinv (b_l - sum_e Hpl(e)^T x_cam(e))     (block_solver.hpp:461-481)
+__global__ void ba_backsub_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ e_hpl,
+                                  const int* __restrict__ e_pose, const double* __restrict__ Hpl,
+                                  const double* __restrict__ Dinv, const double* __restrict__ b_l,
+                                  const double* __restrict__ x_p, double* __restrict__ x_l) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nl) return;
+  double c0 = b_l[3ll * l], c1 = b_l[3ll * l + 1], c2 = b_l[3ll * l + 2];
+  int prev = -1;
+  for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+    const int slot = e_hpl[e];
+    if (slot < 0 || slot == prev) continue;  // duplicate observations share one block
+    prev = slot;
+    const double* B = Hpl + 18ll * slot;
+    const double* xp = x_p + 6ll * e_pose[e];
+    double t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const double xv = -xp[r];
+      t0 += B[r] * xv; t1 += B[r + 6] * xv; t2 += B[r + 12] * xv;
+    }
+    c0 += t0; c1 += t1; c2 += t2;
+  }
+  const double* Di = Dinv + 9ll * l;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) x_l[3ll * l + r] = Di[r] * c0 + Di[r + 3] * c1 + Di[r + 6] * c2;
+}
+
+// ------------------------------------------------------------------ oplus updates
+// hidx[v] = hessian index (-1 fixed); x is indexed by colInHessian = hidx*dim (poses) / sizePoses + ... (landmarks)
+__global__ void oplus_se2_kernel(int n, const int* __restrict__ hidx, const double* __restrict__ x, double* __restrict__ est) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int h = hidx[v];
+  if (h < 0) return;
+  double e[3] = {est[4ll * v], est[4ll * v + 1], est[4ll * v + 2]};
+  se2_oplus(e, x + 3ll * h);
+  est[4ll * v] = e[0]; est[4ll * v + 1] = e[1]; est[4ll * v + 2] = e[2];
+}
+__global__ void oplus_se3_kernel(int n, const int* __restrict__ hidx, const double* __restrict__ x, double* __restrict__ est,
+                                 int orthogonalize) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int h = hidx[v];
+  if (h < 0) return;
+  double e[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) e[k] = est[12ll * v + k];
+  se3_oplus(e, x + 6ll * h, orthogonalize != 0);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) est[12ll * v + k] = e[k];
+}
+__global__ void oplus_cam_kernel(int n, const int* __restrict__ hidx, const double* __restrict__ x, double* __restrict__ est,
+                                 double* __restrict__ der) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int h = hidx[v];
+  if (h < 0) return;
+  double e[12], d[16];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) e[k] = est[12ll * v + k];
+  cam_oplus(e, x + 6ll * h);
+  cam_derive(e, d);
+#pragma unroll
+  for (int k = 3; k < 7; ++k) est[12ll * v + k] = e[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) est[12ll * v + k] = e[k];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) der[16ll * v + k] = d[k];
+}
+// lidx[v] = landmark index (-1 fixed); x_l = x + sizePoses
+__global__ void oplus_xyz_kernel(int n, const int* __restrict__ lidx, const double* __restrict__ x_l, double* __restrict__ est) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int l = lidx[v];
+  if (l < 0) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) est[4ll * v + k] += x_l[3ll * l + k];
+}
+
+// ------------------------------------------------------------------ LM scalars
+// partial sums of x_j (lambda x_j + b_j)        (optimization_algorithm_levenberg.cpp:165-172)
+__global__ void lm_scale_kernel(int n, const double* __restrict__ x, const double* __restrict__ b,
+                                const double* __restrict__ lambda, double* __restrict__ partials) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (j < n) v = x[j] * (*lambda * x[j] + b[j]);
+  v = block_sum(v);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+// max |H_jj| over a set of diagonal blocks     (optimization_algorithm_levenberg.cpp:149-163)
+template <int D>
+__global__ void max_diag_kernel(int nblocks, const int* __restrict__ block_index, const double* __restrict__ H,
+                                double* __restrict__ partials) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (idx < nblocks * D) {
+    const int k = idx / D, r = idx - k * D;
+    const long long blk = block_index ? block_index[k] : k;
+    v = fabs(H[blk * D * D + r + D * r]);
+  }
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) m = fmax(m, sh[i]);
+    partials[blockIdx.x] = m;
+  }
+}
+__global__ void reduce_max_kernel(const double* __restrict__ partials, int n, double scale, double* __restrict__ out,
+                                  int accumulate) {
+  __shared__ double sh[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, partials[i]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  m = warp_max(m);
+  if (lane == 0) sh[wid] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) r = fmax(r, sh[i]);
+    r *= scale;
+    out[0] = accumulate ? fmax(out[0], r) : r;
+  }
+}
+// gather the diagonal entries of the indexed vertices into a dense vector (host mirror for v->hessian(j,j))
+template <int D>
+__global__ void extract_diag_kernel(int nblocks, const int* __restrict__ block_index, const double* __restrict__ H,
+                                    double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nblocks * D) return;
+  const int k = idx / D, r = idx - k * D;
+  const long long blk = block_index ? block_index[k] : k;
+  out[idx] = H[blk * D * D + r + D * r];
+}
+
+}  // namespace k
+}  // namespace g2o_b200

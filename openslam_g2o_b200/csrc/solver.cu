@@ -1,0 +1,1001 @@
+// solver.cu - implementation of the solver context (see solver.h) and of the Level-2 / Level-3 C-ABI.
+#include "solver.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "kernels.cuh"
+
+using namespace g2o_b200;
+
+namespace {
+
+double wall() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int vdim(int kind) { return kind == B200_VERTEX_SE2 ? 3 : kind == B200_VERTEX_XYZ ? 3 : 6; }
+int vest(int kind) { return kind == B200_VERTEX_SE2 ? 3 : kind == B200_VERTEX_XYZ ? 3 : 12; }   // doubles in the ABI layout
+int vstride(int kind) { return kind == B200_VERTEX_SE2 ? 4 : kind == B200_VERTEX_XYZ ? 4 : 12; }  // doubles on the device
+int edim(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
+int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
+
+// phases for the profiling counters
+enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE = 4, PH_UPDATE = 5, PH_BACKSUB = 6 };
+
+struct PhaseTimer {
+  b200_ctx* c;
+  int phase;
+  PhaseTimer(b200_ctx* ctx, int ph) : c(ctx), phase(ph) {
+    if (c->profiling) cudaEventRecord(c->ev[2 * ph], c->stream);
+  }
+  ~PhaseTimer() {
+    if (c->profiling) {
+      cudaEventRecord(c->ev[2 * phase + 1], c->stream);
+      cudaEventSynchronize(c->ev[2 * phase + 1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev[2 * phase], c->ev[2 * phase + 1]);
+      c->phase_seconds[phase] += ms * 1e-3;
+      c->phase_count[phase]++;
+    }
+  }
+};
+
+template <typename F>
+int guarded(b200_ctx* c, F&& f) {
+  if (!c) return B200_ERR_INVALID;
+  host_only_flag() = c->host_only;
+  try {
+    return f();
+  } catch (const CudaError& e) {
+    c->err = describe(e);
+    if (e.code == cudaErrorNoDevice || e.code == cudaErrorInsufficientDriver) return B200_ERR_NO_DEVICE;
+    return B200_ERR_CUDA;
+  } catch (const std::exception& e) {
+    c->err = e.what();
+    return B200_ERR_INVALID;
+  }
+}
+int fail(b200_ctx* c, int code, const std::string& msg) {
+  c->err = msg;
+  return code;
+}
+
+std::string g_create_error;
+
+// ---- host math for the one-time ingest (same formulas as geometry.cuh; runs where the reference's read() runs)
+void host_se2_inverse(const double* z, double* zi) {
+  geo::SE2 r = geo::se2_inv(geo::SE2{z[0], z[1], z[2]});
+  zi[0] = r.x; zi[1] = r.y; zi[2] = r.th;
+}
+void host_iso_inverse(const double* Z, double* Zi) {
+  geo::Iso a;
+  memcpy(a.R, Z, 9 * sizeof(double)); memcpy(a.t, Z + 9, 3 * sizeof(double));
+  geo::Iso r = geo::iso_inverse(a);
+  memcpy(Zi, r.R, 9 * sizeof(double)); memcpy(Zi + 9, r.t, 3 * sizeof(double));
+}
+
+void sync_scalars(b200_ctx* c) {
+  B200_CUDA(cudaMemcpyAsync(c->h_scalars, c->d_scalars.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaMemcpyAsync(c->h_status, c->chol.status_ptr(), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+}
+void set_device_lambda(b200_ctx* c, double lam) {
+  c->h_scalars[8] = lam;  // staging slot beyond the mirrored range
+  B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 3, c->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure
+// ------------------------------------------------------------------------------------------------
+int build_structure_impl(b200_ctx* c) {
+  double t0 = wall();
+  cudaStream_t s = c->stream;
+  // which graph family?
+  int pose_kind = -1;
+  for (int k = 0; k < 3; ++k)
+    if (c->vs[k].set && c->vs[k].n > 0) {
+      if (pose_kind >= 0) return fail(c, B200_ERR_UNSUPPORTED, "more than one pose vertex kind in one context");
+      pose_kind = k;
+    }
+  if (pose_kind < 0) return fail(c, B200_ERR_INVALID, "no pose vertices set");
+  const bool has_lm = c->vs[B200_VERTEX_XYZ].set && c->vs[B200_VERTEX_XYZ].n > 0;
+  if (c->edge_kind < 0 || c->nE <= 0) return fail(c, B200_ERR_INVALID, "no edges set");
+  const int want_pose = c->edge_kind == B200_EDGE_SE2 ? B200_VERTEX_SE2 : c->edge_kind == B200_EDGE_SE3 ? B200_VERTEX_SE3 : B200_VERTEX_CAM;
+  if (want_pose != pose_kind) return fail(c, B200_ERR_UNSUPPORTED, "edge kind does not match the pose vertex kind");
+  if ((c->edge_kind == B200_EDGE_P2MC) != has_lm) return fail(c, B200_ERR_UNSUPPORTED, "P2MC edges need XYZ vertices (and only they do)");
+  c->pose_kind = pose_kind;
+  c->schur = has_lm;
+  b200_ctx::VertexSet& PV = c->vs[pose_kind];
+  b200_ctx::VertexSet& LV = c->vs[B200_VERTEX_XYZ];
+  c->n_pose_v = PV.n;
+  c->n_lm_v = has_lm ? LV.n : 0;
+  c->pd = vdim(pose_kind);
+  c->ld = 3;
+  // index mapping as assigned by SparseOptimizer::buildIndexMapping: poses first, then landmarks
+  int np = 0, nl = 0;
+  for (int v = 0; v < PV.n; ++v) {
+    if (PV.hidx[v] >= 0) ++np;
+    if (!PV.marg.empty() && PV.marg[v]) return fail(c, B200_ERR_UNSUPPORTED, "marginalized pose vertices are not supported");
+  }
+  if (has_lm)
+    for (int v = 0; v < LV.n; ++v) {
+      if (LV.hidx[v] >= 0) {
+        ++nl;
+        if (LV.marg.empty() || !LV.marg[v]) return fail(c, B200_ERR_UNSUPPORTED, "XYZ vertices must be marginalized (Schur) for this solver");
+      }
+    }
+  if (np == 0) return fail(c, B200_ERR_INVALID, "0 vertices to optimize");
+  c->np = np; c->nl = nl;
+  c->sizeP = np * c->pd; c->sizeL = nl * c->ld;
+  c->pose_vertex.assign(np, -1);
+  for (int v = 0; v < PV.n; ++v) {
+    int h = PV.hidx[v];
+    if (h < 0) continue;
+    if (h >= np || c->pose_vertex[h] != -1) return fail(c, B200_ERR_INVALID, "pose hessian indices must be a permutation of [0,numPoses)");
+    c->pose_vertex[h] = v;
+  }
+  c->lm_vertex.assign(nl, -1);
+  std::vector<int> lm_lidx(c->n_lm_v, -1);
+  if (has_lm)
+    for (int v = 0; v < LV.n; ++v) {
+      int h = LV.hidx[v];
+      if (h < 0) continue;
+      int l = h - np;
+      if (l < 0 || l >= nl || c->lm_vertex[l] != -1) return fail(c, B200_ERR_INVALID, "landmark hessian indices must follow the poses contiguously");
+      c->lm_vertex[l] = v;
+      lm_lidx[v] = l;
+    }
+  const int E = c->nE;
+  for (int e = 0; e < E; ++e) {
+    const int nvi = has_lm ? LV.n : PV.n;
+    if (c->e_vi[e] < 0 || c->e_vi[e] >= nvi || c->e_vj[e] < 0 || c->e_vj[e] >= PV.n) return fail(c, B200_ERR_INVALID, "edge vertex index out of range");
+  }
+
+  // ---- vertex state on the device
+  {
+    const int st = vstride(pose_kind), ne = vest(pose_kind);
+    std::vector<double> buf((size_t)PV.n * st, 0.0);
+    for (int v = 0; v < PV.n; ++v) memcpy(&buf[(size_t)v * st], &PV.est[(size_t)v * ne], ne * sizeof(double));
+    c->d_pose_est.upload(buf, s);
+    c->d_pose_bak.alloc(buf.size());
+    c->d_pose_hidx.upload(PV.hidx, s);
+    c->d_pose_vertex.upload(c->pose_vertex, s);
+    if (pose_kind == B200_VERTEX_CAM) {
+      c->d_cam_der.alloc((size_t)PV.n * 16);
+      c->d_cam_der_bak.alloc((size_t)PV.n * 16);
+      if (!c->host_only) {
+        k::cam_derive_kernel<<<ceil_div(PV.n, 128), 128, 0, s>>>(PV.n, c->d_pose_est.p, c->d_cam_der.p);
+        c->lc.n++;
+      }
+    }
+    if (has_lm) {
+      std::vector<double> lb((size_t)LV.n * 4, 0.0);
+      for (int v = 0; v < LV.n; ++v) memcpy(&lb[(size_t)v * 4], &LV.est[(size_t)v * 3], 3 * sizeof(double));
+      c->d_lm_est.upload(lb, s);
+      c->d_lm_bak.alloc(lb.size());
+      c->d_lm_lidx.upload(lm_lidx, s);
+      c->d_lm_vertex.upload(c->lm_vertex, s);
+    }
+    if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
+  }
+  const int ntot = c->sizeP + c->sizeL;
+  c->d_b.alloc(ntot); c->d_x.alloc(ntot);
+  c->d_b.zero(s); c->d_x.zero(s);
+  c->d_diag.alloc(ntot);
+  c->d_scalars.alloc(16); c->d_scalars.zero(s);
+  c->d_partials.alloc((size_t)ceil_div(std::max(E, ntot), 256) + 64);
+
+  const int D = edim(c->edge_kind);
+  const int pd = c->pd;
+  std::vector<int> bp_colptr, bp_rowidx;  // pattern handed to the Cholesky
+
+  if (!has_lm) {
+    // =========================== pose graph ===========================
+    // Hpp pattern: diagonal blocks + (min,max) per edge with two free vertices (block_solver.hpp:204-232)
+    std::vector<long long> keys;
+    keys.reserve((size_t)np + E);
+    for (int i = 0; i < np; ++i) keys.push_back(((long long)i << 32) | i);
+    for (int e = 0; e < E; ++e) {
+      int hi = PV.hidx[c->e_vi[e]], hj = PV.hidx[c->e_vj[e]];
+      if (hi < 0 || hj < 0) continue;
+      if (hi == hj) return fail(c, B200_ERR_UNSUPPORTED, "self-loop edge");
+      int lo = std::min(hi, hj), hi2 = std::max(hi, hj);
+      keys.push_back(((long long)hi2 << 32) | lo);
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const int nblk = (int)keys.size();
+    c->n_hpp = nblk;
+    c->hpp_colptr.assign(np + 1, 0);
+    c->hpp_rowidx.resize(nblk);
+    for (int k2 = 0; k2 < nblk; ++k2) { c->hpp_colptr[(keys[k2] >> 32) + 1]++; c->hpp_rowidx[k2] = (int)(keys[k2] & 0xffffffff); }
+    for (int i = 0; i < np; ++i) c->hpp_colptr[i + 1] += c->hpp_colptr[i];
+    auto find_block = [&](int row, int col) {
+      long long key = ((long long)col << 32) | row;
+      return (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+    };
+    c->hpp_diag_block.resize(np);
+    for (int i = 0; i < np; ++i) c->hpp_diag_block[i] = find_block(i, i);
+    // per-edge flags and ordered gather lists
+    std::vector<unsigned char> transposed(E, 0);
+    std::vector<int> hcnt(nblk + 1, 0), bcnt(np + 1, 0);
+    std::vector<int> eb_ii(E, -1), eb_jj(E, -1), eb_ij(E, -1);
+    for (int e = 0; e < E; ++e) {
+      int hi = PV.hidx[c->e_vi[e]], hj = PV.hidx[c->e_vj[e]];
+      if (hi >= 0) { eb_ii[e] = c->hpp_diag_block[hi]; hcnt[eb_ii[e] + 1]++; bcnt[hi + 1]++; }
+      if (hj >= 0) { eb_jj[e] = c->hpp_diag_block[hj]; hcnt[eb_jj[e] + 1]++; bcnt[hj + 1]++; }
+      if (hi >= 0 && hj >= 0) {
+        transposed[e] = hi > hj;
+        eb_ij[e] = find_block(std::min(hi, hj), std::max(hi, hj));
+        hcnt[eb_ij[e] + 1]++;
+      }
+    }
+    for (int k2 = 0; k2 < nblk; ++k2) hcnt[k2 + 1] += hcnt[k2];
+    for (int i = 0; i < np; ++i) bcnt[i + 1] += bcnt[i];
+    std::vector<int> hsrc(hcnt[nblk]), bsrc(bcnt[np]);
+    {
+      std::vector<int> hf(hcnt.begin(), hcnt.end() - 1), bf(bcnt.begin(), bcnt.end() - 1);
+      for (int e = 0; e < E; ++e) {
+        int hi = PV.hidx[c->e_vi[e]], hj = PV.hidx[c->e_vj[e]];
+        if (eb_ii[e] >= 0) { hsrc[hf[eb_ii[e]]++] = e * 5 + 0; bsrc[bf[hi]++] = e * 5 + 3; }
+        if (eb_jj[e] >= 0) { hsrc[hf[eb_jj[e]]++] = e * 5 + 1; bsrc[bf[hj]++] = e * 5 + 4; }
+        if (eb_ij[e] >= 0) hsrc[hf[eb_ij[e]]++] = e * 5 + 2;
+      }
+    }
+    // edge data, SoA
+    const int MS = c->edge_kind == B200_EDGE_SE2 ? 3 : 12;
+    const int IS = D * (D + 1) / 2;
+    std::vector<double> meas((size_t)MS * E), info((size_t)IS * E);
+    for (int e = 0; e < E; ++e) {
+      double zi[12];
+      if (c->edge_kind == B200_EDGE_SE2) host_se2_inverse(&c->e_meas[(size_t)e * 3], zi);
+      else host_iso_inverse(&c->e_meas[(size_t)e * 12], zi);
+      for (int f = 0; f < MS; ++f) meas[(size_t)f * E + e] = zi[f];
+      int f = 0;
+      const double* W = &c->e_info[(size_t)e * D * D];
+      for (int i = 0; i < D; ++i) for (int j = i; j < D; ++j) info[(size_t)(f++) * E + e] = W[i + D * j];
+    }
+    c->d_ev0.upload(c->e_vi, s); c->d_ev1.upload(c->e_vj, s);
+    c->d_meas.upload(meas, s); c->d_info.upload(info, s);
+    c->d_e_flag.upload(transposed, s);
+    c->d_hsrc_ptr.upload(hcnt, s); c->d_hsrc_id.upload(hsrc, s);
+    c->d_bsrc_ptr.upload(bcnt, s); c->d_bsrc_id.upload(bsrc, s);
+    c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
+    c->d_stage.alloc((size_t)E * (3 * D * D + 2 * D));
+    c->d_Hpp.alloc((size_t)nblk * pd * pd);
+    if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
+    bp_colptr = c->hpp_colptr; bp_rowidx = c->hpp_rowidx;
+  } else {
+    // =========================== bundle adjustment ===========================
+    // device edge order: by landmark (fixed points last), then camera pose index, then input order
+    std::vector<int> order(E);
+    for (int e = 0; e < E; ++e) order[e] = e;
+    auto lkey = [&](int e) { int l = lm_lidx[c->e_vi[e]]; return l < 0 ? nl : l; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      int la = lkey(a), lb = lkey(b);
+      if (la != lb) return la < lb;
+      return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
+    });
+    c->e_order = order;
+    std::vector<int> e_pt(E), e_cam(E), e_pose(E), e_hpl(E, -1), lm_eptr(nl + 1, 0);
+    std::vector<unsigned char> e_first(E, 0);
+    std::vector<double> meas((size_t)2 * E), info((size_t)3 * E);
+    c->hpl_row.clear(); c->hpl_col.clear();
+    int nslot = 0;
+    for (int q = 0; q < E; ++q) {
+      int e = order[q];
+      e_pt[q] = c->e_vi[e]; e_cam[q] = c->e_vj[e];
+      e_pose[q] = PV.hidx[c->e_vj[e]];
+      int l = lm_lidx[c->e_vi[e]];
+      if (l >= 0) lm_eptr[l + 1]++;
+      if (l >= 0 && e_pose[q] >= 0) {
+        bool dup = q > 0 && lm_lidx[e_pt[q - 1]] == l && e_pose[q - 1] == e_pose[q];
+        if (dup) e_hpl[q] = e_hpl[q - 1];
+        else { e_hpl[q] = nslot++; e_first[q] = 1; c->hpl_row.push_back(e_pose[q]); c->hpl_col.push_back(l); }
+      }
+      meas[q] = c->e_meas[(size_t)e * 2]; meas[(size_t)E + q] = c->e_meas[(size_t)e * 2 + 1];
+      const double* W = &c->e_info[(size_t)e * 4];
+      info[q] = W[0]; info[(size_t)E + q] = W[2]; info[(size_t)2 * E + q] = W[3];
+    }
+    for (int l = 0; l < nl; ++l) lm_eptr[l + 1] += lm_eptr[l];
+    c->n_hpl = nslot;
+    // camera observation lists (ascending device edge index)
+    std::vector<int> cam_eptr(np + 1, 0), cam_eidx;
+    for (int q = 0; q < E; ++q) if (e_pose[q] >= 0) cam_eptr[e_pose[q] + 1]++;
+    for (int i = 0; i < np; ++i) cam_eptr[i + 1] += cam_eptr[i];
+    cam_eidx.resize(cam_eptr[np]);
+    {
+      std::vector<int> f(cam_eptr.begin(), cam_eptr.end() - 1);
+      for (int q = 0; q < E; ++q) if (e_pose[q] >= 0) cam_eidx[f[e_pose[q]]++] = q;
+    }
+    // Hpp: P2MC graphs have no camera-camera edges -> block diagonal
+    c->n_hpp = np;
+    c->hpp_colptr.resize(np + 1); c->hpp_rowidx.resize(np); c->hpp_diag_block.resize(np);
+    for (int i = 0; i < np; ++i) { c->hpp_colptr[i] = i; c->hpp_rowidx[i] = i; c->hpp_diag_block[i] = i; }
+    c->hpp_colptr[np] = np;
+    // Hschur pattern (block_solver.hpp:262-288): Hpp pattern + co-observation pairs (i1<=i2)
+    std::vector<long long> keys;
+    auto compact = [&]() { std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end()); };
+    for (int i = 0; i < np; ++i) keys.push_back(((long long)i << 32) | i);
+    for (long long k2 : c->extra_schur_keys) keys.push_back(k2);
+    size_t next_compact = std::max<size_t>(keys.size() * 2, (size_t)1 << 24);
+    for (int l = 0; l < nl; ++l) {
+      int prev_a = -1;
+      for (int a = lm_eptr[l]; a < lm_eptr[l + 1]; ++a) {
+        if (e_hpl[a] < 0 || e_hpl[a] == prev_a) continue;
+        prev_a = e_hpl[a];
+        int prev_b = -1;
+        for (int b2 = a; b2 < lm_eptr[l + 1]; ++b2) {
+          if (e_hpl[b2] < 0 || e_hpl[b2] == prev_b) continue;
+          prev_b = e_hpl[b2];
+          keys.push_back(((long long)e_pose[b2] << 32) | e_pose[a]);
+        }
+      }
+      if (keys.size() > next_compact) { compact(); next_compact = std::max<size_t>(keys.size() * 2, (size_t)1 << 24); }
+    }
+    compact();
+    const int nT = (int)keys.size();
+    c->n_hs = nT;
+    c->hs_colptr.assign(np + 1, 0); c->hs_rowidx.resize(nT);
+    std::vector<int> t_row(nT), t_col(nT), t_hpp(nT, -1);
+    for (int t = 0; t < nT; ++t) {
+      t_col[t] = (int)(keys[t] >> 32); t_row[t] = (int)(keys[t] & 0xffffffff);
+      c->hs_colptr[t_col[t] + 1]++; c->hs_rowidx[t] = t_row[t];
+      if (t_row[t] == t_col[t]) t_hpp[t] = t_row[t];
+    }
+    for (int i = 0; i < np; ++i) c->hs_colptr[i + 1] += c->hs_colptr[i];
+    // contributions per target, ascending landmark
+    std::vector<int> sc_ptr(nT + 1, 0);
+    auto find_t = [&](int row, int col) {
+      long long key = ((long long)col << 32) | row;
+      return (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<int> fillp;
+      std::vector<int> sc_lm, sc_a, sc_b;
+      if (pass == 1) {
+        for (int t = 0; t < nT; ++t) sc_ptr[t + 1] += sc_ptr[t];
+        fillp.assign(sc_ptr.begin(), sc_ptr.end() - 1);
+        sc_lm.resize(sc_ptr[nT]); sc_a.resize(sc_ptr[nT]); sc_b.resize(sc_ptr[nT]);
+      }
+      for (int l = 0; l < nl; ++l) {
+        int prev_a = -1;
+        for (int a = lm_eptr[l]; a < lm_eptr[l + 1]; ++a) {
+          if (e_hpl[a] < 0 || e_hpl[a] == prev_a) continue;
+          prev_a = e_hpl[a];
+          int prev_b = -1;
+          for (int b2 = a; b2 < lm_eptr[l + 1]; ++b2) {
+            if (e_hpl[b2] < 0 || e_hpl[b2] == prev_b) continue;
+            prev_b = e_hpl[b2];
+            int t = find_t(e_pose[a], e_pose[b2]);
+            if (pass == 0) sc_ptr[t + 1]++;
+            else { int p = fillp[t]++; sc_lm[p] = l; sc_a[p] = e_hpl[a]; sc_b[p] = e_hpl[b2]; }
+          }
+        }
+      }
+      if (pass == 1) { c->d_sc_lm.upload(sc_lm, s); c->d_sc_a.upload(sc_a, s); c->d_sc_b.upload(sc_b, s); if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s)); }
+    }
+    c->d_ev0.upload(e_pt, s); c->d_ev1.upload(e_cam, s); c->d_e_pose.upload(e_pose, s); c->d_e_hpl.upload(e_hpl, s);
+    c->d_e_flag.upload(e_first, s);
+    c->d_meas.upload(meas, s); c->d_info.upload(info, s);
+    c->d_lm_eptr.upload(lm_eptr, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
+    c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
+    c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s); c->d_sc_ptr.upload(sc_ptr, s);
+    c->d_Hpp.alloc((size_t)np * 36 + (size_t)c->sizeP);  // [Hpp | b_p staging] contiguous for one all-reduce
+    c->d_Hll.alloc((size_t)std::max(nl, 1) * 9); c->d_Hpl.alloc((size_t)std::max(nslot, 1) * 18);
+    c->d_Dinv.alloc((size_t)std::max(nl, 1) * 9); c->d_db.alloc((size_t)std::max(nl, 1) * 3);
+    c->d_Hschur.alloc((size_t)nT * 36 + (size_t)c->sizeP + 8);  // [Hschur | bschur | scalars] contiguous
+    if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
+    bp_colptr = c->hs_colptr; bp_rowidx = c->hs_rowidx;
+  }
+  // ---- symbolic phase of the linear solver
+  SymbolicOptions opt;
+  c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
+  c->structured = true;
+  c->backup_depth = 0;
+  c->time_symbolic = wall() - t0;
+  return B200_OK;
+}
+
+double* bschur_ptr(b200_ctx* c) { return c->d_Hschur.p + (size_t)c->n_hs * 36; }
+
+// ------------------------------------------------------------------------------------------------
+// per-iteration phases (all asynchronous on c->stream)
+// ------------------------------------------------------------------------------------------------
+void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
+  PhaseTimer pt(c, PH_ERRORS);
+  const int E = c->nE, nb = ceil_div(E, 256);
+  cudaStream_t s = c->stream;
+  if (c->edge_kind == B200_EDGE_SE2)
+    k::pg_chi2_kernel<0><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_partials.p);
+  else if (c->edge_kind == B200_EDGE_SE3)
+    k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_partials.p);
+  else
+    k::ba_chi2_kernel<<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->d_partials.p);
+  k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 0);
+  c->lc.n += 2;
+  B200_CUDA(cudaGetLastError());
+}
+
+int allreduce_dev(b200_ctx* c, double* p, long long count) {
+  if (!c->allreduce || c->world <= 1) return 0;
+  int rc = c->allreduce(p, count, (void*)c->stream, c->allreduce_user);
+  if (rc != 0) { c->err = "all-reduce callback failed"; return B200_ERR_COLLECTIVE; }
+  return 0;
+}
+
+int enqueue_build_system(b200_ctx* c) {
+  PhaseTimer pt(c, PH_LINEARIZE);
+  cudaStream_t s = c->stream;
+  const int E = c->nE, np = c->np;
+  if (!c->schur) {
+    if (c->edge_kind == B200_EDGE_SE2) {
+      k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p);
+      k::gather_segments_kernel<3, 9><<<ceil_div((long long)c->n_hpp * 9, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
+      k::gather_segments_kernel<3, 3><<<ceil_div((long long)np * 3, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
+    } else {
+      k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p);
+      k::gather_segments_kernel<6, 36><<<ceil_div((long long)c->n_hpp * 36, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
+      k::gather_segments_kernel<6, 6><<<ceil_div((long long)np * 6, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
+    }
+    c->lc.n += 3;
+  } else {
+    double* b_p_stage = c->d_Hpp.p + (size_t)np * 36;
+    if (c->nl > 0) {
+      k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
+      c->lc.n++;
+    }
+    k::ba_linearize_cams_kernel<<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage);
+    c->lc.n++;
+    B200_CUDA(cudaGetLastError());
+    int rc = allreduce_dev(c, c->d_Hpp.p, (long long)np * 36 + c->sizeP);  // sharded: partial camera blocks -> full
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(c->d_b.p, b_p_stage, (size_t)c->sizeP * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses and landmarks
+  cudaStream_t s = c->stream;
+  const int np = c->np, nl = c->nl;
+  int nb = ceil_div((long long)np * c->pd, 256);
+  if (c->pd == 3) k::max_diag_kernel<3><<<nb, 256, 0, s>>>(np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_partials.p);
+  else k::max_diag_kernel<6><<<nb, 256, 0, s>>>(np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_partials.p);
+  k::reduce_max_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, 1.0, c->d_scalars.p + 2, 0);
+  c->lc.n += 2;
+  if (c->schur && nl > 0) {
+    nb = ceil_div((long long)nl * 3, 256);
+    k::max_diag_kernel<3><<<nb, 256, 0, s>>>(nl, nullptr, c->d_Hll.p, c->d_partials.p);
+    k::reduce_max_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, 1.0, c->d_scalars.p + 2, 1);
+    c->lc.n += 2;
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+// Solver::solve with the lambda currently stored at d_scalars[3]
+int enqueue_solve(b200_ctx* c) {
+  cudaStream_t s = c->stream;
+  const double* d_lambda = c->d_scalars.p + 3;
+  if (!c->schur) {
+    { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hpp.p, d_lambda, s, &c->lc); }
+    { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(c->d_b.p, c->d_x.p, s, &c->lc); }
+    return 0;
+  }
+  {
+    PhaseTimer pt(c, PH_SCHUR);
+    if (c->nl > 0) {
+      k::schur_landmark_inverse_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_Hll.p, c->d_b.p + c->sizeP, d_lambda, c->d_Dinv.p, c->d_db.p);
+      c->lc.n++;
+    }
+    const double hpp_scale = (c->world > 1 && c->rank != 0) ? 0.0 : 1.0;
+    k::schur_reduce_kernel<<<ceil_div((long long)c->n_hs * 32, 128), 128, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
+    c->lc.n++;
+    B200_CUDA(cudaGetLastError());
+    int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);
+    if (rc) return rc;
+  }
+  { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, s, &c->lc); }
+  { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc); }
+  if (c->nl > 0) {
+    PhaseTimer pt(c, PH_BACKSUB);
+    // on a failed factorisation the reference returns before touching the landmark part of x; the pose part
+    // is left untouched by chol.solve, the landmark part is recomputed from the stale pose part (harmless:
+    // LM discards the step, GN reports Fail).
+    k::ba_backsub_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_e_hpl.p, c->d_e_pose.p, c->d_Hpl.p, c->d_Dinv.p, c->d_b.p + c->sizeP, c->d_x.p, c->d_x.p + c->sizeP);
+    c->lc.n++;
+    B200_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+void enqueue_update(b200_ctx* c) {
+  PhaseTimer pt(c, PH_UPDATE);
+  cudaStream_t s = c->stream;
+  const int n = c->n_pose_v;
+  if (c->pose_kind == B200_VERTEX_SE2) k::oplus_se2_kernel<<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p);
+  else if (c->pose_kind == B200_VERTEX_SE3) {
+    int orth = 0;
+    if (++c->num_oplus_calls > 1000) { c->num_oplus_calls = 0; orth = 1; }  // VertexSE3::orthogonalizeAfter (vertex_se3.h:56,111)
+    k::oplus_se3_kernel<<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, orth);
+  } else {
+    k::oplus_cam_kernel<<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, c->d_cam_der.p);
+  }
+  c->lc.n++;
+  if (c->schur && c->n_lm_v > 0) {
+    k::oplus_xyz_kernel<<<ceil_div(c->n_lm_v, 128), 128, 0, s>>>(c->n_lm_v, c->d_lm_lidx.p, c->d_x.p + c->sizeP, c->d_lm_est.p);
+    c->lc.n++;
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+void enqueue_scale(b200_ctx* c) {  // d_scalars[1] = sum_j x_j (lambda x_j + b_j)
+  cudaStream_t s = c->stream;
+  const int n = c->sizeP + c->sizeL, nb = ceil_div(n, 256);
+  k::lm_scale_kernel<<<nb, 256, 0, s>>>(n, c->d_x.p, c->d_b.p, c->d_scalars.p + 3, c->d_partials.p);
+  k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 1);
+  c->lc.n += 2;
+  B200_CUDA(cudaGetLastError());
+}
+
+void do_push(b200_ctx* c) {
+  cudaStream_t s = c->stream;
+  B200_CUDA(cudaMemcpyAsync(c->d_pose_bak.p, c->d_pose_est.p, c->d_pose_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (c->pose_kind == B200_VERTEX_CAM) B200_CUDA(cudaMemcpyAsync(c->d_cam_der_bak.p, c->d_cam_der.p, c->d_cam_der.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (c->schur && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_bak.p, c->d_lm_est.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+void do_pop(b200_ctx* c) {
+  cudaStream_t s = c->stream;
+  B200_CUDA(cudaMemcpyAsync(c->d_pose_est.p, c->d_pose_bak.p, c->d_pose_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (c->pose_kind == B200_VERTEX_CAM) B200_CUDA(cudaMemcpyAsync(c->d_cam_der.p, c->d_cam_der_bak.p, c->d_cam_der.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (c->schur && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_est.p, c->d_lm_bak.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+
+// sharded runs: chi2 and the landmark part of the LM scale are partial sums -> one tiny all-reduce
+int reduce_trial_scalars(b200_ctx* c) {
+  if (!c->allreduce || c->world <= 1) return 0;
+  // every rank holds the same pose part of x and b; only the landmark part differs.  To keep the sum exact
+  // we all-reduce chi2 (slot 0) only; the scale is assembled as pose part (local) + all-reduced landmark part.
+  return allreduce_dev(c, c->d_scalars.p + 0, 1);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+const char* b200_version(void) { return "g2o_b200 0.1 (sm_100a)"; }
+
+int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int b200_create(int device, b200_ctx** out) {
+  if (!out) return B200_ERR_INVALID;
+  *out = nullptr;
+  if (device == -1) {  // host-only context: structure phase for CPU-side tests, compute calls fail with NO_DEVICE
+    b200_ctx* c = new b200_ctx();
+    c->device = -1;
+    c->host_only = true;
+    *out = c;
+    return B200_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device available: the B200 solve path has no CPU fallback";
+    return B200_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { g_create_error = "invalid device index"; return B200_ERR_INVALID; }
+  b200_ctx* c = new b200_ctx();
+  c->device = device;
+  try {
+    B200_CUDA(cudaSetDevice(device));
+    B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(double)));
+    B200_CUDA(cudaMallocHost((void**)&c->h_status, sizeof(int)));
+    for (int i = 0; i < 16; ++i) B200_CUDA(cudaEventCreate(&c->ev[i]));
+  } catch (const CudaError& err) {
+    g_create_error = describe(err);
+    delete c;
+    return B200_ERR_CUDA;
+  }
+  *out = c;
+  return B200_OK;
+}
+
+void b200_destroy(b200_ctx* c) {
+  if (!c) return;
+  if (c->host_only) { host_only_flag() = true; delete c; host_only_flag() = false; return; }
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 16; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  cudaStream_t s = c->stream;
+  delete c;
+  if (s) cudaStreamDestroy(s);
+}
+
+const char* b200_last_error(const b200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int b200_set_vertices(b200_ctx* c, int kind, int n, const double* est, const int32_t* hidx, const uint8_t* marg) {
+  if (!c || kind < 0 || kind > 3 || n < 0 || (n > 0 && (!est || !hidx))) return B200_ERR_INVALID;
+  b200_ctx::VertexSet& V = c->vs[kind];
+  V.set = true; V.n = n;
+  V.est.assign(est, est + (size_t)n * vest(kind));
+  V.hidx.assign(hidx, hidx + n);
+  if (marg) V.marg.assign(marg, marg + n); else V.marg.clear();
+  c->structured = false;
+  return B200_OK;
+}
+
+int b200_set_edges(b200_ctx* c, int kind, int n, const int32_t* vi, const int32_t* vj, const double* meas, const double* info) {
+  if (!c || kind < 0 || kind > 2 || n < 0 || (n > 0 && (!vi || !vj || !meas || !info))) return B200_ERR_INVALID;
+  c->edge_kind = kind; c->nE = n;
+  c->e_vi.assign(vi, vi + n); c->e_vj.assign(vj, vj + n);
+  c->e_meas.assign(meas, meas + (size_t)n * emeas(kind));
+  const int D = edim(kind);
+  c->e_info.assign(info, info + (size_t)n * D * D);
+  c->structured = false;
+  return B200_OK;
+}
+
+int b200_set_allreduce(b200_ctx* c, b200_allreduce_fn fn, void* user, int rank, int world) {
+  if (!c || world < 1 || rank < 0 || rank >= world) return B200_ERR_INVALID;
+  c->allreduce = fn; c->allreduce_user = user; c->rank = rank; c->world = world;
+  return B200_OK;
+}
+
+int b200_add_schur_pattern(b200_ctx* c, int n, const int32_t* rows, const int32_t* cols) {
+  if (!c || n < 0) return B200_ERR_INVALID;
+  for (int i = 0; i < n; ++i) c->extra_schur_keys.push_back(((long long)cols[i] << 32) | (unsigned)rows[i]);
+  c->structured = false;
+  return B200_OK;
+}
+
+int b200_build_structure(b200_ctx* c) {
+  return guarded(c, [&]() {
+    if (!c->host_only) B200_CUDA(cudaSetDevice(c->device));
+    return build_structure_impl(c);
+  });
+}
+
+#define NEED_STRUCTURE(c) \
+  if (!(c)->structured) return fail((c), B200_ERR_INVALID, "call b200_build_structure first")
+#define NEED_DEVICE(c) \
+  if ((c)->host_only) return fail((c), B200_ERR_NO_DEVICE, "host-only context: the B200 solve path has no CPU fallback")
+
+int b200_compute_active_errors(b200_ctx* c, double* chi2) {
+  return guarded(c, [&]() {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    enqueue_chi2(c);
+    int rc = reduce_trial_scalars(c);
+    if (rc) return rc;
+    sync_scalars(c);
+    c->last_chi2 = c->h_scalars[0];
+    if (chi2) *chi2 = c->h_scalars[0];
+    return (int)B200_OK;
+  });
+}
+
+int b200_build_system(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    return enqueue_build_system(c);
+  });
+}
+
+int b200_set_lambda(b200_ctx* c, double lambda, int /*backup*/) {
+  return guarded(c, [&]() {
+    NEED_STRUCTURE(c);
+    // the diagonal is never modified in place: lambda is applied where H is consumed (Cholesky scatter,
+    // landmark inverses, Schur diagonal), which is what backup + restoreDiagonal achieve in the reference
+    c->lambda_for_solve = lambda;
+    return (int)B200_OK;
+  });
+}
+int b200_restore_diagonal(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_STRUCTURE(c);
+    c->lambda_for_solve = 0.0;
+    return (int)B200_OK;
+  });
+}
+
+int b200_solve(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    set_device_lambda(c, c->lambda_for_solve);
+    int rc = enqueue_solve(c);
+    if (rc) return rc;
+    sync_scalars(c);
+    return *c->h_status ? (int)B200_NOT_POSITIVE_DEFINITE : (int)B200_OK;
+  });
+}
+
+int b200_update(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    enqueue_update(c);
+    return (int)B200_OK;
+  });
+}
+int b200_push(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_STRUCTURE(c);
+    NEED_DEVICE(c);
+    if (c->backup_depth >= 1) return fail(c, B200_ERR_UNSUPPORTED, "backup stack depth > 1 (LM needs 1)");
+    B200_CUDA(cudaSetDevice(c->device));
+    do_push(c);
+    c->backup_depth = 1;
+    return (int)B200_OK;
+  });
+}
+int b200_pop(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_STRUCTURE(c);
+    if (c->backup_depth < 1) return fail(c, B200_ERR_INVALID, "pop on an empty backup stack");
+    B200_CUDA(cudaSetDevice(c->device));
+    do_pop(c);
+    c->backup_depth = 0;
+    return (int)B200_OK;
+  });
+}
+int b200_discard_top(b200_ctx* c) {
+  return guarded(c, [&]() {
+    NEED_STRUCTURE(c);
+    if (c->backup_depth < 1) return fail(c, B200_ERR_INVALID, "discardTop on an empty backup stack");
+    c->backup_depth = 0;
+    return (int)B200_OK;
+  });
+}
+
+int b200_set_lm_params(b200_ctx* c, double user_lambda_init, int max_trials) {
+  if (!c || max_trials < 1) return B200_ERR_INVALID;
+  c->user_lambda_init = user_lambda_init;
+  c->max_trials_after_failure = max_trials;
+  return B200_OK;
+}
+
+// one OptimizationAlgorithm::solve(iteration); returns SolverResult in st->result and as return value
+int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_stats* st) {
+  return guarded(c, [&]() -> int {
+    NEED_DEVICE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    b200_iter_stats local;
+    if (!st) st = &local;
+    memset(st, 0, sizeof(*st));
+    st->iteration = iteration;
+    const double t_start = wall();
+    if (iteration == 0 && !c->structured) {
+      int rc = build_structure_impl(c);
+      if (rc) return rc;
+    }
+    NEED_STRUCTURE(c);
+    if (iteration == 0) st->time_symbolic = c->time_symbolic;
+    int rc = 0;
+    if (algorithm == B200_GAUSS_NEWTON) {
+      // core/optimization_algorithm_gauss_newton.cpp:50-93 (computeActiveErrors only caches edge errors there)
+      set_device_lambda(c, 0.0);
+      if ((rc = enqueue_build_system(c))) return rc;
+      if ((rc = enqueue_solve(c))) return rc;
+      enqueue_update(c);
+      sync_scalars(c);
+      st->result = *c->h_status ? B200_RESULT_FAIL : B200_RESULT_OK;
+      st->time_iteration = wall() - t_start;
+      return st->result;
+    }
+    // ---- Levenberg-Marquardt: core/optimization_algorithm_levenberg.cpp:57-147
+    enqueue_chi2(c);
+    if ((rc = reduce_trial_scalars(c))) return rc;
+    if ((rc = enqueue_build_system(c))) return rc;
+    if (iteration == 0) enqueue_max_diag(c);
+    sync_scalars(c);
+    double currentChi = c->h_scalars[0];
+    double tempChi = currentChi;
+    if (iteration == 0) {
+      c->lambda = c->user_lambda_init > 0 ? c->user_lambda_init : 1e-5 * c->h_scalars[2];
+      c->ni = 2;
+    }
+    double rho = 0;
+    int& qmax = c->levenberg_iterations;
+    qmax = 0;
+    do {
+      do_push(c);
+      set_device_lambda(c, c->lambda);
+      if ((rc = enqueue_solve(c))) return rc;
+      enqueue_update(c);
+      enqueue_chi2(c);
+      if ((rc = reduce_trial_scalars(c))) return rc;
+      enqueue_scale(c);
+      sync_scalars(c);
+      const bool ok2 = *c->h_status == 0;
+      tempChi = c->h_scalars[0];
+      if (!ok2) tempChi = DBL_MAX;
+      rho = currentChi - tempChi;
+      double scale = c->h_scalars[1];
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        double scaleFactor = std::max(1. / 3., alpha);
+        c->lambda *= scaleFactor;
+        c->ni = 2;
+        currentChi = tempChi;
+      } else {
+        c->lambda *= c->ni;
+        c->ni *= 2;
+        do_pop(c);
+      }
+      qmax++;
+    } while (rho < 0 && qmax < c->max_trials_after_failure);
+    c->last_chi2 = currentChi;
+    st->chi2 = currentChi;
+    st->lambda = c->lambda;
+    st->levenberg_iterations = qmax;
+    st->result = (qmax == c->max_trials_after_failure || rho == 0) ? B200_RESULT_TERMINATE : B200_RESULT_OK;
+    st->time_iteration = wall() - t_start;
+    return st->result;
+  });
+}
+
+int b200_optimize(b200_ctx* c, int algorithm, int max_iterations, b200_iter_stats* stats) {
+  if (!c) return B200_ERR_INVALID;
+  // OptimizationAlgorithmWithHessian::init -> BlockSolver::init -> LinearSolver::init would drop the symbolic
+  // factor here; the structure is a pure function of the graph handed over, so it is kept until the graph changes
+  int done = 0, result = B200_RESULT_OK;
+  bool ok = true;
+  for (int i = 0; i < max_iterations && ok; ++i) {
+    b200_iter_stats local;
+    b200_iter_stats* st = stats ? &stats[i] : &local;
+    result = b200_algorithm_solve(c, algorithm, i, st);
+    if (result < 0 && result != B200_RESULT_FAIL) return result;  // hard error
+    ok = result == B200_RESULT_OK;
+    // what SparseOptimizer::optimize does when statistics are on: chi2 of the state after the iteration
+    // (LM already knows it; GN needs one more error pass)
+    if (stats && algorithm == B200_GAUSS_NEWTON) {
+      double chi = 0;
+      int rc = b200_compute_active_errors(c, &chi);
+      if (rc) return rc;
+      st->chi2 = chi;
+    }
+    ++done;
+  }
+  if (result == B200_RESULT_FAIL) return 0;
+  return done;
+}
+
+// ------------------------------------------------------------------------------------------------ read-back
+int b200_get_dims(b200_ctx* c, int32_t* d) {
+  if (!c || !d) return B200_ERR_INVALID;
+  d[0] = c->np; d[1] = c->nl; d[2] = c->sizeP; d[3] = c->sizeL; d[4] = c->nE; d[5] = c->n_pose_v + c->n_lm_v; d[6] = c->pd; d[7] = c->schur ? c->ld : 0;
+  return B200_OK;
+}
+static int copy_out(b200_ctx* c, const double* dev, double* host, size_t n) {
+  NEED_DEVICE(c);
+  B200_CUDA(cudaSetDevice(c->device));
+  B200_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  return B200_OK;
+}
+int b200_get_x(b200_ctx* c, double* x) {
+  return guarded(c, [&]() { NEED_STRUCTURE(c); return copy_out(c, c->d_x.p, x, (size_t)c->sizeP + c->sizeL); });
+}
+int b200_get_b(b200_ctx* c, double* b) {
+  return guarded(c, [&]() { NEED_STRUCTURE(c); return copy_out(c, c->d_b.p, b, (size_t)c->sizeP + c->sizeL); });
+}
+int b200_get_bschur(b200_ctx* c, double* out) {
+  return guarded(c, [&]() { NEED_STRUCTURE(c); if (!c->schur) return fail(c, B200_ERR_INVALID, "no Schur complement in this problem"); return copy_out(c, bschur_ptr(c), out, (size_t)c->sizeP); });
+}
+int b200_get_estimates(b200_ctx* c, int kind, double* out) {
+  return guarded(c, [&]() {
+    NEED_STRUCTURE(c);
+    const bool lm = kind == B200_VERTEX_XYZ;
+    if (!lm && kind != c->pose_kind) return fail(c, B200_ERR_INVALID, "vertex kind not present");
+    if (lm && !c->schur) return fail(c, B200_ERR_INVALID, "vertex kind not present");
+    const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
+    std::vector<double> buf((size_t)n * st);
+    copy_out(c, lm ? c->d_lm_est.p : c->d_pose_est.p, buf.data(), buf.size());
+    for (int v = 0; v < n; ++v) memcpy(out + (size_t)v * ne, &buf[(size_t)v * st], ne * sizeof(double));
+    return (int)B200_OK;
+  });
+}
+int b200_get_hessian_diagonal(b200_ctx* c, double* diag) {
+  return guarded(c, [&]() {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (c->pd == 3) k::extract_diag_kernel<3><<<ceil_div((long long)c->np * 3, 256), 256, 0, s>>>(c->np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_diag.p);
+    else k::extract_diag_kernel<6><<<ceil_div((long long)c->np * 6, 256), 256, 0, s>>>(c->np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_diag.p);
+    c->lc.n++;
+    if (c->schur && c->nl > 0) { k::extract_diag_kernel<3><<<ceil_div((long long)c->nl * 3, 256), 256, 0, s>>>(c->nl, nullptr, c->d_Hll.p, c->d_diag.p + c->sizeP); c->lc.n++; }
+    B200_CUDA(cudaGetLastError());
+    return copy_out(c, c->d_diag.p, diag, (size_t)c->sizeP + c->sizeL);
+  });
+}
+int b200_get_blocks(b200_ctx* c, int which, int32_t* rows, int32_t* cols, double* values) {
+  return guarded(c, [&]() -> int {
+    NEED_STRUCTURE(c);
+    const int pd = c->pd;
+    if (which == 0) {
+      if (!rows) return c->n_hpp;
+      int k2 = 0;
+      for (int col = 0; col < c->np; ++col) for (int p = c->hpp_colptr[col]; p < c->hpp_colptr[col + 1]; ++p, ++k2) { rows[k2] = c->hpp_rowidx[p]; cols[k2] = col; }
+      if (values) { int rc2 = copy_out(c, c->d_Hpp.p, values, (size_t)c->n_hpp * pd * pd); if (rc2) return rc2; }
+      return c->n_hpp;
+    }
+    if (!c->schur) return fail(c, B200_ERR_INVALID, "no landmark blocks in this problem");
+    if (which == 1) {
+      if (!rows) return c->nl;
+      for (int l = 0; l < c->nl; ++l) rows[l] = cols[l] = l;
+      if (values) { int rc2 = copy_out(c, c->d_Hll.p, values, (size_t)c->nl * 9); if (rc2) return rc2; }
+      return c->nl;
+    }
+    if (which == 2) {  // Hpl slots are stored landmark-major, ascending camera: already SparseBlockMatrix order
+      if (!rows) return c->n_hpl;
+      for (int q = 0; q < c->n_hpl; ++q) { rows[q] = c->hpl_row[q]; cols[q] = c->hpl_col[q]; }
+      if (values) { int rc2 = copy_out(c, c->d_Hpl.p, values, (size_t)c->n_hpl * 18); if (rc2) return rc2; }
+      return c->n_hpl;
+    }
+    if (which == 3) {
+      if (!rows) return c->n_hs;
+      int k2 = 0;
+      for (int col = 0; col < c->np; ++col) for (int p = c->hs_colptr[col]; p < c->hs_colptr[col + 1]; ++p, ++k2) { rows[k2] = c->hs_rowidx[p]; cols[k2] = col; }
+      if (values) { int rc2 = copy_out(c, c->d_Hschur.p, values, (size_t)c->n_hs * 36); if (rc2) return rc2; }
+      return c->n_hs;
+    }
+    return fail(c, B200_ERR_INVALID, "which must be 0..3");
+  });
+}
+int b200_get_block_ordering(b200_ctx* c, int32_t* perm) {
+  if (!c || !c->structured) return B200_ERR_INVALID;
+  const std::vector<int>& P = c->chol.symbolic().perm;
+  if (perm) memcpy(perm, P.data(), P.size() * sizeof(int));
+  return (int)P.size();
+}
+int64_t b200_get_factor_nnz(b200_ctx* c) { return (c && c->structured) ? c->chol.symbolic().scalar_lnz : -1; }
+int b200_get_factor_info(b200_ctx* c, int64_t* out) {
+  if (!c || !c->structured || !out) return B200_ERR_INVALID;
+  const SymbolicFactor& S = c->chol.symbolic();
+  out[0] = S.nsn; out[1] = (int64_t)S.task_ptr.size() - 1; out[2] = S.nlevels; out[3] = S.max_nrow; out[4] = S.max_ncol; out[5] = S.factor_doubles;
+  return B200_OK;
+}
+int64_t b200_get_launch_count(b200_ctx* c) { return c ? c->lc.n : -1; }
+int b200_set_profiling(b200_ctx* c, int on) {
+  if (!c) return B200_ERR_INVALID;
+  c->profiling = on != 0;
+  for (int i = 0; i < 8; ++i) { c->phase_seconds[i] = 0; c->phase_count[i] = 0; }
+  return B200_OK;
+}
+int b200_get_phase_time(b200_ctx* c, int phase, double* seconds, int64_t* count) {
+  if (!c || phase < 0 || phase >= 8) return B200_ERR_INVALID;
+  if (seconds) *seconds = c->phase_seconds[phase];
+  if (count) *count = c->phase_count[phase];
+  return B200_OK;
+}
+void* b200_get_stream(b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int b200_synchronize(b200_ctx* c) {
+  return guarded(c, [&]() { NEED_DEVICE(c); B200_CUDA(cudaSetDevice(c->device)); B200_CUDA(cudaStreamSynchronize(c->stream)); return (int)B200_OK; });
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// solver.h - the device-resident solver context behind the C-ABI (include/g2o_b200.h).
+//
+// Host-side mirror of the reference's BlockSolver<Traits> + OptimizationAlgorithm{GaussNewton,Levenberg}
+// for the three configured graph families (SE2 pose graph, SE3 pose graph, CAM+XYZ bundle adjustment):
+// same phases, same names, same error behaviour (bool / status, never exceptions across the ABI), with all
+// per-edge / per-vertex / per-landmark loops and the sparse Cholesky running as sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/g2o_b200.h"
+#include "chol.h"
+#include "common.h"
+
+struct b200_ctx {
+  int device = 0;
+  bool host_only = false;  // created with device -1: structure phase only, no compute
+  cudaStream_t stream = nullptr;
+  std::string err;
+  g2o_b200::LaunchCounter lc;
+
+  // ---------------- inputs as handed over by the adapter (host copies)
+  struct VertexSet {
+    bool set = false;
+    int n = 0;
+    std::vector<double> est;
+    std::vector<int> hidx;
+    std::vector<unsigned char> marg;
+  } vs[4];
+  int edge_kind = -1;
+  int nE = 0;
+  std::vector<int> e_vi, e_vj;
+  std::vector<double> e_meas, e_info;
+  std::vector<long long> extra_schur_keys;  // (col<<32|row) blocks other shards contribute to Hschur
+
+  // ---------------- structure (host)
+  bool structured = false;
+  int pose_kind = -1;
+  bool schur = false;
+  int np = 0, nl = 0, pd = 0, ld = 0, sizeP = 0, sizeL = 0;
+  int n_pose_v = 0, n_lm_v = 0;
+  std::vector<int> pose_vertex, lm_vertex;     // index -> vertex slot
+  std::vector<int> hpp_colptr, hpp_rowidx;     // upper block pattern of Hpp (CCS)
+  std::vector<int> hpp_diag_block;             // pose i -> block index of (i,i)
+  std::vector<int> hs_colptr, hs_rowidx;       // Hschur pattern
+  std::vector<int> e_order;                    // device edge order -> input edge index (BA)
+  std::vector<int> hpl_row, hpl_col;           // per Hpl slot
+  int n_hpl = 0, n_hs = 0, n_hpp = 0;
+
+  // ---------------- device state
+  g2o_b200::DevBuf<double> d_pose_est, d_lm_est, d_cam_der, d_pose_bak, d_lm_bak, d_cam_der_bak;
+  g2o_b200::DevBuf<int> d_pose_hidx, d_lm_lidx, d_pose_vertex, d_lm_vertex;
+  g2o_b200::DevBuf<int> d_ev0, d_ev1, d_e_pose, d_e_hpl;
+  g2o_b200::DevBuf<unsigned char> d_e_flag;  // pose graphs: transposed; BA: first-occurrence of its Hpl block
+  g2o_b200::DevBuf<double> d_meas, d_info, d_stage;
+  g2o_b200::DevBuf<int> d_hsrc_ptr, d_hsrc_id, d_bsrc_ptr, d_bsrc_id;
+  g2o_b200::DevBuf<int> d_lm_eptr, d_cam_eptr, d_cam_eidx, d_hpp_diag_block;
+  g2o_b200::DevBuf<double> d_Hpp, d_Hll, d_Hpl, d_Hschur, d_Dinv, d_db, d_b, d_x, d_bschur, d_diag;
+  g2o_b200::DevBuf<int> d_t_row, d_t_col, d_t_hpp, d_sc_ptr, d_sc_lm, d_sc_a, d_sc_b;
+  g2o_b200::DevBuf<double> d_partials, d_scalars;  // scalars: [0] chi2 [1] scale [2] maxdiag [3] lambda
+  double* h_scalars = nullptr;                     // pinned mirror of d_scalars (+ status as double)
+  int* h_status = nullptr;
+  int backup_depth = 0;
+  g2o_b200::CholeskyGpu chol;
+
+  // ---------------- algorithm state (core/optimization_algorithm_levenberg.h)
+  double lambda = -1.0, ni = 2.0;
+  double lambda_for_solve = 0.0;
+  int levenberg_iterations = 0;
+  double user_lambda_init = 0.0;
+  int max_trials_after_failure = 10;
+  int num_oplus_calls = 0;
+  double last_chi2 = 0.0;
+
+  // ---------------- sharding
+  b200_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  int rank = 0, world = 1;
+
+  // ---------------- profiling
+  bool profiling = false;
+  cudaEvent_t ev[16] = {};
+  double phase_seconds[8] = {};
+  long long phase_count[8] = {};
+  double time_symbolic = 0.0;
+};

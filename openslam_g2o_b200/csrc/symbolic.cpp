@@ -1,0 +1,346 @@
+// symbolic.cpp - see symbolic.h.  All of this is integer-only host work done once per structure.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <numeric>
+
+#include "block_amd.h"
+
+namespace g2o_b200 {
+
+SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt) {
+  SymbolicFactor S;
+  S.nb = nb;
+  S.d = d;
+  const int nblk = colptr[nb];
+
+  // ---- 1. ordering (bit-exact twin of cs_amd on the block pattern)
+  if (!opt.given_perm.empty()) S.perm = opt.given_perm;
+  else S.perm = block_amd(nb, colptr, rowidx);
+  S.pinv.assign(nb, 0);
+  for (int k = 0; k < nb; ++k) S.pinv[S.perm[k]] = k;
+
+  // ---- 2. permuted pattern, as "upper by column": for column k the rows i < k
+  std::vector<int> up_ptr(nb + 1, 0);
+  for (int c = 0; c < nb; ++c)
+    for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+      int r = rowidx[p];
+      if (r == c) continue;
+      int i = S.pinv[r], j = S.pinv[c];
+      up_ptr[std::max(i, j) + 1]++;
+    }
+  for (int k = 0; k < nb; ++k) up_ptr[k + 1] += up_ptr[k];
+  std::vector<int> up_idx(up_ptr[nb]);
+  {
+    std::vector<int> fill(up_ptr.begin(), up_ptr.end() - 1);
+    for (int c = 0; c < nb; ++c)
+      for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+        int r = rowidx[p];
+        if (r == c) continue;
+        int i = S.pinv[r], j = S.pinv[c];
+        up_idx[fill[std::max(i, j)]++] = std::min(i, j);
+      }
+  }
+
+  // ---- 3. elimination tree (Liu, path compression) and exact column counts (row-subtree walks)
+  S.parent.assign(nb, -1);
+  {
+    std::vector<int> anc(nb, -1);
+    for (int k = 0; k < nb; ++k)
+      for (int p = up_ptr[k]; p < up_ptr[k + 1]; ++p) {
+        int i = up_idx[p];
+        while (i != -1 && i < k) {
+          int nxt = anc[i];
+          anc[i] = k;
+          if (nxt == -1) S.parent[i] = k;
+          i = nxt;
+        }
+      }
+  }
+  S.colcount.assign(nb, 1);
+  {
+    std::vector<int> mark(nb, -1);
+    for (int k = 0; k < nb; ++k) {
+      mark[k] = k;
+      for (int p = up_ptr[k]; p < up_ptr[k + 1]; ++p)
+        for (int j = up_idx[p]; mark[j] != k; j = S.parent[j]) {
+          S.colcount[j]++;
+          mark[j] = k;
+        }
+    }
+  }
+  S.scalar_lnz = 0;
+  for (int k = 0; k < nb; ++k)
+    S.scalar_lnz += (int64_t)d * d * (S.colcount[k] - 1) + (int64_t)d * (d + 1) / 2;
+
+  // ---- 4. supernodes: fundamental partition
+  std::vector<int> first;  // first column of each supernode
+  for (int j = 0; j < nb; ++j) {
+    bool join = j > 0 && S.parent[j - 1] == j && S.colcount[j - 1] == S.colcount[j] + 1;
+    if (!join) first.push_back(j);
+  }
+  int ns = (int)first.size();
+  std::vector<int> nc(ns), nr(ns);
+  for (int s = 0; s < ns; ++s) {
+    int end = (s + 1 < ns) ? first[s + 1] : nb;
+    nc[s] = end - first[s];
+    nr[s] = S.colcount[first[s]];
+  }
+  // relaxed amalgamation of a supernode with its parent when they are adjacent in column order
+  if (opt.relax && ns > 1) {
+    std::vector<int> c2s(nb);
+    for (int s = 0; s < ns; ++s) for (int j = first[s]; j < first[s] + nc[s]; ++j) c2s[j] = s;
+    std::vector<int> merged_into(ns, -1);
+    std::vector<double> zeros(ns, 0.0);
+    for (int s = 0; s + 1 < ns; ++s) {
+      int last = first[s] + nc[s] - 1;
+      int pj = S.parent[last];
+      if (pj < 0) continue;
+      int p = c2s[pj];
+      if (p != s + 1 || first[p] != last + 1) continue;  // parent must start right after s
+      double add = (double)nc[s] * (nc[s] + nr[p] - nr[s]);
+      double z = zeros[s] + zeros[p] + add;
+      int mc = nc[s] + nc[p];
+      double total = (double)mc * (nc[s] + nr[p]) - 0.5 * (double)mc * (mc - 1);
+      double frac = z / std::max(total, 1.0);
+      bool ok = (mc * d <= 12) || (mc * d <= 48 && frac < 0.6) || (mc * d <= 96 && frac < 0.25) || frac < 0.05;
+      if (!ok) continue;
+      // merge s into p (p keeps its index; its first column moves down)
+      first[p] = first[s];
+      nr[p] = nc[s] + nr[p];
+      nc[p] = mc;
+      zeros[p] = z;
+      merged_into[s] = p;
+    }
+    std::vector<int> f2, c2, r2;
+    for (int s = 0; s < ns; ++s)
+      if (merged_into[s] < 0) { f2.push_back(first[s]); c2.push_back(nc[s]); r2.push_back(nr[s]); }
+    first.swap(f2); nc.swap(c2); nr.swap(r2);
+    ns = (int)first.size();
+  }
+  // width cap: split wide supernodes into a chain of panels
+  {
+    const int wmax = std::max(1, opt.max_panel_cols_scalar / d);
+    std::vector<int> f2, c2;
+    for (int s = 0; s < ns; ++s) {
+      int rem = nc[s], c0 = first[s];
+      int pieces = (rem + wmax - 1) / wmax;
+      int base = rem / pieces, extra = rem % pieces;
+      for (int q = 0; q < pieces; ++q) {
+        int w = base + (q < extra ? 1 : 0);
+        f2.push_back(c0); c2.push_back(w);
+        c0 += w;
+      }
+    }
+    first.swap(f2); nc.swap(c2);
+    ns = (int)first.size();
+  }
+  S.nsn = ns;
+  S.sn_col0 = first;
+  S.sn_ncol = nc;
+  S.col2sn.assign(nb, 0);
+  for (int s = 0; s < ns; ++s) for (int j = first[s]; j < first[s] + nc[s]; ++j) S.col2sn[j] = s;
+  S.sn_parent.assign(ns, -1);
+  for (int s = 0; s < ns; ++s) {
+    int pj = S.parent[first[s] + nc[s] - 1];
+    S.sn_parent[s] = pj < 0 ? -1 : S.col2sn[pj];
+  }
+
+  // ---- 5. row structures: own columns, pattern of A below them, children's below-rows
+  // lower pattern by column: column c holds rows i > c ("transpose" of up_*)
+  std::vector<int> lo_ptr(nb + 1, 0);
+  for (int k = 0; k < nb; ++k) for (int p = up_ptr[k]; p < up_ptr[k + 1]; ++p) lo_ptr[up_idx[p] + 1]++;
+  for (int k = 0; k < nb; ++k) lo_ptr[k + 1] += lo_ptr[k];
+  std::vector<int> lo_idx(lo_ptr[nb]);
+  {
+    std::vector<int> fill(lo_ptr.begin(), lo_ptr.end() - 1);
+    for (int k = 0; k < nb; ++k) for (int p = up_ptr[k]; p < up_ptr[k + 1]; ++p) lo_idx[fill[up_idx[p]]++] = k;
+  }
+  std::vector<int> child_ptr(ns + 1, 0), child_idx(ns);
+  for (int s = 0; s < ns; ++s) if (S.sn_parent[s] >= 0) child_ptr[S.sn_parent[s] + 1]++;
+  for (int s = 0; s < ns; ++s) child_ptr[s + 1] += child_ptr[s];
+  {
+    std::vector<int> fill(child_ptr.begin(), child_ptr.end() - 1);
+    for (int s = 0; s < ns; ++s) if (S.sn_parent[s] >= 0) child_idx[fill[S.sn_parent[s]]++] = s;
+  }
+  S.sn_rowptr.assign(ns + 1, 0);
+  S.sn_nrow.assign(ns, 0);
+  {
+    std::vector<int> stamp(nb, -1);
+    std::vector<int> tmp;
+    for (int s = 0; s < ns; ++s) {
+      tmp.clear();
+      const int c0 = first[s], c1 = first[s] + nc[s];
+      for (int j = c0; j < c1; ++j) stamp[j] = s;
+      for (int j = c0; j < c1; ++j)
+        for (int p = lo_ptr[j]; p < lo_ptr[j + 1]; ++p) {
+          int i = lo_idx[p];
+          if (stamp[i] != s) { stamp[i] = s; tmp.push_back(i); }
+        }
+      for (int q = child_ptr[s]; q < child_ptr[s + 1]; ++q) {
+        int c = child_idx[q];
+        for (int p = S.sn_rowptr[c] + S.sn_ncol[c]; p < S.sn_rowptr[c + 1]; ++p) {
+          int i = S.sn_rows[p];
+          if (stamp[i] != s) { stamp[i] = s; tmp.push_back(i); }
+        }
+      }
+      std::sort(tmp.begin(), tmp.end());
+      for (int j = c0; j < c1; ++j) S.sn_rows.push_back(j);
+      S.sn_rows.insert(S.sn_rows.end(), tmp.begin(), tmp.end());
+      S.sn_nrow[s] = nc[s] + (int)tmp.size();
+      S.sn_rowptr[s + 1] = (int)S.sn_rows.size();
+    }
+  }
+  S.sn_lptr.assign(ns + 1, 0);
+  S.flops = 0;
+  for (int s = 0; s < ns; ++s) {
+    S.sn_lptr[s + 1] = S.sn_lptr[s] + (int64_t)S.sn_nrow[s] * d * S.sn_ncol[s] * d;
+    S.max_nrow = std::max(S.max_nrow, S.sn_nrow[s]);
+    S.max_ncol = std::max(S.max_ncol, S.sn_ncol[s]);
+  }
+  S.factor_doubles = S.sn_lptr[ns];
+
+  // ---- 6. scatter plan for the input blocks
+  S.a_dst.assign(nblk, 0); S.a_ld.assign(nblk, 0); S.a_trans.assign(nblk, 0);
+  S.diag_dst.assign(nb, 0); S.diag_ld.assign(nb, 0);
+  {
+    // position of a block row inside a supernode's row list: binary search
+    auto local_row = [&](int s, int row) {
+      const int* b = S.sn_rows.data() + S.sn_rowptr[s];
+      const int* e = S.sn_rows.data() + S.sn_rowptr[s + 1];
+      const int* it = std::lower_bound(b, e, row);
+      assert(it != e && *it == row);
+      return (int)(it - b);
+    };
+    for (int c = 0; c < nb; ++c)
+      for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+        int r = rowidx[p];
+        int i = S.pinv[r], j = S.pinv[c];
+        int col = std::min(i, j), row = std::max(i, j);
+        int s = S.col2sn[col];
+        int ld = S.sn_nrow[s] * d;
+        int lr = local_row(s, row), lc = col - S.sn_col0[s];
+        S.a_dst[p] = S.sn_lptr[s] + (int64_t)lr * d + (int64_t)lc * d * ld;
+        S.a_ld[p] = ld;
+        S.a_trans[p] = (i < j) ? 1 : 0;  // A(r,c) lands at C(i,j); the stored lower entry is C(j,i) = A(r,c)^T
+      }
+    for (int k = 0; k < nb; ++k) {
+      int s = S.col2sn[k];
+      int ld = S.sn_nrow[s] * d;
+      int lc = k - S.sn_col0[s];
+      S.diag_dst[k] = S.sn_lptr[s] + (int64_t)lc * d + (int64_t)lc * d * ld;
+      S.diag_ld[k] = ld;
+    }
+  }
+
+  // ---- 7. left-looking update lists with relative indices
+  {
+    std::vector<int> cnt(ns + 1, 0);
+    for (int K = 0; K < ns; ++K) {
+      const int* rows = S.sn_rows.data() + S.sn_rowptr[K];
+      int prev = -1;
+      for (int p = S.sn_ncol[K]; p < S.sn_nrow[K]; ++p) {
+        int J = S.col2sn[rows[p]];
+        if (J != prev) { cnt[J + 1]++; prev = J; }
+      }
+    }
+    S.upd_ptr.assign(ns + 1, 0);
+    for (int s = 0; s < ns; ++s) S.upd_ptr[s + 1] = S.upd_ptr[s] + cnt[s + 1];
+    const int nu = S.upd_ptr[ns];
+    S.upd_k.assign(nu, 0); S.upd_p0.assign(nu, 0); S.upd_p1.assign(nu, 0); S.upd_relptr.assign(nu + 1, 0);
+    std::vector<int> fill(S.upd_ptr.begin(), S.upd_ptr.end() - 1);
+    for (int K = 0; K < ns; ++K) {
+      const int* rows = S.sn_rows.data() + S.sn_rowptr[K];
+      int p = S.sn_ncol[K];
+      while (p < S.sn_nrow[K]) {
+        int J = S.col2sn[rows[p]];
+        int q = p;
+        while (q < S.sn_nrow[K] && S.col2sn[rows[q]] == J) ++q;
+        int u = fill[J]++;
+        S.upd_k[u] = K; S.upd_p0[u] = p; S.upd_p1[u] = q;
+        p = q;
+      }
+    }
+    int64_t tot = 0;
+    for (int u = 0; u < nu; ++u) { S.upd_relptr[u] = tot; tot += S.sn_nrow[S.upd_k[u]] - S.upd_p0[u]; }
+    S.upd_relptr[nu] = tot;
+    S.rel.assign(tot, 0);
+    std::vector<int> pos(nb, -1);
+    for (int J = 0; J < ns; ++J) {
+      const int* jr = S.sn_rows.data() + S.sn_rowptr[J];
+      for (int q = 0; q < S.sn_nrow[J]; ++q) pos[jr[q]] = q;
+      for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
+        int K = S.upd_k[u];
+        const int* kr = S.sn_rows.data() + S.sn_rowptr[K];
+        int64_t o = S.upd_relptr[u];
+        for (int p = S.upd_p0[u]; p < S.sn_nrow[K]; ++p) {
+          assert(pos[kr[p]] >= 0);
+          S.rel[o++] = pos[kr[p]];
+        }
+      }
+      for (int q = 0; q < S.sn_nrow[J]; ++q) pos[jr[q]] = -1;
+    }
+  }
+
+  // ---- 8. work estimates and the task / level schedule
+  std::vector<double> work(ns, 0.0), sub(ns, 0.0);
+  const double d3 = (double)d * d * d;
+  for (int J = 0; J < ns; ++J) {
+    double w = 0;
+    for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
+      int K = S.upd_k[u];
+      w += 2.0 * (S.sn_nrow[K] - S.upd_p0[u]) * (double)(S.upd_p1[u] - S.upd_p0[u]) * S.sn_ncol[K] * d3;
+    }
+    double ncs = S.sn_ncol[J], nrs = S.sn_nrow[J];
+    w += d3 * (ncs * ncs * ncs / 3.0 + (nrs - ncs) * ncs * ncs);
+    work[J] = w;
+    S.flops += w;
+  }
+  for (int s = 0; s < ns; ++s) {
+    sub[s] += work[s];
+    if (S.sn_parent[s] >= 0) sub[S.sn_parent[s]] += sub[s];
+  }
+  const double thresh = std::max(S.flops * opt.subtree_work_fraction, 2.0e4);
+  // task id per supernode: a maximal subtree with sub <= thresh becomes one task (rooted at `root`)
+  std::vector<int> root(ns, -1);
+  for (int s = ns - 1; s >= 0; --s) {
+    int p = S.sn_parent[s];
+    if (p >= 0 && root[p] >= 0) root[s] = root[p];                 // inside a subtree task
+    else if (sub[s] <= thresh) root[s] = s;                        // new subtree task rooted here
+    else root[s] = -1;                                             // own task, level-scheduled
+  }
+  std::vector<int> task_of(ns, -1);
+  std::vector<std::vector<int>> tasks;
+  for (int s = 0; s < ns; ++s) {
+    if (root[s] == -1) { task_of[s] = (int)tasks.size(); tasks.push_back({s}); }
+    else if (root[s] == s) { task_of[s] = (int)tasks.size(); tasks.push_back({}); }
+  }
+  for (int s = 0; s < ns; ++s) if (root[s] >= 0) { task_of[s] = task_of[root[s]]; tasks[task_of[s]].push_back(s); }
+  const int nt = (int)tasks.size();
+  std::vector<int> tlevel(nt, 0);
+  for (int s = 0; s < ns; ++s) {  // ascending: children first
+    int p = S.sn_parent[s];
+    if (p < 0) continue;
+    int ts = task_of[s], tp = task_of[p];
+    if (ts != tp) tlevel[tp] = std::max(tlevel[tp], tlevel[ts] + 1);
+  }
+  S.nlevels = 0;
+  for (int t = 0; t < nt; ++t) S.nlevels = std::max(S.nlevels, tlevel[t] + 1);
+  std::vector<int> order(nt);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tlevel[a] < tlevel[b]; });
+  S.level_ptr.assign(S.nlevels + 1, 0);
+  for (int t = 0; t < nt; ++t) S.level_ptr[tlevel[t] + 1]++;
+  for (int l = 0; l < S.nlevels; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
+  S.task_ptr.assign(nt + 1, 0);
+  for (int q = 0; q < nt; ++q) {
+    const std::vector<int>& t = tasks[order[q]];
+    S.task_ptr[q + 1] = S.task_ptr[q] + (int)t.size();
+    S.task_sn.insert(S.task_sn.end(), t.begin(), t.end());
+  }
+  return S;
+}
+
+}  // namespace g2o_b200

@@ -1,0 +1,60 @@
+// symbolic.h - host-side symbolic analysis for the supernodal left-looking block Cholesky.
+//
+// Replaces (one-time, per structure) what the reference does in
+// LinearSolverCSparse::computeSymbolicDecomposition (solvers/csparse/linear_solver_csparse.h:246-300):
+// block AMD -> permuted pattern -> elimination tree -> column counts (nnz(L)), and adds what a GPU
+// numeric phase needs and CSparse's scalar up-looking factorisation does not: supernodes (fundamental,
+// relaxed amalgamation, width cap), per-supernode row structures, left-looking update lists with
+// relative indices, and a task/level schedule (small subtrees run inside one CTA, the top of the tree is
+// level-scheduled).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace g2o_b200 {
+
+struct SymbolicOptions {
+  int max_panel_cols_scalar = 96;   // supernodes wider than this are split into a chain of panels
+  double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
+  bool relax = true;
+  // set when the caller already knows the ordering (tests); empty = run block AMD
+  std::vector<int> given_perm;
+};
+
+struct SymbolicFactor {
+  int nb = 0;  // block columns
+  int d = 0;   // block dimension (3 or 6)
+  std::vector<int> perm, pinv;  // perm[new] = old block index
+  // block-level elimination tree / exact column counts of the permuted matrix
+  std::vector<int> parent, colcount;
+  int64_t scalar_lnz = 0;  // == css::lnz of the reference for the same ordering
+  // scatter plan of the input blocks (input order) into the panels of L
+  std::vector<int64_t> a_dst;     // offset of element (0,0) of the destination block
+  std::vector<int32_t> a_ld;      // leading dimension of the destination panel
+  std::vector<uint8_t> a_trans;   // 1: store the transposed block
+  std::vector<int64_t> diag_dst;  // per permuted block column: offset of its diagonal block (for lambda)
+  std::vector<int32_t> diag_ld;
+  // supernodes (ascending column order)
+  int nsn = 0;
+  std::vector<int> sn_col0, sn_ncol, sn_nrow;  // block units; nrow includes the ncol diagonal rows
+  std::vector<int> sn_rowptr, sn_rows;         // block rows, ascending; first ncol entries = own columns
+  std::vector<int64_t> sn_lptr;                // offset of the panel in L ((nrow*d) x (ncol*d), col-major)
+  std::vector<int> sn_parent, col2sn;
+  // left-looking updates: target J receives from K rows [p0,p1) (the rows of K inside J's columns)
+  std::vector<int> upd_ptr;                    // nsn+1
+  std::vector<int> upd_k, upd_p0, upd_p1;
+  std::vector<int64_t> upd_relptr;             // into rel
+  std::vector<int> rel;                        // for p in [p0,nrow_K): local block row in J
+  // schedule: tasks = supernode sequences processed by one CTA; levels of independent tasks
+  std::vector<int> task_ptr, task_sn;          // task t runs task_sn[task_ptr[t] .. task_ptr[t+1])
+  std::vector<int> level_ptr;                  // tasks sorted by level; level l = tasks [level_ptr[l], level_ptr[l+1])
+  int nlevels = 0;
+  int64_t factor_doubles = 0;
+  double flops = 0;  // factorisation flops of the stored (relaxed) structure
+  int max_nrow = 0, max_ncol = 0;
+};
+
+// colptr/rowidx: upper block pattern (rows <= col, ascending, diagonal present) in input block order.
+SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt);
+
+}  // namespace g2o_b200

@@ -1,0 +1,191 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json's configs name (no datasets ship, no network).
+
+Each generator returns a dict of numpy arrays in ".g2o payload" form (the numbers that follow the ids on the
+text line), so the same arrays feed the product (SparseOptimizer.add_vertices/add_edges), the oracle, and
+`write_g2o`.  Input generation is host-side test/bench plumbing, not part of the hot path.
+
+  sphere(nodes_per_level, laps, ...)   examples/sphere/create_sphere.cpp:95-184 (reference generator)
+  venice_like(cams, points, ...)       SURVEY.md section 8d config 3/4: ring of inward-looking cameras, windowed visibility
+"""
+import numpy as np
+
+from ._lib import EDGE_P2MC, EDGE_SE3, VERTEX_CAM, VERTEX_SE3, VERTEX_XYZ
+
+
+# ---------------------------------------------------------------- quaternion helpers (x y z w), vectorised
+def _qmul(a, b):
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx,
+                     aw * bw - ax * bx - ay * by - az * bz], axis=-1)
+
+
+def _qconj(q):
+    return q * np.array([-1.0, -1.0, -1.0, 1.0])
+
+
+def _qrot(q, v):
+    qv = np.concatenate([v, np.zeros(v.shape[:-1] + (1,))], axis=-1)
+    return _qmul(_qmul(q, qv), _qconj(q))[..., :3]
+
+
+def _compose(qa, ta, qb, tb):
+    return _qmul(qa, qb), ta + _qrot(qa, tb)
+
+
+def _prefix_compose(q, t):
+    """inclusive scan of SE3 composition (Hillis-Steele): out[i] = T0*T1*...*Ti"""
+    q, t = q.copy(), t.copy()
+    n, step = len(q), 1
+    while step < n:
+        q2, t2 = _compose(q[:-step], t[:-step], q[step:], t[step:])
+        q[step:], t[step:] = q2, t2
+        step *= 2
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    return q, t
+
+
+def sphere(nodes_per_level=50, laps=50, radius=100.0, sigma_t=0.01, sigma_r=0.005, seed=2500):
+    """SE3 pose graph on a sphere (create_sphere.cpp:95-184). Defaults = sphere2500 (2500 poses, 9799 edges)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = nodes_per_level * laps
+    ids = np.arange(n)
+    nn = ids % nodes_per_level
+    az = -np.pi + 2 * nn * np.pi / nodes_per_level
+    ay = -0.5 * np.pi + (ids + 1) * np.pi / n       # `id` is already incremented in the reference (:102-105)
+    qz = np.stack([0 * az, 0 * az, np.sin(az / 2), np.cos(az / 2)], axis=-1)
+    qy = np.stack([0 * ay, np.sin(ay / 2), 0 * ay, np.cos(ay / 2)], axis=-1)
+    q = _qmul(qz, qy)
+    t = _qrot(q, np.tile(np.array([radius, 0.0, 0.0]), (n, 1)))
+    # edges: odometry chain, then loop closures to the previous lap in the reference's order
+    # (for f: for nn: for dn in -1,0,+1, skipping +1 on the last lap; :131-147)
+    v0_parts, v1_parts = [ids[:-1]], [ids[1:]]
+    for f in range(1, laps):
+        dns = np.array([-1, 0] if f == laps - 1 else [-1, 0, 1])
+        base = np.arange(nodes_per_level)
+        v0_parts.append(np.repeat((f - 1) * nodes_per_level + base, len(dns)))
+        v1_parts.append(((f * nodes_per_level + base)[:, None] + dns[None, :]).reshape(-1))
+    v0 = np.concatenate(v0_parts)
+    v1 = np.concatenate(v1_parts)
+    # ground-truth relative transforms, then noise (:155-175)
+    qrel = _qmul(_qconj(q[v0]), q[v1])
+    trel = _qrot(_qconj(q[v0]), t[v1] - t[v0])
+    E = len(v0)
+    v = rng.normal(0.0, sigma_r, (E, 3))
+    qw = np.maximum(0.0, 1.0 - np.linalg.norm(v, axis=1))
+    qn = np.concatenate([v, qw[:, None]], axis=1)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    qmeas = _qmul(qrel, qn)
+    tmeas = trel + rng.normal(0.0, sigma_t, (E, 3))
+    info = np.zeros((6, 6))
+    info[:3, :3] = np.eye(3) / sigma_t ** 2
+    info[3:, 3:] = np.eye(3) / sigma_r ** 2
+    iu = np.array([info[i, j] for i in range(6) for j in range(i, 6)])
+    edge_payload = np.concatenate([tmeas, qmeas, np.tile(iu, (E, 1))], axis=1)
+    # initial guess: concatenate the (noisy) odometry (:178-184)
+    qo = np.concatenate([q[:1], qmeas[:n - 1]], axis=0)
+    to = np.concatenate([t[:1], tmeas[:n - 1]], axis=0)
+    qi, ti = _prefix_compose(qo, to)
+    vert_payload = np.concatenate([ti, qi], axis=1)
+    return dict(kind="se3", vertex_kind=VERTEX_SE3, edge_kind=EDGE_SE3, vertex_ids=ids.astype(np.int32),
+                vertex_payload=vert_payload, edge_v0=v0.astype(np.int32), edge_v1=v1.astype(np.int32),
+                edge_payload=edge_payload, truth_payload=np.concatenate([t, q], axis=1))
+
+
+def venice_like(num_cams=871, num_points=530304, mean_extra_obs=1.8, seed=871, pixel_sigma=1.0, fixed_obs=None):
+    """Bundle adjustment shaped like Venice (871 cameras / 530k points / ~2M observations).
+
+    Cameras sit on a ring looking inward; every point is seen by k = 2 + Poisson(mean_extra_obs) cameras that
+    form a contiguous window of the ring (banded + wrap-around reduced camera matrix). `fixed_obs` forces a
+    constant k (config 4 uses k = 10)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Rc = 10.0
+    phi = 2 * np.pi * np.arange(num_cams) / num_cams
+    C = np.stack([Rc * np.cos(phi), Rc * np.sin(phi), np.zeros(num_cams)], axis=1)
+    zc = -C / np.linalg.norm(C, axis=1, keepdims=True)            # optical axis: towards the centre
+    xc = np.stack([-np.sin(phi), np.cos(phi), np.zeros(num_cams)], axis=1)
+    yc = np.cross(zc, xc)
+    Rm = np.stack([xc, yc, zc], axis=2)                            # camera-to-world rotation, columns = axes
+    q = _rot_to_quat(Rm)
+    fx = fy = 1000.0
+    r = 4.0 * np.sqrt(rng.uniform(0, 1, num_points))
+    ang = rng.uniform(0, 2 * np.pi, num_points)
+    X = np.stack([r * np.cos(ang), r * np.sin(ang), rng.uniform(-2, 2, num_points)], axis=1)
+    k = np.full(num_points, fixed_obs) if fixed_obs else 2 + rng.poisson(mean_extra_obs, num_points)
+    k = np.minimum(k, num_cams).astype(np.int64)
+    start = rng.integers(0, num_cams, num_points)
+    pt_of_edge = np.repeat(np.arange(num_points), k)
+    offs = np.arange(k.sum()) - np.repeat(np.cumsum(k) - k, k)
+    cam_of_edge = (start[pt_of_edge] + offs) % num_cams
+    # exact projections + pixel noise
+    Rt = np.transpose(Rm, (0, 2, 1))
+    pc = np.einsum("eij,ej->ei", Rt[cam_of_edge], X[pt_of_edge] - C[cam_of_edge])
+    uv = np.stack([fx * pc[:, 0] / pc[:, 2], fy * pc[:, 1] / pc[:, 2]], axis=1) + rng.normal(0, pixel_sigma, (len(pc), 2))
+    # perturbed initial state
+    Ci = C + rng.normal(0, 0.02, C.shape)
+    dq = np.concatenate([rng.normal(0, 0.001, (num_cams, 3)), np.ones((num_cams, 1))], axis=1)
+    dq /= np.linalg.norm(dq, axis=1, keepdims=True)
+    qi = _qmul(q, dq)
+    Xi = X + rng.normal(0, 0.05, X.shape)
+    cam_payload = np.concatenate([Ci, qi, np.tile(np.array([fx, fy, 0.0, 0.0, 0.0]), (num_cams, 1))], axis=1)
+    cam_ids = np.arange(num_cams, dtype=np.int32)
+    pt_ids = (num_cams + np.arange(num_points)).astype(np.int32)
+    return dict(kind="ba", cam_ids=cam_ids, cam_payload=cam_payload, point_ids=pt_ids, point_payload=Xi,
+                edge_v0=pt_ids[pt_of_edge], edge_v1=cam_ids[cam_of_edge], edge_payload=uv,
+                truth_points=X, truth_cams=np.concatenate([C, q], axis=1))
+
+
+def _rot_to_quat(R):
+    """batched rotation matrix -> quaternion (x y z w), w >= 0"""
+    m = R
+    tr = m[:, 0, 0] + m[:, 1, 1] + m[:, 2, 2]
+    q = np.zeros((len(R), 4))
+    for i in range(len(R)):
+        M = m[i]
+        if tr[i] > 0:
+            s = np.sqrt(tr[i] + 1.0) * 2
+            q[i] = [(M[2, 1] - M[1, 2]) / s, (M[0, 2] - M[2, 0]) / s, (M[1, 0] - M[0, 1]) / s, 0.25 * s]
+        else:
+            a = int(np.argmax([M[0, 0], M[1, 1], M[2, 2]]))
+            b, c = (a + 1) % 3, (a + 2) % 3
+            s = np.sqrt(1.0 + M[a, a] - M[b, b] - M[c, c]) * 2
+            v = np.zeros(4)
+            v[a] = 0.25 * s
+            v[b] = (M[b, a] + M[a, b]) / s
+            v[c] = (M[c, a] + M[a, c]) / s
+            v[3] = (M[c, b] - M[b, c]) / s
+            q[i] = v
+        if q[i, 3] < 0:
+            q[i] = -q[i]
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def feed(problem, target):
+    """push a generated problem into anything with add_vertices/add_edges (product SparseOptimizer or the
+    tests' oracle wrapper)"""
+    if problem["kind"] == "se3":
+        target.add_vertices(VERTEX_SE3, problem["vertex_ids"], problem["vertex_payload"])
+        target.add_edges(EDGE_SE3, problem["edge_v0"], problem["edge_v1"], problem["edge_payload"])
+    else:
+        target.add_vertices(VERTEX_CAM, problem["cam_ids"], problem["cam_payload"])
+        target.add_vertices(VERTEX_XYZ, problem["point_ids"], problem["point_payload"])
+        target.add_edges(EDGE_P2MC, problem["edge_v0"], problem["edge_v1"], problem["edge_payload"])
+
+
+def write_g2o(problem, path):
+    """text form of a generated problem (the on-disk format of core/optimizable_graph.cpp:356-569)"""
+    with open(path, "w") as f:
+        if problem["kind"] == "se3":
+            for i, p in zip(problem["vertex_ids"], problem["vertex_payload"]):
+                f.write("VERTEX_SE3:QUAT %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
+            for a, b, p in zip(problem["edge_v0"], problem["edge_v1"], problem["edge_payload"]):
+                f.write("EDGE_SE3:QUAT %d %d %s\n" % (a, b, " ".join(repr(float(x)) for x in p)))
+        else:
+            for i, p in zip(problem["cam_ids"], problem["cam_payload"]):
+                f.write("VERTEX_CAM %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
+            for i, p in zip(problem["point_ids"], problem["point_payload"]):
+                f.write("VERTEX_XYZ %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
+            for a, b, p in zip(problem["edge_v0"], problem["edge_v1"], problem["edge_payload"]):
+                f.write("EDGE_PROJECT_P2MC %d %d %s\n" % (a, b, " ".join(repr(float(x)) for x in p)))

@@ -1258,6 +1258,14 @@ int oracle_add_vertex(oracle_graph* g, int kind, int id, const double* payload, 
 int oracle_add_edge(oracle_graph* g, int kind, int id1, int id2, const double* payload, int n) {
   return add_edge(g, kind, id1, id2, payload, n);
 }
+int oracle_add_vertices(oracle_graph* g, int kind, int n, const int* ids, const double* payload, int stride) {
+  for (int i = 0; i < n; ++i) { int rc = oracle_add_vertex(g, kind, ids[i], payload + (size_t)i * stride, stride); if (rc) return rc; }
+  return 0;
+}
+int oracle_add_edges(oracle_graph* g, int kind, int n, const int* id1, const int* id2, const double* payload, int stride) {
+  for (int i = 0; i < n; ++i) { int rc = add_edge(g, kind, id1[i], id2[i], payload + (size_t)i * stride, stride); if (rc) return rc; }
+  return 0;
+}
 int oracle_set_fixed(oracle_graph* g, int id, int fixed) {
   Vertex* v = g->vertex(id);
   if (!v) return -1;

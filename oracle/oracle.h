@@ -50,6 +50,8 @@ int oracle_load(oracle_graph* g, const char* path);
 /* programmatic construction; payload = the numbers that follow the ids on the .g2o line */
 int oracle_add_vertex(oracle_graph* g, int kind, int id, const double* payload, int n);
 int oracle_add_edge(oracle_graph* g, int kind, int id1, int id2, const double* payload, int n);
+int oracle_add_vertices(oracle_graph* g, int kind, int n, const int* ids, const double* payload, int stride);
+int oracle_add_edges(oracle_graph* g, int kind, int n, const int* id1, const int* id2, const double* payload, int stride);
 int oracle_set_fixed(oracle_graph* g, int id, int fixed);
 
 /* apps/g2o_cli/g2o.cpp:272-320: gauge fixing + marginalisation of the low-dimensional vertices.
