@@ -914,7 +914,7 @@ int b200_get_estimates(b200_ctx* c, int kind, double* out) {
     if (lm && !c->schur) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
     std::vector<double> buf((size_t)n * st);
-    copy_out(c, lm ? c->d_lm_est.p : c->d_pose_est.p, buf.data(), buf.size());
+    { int rc2 = copy_out(c, lm ? c->d_lm_est.p : c->d_pose_est.p, buf.data(), buf.size()); if (rc2) return rc2; }
     for (int v = 0; v < n; ++v) memcpy(out + (size_t)v * ne, &buf[(size_t)v * st], ne * sizeof(double));
     return (int)B200_OK;
   });

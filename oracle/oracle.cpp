@@ -1377,6 +1377,7 @@ int oracle_dims(oracle_graph* g, int* d) {
 }
 int oracle_get_b(oracle_graph* g, double* b) { memcpy(b, g->b.data(), g->b.size() * sizeof(double)); return (int)g->b.size(); }
 int oracle_get_x(oracle_graph* g, double* x) { memcpy(x, g->x.data(), g->x.size() * sizeof(double)); return (int)g->x.size(); }
+int oracle_set_x(oracle_graph* g, const double* x) { memcpy(g->x.data(), x, g->x.size() * sizeof(double)); return (int)g->x.size(); }
 int oracle_get_errors(oracle_graph* g, double* err) {
   size_t k = 0;
   for (Edge* e : g->activeEdges) for (int i = 0; i < e->D; ++i) err[k++] = e->err[i];

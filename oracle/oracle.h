@@ -84,6 +84,7 @@ int oracle_discard_top(oracle_graph* g);
 int oracle_dims(oracle_graph* g, int* dims);
 int oracle_get_b(oracle_graph* g, double* b);           /* length sizePoses+sizeLandmarks */
 int oracle_get_x(oracle_graph* g, double* x);
+int oracle_set_x(oracle_graph* g, const double* x);   /* overwrite solver.x() (numeric-Jacobian checks) */
 int oracle_get_errors(oracle_graph* g, double* err);    /* active edges in order, D doubles each */
 /* canonical estimate layouts: SE2 [x y th]; SE3 [R col-major 9, t 3]; CAM [t3 q(xyzw)4 fx fy cx cy b];
  * XYZ [x y z].  returns #doubles written or -1 */

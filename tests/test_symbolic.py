@@ -1,0 +1,59 @@
+"""Supernodal symbolic plan (supernodes, row structures, update lists, relative indices, scatter plan, task/level
+schedule) validated by executing it sequentially on the CPU (tests/csrc/host_exec.cpp, test-only) and comparing the
+solution with numpy's dense solve."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from helpers import ROOT, random_spd_blocks
+
+LIB = os.path.join(ROOT, "tests", "csrc", "libhost_exec.so")
+
+
+@pytest.fixture(scope="module")
+def hx():
+    if not os.path.exists(LIB):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "csrc")])
+    return C.CDLL(LIB)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("d", [3, 6])
+def test_schedule_execution_solves_the_system(hx, d):
+    rng = np.random.default_rng(d)
+    for trial in range(24):
+        nb = int(rng.integers(1, 90))
+        kind = trial % 4
+        if kind == 0:
+            edges = [(int(rng.integers(nb)), int(rng.integers(nb))) for _ in range(3 * nb)]
+        elif kind == 1:
+            s = max(2, int(np.sqrt(nb)))
+            edges = [(i, i + 1) for i in range(nb - 1) if (i + 1) % s] + [(i, i + s) for i in range(nb - s)]
+        elif kind == 2:
+            edges = [(i, j) for i in range(nb) for j in range(i + 1, min(nb, i + 6))]
+        else:
+            edges = [(i, j) for i in range(nb) for j in range(i + 1, nb)] if nb < 30 else []  # dense / diagonal
+        cp, ri, vals, A = random_spd_blocks(rng, nb, d, edges)
+        v = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+        b = rng.standard_normal(nb * d)
+        x = np.zeros(nb * d)
+        for maxc, relax in [(96, 1), (12, 1), (96, 0), (6, 0)]:
+            rc = hx.hx_solve(nb, d, _p(cp), _p(ri), _p(v), C.c_double(0.25), _p(b), _p(x), maxc, relax)
+            assert rc == 0, (rc, trial, nb, maxc, relax)
+            xr = np.linalg.solve(A + 0.25 * np.eye(nb * d), b)
+            assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+
+
+def test_not_positive_definite_is_reported(hx):
+    rng = np.random.default_rng(5)
+    cp, ri, vals, A = random_spd_blocks(rng, 8, 3, [(i, i + 1) for i in range(7)], shift=0.0)
+    vals[0] -= 50 * np.eye(3)
+    v = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+    b = np.ones(24)
+    x = np.zeros(24)
+    assert hx.hx_solve(8, 3, _p(cp), _p(ri), _p(v), C.c_double(0.0), _p(b), _p(x), 96, 1) == 1
