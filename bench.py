@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py - LM iterations/sec of the g2o hot path on B200 (see BASELINE.json `metric`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload venice|sphere2500] [--impl reference]
+
+A "step" is one Levenberg-Marquardt iteration (OptimizationAlgorithmLevenberg::solve: errors + chi2, linearize +
+accumulate, [Schur], sparse Cholesky, back-substitution, oplus update, re-evaluation, lambda control) over one
+synthetic input graph.  The optimisation is restarted from the initial estimates every RESTART steps (like running
+`g2o -i 10` repeatedly) so that every step does comparable work; the restart copy is outside the per-step timers.
+
+  value   steps/s with all inputs resident in HBM (CUDA events on the solver's stream, max over ranks)
+  e2e     steps/s through the C-ABI with HOST buffers: per step, H2D of the vertex estimates from pinned memory, one
+          LM iteration, D2H of the updated estimates + chi2 (what a Level-3 g2o adapter does around solve())
+  roofline, cpu_baseline: see DESIGN.md section "Measurement"
+
+N > 1 (torchrun): venice shards its landmarks over the ranks (cameras replicated, NCCL all-reduce of the reduced
+camera system per LM trial) - strong scaling of the same graph.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+RESTART = 10  # LM iterations per optimisation run (the reference protocol: g2o -i 10)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="venice", choices=["venice", "sphere2500", "venice_small"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_problem(workload):
+    from openslam_g2o_b200 import synth
+    if workload == "venice":
+        return synth.venice_like(), "Venice-shaped BA (types_sba): 871 cameras / 530304 points / ~2.0M P2MC edges, seed 871"
+    if workload == "venice_small":
+        return synth.venice_like(100, 20000, seed=7), "small BA: 100 cameras / 20000 points"
+    return synth.sphere(), "sphere2500 SE3 pose graph: 2500 poses / 9799 edges (create_sphere.cpp defaults), seed 2500"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path: the oracle port (Eigen-free restatement of
+    SparseOptimizer/BlockSolver/LM) linked against the reference's vendored CSparse compiled in oracle/_ref.
+    Single thread: the reference builds with OpenMP OFF (CMakeLists.txt:137) and CSparse is sequential."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    prob, desc = make_problem(args.workload)
+    o = Oracle()
+    synth.feed(prob, o)
+    o.setup_cli(True)
+    o.initialize_optimization()
+    total = args.warmup + args.steps
+    budget_s = 150.0
+    t_all = time.time()
+    n, st = o.optimize(LM, 1)  # iteration 0: structure + symbolic (not timed)
+    times, done = [], 1
+    L = o.L
+    import ctypes as C
+    from oracle_binding import OracleStats
+    # continue the same optimisation one LM iteration at a time (iteration index > 0: no re-analysis)
+    L.oracle_lm_iteration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    while done < total + 1 and (time.time() - t_all) < budget_s:
+        s = OracleStats()
+        t0 = time.perf_counter()
+        L.oracle_lm_iteration(o.g, done, C.byref(s))
+        times.append(time.perf_counter() - t0)
+        done += 1
+    timed = times[min(args.warmup, max(len(times) - 1, 0)):] or times
+    ms = 1e3 * float(np.mean(timed))
+    value = 1e3 / ms
+    sample = "%d LM iterations of the same input after %d warm-up (iteration 0 = structure+symbolic excluded)" % (len(timed), len(times) - len(timed))
+    print(json.dumps({
+        "impl": "reference", "metric": "LM iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+        "steps": len(timed), "warmup": len(times) - len(timed), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "solver": "lm_fix6_3 (CSparse flavour, block AMD)"},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "oracle restatement of g2o's LM/BlockSolver + the reference's vendored CSparse compiled from /root/reference (oracle/_ref)"},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def algorithmic_bytes(workload, dims, n_hpl, n_hs, n_contrib, n_edges):
+    """per-launch algorithmic bytes of the candidate dominant kernels, read-once/write-once"""
+    if workload.startswith("venice"):
+        nl = dims["numLandmarks"]
+        return {
+            # ba_linearize_points: per edge cam idx 4 + meas 16 + info 24 + slot 4 + flag 1, write Hpl 144;
+            # per landmark est 32 + eptr 4 + vertex 4, write Hll 72 + b 24
+            "linearize": n_edges * (49 + 144) + nl * 136,
+            # schur_reduce: read Hpl 144/blk + Dinv 72 + db 24 per landmark + 12 B per contribution index + Hpp diag;
+            # write Hschur 288/block + bschur
+            "schur": n_hpl * 144 + nl * 96 + n_contrib * 12 + dims["numPoses"] * (288 + 48) + n_hs * 288 + dims["sizePoses"] * 8,
+        }
+    # pose graph: pg_linearize reads ids 8 + Zinv 96 + info 168 + 2 poses 192, writes the 120-double staging record
+    return {"linearize": n_edges * (8 + 96 + 168 + 192 + 960)}
+
+
+def run_b200(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prob, desc = make_problem(args.workload)
+    sharded = world > 1 and prob["kind"] == "ba"
+    opt = g.SparseOptimizer(device=local_rank, shard=rank if sharded else 0, num_shards=world if sharded else 1)
+    opt.set_algorithm("lm_fix6_3")
+    synth.feed(prob, opt)
+    opt.setup_cli()
+    opt.initialize_optimization()
+    opt._ensure_uploaded()
+    ctx = opt.context
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    if sharded:
+        class _Dev:
+            def __init__(self, p, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 3}
+
+        def allreduce(ptr, count, _stream, _user):
+            try:
+                t = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", local_rank))
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(t)
+                return 0
+            except Exception as e:  # noqa
+                print("all-reduce failed:", e, file=sys.stderr)
+                return 1
+        ctx.set_allreduce(allreduce, rank, world)
+    assert ctx.build_structure()
+    dims = ctx.dims()
+    kinds = [g.VERTEX_CAM, g.VERTEX_XYZ] if prob["kind"] == "ba" else [g.VERTEX_SE3]
+    # initial estimates in pinned host memory (source of the e2e H2D copies, destination of the D2H reads)
+    init, host = {}, {}
+    nverts = {}
+    for kd in kinds:
+        n = _vertex_count(ctx, kd, prob, sharded, opt)
+        nverts[kd] = n
+        a = ctx.estimates(kd, n)
+        init[kd] = torch.from_numpy(a.copy()).pin_memory()
+        host[kd] = torch.empty_like(init[kd]).pin_memory()
+
+    def restart():
+        for kd in kinds:
+            ctx.set_estimates(kd, init[kd].numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda") if args.workload == "sphere2500" else None
+    state = {"it": 0}
+
+    def step(e2e):
+        it = state["it"] % RESTART
+        if it == 0:
+            restart()
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        if e2e:
+            for kd in kinds:
+                ctx.set_estimates(kd, init[kd].numpy() if it == 0 else host[kd].numpy())
+        rc, st = ctx.algorithm_solve(g.LEVENBERG, it)
+        if e2e:
+            for kd in kinds:
+                ctx.get_estimates_into(kd, host[kd].numpy())
+        ev1.record(stream)
+        ev1.synchronize()
+        state["it"] += 1
+        return ev0.elapsed_time(ev1), st
+
+    def timed_run(e2e, steps, warmup):
+        state["it"] = 0
+        for _ in range(warmup):
+            step(e2e)
+        # keep the restart phase of the timed region aligned with a fresh optimisation run
+        barrier()
+        t = 0.0
+        trials = 0
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            ms, st = step(e2e)
+            t += ms
+            trials += st.levenberg_iterations
+        barrier()
+        wall = time.perf_counter() - wall0
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), trials, wall
+
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    if rank == 0:
+        sampler.start()
+    ms_total, trials, wall = timed_run(False, args.steps, max(args.warmup, 3))
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed_run(True, args.steps, 3)
+    value = args.steps / (ms_total * 1e-3)
+    e2e_value = args.steps / (ms_e2e * 1e-3)
+    h2d = sum(int(init[kd].numel()) * 8 for kd in kinds)
+    d2h = h2d + 8
+
+    # ---- roofline of the dominant kernel, CUDA events on the launching stream inside this process
+    ctx.set_profiling(True)
+    state["it"] = 0
+    for _ in range(RESTART):
+        step(False)
+    phases = ctx.phase_times()
+    ctx.set_profiling(False)
+    info = ctx.factor_info()
+    roof = None
+    per_phase = {k: {"ms_total": 1e3 * v[0], "launch_groups": v[1]} for k, v in phases.items() if v[1] > 0}
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = peaks.get("hbm_gbs", 6650.0)
+        n_contrib = _contrib_count(prob) if prob["kind"] == "ba" else 0
+        n_hpl = len(prob["edge_v0"]) if prob["kind"] == "ba" else 0
+        n_hs = lib_blocks(ctx, 3) if prob["kind"] == "ba" else 0
+        ab = algorithmic_bytes(args.workload, dims, n_hpl, n_hs, n_contrib, dims["numEdges"])
+        cand = {k: phases[k] for k in ab if phases.get(k, (0, 0))[1] > 0}
+        dom = max(cand, key=lambda k: cand[k][0])
+        sec = cand[dom][0] / cand[dom][1]
+        achieved = ab[dom] / sec / 1e9
+        roof = {"bound": "hbm", "kernel": {"linearize": "ba_linearize_points_kernel" if prob["kind"] == "ba" else "pg_linearize_kernel<SE3>",
+                                           "schur": "schur_reduce_kernel"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": sec * 1e3, "traffic": None}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.workload, prob)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "LM iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "solver": "lm_fix6_3_b200 (Schur + supernodal Cholesky)" if prob["kind"] == "ba" else "lm_fix6_3_b200 (supernodal Cholesky)",
+                       "restart_every": RESTART, "lm_trials_in_timed_region": trials,
+                       "parallelism": ("landmark-sharded x%d, cameras replicated, NCCL all-reduce of Hschur per trial" % world) if sharded else ("replicas only" if world > 1 else "single GPU"),
+                       "l2": "flushed between steps (256 MiB memset, outside the step timers)" if flush is not None else "working set (Hpl + edge arrays ~0.7 GB) larger than the 126 MB L2",
+                       "timing": "sum of per-step CUDA-event intervals on the solver stream, max over ranks", "wall_s": wall},
+            "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "kernel_groups_ms_per_%d_iterations" % RESTART: per_phase,
+            "factor": info,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def lib_blocks(ctx, which):
+    import openslam_g2o_b200 as g
+    return int(g.lib.b200_get_blocks(ctx.handle, which, None, None, None))
+
+
+def _contrib_count(prob):
+    k = np.bincount(prob["edge_v0"] - prob["point_ids"][0])
+    return int((k * (k + 1) // 2).sum())
+
+
+def _vertex_count(ctx, kind, prob, sharded, opt):
+    import openslam_g2o_b200 as g
+    if kind == g.VERTEX_CAM:
+        return len(prob["cam_ids"])
+    if kind == g.VERTEX_SE3:
+        return len(prob["vertex_ids"])
+    # landmarks handed to this rank
+    d = ctx.dims()
+    return d["numVertices"] - len(prob["cam_ids"])
+
+
+def cpu_baseline(workload, prob):
+    """the oracle on a bounded sample of the same workload, on this box's host cores (1 thread: reference default)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import ctypes as C
+        from oracle_binding import LM, Oracle, OracleStats
+    except Exception as e:  # oracle missing
+        return {"value": None, "unit": "iterations/s", "cores": 1, "kind": "port", "sample": "unavailable: %s" % e}
+    from openslam_g2o_b200 import synth
+    o = Oracle()
+    synth.feed(prob, o)
+    o.setup_cli(True)
+    o.initialize_optimization()
+    o.optimize(LM, 1)
+    o.L.oracle_lm_iteration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    times = []
+    t_all = time.time()
+    it = 1
+    while (it <= 4 or time.time() - t_all < 10.0) and time.time() - t_all < 40.0 and it < 40:
+        s = OracleStats()
+        t0 = time.perf_counter()
+        o.L.oracle_lm_iteration(o.g, it, C.byref(s))
+        times.append(time.perf_counter() - t0)
+        it += 1
+    ms = 1e3 * float(np.mean(times))
+    return {"value": 1e3 / ms, "unit": "iterations/s", "cores": 1, "kind": "port", "ms_per_iteration": ms,
+            "sample": "LM iterations 1..%d of the same input (iteration 0 = structure + symbolic analysis excluded)" % (it - 1),
+            "host_cores_available": os.cpu_count(),
+            "note": "oracle = restatement of g2o's LM + BlockSolver linked to the reference's vendored CSparse (oracle/_ref); "
+                    "single thread like the reference's default build (OpenMP OFF)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,9 @@ int b200_get_dims(b200_ctx* ctx, int32_t* dims);
 int b200_get_x(b200_ctx* ctx, double* x);           /* Solver::x(), length sizePoses+sizeLandmarks */
 int b200_get_b(b200_ctx* ctx, double* b);           /* Solver::b() */
 int b200_get_estimates(b200_ctx* ctx, int kind, double* estimates);  /* same layout/order as set_vertices */
+/* overwrite the device-resident estimates (same layout/order as set_vertices): what a Level-3 adapter does when the
+ * host graph changed between iterations (OptimizableGraph::Vertex::setEstimateData, core/optimizable_graph.h:191) */
+int b200_set_estimates(b200_ctx* ctx, int kind, const double* estimates);
 int b200_get_hessian_diagonal(b200_ctx* ctx, double* diag);          /* v->hessian(j,j), index order */
 /* which: 0 Hpp 1 Hll 2 Hpl 3 Hschur; call with rows==NULL to get the block count.  Blocks are listed
  * column by column, ascending block row (SparseBlockMatrix order), values column-major. */
@@ -138,7 +141,9 @@ int b200_get_factor_info(b200_ctx* ctx, int64_t* out);
 int64_t b200_get_launch_count(b200_ctx* ctx);
 /* seconds of the dominant kernels accumulated with CUDA events when profiling is on */
 int b200_set_profiling(b200_ctx* ctx, int on);
-/* phase id: 0 errors 1 linearize 2 schur 3 factor 4 trisolve 5 update 6 backsub; returns seconds,count */
+/* kernel-group id: 0 errors+chi2, 1 linearize (edges / per-landmark), 2 schur reduce, 3 cholesky factor,
+ * 4 triangular solves, 5 oplus update, 6 landmark back-substitution, 7 linearize per-camera, 8 ordered gather,
+ * 9 landmark inverses, 10 LM scale, 11 collective; returns accumulated seconds and #occurrences */
 int b200_get_phase_time(b200_ctx* ctx, int phase, double* seconds, int64_t* count);
 
 /* ------------------------------------------------------------------ Level 1: g2o::LinearSolver<MatrixType>

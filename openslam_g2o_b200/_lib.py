@@ -80,6 +80,7 @@ def _load():
         "b200_get_x": (i32, [vp, vp]),
         "b200_get_b": (i32, [vp, vp]),
         "b200_get_estimates": (i32, [vp, i32, vp]),
+        "b200_set_estimates": (i32, [vp, i32, vp]),
         "b200_get_hessian_diagonal": (i32, [vp, vp]),
         "b200_get_blocks": (i32, [vp, i32, vp, vp, vp]),
         "b200_get_bschur": (i32, [vp, vp]),

@@ -23,23 +23,40 @@ int vstride(int kind) { return kind == B200_VERTEX_SE2 ? 4 : kind == B200_VERTEX
 int edim(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
 int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
 
-// phases for the profiling counters
-enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE = 4, PH_UPDATE = 5, PH_BACKSUB = 6 };
+// kernel groups for the profiling counters (b200_get_phase_time ids)
+enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE = 4, PH_UPDATE = 5, PH_BACKSUB = 6,
+       PH_LINEARIZE_CAMS = 7, PH_GATHER = 8, PH_SCHUR_INV = 9, PH_SCALE = 10, PH_COLLECTIVE = 11, PH_COUNT = 16 };
 
+cudaEvent_t prof_event(b200_ctx* c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    B200_CUDA(cudaEventCreate(&e));
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[c->ev_used++];
+}
+void prof_flush(b200_ctx* c) {
+  if (c->prof_recs.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (const b200_ctx::ProfRec& r : c->prof_recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->phase_seconds[r.id] += ms * 1e-3; c->phase_count[r.id]++; }
+  }
+  c->prof_recs.clear();
+  c->ev_used = 0;
+}
 struct PhaseTimer {
   b200_ctx* c;
   int phase;
+  cudaEvent_t a = nullptr;
   PhaseTimer(b200_ctx* ctx, int ph) : c(ctx), phase(ph) {
-    if (c->profiling) cudaEventRecord(c->ev[2 * ph], c->stream);
+    if (c->profiling) { a = prof_event(c); cudaEventRecord(a, c->stream); }
   }
   ~PhaseTimer() {
-    if (c->profiling) {
-      cudaEventRecord(c->ev[2 * phase + 1], c->stream);
-      cudaEventSynchronize(c->ev[2 * phase + 1]);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, c->ev[2 * phase], c->ev[2 * phase + 1]);
-      c->phase_seconds[phase] += ms * 1e-3;
-      c->phase_count[phase]++;
+    if (c->profiling && a) {
+      cudaEvent_t b = prof_event(c);
+      cudaEventRecord(b, c->stream);
+      c->prof_recs.push_back({phase, a, b});
     }
   }
 };
@@ -423,22 +440,26 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
 
 int allreduce_dev(b200_ctx* c, double* p, long long count) {
   if (!c->allreduce || c->world <= 1) return 0;
+  PhaseTimer pt(c, PH_COLLECTIVE);
   int rc = c->allreduce(p, count, (void*)c->stream, c->allreduce_user);
   if (rc != 0) { c->err = "all-reduce callback failed"; return B200_ERR_COLLECTIVE; }
   return 0;
 }
 
 int enqueue_build_system(b200_ctx* c) {
-  PhaseTimer pt(c, PH_LINEARIZE);
   cudaStream_t s = c->stream;
   const int E = c->nE, np = c->np;
   if (!c->schur) {
     if (c->edge_kind == B200_EDGE_SE2) {
-      k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p);
+      { PhaseTimer pt(c, PH_LINEARIZE);
+      k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p); }
+      PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<3, 9><<<ceil_div((long long)c->n_hpp * 9, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<3, 3><<<ceil_div((long long)np * 3, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
     } else {
-      k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p);
+      { PhaseTimer pt(c, PH_LINEARIZE);
+      k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p); }
+      PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<6, 36><<<ceil_div((long long)c->n_hpp * 36, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<6, 6><<<ceil_div((long long)np * 6, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
     }
@@ -446,10 +467,12 @@ int enqueue_build_system(b200_ctx* c) {
   } else {
     double* b_p_stage = c->d_Hpp.p + (size_t)np * 36;
     if (c->nl > 0) {
+      PhaseTimer pt(c, PH_LINEARIZE);
       k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
       c->lc.n++;
     }
-    k::ba_linearize_cams_kernel<<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage);
+    { PhaseTimer pt(c, PH_LINEARIZE_CAMS);
+    k::ba_linearize_cams_kernel<<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
     int rc = allreduce_dev(c, c->d_Hpp.p, (long long)np * 36 + c->sizeP);  // sharded: partial camera blocks -> full
@@ -487,13 +510,14 @@ int enqueue_solve(b200_ctx* c) {
     return 0;
   }
   {
-    PhaseTimer pt(c, PH_SCHUR);
     if (c->nl > 0) {
+      PhaseTimer pt(c, PH_SCHUR_INV);
       k::schur_landmark_inverse_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_Hll.p, c->d_b.p + c->sizeP, d_lambda, c->d_Dinv.p, c->d_db.p);
       c->lc.n++;
     }
     const double hpp_scale = (c->world > 1 && c->rank != 0) ? 0.0 : 1.0;
-    k::schur_reduce_kernel<<<ceil_div((long long)c->n_hs * 32, 128), 128, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
+    { PhaseTimer pt(c, PH_SCHUR);
+    k::schur_reduce_kernel<<<ceil_div((long long)c->n_hs * 32, 128), 128, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c)); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
     int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);
@@ -534,6 +558,7 @@ void enqueue_update(b200_ctx* c) {
 }
 
 void enqueue_scale(b200_ctx* c) {  // d_scalars[1] = sum_j x_j (lambda x_j + b_j)
+  PhaseTimer pt(c, PH_SCALE);
   cudaStream_t s = c->stream;
   const int n = c->sizeP + c->sizeL, nb = ceil_div(n, 256);
   k::lm_scale_kernel<<<nb, 256, 0, s>>>(n, c->d_x.p, c->d_b.p, c->d_scalars.p + 3, c->d_partials.p);
@@ -603,7 +628,6 @@ int b200_create(int device, b200_ctx** out) {
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     B200_CUDA(cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(double)));
     B200_CUDA(cudaMallocHost((void**)&c->h_status, sizeof(int)));
-    for (int i = 0; i < 16; ++i) B200_CUDA(cudaEventCreate(&c->ev[i]));
   } catch (const CudaError& err) {
     g_create_error = describe(err);
     delete c;
@@ -618,7 +642,7 @@ void b200_destroy(b200_ctx* c) {
   if (c->host_only) { host_only_flag() = true; delete c; host_only_flag() = false; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < 16; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_status) cudaFreeHost(c->h_status);
   cudaStream_t s = c->stream;
@@ -913,9 +937,33 @@ int b200_get_estimates(b200_ctx* c, int kind, double* out) {
     if (!lm && kind != c->pose_kind) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     if (lm && !c->schur) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
-    std::vector<double> buf((size_t)n * st);
-    { int rc2 = copy_out(c, lm ? c->d_lm_est.p : c->d_pose_est.p, buf.data(), buf.size()); if (rc2) return rc2; }
-    for (int v = 0; v < n; ++v) memcpy(out + (size_t)v * ne, &buf[(size_t)v * st], ne * sizeof(double));
+    NEED_DEVICE(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    const double* dev = lm ? c->d_lm_est.p : c->d_pose_est.p;
+    B200_CUDA(cudaMemcpy2DAsync(out, ne * sizeof(double), dev, st * sizeof(double), ne * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return (int)B200_OK;
+  });
+}
+int b200_set_estimates(b200_ctx* c, int kind, const double* est) {
+  return guarded(c, [&]() {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    const bool lm = kind == B200_VERTEX_XYZ;
+    if ((!lm && kind != c->pose_kind) || (lm && !c->schur) || !est) return fail(c, B200_ERR_INVALID, "vertex kind not present");
+    B200_CUDA(cudaSetDevice(c->device));
+    const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
+    double* dev = lm ? c->d_lm_est.p : c->d_pose_est.p;
+    if (st == ne) {
+      B200_CUDA(cudaMemcpyAsync(dev, est, (size_t)n * ne * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    } else {  // padded rows on the device (3 -> 4 doubles)
+      B200_CUDA(cudaMemcpy2DAsync(dev, st * sizeof(double), est, ne * sizeof(double), ne * sizeof(double), n, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (kind == B200_VERTEX_CAM) {
+      k::cam_derive_kernel<<<ceil_div(n, 128), 128, 0, c->stream>>>(n, c->d_pose_est.p, c->d_cam_der.p);
+      c->lc.n++;
+    }
+    B200_CUDA(cudaStreamSynchronize(c->stream));
     return (int)B200_OK;
   });
 }
@@ -983,12 +1031,14 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
 int64_t b200_get_launch_count(b200_ctx* c) { return c ? c->lc.n : -1; }
 int b200_set_profiling(b200_ctx* c, int on) {
   if (!c) return B200_ERR_INVALID;
+  if (!c->host_only) { cudaSetDevice(c->device); prof_flush(c); }
   c->profiling = on != 0;
-  for (int i = 0; i < 8; ++i) { c->phase_seconds[i] = 0; c->phase_count[i] = 0; }
+  for (int i = 0; i < PH_COUNT; ++i) { c->phase_seconds[i] = 0; c->phase_count[i] = 0; }
   return B200_OK;
 }
 int b200_get_phase_time(b200_ctx* c, int phase, double* seconds, int64_t* count) {
-  if (!c || phase < 0 || phase >= 8) return B200_ERR_INVALID;
+  if (!c || phase < 0 || phase >= PH_COUNT) return B200_ERR_INVALID;
+  if (!c->host_only) { cudaSetDevice(c->device); prof_flush(c); }
   if (seconds) *seconds = c->phase_seconds[phase];
   if (count) *count = c->phase_count[phase];
   return B200_OK;

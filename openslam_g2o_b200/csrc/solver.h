@@ -79,10 +79,13 @@ struct b200_ctx {
   void* allreduce_user = nullptr;
   int rank = 0, world = 1;
 
-  // ---------------- profiling
+  // ---------------- profiling: CUDA-event pairs around kernel groups, resolved lazily (no sync while recording)
   bool profiling = false;
-  cudaEvent_t ev[16] = {};
-  double phase_seconds[8] = {};
-  long long phase_count[8] = {};
+  struct ProfRec { int id; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<ProfRec> prof_recs;
+  double phase_seconds[16] = {};
+  long long phase_count[16] = {};
   double time_symbolic = 0.0;
 };

@@ -172,6 +172,13 @@ class SolverContext:
         _check(lib.b200_get_estimates(self._h, kind, L.ptr(out)), self._h)
         return out
 
+    def set_estimates(self, kind, estimates):
+        est = L.as_f64(estimates)
+        _check(lib.b200_set_estimates(self._h, kind, L.ptr(est)), self._h)
+
+    def get_estimates_into(self, kind, out):
+        _check(lib.b200_get_estimates(self._h, kind, L.ptr(out)), self._h)
+
     def blocks(self, which):
         """(rows, cols, values[n, r, c]) of Hpp(0) / Hll(1) / Hpl(2) / Hschur(3), SparseBlockMatrix order."""
         n = _check(lib.b200_get_blocks(self._h, which, None, None, None), self._h)
@@ -205,7 +212,8 @@ class SolverContext:
         _check(lib.b200_set_profiling(self._h, int(on)), self._h)
 
     def phase_times(self):
-        names = ("errors", "linearize", "schur", "factor", "trisolve", "update", "backsub")
+        names = ("errors", "linearize", "schur", "factor", "trisolve", "update", "backsub", "linearize_cams", "gather",
+                 "schur_inv", "scale", "collective")
         out = {}
         for i, nme in enumerate(names):
             s, c = C.c_double(), C.c_int64()

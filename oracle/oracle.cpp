@@ -1357,6 +1357,20 @@ int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_
   return cj;
 }
 
+// one OptimizationAlgorithmLevenberg::solve(iteration) (bench: time iterations of a continuing optimisation)
+int oracle_lm_iteration(oracle_graph* g, int iteration, oracle_iter_stats* st) {
+  oracle_iter_stats local;
+  if (!st) st = &local;
+  memset(st, 0, sizeof(*st));
+  st->iteration = iteration;
+  double ts = now();
+  int r = solve_lm(g, iteration, st);
+  st->time_iteration = now() - ts;
+  st->result = r;
+  st->lambda = g->currentLambda;
+  st->levenberg_iterations = g->levenbergIterations;
+  return r;
+}
 int oracle_algorithm_init(oracle_graph* g) { return algorithm_init(g) ? 0 : -1; }
 int oracle_build_structure(oracle_graph* g) { return build_structure(g) ? 0 : -1; }
 double oracle_compute_active_errors(oracle_graph* g) { return compute_active_errors(g); }

@@ -65,6 +65,9 @@ void oracle_set_block_ordering(oracle_graph* g, int block_ordering);
 /* SparseOptimizer::optimize (core/sparse_optimizer.cpp:354-419); returns #iterations done (0 on Fail) */
 int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_stats* stats);
 
+/* one OptimizationAlgorithmLevenberg::solve(iteration) of a running optimisation; returns SolverResult */
+int oracle_lm_iteration(oracle_graph* g, int iteration, oracle_iter_stats* stats);
+
 /* ---- step-wise access to the same objects (for fine-grained parity tests) ---- */
 int oracle_algorithm_init(oracle_graph* g);             /* OptimizationAlgorithmWithHessian::init */
 int oracle_build_structure(oracle_graph* g);            /* BlockSolver::buildStructure */
