@@ -15,6 +15,9 @@
 
 namespace g2o_b200 {
 
+struct CholDev;
+struct CholPlanDev;
+
 class CholeskyGpu {
  public:
   CholeskyGpu() = default;
@@ -45,10 +48,14 @@ class CholeskyGpu {
   DevBuf<long long> d_a_dst_, d_diag_dst_;
   DevBuf<int> d_a_ld_, d_diag_ld_, d_perm_;
   DevBuf<unsigned char> d_a_trans_;
-  DevBuf<double> d_L_, d_y_;
+  DevBuf<int> d_tile_sn_, d_tile_r0_, d_tile_c0_, d_tile_work_ptr_, d_work_u_, d_work_a0_, d_work_a1_, d_work_b0_, d_work_b1_;
+  DevBuf<int> d_sn_tile_ptr_, d_sn_chunk_ptr_, d_chunk_sn_, d_chunk_b0_, d_chunk_nb_, d_level_tiles_, d_level_chunks_;
+  DevBuf<long long> d_sn_dinvptr_;
+  DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_;
   DevBuf<int> d_status_;
   int nblk_ = 0;
-  std::vector<int> level_threads_;  // CTA size per level
+  CholDev dev() const;
+  CholPlanDev plan() const;
 };
 
 }  // namespace g2o_b200

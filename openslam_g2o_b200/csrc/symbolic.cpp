@@ -302,7 +302,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     sub[s] += work[s];
     if (S.sn_parent[s] >= 0) sub[S.sn_parent[s]] += sub[s];
   }
-  const double thresh = std::max(S.flops * opt.subtree_work_fraction, 2.0e4);
+  const double thresh = std::max(S.flops * opt.subtree_work_fraction, opt.subtree_min_flops);
   // task id per supernode: a maximal subtree with sub <= thresh becomes one task (rooted at `root`)
   std::vector<int> root(ns, -1);
   for (int s = ns - 1; s >= 0; --s) {
@@ -339,6 +339,112 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     const std::vector<int>& t = tasks[order[q]];
     S.task_ptr[q + 1] = S.task_ptr[q] + (int)t.size();
     S.task_sn.insert(S.task_sn.end(), t.begin(), t.end());
+  }
+
+  // ---- 9. numeric plan: destination tiles + their work items, row chunks, level kinds
+  const int TB = std::max(1, 48 / d);
+  const int CHB = std::max(1, 96 / d);
+  S.tile_blocks = TB;
+  S.chunk_blocks = CHB;
+  S.sn_tile_ptr.assign(ns + 1, 0);
+  std::vector<std::vector<int>> tile_lookup(ns);  // [tr * nct + tc] -> tile id or -1
+  std::vector<int> sn_nct(ns, 0);
+  for (int J = 0; J < ns; ++J) {
+    const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = (S.sn_ncol[J] + TB - 1) / TB;
+    sn_nct[J] = nct;
+    tile_lookup[J].assign((size_t)ntr * nct, -1);
+    for (int tr = 0; tr < ntr; ++tr)
+      for (int tc = 0; tc < nct && tc <= tr; ++tc) {
+        tile_lookup[J][(size_t)tr * nct + tc] = (int)S.tile_sn.size();
+        S.tile_sn.push_back(J); S.tile_r0.push_back(tr * TB); S.tile_c0.push_back(tc * TB);
+      }
+    S.sn_tile_ptr[J + 1] = (int)S.tile_sn.size();
+  }
+  const int ntiles = (int)S.tile_sn.size();
+  S.tile_work_ptr.assign(ntiles + 1, 0);
+  {
+    std::vector<int> bound;
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<int> fill;
+      if (pass == 1) {
+        for (int t = 0; t < ntiles; ++t) S.tile_work_ptr[t + 1] += S.tile_work_ptr[t];
+        const int nw = S.tile_work_ptr[ntiles];
+        S.work_u.assign(nw, 0); S.work_a0.assign(nw, 0); S.work_a1.assign(nw, 0); S.work_b0.assign(nw, 0); S.work_b1.assign(nw, 0);
+        fill.assign(S.tile_work_ptr.begin(), S.tile_work_ptr.end() - 1);
+      }
+      for (int J = 0; J < ns; ++J) {
+        const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = sn_nct[J];
+        for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
+          const int K = S.upd_k[u];
+          const int h = S.sn_nrow[K] - S.upd_p0[u], w = S.upd_p1[u] - S.upd_p0[u];
+          const int* rel = S.rel.data() + S.upd_relptr[u];
+          bound.assign(ntr + 1, h);  // bound[t] = first a with rel[a] >= t*TB
+          int a = 0;
+          for (int t = 0; t <= ntr; ++t) {
+            while (a < h && rel[a] < t * TB) ++a;
+            bound[t] = a;
+          }
+          for (int tc = 0; tc < nct; ++tc) {
+            const int b0 = std::min(bound[tc], w), b1 = std::min(bound[tc + 1], w);
+            if (b0 >= b1) continue;
+            for (int tr = tc; tr < ntr; ++tr) {
+              const int a0 = bound[tr], a1 = bound[tr + 1];
+              if (a0 >= a1) continue;
+              if (a1 - 1 < b0) continue;  // entirely above the diagonal of the update
+              const int t = tile_lookup[J][(size_t)tr * nct + tc];
+              if (pass == 0) S.tile_work_ptr[t + 1]++;
+              else { int q = fill[t]++; S.work_u[q] = u; S.work_a0[q] = a0; S.work_a1[q] = a1; S.work_b0[q] = b0; S.work_b1[q] = b1; }
+            }
+          }
+        }
+      }
+    }
+  }
+  S.sn_chunk_ptr.assign(ns + 1, 0);
+  S.sn_dinvptr.assign(ns + 1, 0);
+  for (int J = 0; J < ns; ++J) {
+    const int below = S.sn_nrow[J] - S.sn_ncol[J];
+    int b0 = S.sn_ncol[J];
+    if (below == 0) { S.chunk_sn.push_back(J); S.chunk_b0.push_back(b0); S.chunk_nb.push_back(0); }
+    for (int rem = below; rem > 0;) {
+      const int nbk = std::min(rem, CHB);
+      S.chunk_sn.push_back(J); S.chunk_b0.push_back(b0); S.chunk_nb.push_back(nbk);
+      b0 += nbk; rem -= nbk;
+    }
+    S.sn_chunk_ptr[J + 1] = (int)S.chunk_sn.size();
+    S.sn_dinvptr[J + 1] = S.sn_dinvptr[J] + (int64_t)S.sn_ncol[J] * d * S.sn_ncol[J] * d;
+  }
+  S.dinv_doubles = S.sn_dinvptr[ns];
+  S.level_kind.assign(S.nlevels, 0);
+  S.level_smem.assign(S.nlevels, 0);
+  S.level_tile_ptr.assign(S.nlevels + 1, 0);
+  S.level_chunk_ptr.assign(S.nlevels + 1, 0);
+  for (int l = 0; l < S.nlevels; ++l) {
+    bool singletons = true;
+    int tiles = 0, chunks = 0, ntask = S.level_ptr[l + 1] - S.level_ptr[l], smem = 0;
+    for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+      if (S.task_ptr[t + 1] - S.task_ptr[t] != 1) singletons = false;
+      for (int q = S.task_ptr[t]; q < S.task_ptr[t + 1]; ++q) {
+        const int J = S.task_sn[q];
+        tiles += S.sn_tile_ptr[J + 1] - S.sn_tile_ptr[J];
+        chunks += S.sn_chunk_ptr[J + 1] - S.sn_chunk_ptr[J];
+        const int N = S.sn_ncol[J] * d;
+        const int rows = N + std::min(S.sn_nrow[J] - S.sn_ncol[J], CHB) * d;
+        smem = std::max(smem, rows * N * 8);
+      }
+    }
+    S.level_smem[l] = smem;
+    if (singletons && (tiles > ntask || chunks > ntask)) {
+      S.level_kind[l] = 1;
+      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+        const int J = S.task_sn[S.task_ptr[t]];
+        for (int q = S.sn_tile_ptr[J]; q < S.sn_tile_ptr[J + 1]; ++q)
+          if (S.tile_work_ptr[q + 1] > S.tile_work_ptr[q]) S.level_tiles.push_back(q);
+        for (int q = S.sn_chunk_ptr[J]; q < S.sn_chunk_ptr[J + 1]; ++q) S.level_chunks.push_back(q);
+      }
+    }
+    S.level_tile_ptr[l + 1] = (int)S.level_tiles.size();
+    S.level_chunk_ptr[l + 1] = (int)S.level_chunks.size();
   }
   return S;
 }

@@ -16,6 +16,7 @@ namespace g2o_b200 {
 struct SymbolicOptions {
   int max_panel_cols_scalar = 96;   // supernodes wider than this are split into a chain of panels
   double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
+  double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
   bool relax = true;
   // set when the caller already knows the ordering (tests); empty = run block AMD
   std::vector<int> given_perm;
@@ -52,6 +53,25 @@ struct SymbolicFactor {
   int64_t factor_doubles = 0;
   double flops = 0;  // factorisation flops of the stored (relaxed) structure
   int max_nrow = 0, max_ncol = 0;
+
+  // ---- numeric plan of the GPU kernels (chol.cu)
+  // destination tiles: a panel is cut into tile_blocks x tile_blocks block tiles (48 x 48 scalars); only tiles that
+  // touch the lower triangle exist.  Each tile owns the list of update pieces (work items) that land in it.
+  int tile_blocks = 0;
+  std::vector<int> sn_tile_ptr;                    // nsn+1
+  std::vector<int> tile_sn, tile_r0, tile_c0;      // supernode, first local block row / block column
+  std::vector<int> tile_work_ptr;                  // ntiles+1
+  std::vector<int> work_u, work_a0, work_a1, work_b0, work_b1;  // update index; row / column ranges relative to p0
+  // row chunks of the panel factorisation: every chunk CTA factors the diagonal block and solves its block rows
+  int chunk_blocks = 0;
+  std::vector<int> sn_chunk_ptr;                   // nsn+1
+  std::vector<int> chunk_sn, chunk_b0, chunk_nb;   // supernode, first local block row (>= ncol), #block rows
+  // level plan: kind 0 = fused (one CTA per task does update + factor), 1 = split (tiles kernel, then chunks kernel)
+  std::vector<int> level_kind, level_smem;         // dynamic shared memory (bytes) the level's factor kernel needs
+  std::vector<int> level_tile_ptr, level_tiles, level_chunk_ptr, level_chunks;
+  // inverses of the triangular diagonal blocks (for the solves)
+  std::vector<int64_t> sn_dinvptr;                 // nsn+1
+  int64_t dinv_doubles = 0;
 };
 
 // colptr/rowidx: upper block pattern (rows <= col, ascending, diagonal present) in input block order.

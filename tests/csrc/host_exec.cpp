@@ -46,27 +46,48 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
     double* P = L.data() + S.sn_lptr[J];
     const int M = S.sn_nrow[J] * d, N = S.sn_ncol[J] * d;
     const int* jrows = S.sn_rows.data() + S.sn_rowptr[J];
-    for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
-      int K = S.upd_k[u], p0 = S.upd_p0[u], p1 = S.upd_p1[u];
-      if (!done[K]) return -2;  // schedule violation
-      const double* Kp = L.data() + S.sn_lptr[K];
-      const int Mk = S.sn_nrow[K] * d, Nk = S.sn_ncol[K] * d;
-      const int* krows = S.sn_rows.data() + S.sn_rowptr[K];
-      const int* rel = S.rel.data() + S.upd_relptr[u];
-      for (int pc = p0; pc < p1; ++pc) {
-        int lc = krows[pc] - S.sn_col0[J];
-        if (jrows[rel[pc - p0]] != krows[pc]) return -3;
-        for (int pr = pc; pr < S.sn_nrow[K]; ++pr) {
-          int lr = rel[pr - p0];
-          if (jrows[lr] != krows[pr]) return -3;
-          for (int cc = 0; cc < d; ++cc)
-            for (int rr = 0; rr < d; ++rr) {
-              double s = 0;
-              for (int k = 0; k < Nk; ++k) s += Kp[pr * d + rr + (size_t)k * Mk] * Kp[pc * d + cc + (size_t)k * Mk];
-              P[lr * d + rr + (size_t)(lc * d + cc) * M] -= s;
-            }
-        }
+    // the GPU's update plan: destination tiles, each with its ordered list of work items
+    const int TB = S.tile_blocks;
+    for (int tile = S.sn_tile_ptr[J]; tile < S.sn_tile_ptr[J + 1]; ++tile) {
+      if (S.tile_sn[tile] != J) return -5;
+      const int R0 = S.tile_r0[tile], C0 = S.tile_c0[tile];
+      std::vector<double> acc((size_t)TB * d * TB * d, 0.0);
+      const int TS = TB * d;
+      for (int wi = S.tile_work_ptr[tile]; wi < S.tile_work_ptr[tile + 1]; ++wi) {
+        const int u = S.work_u[wi];
+        if (u < S.upd_ptr[J] || u >= S.upd_ptr[J + 1]) return -6;
+        const int K = S.upd_k[u], p0 = S.upd_p0[u];
+        if (!done[K]) return -2;  // schedule violation
+        const double* Kp = L.data() + S.sn_lptr[K];
+        const int Mk = S.sn_nrow[K] * d, Nk = S.sn_ncol[K] * d;
+        const int* krows = S.sn_rows.data() + S.sn_rowptr[K];
+        const int* rel = S.rel.data() + S.upd_relptr[u];
+        for (int b = S.work_b0[wi]; b < S.work_b1[wi]; ++b)
+          for (int a = S.work_a0[wi]; a < S.work_a1[wi]; ++a) {
+            if (a < b) continue;
+            if (jrows[rel[a]] != krows[p0 + a] || jrows[rel[b]] != krows[p0 + b]) return -3;
+            const int tr = (rel[a] - R0) * d, tc = (rel[b] - C0) * d;
+            if (tr < 0 || tr + d > TS || tc < 0 || tc + d > TS) return -7;
+            for (int cc = 0; cc < d; ++cc)
+              for (int rr = 0; rr < d; ++rr) {
+                double s = 0;
+                for (int k = 0; k < Nk; ++k) s += Kp[(p0 + a) * d + rr + (size_t)k * Mk] * Kp[(p0 + b) * d + cc + (size_t)k * Mk];
+                acc[tr + rr + (size_t)(tc + cc) * TS] += s;
+              }
+          }
       }
+      const int rows = std::min(TS, M - R0 * d), cols = std::min(TS, N - C0 * d);
+      for (int c = 0; c < cols; ++c)
+        for (int r = 0; r < rows; ++r) P[R0 * d + r + (size_t)(C0 * d + c) * M] -= acc[r + (size_t)c * TS];
+    }
+    // the chunk plan must cover every block row below the diagonal block exactly once
+    {
+      int expect = S.sn_ncol[J];
+      for (int ch = S.sn_chunk_ptr[J]; ch < S.sn_chunk_ptr[J + 1]; ++ch) {
+        if (S.chunk_sn[ch] != J || S.chunk_b0[ch] != expect || S.chunk_nb[ch] > S.chunk_blocks) return -8;
+        expect += S.chunk_nb[ch];
+      }
+      if (expect != S.sn_nrow[J]) return -8;
     }
     for (int j = 0; j < N; ++j) {
       double dj = P[j + (size_t)j * M];
