@@ -143,7 +143,9 @@ int64_t b200_get_launch_count(b200_ctx* ctx);
 int b200_set_profiling(b200_ctx* ctx, int on);
 /* kernel-group id: 0 errors+chi2, 1 linearize (edges / per-landmark), 2 schur reduce, 3 cholesky factor,
  * 4 triangular solves, 5 oplus update, 6 landmark back-substitution, 7 linearize per-camera, 8 ordered gather,
- * 9 landmark inverses, 10 LM scale, 11 collective; returns accumulated seconds and #occurrences */
+ * 9 landmark inverses, 10 LM scale, 11 collective; inside the Cholesky: 12 scatter, 13 tile updates, 14 split-K
+ * reduce, 15 panel factor, 16 fused subtree tasks, 17 diagonal inverses, 18 forward solve, 19 backward solve.
+ * Profiling turns CUDA-graph replay off.  returns accumulated seconds and #occurrences */
 int b200_get_phase_time(b200_ctx* ctx, int phase, double* seconds, int64_t* count);
 
 /* ------------------------------------------------------------------ Level 1: g2o::LinearSolver<MatrixType>

@@ -59,39 +59,52 @@ __global__ void chol_add_lambda_kernel(int nb, const long long* __restrict__ dia
 // level-scheduled with the two phases as separate multi-CTA kernels.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTile = 48;        // scalar rows / cols of a destination tile
+constexpr int kMaxPanelCols = 96;
 constexpr int kCholThreads = 256;
+constexpr int kUpdateSmemDoubles = kTile * kTile + 2 * kTile * kMaxPanelCols;  // acc | A rows | B rows
 
 struct CholPlanDev {
   const int *tile_sn, *tile_r0, *tile_c0, *tile_work_ptr;
   const int *work_u, *work_a0, *work_a1, *work_b0, *work_b1;
   const int *sn_tile_ptr, *sn_chunk_ptr, *chunk_sn, *chunk_b0, *chunk_nb;
-  const long long* sn_dinvptr;
+  const long long *sn_dinvptr, *sn_cptr;
 };
 
+// acc (shared, kTile x kTile) = sum over work items [w0,w1) of the tile, in list order.
+// Operand rows of the updating panel are staged in shared memory with coalesced loads; every thread then owns
+// 3x3 micro tiles of the product.
 template <int D>
-__device__ void update_tile(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, int tile,
-                            double* __restrict__ acc /* kTile*kTile shared */) {
-  constexpr int S = D / 3;  // 3x3 micro blocks per block edge
+__device__ void accumulate_items(const CholDev& P, const CholPlanDev& Q, const double* __restrict__ L, int w0, int w1,
+                                 int R0, int C0, double* __restrict__ acc, double* __restrict__ As,
+                                 double* __restrict__ Bs) {
+  constexpr int S = D / 3;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int w0 = Q.tile_work_ptr[tile], w1 = Q.tile_work_ptr[tile + 1];
-  if (w0 == w1) return;
-  const int J = Q.tile_sn[tile], R0 = Q.tile_r0[tile], C0 = Q.tile_c0[tile];
   for (int i = tid; i < kTile * kTile; i += nt) acc[i] = 0.0;
-  __syncthreads();
   for (int wi = w0; wi < w1; ++wi) {
     const int u = Q.work_u[wi];
-    const int a0 = Q.work_a0[wi] * S, a1 = Q.work_a1[wi] * S, b0 = Q.work_b0[wi] * S, b1 = Q.work_b1[wi] * S;
+    const int a0 = Q.work_a0[wi], a1 = Q.work_a1[wi], b0 = Q.work_b0[wi], b1 = Q.work_b1[wi];
     const int K = P.upd_k[u], p0 = P.upd_p0[u];
     const int Mk = P.sn_nrow[K] * D, Nk = P.sn_ncol[K] * D;
     const double* Kp = L + P.sn_lptr[K] + (long long)p0 * D;
     const int* rel = P.rel + P.upd_relptr[u];
-    const int na = a1 - a0, nb = b1 - b0;
+    const int nA = (a1 - a0) * D, nB = (b1 - b0) * D;
+    __syncthreads();  // previous item's operands fully consumed, acc zeroing done
+    for (int i = tid; i < nA * Nk; i += nt) {
+      const int k = i / nA, r = i - k * nA;
+      As[r + k * kTile] = Kp[a0 * D + r + (long long)k * Mk];
+    }
+    for (int i = tid; i < nB * Nk; i += nt) {
+      const int k = i / nB, r = i - k * nB;
+      Bs[r + k * kTile] = Kp[b0 * D + r + (long long)k * Mk];
+    }
+    __syncthreads();
+    const int na = (a1 - a0) * S, nb = (b1 - b0) * S;
     for (int idx = tid; idx < na * nb; idx += nt) {
-      const int mb = b0 + idx / na;
-      const int ma = a0 + idx % na;
+      const int j = idx / na, i = idx - j * na;
+      const int ma = a0 * S + i, mb = b0 * S + j;
       if (ma < mb) continue;
-      const double* ra = Kp + ma * 3;
-      const double* rb = Kp + mb * 3;
+      const double* ra = As + i * 3;
+      const double* rb = Bs + j * 3;
       double c00 = 0, c01 = 0, c02 = 0, c10 = 0, c11 = 0, c12 = 0, c20 = 0, c21 = 0, c22 = 0;
 #pragma unroll 4
       for (int k = 0; k < Nk; ++k) {
@@ -100,8 +113,8 @@ __device__ void update_tile(const CholDev& P, const CholPlanDev& Q, double* __re
         c00 = fma(x0, y0, c00); c01 = fma(x0, y1, c01); c02 = fma(x0, y2, c02);
         c10 = fma(x1, y0, c10); c11 = fma(x1, y1, c11); c12 = fma(x1, y2, c12);
         c20 = fma(x2, y0, c20); c21 = fma(x2, y1, c21); c22 = fma(x2, y2, c22);
-        ra += Mk;
-        rb += Mk;
+        ra += kTile;
+        rb += kTile;
       }
       const int ab = ma / S, bb = mb / S;
       const int tr = (rel[ab] - R0) * D + (ma - ab * S) * 3;
@@ -111,16 +124,21 @@ __device__ void update_tile(const CholDev& P, const CholPlanDev& Q, double* __re
       dst[kTile] += c01; dst[kTile + 1] += c11; dst[kTile + 2] += c21;
       dst[2 * kTile] += c02; dst[2 * kTile + 1] += c12; dst[2 * kTile + 2] += c22;
     }
-    __syncthreads();
   }
+  __syncthreads();
+}
+
+template <int D>
+__device__ void subtract_tile(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, int tile,
+                              const double* __restrict__ acc) {
+  const int J = Q.tile_sn[tile], R0 = Q.tile_r0[tile], C0 = Q.tile_c0[tile];
   const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
   double* Pj = L + P.sn_lptr[J];
   const int rows = min(kTile, M - R0 * D), cols = min(kTile, N - C0 * D);
-  for (int i = tid; i < rows * cols; i += nt) {
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
     const int c = i / rows, r = i - c * rows;
     Pj[(long long)(R0 * D + r) + (long long)(C0 * D + c) * M] -= acc[r + c * kTile];
   }
-  __syncthreads();
 }
 
 template <int D>
@@ -132,6 +150,7 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
   const int crow0 = Q.chunk_b0[chunk] * D, crows = Q.chunk_nb[chunk] * D;
   const int R = N + crows;  // rows staged: the diagonal block, then this chunk's rows
   double* Pj = L + P.sn_lptr[J];
+  __syncthreads();
   for (int i = tid; i < R * N; i += nt) {
     const int c = i / R, r = i - c * R;
     const int gr = r < N ? r : crow0 + (r - N);
@@ -144,7 +163,7 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
   for (int jb = 0; jb < ncb; ++jb) {
     const int j0 = jb * D;
     // pivot block (already carries every earlier update): factor redundantly in registers
-    double Lp[D][D];
+    double Lp[D][D], inv[D];
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
@@ -157,12 +176,13 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
       if (!(s > 0.0)) { bad = true; s = 1.0; }  // d <= 0: not positive definite (csparse_helper.cpp:136)
       const double lkk = sqrt(s);
       Lp[k][k] = lkk;
+      inv[k] = 1.0 / lkk;
 #pragma unroll
       for (int r = k + 1; r < D; ++r) {
         double t = Lp[r][k];
 #pragma unroll
         for (int m = 0; m < k; ++m) t = fma(-Lp[r][m], Lp[k][m], t);
-        Lp[r][k] = t / lkk;
+        Lp[r][k] = t * inv[k];
       }
     }
     double x[D];
@@ -183,7 +203,7 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
         double t = x[c];
 #pragma unroll
         for (int m = 0; m < c; ++m) t = fma(-x[m], Lp[c][m], t);
-        x[c] = t / Lp[c][c];
+        x[c] = t * inv[c];
       }
 #pragma unroll
       for (int c = 0; c < D; ++c) Sm[row + (j0 + c) * R] = x[c];
@@ -191,7 +211,18 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
     __syncthreads();
     if (below) {
       const int cend = row < N ? row : N - 1;
-      for (int c = j0 + D; c <= cend; ++c) {
+      int c = j0 + D;
+      for (; c + 3 <= cend; c += 4) {  // 4 independent accumulators: hide the FP64 FMA latency
+        double v0 = Sm[row + c * R], v1 = Sm[row + (c + 1) * R], v2 = Sm[row + (c + 2) * R], v3 = Sm[row + (c + 3) * R];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double xk = x[k];
+          const double* lr = Sm + c + (j0 + k) * R;
+          v0 = fma(-xk, lr[0], v0); v1 = fma(-xk, lr[1], v1); v2 = fma(-xk, lr[2], v2); v3 = fma(-xk, lr[3], v3);
+        }
+        Sm[row + c * R] = v0; Sm[row + (c + 1) * R] = v1; Sm[row + (c + 2) * R] = v2; Sm[row + (c + 3) * R] = v3;
+      }
+      for (; c <= cend; ++c) {
         double v = Sm[row + c * R];
 #pragma unroll
         for (int k = 0; k < D; ++k) v = fma(-x[k], Sm[c + (j0 + k) * R], v);
@@ -211,28 +242,69 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
       Pj[crow0 + (r - N) + (long long)c * M] = Sm[i];
     }
   }
-  __syncthreads();
 }
 
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
 chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag, int task0, int* status) {
-  extern __shared__ __align__(16) double smem[];
-  double* acc = smem;                    // kTile*kTile
-  double* Sm = smem + kTile * kTile;     // factor staging
+  extern __shared__ __align__(16) double smem[];  // update operands and factor staging share the same bytes
+  double* acc = smem;
+  double* As = smem + kTile * kTile;
+  double* Bs = As + kTile * kMaxPanelCols;
   const int t = task0 + blockIdx.x;
   for (int q = P.task_ptr[t]; q < P.task_ptr[t + 1]; ++q) {
     const int J = P.task_sn[q];
-    for (int tile = Q.sn_tile_ptr[J]; tile < Q.sn_tile_ptr[J + 1]; ++tile) update_tile<D>(P, Q, L, tile, acc);
+    for (int tile = Q.sn_tile_ptr[J]; tile < Q.sn_tile_ptr[J + 1]; ++tile) {
+      const int w0 = Q.tile_work_ptr[tile], w1 = Q.tile_work_ptr[tile + 1];
+      if (w0 == w1) continue;
+      accumulate_items<D>(P, Q, L, w0, w1, Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs);
+      subtract_tile<D>(P, Q, L, tile, acc);
+      __syncthreads();
+    }
     const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
-    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, Sm, status);
+    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, smem, status);
+    __syncthreads();
   }
 }
+
+// split levels, phase 1: one CTA per (tile, split-K group)
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
-chol_update_tiles_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const int* __restrict__ tiles) {
+chol_update_groups_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const int* __restrict__ g_tile,
+                          const int* __restrict__ g_w0, const int* __restrict__ g_w1, const int* __restrict__ g_slot,
+                          double* __restrict__ scratch) {
+  extern __shared__ __align__(16) double smem[];
+  double* acc = smem;
+  double* As = smem + kTile * kTile;
+  double* Bs = As + kTile * kMaxPanelCols;
+  const int g = blockIdx.x;
+  const int tile = g_tile[g];
+  accumulate_items<D>(P, Q, L, g_w0[g], g_w1[g], Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs);
+  const int slot = g_slot[g];
+  if (slot < 0) {
+    subtract_tile<D>(P, Q, L, tile, acc);
+  } else {
+    double* out = scratch + (long long)slot * kTile * kTile;
+    for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) out[i] = acc[i];
+  }
+}
+// split levels, phase 1b: tiles cut into several groups: add the partial sums in group order, subtract once
+template <int D>
+__global__ void __launch_bounds__(kCholThreads)
+chol_reduce_tiles_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const int* __restrict__ r_tile,
+                         const int* __restrict__ r_slot0, const int* __restrict__ r_nslots,
+                         const double* __restrict__ scratch) {
   __shared__ __align__(16) double acc[kTile * kTile];
-  update_tile<D>(P, Q, L, tiles[blockIdx.x], acc);
+  const int t = blockIdx.x;
+  const double* in = scratch + (long long)r_slot0[t] * kTile * kTile;
+  const int ns = r_nslots[t];
+  for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) {
+    double s = 0.0;
+    for (int g = 0; g < ns; ++g) s += in[(long long)g * kTile * kTile + i];
+    acc[i] = s;
+  }
+  __syncthreads();
+  subtract_tile<D>(P, Q, L, r_tile[t], acc);
 }
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
@@ -243,26 +315,36 @@ chol_factor_chunks_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, doub
   factor_chunk<D>(P, Q, L, Ldiag, ch, ch == Q.sn_chunk_ptr[Q.chunk_sn[ch]], smem, status);
 }
 
-// inverse of every triangular diagonal block (one CTA per supernode): the solves become matrix-vector products
+// inverse of every triangular diagonal block (one CTA per supernode): the solves become matrix-vector products.
+// Zt holds the inverse transposed (Zt[j + k*N] = inv(k,j)) so that thread j walks its column conflict-free.
 template <int D>
 __global__ void __launch_bounds__(128)
 chol_invert_diag_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ Ldiag, double* __restrict__ Dinv) {
-  extern __shared__ __align__(16) double Ls[];  // N*N
+  extern __shared__ __align__(16) double sm[];
   const int J = blockIdx.x;
   const int N = P.sn_ncol[J] * D;
+  double* Ls = sm;           // N*N, Ls[i + k*N]
+  double* Zt = sm + N * N;   // N*N
   const double* Lj = Ldiag + Q.sn_dinvptr[J];
   double* out = Dinv + Q.sn_dinvptr[J];
   for (int i = threadIdx.x; i < N * N; i += blockDim.x) Ls[i] = Lj[i];
   __syncthreads();
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    // column j of the inverse: solve L z = e_j by forward substitution, z stored in place in `out`
-    double* z = out + (long long)j * N;
-    for (int i = 0; i < j; ++i) z[i] = 0.0;
     for (int i = j; i < N; ++i) {
-      double s = (i == j) ? 1.0 : 0.0;
-      for (int k = j; k < i; ++k) s = fma(-Ls[i + k * N], z[k], s);
-      z[i] = s / Ls[i + i * N];
+      double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0;
+      int k = j;
+      for (; k + 1 < i; k += 2) {
+        s0 = fma(-Ls[i + k * N], Zt[j + k * N], s0);
+        s1 = fma(-Ls[i + (k + 1) * N], Zt[j + (k + 1) * N], s1);
+      }
+      if (k < i) s0 = fma(-Ls[i + k * N], Zt[j + k * N], s0);
+      Zt[j + i * N] = (s0 + s1) / Ls[i + i * N];
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+    const int c = i / N, r = i - c * N;  // out(r,c) = inv(r,c) = Zt[c + r*N]
+    out[i] = r >= c ? Zt[c + r * N] : 0.0;
   }
 }
 
@@ -287,45 +369,62 @@ __global__ void chol_permute_out_kernel(int nb, const int* __restrict__ perm, co
   x[perm[k] * D + r] = y[idx];
 }
 
-constexpr int kMaxPanelCols = 96;
-
+// forward: y_J = Linv (P b - contributions of the descendants); every supernode then leaves c_J = L21 y_J in its own
+// scratch segment, so ancestors only add precomputed numbers (in update order -> deterministic) and L is read once,
+// coalesced, by its owner.
 template <int D>
 __global__ void __launch_bounds__(128)
 chol_forward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
-                    double* __restrict__ y, int task0) {
+                    double* __restrict__ y, double* __restrict__ contrib, int task0) {
   __shared__ double tvec[kMaxPanelCols];
+  __shared__ double yv[kMaxPanelCols];
   const int t = task0 + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int q = P.task_ptr[t]; q < P.task_ptr[t + 1]; ++q) {
     const int J = P.task_sn[q];
     const int col0 = P.sn_col0[J];
-    const int N = P.sn_ncol[J] * D;
+    const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
     double* yj = y + (long long)col0 * D;
+    __syncthreads();
     for (int i = tid; i < N; i += nt) tvec[i] = yj[i];
     __syncthreads();
     for (int u = P.upd_ptr[J]; u < P.upd_ptr[J + 1]; ++u) {
       const int K = P.upd_k[u], p0 = P.upd_p0[u], p1 = P.upd_p1[u];
-      const int Mk = P.sn_nrow[K] * D, Nk = P.sn_ncol[K] * D;
-      const double* Kp = L + P.sn_lptr[K];
       const int* krows = P.sn_rows + P.sn_rowptr[K];
-      const double* yk = y + (long long)P.sn_col0[K] * D;
+      const double* ck = contrib + Q.sn_cptr[K] - (long long)P.sn_ncol[K] * D;  // indexed by panel row
       const int nrow = (p1 - p0) * D;
       for (int i = tid; i < nrow; i += nt) {
         const int p = p0 + i / D, rr = i % D;
-        const double* lrow = Kp + p * D + rr;
-        double s = 0.0;
-        for (int k = 0; k < Nk; ++k) s = fma(lrow[(long long)k * Mk], yk[k], s);
-        tvec[(krows[p] - col0) * D + rr] -= s;
+        tvec[(krows[p] - col0) * D + rr] -= ck[p * D + rr];
       }
       __syncthreads();
     }
     const double* Di = Dinv + Q.sn_dinvptr[J];
     for (int i = tid; i < N; i += nt) {
-      double s = 0.0;
-      for (int j = 0; j <= i; ++j) s = fma(Di[i + (long long)j * N], tvec[j], s);
-      yj[i] = s;
+      double s0 = 0.0, s1 = 0.0;
+      int j = 0;
+      for (; j + 1 <= i; j += 2) {
+        s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
+        s1 = fma(Di[i + (long long)(j + 1) * N], tvec[j + 1], s1);
+      }
+      if (j <= i) s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
+      const double v = s0 + s1;
+      yj[i] = v;
+      yv[i] = v;
     }
     __syncthreads();
+    const double* Pj = L + P.sn_lptr[J];
+    double* cj = contrib + Q.sn_cptr[J];
+    for (int r = N + tid; r < M; r += nt) {
+      double s0 = 0.0, s1 = 0.0;
+      int k = 0;
+      for (; k + 1 < N; k += 2) {
+        s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
+        s1 = fma(Pj[r + (long long)(k + 1) * M], yv[k + 1], s1);
+      }
+      if (k < N) s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
+      cj[r - N] = s0 + s1;
+    }
   }
 }
 
@@ -333,6 +432,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
                      double* __restrict__ y, int task0) {
+  extern __shared__ __align__(16) double xb[];  // x at the rows below the diagonal block
   __shared__ double tvec[kMaxPanelCols];
   const int t = task0 + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -340,15 +440,19 @@ chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, con
   for (int q = P.task_ptr[t + 1] - 1; q >= P.task_ptr[t]; --q) {
     const int J = P.task_sn[q];
     const int col0 = P.sn_col0[J];
-    const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
+    const int nc = P.sn_ncol[J], nr = P.sn_nrow[J];
+    const int M = nr * D, N = nc * D;
     const double* Pj = L + P.sn_lptr[J];
     const int* jrows = P.sn_rows + P.sn_rowptr[J];
     double* xj = y + (long long)col0 * D;
+    __syncthreads();
+    for (int i = tid; i < M - N; i += nt) xb[i] = y[(long long)jrows[nc + i / D] * D + (i % D)];
+    __syncthreads();
     // t = y_J - L21^T x_below : one warp per column, lanes stride the rows (coalesced), fixed-order shuffle tree
     for (int j = wid; j < N; j += nw) {
-      const double* cj = Pj + (long long)j * M;
+      const double* cj = Pj + (long long)j * M + N;
       double s = 0.0;
-      for (int i = N + lane; i < M; i += 32) s = fma(cj[i], y[(long long)jrows[i / D] * D + (i % D)], s);
+      for (int i = lane; i < M - N; i += 32) s = fma(cj[i], xb[i], s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) tvec[j] = xj[j] - s;
@@ -356,12 +460,13 @@ chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, con
     __syncthreads();
     const double* Di = Dinv + Q.sn_dinvptr[J];
     for (int i = tid; i < N; i += nt) {  // x_J = Linv^T t
-      double s = 0.0;
       const double* ci = Di + (long long)i * N;
-      for (int j = i; j < N; ++j) s = fma(ci[j], tvec[j], s);
-      xj[i] = s;
+      double s0 = 0.0, s1 = 0.0;
+      int j = i;
+      for (; j + 1 < N; j += 2) { s0 = fma(ci[j], tvec[j], s0); s1 = fma(ci[j + 1], tvec[j + 1], s1); }
+      if (j < N) s0 = fma(ci[j], tvec[j], s0);
+      xj[i] = s0 + s1;
     }
-    __syncthreads();
   }
 }
 
@@ -382,10 +487,15 @@ void set_smem_attrs() {
   static bool done = false;
   if (done) return;
   B200_CUDA(cudaFuncSetAttribute(chol_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_update_groups_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_factor_chunks_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_invert_diag_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   done = true;
 }
+// profiler ids of the kernel groups inside the Cholesky (continue the numbering of solver.cu)
+enum { PH_CH_SCATTER = 12, PH_CH_UPDATE = 13, PH_CH_REDUCE = 14, PH_CH_PANEL = 15, PH_CH_FUSED = 16, PH_CH_INVERT = 17,
+       PH_CH_FORWARD = 18, PH_CH_BACKWARD = 19 };
 }  // namespace
 
 void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt,
@@ -410,11 +520,17 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_work_b0_.upload(S_.work_b0, s); d_work_b1_.upload(S_.work_b1, s);
   d_sn_tile_ptr_.upload(S_.sn_tile_ptr, s); d_sn_chunk_ptr_.upload(S_.sn_chunk_ptr, s);
   d_chunk_sn_.upload(S_.chunk_sn, s); d_chunk_b0_.upload(S_.chunk_b0, s); d_chunk_nb_.upload(S_.chunk_nb, s);
-  d_level_tiles_.upload(S_.level_tiles, s); d_level_chunks_.upload(S_.level_chunks, s);
+  d_level_chunks_.upload(S_.level_chunks, s);
+  d_group_tile_.upload(S_.group_tile, s); d_group_w0_.upload(S_.group_w0, s); d_group_w1_.upload(S_.group_w1, s);
+  d_group_slot_.upload(S_.group_slot, s);
+  d_rtile_tile_.upload(S_.rtile_tile, s); d_rtile_slot0_.upload(S_.rtile_slot0, s); d_rtile_nslots_.upload(S_.rtile_nslots, s);
   up64(d_sn_dinvptr_, S_.sn_dinvptr, s, keep);
+  up64(d_sn_cptr_, S_.sn_cptr, s, keep);
   d_L_.alloc((size_t)S_.factor_doubles);
   d_Dinv_.alloc((size_t)S_.dinv_doubles);
   d_Ldiag_.alloc((size_t)S_.dinv_doubles);
+  d_gscratch_.alloc((size_t)std::max(S_.max_group_slots, 1) * kTile * kTile);
+  d_contrib_.alloc((size_t)std::max<int64_t>(S_.sn_cptr[S_.nsn], 1));
   d_y_.alloc((size_t)nb * d);
   d_status_.alloc(1);
   if (!host_only_flag()) {
@@ -424,43 +540,6 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   analyzed_ = true;
 }
 
-template <int D>
-static void factor_t(const SymbolicFactor& S, const CholDev& P, const CholPlanDev& Q, int nblk, const double* dA,
-                     const double* d_lambda, const long long* a_dst, const int* a_ld, const unsigned char* a_trans,
-                     const long long* diag_dst, const int* diag_ld, double* L, double* Ldiag, double* Dinv, const int* level_tiles,
-                     const int* level_chunks, int* status, cudaStream_t s, LaunchCounter* lc) {
-  B200_CUDA(cudaMemsetAsync(L, 0, (size_t)S.factor_doubles * sizeof(double), s));
-  B200_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
-  chol_scatter_kernel<D><<<ceil_div((int64_t)nblk * D * D, 256), 256, 0, s>>>(dA, nblk, a_dst, a_ld, a_trans, L);
-  if (lc) lc->n++;
-  if (d_lambda) {
-    chol_add_lambda_kernel<D><<<ceil_div((int64_t)S.nb * D, 256), 256, 0, s>>>(S.nb, diag_dst, diag_ld, d_lambda, L);
-    if (lc) lc->n++;
-  }
-  for (int l = 0; l < S.nlevels; ++l) {
-    const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
-    if (nt == 0) continue;
-    if (S.level_kind[l] == 0) {
-      const size_t smem = (size_t)kTile * kTile * 8 + S.level_smem[l];
-      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, Ldiag, t0, status);
-      if (lc) lc->n++;
-    } else {
-      const int ntile = S.level_tile_ptr[l + 1] - S.level_tile_ptr[l];
-      const int nchunk = S.level_chunk_ptr[l + 1] - S.level_chunk_ptr[l];
-      if (ntile > 0) {
-        chol_update_tiles_kernel<D><<<ntile, kCholThreads, 0, s>>>(P, Q, L, level_tiles + S.level_tile_ptr[l]);
-        if (lc) lc->n++;
-      }
-      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l], s>>>(P, Q, L, Ldiag, level_chunks + S.level_chunk_ptr[l], status);
-      if (lc) lc->n++;
-    }
-  }
-  const size_t ismem = (size_t)S.max_ncol * D * S.max_ncol * D * 8;
-  chol_invert_diag_kernel<D><<<S.nsn, 128, ismem, s>>>(P, Q, Ldiag, Dinv);
-  if (lc) lc->n++;
-  B200_CUDA(cudaGetLastError());
-}
-
 CholDev CholeskyGpu::dev() const {
   return CholDev{d_sn_col0_.p, d_sn_ncol_.p, d_sn_nrow_.p, d_sn_rowptr_.p, d_sn_rows_.p, d_sn_lptr_.p, d_upd_ptr_.p,
                  d_upd_k_.p,   d_upd_p0_.p,  d_upd_p1_.p,  d_upd_relptr_.p, d_rel_.p,    d_task_ptr_.p, d_task_sn_.p};
@@ -468,49 +547,109 @@ CholDev CholeskyGpu::dev() const {
 CholPlanDev CholeskyGpu::plan() const {
   return CholPlanDev{d_tile_sn_.p, d_tile_r0_.p, d_tile_c0_.p, d_tile_work_ptr_.p, d_work_u_.p, d_work_a0_.p, d_work_a1_.p,
                      d_work_b0_.p, d_work_b1_.p, d_sn_tile_ptr_.p, d_sn_chunk_ptr_.p, d_chunk_sn_.p, d_chunk_b0_.p,
-                     d_chunk_nb_.p, d_sn_dinvptr_.p};
-}
-
-void CholeskyGpu::factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc) {
-  const CholDev P = dev();
-  const CholPlanDev Q = plan();
-  if (S_.d == 3)
-    factor_t<3>(S_, P, Q, nblk_, dA, d_lambda, d_a_dst_.p, d_a_ld_.p, d_a_trans_.p, d_diag_dst_.p, d_diag_ld_.p, d_L_.p,
-                d_Ldiag_.p, d_Dinv_.p, d_level_tiles_.p, d_level_chunks_.p, d_status_.p, s, lc);
-  else
-    factor_t<6>(S_, P, Q, nblk_, dA, d_lambda, d_a_dst_.p, d_a_ld_.p, d_a_trans_.p, d_diag_dst_.p, d_diag_ld_.p, d_L_.p,
-                d_Ldiag_.p, d_Dinv_.p, d_level_tiles_.p, d_level_chunks_.p, d_status_.p, s, lc);
+                     d_chunk_nb_.p, d_sn_dinvptr_.p, d_sn_cptr_.p};
 }
 
 template <int D>
-static void solve_t(const SymbolicFactor& S, const CholDev& P, const CholPlanDev& Q, const int* perm, const double* L,
-                    const double* Dinv, double* y, const double* b, double* x, const int* status, cudaStream_t s,
-                    LaunchCounter* lc) {
-  const int n = S.nb * D;
-  chol_permute_in_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, perm, b, y);
-  if (lc) lc->n++;
+void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
+  const SymbolicFactor& S = S_;
+  const CholDev P = dev();
+  const CholPlanDev Q = plan();
+  double* L = d_L_.p;
+  int* status = d_status_.p;
+  auto count = [&](int n = 1) { if (lc) lc->n += n; };
+  {
+    ScopedPhase ph(prof, PH_CH_SCATTER);
+    B200_CUDA(cudaMemsetAsync(L, 0, (size_t)S.factor_doubles * sizeof(double), s));
+    B200_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+    chol_scatter_kernel<D><<<ceil_div((int64_t)nblk_ * D * D, 256), 256, 0, s>>>(dA, nblk_, d_a_dst_.p, d_a_ld_.p, d_a_trans_.p, L);
+    count();
+    if (d_lambda) {
+      chol_add_lambda_kernel<D><<<ceil_div((int64_t)S.nb * D, 256), 256, 0, s>>>(S.nb, d_diag_dst_.p, d_diag_ld_.p, d_lambda, L);
+      count();
+    }
+  }
+  const size_t upd_smem = (size_t)kUpdateSmemDoubles * sizeof(double);
   for (int l = 0; l < S.nlevels; ++l) {
     const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
     if (nt == 0) continue;
-    chol_forward_kernel<D><<<nt, 128, 0, s>>>(P, Q, L, Dinv, y, t0);
-    if (lc) lc->n++;
+    if (S.level_kind[l] == 0) {
+      ScopedPhase ph(prof, PH_CH_FUSED);
+      const size_t smem = std::max(upd_smem, (size_t)S.level_smem[l]);
+      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, d_Ldiag_.p, t0, status);
+      count();
+    } else {
+      const int g0 = S.level_group_ptr[l], ng = S.level_group_ptr[l + 1] - g0;
+      const int r0 = S.level_rtile_ptr[l], nr = S.level_rtile_ptr[l + 1] - r0;
+      const int c0 = S.level_chunk_ptr[l], nchunk = S.level_chunk_ptr[l + 1] - c0;
+      if (ng > 0) {
+        ScopedPhase ph(prof, PH_CH_UPDATE);
+        chol_update_groups_kernel<D><<<ng, kCholThreads, upd_smem, s>>>(P, Q, L, d_group_tile_.p + g0, d_group_w0_.p + g0,
+                                                                       d_group_w1_.p + g0, d_group_slot_.p + g0, d_gscratch_.p);
+        count();
+      }
+      if (nr > 0) {
+        ScopedPhase ph(prof, PH_CH_REDUCE);
+        chol_reduce_tiles_kernel<D><<<nr, kCholThreads, 0, s>>>(P, Q, L, d_rtile_tile_.p + r0, d_rtile_slot0_.p + r0,
+                                                               d_rtile_nslots_.p + r0, d_gscratch_.p);
+        count();
+      }
+      ScopedPhase ph(prof, PH_CH_PANEL);
+      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l], s>>>(P, Q, L, d_Ldiag_.p, d_level_chunks_.p + c0, status);
+      count();
+    }
   }
-  for (int l = S.nlevels - 1; l >= 0; --l) {
-    const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
-    if (nt == 0) continue;
-    chol_backward_kernel<D><<<nt, 128, 0, s>>>(P, Q, L, Dinv, y, t0);
-    if (lc) lc->n++;
+  {
+    ScopedPhase ph(prof, PH_CH_INVERT);
+    const size_t ismem = 2 * (size_t)S.max_ncol * D * S.max_ncol * D * 8;
+    chol_invert_diag_kernel<D><<<S.nsn, 128, ismem, s>>>(P, Q, d_Ldiag_.p, d_Dinv_.p);
+    count();
   }
-  chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, perm, y, x, status);
-  if (lc) lc->n++;
   B200_CUDA(cudaGetLastError());
 }
 
-void CholeskyGpu::solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc) {
+void CholeskyGpu::factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
+  if (S_.d == 3) factor_t<3>(dA, d_lambda, s, lc, prof);
+  else factor_t<6>(dA, d_lambda, s, lc, prof);
+}
+
+template <int D>
+void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
+  const SymbolicFactor& S = S_;
   const CholDev P = dev();
   const CholPlanDev Q = plan();
-  if (S_.d == 3) solve_t<3>(S_, P, Q, d_perm_.p, d_L_.p, d_Dinv_.p, d_y_.p, d_b, d_x, d_status_.p, s, lc);
-  else solve_t<6>(S_, P, Q, d_perm_.p, d_L_.p, d_Dinv_.p, d_y_.p, d_b, d_x, d_status_.p, s, lc);
+  const int n = S.nb * D;
+  auto count = [&](int k = 1) { if (lc) lc->n += k; };
+  double* y = d_y_.p;
+  {
+    ScopedPhase ph(prof, PH_CH_FORWARD);
+    chol_permute_in_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, b, y);
+    count();
+    for (int l = 0; l < S.nlevels; ++l) {
+      const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
+      if (nt == 0) continue;
+      chol_forward_kernel<D><<<nt, 128, 0, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, d_contrib_.p, t0);
+      count();
+    }
+  }
+  {
+    ScopedPhase ph(prof, PH_CH_BACKWARD);
+    const size_t bsmem = (size_t)S.max_nrow * D * sizeof(double);
+    for (int l = S.nlevels - 1; l >= 0; --l) {
+      const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
+      if (nt == 0) continue;
+      chol_backward_kernel<D><<<nt, 128, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, t0);
+      count();
+    }
+    chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, d_status_.p);
+    count();
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+void CholeskyGpu::solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
+  if (S_.d == 3) solve_t<3>(d_b, d_x, s, lc, prof);
+  else solve_t<6>(d_b, d_x, s, lc, prof);
 }
 
 }  // namespace g2o_b200

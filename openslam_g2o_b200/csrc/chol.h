@@ -31,9 +31,9 @@ class CholeskyGpu {
   // numeric factorisation of A + lambda*I (A: device, input block order, d*d col-major per block).
   // d_lambda may be nullptr (lambda = 0).  Asynchronous on s; the not-positive-definite outcome lands in
   // the device flag read by status().
-  void factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc);
+  void factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
   // x = A^-1 b (both device, length nb*d, original ordering).  Asynchronous on s.
-  void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc);
+  void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
   int* status_ptr() { return d_status_.p; }  // device int: 0 ok, 1 not positive definite
   double* factor_values() { return d_L_.p; }
 
@@ -49,13 +49,18 @@ class CholeskyGpu {
   DevBuf<int> d_a_ld_, d_diag_ld_, d_perm_;
   DevBuf<unsigned char> d_a_trans_;
   DevBuf<int> d_tile_sn_, d_tile_r0_, d_tile_c0_, d_tile_work_ptr_, d_work_u_, d_work_a0_, d_work_a1_, d_work_b0_, d_work_b1_;
-  DevBuf<int> d_sn_tile_ptr_, d_sn_chunk_ptr_, d_chunk_sn_, d_chunk_b0_, d_chunk_nb_, d_level_tiles_, d_level_chunks_;
-  DevBuf<long long> d_sn_dinvptr_;
-  DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_;
+  DevBuf<int> d_sn_tile_ptr_, d_sn_chunk_ptr_, d_chunk_sn_, d_chunk_b0_, d_chunk_nb_, d_level_chunks_;
+  DevBuf<int> d_group_tile_, d_group_w0_, d_group_w1_, d_group_slot_, d_rtile_tile_, d_rtile_slot0_, d_rtile_nslots_;
+  DevBuf<long long> d_sn_dinvptr_, d_sn_cptr_;
+  DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_, d_gscratch_, d_contrib_;
   DevBuf<int> d_status_;
   int nblk_ = 0;
   CholDev dev() const;
   CholPlanDev plan() const;
+  template <int D>
+  void factor_t(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof);
+  template <int D>
+  void solve_t(const double* b, double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof);
 };
 
 }  // namespace g2o_b200

@@ -76,6 +76,53 @@ struct DevBuf {
   }
 };
 
+// CUDA-event pairs around kernel groups, resolved lazily (no sync while recording).  ids: see solver.cu / g2o_b200.h
+struct EventProfiler {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  struct Rec { int id; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<Rec> recs;
+  double seconds[24] = {};
+  long long count[24] = {};
+  cudaEvent_t event() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      B200_CUDA(cudaEventCreate(&e));
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void flush() {
+    if (recs.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (const Rec& r : recs) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { seconds[r.id] += ms * 1e-3; count[r.id]++; }
+    }
+    recs.clear();
+    used = 0;
+  }
+  void reset() { flush(); for (int i = 0; i < 24; ++i) { seconds[i] = 0; count[i] = 0; } }
+  void destroy() { for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear(); }
+};
+struct ScopedPhase {
+  EventProfiler* p;
+  int id;
+  cudaEvent_t a = nullptr;
+  ScopedPhase(EventProfiler* prof, int phase) : p(prof), id(phase) {
+    if (p && p->on) { a = p->event(); cudaEventRecord(a, p->stream); }
+  }
+  ~ScopedPhase() {
+    if (p && p->on && a) {
+      cudaEvent_t b = p->event();
+      cudaEventRecord(b, p->stream);
+      p->recs.push_back({id, a, b});
+    }
+  }
+};
+
 // counts every kernel launch of this library (reported as bench "gpu_launches")
 struct LaunchCounter {
   int64_t n = 0;

@@ -25,40 +25,11 @@ int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ?
 
 // kernel groups for the profiling counters (b200_get_phase_time ids)
 enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE = 4, PH_UPDATE = 5, PH_BACKSUB = 6,
-       PH_LINEARIZE_CAMS = 7, PH_GATHER = 8, PH_SCHUR_INV = 9, PH_SCALE = 10, PH_COLLECTIVE = 11, PH_COUNT = 16 };
+       PH_LINEARIZE_CAMS = 7, PH_GATHER = 8, PH_SCHUR_INV = 9, PH_SCALE = 10, PH_COLLECTIVE = 11,
+       /* 12.. : inside the Cholesky, see chol.h */ PH_COUNT = 24 };
 
-cudaEvent_t prof_event(b200_ctx* c) {
-  if (c->ev_used == c->ev_pool.size()) {
-    cudaEvent_t e;
-    B200_CUDA(cudaEventCreate(&e));
-    c->ev_pool.push_back(e);
-  }
-  return c->ev_pool[c->ev_used++];
-}
-void prof_flush(b200_ctx* c) {
-  if (c->prof_recs.empty()) return;
-  cudaStreamSynchronize(c->stream);
-  for (const b200_ctx::ProfRec& r : c->prof_recs) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->phase_seconds[r.id] += ms * 1e-3; c->phase_count[r.id]++; }
-  }
-  c->prof_recs.clear();
-  c->ev_used = 0;
-}
-struct PhaseTimer {
-  b200_ctx* c;
-  int phase;
-  cudaEvent_t a = nullptr;
-  PhaseTimer(b200_ctx* ctx, int ph) : c(ctx), phase(ph) {
-    if (c->profiling) { a = prof_event(c); cudaEventRecord(a, c->stream); }
-  }
-  ~PhaseTimer() {
-    if (c->profiling && a) {
-      cudaEvent_t b = prof_event(c);
-      cudaEventRecord(b, c->stream);
-      c->prof_recs.push_back({phase, a, b});
-    }
-  }
+struct PhaseTimer : ScopedPhase {
+  PhaseTimer(b200_ctx* c, int ph) : ScopedPhase(&c->prof, ph) {}
 };
 
 template <typename F>
@@ -108,8 +79,14 @@ void set_device_lambda(b200_ctx* c, double lam) {
 // ------------------------------------------------------------------------------------------------
 // structure
 // ------------------------------------------------------------------------------------------------
+void drop_graphs(b200_ctx* c) {
+  if (c->graph_prologue) { cudaGraphExecDestroy(c->graph_prologue); c->graph_prologue = nullptr; }
+  if (c->graph_trial) { cudaGraphExecDestroy(c->graph_trial); c->graph_trial = nullptr; }
+}
+
 int build_structure_impl(b200_ctx* c) {
   double t0 = wall();
+  drop_graphs(c);
   cudaStream_t s = c->stream;
   // which graph family?
   int pose_kind = -1;
@@ -505,8 +482,8 @@ int enqueue_solve(b200_ctx* c) {
   cudaStream_t s = c->stream;
   const double* d_lambda = c->d_scalars.p + 3;
   if (!c->schur) {
-    { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hpp.p, d_lambda, s, &c->lc); }
-    { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(c->d_b.p, c->d_x.p, s, &c->lc); }
+    { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hpp.p, d_lambda, s, &c->lc, &c->prof); }
+    { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(c->d_b.p, c->d_x.p, s, &c->lc, &c->prof); }
     return 0;
   }
   {
@@ -523,8 +500,8 @@ int enqueue_solve(b200_ctx* c) {
     int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);
     if (rc) return rc;
   }
-  { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, s, &c->lc); }
-  { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc); }
+  { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, s, &c->lc, &c->prof); }
+  { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc, &c->prof); }
   if (c->nl > 0) {
     PhaseTimer pt(c, PH_BACKSUB);
     // on a failed factorisation the reference returns before touching the landmark part of x; the pose part
@@ -588,6 +565,82 @@ int reduce_trial_scalars(b200_ctx* c) {
   return allreduce_dev(c, c->d_scalars.p + 0, 1);
 }
 
+
+// ---- CUDA graph replay of the launch-bound sequences (about 150-250 small kernels each)
+bool graphs_usable(b200_ctx* c) { return c->use_graphs && !c->prof.on && (c->world <= 1 || !c->allreduce); }
+
+template <typename F>
+int run_captured(b200_ctx* c, cudaGraphExec_t* exec, long long* launches, F&& enqueue) {
+  if (!*exec) {
+    const long long before = c->lc.n;
+    cudaGraph_t graph = nullptr;
+    B200_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    try {
+      rc = enqueue();
+    } catch (...) {
+      cudaStreamEndCapture(c->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    B200_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    if (rc) { cudaGraphDestroy(graph); return rc; }
+    cudaError_t e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { *exec = nullptr; throw CudaError{e, "cudaGraphInstantiate", __FILE__, __LINE__}; }
+    *launches = c->lc.n - before;
+    c->lc.n = before;  // counted per replay below
+  }
+  B200_CUDA(cudaGraphLaunch(*exec, c->stream));
+  c->lc.n += *launches;
+  return 0;
+}
+
+// errors + chi2 + buildSystem of the current state
+int run_prologue(b200_ctx* c) {
+  auto body = [&]() -> int {
+    enqueue_chi2(c);
+    return enqueue_build_system(c);
+  };
+  if (!graphs_usable(c)) {
+    enqueue_chi2(c);
+    int rc = reduce_trial_scalars(c);
+    if (rc) return rc;
+    return enqueue_build_system(c);
+  }
+  return run_captured(c, &c->graph_prologue, &c->graph_prologue_launches, body);
+}
+
+// one LM trial: lambda -> solve -> update -> errors + chi2 -> scale
+int run_trial(b200_ctx* c) {
+  c->h_scalars[8] = c->lambda;
+  bool orth_now = false;
+  if (c->pose_kind == B200_VERTEX_SE3 && c->num_oplus_calls + 1 > 1000) orth_now = true;  // rare: take the plain path
+  if (!graphs_usable(c) || orth_now) {
+    set_device_lambda(c, c->lambda);
+    int rc = enqueue_solve(c);
+    if (rc) return rc;
+    enqueue_update(c);
+    enqueue_chi2(c);
+    if ((rc = reduce_trial_scalars(c))) return rc;
+    enqueue_scale(c);
+    return 0;
+  }
+  const int saved = c->num_oplus_calls;
+  auto body = [&]() -> int {
+    B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 3, c->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    int rc = enqueue_solve(c);
+    if (rc) return rc;
+    enqueue_update(c);
+    enqueue_chi2(c);
+    enqueue_scale(c);
+    return 0;
+  };
+  int rc = run_captured(c, &c->graph_trial, &c->graph_trial_launches, body);
+  c->num_oplus_calls = saved + 1;  // the captured enqueue_update only counts once
+  return rc;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -642,7 +695,8 @@ void b200_destroy(b200_ctx* c) {
   if (c->host_only) { host_only_flag() = true; delete c; host_only_flag() = false; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  c->prof.destroy();
+  drop_graphs(c);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_status) cudaFreeHost(c->h_status);
   cudaStream_t s = c->stream;
@@ -828,9 +882,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       return st->result;
     }
     // ---- Levenberg-Marquardt: core/optimization_algorithm_levenberg.cpp:57-147
-    enqueue_chi2(c);
-    if ((rc = reduce_trial_scalars(c))) return rc;
-    if ((rc = enqueue_build_system(c))) return rc;
+    if ((rc = run_prologue(c))) return rc;
     if (iteration == 0) enqueue_max_diag(c);
     sync_scalars(c);
     double currentChi = c->h_scalars[0];
@@ -844,12 +896,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
     qmax = 0;
     do {
       do_push(c);
-      set_device_lambda(c, c->lambda);
-      if ((rc = enqueue_solve(c))) return rc;
-      enqueue_update(c);
-      enqueue_chi2(c);
-      if ((rc = reduce_trial_scalars(c))) return rc;
-      enqueue_scale(c);
+      if ((rc = run_trial(c))) return rc;
       sync_scalars(c);
       const bool ok2 = *c->h_status == 0;
       tempChi = c->h_scalars[0];
@@ -1031,16 +1078,15 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
 int64_t b200_get_launch_count(b200_ctx* c) { return c ? c->lc.n : -1; }
 int b200_set_profiling(b200_ctx* c, int on) {
   if (!c) return B200_ERR_INVALID;
-  if (!c->host_only) { cudaSetDevice(c->device); prof_flush(c); }
-  c->profiling = on != 0;
-  for (int i = 0; i < PH_COUNT; ++i) { c->phase_seconds[i] = 0; c->phase_count[i] = 0; }
+  if (!c->host_only) { cudaSetDevice(c->device); c->prof.stream = c->stream; c->prof.reset(); }
+  c->prof.on = on != 0;
   return B200_OK;
 }
 int b200_get_phase_time(b200_ctx* c, int phase, double* seconds, int64_t* count) {
   if (!c || phase < 0 || phase >= PH_COUNT) return B200_ERR_INVALID;
-  if (!c->host_only) { cudaSetDevice(c->device); prof_flush(c); }
-  if (seconds) *seconds = c->phase_seconds[phase];
-  if (count) *count = c->phase_count[phase];
+  if (!c->host_only) { cudaSetDevice(c->device); c->prof.flush(); }
+  if (seconds) *seconds = c->prof.seconds[phase];
+  if (count) *count = c->prof.count[phase];
   return B200_OK;
 }
 void* b200_get_stream(b200_ctx* c) { return c ? (void*)c->stream : nullptr; }

@@ -79,13 +79,12 @@ struct b200_ctx {
   void* allreduce_user = nullptr;
   int rank = 0, world = 1;
 
-  // ---------------- profiling: CUDA-event pairs around kernel groups, resolved lazily (no sync while recording)
-  bool profiling = false;
-  struct ProfRec { int id; cudaEvent_t a, b; };
-  std::vector<cudaEvent_t> ev_pool;
-  size_t ev_used = 0;
-  std::vector<ProfRec> prof_recs;
-  double phase_seconds[16] = {};
-  long long phase_count[16] = {};
+  // ---------------- CUDA graphs of the two launch-bound sequences of an LM iteration (single GPU, profiling off)
+  cudaGraphExec_t graph_prologue = nullptr, graph_trial = nullptr;
+  long long graph_prologue_launches = 0, graph_trial_launches = 0;
+  bool use_graphs = true;
+
+  // ---------------- profiling
+  g2o_b200::EventProfiler prof;
   double time_symbolic = 0.0;
 };

@@ -419,6 +419,11 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   S.level_smem.assign(S.nlevels, 0);
   S.level_tile_ptr.assign(S.nlevels + 1, 0);
   S.level_chunk_ptr.assign(S.nlevels + 1, 0);
+  S.level_group_ptr.assign(S.nlevels + 1, 0);
+  S.level_rtile_ptr.assign(S.nlevels + 1, 0);
+  S.group_items = 6;
+  S.sn_cptr.assign(ns + 1, 0);
+  for (int J = 0; J < ns; ++J) S.sn_cptr[J + 1] = S.sn_cptr[J] + (int64_t)(S.sn_nrow[J] - S.sn_ncol[J]) * d;
   for (int l = 0; l < S.nlevels; ++l) {
     bool singletons = true;
     int tiles = 0, chunks = 0, ntask = S.level_ptr[l + 1] - S.level_ptr[l], smem = 0;
@@ -434,17 +439,36 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
       }
     }
     S.level_smem[l] = smem;
+    int slots = 0;
     if (singletons && (tiles > ntask || chunks > ntask)) {
       S.level_kind[l] = 1;
       for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
         const int J = S.task_sn[S.task_ptr[t]];
-        for (int q = S.sn_tile_ptr[J]; q < S.sn_tile_ptr[J + 1]; ++q)
-          if (S.tile_work_ptr[q + 1] > S.tile_work_ptr[q]) S.level_tiles.push_back(q);
+        for (int q = S.sn_tile_ptr[J]; q < S.sn_tile_ptr[J + 1]; ++q) {
+          const int w0 = S.tile_work_ptr[q], w1 = S.tile_work_ptr[q + 1];
+          if (w1 == w0) continue;
+          S.level_tiles.push_back(q);
+          const int ng = (w1 - w0 + S.group_items - 1) / S.group_items;
+          if (ng == 1) {
+            S.group_tile.push_back(q); S.group_w0.push_back(w0); S.group_w1.push_back(w1); S.group_slot.push_back(-1);
+          } else {
+            S.rtile_tile.push_back(q); S.rtile_slot0.push_back(slots); S.rtile_nslots.push_back(ng);
+            for (int gi = 0; gi < ng; ++gi) {
+              S.group_tile.push_back(q);
+              S.group_w0.push_back(w0 + (int)((long long)(w1 - w0) * gi / ng));
+              S.group_w1.push_back(w0 + (int)((long long)(w1 - w0) * (gi + 1) / ng));
+              S.group_slot.push_back(slots++);
+            }
+          }
+        }
         for (int q = S.sn_chunk_ptr[J]; q < S.sn_chunk_ptr[J + 1]; ++q) S.level_chunks.push_back(q);
       }
     }
+    S.max_group_slots = std::max(S.max_group_slots, slots);
     S.level_tile_ptr[l + 1] = (int)S.level_tiles.size();
     S.level_chunk_ptr[l + 1] = (int)S.level_chunks.size();
+    S.level_group_ptr[l + 1] = (int)S.group_tile.size();
+    S.level_rtile_ptr[l + 1] = (int)S.rtile_tile.size();
   }
   return S;
 }

@@ -69,6 +69,15 @@ struct SymbolicFactor {
   // level plan: kind 0 = fused (one CTA per task does update + factor), 1 = split (tiles kernel, then chunks kernel)
   std::vector<int> level_kind, level_smem;         // dynamic shared memory (bytes) the level's factor kernel needs
   std::vector<int> level_tile_ptr, level_tiles, level_chunk_ptr, level_chunks;
+  // split-K groups of the split levels: a tile with many work items is cut into groups of <= group_items items;
+  // each group is one CTA.  slot < 0: the tile has a single group and subtracts from the panel directly; otherwise
+  // the group writes its partial 48x48 sum to scratch slot `slot` and the tile's reduce CTA adds the slots in order.
+  int group_items = 0;
+  std::vector<int> level_group_ptr, group_tile, group_w0, group_w1, group_slot;   // per level: its groups
+  std::vector<int> level_rtile_ptr, rtile_tile, rtile_slot0, rtile_nslots;        // per level: tiles needing a reduce
+  int max_group_slots = 0;
+  // forward solve: supernode J leaves L21*y_J (its contribution to every ancestor) at sn_cptr[J]
+  std::vector<int64_t> sn_cptr;                    // nsn+1, scalar units
   // inverses of the triangular diagonal blocks (for the solves)
   std::vector<int64_t> sn_dinvptr;                 // nsn+1
   int64_t dinv_doubles = 0;

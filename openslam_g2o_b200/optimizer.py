@@ -213,7 +213,8 @@ class SolverContext:
 
     def phase_times(self):
         names = ("errors", "linearize", "schur", "factor", "trisolve", "update", "backsub", "linearize_cams", "gather",
-                 "schur_inv", "scale", "collective")
+                 "schur_inv", "scale", "collective", "chol_scatter", "chol_update", "chol_reduce", "chol_panel",
+                 "chol_fused", "chol_invert", "chol_forward", "chol_backward")
         out = {}
         for i, nme in enumerate(names):
             s, c = C.c_double(), C.c_int64()
