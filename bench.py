@@ -170,20 +170,8 @@ def run_b200(args, rank, world):
     ctx = opt.context
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     if sharded:
-        class _Dev:
-            def __init__(self, p, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 3}
-
-        def allreduce(ptr, count, _stream, _user):
-            try:
-                t = torch.as_tensor(_Dev(ptr, count), device=torch.device("cuda", local_rank))
-                with torch.cuda.stream(stream):
-                    dist.all_reduce(t)
-                return 0
-            except Exception as e:  # noqa
-                print("all-reduce failed:", e, file=sys.stderr)
-                return 1
-        ctx.set_allreduce(allreduce, rank, world)
+        from openslam_g2o_b200.distributed import make_allreduce
+        ctx.set_allreduce(make_allreduce(ctx, local_rank), rank, world)
     assert ctx.build_structure()
     dims = ctx.dims()
     kinds = [g.VERTEX_CAM, g.VERTEX_XYZ] if prob["kind"] == "ba" else [g.VERTEX_SE3]

@@ -51,10 +51,11 @@ typedef struct b200_iter_stats {
          time_linear_solver, time_linear_solution, time_update, time_iteration;
 } b200_iter_stats;
 
-/* optional collective for landmark-sharded BA: sum-all-reduce `count` doubles living at DEVICE pointer
- * `dev_ptr`, ordered on CUDA stream `stream` (a cudaStream_t).  The host side supplies it (NCCL through
- * torch.distributed in the Python harness, ncclAllReduce in a C++ host).  return 0 on success. */
-typedef int (*b200_allreduce_fn)(void* dev_ptr, int64_t count, void* stream, void* user);
+/* optional collective for landmark-sharded BA: all-reduce (op 0 = sum, 1 = max) `count` doubles living at DEVICE
+ * pointer `dev_ptr`, ordered on CUDA stream `stream` (a cudaStream_t).  The host side supplies it (NCCL through
+ * torch.distributed in the Python harness, ncclAllReduce(ncclDouble, ncclSum|ncclMax) in a C++ host).
+ * return 0 on success. */
+typedef int (*b200_allreduce_fn)(void* dev_ptr, int64_t count, int op, void* stream, void* user);
 
 /* ------------------------------------------------------------------ lifetime */
 int b200_device_count(void);

@@ -35,7 +35,7 @@ class IterStats(C.Structure):
                 ("time_linear_solution", C.c_double), ("time_update", C.c_double), ("time_iteration", C.c_double)]
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p)
 
 
 class B200Error(RuntimeError):

@@ -535,6 +535,21 @@ __global__ void oplus_xyz_kernel(int n, const int* __restrict__ lidx, const doub
   for (int k = 0; k < 3; ++k) est[4ll * v + k] += x_l[3ll * l + k];
 }
 
+// ------------------------------------------------------------------ host <-> device estimate staging
+// device rows are padded (3 -> 4 doubles) for aligned vector loads; the ABI layout is dense
+__global__ void unpack_rows_kernel(int n, int ne, int st, const double* __restrict__ dense, double* __restrict__ padded) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * ne) return;
+  const int v = (int)(i / ne), k = (int)(i - (long long)v * ne);
+  padded[(long long)v * st + k] = dense[i];
+}
+__global__ void pack_rows_kernel(int n, int ne, int st, const double* __restrict__ padded, double* __restrict__ dense) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * ne) return;
+  const int v = (int)(i / ne), k = (int)(i - (long long)v * ne);
+  dense[i] = padded[(long long)v * st + k];
+}
+
 // ------------------------------------------------------------------ LM scalars
 // partial sums of x_j (lambda x_j + b_j)        (optimization_algorithm_levenberg.cpp:165-172)
 __global__ void lm_scale_kernel(int n, const double* __restrict__ x, const double* __restrict__ b,

@@ -415,10 +415,10 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
   B200_CUDA(cudaGetLastError());
 }
 
-int allreduce_dev(b200_ctx* c, double* p, long long count) {
+int allreduce_dev(b200_ctx* c, double* p, long long count, int op = 0) {
   if (!c->allreduce || c->world <= 1) return 0;
   PhaseTimer pt(c, PH_COLLECTIVE);
-  int rc = c->allreduce(p, count, (void*)c->stream, c->allreduce_user);
+  int rc = c->allreduce(p, count, op, (void*)c->stream, c->allreduce_user);
   if (rc != 0) { c->err = "all-reduce callback failed"; return B200_ERR_COLLECTIVE; }
   return 0;
 }
@@ -475,6 +475,7 @@ void enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses 
     c->lc.n += 2;
   }
   B200_CUDA(cudaGetLastError());
+  allreduce_dev(c, c->d_scalars.p + 2, 1, /*max*/ 1);  // sharded: landmark diagonals live on different ranks
 }
 
 // Solver::solve with the lambda currently stored at d_scalars[3]
@@ -534,13 +535,23 @@ void enqueue_update(b200_ctx* c) {
   B200_CUDA(cudaGetLastError());
 }
 
-void enqueue_scale(b200_ctx* c) {  // d_scalars[1] = sum_j x_j (lambda x_j + b_j)
+// sum_j x_j (lambda x_j + b_j): pose part -> d_scalars[4] (identical on every rank), landmark part -> d_scalars[1]
+// (a partial sum when landmarks are sharded; all-reduced together with chi2 in d_scalars[0])
+void enqueue_scale(b200_ctx* c) {
   PhaseTimer pt(c, PH_SCALE);
   cudaStream_t s = c->stream;
-  const int n = c->sizeP + c->sizeL, nb = ceil_div(n, 256);
-  k::lm_scale_kernel<<<nb, 256, 0, s>>>(n, c->d_x.p, c->d_b.p, c->d_scalars.p + 3, c->d_partials.p);
-  k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 1);
+  int nb = ceil_div(c->sizeP, 256);
+  k::lm_scale_kernel<<<nb, 256, 0, s>>>(c->sizeP, c->d_x.p, c->d_b.p, c->d_scalars.p + 3, c->d_partials.p);
+  k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 4);
   c->lc.n += 2;
+  if (c->sizeL > 0) {
+    nb = ceil_div(c->sizeL, 256);
+    k::lm_scale_kernel<<<nb, 256, 0, s>>>(c->sizeL, c->d_x.p + c->sizeP, c->d_b.p + c->sizeP, c->d_scalars.p + 3, c->d_partials.p);
+    k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 1);
+    c->lc.n += 2;
+  } else {
+    B200_CUDA(cudaMemsetAsync(c->d_scalars.p + 1, 0, sizeof(double), s));
+  }
   B200_CUDA(cudaGetLastError());
 }
 
@@ -558,11 +569,10 @@ void do_pop(b200_ctx* c) {
 }
 
 // sharded runs: chi2 and the landmark part of the LM scale are partial sums -> one tiny all-reduce
-int reduce_trial_scalars(b200_ctx* c) {
+int reduce_trial_scalars(b200_ctx* c, int count = 1) {
   if (!c->allreduce || c->world <= 1) return 0;
-  // every rank holds the same pose part of x and b; only the landmark part differs.  To keep the sum exact
-  // we all-reduce chi2 (slot 0) only; the scale is assembled as pose part (local) + all-reduced landmark part.
-  return allreduce_dev(c, c->d_scalars.p + 0, 1);
+  // [0] chi2 partial, [1] landmark part of the LM scale; the pose part (slot 4) is identical on every rank
+  return allreduce_dev(c, c->d_scalars.p + 0, count);
 }
 
 
@@ -622,9 +632,8 @@ int run_trial(b200_ctx* c) {
     if (rc) return rc;
     enqueue_update(c);
     enqueue_chi2(c);
-    if ((rc = reduce_trial_scalars(c))) return rc;
     enqueue_scale(c);
-    return 0;
+    return reduce_trial_scalars(c, 2);
   }
   const int saved = c->num_oplus_calls;
   auto body = [&]() -> int {
@@ -902,7 +911,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       tempChi = c->h_scalars[0];
       if (!ok2) tempChi = DBL_MAX;
       rho = currentChi - tempChi;
-      double scale = c->h_scalars[1];
+      double scale = c->h_scalars[4] + c->h_scalars[1];
       scale += 1e-3;
       rho /= scale;
       if (rho > 0 && std::isfinite(tempChi)) {
@@ -987,7 +996,14 @@ int b200_get_estimates(b200_ctx* c, int kind, double* out) {
     NEED_DEVICE(c);
     B200_CUDA(cudaSetDevice(c->device));
     const double* dev = lm ? c->d_lm_est.p : c->d_pose_est.p;
-    B200_CUDA(cudaMemcpy2DAsync(out, ne * sizeof(double), dev, st * sizeof(double), ne * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream));
+    if (st == ne) {
+      B200_CUDA(cudaMemcpyAsync(out, dev, (size_t)n * ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      c->d_stage_est.alloc((size_t)n * ne);
+      k::pack_rows_kernel<<<ceil_div((long long)n * ne, 256), 256, 0, c->stream>>>(n, ne, st, dev, c->d_stage_est.p);
+      c->lc.n++;
+      B200_CUDA(cudaMemcpyAsync(out, c->d_stage_est.p, (size_t)n * ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
     B200_CUDA(cudaStreamSynchronize(c->stream));
     return (int)B200_OK;
   });
@@ -1003,8 +1019,11 @@ int b200_set_estimates(b200_ctx* c, int kind, const double* est) {
     double* dev = lm ? c->d_lm_est.p : c->d_pose_est.p;
     if (st == ne) {
       B200_CUDA(cudaMemcpyAsync(dev, est, (size_t)n * ne * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    } else {  // padded rows on the device (3 -> 4 doubles)
-      B200_CUDA(cudaMemcpy2DAsync(dev, st * sizeof(double), est, ne * sizeof(double), ne * sizeof(double), n, cudaMemcpyHostToDevice, c->stream));
+    } else {  // padded rows on the device (3 -> 4 doubles): one contiguous copy, then expand on the device
+      c->d_stage_est.alloc((size_t)n * ne);
+      B200_CUDA(cudaMemcpyAsync(c->d_stage_est.p, est, (size_t)n * ne * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      k::unpack_rows_kernel<<<ceil_div((long long)n * ne, 256), 256, 0, c->stream>>>(n, ne, st, c->d_stage_est.p, dev);
+      c->lc.n++;
     }
     if (kind == B200_VERTEX_CAM) {
       k::cam_derive_kernel<<<ceil_div(n, 128), 128, 0, c->stream>>>(n, c->d_pose_est.p, c->d_cam_der.p);
