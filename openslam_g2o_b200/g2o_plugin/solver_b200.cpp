@@ -1,0 +1,240 @@
+// solver_b200.cpp - g2o plugin "libg2o_solver_b200.so": registers {gn,lm}_{fix3_2,fix6_3}_b200 with g2o's
+// OptimizationAlgorithmFactory (g2o/core/optimization_algorithm_factory.h:153-162), same naming scheme as
+// g2o/solvers/cholmod/solver_cholmod.cpp:41-132.  The `g2o` binary picks it up through its *_solver_*.so glob
+// (apps/g2o_cli/g2o_common.cpp:82,133-167); programmatic users `new OptimizationAlgorithmB200(...)` directly.
+//
+// Level 3 (this file): OptimizationAlgorithmB200 keeps the whole LM / GN iteration on the GPU behind
+// b200_algorithm_solve(); the host only sees a handful of scalars per trial and gets the estimates written back into
+// the vertices at the end of every solve() (what SparseOptimizer::optimize reads when verbose / statistics are on,
+// core/sparse_optimizer.cpp:392-411).
+// Level 1 is linear_solver_b200.h (LinearSolverB200 under the stock BlockSolver).
+//
+// Compiles only inside a g2o source tree (needs Eigen + g2o headers; neither exists in the build container).
+#include <iostream>
+#include <vector>
+
+#include "g2o/core/batch_stats.h"
+#include "g2o/core/block_solver.h"
+#include "g2o/core/optimization_algorithm.h"
+#include "g2o/core/optimization_algorithm_factory.h"
+#include "g2o/core/optimization_algorithm_gauss_newton.h"
+#include "g2o/core/optimization_algorithm_levenberg.h"
+#include "g2o/core/sparse_optimizer.h"
+#include "g2o/stuff/macros.h"
+#include "g2o/types/sba/types_sba.h"
+#include "g2o/types/slam2d/edge_se2.h"
+#include "g2o/types/slam2d/vertex_se2.h"
+#include "g2o/types/slam3d/edge_se3.h"
+#include "g2o/types/slam3d/vertex_se3.h"
+#include "g2o_b200.h"
+#include "linear_solver_b200.h"
+
+namespace g2o {
+
+class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
+ public:
+  explicit OptimizationAlgorithmB200(int algorithm) : OptimizationAlgorithm(), _ctx(0), _algorithm(algorithm) {
+    _device = _properties.makeProperty<Property<int> >("device", 0);
+    _userLambdaInit = _properties.makeProperty<Property<double> >("initialLambda", 0.);
+    _maxTrialsAfterFailure = _properties.makeProperty<Property<int> >("maxTrialsAfterFailure", 10);
+  }
+  virtual ~OptimizationAlgorithmB200() { b200_destroy(_ctx); }
+
+  // OptimizationAlgorithmWithHessian::init (core/optimization_algorithm_with_hessian.cpp:50-73): (re)ingest the graph
+  virtual bool init(bool /*online*/ = false) {
+    if (!_ctx && b200_create(_device->value(), &_ctx) != B200_OK) {
+      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(0) << std::endl;  // no CPU fallback
+      return false;
+    }
+    b200_set_lm_params(_ctx, _userLambdaInit->value(), _maxTrialsAfterFailure->value());
+    return ingest();
+  }
+
+  virtual SolverResult solve(int iteration, bool /*online*/ = false) {
+    b200_iter_stats st;
+    int rc = b200_algorithm_solve(_ctx, _algorithm, iteration, &st);
+    if (rc < 0 && rc != B200_RESULT_FAIL) {
+      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
+      return Fail;
+    }
+    G2OBatchStatistics* gs = G2OBatchStatistics::globalStats();
+    if (gs) {  // same fields the CPU path fills (core/batch_stats.h:40-77)
+      gs->levenbergIterations = st.levenberg_iterations;
+      gs->timeIteration = st.time_iteration;
+      gs->timeSymbolicDecomposition = st.time_symbolic;
+      gs->choleskyNNZ = static_cast<size_t>(b200_get_factor_nnz(_ctx));
+    }
+    _lambda = st.lambda;
+    _levenbergIterations = st.levenberg_iterations;
+    writeBack();
+    return static_cast<SolverResult>(st.result);
+  }
+
+  virtual bool computeMarginals(SparseBlockMatrix<MatrixXd>&, const std::vector<std::pair<int, int> >&) { return false; }
+  virtual bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) { return false; }
+  virtual void printVerbose(std::ostream& os) const {
+    os << "\t schur= " << (_hasLandmarks ? 1 : 0) << "\t lambda= " << FIXED(_lambda) << "\t levenbergIter= " << _levenbergIterations;
+  }
+
+ protected:
+  // one-time packing of the pointer graph into SoA arrays (what BlockSolver::buildStructure walks,
+  // core/block_solver.hpp:142-295).  Unknown vertex / edge types -> false (no CPU fallback).
+  bool ingest() {
+    const SparseOptimizer::VertexContainer& verts = _optimizer->activeVertices();
+    const SparseOptimizer::EdgeContainer& edges = _optimizer->activeEdges();
+    std::vector<double> est[4];
+    std::vector<int32_t> hidx[4];
+    std::vector<uint8_t> marg[4];
+    _slot.clear();
+    for (int k = 0; k < 4; ++k) _verts[k].clear();
+    for (size_t i = 0; i < verts.size(); ++i) {
+      OptimizableGraph::Vertex* v = verts[i];
+      int kind = -1;
+      double e[12];
+      if (VertexSE2* p = dynamic_cast<VertexSE2*>(v)) {
+        kind = B200_VERTEX_SE2;
+        e[0] = p->estimate().translation().x(); e[1] = p->estimate().translation().y(); e[2] = p->estimate().rotation().angle();
+      } else if (VertexSE3* p = dynamic_cast<VertexSE3*>(v)) {
+        kind = B200_VERTEX_SE3;  // the state is the Isometry3d itself: R (col-major) | t, never re-quaternionised
+        Eigen::Map<Eigen::Matrix3d>(e) = p->estimate().linear();
+        Eigen::Map<Eigen::Vector3d>(e + 9) = p->estimate().translation();
+      } else if (VertexCam* p = dynamic_cast<VertexCam*>(v)) {
+        kind = B200_VERTEX_CAM;
+        const SBACam& c = p->estimate();
+        Eigen::Map<Eigen::Vector3d>(e) = c.translation();
+        Eigen::Map<Eigen::Vector4d>(e + 3) = c.rotation().coeffs();  // x y z w
+        e[7] = c.Kcam(0, 0); e[8] = c.Kcam(1, 1); e[9] = c.Kcam(0, 2); e[10] = c.Kcam(1, 2); e[11] = c.baseline;
+      } else if (VertexSBAPointXYZ* p = dynamic_cast<VertexSBAPointXYZ*>(v)) {
+        kind = B200_VERTEX_XYZ;
+        Eigen::Map<Eigen::Vector3d>(e) = p->estimate();
+      } else {
+        std::cerr << "OptimizationAlgorithmB200: unsupported vertex type (id " << v->id() << ")" << std::endl;
+        return false;
+      }
+      const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
+      _slot[v] = static_cast<int>(hidx[kind].size());
+      _verts[kind].push_back(v);
+      est[kind].insert(est[kind].end(), e, e + ne);
+      hidx[kind].push_back(v->hessianIndex());
+      marg[kind].push_back(v->marginalized() ? 1 : 0);
+    }
+    _hasLandmarks = !hidx[B200_VERTEX_XYZ].empty();
+    for (int k = 0; k < 4; ++k)
+      if (!hidx[k].empty() && b200_set_vertices(_ctx, k, static_cast<int>(hidx[k].size()), &est[k][0], &hidx[k][0], &marg[k][0]) != B200_OK)
+        return false;
+    std::vector<int32_t> vi, vj;
+    std::vector<double> meas, info;
+    int ekind = -1;
+    for (size_t k = 0; k < edges.size(); ++k) {
+      OptimizableGraph::Edge* e = edges[k];
+      int kind = -1;
+      if (EdgeSE2* p = dynamic_cast<EdgeSE2*>(e)) {
+        kind = B200_EDGE_SE2;
+        Eigen::Vector3d z = p->measurement().toVector();
+        meas.insert(meas.end(), z.data(), z.data() + 3);
+        info.insert(info.end(), p->information().data(), p->information().data() + 9);
+      } else if (EdgeSE3* p = dynamic_cast<EdgeSE3*>(e)) {
+        kind = B200_EDGE_SE3;
+        double z[12];
+        Eigen::Map<Eigen::Matrix3d>(z) = p->measurement().linear();
+        Eigen::Map<Eigen::Vector3d>(z + 9) = p->measurement().translation();
+        meas.insert(meas.end(), z, z + 12);
+        info.insert(info.end(), p->information().data(), p->information().data() + 36);
+      } else if (EdgeProjectP2MC* p = dynamic_cast<EdgeProjectP2MC*>(e)) {
+        kind = B200_EDGE_P2MC;
+        meas.insert(meas.end(), p->measurement().data(), p->measurement().data() + 2);
+        info.insert(info.end(), p->information().data(), p->information().data() + 4);
+      }
+      if (kind < 0 || (ekind >= 0 && kind != ekind) || e->robustKernel()) {
+        std::cerr << "OptimizationAlgorithmB200: unsupported / mixed edge types or robust kernel" << std::endl;
+        return false;
+      }
+      ekind = kind;
+      vi.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(0))]);
+      vj.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(1))]);
+    }
+    if (vi.empty()) return false;
+    if (b200_set_edges(_ctx, ekind, static_cast<int>(vi.size()), &vi[0], &vj[0], &meas[0], &info[0]) != B200_OK) return false;
+    int rc = b200_build_structure(_ctx);
+    if (rc != B200_OK) std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
+    return rc == B200_OK;
+  }
+
+  // device estimates -> vertices
+  void writeBack() {
+    std::vector<double> buf;
+    for (int kind = 0; kind < 4; ++kind) {
+      const std::vector<OptimizableGraph::Vertex*>& vs = _verts[kind];
+      if (vs.empty()) continue;
+      const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
+      buf.resize(vs.size() * ne);
+      if (b200_get_estimates(_ctx, kind, &buf[0]) != B200_OK) continue;
+      for (size_t i = 0; i < vs.size(); ++i) {
+        const double* e = &buf[i * ne];
+        if (vs[i]->fixed()) continue;
+        if (kind == B200_VERTEX_SE2) static_cast<VertexSE2*>(vs[i])->setEstimate(SE2(e[0], e[1], e[2]));
+        else if (kind == B200_VERTEX_XYZ) static_cast<VertexSBAPointXYZ*>(vs[i])->setEstimate(Eigen::Vector3d(e[0], e[1], e[2]));
+        else if (kind == B200_VERTEX_SE3) {
+          Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
+          T.linear() = Eigen::Map<const Eigen::Matrix3d>(e);
+          T.translation() = Eigen::Map<const Eigen::Vector3d>(e + 9);
+          static_cast<VertexSE3*>(vs[i])->setEstimate(T);
+        } else {
+          SBACam cam(Eigen::Quaterniond(e[6], e[3], e[4], e[5]), Eigen::Vector3d(e[0], e[1], e[2]));
+          cam.setKcam(e[7], e[8], e[9], e[10], e[11]);
+          static_cast<VertexCam*>(vs[i])->setEstimate(cam);
+        }
+      }
+    }
+  }
+
+  b200_ctx* _ctx;
+  int _algorithm;
+  bool _hasLandmarks;
+  double _lambda;
+  int _levenbergIterations;
+  Property<int>* _device;
+  Property<double>* _userLambdaInit;
+  Property<int>* _maxTrialsAfterFailure;
+  std::map<OptimizableGraph::Vertex*, int> _slot;
+  std::vector<OptimizableGraph::Vertex*> _verts[4];
+};
+
+// ----------------------------------------------------------------------------------------------- registration
+static OptimizationAlgorithm* createSolverB200(const std::string& fullSolverName) {
+  const std::string method = fullSolverName.substr(0, 2);
+  const std::string rest = fullSolverName.substr(3);
+  if (rest == "fix3_2_b200" || rest == "fix6_3_b200")  // Level 3: whole iteration on the GPU
+    return new OptimizationAlgorithmB200(method == "gn" ? B200_GAUSS_NEWTON : B200_LEVENBERG);
+  // Level 1: stock BlockSolver + LM/GN on the host, only the linear solver on the GPU
+  Solver* s = 0;
+  if (rest == "fix3_2_b200ls") s = new BlockSolver_3_2(new LinearSolverB200<BlockSolver_3_2::PoseMatrixType>());
+  else if (rest == "fix6_3_b200ls") s = new BlockSolver_6_3(new LinearSolverB200<BlockSolver_6_3::PoseMatrixType>());
+  else return 0;
+  if (method == "gn") return new OptimizationAlgorithmGaussNewton(s);
+  if (method == "lm") return new OptimizationAlgorithmLevenberg(s);
+  delete s;
+  return 0;
+}
+
+class B200SolverCreator : public AbstractOptimizationAlgorithmCreator {
+ public:
+  explicit B200SolverCreator(const OptimizationAlgorithmProperty& p) : AbstractOptimizationAlgorithmCreator(p) {}
+  virtual OptimizationAlgorithm* construct() { return createSolverB200(property().name); }
+};
+
+G2O_REGISTER_OPTIMIZATION_LIBRARY(b200);
+
+#define B200_REGISTER(name, desc, pd, ld) \
+  G2O_REGISTER_OPTIMIZATION_ALGORITHM(name, new B200SolverCreator(OptimizationAlgorithmProperty(#name, desc, "B200", true, pd, ld)))
+
+B200_REGISTER(gn_fix3_2_b200, "Gauss-Newton: device-resident solver on B200 (fixed blocksize)", 3, 2);
+B200_REGISTER(gn_fix6_3_b200, "Gauss-Newton: device-resident solver on B200 (fixed blocksize)", 6, 3);
+B200_REGISTER(lm_fix3_2_b200, "Levenberg: device-resident solver on B200 (fixed blocksize)", 3, 2);
+B200_REGISTER(lm_fix6_3_b200, "Levenberg: device-resident solver on B200 (fixed blocksize)", 6, 3);
+B200_REGISTER(gn_fix3_2_b200ls, "Gauss-Newton: BlockSolver + B200 supernodal Cholesky", 3, 2);
+B200_REGISTER(gn_fix6_3_b200ls, "Gauss-Newton: BlockSolver + B200 supernodal Cholesky", 6, 3);
+B200_REGISTER(lm_fix3_2_b200ls, "Levenberg: BlockSolver + B200 supernodal Cholesky", 3, 2);
+B200_REGISTER(lm_fix6_3_b200ls, "Levenberg: BlockSolver + B200 supernodal Cholesky", 6, 3);
+
+}  // namespace g2o
