@@ -60,7 +60,7 @@ __global__ void chol_add_lambda_kernel(int nb, const long long* __restrict__ dia
 // ---------------------------------------------------------------------------------------------
 constexpr int kTile = 48;        // scalar rows / cols of a destination tile
 constexpr int kMaxPanelCols = 96;
-constexpr int kCholThreads = 256;
+constexpr int kCholThreads = 512;
 constexpr int kUpdateSmemDoubles = kTile * kTile + 2 * kTile * kMaxPanelCols;  // acc | A rows | B rows
 
 struct CholPlanDev {
@@ -68,6 +68,8 @@ struct CholPlanDev {
   const int *work_u, *work_a0, *work_a1, *work_b0, *work_b1;
   const int *sn_tile_ptr, *sn_chunk_ptr, *chunk_sn, *chunk_b0, *chunk_nb;
   const long long *sn_dinvptr, *sn_cptr;
+  const long long *work_koff, *work_reloff;
+  const int *work_mk, *work_nk, *fwd_ptr, *fwd_src;
 };
 
 // acc (shared, kTile x kTile) = sum over work items [w0,w1) of the tile, in list order.
@@ -81,21 +83,36 @@ __device__ void accumulate_items(const CholDev& P, const CholPlanDev& Q, const d
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < kTile * kTile; i += nt) acc[i] = 0.0;
   for (int wi = w0; wi < w1; ++wi) {
-    const int u = Q.work_u[wi];
+    // one level of indirection: everything the item needs sits in flat per-item arrays
     const int a0 = Q.work_a0[wi], a1 = Q.work_a1[wi], b0 = Q.work_b0[wi], b1 = Q.work_b1[wi];
-    const int K = P.upd_k[u], p0 = P.upd_p0[u];
-    const int Mk = P.sn_nrow[K] * D, Nk = P.sn_ncol[K] * D;
-    const double* Kp = L + P.sn_lptr[K] + (long long)p0 * D;
-    const int* rel = P.rel + P.upd_relptr[u];
+    const int Mk = Q.work_mk[wi], Nk = Q.work_nk[wi];
+    const double* Kp = L + Q.work_koff[wi];
+    const int* rel = P.rel + Q.work_reloff[wi];
     const int nA = (a1 - a0) * D, nB = (b1 - b0) * D;
     __syncthreads();  // previous item's operands fully consumed, acc zeroing done
-    for (int i = tid; i < nA * Nk; i += nt) {
-      const int k = i / nA, r = i - k * nA;
-      As[r + k * kTile] = Kp[a0 * D + r + (long long)k * Mk];
-    }
-    for (int i = tid; i < nB * Nk; i += nt) {
-      const int k = i / nB, r = i - k * nB;
-      Bs[r + k * kTile] = Kp[b0 * D + r + (long long)k * Mk];
+    {
+      // stage both operand row blocks; 4 independent global loads in flight per thread
+      const int totA = nA * Nk, tot = totA + nB * Nk;
+      for (int i0 = tid; i0 < tot; i0 += 4 * nt) {
+        double v[4];
+        int dst[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * nt;
+          dst[q] = -1;
+          if (i < tot) {
+            const bool isA = i < totA;
+            const int ii = isA ? i : i - totA;
+            const int nR = isA ? nA : nB;
+            const int k = ii / nR, r = ii - k * nR;
+            v[q] = Kp[(isA ? a0 : b0) * D + r + (long long)k * Mk];
+            dst[q] = (isA ? 0 : kTile * kMaxPanelCols) + r + k * kTile;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (dst[q] >= 0) As[dst[q]] = v[q];  // Bs == As + kTile*kMaxPanelCols
+      }
     }
     __syncthreads();
     const int na = (a1 - a0) * S, nb = (b1 - b0) * S;
@@ -174,9 +191,12 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
 #pragma unroll
       for (int m = 0; m < k; ++m) s = fma(-Lp[k][m], Lp[k][m], s);
       if (!(s > 0.0)) { bad = true; s = 1.0; }  // d <= 0: not positive definite (csparse_helper.cpp:136)
-      const double lkk = sqrt(s);
-      Lp[k][k] = lkk;
-      inv[k] = 1.0 / lkk;
+      // one reciprocal square root (+ one Newton step to full double accuracy) instead of sqrt and a division:
+      // this sits on the critical path of every block column
+      double rs = rsqrt(s);
+      rs = fma(rs * 0.5, fma(-s * rs, rs, 1.0), rs);
+      inv[k] = rs;
+      Lp[k][k] = s * rs;
 #pragma unroll
       for (int r = k + 1; r < D; ++r) {
         double t = Lp[r][k];
@@ -209,24 +229,48 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
       for (int c = 0; c < D; ++c) Sm[row + (j0 + c) * R] = x[c];
     }
     __syncthreads();
-    if (below) {
-      const int cend = row < N ? row : N - 1;
-      int c = j0 + D;
-      for (; c + 3 <= cend; c += 4) {  // 4 independent accumulators: hide the FP64 FMA latency
-        double v0 = Sm[row + c * R], v1 = Sm[row + (c + 1) * R], v2 = Sm[row + (c + 2) * R], v3 = Sm[row + (c + 3) * R];
+    {
+      // rank-D trailing update T(i,c) -= sum_k X(i,k) X(c,k), i >= j0+D, c in [j0+D, N): every thread takes
+      // 2 rows x 4 columns per item (rows rp apart so that a warp walks consecutive rows); entries above the
+      // diagonal are never read again, so they may be updated or skipped freely
+      const int base = j0 + D;
+      const int nrows = R - base, ncols = N - base;
+      const int rp = (nrows + 1) >> 1, cq = (ncols + 3) >> 2;
+      for (int item = tid; item < rp * cq; item += nt) {
+        const int ci = item / rp, ri = item - ci * rp;
+        const int r0 = base + ri, r1 = r0 + rp;
+        const int c0 = base + 4 * ci;
+        const bool has1 = r1 < R;
+        if ((has1 ? r1 : r0) < N && c0 > (has1 ? r1 : r0)) continue;  // whole item above the diagonal
+        // all loads first, then 8 independent FMA chains, then the stores: nothing in between can alias
+        double x0[D], x1[D], l[4][D], v0[4], v1[4];
+        const int rr1 = has1 ? r1 : r0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          const double xk = x[k];
-          const double* lr = Sm + c + (j0 + k) * R;
-          v0 = fma(-xk, lr[0], v0); v1 = fma(-xk, lr[1], v1); v2 = fma(-xk, lr[2], v2); v3 = fma(-xk, lr[3], v3);
+          x0[k] = Sm[r0 + (j0 + k) * R];
+          x1[k] = Sm[rr1 + (j0 + k) * R];
         }
-        Sm[row + c * R] = v0; Sm[row + (c + 1) * R] = v1; Sm[row + (c + 2) * R] = v2; Sm[row + (c + 3) * R] = v3;
-      }
-      for (; c <= cend; ++c) {
-        double v = Sm[row + c * R];
 #pragma unroll
-        for (int k = 0; k < D; ++k) v = fma(-x[k], Sm[c + (j0 + k) * R], v);
-        Sm[row + c * R] = v;
+        for (int q = 0; q < 4; ++q) {
+          const int c = min(c0 + q, N - 1);
+          v0[q] = Sm[r0 + c * R];
+          v1[q] = Sm[rr1 + c * R];
+#pragma unroll
+          for (int k = 0; k < D; ++k) l[q][k] = Sm[c + (j0 + k) * R];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            v0[q] = fma(-x0[k], l[q][k], v0[q]);
+            v1[q] = fma(-x1[k], l[q][k], v1[q]);
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c0 + q < N) {
+            Sm[r0 + (c0 + q) * R] = v0[q];
+            if (has1) Sm[r1 + (c0 + q) * R] = v1[q];
+          }
       }
     }
     __syncthreads();
@@ -370,10 +414,12 @@ __global__ void chol_permute_out_kernel(int nb, const int* __restrict__ perm, co
 }
 
 // forward: y_J = Linv (P b - contributions of the descendants); every supernode then leaves c_J = L21 y_J in its own
-// scratch segment, so ancestors only add precomputed numbers (in update order -> deterministic) and L is read once,
-// coalesced, by its owner.
+// scratch segment, so ancestors only add precomputed numbers (per-row lists in a fixed order -> deterministic) and L
+// is read once, coalesced, by its owner.
+constexpr int kSolveThreads = 256;
+
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSolveThreads)
 chol_forward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
                     double* __restrict__ y, double* __restrict__ contrib, int task0) {
   __shared__ double tvec[kMaxPanelCols];
@@ -385,30 +431,27 @@ chol_forward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, cons
     const int col0 = P.sn_col0[J];
     const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
     double* yj = y + (long long)col0 * D;
-    __syncthreads();
-    for (int i = tid; i < N; i += nt) tvec[i] = yj[i];
-    __syncthreads();
-    for (int u = P.upd_ptr[J]; u < P.upd_ptr[J + 1]; ++u) {
-      const int K = P.upd_k[u], p0 = P.upd_p0[u], p1 = P.upd_p1[u];
-      const int* krows = P.sn_rows + P.sn_rowptr[K];
-      const double* ck = contrib + Q.sn_cptr[K] - (long long)P.sn_ncol[K] * D;  // indexed by panel row
-      const int nrow = (p1 - p0) * D;
-      for (int i = tid; i < nrow; i += nt) {
-        const int p = p0 + i / D, rr = i % D;
-        tvec[(krows[p] - col0) * D + rr] -= ck[p * D + rr];
-      }
-      __syncthreads();
+    __syncthreads();  // contributions written by the previous supernode of this task are visible
+    for (int i = tid; i < N; i += nt) {
+      const int g = col0 * D + i;
+      double s = yj[i];
+      const int e0 = Q.fwd_ptr[g], e1 = Q.fwd_ptr[g + 1];
+      for (int e = e0; e < e1; ++e) s -= contrib[Q.fwd_src[e]];
+      tvec[i] = s;
     }
+    __syncthreads();
     const double* Di = Dinv + Q.sn_dinvptr[J];
     for (int i = tid; i < N; i += nt) {
-      double s0 = 0.0, s1 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int j = 0;
-      for (; j + 1 <= i; j += 2) {
+      for (; j + 3 <= i; j += 4) {
         s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
         s1 = fma(Di[i + (long long)(j + 1) * N], tvec[j + 1], s1);
+        s2 = fma(Di[i + (long long)(j + 2) * N], tvec[j + 2], s2);
+        s3 = fma(Di[i + (long long)(j + 3) * N], tvec[j + 3], s3);
       }
-      if (j <= i) s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
-      const double v = s0 + s1;
+      for (; j <= i; ++j) s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
+      const double v = (s0 + s1) + (s2 + s3);
       yj[i] = v;
       yv[i] = v;
     }
@@ -416,20 +459,22 @@ chol_forward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, cons
     const double* Pj = L + P.sn_lptr[J];
     double* cj = contrib + Q.sn_cptr[J];
     for (int r = N + tid; r < M; r += nt) {
-      double s0 = 0.0, s1 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int k = 0;
-      for (; k + 1 < N; k += 2) {
+      for (; k + 3 < N; k += 4) {
         s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
         s1 = fma(Pj[r + (long long)(k + 1) * M], yv[k + 1], s1);
+        s2 = fma(Pj[r + (long long)(k + 2) * M], yv[k + 2], s2);
+        s3 = fma(Pj[r + (long long)(k + 3) * M], yv[k + 3], s3);
       }
-      if (k < N) s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
-      cj[r - N] = s0 + s1;
+      for (; k < N; ++k) s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
+      cj[r - N] = (s0 + s1) + (s2 + s3);
     }
   }
 }
 
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSolveThreads)
 chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
                      double* __restrict__ y, int task0) {
   extern __shared__ __align__(16) double xb[];  // x at the rows below the diagonal block
@@ -451,8 +496,11 @@ chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, con
     // t = y_J - L21^T x_below : one warp per column, lanes stride the rows (coalesced), fixed-order shuffle tree
     for (int j = wid; j < N; j += nw) {
       const double* cj = Pj + (long long)j * M + N;
-      double s = 0.0;
-      for (int i = lane; i < M - N; i += 32) s = fma(cj[i], xb[i], s);
+      double s0 = 0.0, s1 = 0.0;
+      int i = lane;
+      for (; i + 32 < M - N; i += 64) { s0 = fma(cj[i], xb[i], s0); s1 = fma(cj[i + 32], xb[i + 32], s1); }
+      if (i < M - N) s0 = fma(cj[i], xb[i], s0);
+      double s = s0 + s1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) tvec[j] = xj[j] - s;
@@ -461,11 +509,14 @@ chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, con
     const double* Di = Dinv + Q.sn_dinvptr[J];
     for (int i = tid; i < N; i += nt) {  // x_J = Linv^T t
       const double* ci = Di + (long long)i * N;
-      double s0 = 0.0, s1 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int j = i;
-      for (; j + 1 < N; j += 2) { s0 = fma(ci[j], tvec[j], s0); s1 = fma(ci[j + 1], tvec[j + 1], s1); }
-      if (j < N) s0 = fma(ci[j], tvec[j], s0);
-      xj[i] = s0 + s1;
+      for (; j + 3 < N; j += 4) {
+        s0 = fma(ci[j], tvec[j], s0); s1 = fma(ci[j + 1], tvec[j + 1], s1);
+        s2 = fma(ci[j + 2], tvec[j + 2], s2); s3 = fma(ci[j + 3], tvec[j + 3], s3);
+      }
+      for (; j < N; ++j) s0 = fma(ci[j], tvec[j], s0);
+      xj[i] = (s0 + s1) + (s2 + s3);
     }
   }
 }
@@ -526,6 +577,10 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_rtile_tile_.upload(S_.rtile_tile, s); d_rtile_slot0_.upload(S_.rtile_slot0, s); d_rtile_nslots_.upload(S_.rtile_nslots, s);
   up64(d_sn_dinvptr_, S_.sn_dinvptr, s, keep);
   up64(d_sn_cptr_, S_.sn_cptr, s, keep);
+  up64(d_work_koff_, S_.work_koff, s, keep);
+  up64(d_work_reloff_, S_.work_reloff, s, keep);
+  d_work_mk_.upload(S_.work_mk, s); d_work_nk_.upload(S_.work_nk, s);
+  d_fwd_ptr_.upload(S_.fwd_ptr, s); d_fwd_src_.upload(S_.fwd_src, s);
   d_L_.alloc((size_t)S_.factor_doubles);
   d_Dinv_.alloc((size_t)S_.dinv_doubles);
   d_Ldiag_.alloc((size_t)S_.dinv_doubles);
@@ -547,7 +602,8 @@ CholDev CholeskyGpu::dev() const {
 CholPlanDev CholeskyGpu::plan() const {
   return CholPlanDev{d_tile_sn_.p, d_tile_r0_.p, d_tile_c0_.p, d_tile_work_ptr_.p, d_work_u_.p, d_work_a0_.p, d_work_a1_.p,
                      d_work_b0_.p, d_work_b1_.p, d_sn_tile_ptr_.p, d_sn_chunk_ptr_.p, d_chunk_sn_.p, d_chunk_b0_.p,
-                     d_chunk_nb_.p, d_sn_dinvptr_.p, d_sn_cptr_.p};
+                     d_chunk_nb_.p, d_sn_dinvptr_.p, d_sn_cptr_.p, d_work_koff_.p, d_work_reloff_.p, d_work_mk_.p,
+                     d_work_nk_.p, d_fwd_ptr_.p, d_fwd_src_.p};
 }
 
 template <int D>
@@ -628,7 +684,7 @@ void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCoun
     for (int l = 0; l < S.nlevels; ++l) {
       const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
       if (nt == 0) continue;
-      chol_forward_kernel<D><<<nt, 128, 0, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, d_contrib_.p, t0);
+      chol_forward_kernel<D><<<nt, kSolveThreads, 0, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, d_contrib_.p, t0);
       count();
     }
   }
@@ -638,7 +694,7 @@ void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCoun
     for (int l = S.nlevels - 1; l >= 0; --l) {
       const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
       if (nt == 0) continue;
-      chol_backward_kernel<D><<<nt, 128, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, t0);
+      chol_backward_kernel<D><<<nt, kSolveThreads, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, t0);
       count();
     }
     chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, d_status_.p);

@@ -51,7 +51,8 @@ class CholeskyGpu {
   DevBuf<int> d_tile_sn_, d_tile_r0_, d_tile_c0_, d_tile_work_ptr_, d_work_u_, d_work_a0_, d_work_a1_, d_work_b0_, d_work_b1_;
   DevBuf<int> d_sn_tile_ptr_, d_sn_chunk_ptr_, d_chunk_sn_, d_chunk_b0_, d_chunk_nb_, d_level_chunks_;
   DevBuf<int> d_group_tile_, d_group_w0_, d_group_w1_, d_group_slot_, d_rtile_tile_, d_rtile_slot0_, d_rtile_nslots_;
-  DevBuf<long long> d_sn_dinvptr_, d_sn_cptr_;
+  DevBuf<long long> d_sn_dinvptr_, d_sn_cptr_, d_work_koff_, d_work_reloff_;
+  DevBuf<int> d_work_mk_, d_work_nk_, d_fwd_ptr_, d_fwd_src_;
   DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_, d_gscratch_, d_contrib_;
   DevBuf<int> d_status_;
   int nblk_ = 0;

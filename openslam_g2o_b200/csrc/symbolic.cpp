@@ -400,6 +400,17 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
       }
     }
   }
+  {
+    const int nw = (int)S.work_u.size();
+    S.work_koff.resize(nw); S.work_reloff.resize(nw); S.work_mk.resize(nw); S.work_nk.resize(nw);
+    for (int q = 0; q < nw; ++q) {
+      const int u = S.work_u[q], K = S.upd_k[u];
+      S.work_koff[q] = S.sn_lptr[K] + (int64_t)S.upd_p0[u] * d;
+      S.work_reloff[q] = S.upd_relptr[u];
+      S.work_mk[q] = S.sn_nrow[K] * d;
+      S.work_nk[q] = S.sn_ncol[K] * d;
+    }
+  }
   S.sn_chunk_ptr.assign(ns + 1, 0);
   S.sn_dinvptr.assign(ns + 1, 0);
   for (int J = 0; J < ns; ++J) {
@@ -424,6 +435,28 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   S.group_items = 6;
   S.sn_cptr.assign(ns + 1, 0);
   for (int J = 0; J < ns; ++J) S.sn_cptr[J + 1] = S.sn_cptr[J] + (int64_t)(S.sn_nrow[J] - S.sn_ncol[J]) * d;
+  {  // forward-solve gather lists
+    const int n = nb * d;
+    S.fwd_ptr.assign(n + 1, 0);
+    for (int J = 0; J < ns; ++J)
+      for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
+        const int K = S.upd_k[u];
+        const int* kr = S.sn_rows.data() + S.sn_rowptr[K];
+        for (int p = S.upd_p0[u]; p < S.upd_p1[u]; ++p)
+          for (int rr = 0; rr < d; ++rr) S.fwd_ptr[kr[p] * d + rr + 1]++;
+      }
+    for (int i = 0; i < n; ++i) S.fwd_ptr[i + 1] += S.fwd_ptr[i];
+    S.fwd_src.assign(S.fwd_ptr[n], 0);
+    std::vector<int> fill(S.fwd_ptr.begin(), S.fwd_ptr.end() - 1);
+    for (int J = 0; J < ns; ++J)  // ascending J, then ascending K inside: every row list is in (K, p) order
+      for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
+        const int K = S.upd_k[u];
+        const int* kr = S.sn_rows.data() + S.sn_rowptr[K];
+        for (int p = S.upd_p0[u]; p < S.upd_p1[u]; ++p)
+          for (int rr = 0; rr < d; ++rr)
+            S.fwd_src[fill[kr[p] * d + rr]++] = (int)(S.sn_cptr[K] + (int64_t)(p - S.sn_ncol[K]) * d + rr);
+      }
+  }
   for (int l = 0; l < S.nlevels; ++l) {
     bool singletons = true;
     int tiles = 0, chunks = 0, ntask = S.level_ptr[l + 1] - S.level_ptr[l], smem = 0;

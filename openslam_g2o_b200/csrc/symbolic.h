@@ -62,6 +62,9 @@ struct SymbolicFactor {
   std::vector<int> tile_sn, tile_r0, tile_c0;      // supernode, first local block row / block column
   std::vector<int> tile_work_ptr;                  // ntiles+1
   std::vector<int> work_u, work_a0, work_a1, work_b0, work_b1;  // update index; row / column ranges relative to p0
+  // the same work items flattened for the device (one level of indirection instead of four)
+  std::vector<int64_t> work_koff, work_reloff;     // offset of row p0 of the updating panel in L; offset into rel
+  std::vector<int> work_mk, work_nk;               // leading dimension / #columns of the updating panel (scalars)
   // row chunks of the panel factorisation: every chunk CTA factors the diagonal block and solves its block rows
   int chunk_blocks = 0;
   std::vector<int> sn_chunk_ptr;                   // nsn+1
@@ -78,6 +81,9 @@ struct SymbolicFactor {
   int max_group_slots = 0;
   // forward solve: supernode J leaves L21*y_J (its contribution to every ancestor) at sn_cptr[J]
   std::vector<int64_t> sn_cptr;                    // nsn+1, scalar units
+  // ... and every scalar row of the permuted system lists the contribution entries it has to subtract, in
+  // ascending (supernode, row) order (fixed summation order)
+  std::vector<int> fwd_ptr, fwd_src;               // n+1 ; indices into the contribution array
   // inverses of the triangular diagonal blocks (for the solves)
   std::vector<int64_t> sn_dinvptr;                 // nsn+1
   int64_t dinv_doubles = 0;
