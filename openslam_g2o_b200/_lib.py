@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libg2o_b200.so")
+LIB_PATH = os.environ.get("G2O_B200_LIB", os.path.join(_HERE, "libg2o_b200.so"))  # override: instrumented debug builds
 
 OK = 0
 NOT_POSITIVE_DEFINITE = 1

@@ -158,22 +158,57 @@ __device__ void subtract_tile(const CholDev& P, const CholPlanDev& Q, double* __
   }
 }
 
+#ifdef CHOL_TIMING
+__device__ unsigned long long g_chol_timing[8];
+#define TCK(i) do { if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_chol_timing[i], _n - _t0); _t0 = _n; } } while (0)
+#else
+#define TCK(i) do {} while (0)
+#endif
+
+// 1/sqrt(s) to full double accuracy: single-precision seed (one MUFU) + two Newton steps in double; falls back to the
+// library routine outside the float range.  Sits on the critical path of every block column.
+__device__ __forceinline__ double fast_rsqrt(double s) {
+  if (s < 1e-30 || s > 1e30) return rsqrt(s);
+  double r = (double)rsqrtf((float)s);
+  const double hs = -0.5 * s;
+  r = r * fma(hs * r, r, 1.5);
+  r = r * fma(hs * r, r, 1.5);
+  return r;
+}
+
 template <int D>
 __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                             int chunk, bool write_diag, double* __restrict__ Sm, int* status) {
+                             int chunk, bool write_diag, double* __restrict__ Sm, int* status, double* y,
+                             double* contrib) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int J = Q.chunk_sn[chunk];
   const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
   const int crow0 = Q.chunk_b0[chunk] * D, crows = Q.chunk_nb[chunk] * D;
-  const int R = N + crows;  // rows staged: the diagonal block, then this chunk's rows
+  // rows staged: the diagonal block, this chunk's rows and - when the forward solve rides along - the right-hand
+  // side of the supernode as one more row: its "triangular solve" IS the forward substitution y_J = L11^-1 t
+  const bool rhs = y != nullptr;
+  const int Rp = N + crows;
+  const int R = Rp + (rhs ? 1 : 0);
+  const int col0s = P.sn_col0[J] * D;
   double* Pj = L + P.sn_lptr[J];
+#ifdef CHOL_TIMING
+  unsigned long long _t0 = clock64();
+#endif
   __syncthreads();
   for (int i = tid; i < R * N; i += nt) {
     const int c = i / R, r = i - c * R;
-    const int gr = r < N ? r : crow0 + (r - N);
-    Sm[i] = Pj[gr + (long long)c * M];
+    if (r < Rp) {
+      const int gr = r < N ? r : crow0 + (r - N);
+      Sm[i] = Pj[gr + (long long)c * M];
+    } else {  // t_c = (P b)_c - contributions of the descendants, summed in list order
+      const int g = col0s + c;
+      double tsum = y[g];
+      for (int e = Q.fwd_ptr[g]; e < Q.fwd_ptr[g + 1]; ++e) tsum -= contrib[Q.fwd_src[e]];
+      Sm[i] = tsum;
+    }
   }
   __syncthreads();
+  TCK(0);
   const int row = tid;  // one panel row per thread (R <= 192 <= blockDim)
   const int ncb = N / D;
   bool bad = false;
@@ -185,26 +220,23 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
     for (int r = 0; r < D; ++r)
 #pragma unroll
       for (int c = 0; c <= r; ++c) Lp[r][c] = Sm[(j0 + r) + (j0 + c) * R];
+    // right-looking inside the block: as soon as column k is scaled the remaining entries are updated with
+    // independent FMAs, so the dependent chain per column is rsqrt -> multiply -> one FMA
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       double s = Lp[k][k];
-#pragma unroll
-      for (int m = 0; m < k; ++m) s = fma(-Lp[k][m], Lp[k][m], s);
       if (!(s > 0.0)) { bad = true; s = 1.0; }  // d <= 0: not positive definite (csparse_helper.cpp:136)
-      // one reciprocal square root (+ one Newton step to full double accuracy) instead of sqrt and a division:
-      // this sits on the critical path of every block column
-      double rs = rsqrt(s);
-      rs = fma(rs * 0.5, fma(-s * rs, rs, 1.0), rs);
+      const double rs = fast_rsqrt(s);
       inv[k] = rs;
       Lp[k][k] = s * rs;
 #pragma unroll
-      for (int r = k + 1; r < D; ++r) {
-        double t = Lp[r][k];
+      for (int r = k + 1; r < D; ++r) Lp[r][k] *= rs;
 #pragma unroll
-        for (int m = 0; m < k; ++m) t = fma(-Lp[r][m], Lp[k][m], t);
-        Lp[r][k] = t * inv[k];
-      }
+      for (int c = k + 1; c < D; ++c)
+#pragma unroll
+        for (int r = c; r < D; ++r) Lp[r][c] = fma(-Lp[r][k], Lp[c][k], Lp[r][c]);
     }
+    TCK(1);
     double x[D];
     const bool below = row >= j0 + D && row < R;
     if (row >= j0 && row < j0 + D) {
@@ -219,16 +251,17 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
 #pragma unroll
       for (int c = 0; c < D; ++c) x[c] = Sm[row + (j0 + c) * R];
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
-        double t = x[c];
+      for (int c = 0; c < D; ++c) {  // right-looking substitution: chain per column = multiply -> one FMA
+        x[c] *= inv[c];
 #pragma unroll
-        for (int m = 0; m < c; ++m) t = fma(-x[m], Lp[c][m], t);
-        x[c] = t * inv[c];
+        for (int m = c + 1; m < D; ++m) x[m] = fma(-x[c], Lp[m][c], x[m]);
       }
 #pragma unroll
       for (int c = 0; c < D; ++c) Sm[row + (j0 + c) * R] = x[c];
     }
+    TCK(2);
     __syncthreads();
+    TCK(3);
     {
       // rank-D trailing update T(i,c) -= sum_k X(i,k) X(c,k), i >= j0+D, c in [j0+D, N): every thread takes
       // 2 rows x 4 columns per item (rows rp apart so that a warp walks consecutive rows); entries above the
@@ -273,7 +306,9 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
           }
       }
     }
+    TCK(4);
     __syncthreads();
+    TCK(5);
   }
   if (bad && tid == 0) *status = 1;
   for (int i = tid; i < R * N; i += nt) {
@@ -282,15 +317,35 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
       // the factored diagonal block goes to its own array: sibling chunk CTAs are still reading the unfactored
       // block from the panel (every chunk factors it redundantly), so it must not be overwritten in place
       if (write_diag && r >= c) Ldiag[Q.sn_dinvptr[J] + r + (long long)c * N] = Sm[i];
-    } else {
+    } else if (r < Rp) {
       Pj[crow0 + (r - N) + (long long)c * M] = Sm[i];
+    } else if (write_diag) {
+      y[col0s + c] = Sm[i];  // y_J
     }
   }
+  if (rhs) {
+    // c_J = L21 y_J for this chunk's rows: what every ancestor will subtract from its right-hand side
+    double* cj = contrib + Q.sn_cptr[J] + (crow0 - N);
+    for (int r = tid; r < crows; r += nt) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = 0;
+      for (; c + 3 < N; c += 4) {
+        s0 = fma(Sm[N + r + c * R], Sm[Rp + c * R], s0);
+        s1 = fma(Sm[N + r + (c + 1) * R], Sm[Rp + (c + 1) * R], s1);
+        s2 = fma(Sm[N + r + (c + 2) * R], Sm[Rp + (c + 2) * R], s2);
+        s3 = fma(Sm[N + r + (c + 3) * R], Sm[Rp + (c + 3) * R], s3);
+      }
+      for (; c < N; ++c) s0 = fma(Sm[N + r + c * R], Sm[Rp + c * R], s0);
+      cj[r] = (s0 + s1) + (s2 + s3);
+    }
+  }
+  TCK(6);
 }
 
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
-chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag, int task0, int* status) {
+chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag, int task0, int* status,
+                  double* y, double* contrib) {
   extern __shared__ __align__(16) double smem[];  // update operands and factor staging share the same bytes
   double* acc = smem;
   double* As = smem + kTile * kTile;
@@ -306,7 +361,7 @@ chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __re
       __syncthreads();
     }
     const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
-    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, smem, status);
+    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, smem, status, y, contrib);
     __syncthreads();
   }
 }
@@ -353,10 +408,10 @@ chol_reduce_tiles_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
 chol_factor_chunks_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                          const int* __restrict__ chunks, int* status) {
+                          const int* __restrict__ chunks, int* status, double* y, double* contrib) {
   extern __shared__ __align__(16) double smem[];
   const int ch = chunks[blockIdx.x];
-  factor_chunk<D>(P, Q, L, Ldiag, ch, ch == Q.sn_chunk_ptr[Q.chunk_sn[ch]], smem, status);
+  factor_chunk<D>(P, Q, L, Ldiag, ch, ch == Q.sn_chunk_ptr[Q.chunk_sn[ch]], smem, status, y, contrib);
 }
 
 // inverse of every triangular diagonal block (one CTA per supernode): the solves become matrix-vector products.
@@ -607,7 +662,8 @@ CholPlanDev CholeskyGpu::plan() const {
 }
 
 template <int D>
-void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
+void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
+                           EventProfiler* prof) {
   const SymbolicFactor& S = S_;
   const CholDev P = dev();
   const CholPlanDev Q = plan();
@@ -624,15 +680,23 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, cudaStream_
       chol_add_lambda_kernel<D><<<ceil_div((int64_t)S.nb * D, 256), 256, 0, s>>>(S.nb, d_diag_dst_.p, d_diag_ld_.p, d_lambda, L);
       count();
     }
+    if (d_b) {  // the forward substitution rides along with the factorisation (one more row per panel)
+      chol_permute_in_kernel<D><<<ceil_div(S.nb * D, 256), 256, 0, s>>>(S.nb, d_perm_.p, d_b, d_y_.p);
+      count();
+    }
   }
+  double* yv = d_b ? d_y_.p : nullptr;
+  double* contrib = d_contrib_.p;
+  const size_t rhs_smem = d_b ? (size_t)S.max_ncol * D * sizeof(double) : 0;
+  forward_done_ = d_b != nullptr;
   const size_t upd_smem = (size_t)kUpdateSmemDoubles * sizeof(double);
   for (int l = 0; l < S.nlevels; ++l) {
     const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
     if (nt == 0) continue;
     if (S.level_kind[l] == 0) {
       ScopedPhase ph(prof, PH_CH_FUSED);
-      const size_t smem = std::max(upd_smem, (size_t)S.level_smem[l]);
-      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, d_Ldiag_.p, t0, status);
+      const size_t smem = std::max(upd_smem, (size_t)S.level_smem[l] + rhs_smem);
+      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, d_Ldiag_.p, t0, status, yv, contrib);
       count();
     } else {
       const int g0 = S.level_group_ptr[l], ng = S.level_group_ptr[l + 1] - g0;
@@ -651,7 +715,7 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, cudaStream_
         count();
       }
       ScopedPhase ph(prof, PH_CH_PANEL);
-      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l], s>>>(P, Q, L, d_Ldiag_.p, d_level_chunks_.p + c0, status);
+      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l] + rhs_smem, s>>>(P, Q, L, d_Ldiag_.p, d_level_chunks_.p + c0, status, yv, contrib);
       count();
     }
   }
@@ -664,9 +728,10 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, cudaStream_
   B200_CUDA(cudaGetLastError());
 }
 
-void CholeskyGpu::factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
-  if (S_.d == 3) factor_t<3>(dA, d_lambda, s, lc, prof);
-  else factor_t<6>(dA, d_lambda, s, lc, prof);
+void CholeskyGpu::factor(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
+                         EventProfiler* prof) {
+  if (S_.d == 3) factor_t<3>(dA, d_lambda, d_b, s, lc, prof);
+  else factor_t<6>(dA, d_lambda, d_b, s, lc, prof);
 }
 
 template <int D>
@@ -677,7 +742,7 @@ void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCoun
   const int n = S.nb * D;
   auto count = [&](int k = 1) { if (lc) lc->n += k; };
   double* y = d_y_.p;
-  {
+  if (!forward_done_) {
     ScopedPhase ph(prof, PH_CH_FORWARD);
     chol_permute_in_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, b, y);
     count();
@@ -700,6 +765,7 @@ void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCoun
     chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, d_status_.p);
     count();
   }
+  forward_done_ = false;
   B200_CUDA(cudaGetLastError());
 }
 
@@ -709,3 +775,10 @@ void CholeskyGpu::solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCo
 }
 
 }  // namespace g2o_b200
+
+#ifdef CHOL_TIMING
+extern "C" void b200_debug_chol_timing(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g2o_b200::g_chol_timing, z, sizeof(z)); }
+}
+#endif

@@ -31,7 +31,10 @@ class CholeskyGpu {
   // numeric factorisation of A + lambda*I (A: device, input block order, d*d col-major per block).
   // d_lambda may be nullptr (lambda = 0).  Asynchronous on s; the not-positive-definite outcome lands in
   // the device flag read by status().
-  void factor(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
+  // d_b (optional): right-hand side; when given, the forward substitution is fused into the factorisation (the
+  // supernode's right-hand side rides along as one more panel row) and the next solve() only runs the backward sweep.
+  void factor(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
+              EventProfiler* prof = nullptr);
   // x = A^-1 b (both device, length nb*d, original ordering).  Asynchronous on s.
   void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
   int* status_ptr() { return d_status_.p; }  // device int: 0 ok, 1 not positive definite
@@ -59,7 +62,9 @@ class CholeskyGpu {
   CholDev dev() const;
   CholPlanDev plan() const;
   template <int D>
-  void factor_t(const double* dA, const double* d_lambda, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof);
+  void factor_t(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
+                EventProfiler* prof);
+  bool forward_done_ = false;
   template <int D>
   void solve_t(const double* b, double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof);
 };

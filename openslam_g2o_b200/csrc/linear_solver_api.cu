@@ -101,7 +101,7 @@ int b200_ls_solve(b200_linear_solver* ls, int nblocks, int block_dim, const int3
     ls->dA.upload(values, (size_t)nblk * block_dim * block_dim, s);
     ls->db.upload(b, n, s);
     ls->dx.alloc(n);
-    ls->chol.factor(ls->dA.p, nullptr, s, &ls->lc);
+    ls->chol.factor(ls->dA.p, nullptr, ls->db.p, s, &ls->lc);
     ls->chol.solve(ls->db.p, ls->dx.p, s, &ls->lc);
     B200_CUDA(cudaMemcpyAsync(ls->h_status, ls->chol.status_ptr(), sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));

@@ -483,7 +483,7 @@ int enqueue_solve(b200_ctx* c) {
   cudaStream_t s = c->stream;
   const double* d_lambda = c->d_scalars.p + 3;
   if (!c->schur) {
-    { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hpp.p, d_lambda, s, &c->lc, &c->prof); }
+    { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hpp.p, d_lambda, c->d_b.p, s, &c->lc, &c->prof); }
     { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(c->d_b.p, c->d_x.p, s, &c->lc, &c->prof); }
     return 0;
   }
@@ -501,7 +501,7 @@ int enqueue_solve(b200_ctx* c) {
     int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);
     if (rc) return rc;
   }
-  { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, s, &c->lc, &c->prof); }
+  { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, bschur_ptr(c), s, &c->lc, &c->prof); }
   { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc, &c->prof); }
   if (c->nl > 0) {
     PhaseTimer pt(c, PH_BACKSUB);

@@ -432,7 +432,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   S.level_chunk_ptr.assign(S.nlevels + 1, 0);
   S.level_group_ptr.assign(S.nlevels + 1, 0);
   S.level_rtile_ptr.assign(S.nlevels + 1, 0);
-  S.group_items = 6;
+  S.group_items = 3;
   S.sn_cptr.assign(ns + 1, 0);
   for (int J = 0; J < ns; ++J) S.sn_cptr[J + 1] = S.sn_cptr[J] + (int64_t)(S.sn_nrow[J] - S.sn_ncol[J]) * d;
   {  // forward-solve gather lists
