@@ -178,8 +178,8 @@ __device__ __forceinline__ double fast_rsqrt(double s) {
 
 template <int D>
 __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                             int chunk, bool write_diag, double* __restrict__ Sm, int* status, double* y,
-                             double* contrib) {
+                             int chunk, bool write_diag, double* __restrict__ Sm, int* status,
+                             const double* __restrict__ y, double* __restrict__ z, double* contrib) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int J = Q.chunk_sn[chunk];
   const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
@@ -195,16 +195,28 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
   unsigned long long _t0 = clock64();
 #endif
   __syncthreads();
-  for (int i = tid; i < R * N; i += nt) {
-    const int c = i / R, r = i - c * R;
-    if (r < Rp) {
-      const int gr = r < N ? r : crow0 + (r - N);
-      Sm[i] = Pj[gr + (long long)c * M];
-    } else {  // t_c = (P b)_c - contributions of the descendants, summed in list order
-      const int g = col0s + c;
-      double tsum = y[g];
-      for (int e = Q.fwd_ptr[g]; e < Q.fwd_ptr[g + 1]; ++e) tsum -= contrib[Q.fwd_src[e]];
-      Sm[i] = tsum;
+  {
+    // warps split in two groups: one streams the panel in, the other gathers the right-hand side
+    // t_c = (P b)_c - sum of the descendants' contributions (lanes stride the list, fixed shuffle tree)
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int ngather = rhs ? max(1, nw / 4) : 0;
+    if (wid < ngather) {
+      for (int c = wid; c < N; c += ngather) {
+        const int g = col0s + c;
+        const int e0 = Q.fwd_ptr[g], e1 = Q.fwd_ptr[g + 1];
+        double part = 0.0;
+        for (int e = e0 + lane; e < e1; e += 32) part += contrib[Q.fwd_src[e]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) Sm[Rp + c * R] = y[g] - part;
+      }
+    } else {
+      const int t2 = tid - ngather * 32, n2 = nt - ngather * 32;
+      for (int i = t2; i < Rp * N; i += n2) {
+        const int c = i / Rp, r = i - c * Rp;
+        const int gr = r < N ? r : crow0 + (r - N);
+        Sm[r + c * R] = Pj[gr + (long long)c * M];
+      }
     }
   }
   __syncthreads();
@@ -320,7 +332,7 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
     } else if (r < Rp) {
       Pj[crow0 + (r - N) + (long long)c * M] = Sm[i];
     } else if (write_diag) {
-      y[col0s + c] = Sm[i];  // y_J
+      z[col0s + c] = Sm[i];  // y_J goes to its own vector: sibling chunks still read (P b)_J from y
     }
   }
   if (rhs) {
@@ -345,7 +357,7 @@ __device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __r
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
 chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag, int task0, int* status,
-                  double* y, double* contrib) {
+                  const double* __restrict__ y, double* __restrict__ z, double* contrib) {
   extern __shared__ __align__(16) double smem[];  // update operands and factor staging share the same bytes
   double* acc = smem;
   double* As = smem + kTile * kTile;
@@ -361,7 +373,7 @@ chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __re
       __syncthreads();
     }
     const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
-    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, smem, status, y, contrib);
+    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, smem, status, y, z, contrib);
     __syncthreads();
   }
 }
@@ -408,10 +420,11 @@ chol_reduce_tiles_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const
 template <int D>
 __global__ void __launch_bounds__(kCholThreads)
 chol_factor_chunks_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                          const int* __restrict__ chunks, int* status, double* y, double* contrib) {
+                          const int* __restrict__ chunks, int* status, const double* __restrict__ y,
+                          double* __restrict__ z, double* contrib) {
   extern __shared__ __align__(16) double smem[];
   const int ch = chunks[blockIdx.x];
-  factor_chunk<D>(P, Q, L, Ldiag, ch, ch == Q.sn_chunk_ptr[Q.chunk_sn[ch]], smem, status, y, contrib);
+  factor_chunk<D>(P, Q, L, Ldiag, ch, ch == Q.sn_chunk_ptr[Q.chunk_sn[ch]], smem, status, y, z, contrib);
 }
 
 // inverse of every triangular diagonal block (one CTA per supernode): the solves become matrix-vector products.
@@ -642,6 +655,7 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_gscratch_.alloc((size_t)std::max(S_.max_group_slots, 1) * kTile * kTile);
   d_contrib_.alloc((size_t)std::max<int64_t>(S_.sn_cptr[S_.nsn], 1));
   d_y_.alloc((size_t)nb * d);
+  d_z_.alloc((size_t)nb * d);
   d_status_.alloc(1);
   if (!host_only_flag()) {
     B200_CUDA(cudaStreamSynchronize(s));  // the temporaries above die here
@@ -685,7 +699,8 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
       count();
     }
   }
-  double* yv = d_b ? d_y_.p : nullptr;
+  const double* yv = d_b ? d_y_.p : nullptr;
+  double* zv = d_z_.p;
   double* contrib = d_contrib_.p;
   const size_t rhs_smem = d_b ? (size_t)S.max_ncol * D * sizeof(double) : 0;
   forward_done_ = d_b != nullptr;
@@ -696,7 +711,7 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
     if (S.level_kind[l] == 0) {
       ScopedPhase ph(prof, PH_CH_FUSED);
       const size_t smem = std::max(upd_smem, (size_t)S.level_smem[l] + rhs_smem);
-      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, d_Ldiag_.p, t0, status, yv, contrib);
+      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, d_Ldiag_.p, t0, status, yv, zv, contrib);
       count();
     } else {
       const int g0 = S.level_group_ptr[l], ng = S.level_group_ptr[l + 1] - g0;
@@ -715,7 +730,7 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
         count();
       }
       ScopedPhase ph(prof, PH_CH_PANEL);
-      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l] + rhs_smem, s>>>(P, Q, L, d_Ldiag_.p, d_level_chunks_.p + c0, status, yv, contrib);
+      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l] + rhs_smem, s>>>(P, Q, L, d_Ldiag_.p, d_level_chunks_.p + c0, status, yv, zv, contrib);
       count();
     }
   }
@@ -741,7 +756,7 @@ void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCoun
   const CholPlanDev Q = plan();
   const int n = S.nb * D;
   auto count = [&](int k = 1) { if (lc) lc->n += k; };
-  double* y = d_y_.p;
+  double* y = d_z_.p;  // forward result / backward in place
   if (!forward_done_) {
     ScopedPhase ph(prof, PH_CH_FORWARD);
     chol_permute_in_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, b, y);

@@ -56,7 +56,7 @@ class CholeskyGpu {
   DevBuf<int> d_group_tile_, d_group_w0_, d_group_w1_, d_group_slot_, d_rtile_tile_, d_rtile_slot0_, d_rtile_nslots_;
   DevBuf<long long> d_sn_dinvptr_, d_sn_cptr_, d_work_koff_, d_work_reloff_;
   DevBuf<int> d_work_mk_, d_work_nk_, d_fwd_ptr_, d_fwd_src_;
-  DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_, d_gscratch_, d_contrib_;
+  DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_, d_z_, d_gscratch_, d_contrib_;
   DevBuf<int> d_status_;
   int nblk_ = 0;
   CholDev dev() const;

@@ -371,6 +371,8 @@ ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict
 }
 
 // ------------------------------------------------------------------ Schur complement
+constexpr int kDinvStride = 10;  // 9 doubles padded to 80 B: rows stay 16-byte aligned for double2 loads
+
 // S1: per landmark Dinv = (Hll + lambda I)^-1, db = Dinv b_l           (block_solver.hpp:381-395)
 __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__ Hll, const double* __restrict__ b_l,
                                               const double* __restrict__ lambda, double* __restrict__ Dinv,
@@ -385,7 +387,7 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
   inverse3(D, Di);
   const double b0 = b_l[3ll * l], b1 = b_l[3ll * l + 1], b2 = b_l[3ll * l + 2];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) Dinv[9ll * l + i] = Di[i];
+  for (int i = 0; i < 9; ++i) Dinv[kDinvStride * (long long)l + i] = Di[i];
 #pragma unroll
   for (int r = 0; r < 3; ++r) db[3ll * l + r] = Di[r] * b0 + Di[r + 3] * b1 + Di[r + 6] * b2;
 }
@@ -395,7 +397,7 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
 //   bschur_i1     = hpp_scale*b_i1 - sum_l Hpl(i1,l) db_l        (diagonal targets only)
 // contributions of a target are stored in ascending landmark order (block_solver.hpp:397-439).
 // hpp_scale is 1 on a single GPU; with landmark sharding only rank 0 adds the (already reduced) Hpp term.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __restrict__ t_col,
                     const int* __restrict__ t_hpp, const int* __restrict__ sc_ptr, const int* __restrict__ sc_lm,
                     const int* __restrict__ sc_a, const int* __restrict__ sc_b, const double* __restrict__ Hpp,
@@ -414,25 +416,32 @@ schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __res
   for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
   for (int c = sc_ptr[t] + lane; c < sc_ptr[t + 1]; c += 32) {
     const int l = sc_lm[c];
-    const double* Ba = Hpl + 18ll * sc_a[c];
-    const double* Bb = Hpl + 18ll * sc_b[c];
-    double Di[9], A[18], T[18];
+    // 16-byte vector loads: a 6x3 block is 9 double2, a padded Dinv row 5
+    const double2* Ba = reinterpret_cast<const double2*>(Hpl + 18ll * sc_a[c]);
+    const double2* Bb = reinterpret_cast<const double2*>(Hpl + 18ll * sc_b[c]);
+    const double2* Dp = reinterpret_cast<const double2*>(Dinv + kDinvStride * (long long)l);
+    double Di[10], A[18], T[18];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Di[k] = Dinv[9ll * l + k];
+    for (int k = 0; k < 5; ++k) { const double2 v = __ldg(Dp + k); Di[2 * k] = v.x; Di[2 * k + 1] = v.y; }
 #pragma unroll
-    for (int k = 0; k < 18; ++k) A[k] = Ba[k];
+    for (int k = 0; k < 9; ++k) { const double2 v = __ldg(Ba + k); A[2 * k] = v.x; A[2 * k + 1] = v.y; }
     mm<6, 3, 3>(A, Di, T);  // BDinv
     if (diag) {
       const double d0 = db[3ll * l], d1 = db[3ll * l + 1], d2 = db[3ll * l + 2];
 #pragma unroll
       for (int r = 0; r < 6; ++r) cacc[r] += A[r] * d0 + A[r + 6] * d1 + A[r + 12] * d2;
     }
+    // Hschur(i1,i2) -= T * Bb^T, one column of Bb (6 values = 3 double2) at a time to keep registers low
 #pragma unroll
-    for (int k = 0; k < 18; ++k) A[k] = Bb[k];
+    for (int j = 0; j < 3; ++j) {
+      double bj[6];
 #pragma unroll
-    for (int c2 = 0; c2 < 6; ++c2)
+      for (int k = 0; k < 3; ++k) { const double2 v = __ldg(Bb + 3 * j + k); bj[2 * k] = v.x; bj[2 * k + 1] = v.y; }
 #pragma unroll
-      for (int r = 0; r < 6; ++r) acc[r + 6 * c2] += T[r] * A[c2] + T[r + 6] * A[c2 + 6] + T[r + 12] * A[c2 + 12];
+      for (int c2 = 0; c2 < 6; ++c2)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[r + 6 * c2] = fma(T[r + 6 * j], bj[c2], acc[r + 6 * c2]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
@@ -478,7 +487,7 @@ __global__ void ba_backsub_kernel(int nl, const int* __restrict__ lm_eptr, const
     }
     c0 += t0; c1 += t1; c2 += t2;
   }
-  const double* Di = Dinv + 9ll * l;
+  const double* Di = Dinv + kDinvStride * (long long)l;
 #pragma unroll
   for (int r = 0; r < 3; ++r) x_l[3ll * l + r] = Di[r] * c0 + Di[r + 3] * c1 + Di[r + 6] * c2;
 }

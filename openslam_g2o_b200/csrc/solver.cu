@@ -381,7 +381,7 @@ int build_structure_impl(b200_ctx* c) {
     c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s); c->d_sc_ptr.upload(sc_ptr, s);
     c->d_Hpp.alloc((size_t)np * 36 + (size_t)c->sizeP);  // [Hpp | b_p staging] contiguous for one all-reduce
     c->d_Hll.alloc((size_t)std::max(nl, 1) * 9); c->d_Hpl.alloc((size_t)std::max(nslot, 1) * 18);
-    c->d_Dinv.alloc((size_t)std::max(nl, 1) * 9); c->d_db.alloc((size_t)std::max(nl, 1) * 3);
+    c->d_Dinv.alloc((size_t)std::max(nl, 1) * k::kDinvStride); c->d_Dinv.zero(s); c->d_db.alloc((size_t)std::max(nl, 1) * 3);
     c->d_Hschur.alloc((size_t)nT * 36 + (size_t)c->sizeP + 8);  // [Hschur | bschur | scalars] contiguous
     if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
     bp_colptr = c->hs_colptr; bp_rowidx = c->hs_rowidx;
