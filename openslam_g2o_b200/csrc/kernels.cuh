@@ -397,16 +397,22 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
 //   bschur_i1     = hpp_scale*b_i1 - sum_l Hpl(i1,l) db_l        (diagonal targets only)
 // contributions of a target are stored in ascending landmark order (block_solver.hpp:397-439).
 // hpp_scale is 1 on a single GPU; with landmark sharding only rank 0 adds the (already reduced) Hpp term.
+// WPT warps per target: 1 for ordinary blocks (4 targets per CTA), 4 (a whole CTA) for the hot ones - mostly the
+// diagonal blocks, which collect every observation of a camera.  Partial sums are combined in a fixed order.
+template <int WPT>
 __global__ void __launch_bounds__(128, 3)
-schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __restrict__ t_col,
-                    const int* __restrict__ t_hpp, const int* __restrict__ sc_ptr, const int* __restrict__ sc_lm,
-                    const int* __restrict__ sc_a, const int* __restrict__ sc_b, const double* __restrict__ Hpp,
-                    const double* __restrict__ Hpl, const double* __restrict__ Dinv, const double* __restrict__ db,
-                    const double* __restrict__ b_p, const double* __restrict__ lambda, double hpp_scale,
-                    double* __restrict__ Hschur, double* __restrict__ bschur) {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+schur_reduce_kernel(int nlist, const int* __restrict__ tlist, const int* __restrict__ t_row,
+                    const int* __restrict__ t_col, const int* __restrict__ t_hpp, const int* __restrict__ sc_ptr,
+                    const int* __restrict__ sc_lm, const int* __restrict__ sc_a, const int* __restrict__ sc_b,
+                    const double* __restrict__ Hpp, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+                    const double* __restrict__ db, const double* __restrict__ b_p, const double* __restrict__ lambda,
+                    double hpp_scale, double* __restrict__ Hschur, double* __restrict__ bschur) {
+  constexpr int STRIDE = 32 * WPT;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / STRIDE;
+  const int g = threadIdx.x % STRIDE;
   const int lane = threadIdx.x & 31;
-  if (t >= ntarget) return;
+  const bool active = slot < nlist;
+  const int t = active ? tlist[slot] : 0;
   const int i1 = t_row[t], i2 = t_col[t];
   const bool diag = i1 == i2;
   double acc[36], cacc[6];
@@ -414,11 +420,18 @@ schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __res
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
-  for (int c = sc_ptr[t] + lane; c < sc_ptr[t + 1]; c += 32) {
-    const int l = sc_lm[c];
+  int c = sc_ptr[t] + g;
+  const int cend = active ? sc_ptr[t + 1] : 0;
+  int l = 0, sa = 0, sb = 0;
+  if (c < cend) { l = sc_lm[c]; sa = sc_a[c]; sb = sc_b[c]; }
+  while (c < cend) {
+    // indices of the next contribution are fetched while this one is being multiplied
+    const int cn = c + STRIDE;
+    int ln = 0, san = 0, sbn = 0;
+    if (cn < cend) { ln = sc_lm[cn]; san = sc_a[cn]; sbn = sc_b[cn]; }
     // 16-byte vector loads: a 6x3 block is 9 double2, a padded Dinv row 5
-    const double2* Ba = reinterpret_cast<const double2*>(Hpl + 18ll * sc_a[c]);
-    const double2* Bb = reinterpret_cast<const double2*>(Hpl + 18ll * sc_b[c]);
+    const double2* Ba = reinterpret_cast<const double2*>(Hpl + 18ll * sa);
+    const double2* Bb = reinterpret_cast<const double2*>(Hpl + 18ll * sb);
     const double2* Dp = reinterpret_cast<const double2*>(Dinv + kDinvStride * (long long)l);
     double Di[10], A[18], T[18];
 #pragma unroll
@@ -442,9 +455,37 @@ schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __res
 #pragma unroll
         for (int r = 0; r < 6; ++r) acc[r + 6 * c2] = fma(T[r + 6 * j], bj[c2], acc[r + 6 * c2]);
     }
+    c = cn; l = ln; sa = san; sb = sbn;
   }
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cacc[k] = warp_sum(cacc[k]);
+  if (WPT > 1) {  // combine the warps of the target in warp order
+    __shared__ double part[WPT][42];
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) if (lane == (k & 31)) part[w][k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (lane == k) part[w][36 + k] = cacc[k];
+    __syncthreads();
+    if (w != 0) return;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) {
+      double sum = 0.0;
+#pragma unroll
+      for (int q = 0; q < WPT; ++q) sum += part[q][k];
+      acc[k] = sum;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double sum = 0.0;
+#pragma unroll
+      for (int q = 0; q < WPT; ++q) sum += part[q][36 + k];
+      cacc[k] = sum;
+    }
+  }
+  if (!active) return;
   const int hb = t_hpp[t];
   const double lam = diag ? *lambda : 0.0;
 #pragma unroll
@@ -456,8 +497,6 @@ schur_reduce_kernel(int ntarget, const int* __restrict__ t_row, const int* __res
     }
   }
   if (diag) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cacc[k] = warp_sum(cacc[k]);
 #pragma unroll
     for (int k = 0; k < 6; ++k)
       if (lane == k) bschur[6ll * i1 + k] = hpp_scale * b_p[6ll * i1 + k] - cacc[k];

@@ -379,6 +379,12 @@ int build_structure_impl(b200_ctx* c) {
     c->d_lm_eptr.upload(lm_eptr, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
     c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
     c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s); c->d_sc_ptr.upload(sc_ptr, s);
+    {  // hot targets (mostly the diagonal blocks) get a whole CTA, the rest one warp each
+      std::vector<int> heavy, light;
+      for (int t = 0; t < nT; ++t) (sc_ptr[t + 1] - sc_ptr[t] > 192 ? heavy : light).push_back(t);
+      c->n_t_heavy = (int)heavy.size(); c->n_t_light = (int)light.size();
+      c->d_t_heavy.upload(heavy, s); c->d_t_light.upload(light, s);
+    }
     c->d_Hpp.alloc((size_t)np * 36 + (size_t)c->sizeP);  // [Hpp | b_p staging] contiguous for one all-reduce
     c->d_Hll.alloc((size_t)std::max(nl, 1) * 9); c->d_Hpl.alloc((size_t)std::max(nslot, 1) * 18);
     c->d_Dinv.alloc((size_t)std::max(nl, 1) * k::kDinvStride); c->d_Dinv.zero(s); c->d_db.alloc((size_t)std::max(nl, 1) * 3);
@@ -495,7 +501,12 @@ int enqueue_solve(b200_ctx* c) {
     }
     const double hpp_scale = (c->world > 1 && c->rank != 0) ? 0.0 : 1.0;
     { PhaseTimer pt(c, PH_SCHUR);
-    k::schur_reduce_kernel<<<ceil_div((long long)c->n_hs * 32, 128), 128, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c)); }
+    if (c->n_t_heavy > 0) {
+      k::schur_reduce_kernel<4><<<c->n_t_heavy, 128, 0, s>>>(c->n_t_heavy, c->d_t_heavy.p, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
+      c->lc.n++;
+    }
+    if (c->n_t_light > 0)
+      k::schur_reduce_kernel<1><<<ceil_div((long long)c->n_t_light * 32, 128), 128, 0, s>>>(c->n_t_light, c->d_t_light.p, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c)); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
     int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);

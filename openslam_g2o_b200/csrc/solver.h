@@ -58,7 +58,8 @@ struct b200_ctx {
   g2o_b200::DevBuf<int> d_hsrc_ptr, d_hsrc_id, d_bsrc_ptr, d_bsrc_id;
   g2o_b200::DevBuf<int> d_lm_eptr, d_cam_eptr, d_cam_eidx, d_hpp_diag_block;
   g2o_b200::DevBuf<double> d_Hpp, d_Hll, d_Hpl, d_Hschur, d_Dinv, d_db, d_b, d_x, d_bschur, d_diag;
-  g2o_b200::DevBuf<int> d_t_row, d_t_col, d_t_hpp, d_sc_ptr, d_sc_lm, d_sc_a, d_sc_b;
+  g2o_b200::DevBuf<int> d_t_row, d_t_col, d_t_hpp, d_sc_ptr, d_sc_lm, d_sc_a, d_sc_b, d_t_heavy, d_t_light;
+  int n_t_heavy = 0, n_t_light = 0;
   g2o_b200::DevBuf<double> d_stage_est;            // dense staging for host<->device estimate copies
   g2o_b200::DevBuf<double> d_partials, d_scalars;  // scalars: [0] chi2 [1] scale [2] maxdiag [3] lambda
   double* h_scalars = nullptr;                     // pinned mirror of d_scalars (+ status as double)
