@@ -14,7 +14,8 @@
 namespace g2o_b200 {
 
 struct SymbolicOptions {
-  int max_panel_cols_scalar = 96;   // supernodes wider than this are split into a chain of panels
+  int max_panel_cols_scalar = 72;   // supernodes wider than this are split into a chain of panels (<= 96; 72
+                                    // measured best on sphere2500, flat on Venice: profiles/r01_sweep_panel_cols.txt)
   double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
   double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
   bool relax = true;
