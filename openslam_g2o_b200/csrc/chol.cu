@@ -4,20 +4,25 @@
 // (nrow_s*d) x (ncol_s*d) at sn_lptr[s] whose first ncol_s block rows are the (lower-triangular)
 // diagonal block.  All index arrays are 32-bit block indices; panel offsets are 64-bit.
 //
-// Determinism: every panel is written by exactly one CTA and the updates it pulls from its
-// descendants are applied in a fixed order, so repeated factorizations are bit-identical (no atomics).
+// Execution: ONE persistent dataflow kernel per factorisation (and one per backward sweep).  The numeric work is a
+// list of tasks in level-major order (symbolic.h: flow_kind / flow_arg); a CTA takes the next task from a global
+// counter and spins on the completion counters of what the task consumes.  Dependencies only point backwards in
+// the list, so the earliest unfinished task is always held by a running CTA: no deadlock for any grid size, no
+// level barriers, and the updates a supernode receives from early descendants are applied while the late ones are
+// still being factored.
+//
+// Determinism: every panel tile is written by exactly one CTA and the updates it pulls from its descendants are
+// applied in a fixed order, so repeated factorizations are bit-identical (no floating-point atomics).
 #include "chol.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace g2o_b200 {
 
 struct CholDev {
   const int *sn_col0, *sn_ncol, *sn_nrow, *sn_rowptr, *sn_rows;
   const long long* sn_lptr;
-  const int *upd_ptr, *upd_k, *upd_p0, *upd_p1;
-  const long long* upd_relptr;
-  const int* rel;
   const int *task_ptr, *task_sn;
 };
 
@@ -51,47 +56,119 @@ __global__ void chol_add_lambda_kernel(int nb, const long long* __restrict__ dia
 
 // ---------------------------------------------------------------------------------------------
 // numeric factorisation
-//   update : one CTA per destination tile (48 x 48 scalars) pulls every update piece that lands in the tile,
-//            accumulates them in shared memory in a fixed order and subtracts the sum from the panel once
-//   factor : one CTA per (supernode, row chunk): diagonal block + chunk rows staged in shared memory, blocked
-//            right-looking Cholesky with one panel row per thread (pivot block factored redundantly in registers)
-// Small subtrees run both phases for all their supernodes inside one CTA (fused kernel); the top of the tree is
-// level-scheduled with the two phases as separate multi-CTA kernels.
+//   GROUP  : one CTA per (destination tile of 48 x 48 scalars, split-K group): pulls the update pieces that land in
+//            the tile, accumulates them in shared memory in list order, subtracts the sum from the panel (or leaves a
+//            partial sum for the tile's RTILE task)
+//   CHUNK  : one CTA per (supernode, row chunk): diagonal block + chunk rows (+ the right-hand side as one more row)
+//            staged in shared memory, then held in REGISTERS: warp = block column, lane = block row, one d x d block
+//            per thread; blocked right-looking Cholesky with one barrier per block column
+//   SUBTREE: small subtrees run both phases for all their supernodes inside one CTA
 // ---------------------------------------------------------------------------------------------
 constexpr int kTile = 48;        // scalar rows / cols of a destination tile
-constexpr int kMaxPanelCols = 96;
-constexpr int kCholThreads = 512;
+constexpr int kMaxBlockCols = 12;  // block columns of a panel = warps of a CTA (symbolic.cpp caps the supernode width)
+constexpr int kMaxPanelCols = 6 * kMaxBlockCols;
+constexpr int kCholThreads = 32 * kMaxBlockCols;
 constexpr int kUpdateSmemDoubles = kTile * kTile + 2 * kTile * kMaxPanelCols;  // acc | A rows | B rows
+constexpr int kLds = 33;         // lane stride of the staged panel: element (slot, i) of column c at (c*D+i)*kLds+slot
 
 struct CholPlanDev {
   const int *tile_sn, *tile_r0, *tile_c0, *tile_work_ptr;
-  const int *work_u, *work_a0, *work_a1, *work_b0, *work_b1;
+  const int *work_a0, *work_a1, *work_b0, *work_b1;
   const int *sn_tile_ptr, *sn_chunk_ptr, *chunk_sn, *chunk_b0, *chunk_nb;
   const long long *sn_dinvptr, *sn_cptr;
   const long long *work_koff, *work_reloff;
   const int *work_mk, *work_nk, *fwd_ptr, *fwd_src;
+  const int* rel;
 };
 
-// acc (shared, kTile x kTile) = sum over work items [w0,w1) of the tile, in list order.
-// Operand rows of the updating panel are staged in shared memory with coalesced loads; every thread then owns
-// 3x3 micro tiles of the product.
+// dataflow state: task list, completion counters (zeroed before every factorisation)
+struct CholFlowDev {
+  const int *kind, *arg;
+  int ntasks;
+  int* next_task;
+  int *upd_done, *chunk_done, *slot_done;
+  const int *sn_nupd, *sn_nchunk, *work_ksn, *group_rtile;
+  const int *g_tile, *g_w0, *g_w1, *g_slot;
+  const int *r_tile, *r_slot0, *r_nslots;
+  double* scratch;
+};
+
+constexpr unsigned kSpinLimit = 1u << 24;  // several seconds of polling
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// called by every thread of the CTA after its global writes: publishes them and bumps a completion counter
+__device__ __forceinline__ void cta_signal(int* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1);
+  }
+}
+// called by every thread: returns when *counter >= target (thread 0 spins, the barrier hands the acquire on)
+__device__ __forceinline__ void cta_wait(const int* counter, int target) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire(counter) < target)
+      if (++spins > kSpinLimit) __trap();  // a producer died: fail loudly instead of hanging the device
+  }
+  __syncthreads();
+}
+
+#ifdef CHOL_TIMING
+__device__ unsigned long long g_chol_timing[16];
+#define TCK(i) do { if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_chol_timing[i], _n - _t0); _t0 = _n; } } while (0)
+#define TCK_INIT unsigned long long _t0 = clock64()
+#else
+#define TCK(i) do {} while (0)
+#define TCK_INIT do {} while (0)
+#endif
+
+// acc (shared, kTile x kTile) = sum over work items [w0,w1) of the tile, in list order.  Every item waits until its
+// source supernode is completely stored (warp 0 polls up to 32 items at once).  Operand rows of the updating panel
+// are staged in shared memory with coalesced L2 loads; every thread then owns 3x3 micro tiles of the product.
 template <int D>
-__device__ void accumulate_items(const CholDev& P, const CholPlanDev& Q, const double* __restrict__ L, int w0, int w1,
+__device__ void accumulate_items(const CholPlanDev& Q, const CholFlowDev& F, const double* __restrict__ L, int w0, int w1,
                                  int R0, int C0, double* __restrict__ acc, double* __restrict__ As,
-                                 double* __restrict__ Bs) {
+                                 double* __restrict__ Bs, int* s_nready) {
   constexpr int S = D / 3;
   const int tid = threadIdx.x, nt = blockDim.x;
+  TCK_INIT;
+  __syncthreads();  // whoever used the shared bytes before (a panel factorisation of the same task) is done
   for (int i = tid; i < kTile * kTile; i += nt) acc[i] = 0.0;
+  int nready = w0;
   for (int wi = w0; wi < w1; ++wi) {
+    if (wi >= nready) {
+      if (tid < 32) {
+        const int idx = wi + tid;
+        const int K = idx < w1 ? F.work_ksn[idx] : -1;
+        const int target = K >= 0 ? F.sn_nchunk[K] : 0;
+        int lead;
+        unsigned spins = 0;
+        do {
+          if (++spins > kSpinLimit) __trap();
+          const bool ok = K < 0 || ld_acquire(F.chunk_done + K) >= target;
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          lead = __ffs(~m) - 1;  // leading ready items; -1 when all 32 are
+          if (lead < 0) lead = 32;
+        } while (lead == 0);
+        if (tid == 0) *s_nready = wi + lead;
+      }
+      __syncthreads();
+      nready = *s_nready;
+      TCK(0);
+    }
     // one level of indirection: everything the item needs sits in flat per-item arrays
     const int a0 = Q.work_a0[wi], a1 = Q.work_a1[wi], b0 = Q.work_b0[wi], b1 = Q.work_b1[wi];
     const int Mk = Q.work_mk[wi], Nk = Q.work_nk[wi];
     const double* Kp = L + Q.work_koff[wi];
-    const int* rel = P.rel + Q.work_reloff[wi];
+    const int* rel = Q.rel + Q.work_reloff[wi];
     const int nA = (a1 - a0) * D, nB = (b1 - b0) * D;
-    __syncthreads();  // previous item's operands fully consumed, acc zeroing done
+    __syncthreads();  // previous item's operands fully consumed, acc zeroing done, s_nready read by everyone
     {
-      // stage both operand row blocks; 4 independent global loads in flight per thread
+      // stage both operand row blocks; 4 independent loads in flight per thread
       const int totA = nA * Nk, tot = totA + nB * Nk;
       for (int i0 = tid; i0 < tot; i0 += 4 * nt) {
         double v[4];
@@ -105,7 +182,7 @@ __device__ void accumulate_items(const CholDev& P, const CholPlanDev& Q, const d
             const int ii = isA ? i : i - totA;
             const int nR = isA ? nA : nB;
             const int k = ii / nR, r = ii - k * nR;
-            v[q] = Kp[(isA ? a0 : b0) * D + r + (long long)k * Mk];
+            v[q] = __ldcg(Kp + ((isA ? a0 : b0) * D + r + (long long)k * Mk));
             dst[q] = (isA ? 0 : kTile * kMaxPanelCols) + r + k * kTile;
           }
         }
@@ -141,6 +218,7 @@ __device__ void accumulate_items(const CholDev& P, const CholPlanDev& Q, const d
       dst[kTile] += c01; dst[kTile + 1] += c11; dst[kTile + 2] += c21;
       dst[2 * kTile] += c02; dst[2 * kTile + 1] += c12; dst[2 * kTile + 2] += c22;
     }
+    TCK(1);
   }
   __syncthreads();
 }
@@ -154,16 +232,10 @@ __device__ void subtract_tile(const CholDev& P, const CholPlanDev& Q, double* __
   const int rows = min(kTile, M - R0 * D), cols = min(kTile, N - C0 * D);
   for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
     const int c = i / rows, r = i - c * rows;
-    Pj[(long long)(R0 * D + r) + (long long)(C0 * D + c) * M] -= acc[r + c * kTile];
+    double* p = Pj + ((long long)(R0 * D + r) + (long long)(C0 * D + c) * M);
+    __stcg(p, __ldcg(p) - acc[r + c * kTile]);
   }
 }
-
-#ifdef CHOL_TIMING
-__device__ unsigned long long g_chol_timing[8];
-#define TCK(i) do { if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_chol_timing[i], _n - _t0); _t0 = _n; } } while (0)
-#else
-#define TCK(i) do {} while (0)
-#endif
 
 // 1/sqrt(s) to full double accuracy: single-precision seed (one MUFU) + two Newton steps in double; falls back to the
 // library routine outside the float range.  Sits on the critical path of every block column.
@@ -176,292 +248,272 @@ __device__ __forceinline__ double fast_rsqrt(double s) {
   return r;
 }
 
+// Panel factorisation of one (supernode, row chunk).  Block rows map to lanes ("slots"): slot s < ncb is block row s
+// of the diagonal block, slots ncb .. ncb+cnb-1 are the chunk's block rows, slot ncb+cnb carries the right-hand side
+// of the supernode in its first row - its triangular solve IS the forward substitution y_J = L11^-1 t.
+// Warp w owns block column w: every thread keeps its d x d block in registers over the whole sweep.  Per block
+// column jb: lane jb of warp jb factors the pivot block in place and publishes it, the rest of warp jb solves its
+// blocks against it and writes the finished block column to shared memory (one barrier), then every warp w > jb
+// applies the rank-d update to its registers.  Warp jb+1 proceeds to its pivot while the others still update.
 template <int D>
-__device__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                             int chunk, bool write_diag, double* __restrict__ Sm, int* status,
-                             const double* __restrict__ y, double* __restrict__ z, double* contrib) {
+__device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, double* __restrict__ Ldiag,
+                             double* __restrict__ Dinv, int chunk, bool first, double* __restrict__ Sm, int* status,
+                             const double* __restrict__ y, double* __restrict__ z, double* contrib, int* chunk_done) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
   const int J = Q.chunk_sn[chunk];
-  const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
-  const int crow0 = Q.chunk_b0[chunk] * D, crows = Q.chunk_nb[chunk] * D;
-  // rows staged: the diagonal block, this chunk's rows and - when the forward solve rides along - the right-hand
-  // side of the supernode as one more row: its "triangular solve" IS the forward substitution y_J = L11^-1 t
-  const bool rhs = y != nullptr;
-  const int Rp = N + crows;
-  const int R = Rp + (rhs ? 1 : 0);
+  const int ncb = P.sn_ncol[J];
+  const int M = P.sn_nrow[J] * D, N = ncb * D;
+  const int cnb = Q.chunk_nb[chunk];
+  const int crow0 = Q.chunk_b0[chunk] * D, crows = cnb * D;
+  const int Rp = N + crows;       // panel rows staged
+  const int rs = ncb + cnb;       // slot of the right-hand side
+  const int nslots = rs + 1;
   const int col0s = P.sn_col0[J] * D;
   double* Pj = L + P.sn_lptr[J];
-#ifdef CHOL_TIMING
-  unsigned long long _t0 = clock64();
-#endif
+  double* piv = Sm + N * D * kLds;           // D*D factored pivot block | D reciprocal diagonal entries
+  TCK_INIT;
   __syncthreads();
   {
-    // warps split in two groups: one streams the panel in, the other gathers the right-hand side
-    // t_c = (P b)_c - sum of the descendants' contributions (lanes stride the list, fixed shuffle tree)
-    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    const int ngather = rhs ? max(1, nw / 4) : 0;
-    if (wid < ngather) {
-      for (int c = wid; c < N; c += ngather) {
+    // warps split in two groups: one gathers the right-hand side
+    // t_c = (P b)_c - sum of the descendants' contributions (lanes stride the list, fixed shuffle tree),
+    // the other streams the panel in (coalesced along the rows of a column)
+    const int ngather = max(1, nw / 4);
+    if (w < ngather) {
+      for (int c = w; c < N; c += ngather) {
         const int g = col0s + c;
         const int e0 = Q.fwd_ptr[g], e1 = Q.fwd_ptr[g + 1];
         double part = 0.0;
-        for (int e = e0 + lane; e < e1; e += 32) part += contrib[Q.fwd_src[e]];
+        for (int e = e0 + lane; e < e1; e += 32) part += __ldcg(contrib + Q.fwd_src[e]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) Sm[Rp + c * R] = y[g] - part;
+        if (lane < D) Sm[(c * D + lane) * kLds + rs] = lane == 0 ? y[g] - part : 0.0;
       }
     } else {
       const int t2 = tid - ngather * 32, n2 = nt - ngather * 32;
       for (int i = t2; i < Rp * N; i += n2) {
         const int c = i / Rp, r = i - c * Rp;
         const int gr = r < N ? r : crow0 + (r - N);
-        Sm[r + c * R] = Pj[gr + (long long)c * M];
+        const int slot = r / D;
+        Sm[(c * D + (r - slot * D)) * kLds + slot] = __ldcg(Pj + (gr + (long long)c * M));
       }
     }
   }
   __syncthreads();
-  TCK(0);
-  const int row = tid;  // one panel row per thread (R <= 192 <= blockDim)
-  const int ncb = N / D;
-  bool bad = false;
+  TCK(2);
+  // lanes above the diagonal of the diagonal block hold nothing
+  const bool active = w < ncb && lane < nslots && lane >= w;
+  double B[D][D];  // B[i][j]: row i, column j of my block
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+      for (int i = 0; i < D; ++i) B[i][j] = Sm[((w * D + j) * D + i) * kLds + lane];
+  }
   for (int jb = 0; jb < ncb; ++jb) {
-    const int j0 = jb * D;
-    // pivot block (already carries every earlier update): factor redundantly in registers
-    double Lp[D][D], inv[D];
-#pragma unroll
-    for (int r = 0; r < D; ++r)
-#pragma unroll
-      for (int c = 0; c <= r; ++c) Lp[r][c] = Sm[(j0 + r) + (j0 + c) * R];
-    // right-looking inside the block: as soon as column k is scaled the remaining entries are updated with
-    // independent FMAs, so the dependent chain per column is rsqrt -> multiply -> one FMA
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      double s = Lp[k][k];
-      if (!(s > 0.0)) { bad = true; s = 1.0; }  // d <= 0: not positive definite (csparse_helper.cpp:136)
-      const double rs = fast_rsqrt(s);
-      inv[k] = rs;
-      Lp[k][k] = s * rs;
-#pragma unroll
-      for (int r = k + 1; r < D; ++r) Lp[r][k] *= rs;
-#pragma unroll
-      for (int c = k + 1; c < D; ++c)
-#pragma unroll
-        for (int r = c; r < D; ++r) Lp[r][c] = fma(-Lp[r][k], Lp[c][k], Lp[r][c]);
-    }
-    TCK(1);
-    double x[D];
-    const bool below = row >= j0 + D && row < R;
-    if (row >= j0 && row < j0 + D) {
-      const int rr = row - j0;
-#pragma unroll
-      for (int r = 0; r < D; ++r)
-        if (r == rr) {
-#pragma unroll
-          for (int c = 0; c <= r; ++c) Sm[row + (j0 + c) * R] = Lp[r][c];
-        }
-    } else if (below) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) x[c] = Sm[row + (j0 + c) * R];
-#pragma unroll
-      for (int c = 0; c < D; ++c) {  // right-looking substitution: chain per column = multiply -> one FMA
-        x[c] *= inv[c];
-#pragma unroll
-        for (int m = c + 1; m < D; ++m) x[m] = fma(-x[c], Lp[m][c], x[m]);
-      }
-#pragma unroll
-      for (int c = 0; c < D; ++c) Sm[row + (j0 + c) * R] = x[c];
-    }
-    TCK(2);
-    __syncthreads();
-    TCK(3);
-    {
-      // rank-D trailing update T(i,c) -= sum_k X(i,k) X(c,k), i >= j0+D, c in [j0+D, N): every thread takes
-      // 2 rows x 4 columns per item (rows rp apart so that a warp walks consecutive rows); entries above the
-      // diagonal are never read again, so they may be updated or skipped freely
-      const int base = j0 + D;
-      const int nrows = R - base, ncols = N - base;
-      const int rp = (nrows + 1) >> 1, cq = (ncols + 3) >> 2;
-      for (int item = tid; item < rp * cq; item += nt) {
-        const int ci = item / rp, ri = item - ci * rp;
-        const int r0 = base + ri, r1 = r0 + rp;
-        const int c0 = base + 4 * ci;
-        const bool has1 = r1 < R;
-        if ((has1 ? r1 : r0) < N && c0 > (has1 ? r1 : r0)) continue;  // whole item above the diagonal
-        // all loads first, then 8 independent FMA chains, then the stores: nothing in between can alias
-        double x0[D], x1[D], l[4][D], v0[4], v1[4];
-        const int rr1 = has1 ? r1 : r0;
+    if (w == jb) {
+      if (lane == jb) {
+        // right-looking inside the block: as soon as column k is scaled the remaining entries are updated with
+        // independent FMAs, so the dependent chain per column is rsqrt -> multiply -> one FMA
+        bool bad = false;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          x0[k] = Sm[r0 + (j0 + k) * R];
-          x1[k] = Sm[rr1 + (j0 + k) * R];
+          double s = B[k][k];
+          if (!(s > 0.0)) { bad = true; s = 1.0; }  // d <= 0: not positive definite (csparse_helper.cpp:136)
+          const double r = fast_rsqrt(s);
+          piv[D * D + k] = r;
+          B[k][k] = s * r;
+#pragma unroll
+          for (int i = k + 1; i < D; ++i) B[i][k] *= r;
+#pragma unroll
+          for (int c = k + 1; c < D; ++c)
+#pragma unroll
+            for (int i = c; i < D; ++i) B[i][c] = fma(-B[i][k], B[c][k], B[i][c]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = min(c0 + q, N - 1);
-          v0[q] = Sm[r0 + c * R];
-          v1[q] = Sm[rr1 + c * R];
+        for (int i = 0; i < D; ++i)
 #pragma unroll
-          for (int k = 0; k < D; ++k) l[q][k] = Sm[c + (j0 + k) * R];
+          for (int c = 0; c <= i; ++c) piv[i * D + c] = B[i][c];
+        if (bad) *status = 1;
+      }
+      __syncwarp();
+      if (active && lane > jb) {
+        // right-looking substitution per row: chain per column = multiply -> one FMA
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const double r = piv[D * D + c];
+#pragma unroll
+          for (int i = 0; i < D; ++i) B[i][c] *= r;
+#pragma unroll
+          for (int m = c + 1; m < D; ++m) {
+            const double l = piv[m * D + c];
+#pragma unroll
+            for (int i = 0; i < D; ++i) B[i][m] = fma(-B[i][c], l, B[i][m]);
+          }
         }
+      }
+      if (active) {
 #pragma unroll
-        for (int k = 0; k < D; ++k)
+        for (int j = 0; j < D; ++j)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v0[q] = fma(-x0[k], l[q][k], v0[q]);
-            v1[q] = fma(-x1[k], l[q][k], v1[q]);
-          }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (c0 + q < N) {
-            Sm[r0 + (c0 + q) * R] = v0[q];
-            if (has1) Sm[r1 + (c0 + q) * R] = v1[q];
-          }
+          for (int i = 0; i < D; ++i) Sm[((jb * D + j) * D + i) * kLds + lane] = B[i][j];
       }
     }
-    TCK(4);
     __syncthreads();
+    if (active && w > jb) {
+      // rank-D update of my block: B -= X(my block row) * X(block row w)^T over the finished block column jb
+      const double* xa = Sm + (jb * D * D) * kLds + lane;
+      const double* xb = Sm + (jb * D * D) * kLds + w;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double a[D], b[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          a[i] = xa[(k * D + i) * kLds];
+          b[i] = xb[(k * D + i) * kLds];
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+          for (int i = 0; i < D; ++i) B[i][j] = fma(-a[i], b[j], B[i][j]);
+      }
+    }
+  }
+  TCK(3);
+  // the finished panel sits in shared memory (the last iteration ended with a barrier and no update)
+  {
+    const int R = Rp + 1;
+    for (int i = tid; i < R * N; i += nt) {
+      const int c = i / R, r = i - c * R;
+      if (r < Rp) {
+        const int slot = r / D;
+        const double v = Sm[(c * D + (r - slot * D)) * kLds + slot];
+        if (r < N) {
+          // the factored diagonal block goes to its own array: sibling chunk CTAs are still reading the unfactored
+          // block from the panel (every chunk factors it redundantly), so it must not be overwritten in place
+          if (first && r >= c) Ldiag[Q.sn_dinvptr[J] + r + (long long)c * N] = v;
+        } else {
+          __stcg(Pj + (crow0 + (r - N) + (long long)c * M), v);
+        }
+      } else if (first) {
+        z[col0s + c] = Sm[(c * D) * kLds + rs];  // y_J goes to its own vector: sibling chunks still read (P b)_J from y
+      }
+    }
+    // c_J = L21 y_J for this chunk's rows: what every ancestor will subtract from its right-hand side.
+    // 4 threads per row, each a quarter of the columns, fixed shuffle tree
+    double* cj = contrib + Q.sn_cptr[J] + (crow0 - N);
+    for (int r0 = 0; r0 < crows; r0 += nt / 4) {
+      const int r = r0 + (tid >> 2), q = tid & 3;
+      double s = 0.0;
+      if (r < crows) {
+        const int lr = N + r, slot = lr / D, ii = lr - slot * D;
+        for (int c = q; c < N; c += 4) s = fma(Sm[(c * D + ii) * kLds + slot], Sm[(c * D) * kLds + rs], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (r < crows && q == 0) __stcg(cj + r, s);
+    }
+  }
+  cta_signal(chunk_done + J);
+  TCK(4);
+  if (first) {
+    // off the critical path: inverse of the triangular diagonal block, so that the solves are matrix-vector
+    // products.  Thread j builds column j of the inverse; Zt holds it transposed (Zt[j + i*N] = inv(i,j)) so that
+    // the threads walk it conflict-free and the factor entries are warp-wide broadcasts.
+    double* Zt = piv + D * D + D;
+    for (int j = tid; j < N; j += nt) {
+      for (int i = j; i < N; ++i) {
+        const int si = i / D;
+        const double* li = Sm + (i - si * D) * kLds + si;  // L(i,k) = li[k*D*kLds]
+        double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0;
+        int k = j;
+        for (; k + 1 < i; k += 2) {
+          s0 = fma(-li[k * D * kLds], Zt[j + k * N], s0);
+          s1 = fma(-li[(k + 1) * D * kLds], Zt[j + (k + 1) * N], s1);
+        }
+        if (k < i) s0 = fma(-li[k * D * kLds], Zt[j + k * N], s0);
+        Zt[j + i * N] = (s0 + s1) / li[i * D * kLds];
+      }
+    }
+    __syncthreads();
+    double* out = Dinv + Q.sn_dinvptr[J];
+    for (int i = tid; i < N * N; i += nt) {
+      const int c = i / N, r = i - c * N;  // out(r,c) = inv(r,c) = Zt[c + r*N]
+      out[i] = r >= c ? Zt[c + r * N] : 0.0;
+    }
     TCK(5);
   }
-  if (bad && tid == 0) *status = 1;
-  for (int i = tid; i < R * N; i += nt) {
-    const int c = i / R, r = i - c * R;
-    if (r < N) {
-      // the factored diagonal block goes to its own array: sibling chunk CTAs are still reading the unfactored
-      // block from the panel (every chunk factors it redundantly), so it must not be overwritten in place
-      if (write_diag && r >= c) Ldiag[Q.sn_dinvptr[J] + r + (long long)c * N] = Sm[i];
-    } else if (r < Rp) {
-      Pj[crow0 + (r - N) + (long long)c * M] = Sm[i];
-    } else if (write_diag) {
-      z[col0s + c] = Sm[i];  // y_J goes to its own vector: sibling chunks still read (P b)_J from y
-    }
-  }
-  if (rhs) {
-    // c_J = L21 y_J for this chunk's rows: what every ancestor will subtract from its right-hand side
-    double* cj = contrib + Q.sn_cptr[J] + (crow0 - N);
-    for (int r = tid; r < crows; r += nt) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int c = 0;
-      for (; c + 3 < N; c += 4) {
-        s0 = fma(Sm[N + r + c * R], Sm[Rp + c * R], s0);
-        s1 = fma(Sm[N + r + (c + 1) * R], Sm[Rp + (c + 1) * R], s1);
-        s2 = fma(Sm[N + r + (c + 2) * R], Sm[Rp + (c + 2) * R], s2);
-        s3 = fma(Sm[N + r + (c + 3) * R], Sm[Rp + (c + 3) * R], s3);
-      }
-      for (; c < N; ++c) s0 = fma(Sm[N + r + c * R], Sm[Rp + c * R], s0);
-      cj[r] = (s0 + s1) + (s2 + s3);
-    }
-  }
-  TCK(6);
 }
 
 template <int D>
-__global__ void __launch_bounds__(kCholThreads)
-chol_fused_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag, int task0, int* status,
-                  const double* __restrict__ y, double* __restrict__ z, double* contrib) {
+__global__ void __launch_bounds__(kCholThreads, 1)
+chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant__ CholPlanDev Q,
+                        const __grid_constant__ CholFlowDev F, double* __restrict__ L, double* __restrict__ Ldiag,
+                        double* __restrict__ Dinv, int* status, const double* __restrict__ y, double* __restrict__ z,
+                        double* contrib) {
   extern __shared__ __align__(16) double smem[];  // update operands and factor staging share the same bytes
+  __shared__ int s_task, s_nready;
   double* acc = smem;
   double* As = smem + kTile * kTile;
   double* Bs = As + kTile * kMaxPanelCols;
-  const int t = task0 + blockIdx.x;
-  for (int q = P.task_ptr[t]; q < P.task_ptr[t + 1]; ++q) {
-    const int J = P.task_sn[q];
-    for (int tile = Q.sn_tile_ptr[J]; tile < Q.sn_tile_ptr[J + 1]; ++tile) {
-      const int w0 = Q.tile_work_ptr[tile], w1 = Q.tile_work_ptr[tile + 1];
-      if (w0 == w1) continue;
-      accumulate_items<D>(P, Q, L, w0, w1, Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs);
-      subtract_tile<D>(P, Q, L, tile, acc);
-      __syncthreads();
-    }
-    const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
-    for (int ch = c0; ch < c1; ++ch) factor_chunk<D>(P, Q, L, Ldiag, ch, ch == c0, smem, status, y, z, contrib);
+  const int tid = threadIdx.x;
+  for (;;) {
     __syncthreads();
-  }
-}
-
-// split levels, phase 1: one CTA per (tile, split-K group)
-template <int D>
-__global__ void __launch_bounds__(kCholThreads)
-chol_update_groups_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const int* __restrict__ g_tile,
-                          const int* __restrict__ g_w0, const int* __restrict__ g_w1, const int* __restrict__ g_slot,
-                          double* __restrict__ scratch) {
-  extern __shared__ __align__(16) double smem[];
-  double* acc = smem;
-  double* As = smem + kTile * kTile;
-  double* Bs = As + kTile * kMaxPanelCols;
-  const int g = blockIdx.x;
-  const int tile = g_tile[g];
-  accumulate_items<D>(P, Q, L, g_w0[g], g_w1[g], Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs);
-  const int slot = g_slot[g];
-  if (slot < 0) {
-    subtract_tile<D>(P, Q, L, tile, acc);
-  } else {
-    double* out = scratch + (long long)slot * kTile * kTile;
-    for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) out[i] = acc[i];
-  }
-}
-// split levels, phase 1b: tiles cut into several groups: add the partial sums in group order, subtract once
-template <int D>
-__global__ void __launch_bounds__(kCholThreads)
-chol_reduce_tiles_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, const int* __restrict__ r_tile,
-                         const int* __restrict__ r_slot0, const int* __restrict__ r_nslots,
-                         const double* __restrict__ scratch) {
-  __shared__ __align__(16) double acc[kTile * kTile];
-  const int t = blockIdx.x;
-  const double* in = scratch + (long long)r_slot0[t] * kTile * kTile;
-  const int ns = r_nslots[t];
-  for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) {
-    double s = 0.0;
-    for (int g = 0; g < ns; ++g) s += in[(long long)g * kTile * kTile + i];
-    acc[i] = s;
-  }
-  __syncthreads();
-  subtract_tile<D>(P, Q, L, r_tile[t], acc);
-}
-template <int D>
-__global__ void __launch_bounds__(kCholThreads)
-chol_factor_chunks_kernel(CholDev P, CholPlanDev Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                          const int* __restrict__ chunks, int* status, const double* __restrict__ y,
-                          double* __restrict__ z, double* contrib) {
-  extern __shared__ __align__(16) double smem[];
-  const int ch = chunks[blockIdx.x];
-  factor_chunk<D>(P, Q, L, Ldiag, ch, ch == Q.sn_chunk_ptr[Q.chunk_sn[ch]], smem, status, y, z, contrib);
-}
-
-// inverse of every triangular diagonal block (one CTA per supernode): the solves become matrix-vector products.
-// Zt holds the inverse transposed (Zt[j + k*N] = inv(k,j)) so that thread j walks its column conflict-free.
-template <int D>
-__global__ void __launch_bounds__(128)
-chol_invert_diag_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ Ldiag, double* __restrict__ Dinv) {
-  extern __shared__ __align__(16) double sm[];
-  const int J = blockIdx.x;
-  const int N = P.sn_ncol[J] * D;
-  double* Ls = sm;           // N*N, Ls[i + k*N]
-  double* Zt = sm + N * N;   // N*N
-  const double* Lj = Ldiag + Q.sn_dinvptr[J];
-  double* out = Dinv + Q.sn_dinvptr[J];
-  for (int i = threadIdx.x; i < N * N; i += blockDim.x) Ls[i] = Lj[i];
-  __syncthreads();
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    for (int i = j; i < N; ++i) {
-      double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0;
-      int k = j;
-      for (; k + 1 < i; k += 2) {
-        s0 = fma(-Ls[i + k * N], Zt[j + k * N], s0);
-        s1 = fma(-Ls[i + (k + 1) * N], Zt[j + (k + 1) * N], s1);
+    if (tid == 0) s_task = atomicAdd(F.next_task, 1);
+    __syncthreads();
+    const int ti = s_task;
+    if (ti >= F.ntasks) break;
+    const int kind = F.kind[ti], arg = F.arg[ti];
+    if (kind == 1) {  // GROUP
+      const int tile = F.g_tile[arg];
+      accumulate_items<D>(Q, F, L, F.g_w0[arg], F.g_w1[arg], Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs, &s_nready);
+      const int slot = F.g_slot[arg];
+      if (slot < 0) {
+        subtract_tile<D>(P, Q, L, tile, acc);
+        cta_signal(F.upd_done + Q.tile_sn[tile]);
+      } else {
+        double* out = F.scratch + (long long)slot * kTile * kTile;
+        for (int i = tid; i < kTile * kTile; i += blockDim.x) __stcg(out + i, acc[i]);
+        cta_signal(F.slot_done + F.group_rtile[arg]);
       }
-      if (k < i) s0 = fma(-Ls[i + k * N], Zt[j + k * N], s0);
-      Zt[j + i * N] = (s0 + s1) / Ls[i + i * N];
+    } else if (kind == 2) {  // RTILE: add the partial sums in group order, subtract once
+      const int ns = F.r_nslots[arg];
+      cta_wait(F.slot_done + arg, ns);
+      const double* in = F.scratch + (long long)F.r_slot0[arg] * kTile * kTile;
+      for (int i = tid; i < kTile * kTile; i += blockDim.x) {
+        double s = 0.0;
+        for (int g = 0; g < ns; ++g) s += __ldcg(in + ((long long)g * kTile * kTile + i));
+        acc[i] = s;
+      }
+      __syncthreads();
+      const int tile = F.r_tile[arg];
+      subtract_tile<D>(P, Q, L, tile, acc);
+      cta_signal(F.upd_done + Q.tile_sn[tile]);
+    } else if (kind == 3) {  // CHUNK
+      const int J = Q.chunk_sn[arg];
+      const int need = F.sn_nupd[J];
+      if (need > 0) cta_wait(F.upd_done + J, need);
+      factor_chunk<D>(P, Q, L, Ldiag, Dinv, arg, arg == Q.sn_chunk_ptr[J], smem, status, y, z, contrib, F.chunk_done);
+    } else {  // SUBTREE
+      for (int q = P.task_ptr[arg]; q < P.task_ptr[arg + 1]; ++q) {
+        const int J = P.task_sn[q];
+        for (int tile = Q.sn_tile_ptr[J]; tile < Q.sn_tile_ptr[J + 1]; ++tile) {
+          const int w0 = Q.tile_work_ptr[tile], w1 = Q.tile_work_ptr[tile + 1];
+          if (w0 == w1) continue;
+          accumulate_items<D>(Q, F, L, w0, w1, Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs, &s_nready);
+          subtract_tile<D>(P, Q, L, tile, acc);
+          __syncthreads();
+        }
+        const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
+        for (int ch = c0; ch < c1; ++ch)
+          factor_chunk<D>(P, Q, L, Ldiag, Dinv, ch, ch == c0, smem, status, y, z, contrib, F.chunk_done);
+      }
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
-    const int c = i / N, r = i - c * N;  // out(r,c) = inv(r,c) = Zt[c + r*N]
-    out[i] = r >= c ? Zt[c + r * N] : 0.0;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// triangular solves on the permuted vector y (in place)
+// triangular solves on the permuted vector (in place)
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void chol_permute_in_kernel(int nb, const int* __restrict__ perm, const double* __restrict__ b,
@@ -481,110 +533,90 @@ __global__ void chol_permute_out_kernel(int nb, const int* __restrict__ perm, co
   x[perm[k] * D + r] = y[idx];
 }
 
-// forward: y_J = Linv (P b - contributions of the descendants); every supernode then leaves c_J = L21 y_J in its own
-// scratch segment, so ancestors only add precomputed numbers (per-row lists in a fixed order -> deterministic) and L
-// is read once, coalesced, by its owner.
-constexpr int kSolveThreads = 256;
+// backward sweep, dataflow: tasks from the top of the tree down; a task waits for the task holding the parent of its
+// root supernode (which waited for its own parent, ...: every ancestor's x is final).  Before it waits it stages the
+// rows below the diagonal block of its root panel and the inverse diagonal block in shared memory, so that the
+// critical path per tree level is: flag -> gather x_below -> L21^T x_below -> Linv^T t -> flag.
+constexpr int kSolveThreads = 512;
 
 template <int D>
-__global__ void __launch_bounds__(kSolveThreads)
-chol_forward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
-                    double* __restrict__ y, double* __restrict__ contrib, int task0) {
-  __shared__ double tvec[kMaxPanelCols];
-  __shared__ double yv[kMaxPanelCols];
-  const int t = task0 + blockIdx.x;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int q = P.task_ptr[t]; q < P.task_ptr[t + 1]; ++q) {
-    const int J = P.task_sn[q];
-    const int col0 = P.sn_col0[J];
-    const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
-    double* yj = y + (long long)col0 * D;
-    __syncthreads();  // contributions written by the previous supernode of this task are visible
-    for (int i = tid; i < N; i += nt) {
-      const int g = col0 * D + i;
-      double s = yj[i];
-      const int e0 = Q.fwd_ptr[g], e1 = Q.fwd_ptr[g + 1];
-      for (int e = e0; e < e1; ++e) s -= contrib[Q.fwd_src[e]];
-      tvec[i] = s;
-    }
-    __syncthreads();
-    const double* Di = Dinv + Q.sn_dinvptr[J];
-    for (int i = tid; i < N; i += nt) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int j = 0;
-      for (; j + 3 <= i; j += 4) {
-        s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
-        s1 = fma(Di[i + (long long)(j + 1) * N], tvec[j + 1], s1);
-        s2 = fma(Di[i + (long long)(j + 2) * N], tvec[j + 2], s2);
-        s3 = fma(Di[i + (long long)(j + 3) * N], tvec[j + 3], s3);
-      }
-      for (; j <= i; ++j) s0 = fma(Di[i + (long long)j * N], tvec[j], s0);
-      const double v = (s0 + s1) + (s2 + s3);
-      yj[i] = v;
-      yv[i] = v;
-    }
-    __syncthreads();
-    const double* Pj = L + P.sn_lptr[J];
-    double* cj = contrib + Q.sn_cptr[J];
-    for (int r = N + tid; r < M; r += nt) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = 0;
-      for (; k + 3 < N; k += 4) {
-        s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
-        s1 = fma(Pj[r + (long long)(k + 1) * M], yv[k + 1], s1);
-        s2 = fma(Pj[r + (long long)(k + 2) * M], yv[k + 2], s2);
-        s3 = fma(Pj[r + (long long)(k + 3) * M], yv[k + 3], s3);
-      }
-      for (; k < N; ++k) s0 = fma(Pj[r + (long long)k * M], yv[k], s0);
-      cj[r - N] = (s0 + s1) + (s2 + s3);
-    }
-  }
-}
-
-template <int D>
-__global__ void __launch_bounds__(kSolveThreads)
-chol_backward_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
-                     double* __restrict__ y, int task0) {
-  extern __shared__ __align__(16) double xb[];  // x at the rows below the diagonal block
-  __shared__ double tvec[kMaxPanelCols];
-  const int t = task0 + blockIdx.x;
+__global__ void __launch_bounds__(kSolveThreads, 1)
+chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
+                          double* __restrict__ y, int ntasks, const int* __restrict__ task_parent, int* next_task,
+                          int* bdone, int xb_doubles, int stage_doubles) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_task;
+  double* xb = smem;                 // x at the rows below the diagonal block
+  double* tvec = xb + xb_doubles;    // kMaxPanelCols
+  double* stage = tvec + kMaxPanelCols;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-  for (int q = P.task_ptr[t + 1] - 1; q >= P.task_ptr[t]; --q) {
-    const int J = P.task_sn[q];
-    const int col0 = P.sn_col0[J];
-    const int nc = P.sn_ncol[J], nr = P.sn_nrow[J];
-    const int M = nr * D, N = nc * D;
-    const double* Pj = L + P.sn_lptr[J];
-    const int* jrows = P.sn_rows + P.sn_rowptr[J];
-    double* xj = y + (long long)col0 * D;
+  for (;;) {
     __syncthreads();
-    for (int i = tid; i < M - N; i += nt) xb[i] = y[(long long)jrows[nc + i / D] * D + (i % D)];
+    if (tid == 0) s_task = atomicAdd(next_task, 1);
     __syncthreads();
-    // t = y_J - L21^T x_below : one warp per column, lanes stride the rows (coalesced), fixed-order shuffle tree
-    for (int j = wid; j < N; j += nw) {
-      const double* cj = Pj + (long long)j * M + N;
-      double s0 = 0.0, s1 = 0.0;
-      int i = lane;
-      for (; i + 32 < M - N; i += 64) { s0 = fma(cj[i], xb[i], s0); s1 = fma(cj[i + 32], xb[i + 32], s1); }
-      if (i < M - N) s0 = fma(cj[i], xb[i], s0);
-      double s = s0 + s1;
+    if (s_task >= ntasks) break;
+    const int t = ntasks - 1 - s_task;
+    const int q_root = P.task_ptr[t + 1] - 1;
+    bool staged = false;
+    {
+      const int J = P.task_sn[q_root];
+      const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D, B = M - N;
+      if (B * N + N * N <= stage_doubles) {
+        staged = true;
+        const double* Pj = L + P.sn_lptr[J];
+        for (int i = tid; i < B * N; i += nt) {
+          const int c = i / B, r = i - c * B;
+          stage[i] = Pj[N + r + (long long)c * M];
+        }
+        const double* Di = Dinv + Q.sn_dinvptr[J];
+        for (int i = tid; i < N * N; i += nt) stage[B * N + i] = Di[i];
+      }
+    }
+    const int tp = task_parent[t];
+    if (tp >= 0) cta_wait(bdone + tp, 1);
+    for (int q = q_root; q >= P.task_ptr[t]; --q) {
+      const int J = P.task_sn[q];
+      const int col0 = P.sn_col0[J];
+      const int nc = P.sn_ncol[J], nr = P.sn_nrow[J];
+      const int M = nr * D, N = nc * D, B = M - N;
+      const bool st = staged && q == q_root;
+      const double* Pj = L + P.sn_lptr[J];
+      const int* jrows = P.sn_rows + P.sn_rowptr[J];
+      double* xj = y + (long long)col0 * D;
+      __syncthreads();
+      for (int i = tid; i < B; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
+      __syncthreads();
+      // t = y_J - L21^T x_below : one warp per column, lanes stride the rows, fixed-order shuffle tree
+      for (int j = wid; j < N; j += nw) {
+        const double* cj = st ? stage + j * B : Pj + ((long long)j * M + N);
+        double s0 = 0.0, s1 = 0.0;
+        int i = lane;
+        for (; i + 32 < B; i += 64) { s0 = fma(cj[i], xb[i], s0); s1 = fma(cj[i + 32], xb[i + 32], s1); }
+        if (i < B) s0 = fma(cj[i], xb[i], s0);
+        double s = s0 + s1;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) tvec[j] = xj[j] - s;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) tvec[j] = xj[j] - s;
+      }
+      __syncthreads();
+      const double* Di = st ? stage + B * N : Dinv + Q.sn_dinvptr[J];
+      for (int i = tid; i < N; i += nt) {  // x_J = Linv^T t
+        const double* ci = Di + (long long)i * N;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = i;
+        for (; j + 3 < N; j += 4) {
+          s0 = fma(ci[j], tvec[j], s0); s1 = fma(ci[j + 1], tvec[j + 1], s1);
+          s2 = fma(ci[j + 2], tvec[j + 2], s2); s3 = fma(ci[j + 3], tvec[j + 3], s3);
+        }
+        for (; j < N; ++j) s0 = fma(ci[j], tvec[j], s0);
+        __stcg(xj + i, (s0 + s1) + (s2 + s3));
+      }
     }
     __syncthreads();
-    const double* Di = Dinv + Q.sn_dinvptr[J];
-    for (int i = tid; i < N; i += nt) {  // x_J = Linv^T t
-      const double* ci = Di + (long long)i * N;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int j = i;
-      for (; j + 3 < N; j += 4) {
-        s0 = fma(ci[j], tvec[j], s0); s1 = fma(ci[j + 1], tvec[j + 1], s1);
-        s2 = fma(ci[j + 2], tvec[j + 2], s2); s3 = fma(ci[j + 3], tvec[j + 3], s3);
-      }
-      for (; j < N; ++j) s0 = fma(ci[j], tvec[j], s0);
-      xj[i] = (s0 + s1) + (s2 + s3);
+    if (tid == 0) {
+      __threadfence();
+      atomicExch(bdone + t, 1);
     }
   }
 }
@@ -600,21 +632,17 @@ void up64(DevBuf<long long>& d, const std::vector<T>& v, cudaStream_t s, std::ve
   keep.emplace_back(v.begin(), v.end());
   d.upload(keep.back(), s);
 }
-constexpr int kMaxDynSmem = 200 * 1024;
+constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per CTA minus the static shared variables
 template <int D>
 void set_smem_attrs() {
   static bool done = false;
   if (done) return;
-  B200_CUDA(cudaFuncSetAttribute(chol_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  B200_CUDA(cudaFuncSetAttribute(chol_update_groups_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  B200_CUDA(cudaFuncSetAttribute(chol_factor_chunks_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  B200_CUDA(cudaFuncSetAttribute(chol_invert_diag_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  B200_CUDA(cudaFuncSetAttribute(chol_backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_factor_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_backward_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   done = true;
 }
 // profiler ids of the kernel groups inside the Cholesky (continue the numbering of solver.cu)
-enum { PH_CH_SCATTER = 12, PH_CH_UPDATE = 13, PH_CH_REDUCE = 14, PH_CH_PANEL = 15, PH_CH_FUSED = 16, PH_CH_INVERT = 17,
-       PH_CH_FORWARD = 18, PH_CH_BACKWARD = 19 };
+enum { PH_CH_SCATTER = 12, PH_CH_FLOW = 13, PH_CH_BACKWARD = 19 };
 }  // namespace
 
 void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt,
@@ -625,9 +653,7 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_sn_col0_.upload(S_.sn_col0, s); d_sn_ncol_.upload(S_.sn_ncol, s); d_sn_nrow_.upload(S_.sn_nrow, s);
   d_sn_rowptr_.upload(S_.sn_rowptr, s); d_sn_rows_.upload(S_.sn_rows, s);
   up64(d_sn_lptr_, S_.sn_lptr, s, keep);
-  d_upd_ptr_.upload(S_.upd_ptr, s); d_upd_k_.upload(S_.upd_k, s); d_upd_p0_.upload(S_.upd_p0, s);
-  d_upd_p1_.upload(S_.upd_p1, s); d_rel_.upload(S_.rel, s);
-  up64(d_upd_relptr_, S_.upd_relptr, s, keep);
+  d_rel_.upload(S_.rel, s);
   d_task_ptr_.upload(S_.task_ptr, s); d_task_sn_.upload(S_.task_sn, s);
   up64(d_a_dst_, S_.a_dst, s, keep);
   up64(d_diag_dst_, S_.diag_dst, s, keep);
@@ -635,20 +661,22 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_a_trans_.upload(S_.a_trans, s);
   d_tile_sn_.upload(S_.tile_sn, s); d_tile_r0_.upload(S_.tile_r0, s); d_tile_c0_.upload(S_.tile_c0, s);
   d_tile_work_ptr_.upload(S_.tile_work_ptr, s);
-  d_work_u_.upload(S_.work_u, s); d_work_a0_.upload(S_.work_a0, s); d_work_a1_.upload(S_.work_a1, s);
+  d_work_a0_.upload(S_.work_a0, s); d_work_a1_.upload(S_.work_a1, s);
   d_work_b0_.upload(S_.work_b0, s); d_work_b1_.upload(S_.work_b1, s);
   d_sn_tile_ptr_.upload(S_.sn_tile_ptr, s); d_sn_chunk_ptr_.upload(S_.sn_chunk_ptr, s);
   d_chunk_sn_.upload(S_.chunk_sn, s); d_chunk_b0_.upload(S_.chunk_b0, s); d_chunk_nb_.upload(S_.chunk_nb, s);
-  d_level_chunks_.upload(S_.level_chunks, s);
   d_group_tile_.upload(S_.group_tile, s); d_group_w0_.upload(S_.group_w0, s); d_group_w1_.upload(S_.group_w1, s);
-  d_group_slot_.upload(S_.group_slot, s);
+  d_group_slot_.upload(S_.group_slot, s); d_group_rtile_.upload(S_.group_rtile, s);
   d_rtile_tile_.upload(S_.rtile_tile, s); d_rtile_slot0_.upload(S_.rtile_slot0, s); d_rtile_nslots_.upload(S_.rtile_nslots, s);
   up64(d_sn_dinvptr_, S_.sn_dinvptr, s, keep);
   up64(d_sn_cptr_, S_.sn_cptr, s, keep);
   up64(d_work_koff_, S_.work_koff, s, keep);
   up64(d_work_reloff_, S_.work_reloff, s, keep);
-  d_work_mk_.upload(S_.work_mk, s); d_work_nk_.upload(S_.work_nk, s);
+  d_work_mk_.upload(S_.work_mk, s); d_work_nk_.upload(S_.work_nk, s); d_work_ksn_.upload(S_.work_ksn, s);
   d_fwd_ptr_.upload(S_.fwd_ptr, s); d_fwd_src_.upload(S_.fwd_src, s);
+  d_flow_kind_.upload(S_.flow_kind, s); d_flow_arg_.upload(S_.flow_arg, s);
+  d_sn_nupd_.upload(S_.sn_nupd, s); d_sn_nchunk_.upload(S_.sn_nchunk, s);
+  d_task_parent_.upload(S_.task_parent, s);
   d_L_.alloc((size_t)S_.factor_doubles);
   d_Dinv_.alloc((size_t)S_.dinv_doubles);
   d_Ldiag_.alloc((size_t)S_.dinv_doubles);
@@ -656,23 +684,43 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_contrib_.alloc((size_t)std::max<int64_t>(S_.sn_cptr[S_.nsn], 1));
   d_y_.alloc((size_t)nb * d);
   d_z_.alloc((size_t)nb * d);
-  d_status_.alloc(1);
+  // completion counters: [0] next factor task | [1] next backward task | status | upd_done | chunk_done | slot_done | bdone
+  const int ntask = (int)S_.task_ptr.size() - 1;
+  cnt_upd_ = 4;
+  cnt_chunk_ = cnt_upd_ + S_.nsn;
+  cnt_slot_ = cnt_chunk_ + S_.nsn;
+  cnt_bdone_ = cnt_slot_ + (int)S_.rtile_tile.size();
+  d_counters_.alloc((size_t)cnt_bdone_ + ntask);
+  // shared memory of the two persistent kernels
+  const int Nmax = S_.max_ncol * d;
+  const size_t factor_doubles = (size_t)Nmax * d * kLds + d * d + d + (size_t)Nmax * Nmax;
+  flow_smem_ = std::max((size_t)kUpdateSmemDoubles, factor_doubles) * sizeof(double);
+  xb_doubles_ = (S_.max_nrow * d + 1) & ~1;
+  stage_doubles_ = (int)((kMaxDynSmem - 1024) / sizeof(double)) - xb_doubles_ - kMaxPanelCols;
   if (!host_only_flag()) {
     B200_CUDA(cudaStreamSynchronize(s));  // the temporaries above die here
+    if (flow_smem_ > (size_t)kMaxDynSmem || stage_doubles_ < 0) throw CudaError{cudaErrorInvalidValue, "panel too large for shared memory", __FILE__, __LINE__};
     if (d == 3) set_smem_attrs<3>(); else set_smem_attrs<6>();
+    int dev = 0, sms = 0, occ = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (d == 3) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<3>, kCholThreads, flow_smem_));
+    else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<6>, kCholThreads, flow_smem_));
+    flow_grid_ = std::max(1, std::min((int)S_.flow_kind.size(), sms * std::max(occ, 1)));
+    back_grid_ = std::max(1, std::min(ntask, sms));
+    if (const char* e = getenv("G2O_B200_FLOW_GRID")) flow_grid_ = std::max(1, std::min(flow_grid_, atoi(e)));
   }
   analyzed_ = true;
 }
 
 CholDev CholeskyGpu::dev() const {
-  return CholDev{d_sn_col0_.p, d_sn_ncol_.p, d_sn_nrow_.p, d_sn_rowptr_.p, d_sn_rows_.p, d_sn_lptr_.p, d_upd_ptr_.p,
-                 d_upd_k_.p,   d_upd_p0_.p,  d_upd_p1_.p,  d_upd_relptr_.p, d_rel_.p,    d_task_ptr_.p, d_task_sn_.p};
+  return CholDev{d_sn_col0_.p, d_sn_ncol_.p, d_sn_nrow_.p, d_sn_rowptr_.p, d_sn_rows_.p, d_sn_lptr_.p, d_task_ptr_.p, d_task_sn_.p};
 }
 CholPlanDev CholeskyGpu::plan() const {
-  return CholPlanDev{d_tile_sn_.p, d_tile_r0_.p, d_tile_c0_.p, d_tile_work_ptr_.p, d_work_u_.p, d_work_a0_.p, d_work_a1_.p,
+  return CholPlanDev{d_tile_sn_.p, d_tile_r0_.p, d_tile_c0_.p, d_tile_work_ptr_.p, d_work_a0_.p, d_work_a1_.p,
                      d_work_b0_.p, d_work_b1_.p, d_sn_tile_ptr_.p, d_sn_chunk_ptr_.p, d_chunk_sn_.p, d_chunk_b0_.p,
                      d_chunk_nb_.p, d_sn_dinvptr_.p, d_sn_cptr_.p, d_work_koff_.p, d_work_reloff_.p, d_work_mk_.p,
-                     d_work_nk_.p, d_fwd_ptr_.p, d_fwd_src_.p};
+                     d_work_nk_.p, d_fwd_ptr_.p, d_fwd_src_.p, d_rel_.p};
 }
 
 template <int D>
@@ -682,62 +730,30 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
   const CholDev P = dev();
   const CholPlanDev Q = plan();
   double* L = d_L_.p;
-  int* status = d_status_.p;
+  int* cnt = d_counters_.p;
   auto count = [&](int n = 1) { if (lc) lc->n += n; };
   {
     ScopedPhase ph(prof, PH_CH_SCATTER);
     B200_CUDA(cudaMemsetAsync(L, 0, (size_t)S.factor_doubles * sizeof(double), s));
-    B200_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+    B200_CUDA(cudaMemsetAsync(cnt, 0, d_counters_.n * sizeof(int), s));
     chol_scatter_kernel<D><<<ceil_div((int64_t)nblk_ * D * D, 256), 256, 0, s>>>(dA, nblk_, d_a_dst_.p, d_a_ld_.p, d_a_trans_.p, L);
     count();
     if (d_lambda) {
       chol_add_lambda_kernel<D><<<ceil_div((int64_t)S.nb * D, 256), 256, 0, s>>>(S.nb, d_diag_dst_.p, d_diag_ld_.p, d_lambda, L);
       count();
     }
-    if (d_b) {  // the forward substitution rides along with the factorisation (one more row per panel)
-      chol_permute_in_kernel<D><<<ceil_div(S.nb * D, 256), 256, 0, s>>>(S.nb, d_perm_.p, d_b, d_y_.p);
-      count();
-    }
-  }
-  const double* yv = d_b ? d_y_.p : nullptr;
-  double* zv = d_z_.p;
-  double* contrib = d_contrib_.p;
-  const size_t rhs_smem = d_b ? (size_t)S.max_ncol * D * sizeof(double) : 0;
-  forward_done_ = d_b != nullptr;
-  const size_t upd_smem = (size_t)kUpdateSmemDoubles * sizeof(double);
-  for (int l = 0; l < S.nlevels; ++l) {
-    const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
-    if (nt == 0) continue;
-    if (S.level_kind[l] == 0) {
-      ScopedPhase ph(prof, PH_CH_FUSED);
-      const size_t smem = std::max(upd_smem, (size_t)S.level_smem[l] + rhs_smem);
-      chol_fused_kernel<D><<<nt, kCholThreads, smem, s>>>(P, Q, L, d_Ldiag_.p, t0, status, yv, zv, contrib);
-      count();
-    } else {
-      const int g0 = S.level_group_ptr[l], ng = S.level_group_ptr[l + 1] - g0;
-      const int r0 = S.level_rtile_ptr[l], nr = S.level_rtile_ptr[l + 1] - r0;
-      const int c0 = S.level_chunk_ptr[l], nchunk = S.level_chunk_ptr[l + 1] - c0;
-      if (ng > 0) {
-        ScopedPhase ph(prof, PH_CH_UPDATE);
-        chol_update_groups_kernel<D><<<ng, kCholThreads, upd_smem, s>>>(P, Q, L, d_group_tile_.p + g0, d_group_w0_.p + g0,
-                                                                       d_group_w1_.p + g0, d_group_slot_.p + g0, d_gscratch_.p);
-        count();
-      }
-      if (nr > 0) {
-        ScopedPhase ph(prof, PH_CH_REDUCE);
-        chol_reduce_tiles_kernel<D><<<nr, kCholThreads, 0, s>>>(P, Q, L, d_rtile_tile_.p + r0, d_rtile_slot0_.p + r0,
-                                                               d_rtile_nslots_.p + r0, d_gscratch_.p);
-        count();
-      }
-      ScopedPhase ph(prof, PH_CH_PANEL);
-      chol_factor_chunks_kernel<D><<<nchunk, kCholThreads, S.level_smem[l] + rhs_smem, s>>>(P, Q, L, d_Ldiag_.p, d_level_chunks_.p + c0, status, yv, zv, contrib);
-      count();
-    }
+    // the forward substitution rides along with the factorisation (one more row per panel)
+    chol_permute_in_kernel<D><<<ceil_div(S.nb * D, 256), 256, 0, s>>>(S.nb, d_perm_.p, d_b, d_y_.p);
+    count();
   }
   {
-    ScopedPhase ph(prof, PH_CH_INVERT);
-    const size_t ismem = 2 * (size_t)S.max_ncol * D * S.max_ncol * D * 8;
-    chol_invert_diag_kernel<D><<<S.nsn, 128, ismem, s>>>(P, Q, d_Ldiag_.p, d_Dinv_.p);
+    ScopedPhase ph(prof, PH_CH_FLOW);
+    CholFlowDev F{d_flow_kind_.p, d_flow_arg_.p, (int)S.flow_kind.size(), cnt + 0, cnt + cnt_upd_, cnt + cnt_chunk_,
+                  cnt + cnt_slot_, d_sn_nupd_.p, d_sn_nchunk_.p, d_work_ksn_.p, d_group_rtile_.p, d_group_tile_.p,
+                  d_group_w0_.p, d_group_w1_.p, d_group_slot_.p, d_rtile_tile_.p, d_rtile_slot0_.p, d_rtile_nslots_.p,
+                  d_gscratch_.p};
+    chol_factor_flow_kernel<D><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2,
+                                                                            d_y_.p, d_z_.p, d_contrib_.p);
     count();
   }
   B200_CUDA(cudaGetLastError());
@@ -745,55 +761,42 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
 
 void CholeskyGpu::factor(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
                          EventProfiler* prof) {
+  if (!d_b) throw CudaError{cudaErrorInvalidValue, "factor() needs the right-hand side", __FILE__, __LINE__};
   if (S_.d == 3) factor_t<3>(dA, d_lambda, d_b, s, lc, prof);
   else factor_t<6>(dA, d_lambda, d_b, s, lc, prof);
 }
 
 template <int D>
-void CholeskyGpu::solve_t(const double* b, double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
+void CholeskyGpu::solve_t(double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
   const SymbolicFactor& S = S_;
   const CholDev P = dev();
   const CholPlanDev Q = plan();
   const int n = S.nb * D;
+  const int ntask = (int)S.task_ptr.size() - 1;
+  int* cnt = d_counters_.p;
   auto count = [&](int k = 1) { if (lc) lc->n += k; };
-  double* y = d_z_.p;  // forward result / backward in place
-  if (!forward_done_) {
-    ScopedPhase ph(prof, PH_CH_FORWARD);
-    chol_permute_in_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, b, y);
-    count();
-    for (int l = 0; l < S.nlevels; ++l) {
-      const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
-      if (nt == 0) continue;
-      chol_forward_kernel<D><<<nt, kSolveThreads, 0, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, d_contrib_.p, t0);
-      count();
-    }
-  }
-  {
-    ScopedPhase ph(prof, PH_CH_BACKWARD);
-    const size_t bsmem = (size_t)S.max_nrow * D * sizeof(double);
-    for (int l = S.nlevels - 1; l >= 0; --l) {
-      const int t0 = S.level_ptr[l], nt = S.level_ptr[l + 1] - t0;
-      if (nt == 0) continue;
-      chol_backward_kernel<D><<<nt, kSolveThreads, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, t0);
-      count();
-    }
-    chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, d_status_.p);
-    count();
-  }
-  forward_done_ = false;
+  double* y = d_z_.p;  // forward result (written by the factorisation) / backward in place
+  ScopedPhase ph(prof, PH_CH_BACKWARD);
+  const size_t bsmem = ((size_t)xb_doubles_ + kMaxPanelCols + stage_doubles_) * sizeof(double);
+  chol_backward_flow_kernel<D><<<back_grid_, kSolveThreads, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, ntask, d_task_parent_.p,
+                                                                        cnt + 1, cnt + cnt_bdone_, xb_doubles_, stage_doubles_);
+  count();
+  chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, cnt + 2);
+  count();
   B200_CUDA(cudaGetLastError());
 }
 
-void CholeskyGpu::solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof) {
-  if (S_.d == 3) solve_t<3>(d_b, d_x, s, lc, prof);
-  else solve_t<6>(d_b, d_x, s, lc, prof);
+void CholeskyGpu::solve(const double* /*d_b: consumed by factor()*/, double* d_x, cudaStream_t s, LaunchCounter* lc,
+                        EventProfiler* prof) {
+  if (S_.d == 3) solve_t<3>(d_x, s, lc, prof);
+  else solve_t<6>(d_x, s, lc, prof);
 }
 
 }  // namespace g2o_b200
 
 #ifdef CHOL_TIMING
 extern "C" void b200_debug_chol_timing(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g2o_b200::g_chol_timing, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g2o_b200::g_chol_timing, z, sizeof(z)); }
 }
 #endif

@@ -28,16 +28,16 @@ class CholeskyGpu {
   void reset() { analyzed_ = false; }
   const SymbolicFactor& symbolic() const { return S_; }
 
-  // numeric factorisation of A + lambda*I (A: device, input block order, d*d col-major per block).
-  // d_lambda may be nullptr (lambda = 0).  Asynchronous on s; the not-positive-definite outcome lands in
-  // the device flag read by status().
-  // d_b (optional): right-hand side; when given, the forward substitution is fused into the factorisation (the
-  // supernode's right-hand side rides along as one more panel row) and the next solve() only runs the backward sweep.
+  // numeric factorisation of A + lambda*I (A: device, input block order, d*d col-major per block) and, fused into
+  // it, the forward substitution of the right-hand side d_b (the supernode's right-hand side rides along as one more
+  // panel row).  d_lambda may be nullptr (lambda = 0).  Asynchronous on s: a few setup kernels + ONE persistent
+  // dataflow kernel; the not-positive-definite outcome lands in the device flag behind status_ptr().
   void factor(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
               EventProfiler* prof = nullptr);
-  // x = A^-1 b (both device, length nb*d, original ordering).  Asynchronous on s.
+  // x = A^-1 b for the b given to the preceding factor() (device, length nb*d, original ordering): the backward
+  // sweep (one persistent dataflow kernel) + un-permutation.  One solve() per factor().  Asynchronous on s.
   void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
-  int* status_ptr() { return d_status_.p; }  // device int: 0 ok, 1 not positive definite
+  int* status_ptr() { return d_counters_.p + 2; }  // device int: 0 ok, 1 not positive definite
   double* factor_values() { return d_L_.p; }
 
  private:
@@ -45,28 +45,30 @@ class CholeskyGpu {
   SymbolicFactor S_;
   DevBuf<int> d_sn_col0_, d_sn_ncol_, d_sn_nrow_, d_sn_rowptr_, d_sn_rows_;
   DevBuf<long long> d_sn_lptr_;
-  DevBuf<int> d_upd_ptr_, d_upd_k_, d_upd_p0_, d_upd_p1_, d_rel_;
-  DevBuf<long long> d_upd_relptr_;
-  DevBuf<int> d_task_ptr_, d_task_sn_;
+  DevBuf<int> d_rel_;
+  DevBuf<int> d_task_ptr_, d_task_sn_, d_task_parent_;
   DevBuf<long long> d_a_dst_, d_diag_dst_;
   DevBuf<int> d_a_ld_, d_diag_ld_, d_perm_;
   DevBuf<unsigned char> d_a_trans_;
-  DevBuf<int> d_tile_sn_, d_tile_r0_, d_tile_c0_, d_tile_work_ptr_, d_work_u_, d_work_a0_, d_work_a1_, d_work_b0_, d_work_b1_;
-  DevBuf<int> d_sn_tile_ptr_, d_sn_chunk_ptr_, d_chunk_sn_, d_chunk_b0_, d_chunk_nb_, d_level_chunks_;
-  DevBuf<int> d_group_tile_, d_group_w0_, d_group_w1_, d_group_slot_, d_rtile_tile_, d_rtile_slot0_, d_rtile_nslots_;
+  DevBuf<int> d_tile_sn_, d_tile_r0_, d_tile_c0_, d_tile_work_ptr_, d_work_a0_, d_work_a1_, d_work_b0_, d_work_b1_;
+  DevBuf<int> d_sn_tile_ptr_, d_sn_chunk_ptr_, d_chunk_sn_, d_chunk_b0_, d_chunk_nb_;
+  DevBuf<int> d_group_tile_, d_group_w0_, d_group_w1_, d_group_slot_, d_group_rtile_, d_rtile_tile_, d_rtile_slot0_, d_rtile_nslots_;
   DevBuf<long long> d_sn_dinvptr_, d_sn_cptr_, d_work_koff_, d_work_reloff_;
-  DevBuf<int> d_work_mk_, d_work_nk_, d_fwd_ptr_, d_fwd_src_;
+  DevBuf<int> d_work_mk_, d_work_nk_, d_work_ksn_, d_fwd_ptr_, d_fwd_src_;
+  DevBuf<int> d_flow_kind_, d_flow_arg_, d_sn_nupd_, d_sn_nchunk_;
   DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_, d_z_, d_gscratch_, d_contrib_;
-  DevBuf<int> d_status_;
+  DevBuf<int> d_counters_;  // task counters, status flag, completion counters (zeroed by every factor())
+  int cnt_upd_ = 0, cnt_chunk_ = 0, cnt_slot_ = 0, cnt_bdone_ = 0;
+  size_t flow_smem_ = 0;
+  int xb_doubles_ = 0, stage_doubles_ = 0, flow_grid_ = 1, back_grid_ = 1;
   int nblk_ = 0;
   CholDev dev() const;
   CholPlanDev plan() const;
   template <int D>
   void factor_t(const double* dA, const double* d_lambda, const double* d_b, cudaStream_t s, LaunchCounter* lc,
                 EventProfiler* prof);
-  bool forward_done_ = false;
   template <int D>
-  void solve_t(const double* b, double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof);
+  void solve_t(double* x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof);
 };
 
 }  // namespace g2o_b200

@@ -396,7 +396,7 @@ int build_structure_impl(b200_ctx* c) {
   // ---- symbolic phase of the linear solver
   SymbolicOptions opt;
   // tuning knobs (the adapter exposes them as solver properties; the environment overrides are for experiments)
-  if (const char* e = getenv("G2O_B200_PANEL_COLS")) opt.max_panel_cols_scalar = std::max(pd, std::min(96, atoi(e)));
+  if (const char* e = getenv("G2O_B200_PANEL_COLS")) opt.max_panel_cols_scalar = std::max(pd, std::min(72, atoi(e)));
   if (const char* e = getenv("G2O_B200_SUBTREE_FLOPS")) opt.subtree_min_flops = atof(e);
   if (const char* e = getenv("G2O_B200_RELAX")) opt.relax = atoi(e) != 0;
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);

@@ -122,7 +122,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   }
   // width cap: split wide supernodes into a chain of panels
   {
-    const int wmax = std::max(1, opt.max_panel_cols_scalar / d);
+    const int wmax = std::max(1, std::min(opt.max_panel_cols_scalar / d, 12));  // one warp per block column, 12 warps per CTA
     std::vector<int> f2, c2;
     for (int s = 0; s < ns; ++s) {
       int rem = nc[s], c0 = first[s];
@@ -343,9 +343,10 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
 
   // ---- 9. numeric plan: destination tiles + their work items, row chunks, level kinds
   const int TB = std::max(1, 48 / d);
-  const int CHB = std::max(1, 96 / d);
+  // a chunk CTA maps block rows to the 32 lanes of a warp: diagonal block + chunk rows + the right-hand-side row
+  auto chunk_cap = [&](int J) { return 31 - S.sn_ncol[J]; };
   S.tile_blocks = TB;
-  S.chunk_blocks = CHB;
+  S.chunk_blocks = 30;
   S.sn_tile_ptr.assign(ns + 1, 0);
   std::vector<std::vector<int>> tile_lookup(ns);  // [tr * nct + tc] -> tile id or -1
   std::vector<int> sn_nct(ns, 0);
@@ -402,13 +403,14 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   }
   {
     const int nw = (int)S.work_u.size();
-    S.work_koff.resize(nw); S.work_reloff.resize(nw); S.work_mk.resize(nw); S.work_nk.resize(nw);
+    S.work_koff.resize(nw); S.work_reloff.resize(nw); S.work_mk.resize(nw); S.work_nk.resize(nw); S.work_ksn.resize(nw);
     for (int q = 0; q < nw; ++q) {
       const int u = S.work_u[q], K = S.upd_k[u];
       S.work_koff[q] = S.sn_lptr[K] + (int64_t)S.upd_p0[u] * d;
       S.work_reloff[q] = S.upd_relptr[u];
       S.work_mk[q] = S.sn_nrow[K] * d;
       S.work_nk[q] = S.sn_ncol[K] * d;
+      S.work_ksn[q] = K;
     }
   }
   S.sn_chunk_ptr.assign(ns + 1, 0);
@@ -418,7 +420,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     int b0 = S.sn_ncol[J];
     if (below == 0) { S.chunk_sn.push_back(J); S.chunk_b0.push_back(b0); S.chunk_nb.push_back(0); }
     for (int rem = below; rem > 0;) {
-      const int nbk = std::min(rem, CHB);
+      const int nbk = std::min(rem, chunk_cap(J));
       S.chunk_sn.push_back(J); S.chunk_b0.push_back(b0); S.chunk_nb.push_back(nbk);
       b0 += nbk; rem -= nbk;
     }
@@ -432,7 +434,11 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   S.level_chunk_ptr.assign(S.nlevels + 1, 0);
   S.level_group_ptr.assign(S.nlevels + 1, 0);
   S.level_rtile_ptr.assign(S.nlevels + 1, 0);
-  S.group_items = 3;
+  S.group_items = std::max(1, opt.group_items);
+  S.sn_nupd.assign(ns, 0);
+  S.sn_nchunk.assign(ns, 0);
+  for (int J = 0; J < ns; ++J) S.sn_nchunk[J] = S.sn_chunk_ptr[J + 1] - S.sn_chunk_ptr[J];
+  int slots = 0;  // scratch slots are numbered globally
   S.sn_cptr.assign(ns + 1, 0);
   for (int J = 0; J < ns; ++J) S.sn_cptr[J + 1] = S.sn_cptr[J] + (int64_t)(S.sn_nrow[J] - S.sn_ncol[J]) * d;
   {  // forward-solve gather lists
@@ -467,12 +473,11 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         tiles += S.sn_tile_ptr[J + 1] - S.sn_tile_ptr[J];
         chunks += S.sn_chunk_ptr[J + 1] - S.sn_chunk_ptr[J];
         const int N = S.sn_ncol[J] * d;
-        const int rows = N + std::min(S.sn_nrow[J] - S.sn_ncol[J], CHB) * d;
+        const int rows = N + std::min(S.sn_nrow[J] - S.sn_ncol[J], chunk_cap(J)) * d;
         smem = std::max(smem, rows * N * 8);
       }
     }
     S.level_smem[l] = smem;
-    int slots = 0;
     if (singletons && (tiles > ntask || chunks > ntask)) {
       S.level_kind[l] = 1;
       for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
@@ -482,12 +487,15 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
           if (w1 == w0) continue;
           S.level_tiles.push_back(q);
           const int ng = (w1 - w0 + S.group_items - 1) / S.group_items;
+          S.sn_nupd[J]++;
           if (ng == 1) {
             S.group_tile.push_back(q); S.group_w0.push_back(w0); S.group_w1.push_back(w1); S.group_slot.push_back(-1);
+            S.group_rtile.push_back(-1);
           } else {
             S.rtile_tile.push_back(q); S.rtile_slot0.push_back(slots); S.rtile_nslots.push_back(ng);
             for (int gi = 0; gi < ng; ++gi) {
               S.group_tile.push_back(q);
+              S.group_rtile.push_back((int)S.rtile_tile.size() - 1);
               S.group_w0.push_back(w0 + (int)((long long)(w1 - w0) * gi / ng));
               S.group_w1.push_back(w0 + (int)((long long)(w1 - w0) * (gi + 1) / ng));
               S.group_slot.push_back(slots++);
@@ -497,11 +505,31 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         for (int q = S.sn_chunk_ptr[J]; q < S.sn_chunk_ptr[J + 1]; ++q) S.level_chunks.push_back(q);
       }
     }
-    S.max_group_slots = std::max(S.max_group_slots, slots);
+    S.max_group_slots = slots;
     S.level_tile_ptr[l + 1] = (int)S.level_tiles.size();
     S.level_chunk_ptr[l + 1] = (int)S.level_chunks.size();
     S.level_group_ptr[l + 1] = (int)S.group_tile.size();
     S.level_rtile_ptr[l + 1] = (int)S.rtile_tile.size();
+  }
+  // ---- 10. dataflow task list (level-major; inside a split level: groups, reduce tiles, chunks)
+  for (int l = 0; l < S.nlevels; ++l) {
+    if (S.level_kind[l] == 0) {
+      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) { S.flow_kind.push_back(0); S.flow_arg.push_back(t); }
+    } else {
+      for (int g = S.level_group_ptr[l]; g < S.level_group_ptr[l + 1]; ++g) { S.flow_kind.push_back(1); S.flow_arg.push_back(g); }
+      for (int r = S.level_rtile_ptr[l]; r < S.level_rtile_ptr[l + 1]; ++r) { S.flow_kind.push_back(2); S.flow_arg.push_back(r); }
+      for (int c = S.level_chunk_ptr[l]; c < S.level_chunk_ptr[l + 1]; ++c) { S.flow_kind.push_back(3); S.flow_arg.push_back(S.level_chunks[c]); }
+    }
+  }
+  {
+    std::vector<int> sn_task(ns, -1);
+    for (int t = 0; t < nt; ++t) for (int q = S.task_ptr[t]; q < S.task_ptr[t + 1]; ++q) sn_task[S.task_sn[q]] = t;
+    S.task_parent.assign(nt, -1);
+    for (int t = 0; t < nt; ++t) {
+      const int root_sn = S.task_sn[S.task_ptr[t + 1] - 1];  // ascending order inside a task: the root comes last
+      const int p = S.sn_parent[root_sn];
+      S.task_parent[t] = p < 0 ? -1 : sn_task[p];
+    }
   }
   return S;
 }

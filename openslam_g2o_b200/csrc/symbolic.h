@@ -14,11 +14,12 @@
 namespace g2o_b200 {
 
 struct SymbolicOptions {
-  int max_panel_cols_scalar = 72;   // supernodes wider than this are split into a chain of panels (<= 96; 72
-                                    // measured best on sphere2500, flat on Venice: profiles/r01_sweep_panel_cols.txt)
+  int max_panel_cols_scalar = 72;   // supernodes wider than this are split into a chain of panels (<= 72 scalars
+                                    // and <= 12 blocks: the panel factorisation maps one warp per block column)
   double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
   double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
   bool relax = true;
+  int group_items = 4;              // split-K: work items per group task
   // set when the caller already knows the ordering (tests); empty = run block AMD
   std::vector<int> given_perm;
 };
@@ -75,7 +76,8 @@ struct SymbolicFactor {
   std::vector<int> level_tile_ptr, level_tiles, level_chunk_ptr, level_chunks;
   // split-K groups of the split levels: a tile with many work items is cut into groups of <= group_items items;
   // each group is one CTA.  slot < 0: the tile has a single group and subtracts from the panel directly; otherwise
-  // the group writes its partial 48x48 sum to scratch slot `slot` and the tile's reduce CTA adds the slots in order.
+  // the group writes its partial 48x48 sum to scratch slot `slot` (numbered globally: levels overlap in the dataflow
+  // kernel) and the tile's reduce task adds the slots in order.
   int group_items = 0;
   std::vector<int> level_group_ptr, group_tile, group_w0, group_w1, group_slot;   // per level: its groups
   std::vector<int> level_rtile_ptr, rtile_tile, rtile_slot0, rtile_nslots;        // per level: tiles needing a reduce
@@ -85,6 +87,20 @@ struct SymbolicFactor {
   // ... and every scalar row of the permuted system lists the contribution entries it has to subtract, in
   // ascending (supernode, row) order (fixed summation order)
   std::vector<int> fwd_ptr, fwd_src;               // n+1 ; indices into the contribution array
+  // ---- dataflow schedule (chol.cu: one persistent kernel per factorisation / per backward sweep).  The numeric work
+  // is cut into tasks listed in level-major order; a CTA takes the next task from a global counter and spins on the
+  // completion counters of what the task consumes.  Every dependency points to an earlier entry of the list, so
+  // the earliest unfinished task is always held by a running CTA (no deadlock, whatever the grid size).
+  //   kind 0 SUBTREE(task)  update + factor of every supernode of a small subtree, sequentially in one CTA
+  //   kind 1 GROUP(group)   one split-K group of a destination tile: waits for each source supernode in list order
+  //   kind 2 RTILE(rtile)   adds the partial sums of a split tile in group order, subtracts once
+  //   kind 3 CHUNK(chunk)   waits for every update of its supernode, factors diagonal block + its row chunk
+  std::vector<int> flow_kind, flow_arg;
+  std::vector<int> work_ksn;                       // source supernode of a work item
+  std::vector<int> sn_nupd;                        // update completions (direct groups + rtiles) a supernode waits for
+  std::vector<int> sn_nchunk;                      // chunks of a supernode: it is ready when all of them are stored
+  std::vector<int> group_rtile;                    // per group: its rtile (-1: subtracts directly)
+  std::vector<int> task_parent;                    // per task: the task holding the parent of its root supernode
   // inverses of the triangular diagonal blocks (for the solves)
   std::vector<int64_t> sn_dinvptr;                 // nsn+1
   int64_t dinv_doubles = 0;

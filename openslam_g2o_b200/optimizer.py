@@ -213,7 +213,7 @@ class SolverContext:
 
     def phase_times(self):
         names = ("errors", "linearize", "schur", "factor", "trisolve", "update", "backsub", "linearize_cams", "gather",
-                 "schur_inv", "scale", "collective", "chol_scatter", "chol_update", "chol_reduce", "chol_panel",
+                 "schur_inv", "scale", "collective", "chol_scatter", "chol_factor_flow", "chol_reduce", "chol_panel",
                  "chol_fused", "chol_invert", "chol_forward", "chol_backward")
         out = {}
         for i, nme in enumerate(names):

@@ -158,3 +158,80 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
   for (int k = 0; k < nb; ++k) for (int r = 0; r < d; ++r) x[S.perm[k] * d + r] = y[k * d + r];
   return 0;
 }
+
+// Dataflow schedule check: walking flow_kind/flow_arg in list order, everything a task waits for must already be
+// complete (dependencies only point backwards - the no-deadlock argument of chol.cu), every group / reduce tile /
+// chunk must appear exactly once, and the completion targets (sn_nupd, sn_nchunk) must be reached exactly.
+extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int max_cols, int relax, int group_items) {
+  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.group_items = group_items;
+  SymbolicFactor S = analyze(nb, d, cp, ri, o);
+  const int nt = (int)S.task_ptr.size() - 1;
+  std::vector<int> upd(S.nsn, 0), chunk(S.nsn, 0), slot(S.rtile_tile.size(), 0);
+  std::vector<char> seen_g(S.group_tile.size(), 0), seen_r(S.rtile_tile.size(), 0), seen_c(S.chunk_sn.size(), 0), seen_t(nt, 0);
+  auto ready = [&](int K) { return chunk[K] == S.sn_nchunk[K]; };
+  auto items_ready = [&](int w0, int w1) {
+    for (int wi = w0; wi < w1; ++wi) if (!ready(S.work_ksn[wi])) return false;
+    return true;
+  };
+  for (size_t i = 0; i < S.flow_kind.size(); ++i) {
+    const int a = S.flow_arg[i];
+    switch (S.flow_kind[i]) {
+      case 0: {
+        if (a < 0 || a >= nt || seen_t[a]) return -10;
+        seen_t[a] = 1;
+        for (int q = S.task_ptr[a]; q < S.task_ptr[a + 1]; ++q) {
+          const int J = S.task_sn[q];
+          if (S.sn_nupd[J] != 0) return -11;  // subtree supernodes are updated by their own CTA
+          for (int t = S.sn_tile_ptr[J]; t < S.sn_tile_ptr[J + 1]; ++t)
+            if (!items_ready(S.tile_work_ptr[t], S.tile_work_ptr[t + 1])) return -12;
+          for (int c = S.sn_chunk_ptr[J]; c < S.sn_chunk_ptr[J + 1]; ++c) { if (seen_c[c]) return -13; seen_c[c] = 1; chunk[J]++; }
+        }
+        break;
+      }
+      case 1: {
+        if (a < 0 || a >= (int)seen_g.size() || seen_g[a]) return -20;
+        seen_g[a] = 1;
+        if (!items_ready(S.group_w0[a], S.group_w1[a])) return -21;
+        const int r = S.group_rtile[a];
+        if ((r < 0) != (S.group_slot[a] < 0)) return -22;
+        if (r < 0) upd[S.tile_sn[S.group_tile[a]]]++;
+        else { if (S.rtile_tile[r] != S.group_tile[a]) return -23; slot[r]++; }
+        break;
+      }
+      case 2: {
+        if (a < 0 || a >= (int)seen_r.size() || seen_r[a]) return -30;
+        seen_r[a] = 1;
+        if (slot[a] != S.rtile_nslots[a]) return -31;
+        upd[S.tile_sn[S.rtile_tile[a]]]++;
+        break;
+      }
+      case 3: {
+        if (a < 0 || a >= (int)seen_c.size() || seen_c[a]) return -40;
+        seen_c[a] = 1;
+        const int J = S.chunk_sn[a];
+        if (upd[J] != S.sn_nupd[J]) return -41;
+        chunk[J]++;
+        break;
+      }
+      default: return -50;
+    }
+  }
+  for (int J = 0; J < S.nsn; ++J) if (!ready(J) || upd[J] != S.sn_nupd[J]) return -60;
+  for (char c : seen_g) if (!c) return -61;
+  for (char c : seen_r) if (!c) return -62;
+  for (char c : seen_c) if (!c) return -63;
+  // scratch slots must be unique across the whole factorisation (levels overlap in the dataflow kernel)
+  {
+    std::vector<char> used(std::max(S.max_group_slots, 1), 0);
+    for (size_t g = 0; g < S.group_slot.size(); ++g)
+      if (S.group_slot[g] >= 0) { if (S.group_slot[g] >= S.max_group_slots || used[S.group_slot[g]]) return -70; used[S.group_slot[g]] = 1; }
+  }
+  // backward sweep: the parent task of a task must sit later in the (level-sorted) task list
+  for (int t = 0; t < nt; ++t) if (S.task_parent[t] >= 0 && S.task_parent[t] <= t) return -80;
+  // panel geometry the kernels rely on
+  for (int J = 0; J < S.nsn; ++J) {
+    if (S.sn_ncol[J] > 12) return -90;
+    for (int c = S.sn_chunk_ptr[J]; c < S.sn_chunk_ptr[J + 1]; ++c) if (S.sn_ncol[J] + S.chunk_nb[c] + 1 > 32) return -91;
+  }
+  return 0;
+}

@@ -47,6 +47,31 @@ def test_schedule_execution_solves_the_system(hx, d):
             assert rc == 0, (rc, trial, nb, maxc, relax)
             xr = np.linalg.solve(A + 0.25 * np.eye(nb * d), b)
             assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+            # the dataflow task list of the persistent kernels: dependencies only point backwards, counters add up
+            for gi in (1, 4):
+                assert hx.hx_check_flow(nb, d, _p(cp), _p(ri), maxc, relax, gi) == 0, (trial, nb, maxc, relax, gi)
+
+
+def test_dataflow_schedule_on_benchmark_shaped_patterns(hx):
+    """ring band (the reduced camera system of the Venice-shaped BA) and a 50 x 50 torus-like grid (sphere2500)"""
+    def pattern(nb, edges):
+        cols = [set([c]) for c in range(nb)]
+        for i, j in edges:
+            cols[max(i, j)].add(min(i, j))
+        cp = np.zeros(nb + 1, dtype=np.int32)
+        ri = []
+        for c in range(nb):
+            r = sorted(cols[c])
+            ri += r
+            cp[c + 1] = len(ri)
+        return cp, np.asarray(ri, dtype=np.int32)
+    ring = [(i, (i + k) % 871) for i in range(871) for k in range(1, 9)]
+    grid = [(r * 50 + c, r * 50 + (c + 1) % 50) for r in range(50) for c in range(50)] + \
+           [(r * 50 + c, (r + 1) * 50 + c) for r in range(49) for c in range(50)]
+    for nb, edges, d in ((871, ring, 6), (2500, grid, 6), (2500, grid, 3)):
+        cp, ri = pattern(nb, edges)
+        for maxc, gi in ((72, 4), (72, 1), (24, 3)):
+            assert hx.hx_check_flow(nb, d, _p(cp), _p(ri), maxc, 1, gi) == 0, (nb, d, maxc, gi)
 
 
 def test_not_positive_definite_is_reported(hx):
