@@ -118,8 +118,8 @@ __device__ __forceinline__ void cta_wait(const int* counter, int target) {
 }
 
 #ifdef CHOL_TIMING
-__device__ unsigned long long g_chol_timing[16];
-#define TCK(i) do { if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_chol_timing[i], _n - _t0); _t0 = _n; } } while (0)
+__device__ unsigned long long g_chol_timing[32];
+#define TCK(i) do { if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_chol_timing[i], _n - _t0); atomicAdd(&g_chol_timing[16 + (i)], 1ull); _t0 = _n; } } while (0)
 #define TCK_INIT unsigned long long _t0 = clock64()
 #else
 #define TCK(i) do {} while (0)
@@ -237,70 +237,144 @@ __device__ void subtract_tile(const CholDev& P, const CholPlanDev& Q, double* __
   }
 }
 
-// 1/sqrt(s) to full double accuracy: single-precision seed (one MUFU) + two Newton steps in double; falls back to the
-// library routine outside the float range.  Sits on the critical path of every block column.
+// 1/sqrt(s) to full double accuracy: hardware seed (MUFU.RSQ64H, ~2^-22) + two Newton steps in double.  Sits on the
+// critical path of every block column.
 __device__ __forceinline__ double fast_rsqrt(double s) {
-  if (s < 1e-30 || s > 1e30) return rsqrt(s);
-  double r = (double)rsqrtf((float)s);
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
   const double hs = -0.5 * s;
   r = r * fma(hs * r, r, 1.5);
   r = r * fma(hs * r, r, 1.5);
   return r;
 }
 
-// Panel factorisation of one (supernode, row chunk).  Block rows map to lanes ("slots"): slot s < ncb is block row s
-// of the diagonal block, slots ncb .. ncb+cnb-1 are the chunk's block rows, slot ncb+cnb carries the right-hand side
-// of the supernode in its first row - its triangular solve IS the forward substitution y_J = L11^-1 t.
-// Warp w owns block column w: every thread keeps its d x d block in registers over the whole sweep.  Per block
-// column jb: lane jb of warp jb factors the pivot block in place and publishes it, the rest of warp jb solves its
-// blocks against it and writes the finished block column to shared memory (one barrier), then every warp w > jb
-// applies the rank-d update to its registers.  Warp jb+1 proceeds to its pivot while the others still update.
+struct ChunkGeom {
+  int J, ncb, M, N, cnb, crow0, crows, Rp, rs, nslots, col0s;
+  double* Pj;
+};
 template <int D>
-__device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, double* __restrict__ Ldiag,
-                             double* __restrict__ Dinv, int chunk, bool first, double* __restrict__ Sm, int* status,
-                             const double* __restrict__ y, double* __restrict__ z, double* contrib, int* chunk_done) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
-  const int J = Q.chunk_sn[chunk];
-  const int ncb = P.sn_ncol[J];
-  const int M = P.sn_nrow[J] * D, N = ncb * D;
-  const int cnb = Q.chunk_nb[chunk];
-  const int crow0 = Q.chunk_b0[chunk] * D, crows = cnb * D;
-  const int Rp = N + crows;       // panel rows staged
-  const int rs = ncb + cnb;       // slot of the right-hand side
-  const int nslots = rs + 1;
-  const int col0s = P.sn_col0[J] * D;
-  double* Pj = L + P.sn_lptr[J];
-  double* piv = Sm + N * D * kLds;           // D*D factored pivot block | D reciprocal diagonal entries
+__device__ __forceinline__ ChunkGeom chunk_geom(const CholDev& P, const CholPlanDev& Q, double* L, int chunk) {
+  ChunkGeom g;
+  g.J = Q.chunk_sn[chunk];
+  g.ncb = P.sn_ncol[g.J];
+  g.M = P.sn_nrow[g.J] * D;
+  g.N = g.ncb * D;
+  g.cnb = Q.chunk_nb[chunk];
+  g.crow0 = Q.chunk_b0[chunk] * D;
+  g.crows = g.cnb * D;
+  g.Rp = g.N + g.crows;        // panel rows staged
+  g.rs = g.ncb + g.cnb;        // slot of the right-hand side
+  g.nslots = g.rs + 1;
+  g.col0s = P.sn_col0[g.J] * D;
+  g.Pj = L + P.sn_lptr[g.J];
+  return g;
+}
+#define CHUNK_GEOM_LOCALS                                                                                     \
+  const int tid = threadIdx.x, nt = blockDim.x;                                                               \
+  const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;                                                      \
+  const int J = G.J, ncb = G.ncb, M = G.M, N = G.N, crow0 = G.crow0, crows = G.crows, Rp = G.Rp, rs = G.rs,  \
+            nslots = G.nslots, col0s = G.col0s;                                                               \
+  double* Pj = G.Pj;                                                                                          \
+  double* piv = Sm + N * D * kLds; /* D*D factored pivot block | D reciprocal diagonal entries */             \
+  (void)tid; (void)nt; (void)lane; (void)w; (void)nw; (void)J; (void)ncb; (void)M; (void)crow0; (void)crows; \
+  (void)Rp; (void)rs; (void)nslots; (void)col0s; (void)Pj; (void)piv
+
+// phase 1: plan prefetch, wait for the updates of the supernode, right-hand-side gather, panel -> shared memory
+template <int D>
+__device__ __forceinline__ void chunk_load(const ChunkGeom& G, const CholPlanDev& Q, double* __restrict__ Sm,
+                                        const double* __restrict__ y, const double* contrib, const int* wait_counter,
+                                        int wait_target) {
+  CHUNK_GEOM_LOCALS;
   TCK_INIT;
-  __syncthreads();
-  {
-    // warps split in two groups: one gathers the right-hand side
-    // t_c = (P b)_c - sum of the descendants' contributions (lanes stride the list, fixed shuffle tree),
-    // the other streams the panel in (coalesced along the rows of a column)
-    const int ngather = max(1, nw / 4);
-    if (w < ngather) {
-      for (int c = w; c < N; c += ngather) {
-        const int g = col0s + c;
-        const int e0 = Q.fwd_ptr[g], e1 = Q.fwd_ptr[g + 1];
-        double part = 0.0;
-        for (int e = e0 + lane; e < e1; e += 32) part += __ldcg(contrib + Q.fwd_src[e]);
+  // before waiting for the updates of this supernode: everything that only depends on the (static) plan.
+  // Right-hand side gather t_c = (P b)_c - sum of the descendants' contributions: thread c owns column c and
+  // prefetches its list bounds and the first source indices
+  constexpr int kPre = 8;
+  __shared__ int s_ge0[kMaxPanelCols], s_ge1[kMaxPanelCols];
+  int ge0 = 0, ge1 = 0, gsrc[kPre];
+  double gy = 0.0;
+  if (tid < N) {
+    const int g = col0s + tid;
+    ge0 = Q.fwd_ptr[g];
+    ge1 = Q.fwd_ptr[g + 1];
+    gy = y[g];
+    s_ge0[tid] = ge0;
+    s_ge1[tid] = ge1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane < D) Sm[(c * D + lane) * kLds + rs] = lane == 0 ? y[g] - part : 0.0;
-      }
-    } else {
-      const int t2 = tid - ngather * 32, n2 = nt - ngather * 32;
-      for (int i = t2; i < Rp * N; i += n2) {
-        const int c = i / Rp, r = i - c * Rp;
-        const int gr = r < N ? r : crow0 + (r - N);
-        const int slot = r / D;
-        Sm[(c * D + (r - slot * D)) * kLds + slot] = __ldcg(Pj + (gr + (long long)c * M));
+    for (int q = 0; q < kPre; ++q) gsrc[q] = ge0 + q < ge1 ? Q.fwd_src[ge0 + q] : -1;
+  }
+  if (wait_target > 0) {
+    if (tid == 0) {
+      unsigned spins = 0;
+      while (ld_acquire(wait_counter) < wait_target)
+        if (++spins > kSpinLimit) __trap();
+    }
+  }
+  __syncthreads();
+  TCK(6);
+  {
+    // the panel streams in one column per warp pass (coalesced along the rows, 6 independent L2 loads in flight
+    // per thread); the threads owning a right-hand-side column add up their contributions in list order
+    if (tid < N) {
+      double part = 0.0;
+#pragma unroll
+      for (int q = 0; q < kPre; ++q)
+        if (gsrc[q] >= 0) part += __ldcg(contrib + gsrc[q]);
+#pragma unroll
+      for (int i = 1; i < D; ++i) Sm[(tid * D + i) * kLds + rs] = 0.0;
+      if (ge1 - ge0 <= kPre) Sm[(tid * D) * kLds + rs] = gy - part;
+    }
+    // long lists (upper part of the tree): one warp per column, lanes stride the list, fixed shuffle tree
+    for (int c = w; c < N; c += nw) {
+      const int e0 = s_ge0[c], e1 = s_ge1[c];
+      if (e1 - e0 <= kPre) continue;
+      double part = 0.0;
+      for (int e = e0 + lane; e < e1; e += 32) part += __ldcg(contrib + Q.fwd_src[e]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) Sm[(c * D) * kLds + rs] = y[col0s + c] - part;
+    }
+    TCK(8);
+    // kC columns x kU row strides per pass: up to kC*kU independent L2 loads in flight per thread
+    constexpr int kU = 6, kC = 1;
+    for (int c0 = w; c0 < N; c0 += nw * kC) {
+      for (int r0 = lane; r0 < Rp; r0 += 32 * kU) {
+        double v[kC][kU];
+#pragma unroll
+        for (int cc = 0; cc < kC; ++cc) {
+          const int c = c0 + cc * nw;
+          const double* src = Pj + (long long)c * M;
+#pragma unroll
+          for (int q = 0; q < kU; ++q) {
+            const int r = r0 + 32 * q;
+            if (c < N && r < Rp) v[cc][q] = __ldcg(src + (r < N ? r : crow0 + (r - N)));
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < kC; ++cc) {
+          const int c = c0 + cc * nw;
+          double* dst = Sm + c * D * kLds;
+#pragma unroll
+          for (int q = 0; q < kU; ++q) {
+            const int r = r0 + 32 * q;
+            if (c < N && r < Rp) {
+              const int slot = r / D;
+              dst[(r - slot * D) * kLds + slot] = v[cc][q];
+            }
+          }
+        }
       }
     }
   }
   __syncthreads();
   TCK(2);
+}
+
+// phase 2: the register-resident factorisation (see above); leaves the finished panel in shared memory
+template <int D>
+__device__ __forceinline__ void chunk_core(const ChunkGeom& G, double* __restrict__ Sm, int* status) {
+  CHUNK_GEOM_LOCALS;
+  TCK_INIT;
   // lanes above the diagonal of the diagonal block hold nothing
   const bool active = w < ncb && lane < nslots && lane >= w;
   double B[D][D];  // B[i][j]: row i, column j of my block
@@ -360,6 +434,10 @@ __device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q
       }
     }
     __syncthreads();
+    // the warp of the next pivot column updates first: the others start when it is done, so that their updates
+    // run in the shadow of its (latency-bound) pivot factorisation instead of competing for the FP64 pipe
+    const int nupd_threads = 32 * (ncb - jb - 1);
+    if (w > jb + 1 && w < ncb) asm volatile("bar.sync 1, %0;" ::"r"(nupd_threads) : "memory");
     if (active && w > jb) {
       // rank-D update of my block: B -= X(my block row) * X(block row w)^T over the finished block column jb
       const double* xa = Sm + (jb * D * D) * kLds + lane;
@@ -378,27 +456,41 @@ __device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q
           for (int i = 0; i < D; ++i) B[i][j] = fma(-a[i], b[j], B[i][j]);
       }
     }
+    if (w == jb + 1 && w < ncb) asm volatile("bar.arrive 1, %0;" ::"r"(nupd_threads) : "memory");
   }
   TCK(3);
+}
+
+// phase 3: panel rows, forward-substitution results and the contribution vector to global memory, completion signal,
+// then (off the critical path) the inverse of the diagonal block
+template <int D>
+__device__ __forceinline__ void chunk_store(const ChunkGeom& G, const CholPlanDev& Q, double* __restrict__ Sm,
+                                         double* __restrict__ Ldiag, double* __restrict__ Dinv, bool first,
+                                         double* __restrict__ z, double* contrib, int* chunk_done) {
+  CHUNK_GEOM_LOCALS;
+  TCK_INIT;
   // the finished panel sits in shared memory (the last iteration ended with a barrier and no update)
   {
-    const int R = Rp + 1;
-    for (int i = tid; i < R * N; i += nt) {
-      const int c = i / R, r = i - c * R;
-      if (r < Rp) {
-        const int slot = r / D;
-        const double v = Sm[(c * D + (r - slot * D)) * kLds + slot];
-        if (r < N) {
-          // the factored diagonal block goes to its own array: sibling chunk CTAs are still reading the unfactored
-          // block from the panel (every chunk factors it redundantly), so it must not be overwritten in place
-          if (first && r >= c) Ldiag[Q.sn_dinvptr[J] + r + (long long)c * N] = v;
-        } else {
-          __stcg(Pj + (crow0 + (r - N) + (long long)c * M), v);
+    // one column per warp pass, lanes stride the rows (coalesced stores, no divisions by run-time values)
+    for (int c = w; c < N; c += nw) {
+      const double* src = Sm + c * D * kLds;
+      if (first) {
+        // the factored diagonal block goes to its own array: sibling chunk CTAs are still reading the unfactored
+        // block from the panel (every chunk factors it redundantly), so it must not be overwritten in place
+        double* dd = Ldiag + Q.sn_dinvptr[J] + (long long)c * N;
+        for (int r = c + lane; r < N; r += 32) {
+          const int slot = r / D;
+          dd[r] = src[(r - slot * D) * kLds + slot];
         }
-      } else if (first) {
-        z[col0s + c] = Sm[(c * D) * kLds + rs];  // y_J goes to its own vector: sibling chunks still read (P b)_J from y
+        if (lane == 0) z[col0s + c] = src[rs];  // y_J goes to its own vector: sibling chunks still read (P b)_J from y
+      }
+      double* dp = Pj + (crow0 - N + (long long)c * M);
+      for (int r = N + lane; r < Rp; r += 32) {
+        const int slot = r / D;
+        __stcg(dp + r, src[(r - slot * D) * kLds + slot]);
       }
     }
+    TCK(9);
     // c_J = L21 y_J for this chunk's rows: what every ancestor will subtract from its right-hand side.
     // 4 threads per row, each a quarter of the columns, fixed shuffle tree
     double* cj = contrib + Q.sn_cptr[J] + (crow0 - N);
@@ -414,6 +506,7 @@ __device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q
       if (r < crows && q == 0) __stcg(cj + r, s);
     }
   }
+  TCK(10);
   cta_signal(chunk_done + J);
   TCK(4);
   if (first) {
@@ -443,6 +536,17 @@ __device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q
     }
     TCK(5);
   }
+}
+
+template <int D>
+__device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, double* __restrict__ Ldiag,
+                             double* __restrict__ Dinv, int chunk, bool first, double* __restrict__ Sm, int* status,
+                             const double* __restrict__ y, double* __restrict__ z, double* contrib, int* chunk_done,
+                             const int* wait_counter, int wait_target) {
+  const ChunkGeom G = chunk_geom<D>(P, Q, L, chunk);
+  chunk_load<D>(G, Q, Sm, y, contrib, wait_counter, wait_target);
+  chunk_core<D>(G, Sm, status);
+  chunk_store<D>(G, Q, Sm, Ldiag, Dinv, first, z, contrib, chunk_done);
 }
 
 template <int D>
@@ -478,7 +582,9 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
       }
     } else if (kind == 2) {  // RTILE: add the partial sums in group order, subtract once
       const int ns = F.r_nslots[arg];
+      TCK_INIT;
       cta_wait(F.slot_done + arg, ns);
+      TCK(7);
       const double* in = F.scratch + (long long)F.r_slot0[arg] * kTile * kTile;
       for (int i = tid; i < kTile * kTile; i += blockDim.x) {
         double s = 0.0;
@@ -491,9 +597,8 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
       cta_signal(F.upd_done + Q.tile_sn[tile]);
     } else if (kind == 3) {  // CHUNK
       const int J = Q.chunk_sn[arg];
-      const int need = F.sn_nupd[J];
-      if (need > 0) cta_wait(F.upd_done + J, need);
-      factor_chunk<D>(P, Q, L, Ldiag, Dinv, arg, arg == Q.sn_chunk_ptr[J], smem, status, y, z, contrib, F.chunk_done);
+      factor_chunk<D>(P, Q, L, Ldiag, Dinv, arg, arg == Q.sn_chunk_ptr[J], smem, status, y, z, contrib, F.chunk_done,
+                      F.upd_done + J, F.sn_nupd[J]);
     } else {  // SUBTREE
       for (int q = P.task_ptr[arg]; q < P.task_ptr[arg + 1]; ++q) {
         const int J = P.task_sn[q];
@@ -506,7 +611,7 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
         }
         const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
         for (int ch = c0; ch < c1; ++ch)
-          factor_chunk<D>(P, Q, L, Ldiag, Dinv, ch, ch == c0, smem, status, y, z, contrib, F.chunk_done);
+          factor_chunk<D>(P, Q, L, Ldiag, Dinv, ch, ch == c0, smem, status, y, z, contrib, F.chunk_done, nullptr, 0);
       }
     }
   }
@@ -796,7 +901,7 @@ void CholeskyGpu::solve(const double* /*d_b: consumed by factor()*/, double* d_x
 
 #ifdef CHOL_TIMING
 extern "C" void b200_debug_chol_timing(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g2o_b200::g_chol_timing, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g2o_b200::g_chol_timing, z, sizeof(z)); }
 }
 #endif

@@ -399,6 +399,7 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_PANEL_COLS")) opt.max_panel_cols_scalar = std::max(pd, std::min(72, atoi(e)));
   if (const char* e = getenv("G2O_B200_SUBTREE_FLOPS")) opt.subtree_min_flops = atof(e);
   if (const char* e = getenv("G2O_B200_RELAX")) opt.relax = atoi(e) != 0;
+  if (const char* e = getenv("G2O_B200_GROUP_ITEMS")) opt.group_items = std::max(1, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
   c->structured = true;
   c->backup_depth = 0;
