@@ -392,114 +392,202 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
   for (int r = 0; r < 3; ++r) db[3ll * l + r] = Di[r] * b0 + Di[r + 3] * b1 + Di[r + 6] * b2;
 }
 
-// S2: one warp per block (i1,i2) of Hschur:
-//   Hschur(i1,i2) = hpp_scale*(Hpp(i1,i2) + [i1==i2] lambda I) - sum_l (Hpl(i1,l) Dinv_l) Hpl(i2,l)^T
-//   bschur_i1     = hpp_scale*b_i1 - sum_l Hpl(i1,l) db_l        (diagonal targets only)
-// contributions of a target are stored in ascending landmark order (block_solver.hpp:397-439).
+// S2: Hschur(i1,i2) = hpp_scale*(Hpp(i1,i2) + [i1==i2] lambda I) - sum_l (Hpl(i1,l) Dinv_l) Hpl(i2,l)^T
+//     bschur_i1     = hpp_scale*b_i1 - sum_l Hpl(i1,l) db_l                      (block_solver.hpp:397-439)
 // hpp_scale is 1 on a single GPU; with landmark sharding only rank 0 adds the (already reduced) Hpp term.
-// WPT warps per target: 1 for ordinary blocks (4 targets per CTA), 4 (a whole CTA) for the hot ones - mostly the
-// diagonal blocks, which collect every observation of a camera.  Partial sums are combined in a fixed order.
-template <int WPT>
-__global__ void __launch_bounds__(128, 3)
-schur_reduce_kernel(int nlist, const int* __restrict__ tlist, const int* __restrict__ t_row,
-                    const int* __restrict__ t_col, const int* __restrict__ t_hpp, const int* __restrict__ sc_ptr,
-                    const int* __restrict__ sc_lm, const int* __restrict__ sc_a, const int* __restrict__ sc_b,
-                    const double* __restrict__ Hpp, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
-                    const double* __restrict__ db, const double* __restrict__ b_p, const double* __restrict__ lambda,
-                    double hpp_scale, double* __restrict__ Hschur, double* __restrict__ bschur) {
-  constexpr int STRIDE = 32 * WPT;
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / STRIDE;
-  const int g = threadIdx.x % STRIDE;
-  const int lane = threadIdx.x & 31;
-  const bool active = slot < nlist;
-  const int t = active ? tlist[slot] : 0;
-  const int i1 = t_row[t], i2 = t_col[t];
-  const bool diag = i1 == i2;
-  double acc[36], cacc[6];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
-  int c = sc_ptr[t] + g;
-  const int cend = active ? sc_ptr[t + 1] : 0;
-  int l = 0, sa = 0, sb = 0;
-  if (c < cend) { l = sc_lm[c]; sa = sc_a[c]; sb = sc_b[c]; }
-  while (c < cend) {
-    // indices of the next contribution are fetched while this one is being multiplied
-    const int cn = c + STRIDE;
-    int ln = 0, san = 0, sbn = 0;
-    if (cn < cend) { ln = sc_lm[cn]; san = sc_a[cn]; sbn = sc_b[cn]; }
-    // 16-byte vector loads: a 6x3 block is 9 double2, a padded Dinv row 5
-    const double2* Ba = reinterpret_cast<const double2*>(Hpl + 18ll * sa);
-    const double2* Bb = reinterpret_cast<const double2*>(Hpl + 18ll * sb);
-    const double2* Dp = reinterpret_cast<const double2*>(Dinv + kDinvStride * (long long)l);
-    double Di[10], A[18], T[18];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { const double2 v = __ldg(Dp + k); Di[2 * k] = v.x; Di[2 * k + 1] = v.y; }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { const double2 v = __ldg(Ba + k); A[2 * k] = v.x; A[2 * k + 1] = v.y; }
-    mm<6, 3, 3>(A, Di, T);  // BDinv
-    if (diag) {
-      const double d0 = db[3ll * l], d1 = db[3ll * l + 1], d2 = db[3ll * l + 2];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) cacc[r] += A[r] * d0 + A[r + 6] * d1 + A[r + 12] * d2;
-    }
-    // Hschur(i1,i2) -= T * Bb^T, one column of Bb (6 values = 3 double2) at a time to keep registers low
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      double bj[6];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { const double2 v = __ldg(Bb + 3 * j + k); bj[2 * k] = v.x; bj[2 * k + 1] = v.y; }
-#pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2)
-#pragma unroll
-        for (int r = 0; r < 6; ++r) acc[r + 6 * c2] = fma(T[r + 6 * j], bj[c2], acc[r + 6 * c2]);
-    }
-    c = cn; l = ln; sa = san; sb = sbn;
+//
+// Two kernels, no atomics, fixed summation order:
+//  schur_range_kernel   one CTA per RANGE of landmarks.  Hpl slots are numbered so that a range is one contiguous
+//                       piece of Hpl (read from HBM exactly once, coalesced, into shared memory together with the
+//                       landmarks' Dinv / db and the range's contribution indices); landmarks are ordered by their
+//                       camera lists, so a range feeds few distinct Hschur blocks.  The contributions of a range to
+//                       one block form a SEGMENT (<= kSrSegMax products); 4 lanes share a segment, gather their
+//                       operands from shared memory, and leave one 6x6 (+6) partial sum per segment.
+//  schur_finish_kernel  one thread per entry of a block: adds the block's partial sums in segment order and
+//                       subtracts them from the Hpp term.
+constexpr int kSrThreads = 128;   // 32 groups of 4 lanes; 2 CTAs per SM (shared memory), ~200 registers per thread
+constexpr int kSrLanes = 4;
+constexpr int kSrSegMax = 32;     // products per segment
+constexpr int kSrPartial = 42;    // 36 block entries + 6 right-hand-side entries (diagonal blocks)
+
+struct SchurRanges {
+  const int* slot0;    // nr+1: first Hpl slot of a range
+  const int* lm_ptr;   // nr+1: into lm_ids
+  const int* lm_ids;   // landmark (Dinv / db index) of every landmark of the range
+  const int* seg_ptr;  // nr+1: segments of the range
+  const int* seg_t;    // nseg: destination block
+  const int *seg_cb, *seg_ce;  // nseg: contributions of the segment [cb, ce); a range starts at a multiple of 8
+  const unsigned short *sc_a, *sc_b, *sc_l;  // per contribution: Hpl slots / landmark, relative to the range
+  const unsigned char* t_diag;                // per block: 1 = diagonal
+  int cap_slots, cap_lms, cap_contrib;        // shared-memory capacities (a range exceeding one reads that piece from global)
+};
+
+__global__ void __launch_bounds__(kSrThreads, 2)
+schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+                   const double* __restrict__ db, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double sr_sm[];
+  double* sH = sr_sm;
+  double* sD = sH + (size_t)R.cap_slots * 18;
+  double* sdb = sD + (size_t)R.cap_lms * kDinvStride;
+  unsigned short* sA = reinterpret_cast<unsigned short*>(sdb + ((R.cap_lms * 3 + 1) & ~1));
+  unsigned short* sB = sA + R.cap_contrib;
+  unsigned short* sL = sB + R.cap_contrib;
+  __shared__ __align__(8) unsigned long long sr_bar;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int s0 = R.slot0[r], ns = R.slot0[r + 1] - s0;
+  const int l0 = R.lm_ptr[r], nlm = R.lm_ptr[r + 1] - l0;
+  const int g0 = R.seg_ptr[r], g1 = R.seg_ptr[r + 1];
+  const int c0 = R.seg_cb[g0], nc = R.seg_ce[g1 - 1] - c0;  // every range has at least one segment; c0 % 8 == 0
+  const bool stH = ns <= R.cap_slots, stL = nlm <= R.cap_lms, stC = nc <= R.cap_contrib;
+  // staging: the range's piece of Hpl and its contribution indices are contiguous in HBM -> bulk (TMA) copies
+  // tracked by one mbarrier; Dinv / db of the range's landmarks are gathered with 16-/8-byte cp.async
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&sr_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned hbytes = stH ? (unsigned)ns * 144u : 0u;
+    const unsigned cbytes = stC ? (((unsigned)nc * 2u + 15u) & ~15u) : 0u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(hbytes + 3u * cbytes) : "memory");
+    if (hbytes)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(sH)),
+                   "l"(Hpl + 18ll * s0), "r"(hbytes), "r"(bar)
+                   : "memory");
+    if (cbytes) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(sA)),
+                   "l"(R.sc_a + c0), "r"(cbytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(sB)),
+                   "l"(R.sc_b + c0), "r"(cbytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(sL)),
+                   "l"(R.sc_l + c0), "r"(cbytes), "r"(bar)
+                   : "memory");
+    }
+  }
+  if (stL) {
+    for (int i = tid; i < nlm * 5; i += kSrThreads) {
+      const int l = i / 5, k = i - l * 5;
+      const double* src = Dinv + kDinvStride * (long long)R.lm_ids[l0 + l] + 2 * k;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sD + 2 * i)), "l"(src) : "memory");
+    }
+    for (int i = tid; i < nlm * 3; i += kSrThreads) {
+      const int l = i / 3, k = i - l * 3;
+      const double* src = db + 3ll * R.lm_ids[l0 + l] + k;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdb + i)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+  __syncthreads();
+  const double* hb = stH ? sH : Hpl + 18ll * s0;
+  const unsigned short* ia = stC ? sA : R.sc_a + c0;
+  const unsigned short* ib = stC ? sB : R.sc_b + c0;
+  const unsigned short* il = stC ? sL : R.sc_l + c0;
+  const int sub = tid & (kSrLanes - 1);
+  const unsigned gmask = 0xFu << ((tid & 31) & ~3);
+  for (int sgm = g0 + tid / kSrLanes; sgm < g1; sgm += kSrThreads / kSrLanes) {
+    const int t = R.seg_t[sgm];
+    const bool diag = R.t_diag[t] != 0;
+    const int cb = R.seg_cb[sgm] - c0, ce = R.seg_ce[sgm] - c0;
+    double acc[36], cacc[6];
 #pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) cacc[k] = warp_sum(cacc[k]);
-  if (WPT > 1) {  // combine the warps of the target in warp order
-    __shared__ double part[WPT][42];
-    const int w = threadIdx.x >> 5;
+    for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
+    for (int c = cb + sub; c < ce; c += kSrLanes) {
+      const int a = ia[c], b = ib[c], l = il[c];
+      const double2* Ba = reinterpret_cast<const double2*>(hb + 18 * a);
+      const double2* Bb = reinterpret_cast<const double2*>(hb + 18 * b);
+      const double* dl = stL ? sD + kDinvStride * l : Dinv + kDinvStride * (long long)R.lm_ids[l0 + l];
+      const double2* Dp = reinterpret_cast<const double2*>(dl);
+      double Di[10], A[18], T[18];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) if (lane == (k & 31)) part[w][k] = acc[k];
+      for (int k = 0; k < 5; ++k) { const double2 v = Dp[k]; Di[2 * k] = v.x; Di[2 * k + 1] = v.y; }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) if (lane == k) part[w][36 + k] = cacc[k];
-    __syncthreads();
-    if (w != 0) return;
+      for (int k = 0; k < 9; ++k) { const double2 v = Ba[k]; A[2 * k] = v.x; A[2 * k + 1] = v.y; }
+      mm<6, 3, 3>(A, Di, T);  // Hpl(i1,l) Dinv_l
+      if (diag) {
+        const double* dv = stL ? sdb + 3 * l : db + 3ll * R.lm_ids[l0 + l];
+        const double d0 = dv[0], d1 = dv[1], d2 = dv[2];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) cacc[q] += A[q] * d0 + A[q + 6] * d1 + A[q + 12] * d2;
+      }
+      // += T * Hpl(i2,l)^T, one column of Hpl(i2,l) (6 values = 3 double2) at a time to keep registers low
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double bj[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double2 v = Bb[3 * j + k]; bj[2 * k] = v.x; bj[2 * k + 1] = v.y; }
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc[q + 6 * c2] = fma(T[q + 6 * j], bj[c2], acc[q + 6 * c2]);
+      }
+    }
+    // the 4 lanes of the group add up in a fixed tree; afterwards lane `sub` stores the entries k = sub mod 4
+    double* out = partial + (long long)sgm * kSrPartial;
 #pragma unroll
     for (int k = 0; k < 36; ++k) {
-      double sum = 0.0;
-#pragma unroll
-      for (int q = 0; q < WPT; ++q) sum += part[q][k];
-      acc[k] = sum;
+      double v = acc[k];
+      v += __shfl_xor_sync(gmask, v, 1);
+      v += __shfl_xor_sync(gmask, v, 2);
+      if ((k & 3) == sub) out[k] = v;
     }
+    if (diag) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      double sum = 0.0;
-#pragma unroll
-      for (int q = 0; q < WPT; ++q) sum += part[q][36 + k];
-      cacc[k] = sum;
-    }
-  }
-  if (!active) return;
-  const int hb = t_hpp[t];
-  const double lam = diag ? *lambda : 0.0;
-#pragma unroll
-  for (int k = 0; k < 36; ++k) {
-    if (lane == (k & 31)) {
-      double base = 0.0;
-      if (hb >= 0 && hpp_scale != 0.0) base = hpp_scale * (Hpp[36ll * hb + k] + ((k % 7 == 0) ? lam : 0.0));
-      Hschur[36ll * t + k] = base - acc[k];
+      for (int k = 0; k < 6; ++k) {
+        double v = cacc[k];
+        v += __shfl_xor_sync(gmask, v, 1);
+        v += __shfl_xor_sync(gmask, v, 2);
+        if ((k & 3) == sub) out[36 + k] = v;
+      }
     }
   }
-  if (diag) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (lane == k) bschur[6ll * i1 + k] = hpp_scale * b_p[6ll * i1 + k] - cacc[k];
+}
+
+// 64 threads per block of Hschur (42 active), 4 blocks per CTA
+__global__ void __launch_bounds__(256)
+schur_finish_kernel(int nT, const int* __restrict__ t_row, const int* __restrict__ t_col, const int* __restrict__ t_hpp,
+                    const int* __restrict__ tseg_ptr, const int* __restrict__ tseg_idx,
+                    const double* __restrict__ partial, const double* __restrict__ Hpp, const double* __restrict__ b_p,
+                    const double* __restrict__ lambda, double hpp_scale, double* __restrict__ Hschur,
+                    double* __restrict__ bschur) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int e = threadIdx.x & 63;
+  if (t >= nT || e >= kSrPartial) return;
+  const int i1 = t_row[t];
+  const bool diag = i1 == t_col[t];
+  if (e >= 36 && !diag) return;
+  double s0 = 0.0;
+  const int q1 = tseg_ptr[t + 1];
+  int q = tseg_ptr[t];
+  for (; q + 3 < q1; q += 4) {  // 4 independent loads in flight, added in segment order
+    const double v0 = partial[(long long)tseg_idx[q] * kSrPartial + e];
+    const double v1 = partial[(long long)tseg_idx[q + 1] * kSrPartial + e];
+    const double v2 = partial[(long long)tseg_idx[q + 2] * kSrPartial + e];
+    const double v3 = partial[(long long)tseg_idx[q + 3] * kSrPartial + e];
+    s0 = (((s0 + v0) + v1) + v2) + v3;
+  }
+  for (; q < q1; ++q) s0 += partial[(long long)tseg_idx[q] * kSrPartial + e];
+  if (e < 36) {
+    const int hb = t_hpp[t];
+    double base = 0.0;
+    if (hb >= 0 && hpp_scale != 0.0) base = hpp_scale * (Hpp[36ll * hb + e] + ((diag && e % 7 == 0) ? *lambda : 0.0));
+    Hschur[36ll * t + e] = base - s0;
+  } else {
+    bschur[6ll * i1 + (e - 36)] = hpp_scale * b_p[6ll * i1 + (e - 36)] - s0;
   }
 }
 

@@ -85,6 +85,11 @@ void drop_graphs(b200_ctx* c) {
   if (c->graph_trial) { cudaGraphExecDestroy(c->graph_trial); c->graph_trial = nullptr; }
 }
 
+static size_t schur_range_smem(const b200_ctx* c) {
+  const size_t doubles = (size_t)c->sr_cap_slots * 18 + (size_t)c->sr_cap_lms * k::kDinvStride + (size_t)((c->sr_cap_lms * 3 + 1) & ~1);
+  return doubles * sizeof(double) + (size_t)c->sr_cap_contrib * 3 * sizeof(unsigned short);
+}
+
 int build_structure_impl(b200_ctx* c) {
   double t0 = wall();
   drop_graphs(c);
@@ -343,49 +348,107 @@ int build_structure_impl(b200_ctx* c) {
       if (t_row[t] == t_col[t]) t_hpp[t] = t_row[t];
     }
     for (int i = 0; i < np; ++i) c->hs_colptr[i + 1] += c->hs_colptr[i];
-    // contributions per target, ascending landmark
-    std::vector<int> sc_ptr(nT + 1, 0);
     auto find_t = [&](int row, int col) {
       long long key = ((long long)col << 32) | row;
       return (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
     };
-    for (int pass = 0; pass < 2; ++pass) {
-      std::vector<int> fillp;
-      std::vector<int> sc_lm, sc_a, sc_b;
-      if (pass == 1) {
-        for (int t = 0; t < nT; ++t) sc_ptr[t + 1] += sc_ptr[t];
-        fillp.assign(sc_ptr.begin(), sc_ptr.end() - 1);
-        sc_lm.resize(sc_ptr[nT]); sc_a.resize(sc_ptr[nT]); sc_b.resize(sc_ptr[nT]);
-      }
+    // ---- Schur plan (kernels.cuh: schur_range_kernel / schur_finish_kernel)
+    // landmark order: lexicographic by camera list, so that neighbouring landmarks feed the same Hschur blocks
+    std::vector<int> lm_s0(nl + 1, 0);  // distinct Hpl slots per landmark (current numbering: landmark-major)
+    {
+      int prev = -1;
       for (int l = 0; l < nl; ++l) {
-        int prev_a = -1;
-        for (int a = lm_eptr[l]; a < lm_eptr[l + 1]; ++a) {
-          if (e_hpl[a] < 0 || e_hpl[a] == prev_a) continue;
-          prev_a = e_hpl[a];
-          int prev_b = -1;
-          for (int b2 = a; b2 < lm_eptr[l + 1]; ++b2) {
-            if (e_hpl[b2] < 0 || e_hpl[b2] == prev_b) continue;
-            prev_b = e_hpl[b2];
-            int t = find_t(e_pose[a], e_pose[b2]);
-            if (pass == 0) sc_ptr[t + 1]++;
-            else { int p = fillp[t]++; sc_lm[p] = l; sc_a[p] = e_hpl[a]; sc_b[p] = e_hpl[b2]; }
-          }
-        }
+        for (int a = lm_eptr[l]; a < lm_eptr[l + 1]; ++a)
+          if (e_hpl[a] >= 0 && e_hpl[a] != prev) { prev = e_hpl[a]; lm_s0[l + 1]++; }
       }
-      if (pass == 1) { c->d_sc_lm.upload(sc_lm, s); c->d_sc_a.upload(sc_a, s); c->d_sc_b.upload(sc_b, s); if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s)); }
+      for (int l = 0; l < nl; ++l) lm_s0[l + 1] += lm_s0[l];
+    }
+    std::vector<int> pi;
+    for (int l = 0; l < nl; ++l) if (lm_s0[l + 1] > lm_s0[l]) pi.push_back(l);
+    std::stable_sort(pi.begin(), pi.end(), [&](int x, int y) {
+      const int nx = lm_s0[x + 1] - lm_s0[x], ny = lm_s0[y + 1] - lm_s0[y];
+      const int* rx = c->hpl_row.data() + lm_s0[x];
+      const int* ry = c->hpl_row.data() + lm_s0[y];
+      for (int q = 0; q < nx && q < ny; ++q) if (rx[q] != ry[q]) return rx[q] < ry[q];
+      return nx < ny;
+    });
+    {
+      // renumber the Hpl slots in that order (a landmark's slots stay contiguous, ascending camera)
+      std::vector<int> renum(nslot), row2(nslot), col2(nslot);
+      int q2 = 0;
+      for (int l : pi)
+        for (int q = lm_s0[l]; q < lm_s0[l + 1]; ++q, ++q2) { renum[q] = q2; row2[q2] = c->hpl_row[q]; col2[q2] = c->hpl_col[q]; }
+      c->hpl_row.swap(row2); c->hpl_col.swap(col2);
+      for (int q = 0; q < E; ++q) if (e_hpl[q] >= 0) e_hpl[q] = renum[e_hpl[q]];
+      c->hpl_export = renum;  // SparseBlockMatrix (landmark-major) position -> slot
+    }
+    {
+      const int cap_slots = 448, cap_lms = 192, cap_contrib = 4096;  // 2 CTAs per SM (kernels.cuh)
+      std::vector<int> r_slot0{0}, r_lm_ptr{0}, r_lm_ids, r_seg_ptr{0}, seg_t, seg_cb, seg_ce;
+      std::vector<unsigned short> sc_a, sc_b, sc_l;
+      struct Contrib { int t; unsigned short l, a, b; };
+      std::vector<Contrib> rc;
+      int slot = 0;  // next slot (new numbering)
+      auto close_range = [&]() {
+        if (r_lm_ids.size() == (size_t)r_lm_ptr.back()) return;
+        std::stable_sort(rc.begin(), rc.end(), [](const Contrib& x, const Contrib& y) { return x.t < y.t; });
+        for (size_t q = 0; q < rc.size();) {
+          size_t e2 = q;
+          while (e2 < rc.size() && rc[e2].t == rc[q].t && e2 - q < (size_t)k::kSrSegMax) ++e2;
+          seg_t.push_back(rc[q].t);
+          seg_cb.push_back((int)sc_a.size());
+          for (size_t z = q; z < e2; ++z) { sc_a.push_back(rc[z].a); sc_b.push_back(rc[z].b); sc_l.push_back(rc[z].l); }
+          seg_ce.push_back((int)sc_a.size());
+          q = e2;
+        }
+        while (sc_a.size() % 8) { sc_a.push_back(0); sc_b.push_back(0); sc_l.push_back(0); }  // 16-byte aligned ranges (bulk copies)
+        rc.clear();
+        r_slot0.push_back(slot); r_lm_ptr.push_back((int)r_lm_ids.size()); r_seg_ptr.push_back((int)seg_t.size());
+      };
+      for (int l : pi) {
+        const int k2 = lm_s0[l + 1] - lm_s0[l];
+        const int pairs = k2 * (k2 + 1) / 2;
+        if (k2 > 65535) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 65535 cameras");
+        const int cur_slots = slot - r_slot0.back(), cur_lms = (int)r_lm_ids.size() - r_lm_ptr.back();
+        if (cur_lms > 0 && (cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || (int)rc.size() + pairs > cap_contrib)) close_range();
+        const int base = slot - r_slot0.back(), ll = (int)r_lm_ids.size() - r_lm_ptr.back();
+        for (int a = 0; a < k2; ++a)
+          for (int b2 = a; b2 < k2; ++b2)
+            rc.push_back({find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]), (unsigned short)ll, (unsigned short)(base + a), (unsigned short)(base + b2)});
+        r_lm_ids.push_back(l);
+        slot += k2;
+      }
+      close_range();
+      for (int q = 0; q < 8; ++q) { sc_a.push_back(0); sc_b.push_back(0); sc_l.push_back(0); }  // bulk copies round sizes up
+      const int nr = (int)r_slot0.size() - 1, nseg = (int)seg_t.size();
+      // per block: its segments in ascending order (= fixed summation order of the finish kernel)
+      std::vector<int> tseg_ptr(nT + 1, 0), tseg_idx(nseg);
+      for (int sg = 0; sg < nseg; ++sg) tseg_ptr[seg_t[sg] + 1]++;
+      for (int t = 0; t < nT; ++t) tseg_ptr[t + 1] += tseg_ptr[t];
+      {
+        std::vector<int> f(tseg_ptr.begin(), tseg_ptr.end() - 1);
+        for (int sg = 0; sg < nseg; ++sg) tseg_idx[f[seg_t[sg]]++] = sg;
+      }
+      std::vector<unsigned char> t_diag(nT);
+      for (int t = 0; t < nT; ++t) t_diag[t] = t_row[t] == t_col[t];
+      c->sr_n = nr; c->sr_nseg = nseg; c->sr_ncontrib = (long long)sc_a.size();
+      c->sr_cap_slots = cap_slots; c->sr_cap_lms = cap_lms; c->sr_cap_contrib = cap_contrib;
+      c->d_sr_slot0.upload(r_slot0, s); c->d_sr_lm_ptr.upload(r_lm_ptr, s); c->d_sr_lm_ids.upload(r_lm_ids, s);
+      c->d_sr_seg_ptr.upload(r_seg_ptr, s); c->d_sr_seg_t.upload(seg_t, s); c->d_sr_seg_cb.upload(seg_cb, s); c->d_sr_seg_ce.upload(seg_ce, s);
+      c->d_sr_a.upload(sc_a, s); c->d_sr_b.upload(sc_b, s); c->d_sr_l.upload(sc_l, s);
+      c->d_t_diag.upload(t_diag, s); c->d_tseg_ptr.upload(tseg_ptr, s); c->d_tseg_idx.upload(tseg_idx, s);
+      c->d_sr_partial.alloc((size_t)std::max(nseg, 1) * k::kSrPartial);
+      if (!c->host_only) {
+        B200_CUDA(cudaStreamSynchronize(s));
+        B200_CUDA(cudaFuncSetAttribute(k::schur_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_range_smem(c)));
+      }
     }
     c->d_ev0.upload(e_pt, s); c->d_ev1.upload(e_cam, s); c->d_e_pose.upload(e_pose, s); c->d_e_hpl.upload(e_hpl, s);
     c->d_e_flag.upload(e_first, s);
     c->d_meas.upload(meas, s); c->d_info.upload(info, s);
     c->d_lm_eptr.upload(lm_eptr, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
     c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
-    c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s); c->d_sc_ptr.upload(sc_ptr, s);
-    {  // hot targets (mostly the diagonal blocks) get a whole CTA, the rest one warp each
-      std::vector<int> heavy, light;
-      for (int t = 0; t < nT; ++t) (sc_ptr[t + 1] - sc_ptr[t] > 192 ? heavy : light).push_back(t);
-      c->n_t_heavy = (int)heavy.size(); c->n_t_light = (int)light.size();
-      c->d_t_heavy.upload(heavy, s); c->d_t_light.upload(light, s);
-    }
+    c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s);
     c->d_Hpp.alloc((size_t)np * 36 + (size_t)c->sizeP);  // [Hpp | b_p staging] contiguous for one all-reduce
     c->d_Hll.alloc((size_t)std::max(nl, 1) * 9); c->d_Hpl.alloc((size_t)std::max(nslot, 1) * 18);
     c->d_Dinv.alloc((size_t)std::max(nl, 1) * k::kDinvStride); c->d_Dinv.zero(s); c->d_db.alloc((size_t)std::max(nl, 1) * 3);
@@ -490,6 +553,7 @@ void enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses 
   allreduce_dev(c, c->d_scalars.p + 2, 1, /*max*/ 1);  // sharded: landmark diagonals live on different ranks
 }
 
+
 // Solver::solve with the lambda currently stored at d_scalars[3]
 int enqueue_solve(b200_ctx* c) {
   cudaStream_t s = c->stream;
@@ -506,14 +570,18 @@ int enqueue_solve(b200_ctx* c) {
       c->lc.n++;
     }
     const double hpp_scale = (c->world > 1 && c->rank != 0) ? 0.0 : 1.0;
-    { PhaseTimer pt(c, PH_SCHUR);
-    if (c->n_t_heavy > 0) {
-      k::schur_reduce_kernel<4><<<c->n_t_heavy, 128, 0, s>>>(c->n_t_heavy, c->d_t_heavy.p, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
+    {
+      PhaseTimer pt(c, PH_SCHUR);
+      if (c->sr_n > 0) {
+        k::SchurRanges R{c->d_sr_slot0.p, c->d_sr_lm_ptr.p, c->d_sr_lm_ids.p, c->d_sr_seg_ptr.p, c->d_sr_seg_t.p, c->d_sr_seg_cb.p, c->d_sr_seg_ce.p,
+                         c->d_sr_a.p, c->d_sr_b.p, c->d_sr_l.p, c->d_t_diag.p, c->sr_cap_slots, c->sr_cap_lms, c->sr_cap_contrib};
+        k::schur_range_kernel<<<c->sr_n, k::kSrThreads, schur_range_smem(c), s>>>(R, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_sr_partial.p);
+        c->lc.n++;
+      }
+      k::schur_finish_kernel<<<ceil_div(c->n_hs, 4), 256, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_tseg_ptr.p, c->d_tseg_idx.p,
+                                                               c->d_sr_partial.p, c->d_Hpp.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
       c->lc.n++;
     }
-    if (c->n_t_light > 0)
-      k::schur_reduce_kernel<1><<<ceil_div((long long)c->n_t_light * 32, 128), 128, 0, s>>>(c->n_t_light, c->d_t_light.p, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_sc_ptr.p, c->d_sc_lm.p, c->d_sc_a.p, c->d_sc_b.p, c->d_Hpp.p, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c)); }
-    c->lc.n++;
     B200_CUDA(cudaGetLastError());
     int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);
     if (rc) return rc;
@@ -1082,10 +1150,15 @@ int b200_get_blocks(b200_ctx* c, int which, int32_t* rows, int32_t* cols, double
       if (values) { int rc2 = copy_out(c, c->d_Hll.p, values, (size_t)c->nl * 9); if (rc2) return rc2; }
       return c->nl;
     }
-    if (which == 2) {  // Hpl slots are stored landmark-major, ascending camera: already SparseBlockMatrix order
+    if (which == 2) {  // exported in SparseBlockMatrix order (landmark-major, ascending camera); stored in Schur-range order
       if (!rows) return c->n_hpl;
-      for (int q = 0; q < c->n_hpl; ++q) { rows[q] = c->hpl_row[q]; cols[q] = c->hpl_col[q]; }
-      if (values) { int rc2 = copy_out(c, c->d_Hpl.p, values, (size_t)c->n_hpl * 18); if (rc2) return rc2; }
+      for (int q = 0; q < c->n_hpl; ++q) { const int sl = c->hpl_export[q]; rows[q] = c->hpl_row[sl]; cols[q] = c->hpl_col[sl]; }
+      if (values) {
+        std::vector<double> tmp((size_t)c->n_hpl * 18);
+        int rc2 = copy_out(c, c->d_Hpl.p, tmp.data(), tmp.size());
+        if (rc2) return rc2;
+        for (int q = 0; q < c->n_hpl; ++q) std::copy_n(tmp.data() + 18 * (size_t)c->hpl_export[q], 18, values + 18 * (size_t)q);
+      }
       return c->n_hpl;
     }
     if (which == 3) {

@@ -47,6 +47,7 @@ struct b200_ctx {
   std::vector<int> hs_colptr, hs_rowidx;       // Hschur pattern
   std::vector<int> e_order;                    // device edge order -> input edge index (BA)
   std::vector<int> hpl_row, hpl_col;           // per Hpl slot
+  std::vector<int> hpl_export;                 // SparseBlockMatrix (landmark-major) position -> slot
   int n_hpl = 0, n_hs = 0, n_hpp = 0;
 
   // ---------------- device state
@@ -58,8 +59,14 @@ struct b200_ctx {
   g2o_b200::DevBuf<int> d_hsrc_ptr, d_hsrc_id, d_bsrc_ptr, d_bsrc_id;
   g2o_b200::DevBuf<int> d_lm_eptr, d_cam_eptr, d_cam_eidx, d_hpp_diag_block;
   g2o_b200::DevBuf<double> d_Hpp, d_Hll, d_Hpl, d_Hschur, d_Dinv, d_db, d_b, d_x, d_bschur, d_diag;
-  g2o_b200::DevBuf<int> d_t_row, d_t_col, d_t_hpp, d_sc_ptr, d_sc_lm, d_sc_a, d_sc_b, d_t_heavy, d_t_light;
-  int n_t_heavy = 0, n_t_light = 0;
+  g2o_b200::DevBuf<int> d_t_row, d_t_col, d_t_hpp;
+  // Schur plan: landmark ranges, their segments (contributions to one Hschur block), per-block segment lists
+  g2o_b200::DevBuf<int> d_sr_slot0, d_sr_lm_ptr, d_sr_lm_ids, d_sr_seg_ptr, d_sr_seg_t, d_sr_seg_cb, d_sr_seg_ce, d_tseg_ptr, d_tseg_idx;
+  g2o_b200::DevBuf<unsigned short> d_sr_a, d_sr_b, d_sr_l;
+  g2o_b200::DevBuf<unsigned char> d_t_diag;
+  g2o_b200::DevBuf<double> d_sr_partial;
+  int sr_n = 0, sr_nseg = 0, sr_cap_slots = 0, sr_cap_lms = 0, sr_cap_contrib = 0;
+  long long sr_ncontrib = 0;
   g2o_b200::DevBuf<double> d_stage_est;            // dense staging for host<->device estimate copies
   g2o_b200::DevBuf<double> d_partials, d_scalars;  // scalars: [0] chi2 [1] scale [2] maxdiag [3] lambda
   double* h_scalars = nullptr;                     // pinned mirror of d_scalars (+ status as double)
