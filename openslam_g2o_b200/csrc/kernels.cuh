@@ -249,21 +249,23 @@ __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* _
 
 // one thread per landmark: Hll, b_l and one Hpl block per observation (edges of a landmark are contiguous)
 __global__ void __launch_bounds__(128)
-ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ lm_vertex,
+ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ lm_order,
+                           const int* __restrict__ lm_vertex,
                            const int* __restrict__ e_cam, const int* __restrict__ e_hpl,
                            const unsigned char* __restrict__ e_first, const double* __restrict__ pt_est,
                            const double* __restrict__ cam_est, const double* __restrict__ cam_der,
                            const double* __restrict__ meas, const double* __restrict__ info, int E,
                            double* __restrict__ Hll, double* __restrict__ Hpl, double* __restrict__ b_l) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= nl) return;
+  const int rk = blockIdx.x * blockDim.x + threadIdx.x;  // landmark rank: edges and Hpl slots are in this order
+  if (rk >= nl) return;
+  const int l = lm_order[rk];
   const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * lm_vertex[l]);
   const double X[3] = {X4.x, X4.y, X4.z};
   double H[9], bl[3];
 #pragma unroll
   for (int i = 0; i < 9; ++i) H[i] = 0.0;
   bl[0] = bl[1] = bl[2] = 0.0;
-  for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+  for (int e = lm_eptr[rk]; e < lm_eptr[rk + 1]; ++e) {
     const int c = e_cam[e];
     double der[16];
     load_der(cam_der, c, der);
@@ -289,14 +291,17 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
     for (int r = 0; r < 3; ++r) bl[r] += Jp[2 * r] * or0 + Jp[2 * r + 1] * or1;
     const int slot = e_hpl[e];
     if (slot >= 0) {  // Hpl(cam, l) (6x3) += Jc^T W Jp   (the transposed write of base_binary_edge.hpp:81-82)
-      double* dst = Hpl + 18ll * slot;
+      double2* dst = reinterpret_cast<double2*>(Hpl + 18ll * slot);  // 144-byte blocks: 16-byte vector stores
       const bool first = e_first[e] != 0;
 #pragma unroll
       for (int c2 = 0; c2 < 3; ++c2)
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double v = Jc[2 * r] * JpW[c2] + Jc[2 * r + 1] * JpW[c2 + 3];
-          dst[r + 6 * c2] = first ? v : dst[r + 6 * c2] + v;
+        for (int r = 0; r < 6; r += 2) {
+          double2 v;
+          v.x = Jc[2 * r] * JpW[c2] + Jc[2 * r + 1] * JpW[c2 + 3];
+          v.y = Jc[2 * r + 2] * JpW[c2] + Jc[2 * r + 3] * JpW[c2 + 3];
+          if (!first) { const double2 o = dst[(r + 6 * c2) >> 1]; v.x += o.x; v.y += o.y; }
+          dst[(r + 6 * c2) >> 1] = v;
         }
     }
   }
@@ -373,10 +378,15 @@ ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict
 // ------------------------------------------------------------------ Schur complement
 constexpr int kDinvStride = 10;  // 9 doubles padded to 80 B: rows stay 16-byte aligned for double2 loads
 
-// S1: per landmark Dinv = (Hll + lambda I)^-1, db = Dinv b_l           (block_solver.hpp:381-395)
+// S1: per landmark Dinv = (Hll + lambda I)^-1 (back-substitution) and, for the Schur reduction, the triangular factor
+// W with Dinv = W W^T (W = R^-1, R = upper Cholesky factor of Hll + lambda I) and u = W^T b_l:
+//   Hpl(i1,l) Dinv Hpl(i2,l)^T = (Hpl(i1,l) W)(Hpl(i2,l) W)^T,   Hpl(i1,l) Dinv b_l = (Hpl(i1,l) W) u
+// so the reduction multiplies ONE transformed 6x3 block per observation instead of two blocks and a 3x3 inverse
+// (block_solver.hpp:381-395 computes Dinv and Hpl*Dinv per landmark).
+// Wu per landmark: w00 w01 w02 w11 w12 w22 u0 u1 u2 (+1 pad: 80 B, 16-byte aligned rows)
 __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__ Hll, const double* __restrict__ b_l,
                                               const double* __restrict__ lambda, double* __restrict__ Dinv,
-                                              double* __restrict__ db) {
+                                              double* __restrict__ Wu) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= nl) return;
   const double lam = *lambda;
@@ -388,8 +398,23 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
   const double b0 = b_l[3ll * l], b1 = b_l[3ll * l + 1], b2 = b_l[3ll * l + 2];
 #pragma unroll
   for (int i = 0; i < 9; ++i) Dinv[kDinvStride * (long long)l + i] = Di[i];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) db[3ll * l + r] = Di[r] * b0 + Di[r + 3] * b1 + Di[r + 6] * b2;
+  // R^T R = D (column-major symmetric: D[r + 3c])
+  const double r00 = sqrt(D[0]);
+  const double w00 = 1.0 / r00;
+  const double r01 = D[3] * w00, r02 = D[6] * w00;
+  const double r11 = sqrt(D[4] - r01 * r01);
+  const double w11 = 1.0 / r11;
+  const double r12 = (D[7] - r01 * r02) * w11;
+  const double r22 = sqrt(D[8] - r02 * r02 - r12 * r12);
+  const double w22 = 1.0 / r22;
+  const double w01 = -r01 * w11 * w00;
+  const double w12 = -r12 * w22 * w11;
+  const double w02 = -(r01 * w12 + r02 * w22) * w00;
+  double* o = Wu + kDinvStride * (long long)l;
+  o[0] = w00; o[1] = w01; o[2] = w02; o[3] = w11; o[4] = w12; o[5] = w22;
+  o[6] = w00 * b0;
+  o[7] = w01 * b0 + w11 * b1;
+  o[8] = w02 * b0 + w12 * b1 + w22 * b2;
 }
 
 // S2: Hschur(i1,i2) = hpp_scale*(Hpp(i1,i2) + [i1==i2] lambda I) - sum_l (Hpl(i1,l) Dinv_l) Hpl(i2,l)^T
@@ -405,31 +430,33 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
 //                       operands from shared memory, and leave one 6x6 (+6) partial sum per segment.
 //  schur_finish_kernel  one thread per entry of a block: adds the block's partial sums in segment order and
 //                       subtracts them from the Hpp term.
-constexpr int kSrThreads = 128;   // 32 groups of 4 lanes; 2 CTAs per SM (shared memory), ~200 registers per thread
+constexpr int kSrThreads = 128;   // 32 groups of 4 lanes; 3 CTAs per SM (shared memory and registers)
 constexpr int kSrLanes = 4;
 constexpr int kSrSegMax = 32;     // products per segment
 constexpr int kSrPartial = 42;    // 36 block entries + 6 right-hand-side entries (diagonal blocks)
 
 struct SchurRanges {
   const int* slot0;    // nr+1: first Hpl slot of a range
-  const int* lm_ptr;   // nr+1: into lm_ids
-  const int* lm_ids;   // landmark (Dinv / db index) of every landmark of the range
+  const int* lm_ptr;   // nr+1: into lm_ids / lm_slot
+  const int* lm_ids;   // landmark (Wu index) of every landmark of the range
+  const int* lm_slot;  // first Hpl slot of that landmark, relative to the range (+ one end entry per range)
   const int* seg_ptr;  // nr+1: segments of the range
   const int* seg_t;    // nseg: destination block
   const int *seg_cb, *seg_ce;  // nseg: contributions of the segment [cb, ce); a range starts at a multiple of 8
   const unsigned short *sc_a, *sc_b, *sc_l;  // per contribution: Hpl slots / landmark, relative to the range
-  const unsigned char* t_diag;                // per block: 1 = diagonal
-  int cap_slots, cap_lms, cap_contrib;        // shared-memory capacities (a range exceeding one reads that piece from global)
+  const unsigned char* t_diag;        // per block: 1 = diagonal
+  int cap_slots, cap_lms, cap_contrib;  // shared-memory capacities; only the contribution indices may exceed theirs
+                                        // (one landmark seen by > 50 cameras): they are then read from global memory
 };
 
-__global__ void __launch_bounds__(kSrThreads, 2)
-schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
-                   const double* __restrict__ db, double* __restrict__ partial) {
+__global__ void __launch_bounds__(kSrThreads, 3)
+schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* __restrict__ Wu,
+                   double* __restrict__ partial) {
   extern __shared__ __align__(16) double sr_sm[];
-  double* sH = sr_sm;
-  double* sD = sH + (size_t)R.cap_slots * 18;
-  double* sdb = sD + (size_t)R.cap_lms * kDinvStride;
-  unsigned short* sA = reinterpret_cast<unsigned short*>(sdb + ((R.cap_lms * 3 + 1) & ~1));
+  double* sH = sr_sm;                                    // transformed blocks Hpl(i,l) W_l | u-products
+  double* sW = sH + (size_t)R.cap_slots * 18;            // Wu rows of the range's landmarks
+  int* sS = reinterpret_cast<int*>(sW + (size_t)R.cap_lms * kDinvStride);  // first slot per landmark (+ end)
+  unsigned short* sA = reinterpret_cast<unsigned short*>(sS + ((R.cap_lms + 1 + 3) & ~3));
   unsigned short* sB = sA + R.cap_contrib;
   unsigned short* sL = sB + R.cap_contrib;
   __shared__ __align__(8) unsigned long long sr_bar;
@@ -437,10 +464,15 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
   const int s0 = R.slot0[r], ns = R.slot0[r + 1] - s0;
   const int l0 = R.lm_ptr[r], nlm = R.lm_ptr[r + 1] - l0;
   const int g0 = R.seg_ptr[r], g1 = R.seg_ptr[r + 1];
+  // descriptor of this group's first segment: fetched while the staging copies are in flight
+  int sgm = g0 + tid / kSrLanes;
+  int seg_tt = 0, seg_b = 0, seg_e = 0;
+  if (sgm < g1) { seg_tt = R.seg_t[sgm]; seg_b = R.seg_cb[sgm]; seg_e = R.seg_ce[sgm]; }
   const int c0 = R.seg_cb[g0], nc = R.seg_ce[g1 - 1] - c0;  // every range has at least one segment; c0 % 8 == 0
-  const bool stH = ns <= R.cap_slots, stL = nlm <= R.cap_lms, stC = nc <= R.cap_contrib;
+  if (ns > R.cap_slots || nlm > R.cap_lms) __trap();  // the host never builds such a range (solver.cu: build_structure)
+  const bool stC = nc <= R.cap_contrib;
   // staging: the range's piece of Hpl and its contribution indices are contiguous in HBM -> bulk (TMA) copies
-  // tracked by one mbarrier; Dinv / db of the range's landmarks are gathered with 16-/8-byte cp.async
+  // tracked by one mbarrier; the Wu rows of the range's landmarks are gathered with 16-byte cp.async
   const unsigned bar = (unsigned)__cvta_generic_to_shared(&sr_bar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -448,14 +480,13 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
   }
   __syncthreads();
   if (tid == 0) {
-    const unsigned hbytes = stH ? (unsigned)ns * 144u : 0u;
+    const unsigned hbytes = (unsigned)ns * 144u;
     const unsigned cbytes = stC ? (((unsigned)nc * 2u + 15u) & ~15u) : 0u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(hbytes + 3u * cbytes) : "memory");
-    if (hbytes)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       (unsigned)__cvta_generic_to_shared(sH)),
-                   "l"(Hpl + 18ll * s0), "r"(hbytes), "r"(bar)
-                   : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(sH)),
+                 "l"(Hpl + 18ll * s0), "r"(hbytes), "r"(bar)
+                 : "memory");
     if (cbytes) {
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                        (unsigned)__cvta_generic_to_shared(sA)),
@@ -471,60 +502,65 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
                    : "memory");
     }
   }
-  if (stL) {
-    for (int i = tid; i < nlm * 5; i += kSrThreads) {
-      const int l = i / 5, k = i - l * 5;
-      const double* src = Dinv + kDinvStride * (long long)R.lm_ids[l0 + l] + 2 * k;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sD + 2 * i)), "l"(src) : "memory");
-    }
-    for (int i = tid; i < nlm * 3; i += kSrThreads) {
-      const int l = i / 3, k = i - l * 3;
-      const double* src = db + 3ll * R.lm_ids[l0 + l] + k;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdb + i)), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  for (int i = tid; i < nlm * 5; i += kSrThreads) {
+    const int l = i / 5, k = i - l * 5;
+    const double* src = Wu + kDinvStride * (long long)R.lm_ids[l0 + l] + 2 * k;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sW + 2 * i)), "l"(src) : "memory");
   }
+  for (int i = tid; i <= nlm; i += kSrThreads)  // nlm+1 entries: lm_slot carries one end entry per range
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sS + i)), "l"(R.lm_slot + (l0 + r) + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   {
     unsigned done = 0;
     while (!done)
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
   }
   __syncthreads();
-  const double* hb = stH ? sH : Hpl + 18ll * s0;
+  // transform in place: every block Hpl(i,l) becomes Hpl(i,l) W_l (one thread per landmark)
+  for (int l = tid; l < nlm; l += kSrThreads) {
+    const double* wl = sW + kDinvStride * l;
+    const double w00 = wl[0], w01 = wl[1], w02 = wl[2], w11 = wl[3], w12 = wl[4], w22 = wl[5];
+    for (int q = sS[l]; q < sS[l + 1]; ++q) {
+      double* A = sH + 18 * q;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double a0 = A[i], a1 = A[i + 6], a2 = A[i + 12];
+        A[i] = a0 * w00;
+        A[i + 6] = fma(a0, w01, a1 * w11);
+        A[i + 12] = fma(a0, w02, fma(a1, w12, a2 * w22));
+      }
+    }
+  }
+  __syncthreads();
   const unsigned short* ia = stC ? sA : R.sc_a + c0;
   const unsigned short* ib = stC ? sB : R.sc_b + c0;
   const unsigned short* il = stC ? sL : R.sc_l + c0;
   const int sub = tid & (kSrLanes - 1);
   const unsigned gmask = 0xFu << ((tid & 31) & ~3);
-  for (int sgm = g0 + tid / kSrLanes; sgm < g1; sgm += kSrThreads / kSrLanes) {
-    const int t = R.seg_t[sgm];
-    const bool diag = R.t_diag[t] != 0;
-    const int cb = R.seg_cb[sgm] - c0, ce = R.seg_ce[sgm] - c0;
+  for (; sgm < g1; sgm += kSrThreads / kSrLanes) {
+    if (sgm != g0 + tid / kSrLanes) { seg_tt = R.seg_t[sgm]; seg_b = R.seg_cb[sgm]; seg_e = R.seg_ce[sgm]; }
+    const bool diag = R.t_diag[seg_tt] != 0;
+    const int cb = seg_b - c0, ce = seg_e - c0;
     double acc[36], cacc[6];
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
     for (int c = cb + sub; c < ce; c += kSrLanes) {
-      const int a = ia[c], b = ib[c], l = il[c];
-      const double2* Ba = reinterpret_cast<const double2*>(hb + 18 * a);
-      const double2* Bb = reinterpret_cast<const double2*>(hb + 18 * b);
-      const double* dl = stL ? sD + kDinvStride * l : Dinv + kDinvStride * (long long)R.lm_ids[l0 + l];
-      const double2* Dp = reinterpret_cast<const double2*>(dl);
-      double Di[10], A[18], T[18];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) { const double2 v = Dp[k]; Di[2 * k] = v.x; Di[2 * k + 1] = v.y; }
+      const int a = ia[c], b = ib[c];
+      const double2* Ba = reinterpret_cast<const double2*>(sH + 18 * a);
+      const double2* Bb = reinterpret_cast<const double2*>(sH + 18 * b);
+      double A[18];
 #pragma unroll
       for (int k = 0; k < 9; ++k) { const double2 v = Ba[k]; A[2 * k] = v.x; A[2 * k + 1] = v.y; }
-      mm<6, 3, 3>(A, Di, T);  // Hpl(i1,l) Dinv_l
       if (diag) {
-        const double* dv = stL ? sdb + 3 * l : db + 3ll * R.lm_ids[l0 + l];
-        const double d0 = dv[0], d1 = dv[1], d2 = dv[2];
+        const double* u = sW + kDinvStride * il[c] + 6;
+        const double u0 = u[0], u1 = u[1], u2 = u[2];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) cacc[q] += A[q] * d0 + A[q + 6] * d1 + A[q + 12] * d2;
+        for (int q = 0; q < 6; ++q) cacc[q] += A[q] * u0 + A[q + 6] * u1 + A[q + 12] * u2;
       }
-      // += T * Hpl(i2,l)^T, one column of Hpl(i2,l) (6 values = 3 double2) at a time to keep registers low
+      // += (Hpl(i1,l) W)(Hpl(i2,l) W)^T, one column of the second block (6 values = 3 double2) at a time
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         double bj[6];
@@ -533,7 +569,7 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
 #pragma unroll
         for (int c2 = 0; c2 < 6; ++c2)
 #pragma unroll
-          for (int q = 0; q < 6; ++q) acc[q + 6 * c2] = fma(T[q + 6 * j], bj[c2], acc[q + 6 * c2]);
+          for (int q = 0; q < 6; ++q) acc[q + 6 * c2] = fma(A[q + 6 * j], bj[c2], acc[q + 6 * c2]);
       }
     }
     // the 4 lanes of the group add up in a fixed tree; afterwards lane `sub` stores the entries k = sub mod 4
@@ -592,26 +628,30 @@ schur_finish_kernel(int nT, const int* __restrict__ t_row, const int* __restrict
 }
 
 // landmark back-substitution: x_l = Dinv (b_l - sum_e Hpl(e)^T x_cam(e))     (block_solver.hpp:461-481)
-__global__ void ba_backsub_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ e_hpl,
+__global__ void ba_backsub_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ lm_order,
+                                  const int* __restrict__ e_hpl,
                                   const int* __restrict__ e_pose, const double* __restrict__ Hpl,
                                   const double* __restrict__ Dinv, const double* __restrict__ b_l,
                                   const double* __restrict__ x_p, double* __restrict__ x_l) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= nl) return;
+  const int rk = blockIdx.x * blockDim.x + threadIdx.x;  // landmark rank: edges and Hpl slots are in this order
+  if (rk >= nl) return;
+  const int l = lm_order[rk];
   double c0 = b_l[3ll * l], c1 = b_l[3ll * l + 1], c2 = b_l[3ll * l + 2];
   int prev = -1;
-  for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+  for (int e = lm_eptr[rk]; e < lm_eptr[rk + 1]; ++e) {
     const int slot = e_hpl[e];
     if (slot < 0 || slot == prev) continue;  // duplicate observations share one block
     prev = slot;
-    const double* B = Hpl + 18ll * slot;
-    const double* xp = x_p + 6ll * e_pose[e];
+    const double2* B2 = reinterpret_cast<const double2*>(Hpl + 18ll * slot);  // 16-byte vector loads
+    const double2* xp2 = reinterpret_cast<const double2*>(x_p + 6ll * e_pose[e]);
+    double B[18], xv[6];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double2 v = __ldg(B2 + k); B[2 * k] = v.x; B[2 * k + 1] = v.y; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double2 v = xp2[k]; xv[2 * k] = -v.x; xv[2 * k + 1] = -v.y; }
     double t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const double xv = -xp[r];
-      t0 += B[r] * xv; t1 += B[r + 6] * xv; t2 += B[r + 12] * xv;
-    }
+    for (int r = 0; r < 6; ++r) { t0 += B[r] * xv[r]; t1 += B[r + 6] * xv[r]; t2 += B[r + 12] * xv[r]; }
     c0 += t0; c1 += t1; c2 += t2;
   }
   const double* Di = Dinv + kDinvStride * (long long)l;

@@ -86,8 +86,8 @@ void drop_graphs(b200_ctx* c) {
 }
 
 static size_t schur_range_smem(const b200_ctx* c) {
-  const size_t doubles = (size_t)c->sr_cap_slots * 18 + (size_t)c->sr_cap_lms * k::kDinvStride + (size_t)((c->sr_cap_lms * 3 + 1) & ~1);
-  return doubles * sizeof(double) + (size_t)c->sr_cap_contrib * 3 * sizeof(unsigned short);
+  return ((size_t)c->sr_cap_slots * 18 + (size_t)c->sr_cap_lms * k::kDinvStride) * sizeof(double) +
+         (size_t)((c->sr_cap_lms + 1 + 3) & ~3) * sizeof(int) + (size_t)c->sr_cap_contrib * 3 * sizeof(unsigned short);
 }
 
 int build_structure_impl(b200_ctx* c) {
@@ -271,12 +271,48 @@ int build_structure_impl(b200_ctx* c) {
     bp_colptr = c->hpp_colptr; bp_rowidx = c->hpp_rowidx;
   } else {
     // =========================== bundle adjustment ===========================
-    // device edge order: by landmark (fixed points last), then camera pose index, then input order
+    // Landmark processing order ("rank"): lexicographic by the list of observing cameras, so that neighbouring
+    // landmarks feed the same Hschur blocks and a contiguous range of Hpl is one Schur work unit.  Every
+    // landmark-major device structure (edge order, lm_eptr, Hpl slots) follows it; arrays indexed by the landmark's
+    // Hessian index (estimates, Hll, b, x, Dinv) are reached through lm_order.
     std::vector<int> order(E);
     for (int e = 0; e < E; ++e) order[e] = e;
     auto lkey = [&](int e) { int l = lm_lidx[c->e_vi[e]]; return l < 0 ? nl : l; };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       int la = lkey(a), lb = lkey(b);
+      if (la != lb) return la < lb;
+      return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
+    });
+    std::vector<int> lm_order(nl), lm_rank(nl);
+    {
+      std::vector<int> cl_ptr(nl + 1, 0), cl;  // per landmark: ascending distinct free cameras
+      cl.reserve(E);
+      for (int q = 0; q < E;) {
+        const int l = lkey(order[q]);
+        if (l >= nl) break;
+        int prev = -1;
+        for (; q < E && lkey(order[q]) == l; ++q) {
+          const int pz = PV.hidx[c->e_vj[order[q]]];
+          if (pz >= 0 && pz != prev) { cl.push_back(pz); prev = pz; }
+        }
+        cl_ptr[l + 1] = (int)cl.size();
+      }
+      for (int l = 0; l < nl; ++l) cl_ptr[l + 1] = std::max(cl_ptr[l + 1], cl_ptr[l]);
+      for (int l = 0; l < nl; ++l) lm_order[l] = l;
+      std::stable_sort(lm_order.begin(), lm_order.end(), [&](int x, int y) {
+        const int nx = cl_ptr[x + 1] - cl_ptr[x], ny = cl_ptr[y + 1] - cl_ptr[y];
+        if ((nx == 0) != (ny == 0)) return ny == 0;  // landmarks without a free camera last
+        const int* rx = cl.data() + cl_ptr[x];
+        const int* ry = cl.data() + cl_ptr[y];
+        for (int q = 0; q < nx && q < ny; ++q) if (rx[q] != ry[q]) return rx[q] < ry[q];
+        return nx < ny;
+      });
+      for (int i = 0; i < nl; ++i) lm_rank[lm_order[i]] = i;
+    }
+    // device edge order: by landmark rank (fixed points last), then camera pose index, then input order
+    auto rkey = [&](int e) { int l = lm_lidx[c->e_vi[e]]; return l < 0 ? nl : lm_rank[l]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      int la = rkey(a), lb = rkey(b);
       if (la != lb) return la < lb;
       return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
     });
@@ -291,7 +327,7 @@ int build_structure_impl(b200_ctx* c) {
       e_pt[q] = c->e_vi[e]; e_cam[q] = c->e_vj[e];
       e_pose[q] = PV.hidx[c->e_vj[e]];
       int l = lm_lidx[c->e_vi[e]];
-      if (l >= 0) lm_eptr[l + 1]++;
+      if (l >= 0) lm_eptr[lm_rank[l] + 1]++;
       if (l >= 0 && e_pose[q] >= 0) {
         bool dup = q > 0 && lm_lidx[e_pt[q - 1]] == l && e_pose[q - 1] == e_pose[q];
         if (dup) e_hpl[q] = e_hpl[q - 1];
@@ -353,38 +389,30 @@ int build_structure_impl(b200_ctx* c) {
       return (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
     };
     // ---- Schur plan (kernels.cuh: schur_range_kernel / schur_finish_kernel)
-    // landmark order: lexicographic by camera list, so that neighbouring landmarks feed the same Hschur blocks
-    std::vector<int> lm_s0(nl + 1, 0);  // distinct Hpl slots per landmark (current numbering: landmark-major)
+    std::vector<int> lm_s0(nl + 1, 0);  // distinct Hpl slots per landmark rank (slots are numbered in rank order)
     {
       int prev = -1;
-      for (int l = 0; l < nl; ++l) {
-        for (int a = lm_eptr[l]; a < lm_eptr[l + 1]; ++a)
-          if (e_hpl[a] >= 0 && e_hpl[a] != prev) { prev = e_hpl[a]; lm_s0[l + 1]++; }
+      for (int i = 0; i < nl; ++i) {
+        for (int a = lm_eptr[i]; a < lm_eptr[i + 1]; ++a)
+          if (e_hpl[a] >= 0 && e_hpl[a] != prev) { prev = e_hpl[a]; lm_s0[i + 1]++; }
       }
-      for (int l = 0; l < nl; ++l) lm_s0[l + 1] += lm_s0[l];
+      for (int i = 0; i < nl; ++i) lm_s0[i + 1] += lm_s0[i];
     }
-    std::vector<int> pi;
-    for (int l = 0; l < nl; ++l) if (lm_s0[l + 1] > lm_s0[l]) pi.push_back(l);
-    std::stable_sort(pi.begin(), pi.end(), [&](int x, int y) {
-      const int nx = lm_s0[x + 1] - lm_s0[x], ny = lm_s0[y + 1] - lm_s0[y];
-      const int* rx = c->hpl_row.data() + lm_s0[x];
-      const int* ry = c->hpl_row.data() + lm_s0[y];
-      for (int q = 0; q < nx && q < ny; ++q) if (rx[q] != ry[q]) return rx[q] < ry[q];
-      return nx < ny;
-    });
+    std::vector<int> pi;  // ranks with at least one slot
+    for (int i = 0; i < nl; ++i) if (lm_s0[i + 1] > lm_s0[i]) pi.push_back(i);
     {
-      // renumber the Hpl slots in that order (a landmark's slots stay contiguous, ascending camera)
-      std::vector<int> renum(nslot), row2(nslot), col2(nslot);
-      int q2 = 0;
-      for (int l : pi)
-        for (int q = lm_s0[l]; q < lm_s0[l + 1]; ++q, ++q2) { renum[q] = q2; row2[q2] = c->hpl_row[q]; col2[q2] = c->hpl_col[q]; }
-      c->hpl_row.swap(row2); c->hpl_col.swap(col2);
-      for (int q = 0; q < E; ++q) if (e_hpl[q] >= 0) e_hpl[q] = renum[e_hpl[q]];
-      c->hpl_export = renum;  // SparseBlockMatrix (landmark-major) position -> slot
+      // SparseBlockMatrix (landmark-major, ascending camera) position -> slot, for the exported Hpl pattern
+      c->hpl_export.resize(nslot);
+      for (int q = 0; q < nslot; ++q) c->hpl_export[q] = q;
+      std::stable_sort(c->hpl_export.begin(), c->hpl_export.end(), [&](int x, int y) { return c->hpl_col[x] < c->hpl_col[y]; });
     }
     {
-      const int cap_slots = 448, cap_lms = 192, cap_contrib = 4096;  // 2 CTAs per SM (kernels.cuh)
-      std::vector<int> r_slot0{0}, r_lm_ptr{0}, r_lm_ids, r_seg_ptr{0}, seg_t, seg_cb, seg_ce;
+      // shared memory per range CTA (kernels.cuh): 3 CTAs per SM unless one landmark alone needs more slots
+      int kmax = 0;
+      for (int l : pi) kmax = std::max(kmax, lm_s0[l + 1] - lm_s0[l]);
+      const int cap_slots = std::max(352, kmax), cap_lms = 160, cap_contrib = 1536;
+      if (kmax > 1400) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 1400 cameras");
+      std::vector<int> r_slot0{0}, r_lm_ptr{0}, r_lm_ids, r_lm_slot, r_seg_ptr{0}, seg_t, seg_cb, seg_ce;
       std::vector<unsigned short> sc_a, sc_b, sc_l;
       struct Contrib { int t; unsigned short l, a, b; };
       std::vector<Contrib> rc;
@@ -403,6 +431,7 @@ int build_structure_impl(b200_ctx* c) {
         }
         while (sc_a.size() % 8) { sc_a.push_back(0); sc_b.push_back(0); sc_l.push_back(0); }  // 16-byte aligned ranges (bulk copies)
         rc.clear();
+        r_lm_slot.push_back(slot - r_slot0.back());  // end entry of the range
         r_slot0.push_back(slot); r_lm_ptr.push_back((int)r_lm_ids.size()); r_seg_ptr.push_back((int)seg_t.size());
       };
       for (int l : pi) {
@@ -415,7 +444,8 @@ int build_structure_impl(b200_ctx* c) {
         for (int a = 0; a < k2; ++a)
           for (int b2 = a; b2 < k2; ++b2)
             rc.push_back({find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]), (unsigned short)ll, (unsigned short)(base + a), (unsigned short)(base + b2)});
-        r_lm_ids.push_back(l);
+        r_lm_ids.push_back(lm_order[l]);
+        r_lm_slot.push_back(base);
         slot += k2;
       }
       close_range();
@@ -433,7 +463,7 @@ int build_structure_impl(b200_ctx* c) {
       for (int t = 0; t < nT; ++t) t_diag[t] = t_row[t] == t_col[t];
       c->sr_n = nr; c->sr_nseg = nseg; c->sr_ncontrib = (long long)sc_a.size();
       c->sr_cap_slots = cap_slots; c->sr_cap_lms = cap_lms; c->sr_cap_contrib = cap_contrib;
-      c->d_sr_slot0.upload(r_slot0, s); c->d_sr_lm_ptr.upload(r_lm_ptr, s); c->d_sr_lm_ids.upload(r_lm_ids, s);
+      c->d_sr_slot0.upload(r_slot0, s); c->d_sr_lm_ptr.upload(r_lm_ptr, s); c->d_sr_lm_ids.upload(r_lm_ids, s); c->d_sr_lm_slot.upload(r_lm_slot, s);
       c->d_sr_seg_ptr.upload(r_seg_ptr, s); c->d_sr_seg_t.upload(seg_t, s); c->d_sr_seg_cb.upload(seg_cb, s); c->d_sr_seg_ce.upload(seg_ce, s);
       c->d_sr_a.upload(sc_a, s); c->d_sr_b.upload(sc_b, s); c->d_sr_l.upload(sc_l, s);
       c->d_t_diag.upload(t_diag, s); c->d_tseg_ptr.upload(tseg_ptr, s); c->d_tseg_idx.upload(tseg_idx, s);
@@ -446,12 +476,12 @@ int build_structure_impl(b200_ctx* c) {
     c->d_ev0.upload(e_pt, s); c->d_ev1.upload(e_cam, s); c->d_e_pose.upload(e_pose, s); c->d_e_hpl.upload(e_hpl, s);
     c->d_e_flag.upload(e_first, s);
     c->d_meas.upload(meas, s); c->d_info.upload(info, s);
-    c->d_lm_eptr.upload(lm_eptr, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
+    c->d_lm_eptr.upload(lm_eptr, s); c->d_lm_order.upload(lm_order, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
     c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
     c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s);
     c->d_Hpp.alloc((size_t)np * 36 + (size_t)c->sizeP);  // [Hpp | b_p staging] contiguous for one all-reduce
     c->d_Hll.alloc((size_t)std::max(nl, 1) * 9); c->d_Hpl.alloc((size_t)std::max(nslot, 1) * 18);
-    c->d_Dinv.alloc((size_t)std::max(nl, 1) * k::kDinvStride); c->d_Dinv.zero(s); c->d_db.alloc((size_t)std::max(nl, 1) * 3);
+    c->d_Dinv.alloc((size_t)std::max(nl, 1) * k::kDinvStride); c->d_Dinv.zero(s); c->d_Wu.alloc((size_t)std::max(nl, 1) * k::kDinvStride); c->d_Wu.zero(s);
     c->d_Hschur.alloc((size_t)nT * 36 + (size_t)c->sizeP + 8);  // [Hschur | bschur | scalars] contiguous
     if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
     bp_colptr = c->hs_colptr; bp_rowidx = c->hs_rowidx;
@@ -520,7 +550,7 @@ int enqueue_build_system(b200_ctx* c) {
     double* b_p_stage = c->d_Hpp.p + (size_t)np * 36;
     if (c->nl > 0) {
       PhaseTimer pt(c, PH_LINEARIZE);
-      k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
+      k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
       c->lc.n++;
     }
     { PhaseTimer pt(c, PH_LINEARIZE_CAMS);
@@ -566,16 +596,16 @@ int enqueue_solve(b200_ctx* c) {
   {
     if (c->nl > 0) {
       PhaseTimer pt(c, PH_SCHUR_INV);
-      k::schur_landmark_inverse_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_Hll.p, c->d_b.p + c->sizeP, d_lambda, c->d_Dinv.p, c->d_db.p);
+      k::schur_landmark_inverse_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_Hll.p, c->d_b.p + c->sizeP, d_lambda, c->d_Dinv.p, c->d_Wu.p);
       c->lc.n++;
     }
     const double hpp_scale = (c->world > 1 && c->rank != 0) ? 0.0 : 1.0;
     {
       PhaseTimer pt(c, PH_SCHUR);
       if (c->sr_n > 0) {
-        k::SchurRanges R{c->d_sr_slot0.p, c->d_sr_lm_ptr.p, c->d_sr_lm_ids.p, c->d_sr_seg_ptr.p, c->d_sr_seg_t.p, c->d_sr_seg_cb.p, c->d_sr_seg_ce.p,
+        k::SchurRanges R{c->d_sr_slot0.p, c->d_sr_lm_ptr.p, c->d_sr_lm_ids.p, c->d_sr_lm_slot.p, c->d_sr_seg_ptr.p, c->d_sr_seg_t.p, c->d_sr_seg_cb.p, c->d_sr_seg_ce.p,
                          c->d_sr_a.p, c->d_sr_b.p, c->d_sr_l.p, c->d_t_diag.p, c->sr_cap_slots, c->sr_cap_lms, c->sr_cap_contrib};
-        k::schur_range_kernel<<<c->sr_n, k::kSrThreads, schur_range_smem(c), s>>>(R, c->d_Hpl.p, c->d_Dinv.p, c->d_db.p, c->d_sr_partial.p);
+        k::schur_range_kernel<<<c->sr_n, k::kSrThreads, schur_range_smem(c), s>>>(R, c->d_Hpl.p, c->d_Wu.p, c->d_sr_partial.p);
         c->lc.n++;
       }
       k::schur_finish_kernel<<<ceil_div(c->n_hs, 4), 256, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_tseg_ptr.p, c->d_tseg_idx.p,
@@ -593,7 +623,7 @@ int enqueue_solve(b200_ctx* c) {
     // on a failed factorisation the reference returns before touching the landmark part of x; the pose part
     // is left untouched by chol.solve, the landmark part is recomputed from the stale pose part (harmless:
     // LM discards the step, GN reports Fail).
-    k::ba_backsub_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_e_hpl.p, c->d_e_pose.p, c->d_Hpl.p, c->d_Dinv.p, c->d_b.p + c->sizeP, c->d_x.p, c->d_x.p + c->sizeP);
+    k::ba_backsub_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_e_hpl.p, c->d_e_pose.p, c->d_Hpl.p, c->d_Dinv.p, c->d_b.p + c->sizeP, c->d_x.p, c->d_x.p + c->sizeP);
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
   }

@@ -57,11 +57,12 @@ struct b200_ctx {
   g2o_b200::DevBuf<unsigned char> d_e_flag;  // pose graphs: transposed; BA: first-occurrence of its Hpl block
   g2o_b200::DevBuf<double> d_meas, d_info, d_stage;
   g2o_b200::DevBuf<int> d_hsrc_ptr, d_hsrc_id, d_bsrc_ptr, d_bsrc_id;
+  g2o_b200::DevBuf<int> d_lm_order;  // landmark rank (processing order) -> Hessian landmark index
   g2o_b200::DevBuf<int> d_lm_eptr, d_cam_eptr, d_cam_eidx, d_hpp_diag_block;
-  g2o_b200::DevBuf<double> d_Hpp, d_Hll, d_Hpl, d_Hschur, d_Dinv, d_db, d_b, d_x, d_bschur, d_diag;
+  g2o_b200::DevBuf<double> d_Hpp, d_Hll, d_Hpl, d_Hschur, d_Dinv, d_Wu, d_b, d_x, d_bschur, d_diag;
   g2o_b200::DevBuf<int> d_t_row, d_t_col, d_t_hpp;
   // Schur plan: landmark ranges, their segments (contributions to one Hschur block), per-block segment lists
-  g2o_b200::DevBuf<int> d_sr_slot0, d_sr_lm_ptr, d_sr_lm_ids, d_sr_seg_ptr, d_sr_seg_t, d_sr_seg_cb, d_sr_seg_ce, d_tseg_ptr, d_tseg_idx;
+  g2o_b200::DevBuf<int> d_sr_slot0, d_sr_lm_ptr, d_sr_lm_ids, d_sr_lm_slot, d_sr_seg_ptr, d_sr_seg_t, d_sr_seg_cb, d_sr_seg_ce, d_tseg_ptr, d_tseg_idx;
   g2o_b200::DevBuf<unsigned short> d_sr_a, d_sr_b, d_sr_l;
   g2o_b200::DevBuf<unsigned char> d_t_diag;
   g2o_b200::DevBuf<double> d_sr_partial;
