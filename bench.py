@@ -35,8 +35,8 @@ RESTART = 10  # LM iterations per optimisation run (the reference protocol: g2o 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="venice", choices=["venice", "sphere2500", "venice_small"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -134,20 +134,36 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def algorithmic_bytes(workload, dims, n_hpl, n_hs, n_contrib, n_edges):
-    """per-launch algorithmic bytes of the candidate dominant kernels (DESIGN.md section 5), read-once/write-once"""
+def algorithmic_bytes(workload, dims, info, n_hs, n_edges):
+    """per-launch algorithmic bytes of the candidate dominant kernels (DESIGN.md section 4), read-once/write-once"""
     if workload.startswith("venice"):
         nl = dims["numLandmarks"]
+        n_hpl, n_seg, n_contrib = info["hpl_slots"], info["schur_segments"], info["schur_contributions"]
         return {
             # ba_linearize_points: per edge cam idx 4 + meas 16 + info 24 + slot 4 + flag 1, write Hpl 144;
-            # per landmark est 32 + eptr 4 + vertex 4, write Hll 72 + b 24
-            "linearize": n_edges * (49 + 144) + nl * 136,
-            # schur_reduce: read Hpl 144/blk + Dinv 72 + db 24 per landmark + 12 B per contribution index + Hpp diag;
-            # write Hschur 288/block + bschur
-            "schur": n_hpl * 144 + nl * 96 + n_contrib * 12 + dims["numPoses"] * (288 + 48) + n_hs * 288 + dims["sizePoses"] * 8,
+            # per landmark est 32 + eptr 4 + order 4 + vertex 4, write Hll 72 + b 24
+            "linearize": n_edges * (49 + 144) + nl * 140,
+            # schur_range: read every Hpl block once 144 + Wu 80 per landmark + 6 B per contribution index + 12 B per
+            # segment descriptor; write one 36(+6)-double partial sum per segment
+            "schur": n_hpl * 144 + nl * 84 + n_contrib * 6 + n_seg * (12 + 42 * 8),
+            # ba_backsub: read Hpl 144 + slot/pose idx 8 per edge, Dinv 80 + b 24 + eptr/order 8 per landmark, write x 24
+            "backsub": n_hpl * 144 + n_edges * 8 + nl * 136,
         }
     # pose graph: pg_linearize reads ids 8 + Zinv 96 + info 168 + 2 poses 192, writes the 120-double staging record
     return {"linearize": n_edges * (8 + 96 + 168 + 192 + 960)}
+
+
+KERNEL_OF = {"linearize": {"ba": "ba_linearize_points_kernel", "pg": "pg_linearize_kernel<SE3>"},
+             "schur": {"ba": "schur_range_kernel"}, "backsub": {"ba": "ba_backsub_kernel"}}
+
+
+def ncu_traffic(kernel):
+    """dram bytes (read + write) per launch of `kernel` from the committed ncu --set full summary, or None"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return d.get(kernel.split("<")[0])
+    except Exception:
+        return None
 
 
 def run_b200(args, rank, world):
@@ -265,19 +281,20 @@ def run_b200(args, rank, world):
     if rank == 0:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         peak = peaks.get("hbm_gbs", 6650.0)
-        n_contrib = _contrib_count(prob) if prob["kind"] == "ba" else 0
-        n_hpl = len(prob["edge_v0"]) if prob["kind"] == "ba" else 0
         n_hs = lib_blocks(ctx, 3) if prob["kind"] == "ba" else 0
-        ab = algorithmic_bytes(args.workload, dims, n_hpl, n_hs, n_contrib, dims["numEdges"])
+        ab = algorithmic_bytes(args.workload, dims, info, n_hs, dims["numEdges"])
         cand = {k: phases[k] for k in ab if phases.get(k, (0, 0))[1] > 0}
         dom = max(cand, key=lambda k: cand[k][0])
         sec = cand[dom][0] / cand[dom][1]
         achieved = ab[dom] / sec / 1e9
-        roof = {"bound": "hbm", "kernel": {"linearize": "ba_linearize_points_kernel" if prob["kind"] == "ba" else "pg_linearize_kernel<SE3>",
-                                           "schur": "schur_reduce_kernel"}[dom],
+        kname = KERNEL_OF[dom]["ba" if prob["kind"] == "ba" else "pg"]
+        roof = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": sec * 1e3, "traffic": None}
+                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": sec * 1e3, "traffic": ncu_traffic(kname),
+                "others": {KERNEL_OF[k]["ba" if prob["kind"] == "ba" else "pg"]:
+                           {"frac": ab[k] / (cand[k][0] / cand[k][1]) / 1e9 / peak, "avg_launch_ms": 1e3 * cand[k][0] / cand[k][1]}
+                           for k in cand if k != dom}}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -305,11 +322,6 @@ def run_b200(args, rank, world):
 def lib_blocks(ctx, which):
     import openslam_g2o_b200 as g
     return int(g.lib.b200_get_blocks(ctx.handle, which, None, None, None))
-
-
-def _contrib_count(prob):
-    k = np.bincount(prob["edge_v0"] - prob["point_ids"][0])
-    return int((k * (k + 1) // 2).sum())
 
 
 def _vertex_count(ctx, kind, prob, sharded, opt):

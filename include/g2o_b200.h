@@ -135,17 +135,18 @@ int b200_get_bschur(b200_ctx* ctx, double* out);
  * factor it implies (css::lnz, linear_solver_csparse.h:292-293) */
 int b200_get_block_ordering(b200_ctx* ctx, int32_t* perm);   /* returns #blocks */
 int64_t b200_get_factor_nnz(b200_ctx* ctx);
-/* supernodal schedule facts: out[0..5] = #supernodes, #tasks, #levels, max panel rows, max panel cols,
- * stored factor doubles */
+/* schedule facts, out[0..11]: #supernodes, #tasks, #levels, max panel rows, max panel cols, stored factor doubles,
+ * #dataflow tasks of the factorisation kernel; Schur plan (0 without landmarks): #landmark ranges, #segments
+ * (partial sums), #contributions (block products), #Hpl slots, shared-memory bytes of a range CTA */
 int b200_get_factor_info(b200_ctx* ctx, int64_t* out);
 /* kernels launched by this context since creation (bench "gpu_launches") */
 int64_t b200_get_launch_count(b200_ctx* ctx);
 /* seconds of the dominant kernels accumulated with CUDA events when profiling is on */
 int b200_set_profiling(b200_ctx* ctx, int on);
-/* kernel-group id: 0 errors+chi2, 1 linearize (edges / per-landmark), 2 schur reduce, 3 cholesky factor,
+/* kernel-group id: 0 errors+chi2, 1 linearize (edges / per-landmark), 2 schur landmark ranges, 3 cholesky factor,
  * 4 triangular solves, 5 oplus update, 6 landmark back-substitution, 7 linearize per-camera, 8 ordered gather,
- * 9 landmark inverses, 10 LM scale, 11 collective; inside the Cholesky: 12 scatter, 13 tile updates, 14 split-K
- * reduce, 15 panel factor, 16 fused subtree tasks, 17 diagonal inverses, 18 forward solve, 19 backward solve.
+ * 9 landmark inverses, 10 LM scale, 11 collective, 14 schur finish; inside the Cholesky: 12 scatter of the input
+ * blocks, 13 the dataflow factorisation kernel (updates + panels + forward solve), 19 the dataflow backward sweep.
  * Profiling turns CUDA-graph replay off.  returns accumulated seconds and #occurrences */
 int b200_get_phase_time(b200_ctx* ctx, int phase, double* seconds, int64_t* count);
 

@@ -57,8 +57,8 @@ __global__ void chol_add_lambda_kernel(int nb, const long long* __restrict__ dia
 // ---------------------------------------------------------------------------------------------
 // numeric factorisation
 //   GROUP  : one CTA per (destination tile of 48 x 48 scalars, split-K group): pulls the update pieces that land in
-//            the tile, accumulates them in shared memory in list order, subtracts the sum from the panel (or leaves a
-//            partial sum for the tile's RTILE task)
+//            the tile, accumulates them in shared memory in list order, subtracts the sum from the panel (split
+//            tiles: leaves a partial sum; the group that finishes last adds them in group order and subtracts)
 //   CHUNK  : one CTA per (supernode, row chunk): diagonal block + chunk rows (+ the right-hand side as one more row)
 //            staged in shared memory, then held in REGISTERS: warp = block column, lane = block row, one d x d block
 //            per thread; blocked right-looking Cholesky with one barrier per block column
@@ -578,23 +578,28 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
       } else {
         double* out = F.scratch + (long long)slot * kTile * kTile;
         for (int i = tid; i < kTile * kTile; i += blockDim.x) __stcg(out + i, acc[i]);
-        cta_signal(F.slot_done + F.group_rtile[arg]);
+        // split tile: whichever group arrives last adds the partial sums in group order and subtracts once
+        const int rt = F.group_rtile[arg];
+        const int ns = F.r_nslots[rt];
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          s_nready = atomicAdd(F.slot_done + rt, 1) == ns - 1;
+          __threadfence();
+        }
+        __syncthreads();
+        if (s_nready) {
+          const double* in = F.scratch + (long long)F.r_slot0[rt] * kTile * kTile;
+          for (int i = tid; i < kTile * kTile; i += blockDim.x) {
+            double s = 0.0;
+            for (int g = 0; g < ns; ++g) s += __ldcg(in + ((long long)g * kTile * kTile + i));
+            acc[i] = s;
+          }
+          __syncthreads();
+          subtract_tile<D>(P, Q, L, tile, acc);
+          cta_signal(F.upd_done + Q.tile_sn[tile]);
+        }
       }
-    } else if (kind == 2) {  // RTILE: add the partial sums in group order, subtract once
-      const int ns = F.r_nslots[arg];
-      TCK_INIT;
-      cta_wait(F.slot_done + arg, ns);
-      TCK(7);
-      const double* in = F.scratch + (long long)F.r_slot0[arg] * kTile * kTile;
-      for (int i = tid; i < kTile * kTile; i += blockDim.x) {
-        double s = 0.0;
-        for (int g = 0; g < ns; ++g) s += __ldcg(in + ((long long)g * kTile * kTile + i));
-        acc[i] = s;
-      }
-      __syncthreads();
-      const int tile = F.r_tile[arg];
-      subtract_tile<D>(P, Q, L, tile, acc);
-      cta_signal(F.upd_done + Q.tile_sn[tile]);
     } else if (kind == 3) {  // CHUNK
       const int J = Q.chunk_sn[arg];
       factor_chunk<D>(P, Q, L, Ldiag, Dinv, arg, arg == Q.sn_chunk_ptr[J], smem, status, y, z, contrib, F.chunk_done,

@@ -27,7 +27,7 @@ int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ?
 // kernel groups for the profiling counters (b200_get_phase_time ids)
 enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE = 4, PH_UPDATE = 5, PH_BACKSUB = 6,
        PH_LINEARIZE_CAMS = 7, PH_GATHER = 8, PH_SCHUR_INV = 9, PH_SCALE = 10, PH_COLLECTIVE = 11,
-       /* 12.. : inside the Cholesky, see chol.h */ PH_COUNT = 24 };
+       /* 12, 13, 19: inside the Cholesky, see chol.cu */ PH_SCHUR_FINISH = 14, PH_COUNT = 24 };
 
 struct PhaseTimer : ScopedPhase {
   PhaseTimer(b200_ctx* c, int ph) : ScopedPhase(&c->prof, ph) {}
@@ -416,7 +416,8 @@ int build_structure_impl(b200_ctx* c) {
       std::vector<unsigned short> sc_a, sc_b, sc_l;
       struct Contrib { int t; unsigned short l, a, b; };
       std::vector<Contrib> rc;
-      int slot = 0;  // next slot (new numbering)
+      int slot = 0;  // next slot
+      long long npairs = 0;
       auto close_range = [&]() {
         if (r_lm_ids.size() == (size_t)r_lm_ptr.back()) return;
         std::stable_sort(rc.begin(), rc.end(), [](const Contrib& x, const Contrib& y) { return x.t < y.t; });
@@ -437,6 +438,7 @@ int build_structure_impl(b200_ctx* c) {
       for (int l : pi) {
         const int k2 = lm_s0[l + 1] - lm_s0[l];
         const int pairs = k2 * (k2 + 1) / 2;
+        npairs += pairs;
         if (k2 > 65535) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 65535 cameras");
         const int cur_slots = slot - r_slot0.back(), cur_lms = (int)r_lm_ids.size() - r_lm_ptr.back();
         if (cur_lms > 0 && (cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || (int)rc.size() + pairs > cap_contrib)) close_range();
@@ -461,7 +463,7 @@ int build_structure_impl(b200_ctx* c) {
       }
       std::vector<unsigned char> t_diag(nT);
       for (int t = 0; t < nT; ++t) t_diag[t] = t_row[t] == t_col[t];
-      c->sr_n = nr; c->sr_nseg = nseg; c->sr_ncontrib = (long long)sc_a.size();
+      c->sr_n = nr; c->sr_nseg = nseg; c->sr_ncontrib = npairs;
       c->sr_cap_slots = cap_slots; c->sr_cap_lms = cap_lms; c->sr_cap_contrib = cap_contrib;
       c->d_sr_slot0.upload(r_slot0, s); c->d_sr_lm_ptr.upload(r_lm_ptr, s); c->d_sr_lm_ids.upload(r_lm_ids, s); c->d_sr_lm_slot.upload(r_lm_slot, s);
       c->d_sr_seg_ptr.upload(r_seg_ptr, s); c->d_sr_seg_t.upload(seg_t, s); c->d_sr_seg_cb.upload(seg_cb, s); c->d_sr_seg_ce.upload(seg_ce, s);
@@ -608,6 +610,9 @@ int enqueue_solve(b200_ctx* c) {
         k::schur_range_kernel<<<c->sr_n, k::kSrThreads, schur_range_smem(c), s>>>(R, c->d_Hpl.p, c->d_Wu.p, c->d_sr_partial.p);
         c->lc.n++;
       }
+    }
+    {
+      PhaseTimer pt(c, PH_SCHUR_FINISH);
       k::schur_finish_kernel<<<ceil_div(c->n_hs, 4), 256, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_tseg_ptr.p, c->d_tseg_idx.p,
                                                                c->d_sr_partial.p, c->d_Hpp.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
       c->lc.n++;
@@ -1212,6 +1217,8 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
   if (!c || !c->structured || !out) return B200_ERR_INVALID;
   const SymbolicFactor& S = c->chol.symbolic();
   out[0] = S.nsn; out[1] = (int64_t)S.task_ptr.size() - 1; out[2] = S.nlevels; out[3] = S.max_nrow; out[4] = S.max_ncol; out[5] = S.factor_doubles;
+  out[6] = (int64_t)S.flow_kind.size();
+  out[7] = c->sr_n; out[8] = c->sr_nseg; out[9] = c->sr_ncontrib; out[10] = c->n_hpl; out[11] = c->sr_n > 0 ? (int64_t)schur_range_smem(c) : 0;
   return B200_OK;
 }
 int64_t b200_get_launch_count(b200_ctx* c) { return c ? c->lc.n : -1; }

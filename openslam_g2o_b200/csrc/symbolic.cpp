@@ -511,13 +511,13 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     S.level_group_ptr[l + 1] = (int)S.group_tile.size();
     S.level_rtile_ptr[l + 1] = (int)S.rtile_tile.size();
   }
-  // ---- 10. dataflow task list (level-major; inside a split level: groups, reduce tiles, chunks)
+  // ---- 10. dataflow task list (level-major; inside a split level: groups, then chunks; the reduction of a split
+  //          tile is done by whichever of its groups finishes last)
   for (int l = 0; l < S.nlevels; ++l) {
     if (S.level_kind[l] == 0) {
       for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) { S.flow_kind.push_back(0); S.flow_arg.push_back(t); }
     } else {
       for (int g = S.level_group_ptr[l]; g < S.level_group_ptr[l + 1]; ++g) { S.flow_kind.push_back(1); S.flow_arg.push_back(g); }
-      for (int r = S.level_rtile_ptr[l]; r < S.level_rtile_ptr[l + 1]; ++r) { S.flow_kind.push_back(2); S.flow_arg.push_back(r); }
       for (int c = S.level_chunk_ptr[l]; c < S.level_chunk_ptr[l + 1]; ++c) { S.flow_kind.push_back(3); S.flow_arg.push_back(S.level_chunks[c]); }
     }
   }

@@ -19,7 +19,7 @@ struct SymbolicOptions {
   double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
   double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
   bool relax = true;
-  int group_items = 4;              // split-K: work items per group task
+  int group_items = 8;              // split-K: work items per group task (8 measured best: profiles/)
   // set when the caller already knows the ordering (tests); empty = run block AMD
   std::vector<int> given_perm;
 };
@@ -92,8 +92,9 @@ struct SymbolicFactor {
   // completion counters of what the task consumes.  Every dependency points to an earlier entry of the list, so
   // the earliest unfinished task is always held by a running CTA (no deadlock, whatever the grid size).
   //   kind 0 SUBTREE(task)  update + factor of every supernode of a small subtree, sequentially in one CTA
-  //   kind 1 GROUP(group)   one split-K group of a destination tile: waits for each source supernode in list order
-  //   kind 2 RTILE(rtile)   adds the partial sums of a split tile in group order, subtracts once
+  //   kind 1 GROUP(group)   one split-K group of a destination tile: waits for each source supernode in list order;
+  //                         the group of a split tile that finishes last adds the partial sums in group order
+  //                         and subtracts once (rtile_* arrays)
   //   kind 3 CHUNK(chunk)   waits for every update of its supernode, factors diagonal block + its row chunk
   std::vector<int> flow_kind, flow_arg;
   std::vector<int> work_ksn;                       // source supernode of a work item

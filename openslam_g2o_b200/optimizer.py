@@ -200,10 +200,11 @@ class SolverContext:
         return int(lib.b200_get_factor_nnz(self._h))
 
     def factor_info(self):
-        out = np.zeros(6, np.int64)
+        out = np.zeros(12, np.int64)
         _check(lib.b200_get_factor_info(self._h, L.ptr(out)), self._h)
-        return dict(zip(("supernodes", "tasks", "levels", "max_panel_rows", "max_panel_cols", "factor_doubles"),
-                        (int(v) for v in out)))
+        return dict(zip(("supernodes", "tasks", "levels", "max_panel_rows", "max_panel_cols", "factor_doubles",
+                         "flow_tasks", "schur_ranges", "schur_segments", "schur_contributions", "hpl_slots",
+                         "schur_range_smem"), (int(v) for v in out)))
 
     def launch_count(self):
         return int(lib.b200_get_launch_count(self._h))
@@ -213,8 +214,8 @@ class SolverContext:
 
     def phase_times(self):
         names = ("errors", "linearize", "schur", "factor", "trisolve", "update", "backsub", "linearize_cams", "gather",
-                 "schur_inv", "scale", "collective", "chol_scatter", "chol_factor_flow", "chol_reduce", "chol_panel",
-                 "chol_fused", "chol_invert", "chol_forward", "chol_backward")
+                 "schur_inv", "scale", "collective", "chol_scatter", "chol_factor_flow", "schur_finish", "unused15",
+                 "unused16", "unused17", "unused18", "chol_backward")
         out = {}
         for i, nme in enumerate(names):
             s, c = C.c_double(), C.c_int64()

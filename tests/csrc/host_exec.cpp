@@ -160,8 +160,8 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
 }
 
 // Dataflow schedule check: walking flow_kind/flow_arg in list order, everything a task waits for must already be
-// complete (dependencies only point backwards - the no-deadlock argument of chol.cu), every group / reduce tile /
-// chunk must appear exactly once, and the completion targets (sn_nupd, sn_nchunk) must be reached exactly.
+// complete (dependencies only point backwards - the no-deadlock argument of chol.cu), every group / chunk must appear
+// exactly once, every split tile must be completed by exactly one last group, and the completion targets (sn_nupd, sn_nchunk) must be reached exactly.
 extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int max_cols, int relax, int group_items) {
   SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.group_items = group_items;
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
@@ -195,14 +195,14 @@ extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int ma
         const int r = S.group_rtile[a];
         if ((r < 0) != (S.group_slot[a] < 0)) return -22;
         if (r < 0) upd[S.tile_sn[S.group_tile[a]]]++;
-        else { if (S.rtile_tile[r] != S.group_tile[a]) return -23; slot[r]++; }
-        break;
-      }
-      case 2: {
-        if (a < 0 || a >= (int)seen_r.size() || seen_r[a]) return -30;
-        seen_r[a] = 1;
-        if (slot[a] != S.rtile_nslots[a]) return -31;
-        upd[S.tile_sn[S.rtile_tile[a]]]++;
+        else {
+          if (S.rtile_tile[r] != S.group_tile[a]) return -23;
+          if (++slot[r] == S.rtile_nslots[r]) {  // the last group of a split tile reduces and subtracts
+            if (seen_r[r]) return -30;
+            seen_r[r] = 1;
+            upd[S.tile_sn[S.rtile_tile[r]]]++;
+          }
+        }
         break;
       }
       case 3: {
