@@ -68,7 +68,8 @@ constexpr int kTile = 48;        // scalar rows / cols of a destination tile
 constexpr int kMaxBlockCols = 12;  // block columns of a panel = warps of a CTA (symbolic.cpp caps the supernode width)
 constexpr int kMaxPanelCols = 6 * kMaxBlockCols;
 constexpr int kCholThreads = 32 * kMaxBlockCols;
-constexpr int kUpdateSmemDoubles = kTile * kTile + 2 * kTile * kMaxPanelCols;  // acc | A rows | B rows
+constexpr int kSlices = 3;       // k slices of the tile product (kCholThreads = 128 register tiles x kSlices)
+constexpr int kUpdateSmemDoubles = kTile * kTile + 2 * kTile * kMaxPanelCols + (kSlices - 1) * 128 * 18;  // acc | A rows | B rows | slice sums
 constexpr int kLds = 33;         // lane stride of the staged panel: element (slot, i) of column c at (c*D+i)*kLds+slot
 
 struct CholPlanDev {
@@ -102,10 +103,8 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 // called by every thread of the CTA after its global writes: publishes them and bumps a completion counter
 __device__ __forceinline__ void cta_signal(int* counter) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1);
-  }
+  // release at gpu scope by one thread after the CTA barrier: cumulative over the other threads' stores
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(counter) : "memory");
 }
 // called by every thread: returns when *counter >= target (thread 0 spins, the barrier hands the acquire on)
 __device__ __forceinline__ void cta_wait(const int* counter, int target) {
@@ -168,55 +167,95 @@ __device__ void accumulate_items(const CholPlanDev& Q, const CholFlowDev& F, con
     const int nA = (a1 - a0) * D, nB = (b1 - b0) * D;
     __syncthreads();  // previous item's operands fully consumed, acc zeroing done, s_nready read by everyone
     {
-      // stage both operand row blocks; 4 independent loads in flight per thread
-      const int totA = nA * Nk, tot = totA + nB * Nk;
-      for (int i0 = tid; i0 < tot; i0 += 4 * nt) {
-        double v[4];
-        int dst[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = i0 + q * nt;
-          dst[q] = -1;
-          if (i < tot) {
-            const bool isA = i < totA;
-            const int ii = isA ? i : i - totA;
-            const int nR = isA ? nA : nB;
-            const int k = ii / nR, r = ii - k * nR;
-            v[q] = __ldcg(Kp + ((isA ? a0 : b0) * D + r + (long long)k * Mk));
-            dst[q] = (isA ? 0 : kTile * kMaxPanelCols) + r + k * kTile;
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (dst[q] >= 0) As[dst[q]] = v[q];  // Bs == As + kTile*kMaxPanelCols
+      // stage both operand row blocks with cp.async (no register staging: every copy of the item is in flight at
+      // once).  The source panel is complete and this SM's L1 was invalidated by the acquire that observed its
+      // completion counter, so the copies see the producers' stores.  d = 6: rows come in multiples of 48 bytes
+      // -> 16-byte copies; d = 3: 8-byte copies.
+      constexpr int V = (D % 2 == 0) ? 2 : 1;  // doubles per copy
+      const int rA = nA / V, rB = nB / V;
+      const int totA = rA * Nk, tot = totA + rB * Nk;
+      for (int i = tid; i < tot; i += nt) {
+        const bool isA = i < totA;
+        const int ii = isA ? i : i - totA;
+        const int nR = isA ? rA : rB;
+        const int k = ii / nR, r = (ii - k * nR) * V;
+        const double* src = Kp + ((isA ? a0 : b0) * D + r + (long long)k * Mk);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(As + (isA ? 0 : kTile * kMaxPanelCols) + r + k * kTile);
+        if (V == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int na = (a1 - a0) * S, nb = (b1 - b0) * S;
-    for (int idx = tid; idx < na * nb; idx += nt) {
-      const int j = idx / na, i = idx - j * na;
-      const int ma = a0 * S + i, mb = b0 * S + j;
-      if (ma < mb) continue;
-      const double* ra = As + i * 3;
-      const double* rb = Bs + j * 3;
-      double c00 = 0, c01 = 0, c02 = 0, c10 = 0, c11 = 0, c12 = 0, c20 = 0, c21 = 0, c22 = 0;
+    TCK(11);
+    // product: 6 x 3 register tiles (two 3-row units of the A side x one 3-column unit of the B side), the k range
+    // cut into kSlices parts -> 8 x 16 tiles x 3 slices = all 384 threads.  A warp covers 8 A-side and 4 B-side
+    // positions: its 128-bit operand loads are broadcasts (1-2 shared-memory wavefronts per instruction), so the
+    // loop is bound by the FP64 pipe, not by shared memory.
+    const int na = (a1 - a0) * S, nb = (b1 - b0) * S;   // 3-row units
+    const int ks = tid >> 7, m = tid & 127;
+    const int mi = m & 7, mj = m >> 3;
+    const int u0 = 2 * mi, u1 = u0 + 1;
+    const int mb = b0 * S + mj;
+    // a tile entirely above the diagonal of the update is never read again: skip it
+    const bool work = u0 < na && mj < nb && (a0 * S + min(u1, na - 1)) >= mb;
+    double c[6][3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) c[i][0] = c[i][1] = c[i][2] = 0.0;
+    if (work) {
+      const int kc = (Nk + kSlices - 1) / kSlices;
+      const int k0 = ks * kc, k1 = min(Nk, k0 + kc);
+      const double2* ra = reinterpret_cast<const double2*>(As + mi * 6 + k0 * kTile);
+      const double* rb = Bs + mj * 3 + k0 * kTile;
 #pragma unroll 4
-      for (int k = 0; k < Nk; ++k) {
-        const double x0 = ra[0], x1 = ra[1], x2 = ra[2];
+      for (int k = k0; k < k1; ++k) {
+        const double2 x01 = ra[0], x23 = ra[1], x45 = ra[2];
         const double y0 = rb[0], y1 = rb[1], y2 = rb[2];
-        c00 = fma(x0, y0, c00); c01 = fma(x0, y1, c01); c02 = fma(x0, y2, c02);
-        c10 = fma(x1, y0, c10); c11 = fma(x1, y1, c11); c12 = fma(x1, y2, c12);
-        c20 = fma(x2, y0, c20); c21 = fma(x2, y1, c21); c22 = fma(x2, y2, c22);
-        ra += kTile;
+        c[0][0] = fma(x01.x, y0, c[0][0]); c[0][1] = fma(x01.x, y1, c[0][1]); c[0][2] = fma(x01.x, y2, c[0][2]);
+        c[1][0] = fma(x01.y, y0, c[1][0]); c[1][1] = fma(x01.y, y1, c[1][1]); c[1][2] = fma(x01.y, y2, c[1][2]);
+        c[2][0] = fma(x23.x, y0, c[2][0]); c[2][1] = fma(x23.x, y1, c[2][1]); c[2][2] = fma(x23.x, y2, c[2][2]);
+        c[3][0] = fma(x23.y, y0, c[3][0]); c[3][1] = fma(x23.y, y1, c[3][1]); c[3][2] = fma(x23.y, y2, c[3][2]);
+        c[4][0] = fma(x45.x, y0, c[4][0]); c[4][1] = fma(x45.x, y1, c[4][1]); c[4][2] = fma(x45.x, y2, c[4][2]);
+        c[5][0] = fma(x45.y, y0, c[5][0]); c[5][1] = fma(x45.y, y1, c[5][1]); c[5][2] = fma(x45.y, y2, c[5][2]);
+        ra += kTile / 2;
         rb += kTile;
       }
-      const int ab = ma / S, bb = mb / S;
-      const int tr = (rel[ab] - R0) * D + (ma - ab * S) * 3;
+    }
+    TCK(12);
+    // k slices 1.. leave their tiles in scratch; slice 0 adds them in slice order and scatters into the tile
+    double* scr = Bs + kTile * kMaxPanelCols;  // (kSlices-1) x 128 x 18
+    if (ks > 0 && work) {
+      double* o = scr + ((ks - 1) * 128 + m) * 18;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { o[3 * i] = c[i][0]; o[3 * i + 1] = c[i][1]; o[3 * i + 2] = c[i][2]; }
+    }
+    __syncthreads();
+    if (ks == 0 && work) {
+#pragma unroll
+      for (int q = 0; q < kSlices - 1; ++q) {
+        const double* o = scr + (q * 128 + m) * 18;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { c[i][0] += o[3 * i]; c[i][1] += o[3 * i + 1]; c[i][2] += o[3 * i + 2]; }
+      }
+      const int bb = mb / S;
       const int tc = (rel[bb] - C0) * D + (mb - bb * S) * 3;
-      double* dst = acc + tr + tc * kTile;
-      dst[0] += c00; dst[1] += c10; dst[2] += c20;
-      dst[kTile] += c01; dst[kTile + 1] += c11; dst[kTile + 2] += c21;
-      dst[2 * kTile] += c02; dst[2 * kTile + 1] += c12; dst[2 * kTile + 2] += c22;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int u = u0 + h;
+        const int ma = a0 * S + u;
+        if (u < na && ma >= mb) {
+          const int ab = ma / S;
+          const int tr = (rel[ab] - R0) * D + (ma - ab * S) * 3;
+          double* dst = acc + tr + tc * kTile;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            dst[i] += c[3 * h + i][0];
+            dst[kTile + i] += c[3 * h + i][1];
+            dst[2 * kTile + i] += c[3 * h + i][2];
+          }
+        }
+      }
     }
     TCK(1);
   }
@@ -335,36 +374,20 @@ __device__ __forceinline__ void chunk_load(const ChunkGeom& G, const CholPlanDev
       if (lane == 0) Sm[(c * D) * kLds + rs] = y[col0s + c] - part;
     }
     TCK(8);
-    // kC columns x kU row strides per pass: up to kC*kU independent L2 loads in flight per thread
-    constexpr int kU = 6, kC = 1;
-    for (int c0 = w; c0 < N; c0 += nw * kC) {
-      for (int r0 = lane; r0 < Rp; r0 += 32 * kU) {
-        double v[kC][kU];
-#pragma unroll
-        for (int cc = 0; cc < kC; ++cc) {
-          const int c = c0 + cc * nw;
-          const double* src = Pj + (long long)c * M;
-#pragma unroll
-          for (int q = 0; q < kU; ++q) {
-            const int r = r0 + 32 * q;
-            if (c < N && r < Rp) v[cc][q] = __ldcg(src + (r < N ? r : crow0 + (r - N)));
-          }
-        }
-#pragma unroll
-        for (int cc = 0; cc < kC; ++cc) {
-          const int c = c0 + cc * nw;
-          double* dst = Sm + c * D * kLds;
-#pragma unroll
-          for (int q = 0; q < kU; ++q) {
-            const int r = r0 + 32 * q;
-            if (c < N && r < Rp) {
-              const int slot = r / D;
-              dst[(r - slot * D) * kLds + slot] = v[cc][q];
-            }
-          }
-        }
+    // one column per warp pass, lanes stride the rows: 8-byte cp.async straight into the slot layout (every copy
+    // of the panel in flight at once; L1 was invalidated by the acquire above, so the tile updates are visible)
+    for (int c = w; c < N; c += nw) {
+      const double* src = Pj + (long long)c * M;
+      double* dst = Sm + c * D * kLds;
+      for (int r = lane; r < Rp; r += 32) {
+        const int slot = r / D;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (r - slot * D) * kLds + slot)),
+                     "l"(src + (r < N ? r : crow0 + (r - N)))
+                     : "memory");
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   TCK(2);

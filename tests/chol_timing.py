@@ -13,7 +13,7 @@ ctx = opt.context
 ctx.build_system(); ctx.set_lambda(1e-3)
 ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1)
 ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1)
-names = ["item wait", "item compute", "chunk panel load", "chunk factor", "chunk signal", "chunk inverse", "chunk wait", "rtile wait", "chunk rhs gather", "chunk stores", "chunk contrib"]
+names = ["item wait", "item compute", "chunk panel load", "chunk factor", "chunk signal", "chunk inverse", "chunk wait", "rtile wait", "chunk rhs gather", "chunk stores", "chunk contrib", "item staging", "item product"]
 print(wl, "one factorisation, thread 0 of every CTA: total cycles, events, cycles/event (us at 1.965 GHz)")
 for i, n in enumerate(names):
     c, k = out[i], out[16 + i]
