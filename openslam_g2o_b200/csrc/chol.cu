@@ -352,8 +352,21 @@ __device__ __forceinline__ void chunk_load(const ChunkGeom& G, const CholPlanDev
   __syncthreads();
   TCK(6);
   {
-    // the panel streams in one column per warp pass (coalesced along the rows, 6 independent L2 loads in flight
-    // per thread); the threads owning a right-hand-side column add up their contributions in list order
+    // one column per warp pass, lanes stride the rows: 8-byte cp.async straight into the slot layout (every copy
+    // of the panel in flight at once; L1 was invalidated by the acquire above, so the tile updates are visible)
+    for (int c = w; c < N; c += nw) {
+      const double* src = Pj + (long long)c * M;
+      double* dst = Sm + c * D * kLds;
+      for (int r = lane; r < Rp; r += 32) {
+        const int slot = r / D;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (r - slot * D) * kLds + slot)),
+                     "l"(src + (r < N ? r : crow0 + (r - N)))
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ... and while the copies fly: the right-hand side.  The threads owning a right-hand-side column add up their
+    // contributions in list order
     if (tid < N) {
       double part = 0.0;
 #pragma unroll
@@ -374,19 +387,6 @@ __device__ __forceinline__ void chunk_load(const ChunkGeom& G, const CholPlanDev
       if (lane == 0) Sm[(c * D) * kLds + rs] = y[col0s + c] - part;
     }
     TCK(8);
-    // one column per warp pass, lanes stride the rows: 8-byte cp.async straight into the slot layout (every copy
-    // of the panel in flight at once; L1 was invalidated by the acquire above, so the tile updates are visible)
-    for (int c = w; c < N; c += nw) {
-      const double* src = Pj + (long long)c * M;
-      double* dst = Sm + c * D * kLds;
-      for (int r = lane; r < Rp; r += 32) {
-        const int slot = r / D;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (r - slot * D) * kLds + slot)),
-                     "l"(src + (r < N ? r : crow0 + (r - N)))
-                     : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -395,7 +395,8 @@ __device__ __forceinline__ void chunk_load(const ChunkGeom& G, const CholPlanDev
 
 // phase 2: the register-resident factorisation (see above); leaves the finished panel in shared memory
 template <int D>
-__device__ __forceinline__ void chunk_core(const ChunkGeom& G, double* __restrict__ Sm, int* status) {
+__device__ __forceinline__ void chunk_core(const ChunkGeom& G, double* __restrict__ Sm, int* status,
+                                           double* __restrict__ Ldiag, double* __restrict__ z, bool first) {
   CHUNK_GEOM_LOCALS;
   TCK_INIT;
   // lanes above the diagonal of the diagonal block hold nothing
@@ -457,6 +458,29 @@ __device__ __forceinline__ void chunk_core(const ChunkGeom& G, double* __restric
       }
     }
     __syncthreads();
+    if (w == jb && active) {
+      // my block column is final and this warp has nothing left to do: its rows go to HBM now, in the shadow of
+      // the remaining block columns.  Chunk rows -> panel; (first chunk only) diagonal block -> Ldiag: sibling chunk
+      // CTAs are still reading the unfactored block from the panel, so it must not be overwritten in place;
+      // forward-substitution result -> z: sibling chunks still read (P b)_J from y
+      if (lane >= ncb && lane < rs) {
+        double* dp = Pj + (crow0 + (lane - ncb) * D + (long long)(jb * D) * M);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+          for (int i = 0; i < D; ++i) __stcg(dp + i + (long long)j * M, B[i][j]);
+      } else if (first && lane < ncb) {
+        double* dd = Ldiag + (lane * D + (long long)(jb * D) * N);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+          for (int i = 0; i < D; ++i)
+            if (lane > jb || i >= j) dd[i + (long long)j * N] = B[i][j];
+      } else if (first && lane == rs) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[jb * D + j] = B[0][j];
+      }
+    }
     // the warp of the next pivot column updates first: the others start when it is done, so that their updates
     // run in the shadow of its (latency-bound) pivot factorisation instead of competing for the FP64 pipe
     const int nupd_threads = 32 * (ncb - jb - 1);
@@ -494,25 +518,6 @@ __device__ __forceinline__ void chunk_store(const ChunkGeom& G, const CholPlanDe
   TCK_INIT;
   // the finished panel sits in shared memory (the last iteration ended with a barrier and no update)
   {
-    // one column per warp pass, lanes stride the rows (coalesced stores, no divisions by run-time values)
-    for (int c = w; c < N; c += nw) {
-      const double* src = Sm + c * D * kLds;
-      if (first) {
-        // the factored diagonal block goes to its own array: sibling chunk CTAs are still reading the unfactored
-        // block from the panel (every chunk factors it redundantly), so it must not be overwritten in place
-        double* dd = Ldiag + Q.sn_dinvptr[J] + (long long)c * N;
-        for (int r = c + lane; r < N; r += 32) {
-          const int slot = r / D;
-          dd[r] = src[(r - slot * D) * kLds + slot];
-        }
-        if (lane == 0) z[col0s + c] = src[rs];  // y_J goes to its own vector: sibling chunks still read (P b)_J from y
-      }
-      double* dp = Pj + (crow0 - N + (long long)c * M);
-      for (int r = N + lane; r < Rp; r += 32) {
-        const int slot = r / D;
-        __stcg(dp + r, src[(r - slot * D) * kLds + slot]);
-      }
-    }
     TCK(9);
     // c_J = L21 y_J for this chunk's rows: what every ancestor will subtract from its right-hand side.
     // 4 threads per row, each a quarter of the columns, fixed shuffle tree
@@ -568,7 +573,7 @@ __device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q
                              const int* wait_counter, int wait_target) {
   const ChunkGeom G = chunk_geom<D>(P, Q, L, chunk);
   chunk_load<D>(G, Q, Sm, y, contrib, wait_counter, wait_target);
-  chunk_core<D>(G, Sm, status);
+  chunk_core<D>(G, Sm, status, Ldiag + Q.sn_dinvptr[G.J], z + G.col0s, first);
   chunk_store<D>(G, Q, Sm, Ldiag, Dinv, first, z, contrib, chunk_done);
 }
 
