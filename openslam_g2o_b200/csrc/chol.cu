@@ -120,7 +120,17 @@ __device__ __forceinline__ void cta_wait(const int* counter, int target) {
 __device__ unsigned long long g_chol_timing[32];
 #define TCK(i) do { if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_chol_timing[i], _n - _t0); atomicAdd(&g_chol_timing[16 + (i)], 1ull); _t0 = _n; } } while (0)
 #define TCK_INIT unsigned long long _t0 = clock64()
+// global-timer stamps per supernode (ns): [0] chunk saw its updates, [1] chunk signalled, [2] last group signalled an
+// update of it, [3] first consumer saw it complete
+__device__ unsigned long long g_chol_stamp[4][4096];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STAMP_SET(a, j) do { if (threadIdx.x == 0 && (j) < 4096) g_chol_stamp[a][j] = gtime(); } while (0)
+#define STAMP_MAX(a, j) do { if (threadIdx.x == 0 && (j) < 4096) atomicMax(&g_chol_stamp[a][j], gtime()); } while (0)
+#define STAMP_MIN(a, j) do { if (threadIdx.x == 0 && (j) < 4096) atomicMin(&g_chol_stamp[a][j], gtime()); } while (0)
 #else
+#define STAMP_SET(a, j) do {} while (0)
+#define STAMP_MAX(a, j) do {} while (0)
+#define STAMP_MIN(a, j) do {} while (0)
 #define TCK(i) do {} while (0)
 #define TCK_INIT do {} while (0)
 #endif
@@ -139,6 +149,13 @@ __device__ void accumulate_items(const CholPlanDev& Q, const CholFlowDev& F, con
   for (int i = tid; i < kTile * kTile; i += nt) acc[i] = 0.0;
   int nready = w0;
   for (int wi = w0; wi < w1; ++wi) {
+    // one level of indirection: everything the item needs sits in flat per-item arrays (static plan data:
+    // fetched before the item's source is known to be complete, the loads overlap the polling)
+    const int a0 = Q.work_a0[wi], a1 = Q.work_a1[wi], b0 = Q.work_b0[wi], b1 = Q.work_b1[wi];
+    const int Mk = Q.work_mk[wi], Nk = Q.work_nk[wi];
+    const double* Kp = L + Q.work_koff[wi];
+    const int* rel = Q.rel + Q.work_reloff[wi];
+    const int nA = (a1 - a0) * D, nB = (b1 - b0) * D;
     if (wi >= nready) {
       if (tid < 32) {
         const int idx = wi + tid;
@@ -158,13 +175,8 @@ __device__ void accumulate_items(const CholPlanDev& Q, const CholFlowDev& F, con
       __syncthreads();
       nready = *s_nready;
       TCK(0);
+      STAMP_MIN(3, F.work_ksn[wi]);
     }
-    // one level of indirection: everything the item needs sits in flat per-item arrays
-    const int a0 = Q.work_a0[wi], a1 = Q.work_a1[wi], b0 = Q.work_b0[wi], b1 = Q.work_b1[wi];
-    const int Mk = Q.work_mk[wi], Nk = Q.work_nk[wi];
-    const double* Kp = L + Q.work_koff[wi];
-    const int* rel = Q.rel + Q.work_reloff[wi];
-    const int nA = (a1 - a0) * D, nB = (b1 - b0) * D;
     __syncthreads();  // previous item's operands fully consumed, acc zeroing done, s_nready read by everyone
     {
       // stage both operand row blocks with cp.async (no register staging: every copy of the item is in flight at
@@ -351,6 +363,7 @@ __device__ __forceinline__ void chunk_load(const ChunkGeom& G, const CholPlanDev
   }
   __syncthreads();
   TCK(6);
+  STAMP_SET(0, J);
   {
     // one column per warp pass, lanes stride the rows: 8-byte cp.async straight into the slot layout (every copy
     // of the panel in flight at once; L1 was invalidated by the acquire above, so the tile updates are visible)
@@ -536,6 +549,7 @@ __device__ __forceinline__ void chunk_store(const ChunkGeom& G, const CholPlanDe
   }
   TCK(10);
   cta_signal(chunk_done + J);
+  STAMP_SET(1, J);
   TCK(4);
   if (first) {
     // off the critical path: inverse of the triangular diagonal block, so that the solves are matrix-vector
@@ -598,11 +612,33 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
     const int kind = F.kind[ti], arg = F.arg[ti];
     if (kind == 1) {  // GROUP
       const int tile = F.g_tile[arg];
-      accumulate_items<D>(Q, F, L, F.g_w0[arg], F.g_w1[arg], Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs, &s_nready);
       const int slot = F.g_slot[arg];
+      const int J = Q.tile_sn[tile], R0 = Q.tile_r0[tile], C0 = Q.tile_c0[tile];
+      // this task is the only writer of its tile: the values it will subtract from (A + lambda I, scattered by the
+      // previous kernels) are fetched before the updates are even complete
+      constexpr int kPer = (kTile * kTile + kCholThreads - 1) / kCholThreads;
+      double old[kPer];
+      const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
+      const int rows = min(kTile, M - R0 * D), cols = min(kTile, N - C0 * D);
+      double* Pt = L + P.sn_lptr[J] + ((long long)R0 * D + (long long)C0 * D * M);
       if (slot < 0) {
-        subtract_tile<D>(P, Q, L, tile, acc);
-        cta_signal(F.upd_done + Q.tile_sn[tile]);
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int i = tid + q * kCholThreads;
+          const int c = i / rows, r = i - c * rows;
+          old[q] = i < rows * cols ? __ldcg(Pt + (r + (long long)c * M)) : 0.0;
+        }
+      }
+      accumulate_items<D>(Q, F, L, F.g_w0[arg], F.g_w1[arg], R0, C0, acc, As, Bs, &s_nready);
+      if (slot < 0) {
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int i = tid + q * kCholThreads;
+          const int c = i / rows, r = i - c * rows;
+          if (i < rows * cols) __stcg(Pt + (r + (long long)c * M), old[q] - acc[r + c * kTile]);
+        }
+        cta_signal(F.upd_done + J);
+        STAMP_MAX(2, J);
       } else {
         double* out = F.scratch + (long long)slot * kTile * kTile;
         for (int i = tid; i < kTile * kTile; i += blockDim.x) __stcg(out + i, acc[i]);
@@ -933,6 +969,14 @@ void CholeskyGpu::solve(const double* /*d_b: consumed by factor()*/, double* d_x
 }  // namespace g2o_b200
 
 #ifdef CHOL_TIMING
+extern "C" void b200_debug_chol_stamps(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_stamp, sizeof(unsigned long long) * 4 * 4096);
+  if (reset) {
+    static unsigned long long z[4 * 4096];
+    for (int i = 0; i < 4 * 4096; ++i) z[i] = i / 4096 == 3 ? ~0ull : 0ull;
+    cudaMemcpyToSymbol(g2o_b200::g_chol_stamp, z, sizeof(z));
+  }
+}
 extern "C" void b200_debug_chol_timing(unsigned long long* out, int reset) {
   cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 32);
   if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g2o_b200::g_chol_timing, z, sizeof(z)); }

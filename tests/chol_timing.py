@@ -11,11 +11,24 @@ opt.optimize(2)
 out = (C.c_ulonglong * 32)()
 ctx = opt.context
 ctx.build_system(); ctx.set_lambda(1e-3)
-ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1)
-ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1)
+stamps = (C.c_ulonglong * (4 * 4096))()
+ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1); g.lib.b200_debug_chol_stamps(stamps, 1)
+ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1); g.lib.b200_debug_chol_stamps(stamps, 1)
 names = ["item wait", "item compute", "chunk panel load", "chunk factor", "chunk signal", "chunk inverse", "chunk wait", "rtile wait", "chunk rhs gather", "chunk stores", "chunk contrib", "item staging", "item product"]
 print(wl, "one factorisation, thread 0 of every CTA: total cycles, events, cycles/event (us at 1.965 GHz)")
 for i, n in enumerate(names):
     c, k = out[i], out[16 + i]
     print("  %-14s %12d %7d %10.0f  (%.2f us)" % (n, c, k, c / max(k, 1), c / max(k, 1) / 1965.0))
 print(ctx.factor_info())
+
+import numpy as np
+st = np.array(list(stamps), dtype=np.uint64).reshape(4, 4096).astype(np.float64)
+n = ctx.factor_info()["supernodes"]
+saw, sig, lastupd, firstuse = st[0, :n], st[1, :n], st[2, :n], st[3, :n]
+t0 = sig[sig > 0].min()
+ok = (firstuse < 1e19) & (sig > 0)
+print("chunk signal -> first consumer sees it: median %.2f us" % np.median((firstuse - sig)[ok] / 1e3))
+ok2 = (lastupd > 0) & (saw > 0)
+print("last update signal -> chunk sees it:   median %.2f us" % np.median((saw - lastupd)[ok2] / 1e3))
+print("chunk busy (saw -> signalled):         median %.2f us" % np.median((sig - saw)[saw > 0] / 1e3))
+print("whole factorisation (first chunk signal -> last): %.1f us" % ((sig.max() - t0) / 1e3))
