@@ -113,6 +113,13 @@ int b200_discard_top(b200_ctx* ctx);
 int b200_optimize(b200_ctx* ctx, int algorithm, int max_iterations, b200_iter_stats* stats);
 /* one OptimizationAlgorithm::solve(iteration) */
 int b200_algorithm_solve(b200_ctx* ctx, int algorithm, int iteration, b200_iter_stats* stats);
+/* robust kernel applied to every edge, like `g2o -robustKernel NAME -robustKernelWidth W`
+ * (apps/g2o_cli/g2o.cpp:322-336; kernels: core/robust_kernel_impl.cpp:65-126; use sites:
+ * core/base_binary_edge.hpp:91-113 first-order weight rho' on information and omega_r,
+ * core/sparse_optimizer.cpp:100-114 chi2 = sum of rho).  delta = kernel width (DCS: phi).  Default: none. */
+enum { B200_ROBUST_NONE = 0, B200_ROBUST_HUBER = 1, B200_ROBUST_PSEUDO_HUBER = 2, B200_ROBUST_CAUCHY = 3,
+       B200_ROBUST_SATURATED = 4, B200_ROBUST_DCS = 5 };
+int b200_set_robust_kernel(b200_ctx* ctx, int kind, double delta);
 /* LM properties (core/optimization_algorithm_levenberg.cpp:43-49) */
 int b200_set_lm_params(b200_ctx* ctx, double user_lambda_init, int max_trials_after_failure);
 

@@ -123,6 +123,12 @@ struct ScopedPhase {
   }
 };
 
+// robust kernel applied to every edge (kernels.cuh: robustify)
+struct Robust {
+  int kind;      // B200_ROBUST_*: 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS
+  double delta;
+};
+
 // counts every kernel launch of this library (reported as bench "gpu_launches")
 struct LaunchCounter {
   int64_t n = 0;

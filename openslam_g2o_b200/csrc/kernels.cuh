@@ -104,11 +104,47 @@ __device__ __forceinline__ Iso load_iso_soa(const double* __restrict__ meas, int
   return Z;
 }
 
+// ------------------------------------------------------------------ robust kernels
+// One kernel for every edge (what `g2o -robustKernel NAME -robustKernelWidth W` sets up, apps/g2o_cli/g2o.cpp:322-336).
+// rho(e2) and rho'(e2) as core/robust_kernel_impl.cpp:65-126; the quadratic form uses the first-order weight only:
+// information and omega_r are scaled by rho' (base_edge.h:96-102, base_binary_edge.hpp:91-113), chi2 sums rho
+// (sparse_optimizer.cpp:100-114).
+// struct Robust { int kind; double delta; }: common.h
+__device__ __forceinline__ void robustify(const Robust& rk, double e2, double& rho0, double& rho1) {
+  const double dsqr = rk.delta * rk.delta;
+  switch (rk.kind) {
+    case 1:
+      if (e2 <= dsqr) { rho0 = e2; rho1 = 1.0; }
+      else { const double sq = sqrt(e2); rho0 = 2 * sq * rk.delta - dsqr; rho1 = rk.delta / sq; }
+      break;
+    case 2: {
+      const double aux1 = (1.0 / dsqr) * e2 + 1.0, aux2 = sqrt(aux1);
+      rho0 = 2 * dsqr * (aux2 - 1); rho1 = 1.0 / aux2;
+      break;
+    }
+    case 3: {
+      const double aux = (1.0 / dsqr) * e2 + 1.0;
+      rho0 = dsqr * log(aux); rho1 = 1.0 / aux;
+      break;
+    }
+    case 4:
+      if (e2 <= dsqr) { rho0 = e2; rho1 = 1.0; } else { rho0 = dsqr; rho1 = 0.0; }
+      break;
+    case 5: {
+      double scale = (2.0 * rk.delta) / (rk.delta + e2);
+      if (scale >= 1.0) scale = 1.0;
+      rho0 = scale * e2 * scale; rho1 = scale * scale;
+      break;
+    }
+    default: rho0 = e2; rho1 = 1.0;
+  }
+}
+
 // KIND 0 = SE2 (D=3), 1 = SE3 (D=6)
 template <int KIND>
 __global__ void pg_chi2_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v1,
                                const double* __restrict__ est, const double* __restrict__ meas,
-                               const double* __restrict__ info, double* __restrict__ partials) {
+                               const double* __restrict__ info, Robust rk, double* __restrict__ partials) {
   constexpr int D = KIND == 0 ? 3 : 6;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   double chi = 0.0;
@@ -122,6 +158,7 @@ __global__ void pg_chi2_kernel(int E, const int* __restrict__ v0, const int* __r
     }
     load_info<D>(info, E, e, W);
     chi = chi2_of<D>(W, err);
+    if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
   }
   chi = block_sum(chi);
   if (threadIdx.x == 0) partials[blockIdx.x] = chi;
@@ -132,7 +169,7 @@ template <int KIND>
 __global__ void __launch_bounds__(128)
 pg_linearize_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v1, const double* __restrict__ est,
                     const double* __restrict__ meas, const double* __restrict__ info,
-                    const unsigned char* __restrict__ transposed, double* __restrict__ stage) {
+                    const unsigned char* __restrict__ transposed, Robust rk, double* __restrict__ stage) {
   constexpr int D = KIND == 0 ? 3 : 6;
   constexpr int STRIDE = 3 * D * D + 2 * D;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,6 +185,12 @@ pg_linearize_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v
   }
   double W[D * D];
   load_info<D>(info, E, e, W);
+  if (rk.kind) {  // weightedOmega = rho' * information; omega_r = -weightedOmega * error
+    double r0, r1;
+    robustify(rk, chi2_of<D>(W, err), r0, r1);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) W[i] *= r1;
+  }
   double omega_r[D];
 #pragma unroll
   for (int r = 0; r < D; ++r) {
@@ -228,7 +271,7 @@ __device__ __forceinline__ void load_der(const double* __restrict__ der, int c, 
 
 __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* __restrict__ e_cam,
                                const double* __restrict__ pt_est, const double* __restrict__ cam_der,
-                               const double* __restrict__ meas, const double* __restrict__ info,
+                               const double* __restrict__ meas, const double* __restrict__ info, Robust rk,
                                double* __restrict__ partials) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   double chi = 0.0;
@@ -242,6 +285,7 @@ __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* _
     p2mc_error(der, X, z, err);
     const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
     chi = err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]);
+    if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
   }
   chi = block_sum(chi);
   if (threadIdx.x == 0) partials[blockIdx.x] = chi;
@@ -254,18 +298,18 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
                            const int* __restrict__ e_cam, const int* __restrict__ e_hpl,
                            const unsigned char* __restrict__ e_first, const double* __restrict__ pt_est,
                            const double* __restrict__ cam_est, const double* __restrict__ cam_der,
-                           const double* __restrict__ meas, const double* __restrict__ info, int E,
+                           const double* __restrict__ meas, const double* __restrict__ info, int E, Robust rk,
                            double* __restrict__ Hll, double* __restrict__ Hpl, double* __restrict__ b_l) {
-  const int rk = blockIdx.x * blockDim.x + threadIdx.x;  // landmark rank: edges and Hpl slots are in this order
-  if (rk >= nl) return;
-  const int l = lm_order[rk];
+  const int rank = blockIdx.x * blockDim.x + threadIdx.x;  // landmark rank: edges and Hpl slots are in this order
+  if (rank >= nl) return;
+  const int l = lm_order[rank];
   const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * lm_vertex[l]);
   const double X[3] = {X4.x, X4.y, X4.z};
   double H[9], bl[3];
 #pragma unroll
   for (int i = 0; i < 9; ++i) H[i] = 0.0;
   bl[0] = bl[1] = bl[2] = 0.0;
-  for (int e = lm_eptr[rk]; e < lm_eptr[rk + 1]; ++e) {
+  for (int e = lm_eptr[rank]; e < lm_eptr[rank + 1]; ++e) {
     const int c = e_cam[e];
     double der[16];
     load_der(cam_der, c, der);
@@ -274,7 +318,12 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
     p2mc_jacobians(der, ct, X, Jp, Jc);
     const double z[2] = {meas[e], meas[(long long)E + e]};
     p2mc_error(der, X, z, err);
-    const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    if (rk.kind) {
+      double r0, r1;
+      robustify(rk, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), r0, r1);
+      w0 *= r1; w1 *= r1; w2 *= r1;
+    }
     // JpW = Jp^T W (3x2), omega_r = -W err
     double JpW[6];
 #pragma unroll
@@ -317,7 +366,7 @@ ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict
                          const int* __restrict__ pose_vertex, const int* __restrict__ e_pt,
                          const double* __restrict__ pt_est, const double* __restrict__ cam_est,
                          const double* __restrict__ cam_der, const double* __restrict__ meas,
-                         const double* __restrict__ info, int E, const int* __restrict__ hpp_diag_block,
+                         const double* __restrict__ info, int E, Robust rk, const int* __restrict__ hpp_diag_block,
                          double* __restrict__ Hpp, double* __restrict__ b_p) {
   const int i = blockIdx.x;
   const int c = pose_vertex[i];
@@ -335,7 +384,12 @@ ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict
     p2mc_jacobians(der, ct, X, Jp, Jc);
     const double z[2] = {meas[e], meas[(long long)E + e]};
     p2mc_error(der, X, z, err);
-    const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+    if (rk.kind) {
+      double r0, r1;
+      robustify(rk, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), r0, r1);
+      w0 *= r1; w1 *= r1; w2 *= r1;
+    }
     double JW[12];  // Jc^T W : 6x2
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -633,12 +687,12 @@ __global__ void ba_backsub_kernel(int nl, const int* __restrict__ lm_eptr, const
                                   const int* __restrict__ e_pose, const double* __restrict__ Hpl,
                                   const double* __restrict__ Dinv, const double* __restrict__ b_l,
                                   const double* __restrict__ x_p, double* __restrict__ x_l) {
-  const int rk = blockIdx.x * blockDim.x + threadIdx.x;  // landmark rank: edges and Hpl slots are in this order
-  if (rk >= nl) return;
-  const int l = lm_order[rk];
+  const int rank = blockIdx.x * blockDim.x + threadIdx.x;  // landmark rank: edges and Hpl slots are in this order
+  if (rank >= nl) return;
+  const int l = lm_order[rank];
   double c0 = b_l[3ll * l], c1 = b_l[3ll * l + 1], c2 = b_l[3ll * l + 2];
   int prev = -1;
-  for (int e = lm_eptr[rk]; e < lm_eptr[rk + 1]; ++e) {
+  for (int e = lm_eptr[rank]; e < lm_eptr[rank + 1]; ++e) {
     const int slot = e_hpl[e];
     if (slot < 0 || slot == prev) continue;  // duplicate observations share one block
     prev = slot;

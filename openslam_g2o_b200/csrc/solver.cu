@@ -512,11 +512,11 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
   const int E = c->nE, nb = ceil_div(E, 256);
   cudaStream_t s = c->stream;
   if (c->edge_kind == B200_EDGE_SE2)
-    k::pg_chi2_kernel<0><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_partials.p);
+    k::pg_chi2_kernel<0><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
   else if (c->edge_kind == B200_EDGE_SE3)
-    k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_partials.p);
+    k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
   else
-    k::ba_chi2_kernel<<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->d_partials.p);
+    k::ba_chi2_kernel<<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
   k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 0);
   c->lc.n += 2;
   B200_CUDA(cudaGetLastError());
@@ -536,13 +536,13 @@ int enqueue_build_system(b200_ctx* c) {
   if (!c->schur) {
     if (c->edge_kind == B200_EDGE_SE2) {
       { PhaseTimer pt(c, PH_LINEARIZE);
-      k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p); }
+      k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p); }
       PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<3, 9><<<ceil_div((long long)c->n_hpp * 9, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<3, 3><<<ceil_div((long long)np * 3, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
     } else {
       { PhaseTimer pt(c, PH_LINEARIZE);
-      k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->d_stage.p); }
+      k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p); }
       PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<6, 36><<<ceil_div((long long)c->n_hpp * 36, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<6, 6><<<ceil_div((long long)np * 6, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
@@ -552,11 +552,11 @@ int enqueue_build_system(b200_ctx* c) {
     double* b_p_stage = c->d_Hpp.p + (size_t)np * 36;
     if (c->nl > 0) {
       PhaseTimer pt(c, PH_LINEARIZE);
-      k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
+      k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
       c->lc.n++;
     }
     { PhaseTimer pt(c, PH_LINEARIZE_CAMS);
-    k::ba_linearize_cams_kernel<<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage); }
+    k::ba_linearize_cams_kernel<<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
     int rc = allreduce_dev(c, c->d_Hpp.p, (long long)np * 36 + c->sizeP);  // sharded: partial camera blocks -> full
@@ -973,6 +973,14 @@ int b200_discard_top(b200_ctx* c) {
     c->backup_depth = 0;
     return (int)B200_OK;
   });
+}
+
+int b200_set_robust_kernel(b200_ctx* c, int kind, double delta) {
+  if (!c || kind < B200_ROBUST_NONE || kind > B200_ROBUST_DCS || !(delta > 0.0)) return B200_ERR_INVALID;
+  c->robust.kind = kind;
+  c->robust.delta = delta;
+  if (!c->host_only) { cudaSetDevice(c->device); drop_graphs(c); }  // captured launches carry the kernel by value
+  return B200_OK;
 }
 
 int b200_set_lm_params(b200_ctx* c, double user_lambda_init, int max_trials) {

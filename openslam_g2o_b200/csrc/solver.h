@@ -75,6 +75,8 @@ struct b200_ctx {
   int backup_depth = 0;
   g2o_b200::CholeskyGpu chol;
 
+  g2o_b200::Robust robust{0, 1.0};                 // robust kernel applied to every edge (b200_set_robust_kernel)
+
   // ---------------- algorithm state (core/optimization_algorithm_levenberg.h)
   double lambda = -1.0, ni = 2.0;
   double lambda_for_solve = 0.0;

@@ -137,6 +137,11 @@ class SolverContext:
             _check(rc, self._h)
         return rc, st
 
+    def set_robust_kernel(self, kind, delta=1.0):
+        """one robust kernel on every edge (g2o -robustKernel NAME -robustKernelWidth delta)"""
+        _check(lib.b200_set_robust_kernel(self._h, ROBUST_KERNELS[kind] if isinstance(kind, str) else int(kind),
+                                          float(delta)), self._h)
+
     def set_lm_params(self, user_lambda_init=0.0, max_trials_after_failure=10):
         _check(lib.b200_set_lm_params(self._h, user_lambda_init, max_trials_after_failure), self._h)
 
@@ -230,6 +235,10 @@ class SolverContext:
         _check(lib.b200_synchronize(self._h), self._h)
 
 
+# names of the robust kernel factory (core/robust_kernel_impl.cpp:129-136)
+ROBUST_KERNELS = {"none": 0, "Huber": 1, "PseudoHuber": 2, "Cauchy": 3, "Saturated": 4, "DCS": 5}
+
+
 class SparseOptimizer:
     """g2o::SparseOptimizer as driven by the `g2o` binary, for the configured graph families.
 
@@ -288,6 +297,10 @@ class SparseOptimizer:
 
     def set_fixed(self, vid, fixed=True):
         _check(lib.b200_graph_set_fixed(self._g, vid, int(fixed)), self._g, graph=True)
+
+    def set_robust_kernel(self, name, width=1.0):
+        """`g2o -robustKernel name -robustKernelWidth width` (apps/g2o_cli/g2o.cpp:322-336): every edge gets the kernel"""
+        self.context.set_robust_kernel(name, width)
 
     def setup_cli(self):
         """gauge + marginalisation exactly as the g2o binary does (apps/g2o_cli/g2o.cpp:272-320)."""

@@ -182,6 +182,8 @@ struct Edge {
   double Ji[36], Jj[36];  // D x Di, D x Dj col-major
   double* H = nullptr;    // mapped off-diagonal block
   bool transposed = false;  // _hessianRowMajor (base_binary_edge.hpp:207-218)
+  int rkKind = 0;           // robustKernel(): 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS
+  double rkDelta = 1.0;     // RobustKernel::_delta
 };
 
 inline int vertex_dim(int kind) { return kind == ORC_VERTEX_SE2 ? 3 : kind == ORC_VERTEX_XYZ ? 3 : 6; }
@@ -498,7 +500,49 @@ void oplus(Vertex* v, const double* u) {
   }
 }
 
-// core/base_binary_edge.hpp:54-120 (no robust kernel: none of the configs sets one)
+// core/base_edge.h:58-61
+inline double edge_chi2(const Edge* e) {
+  const int D = e->D;
+  double s = 0;
+  for (int r = 0; r < D; ++r) {
+    double t = 0;
+    for (int k = 0; k < D; ++k) t += e->info[r + D * k] * e->err[k];
+    s += e->err[r] * t;
+  }
+  return s;
+}
+// core/robust_kernel_impl.cpp:65-126: rho = [rho(e2), rho'(e2), rho''(e2)]
+inline void robustify(int kind, double delta, double e2, double rho[3]) {
+  const double dsqr = delta * delta;
+  switch (kind) {
+    case 1:  // RobustKernelHuber :65-79
+      if (e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; rho[2] = 0.; }
+      else { double sqrte = sqrt(e2); rho[0] = 2 * sqrte * delta - dsqr; rho[1] = delta / sqrte; rho[2] = -0.5 * rho[1] / e2; }
+      break;
+    case 2: {  // RobustKernelPseudoHuber :81-90
+      double dsqrReci = 1. / dsqr, aux1 = dsqrReci * e2 + 1.0, aux2 = sqrt(aux1);
+      rho[0] = 2 * dsqr * (aux2 - 1); rho[1] = 1. / aux2; rho[2] = -0.5 * dsqrReci * rho[1] / aux1;
+      break;
+    }
+    case 3: {  // RobustKernelCauchy :92-100
+      double dsqrReci = 1. / dsqr, aux = dsqrReci * e2 + 1.0;
+      rho[0] = dsqr * log(aux); rho[1] = 1. / aux; rho[2] = -dsqrReci * rho[1] * rho[1];
+      break;
+    }
+    case 4:  // RobustKernelSaturated :102-114
+      if (e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; rho[2] = 0.; } else { rho[0] = dsqr; rho[1] = 0.; rho[2] = 0.; }
+      break;
+    case 5: {  // RobustKernelDCS :116-127 (delta is phi)
+      double scale = (2.0 * delta) / (delta + e2);
+      if (scale >= 1.0) scale = 1.0;
+      rho[0] = scale * e2 * scale; rho[1] = scale * scale; rho[2] = 0;
+      break;
+    }
+    default: rho[0] = e2; rho[1] = 1.; rho[2] = 0.;
+  }
+}
+
+// core/base_binary_edge.hpp:54-120
 template <int D, int Di, int Dj>
 void construct_quadratic_form_t(Edge* e) {
   Vertex* from = e->v[0];
@@ -513,6 +557,14 @@ void construct_quadratic_form_t(Edge* e) {
     double s = 0;
     for (int k = 0; k < D; ++k) s += omega[r + D * k] * e->err[k];
     omega_r[r] = -s;
+  }
+  double weightedOmega[D * D];
+  if (e->rkKind != 0) {  // :91-113 robust (weighted) error according to some kernel
+    double rho[3];
+    robustify(e->rkKind, e->rkDelta, edge_chi2(e), rho);
+    for (int i = 0; i < D * D; ++i) weightedOmega[i] = rho[1] * e->info[i];  // robustInformation, base_edge.h:96-102
+    for (int r = 0; r < D; ++r) omega_r[r] *= rho[1];
+    omega = weightedOmega;  // A^T wO A, A^T wO B (resp. B^T wO A), B^T wO B: the products below with omega = wO
   }
   if (fromNotFixed) {
     double AtO[Di * D];  // Di x D
@@ -558,18 +610,6 @@ void construct_quadratic_form(Edge* e) {
     case ORC_EDGE_P2MC: construct_quadratic_form_t<2, 3, 6>(e); break;
   }
 }
-// core/base_edge.h:58-61
-inline double edge_chi2(const Edge* e) {
-  const int D = e->D;
-  double s = 0;
-  for (int r = 0; r < D; ++r) {
-    double t = 0;
-    for (int k = 0; k < D; ++k) t += e->info[r + D * k] * e->err[k];
-    s += e->err[r] * t;
-  }
-  return s;
-}
-
 // ---------------------------------------------------------------------------------------------
 // SparseBlockMatrix (core/sparse_block_matrix.h:61-220): per block column a std::map<row, block*>
 // ---------------------------------------------------------------------------------------------
@@ -719,6 +759,8 @@ struct oracle_graph {
   VertexIDMap vertices;
   std::vector<std::unique_ptr<Vertex>> vstore;
   std::vector<std::unique_ptr<Edge>> edges;  // addEdge order = internalId
+  int rkKind = 0;            // robust kernel given to every edge (g2o.cpp:322-336)
+  double rkDelta = 1.0;
   // SparseOptimizer
   std::vector<Vertex*> activeVertices, ivMap;
   std::vector<Edge*> activeEdges;
@@ -863,6 +905,7 @@ int add_edge(G* g, int kind, int id1, int id2, const double* payload, int n) {
   g->edges.emplace_back(new Edge());
   Edge* e = g->edges.back().get();
   e->kind = kind; e->D = edge_dim(kind);
+  e->rkKind = g->rkKind; e->rkDelta = g->rkDelta;
   e->v[0] = from; e->v[1] = to;
   e->internalId = (int)g->edges.size() - 1;
   for (int i = 0; i < 6; ++i) e->err[i] = 0;
@@ -1012,7 +1055,10 @@ bool build_structure(G* g) {
 double compute_active_errors(G* g) {
   for (Edge* e : g->activeEdges) compute_error(e);
   double chi = 0.0;
-  for (Edge* e : g->activeEdges) chi += edge_chi2(e);
+  for (Edge* e : g->activeEdges) {  // activeRobustChi2, sparse_optimizer.cpp:100-114
+    if (e->rkKind != 0) { double rho[3]; robustify(e->rkKind, e->rkDelta, edge_chi2(e), rho); chi += rho[0]; }
+    else chi += edge_chi2(e);
+  }
   return chi;
 }
 
@@ -1326,6 +1372,14 @@ int oracle_setup_cli(oracle_graph* g, int requires_marginalize) {
   return ret;
 }
 int oracle_initialize(oracle_graph* g) { return initialize_optimization(g) ? 0 : -1; }
+void oracle_robustify(int kind, double delta, double e2, double* rho3) { robustify(kind, delta, e2, rho3); }
+// apps/g2o_cli/g2o.cpp:322-336: one kernel of the given width on every edge
+int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta) {
+  if (kind < 0 || kind > 5 || !(delta > 0)) return -1;
+  g->rkKind = kind; g->rkDelta = delta;
+  for (auto& e : g->edges) { e->rkKind = kind; e->rkDelta = delta; }
+  return 0;
+}
 void oracle_set_block_ordering(oracle_graph* g, int bo) { g->linearSolver.blockOrdering = bo != 0; }
 
 int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_stats* stats) {

@@ -91,6 +91,11 @@ class Oracle:
     def initialize_optimization(self):
         return self.L.oracle_initialize(self.g) == 0
 
+    def set_robust_kernel(self, name, width=1.0):
+        kinds = {"none": 0, "Huber": 1, "PseudoHuber": 2, "Cauchy": 3, "Saturated": 4, "DCS": 5}
+        self.L.oracle_set_robust_kernel.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        assert self.L.oracle_set_robust_kernel(self.g, kinds[name], float(width)) == 0
+
     def set_block_ordering(self, on):
         self.L.oracle_set_block_ordering(self.g, int(on))
 
