@@ -13,6 +13,7 @@
 #include <iostream>
 #include <vector>
 
+#include "g2o/core/robust_kernel_impl.h"
 #include "g2o/core/batch_stats.h"
 #include "g2o/core/block_solver.h"
 #include "g2o/core/optimization_algorithm.h"
@@ -125,6 +126,8 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     std::vector<int32_t> vi, vj;
     std::vector<double> meas, info;
     int ekind = -1;
+    int robustKind = B200_ROBUST_NONE;
+    double robustDelta = 1.0;
     for (size_t k = 0; k < edges.size(); ++k) {
       OptimizableGraph::Edge* e = edges[k];
       int kind = -1;
@@ -145,16 +148,34 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
         meas.insert(meas.end(), p->measurement().data(), p->measurement().data() + 2);
         info.insert(info.end(), p->information().data(), p->information().data() + 4);
       }
-      if (kind < 0 || (ekind >= 0 && kind != ekind) || e->robustKernel()) {
-        std::cerr << "OptimizationAlgorithmB200: unsupported / mixed edge types or robust kernel" << std::endl;
+      if (kind < 0 || (ekind >= 0 && kind != ekind)) {
+        std::cerr << "OptimizationAlgorithmB200: unsupported / mixed edge types" << std::endl;
         return false;
       }
+      // one robust kernel (type and width) for every edge - what `g2o -robustKernel` sets up (g2o.cpp:322-336)
+      int rk = B200_ROBUST_NONE;
+      double rkDelta = 1.0;
+      if (RobustKernel* r = e->robustKernel()) {
+        rkDelta = r->delta();
+        if (dynamic_cast<RobustKernelHuber*>(r)) rk = B200_ROBUST_HUBER;
+        else if (dynamic_cast<RobustKernelPseudoHuber*>(r)) rk = B200_ROBUST_PSEUDO_HUBER;
+        else if (dynamic_cast<RobustKernelCauchy*>(r)) rk = B200_ROBUST_CAUCHY;
+        else if (dynamic_cast<RobustKernelSaturated*>(r)) rk = B200_ROBUST_SATURATED;
+        else if (dynamic_cast<RobustKernelDCS*>(r)) rk = B200_ROBUST_DCS;
+        else rk = -1;
+      }
+      if (rk < 0 || (k > 0 && (rk != robustKind || rkDelta != robustDelta))) {
+        std::cerr << "OptimizationAlgorithmB200: unsupported robust kernel, or kernels that differ between edges" << std::endl;
+        return false;
+      }
+      robustKind = rk; robustDelta = rkDelta;
       ekind = kind;
       vi.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(0))]);
       vj.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(1))]);
     }
     if (vi.empty()) return false;
     if (b200_set_edges(_ctx, ekind, static_cast<int>(vi.size()), &vi[0], &vj[0], &meas[0], &info[0]) != B200_OK) return false;
+    if (b200_set_robust_kernel(_ctx, robustKind, robustDelta) != B200_OK) return false;
     int rc = b200_build_structure(_ctx);
     if (rc != B200_OK) std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
     return rc == B200_OK;
