@@ -747,6 +747,19 @@ chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L
         for (int i = tid; i < N * N; i += nt) stage[B * N + i] = Di[i];
       }
     }
+    // ... and, still before the wait, where the x values of the root's rows will come from (static plan data)
+    constexpr int kPreIdx = 2;
+    long long gidx[kPreIdx];
+    {
+      const int J = P.task_sn[q_root];
+      const int nc = P.sn_ncol[J], B = (P.sn_nrow[J] - nc) * D;
+      const int* jrows = P.sn_rows + P.sn_rowptr[J];
+#pragma unroll
+      for (int q = 0; q < kPreIdx; ++q) {
+        const int i = tid + q * nt;
+        gidx[q] = i < B ? (long long)jrows[nc + i / D] * D + (i % D) : -1;
+      }
+    }
     const int tp = task_parent[t];
     if (tp >= 0) cta_wait(bdone + tp, 1);
     for (int q = q_root; q >= P.task_ptr[t]; --q) {
@@ -759,7 +772,14 @@ chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L
       const int* jrows = P.sn_rows + P.sn_rowptr[J];
       double* xj = y + (long long)col0 * D;
       __syncthreads();
-      for (int i = tid; i < B; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
+      if (q == q_root) {
+#pragma unroll
+        for (int k = 0; k < kPreIdx; ++k)
+          if (gidx[k] >= 0) xb[tid + k * nt] = __ldcg(y + gidx[k]);
+        for (int i = tid + kPreIdx * nt; i < B; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
+      } else {
+        for (int i = tid; i < B; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
+      }
       __syncthreads();
       // t = y_J - L21^T x_below : one warp per column, lanes stride the rows, fixed-order shuffle tree
       for (int j = wid; j < N; j += nw) {
@@ -787,11 +807,7 @@ chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L
         __stcg(xj + i, (s0 + s1) + (s2 + s3));
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicExch(bdone + t, 1);
-    }
+    cta_signal(bdone + t);
   }
 }
 
