@@ -160,6 +160,66 @@ def test_bundle_adjustment_matches_oracle(seed, cams, points):
 
 
 @needs_oracle
+def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points():
+    """Schur plan edge cases: landmarks seen by every camera (more Hpl slots / block products than a range's
+    shared-memory budget: the range grows, the product indices are read from global memory), several observations
+    of one point by the same camera (one shared Hpl block), fixed points, a second fixed camera."""
+    import openslam_g2o_b200 as g
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    rng = np.random.default_rng(21)
+    cams = 400
+    p = dict(synth.venice_like(cams, 300, seed=21))
+    pid = p["point_ids"]
+    # 3 points observed by all cameras, duplicates of the first 40 observations
+    wide_pts = pid[:3]
+    extra_v0 = np.repeat(wide_pts, cams).astype(np.int32)
+    extra_v1 = np.tile(p["cam_ids"], 3).astype(np.int32)
+    extra_uv = rng.normal(0, 30.0, (len(extra_v0), 2))
+    dup = np.arange(40)
+    p["edge_v0"] = np.concatenate([p["edge_v0"], extra_v0, p["edge_v0"][dup]]).astype(np.int32)
+    p["edge_v1"] = np.concatenate([p["edge_v1"], extra_v1, p["edge_v1"][dup]]).astype(np.int32)
+    p["edge_payload"] = np.concatenate([p["edge_payload"], extra_uv, p["edge_payload"][dup] + 0.5])
+    opt = g.SparseOptimizer(device=0)
+    opt.set_algorithm("lm_fix6_3")
+    o = Oracle()
+    for t in (opt, o):
+        synth.feed(p, t)
+        for vid in (int(pid[10]), int(pid[11]), int(p["cam_ids"][7])):
+            t.set_fixed(vid, True)
+    assert opt.setup_cli() == o.setup_cli(True)
+    opt.initialize_optimization(); o.initialize_optimization()
+    o.algorithm_init()
+    opt._ensure_uploaded()
+    ctx = opt.context
+    assert ctx.build_structure() and o.build_structure()
+    info = ctx.factor_info()
+    assert info["schur_range_smem"] > 352 * 144 + 160 * 80  # one landmark alone needs more than the default range
+    assert abs(ctx.compute_active_errors() - o.compute_active_errors()) <= 1e-11 * o.compute_active_errors()
+    ctx.build_system(); o.build_system()
+    assert rel_err(ctx.b(), o.b()) < 1e-10
+    for which in (0, 1, 2):
+        gr, gc, gv = ctx.blocks(which)
+        orr, oc, ov = o.blocks(which)
+        assert np.array_equal(gr, orr) and np.array_equal(gc, oc), which
+        assert rel_err(gv, ov) < 1e-10, which
+    lam = o.lambda_init()
+    ctx.set_lambda(lam, True); o.set_lambda(lam, True)
+    assert ctx.solve() and o.solve()
+    gr, gc, gv = ctx.blocks(3)
+    orr, oc, ov = o.blocks(3)
+    assert np.array_equal(gr, orr) and np.array_equal(gc, oc)
+    assert rel_err(gv, ov) < 1e-9
+    assert rel_err(ctx.bschur(), o.bschur()) < 1e-9
+    assert rel_err(ctx.x(), o.x()) < 1e-6
+    ctx.restore_diagonal(); o.restore_diagonal()
+    n = opt.optimize(5)
+    no, st = o.optimize(LM, 5)
+    assert n == no
+    assert rel_err([s.chi2 for s in opt.batch_statistics], [s.chi2 for s in st[:no]]) < CHI_TOL
+
+
+@needs_oracle
 def test_pose_graph_edge_cases_match_oracle():
     """reversed edges (transposed-block path, block_solver.hpp:221-229), duplicate edges between the same pair,
     a fixed vertex in the middle, edges to the gauge"""
