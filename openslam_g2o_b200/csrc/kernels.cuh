@@ -486,7 +486,7 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
 //                       subtracts them from the Hpp term.
 constexpr int kSrThreads = 128;   // 32 groups of 4 lanes; 3 CTAs per SM (shared memory and registers)
 constexpr int kSrLanes = 4;
-constexpr int kSrSegMax = 32;     // products per segment
+constexpr int kSrSegMax = 64;     // products per segment
 constexpr int kSrPartial = 42;    // 36 block entries + 6 right-hand-side entries (diagonal blocks)
 
 struct SchurRanges {
@@ -601,15 +601,21 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) cacc[k] = 0.0;
-    for (int c = cb + sub; c < ce; c += kSrLanes) {
-      const int a = ia[c], b = ib[c];
+    // indices of the next product are fetched while this one is being multiplied
+    int c = cb + sub;
+    int a = 0, b = 0, ln = 0;
+    if (c < ce) { a = ia[c]; b = ib[c]; ln = il[c]; }
+    for (; c < ce; c += kSrLanes) {
+      const int cn = c + kSrLanes;
+      int an = 0, bn = 0, lnn = 0;
+      if (cn < ce) { an = ia[cn]; bn = ib[cn]; lnn = il[cn]; }
       const double2* Ba = reinterpret_cast<const double2*>(sH + 18 * a);
       const double2* Bb = reinterpret_cast<const double2*>(sH + 18 * b);
       double A[18];
 #pragma unroll
       for (int k = 0; k < 9; ++k) { const double2 v = Ba[k]; A[2 * k] = v.x; A[2 * k + 1] = v.y; }
       if (diag) {
-        const double* u = sW + kDinvStride * il[c] + 6;
+        const double* u = sW + kDinvStride * ln + 6;
         const double u0 = u[0], u1 = u[1], u2 = u[2];
 #pragma unroll
         for (int q = 0; q < 6; ++q) cacc[q] += A[q] * u0 + A[q + 6] * u1 + A[q + 12] * u2;
@@ -625,6 +631,7 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
 #pragma unroll
           for (int q = 0; q < 6; ++q) acc[q + 6 * c2] = fma(A[q + 6 * j], bj[c2], acc[q + 6 * c2]);
       }
+      a = an; b = bn; ln = lnn;
     }
     // the 4 lanes of the group add up in a fixed tree; afterwards lane `sub` stores the entries k = sub mod 4
     double* out = partial + (long long)sgm * kSrPartial;

