@@ -122,7 +122,7 @@ __device__ unsigned long long g_chol_timing[32];
 #define TCK_INIT unsigned long long _t0 = clock64()
 // global-timer stamps per supernode (ns): [0] chunk saw its updates, [1] chunk signalled, [2] last group signalled an
 // update of it, [3] first consumer saw it complete
-__device__ unsigned long long g_chol_stamp[4][4096];
+__device__ unsigned long long g_chol_stamp[6][4096];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define STAMP_SET(a, j) do { if (threadIdx.x == 0 && (j) < 4096) g_chol_stamp[a][j] = gtime(); } while (0)
 #define STAMP_MAX(a, j) do { if (threadIdx.x == 0 && (j) < 4096) atomicMax(&g_chol_stamp[a][j], gtime()); } while (0)
@@ -176,6 +176,7 @@ __device__ void accumulate_items(const CholPlanDev& Q, const CholFlowDev& F, con
       nready = *s_nready;
       TCK(0);
       STAMP_MIN(3, F.work_ksn[wi]);
+      STAMP_MAX(5, F.work_ksn[wi]);
     }
     __syncthreads();  // previous item's operands fully consumed, acc zeroing done, s_nready read by everyone
     {
@@ -630,6 +631,7 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
         }
       }
       accumulate_items<D>(Q, F, L, F.g_w0[arg], F.g_w1[arg], R0, C0, acc, As, Bs, &s_nready);
+      STAMP_MAX(4, J);
       if (slot < 0) {
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
@@ -986,10 +988,10 @@ void CholeskyGpu::solve(const double* /*d_b: consumed by factor()*/, double* d_x
 
 #ifdef CHOL_TIMING
 extern "C" void b200_debug_chol_stamps(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_stamp, sizeof(unsigned long long) * 4 * 4096);
+  cudaMemcpyFromSymbol(out, g2o_b200::g_chol_stamp, sizeof(unsigned long long) * 6 * 4096);
   if (reset) {
-    static unsigned long long z[4 * 4096];
-    for (int i = 0; i < 4 * 4096; ++i) z[i] = i / 4096 == 3 ? ~0ull : 0ull;
+    static unsigned long long z[6 * 4096];
+    for (int i = 0; i < 6 * 4096; ++i) z[i] = i / 4096 == 3 ? ~0ull : 0ull;
     cudaMemcpyToSymbol(g2o_b200::g_chol_stamp, z, sizeof(z));
   }
 }

@@ -11,7 +11,7 @@ opt.optimize(2)
 out = (C.c_ulonglong * 32)()
 ctx = opt.context
 ctx.build_system(); ctx.set_lambda(1e-3)
-stamps = (C.c_ulonglong * (4 * 4096))()
+stamps = (C.c_ulonglong * (6 * 4096))()
 ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1); g.lib.b200_debug_chol_stamps(stamps, 1)
 ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1); g.lib.b200_debug_chol_stamps(stamps, 1)
 names = ["item wait", "item compute", "chunk panel load", "chunk factor", "chunk signal", "chunk inverse", "chunk wait", "rtile wait", "chunk rhs gather", "chunk stores", "chunk contrib", "item staging", "item product"]
@@ -22,7 +22,7 @@ for i, n in enumerate(names):
 print(ctx.factor_info())
 
 import numpy as np
-st = np.array(list(stamps), dtype=np.uint64).reshape(4, 4096).astype(np.float64)
+st = np.array(list(stamps), dtype=np.uint64).reshape(6, 4096).astype(np.float64)
 n = ctx.factor_info()["supernodes"]
 saw, sig, lastupd, firstuse = st[0, :n], st[1, :n], st[2, :n], st[3, :n]
 t0 = sig[sig > 0].min()
@@ -31,4 +31,14 @@ print("chunk signal -> first consumer sees it: median %.2f us" % np.median((firs
 ok2 = (lastupd > 0) & (saw > 0)
 print("last update signal -> chunk sees it:   median %.2f us" % np.median((saw - lastupd)[ok2] / 1e3))
 print("chunk busy (saw -> signalled):         median %.2f us" % np.median((sig - saw)[saw > 0] / 1e3))
+lastsaw, proddone = st[5, :n], st[4, :n]
+ok3 = ok & (lastsaw > 0)
+print("chunk signal -> LAST consumer sees it: median %.2f us" % np.median((lastsaw - sig)[ok3] / 1e3))
+ok4 = (proddone > 0) & (lastupd > 0)
+print("last product done -> last update signal: median %.2f us" % np.median((lastupd - proddone)[ok4] / 1e3))
+# chain view: supernode J is updated by J-1 (same chain: J-2 on the two-chain Venice graph); report both
+for dJ in (1, 2):
+    a = proddone[dJ:] - lastsaw[:-dJ]
+    m = (proddone[dJ:] > 0) & (lastsaw[:-dJ] > 0) & (a > 0) & (a < 5e4)
+    if m.any(): print("last consumer saw K -> products of K+%d done: median %.2f us (n=%d)" % (dJ, np.median(a[m]) / 1e3, m.sum()))
 print("whole factorisation (first chunk signal -> last): %.1f us" % ((sig.max() - t0) / 1e3))
