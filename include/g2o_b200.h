@@ -113,6 +113,13 @@ int b200_discard_top(b200_ctx* ctx);
 int b200_optimize(b200_ctx* ctx, int algorithm, int max_iterations, b200_iter_stats* stats);
 /* one OptimizationAlgorithm::solve(iteration) */
 int b200_algorithm_solve(b200_ctx* ctx, int algorithm, int iteration, b200_iter_stats* stats);
+/* fill-reducing ordering of the (reduced) pose system.  nd_levels = 0 (default): block AMD, bit-exact with the
+ * reference's cs_amd(1, .) on the block pattern (solvers/csparse/linear_solver_csparse.h:252-294).  nd_levels = k > 0:
+ * nested dissection with 2^k parts on top of it (separators from breadth-first level structures, AMD inside the parts):
+ * an ordering for PARALLELISM - band-like reduced camera systems, whose AMD elimination tree is one long chain,
+ * become 2^k independent subtrees.  Same solution (to rounding), different elimination order; call before
+ * b200_build_structure.  b200_get_block_ordering reports the ordering in use. */
+int b200_set_ordering(b200_ctx* ctx, int nd_levels);
 /* robust kernel applied to every edge, like `g2o -robustKernel NAME -robustKernelWidth W`
  * (apps/g2o_cli/g2o.cpp:322-336; kernels: core/robust_kernel_impl.cpp:65-126; use sites:
  * core/base_binary_edge.hpp:91-113 first-order weight rho' on information and omega_r,

@@ -3,6 +3,8 @@
 // into plain arrays; this file owns the device-side life cycle: analyse at the first solve after init(),
 // then per call H2D(values,b) -> factor -> solve -> D2H(x), like LinearSolverCSparse::solve
 // (solvers/csparse/linear_solver_csparse.h:106-142).
+#include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/g2o_b200.h"
@@ -94,6 +96,7 @@ int b200_ls_solve(b200_linear_solver* ls, int nblocks, int block_dim, const int3
     const int nblk = colptr[nblocks];
     if (!ls->chol.analyzed() || ls->nb != nblocks || ls->d != block_dim || ls->nblk != nblk) {
       SymbolicOptions opt;
+      if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));  // see b200_set_ordering
       ls->chol.analyze(nblocks, block_dim, colptr, rowidx, opt, s);
       ls->nb = nblocks; ls->d = block_dim; ls->nblk = nblk;
     }

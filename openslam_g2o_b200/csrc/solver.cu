@@ -495,6 +495,8 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_SUBTREE_FLOPS")) opt.subtree_min_flops = atof(e);
   if (const char* e = getenv("G2O_B200_RELAX")) opt.relax = atoi(e) != 0;
   if (const char* e = getenv("G2O_B200_GROUP_ITEMS")) opt.group_items = std::max(1, atoi(e));
+  opt.nd_levels = c->nd_levels;
+  if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
   c->structured = true;
   c->backup_depth = 0;
@@ -973,6 +975,13 @@ int b200_discard_top(b200_ctx* c) {
     c->backup_depth = 0;
     return (int)B200_OK;
   });
+}
+
+int b200_set_ordering(b200_ctx* c, int nd_levels) {
+  if (!c || nd_levels < 0 || nd_levels > 16) return B200_ERR_INVALID;
+  c->nd_levels = nd_levels;
+  c->structured = false;  // takes effect at the next b200_build_structure
+  return B200_OK;
 }
 
 int b200_set_robust_kernel(b200_ctx* c, int kind, double delta) {

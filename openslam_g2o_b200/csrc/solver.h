@@ -75,6 +75,7 @@ struct b200_ctx {
   int backup_depth = 0;
   g2o_b200::CholeskyGpu chol;
 
+  int nd_levels = 0;                           // ordering: 0 = block AMD (reference), k = nested dissection, 2^k parts
   g2o_b200::Robust robust{0, 1.0};                 // robust kernel applied to every edge (b200_set_robust_kernel)
 
   // ---------------- algorithm state (core/optimization_algorithm_levenberg.h)

@@ -18,9 +18,51 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
 
   // ---- 1. ordering (bit-exact twin of cs_amd on the block pattern)
   if (!opt.given_perm.empty()) S.perm = opt.given_perm;
+  else if (opt.nd_levels > 0) S.perm = nested_dissection_order(nb, colptr, rowidx, opt.nd_levels, opt.nd_min_part);
   else S.perm = block_amd(nb, colptr, rowidx);
   S.pinv.assign(nb, 0);
   for (int k = 0; k < nb; ++k) S.pinv[S.perm[k]] = k;
+  if (opt.nd_levels > 0 && opt.given_perm.empty()) {
+    // the supernode detection below wants a post-ordered elimination tree (AMD delivers one; a concatenation of
+    // independently ordered parts need not): post-order the tree of the permuted pattern and compose
+    std::vector<int> parent(nb, -1), anc(nb, -1);
+    std::vector<std::vector<int>> upper(nb);  // for column k (new index): rows i < k
+    for (int c = 0; c < nb; ++c)
+      for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+        const int r = rowidx[p];
+        if (r == c) continue;
+        const int i = S.pinv[r], j = S.pinv[c];
+        upper[std::max(i, j)].push_back(std::min(i, j));
+      }
+    for (int k = 0; k < nb; ++k)
+      for (int i0 : upper[k]) {
+        int i = i0;
+        while (i != -1 && i < k) {
+          const int nxt = anc[i];
+          anc[i] = k;
+          if (nxt == -1) parent[i] = k;
+          i = nxt;
+        }
+      }
+    std::vector<int> head(nb, -1), next(nb, -1), post, stack;
+    for (int j = nb - 1; j >= 0; --j)
+      if (parent[j] >= 0) { next[j] = head[parent[j]]; head[parent[j]] = j; }
+    post.reserve(nb);
+    for (int root = 0; root < nb; ++root) {
+      if (parent[root] >= 0) continue;
+      stack.push_back(root);
+      while (!stack.empty()) {
+        const int v = stack.back();
+        const int ch = head[v];
+        if (ch >= 0) { head[v] = next[ch]; stack.push_back(ch); }
+        else { post.push_back(v); stack.pop_back(); }
+      }
+    }
+    std::vector<int> perm2(nb);
+    for (int k = 0; k < nb; ++k) perm2[k] = S.perm[post[k]];
+    S.perm.swap(perm2);
+    for (int k = 0; k < nb; ++k) S.pinv[S.perm[k]] = k;
+  }
 
   // ---- 2. permuted pattern, as "upper by column": for column k the rows i < k
   std::vector<int> up_ptr(nb + 1, 0);

@@ -20,6 +20,11 @@ struct SymbolicOptions {
   double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
   bool relax = true;
   int group_items = 8;              // split-K: work items per group task (8 measured best: profiles/)
+  // 0 (default): the reference's ordering - block AMD, bit-exact with cs_amd.  k > 0: nested dissection with 2^k parts
+  // on top of it (nested_dissection.cpp): separators first cut band-like systems, whose AMD elimination tree is one
+  // long chain, into independent subtrees; AMD orders the parts and the separators
+  int nd_levels = 0;
+  int nd_min_part = 24;             // parts smaller than this many blocks are not cut further
   // set when the caller already knows the ordering (tests); empty = run block AMD
   std::vector<int> given_perm;
 };
@@ -106,6 +111,9 @@ struct SymbolicFactor {
   std::vector<int64_t> sn_dinvptr;                 // nsn+1
   int64_t dinv_doubles = 0;
 };
+
+// nested_dissection.cpp
+std::vector<int> nested_dissection_order(int nb, const int* colptr, const int* rowidx, int levels, int min_part);
 
 // colptr/rowidx: upper block pattern (rows <= col, ascending, diagonal present) in input block order.
 SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt);

@@ -137,6 +137,10 @@ class SolverContext:
             _check(rc, self._h)
         return rc, st
 
+    def set_ordering(self, nd_levels=0):
+        """0: block AMD (the reference's ordering, default); k > 0: nested dissection with 2^k parts on top of it"""
+        _check(lib.b200_set_ordering(self._h, int(nd_levels)), self._h)
+
     def set_robust_kernel(self, kind, delta=1.0):
         """one robust kernel on every edge (g2o -robustKernel NAME -robustKernelWidth delta)"""
         _check(lib.b200_set_robust_kernel(self._h, ROBUST_KERNELS[kind] if isinstance(kind, str) else int(kind),

@@ -220,6 +220,41 @@ def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points():
 
 
 @needs_oracle
+@pytest.mark.parametrize("kind,nd", [("ba", 2), ("ba", 4), ("se3", 3)])
+def test_nested_dissection_ordering_matches_oracle(kind, nd):
+    """the optional ordering for parallelism changes the elimination order, not the answer"""
+    import openslam_g2o_b200 as g
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    p = synth.venice_like(60, 2500, seed=5) if kind == "ba" else synth.sphere(20, 12, seed=6)
+    opt = g.SparseOptimizer(device=0)
+    opt.set_algorithm("lm_fix6_3")
+    o = Oracle()
+    synth.feed(p, opt)
+    synth.feed(p, o)
+    assert opt.setup_cli() == o.setup_cli(True)
+    opt.initialize_optimization(); o.initialize_optimization()
+    opt._ensure_uploaded()
+    ctx = opt.context
+    ctx.set_ordering(nd)
+    assert ctx.build_structure()
+    amd = o.block_perm() if hasattr(o, "block_perm") else None
+    perm = ctx.block_ordering()
+    assert sorted(perm.tolist()) == list(range(len(perm)))
+    n = opt.optimize(8)
+    no, st = o.optimize(LM, 8)
+    assert n == no
+    assert rel_err([s.chi2 for s in opt.batch_statistics], [s.chi2 for s in st[:no]]) < CHI_TOL
+    opt.sync_estimates()
+    ids, kinds, _, _ = o.vertices()
+    est_g = np.stack([np.pad(opt.vertex_estimate(int(i)), (0, 12))[:12] for i in ids])
+    est_o = np.stack([np.pad(o.vertex_estimate(int(i)), (0, 12))[:12] for i in ids])
+    assert rel_err(est_g, est_o) < EST_TOL
+    if amd is not None and len(amd) == len(perm):
+        assert not np.array_equal(perm, amd)  # it really is another ordering
+
+
+@needs_oracle
 def test_pose_graph_edge_cases_match_oracle():
     """reversed edges (transposed-block path, block_solver.hpp:221-229), duplicate edges between the same pair,
     a fixed vertex in the middle, edges to the gauge"""

@@ -82,3 +82,42 @@ def test_not_positive_definite_is_reported(hx):
     b = np.ones(24)
     x = np.zeros(24)
     assert hx.hx_solve(8, 3, _p(cp), _p(ri), _p(v), C.c_double(0.0), _p(b), _p(x), 96, 1) == 1
+
+
+def test_nested_dissection_option(hx):
+    """optional ordering for parallelism: still a permutation, the schedule still solves the system, the dataflow list
+    is still valid - and on a ring band (the reduced camera system of a BA) the elimination tree gets much shallower"""
+    rng = np.random.default_rng(9)
+    try:
+        for nd in (1, 3):
+            hx.hx_set_nd_levels(nd)
+            for d, nb, edges in ((3, 60, [(i, j) for i in range(60) for j in range(i + 1, min(60, i + 4))]),
+                                 (6, 45, [(i, (i + k) % 45) for i in range(45) for k in range(1, 4)]),
+                                 (6, 30, [(int(rng.integers(30)), int(rng.integers(30))) for _ in range(80)])):
+                cp, ri, vals, A = random_spd_blocks(rng, nb, d, edges)
+                v = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+                b = rng.standard_normal(nb * d)
+                x = np.zeros(nb * d)
+                assert hx.hx_solve(nb, d, _p(cp), _p(ri), _p(v), C.c_double(0.5), _p(b), _p(x), 24, 1) == 0
+                xr = np.linalg.solve(A + 0.5 * np.eye(nb * d), b)
+                assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+                assert hx.hx_check_flow(nb, d, _p(cp), _p(ri), 24, 1, 4) == 0
+                perm = np.zeros(nb, np.int32)
+                info = np.zeros(8, np.int64)
+                hx.hx_analyze(nb, d, _p(cp), _p(ri), 24, 1, _p(info), _p(perm))
+                assert sorted(perm.tolist()) == list(range(nb))
+        # ring of 871 cameras, every camera coupled to the next 8: levels of the task schedule, AMD vs dissection
+        from helpers import upper_pattern_from_edges
+        ring = [(i, (i + k) % 871) for i in range(871) for k in range(1, 9)]
+        cp, ri = upper_pattern_from_edges(871, ring)
+        res = {}
+        for nd in (0, 4):
+            hx.hx_set_nd_levels(nd)
+            info = np.zeros(8, np.int64)
+            hx.hx_analyze(871, 6, _p(cp), _p(ri), 72, 1, _p(info), None)
+            res[nd] = (int(info[2]), int(info[4]))  # levels, factor doubles
+            assert hx.hx_check_flow(871, 6, _p(cp), _p(ri), 72, 1, 8) == 0
+        assert res[4][0] * 2 < res[0][0], res          # much shallower
+        assert res[4][1] < 3 * res[0][1], res          # at a bounded price in fill
+    finally:
+        hx.hx_set_nd_levels(0)
