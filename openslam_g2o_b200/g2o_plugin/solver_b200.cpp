@@ -38,6 +38,8 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     _device = _properties.makeProperty<Property<int> >("device", 0);
     _userLambdaInit = _properties.makeProperty<Property<double> >("initialLambda", 0.);
     _maxTrialsAfterFailure = _properties.makeProperty<Property<int> >("maxTrialsAfterFailure", 10);
+    // 0: block AMD, the reference's ordering; k > 0: nested dissection with 2^k parts on top of it (b200_set_ordering)
+    _ndLevels = _properties.makeProperty<Property<int> >("ndLevels", 0);
   }
   virtual ~OptimizationAlgorithmB200() { b200_destroy(_ctx); }
 
@@ -48,6 +50,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
       return false;
     }
     b200_set_lm_params(_ctx, _userLambdaInit->value(), _maxTrialsAfterFailure->value());
+    b200_set_ordering(_ctx, _ndLevels->value());
     return ingest();
   }
 
@@ -215,6 +218,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
   double _lambda;
   int _levenbergIterations;
   Property<int>* _device;
+  Property<int>* _ndLevels;
   Property<double>* _userLambdaInit;
   Property<int>* _maxTrialsAfterFailure;
   std::map<OptimizableGraph::Vertex*, int> _slot;
