@@ -127,6 +127,12 @@ int b200_set_ordering(b200_ctx* ctx, int nd_levels);
 enum { B200_ROBUST_NONE = 0, B200_ROBUST_HUBER = 1, B200_ROBUST_PSEUDO_HUBER = 2, B200_ROBUST_CAUCHY = 3,
        B200_ROBUST_SATURATED = 4, B200_ROBUST_DCS = 5 };
 int b200_set_robust_kernel(b200_ctx* ctx, int kind, double delta);
+/* Solver::computeMarginals (core/solver.h:100-106, core/block_solver.hpp:490-499, LinearSolver::solvePattern
+ * solvers/csparse/linear_solver_csparse.h:190-225, core/marginal_covariance_cholesky.cpp): blocks (rows[q], cols[q])
+ * of the inverse of the current Hpp (call after b200_build_system; lambda is not added), written to
+ * out + q*d*d column-major.  Pose graphs only (B200_ERR_UNSUPPORTED with a Schur complement).
+ * returns B200_OK / B200_NOT_POSITIVE_DEFINITE / <0 */
+int b200_compute_marginals(b200_ctx* ctx, int nblocks, const int32_t* rows, const int32_t* cols, double* out);
 /* LM properties (core/optimization_algorithm_levenberg.cpp:43-49) */
 int b200_set_lm_params(b200_ctx* ctx, double user_lambda_init, int max_trials_after_failure);
 

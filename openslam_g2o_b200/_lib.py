@@ -89,6 +89,7 @@ def _load():
         "b200_get_factor_info": (i32, [vp, vp]),
         "b200_set_robust_kernel": (i32, [vp, i32, C.c_double]),
         "b200_set_ordering": (i32, [vp, i32]),
+        "b200_compute_marginals": (i32, [vp, i32, vp, vp, vp]),
         "b200_get_launch_count": (i64, [vp]),
         "b200_set_profiling": (i32, [vp, i32]),
         "b200_get_phase_time": (i32, [vp, i32, C.POINTER(dbl), C.POINTER(i64)]),

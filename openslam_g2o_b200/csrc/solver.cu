@@ -938,6 +938,54 @@ int b200_solve(b200_ctx* c) {
   });
 }
 
+// Solver::computeMarginals (core/block_solver.hpp:490-499 -> LinearSolver::solvePattern,
+// solvers/csparse/linear_solver_csparse.h:190-225 -> MarginalCovarianceCholesky, core/marginal_covariance_cholesky.cpp):
+// selected blocks of Hpp^-1.  The reference walks the scalar factor with a recursive formula; here every requested
+// block column is d solves with unit right-hand sides on the GPU factor (factorisation and forward substitution are
+// one kernel, so each solve refactors: fine for the handful of blocks a front-end asks for, slow for all of them).
+int b200_compute_marginals(b200_ctx* c, int nblocks, const int32_t* rows, const int32_t* cols, double* out) {
+  return guarded(c, [&]() -> int {
+    NEED_DEVICE(c);
+    NEED_STRUCTURE(c);
+    if (nblocks < 0 || (nblocks > 0 && (!rows || !cols || !out))) return fail(c, B200_ERR_INVALID, "bad arguments");
+    if (c->schur) return fail(c, B200_ERR_UNSUPPORTED, "marginals are provided for pose graphs (no Schur complement): the reference inverts Hpp there");
+    B200_CUDA(cudaSetDevice(c->device));
+    const int d = c->pd, n = c->sizeP;
+    for (int q = 0; q < nblocks; ++q)
+      if (rows[q] < 0 || rows[q] >= c->np || cols[q] < 0 || cols[q] >= c->np) return fail(c, B200_ERR_INVALID, "block index out of range");
+    std::vector<int> order(nblocks);
+    for (int q = 0; q < nblocks; ++q) order[q] = q;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return cols[a] < cols[b2]; });
+    DevBuf<double> rhs, xs;
+    rhs.alloc(n); xs.alloc(n);
+    std::vector<double> hx(n);
+    const double one = 1.0;
+    cudaStream_t s = c->stream;
+    for (int q0 = 0; q0 < nblocks;) {
+      const int cb = cols[order[q0]];
+      int q1 = q0;
+      while (q1 < nblocks && cols[order[q1]] == cb) ++q1;
+      for (int k = 0; k < d; ++k) {
+        B200_CUDA(cudaMemsetAsync(rhs.p, 0, n * sizeof(double), s));
+        B200_CUDA(cudaMemcpyAsync(rhs.p + (size_t)cb * d + k, &one, sizeof(double), cudaMemcpyHostToDevice, s));
+        c->chol.factor(c->d_Hpp.p, nullptr, rhs.p, s, &c->lc, nullptr);
+        c->chol.solve(rhs.p, xs.p, s, &c->lc, nullptr);
+        int status = 0;
+        B200_CUDA(cudaMemcpyAsync(&status, c->chol.status_ptr(), sizeof(int), cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(hx.data(), xs.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaStreamSynchronize(s));
+        if (status) return (int)B200_NOT_POSITIVE_DEFINITE;
+        for (int q = q0; q < q1; ++q) {
+          const int req = order[q];
+          for (int i = 0; i < d; ++i) out[(size_t)req * d * d + i + (size_t)k * d] = hx[(size_t)rows[req] * d + i];
+        }
+      }
+      q0 = q1;
+    }
+    return (int)B200_OK;
+  });
+}
+
 int b200_update(b200_ctx* c) {
   return guarded(c, [&]() {
     NEED_DEVICE(c);

@@ -74,7 +74,30 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     return static_cast<SolverResult>(st.result);
   }
 
-  virtual bool computeMarginals(SparseBlockMatrix<MatrixXd>&, const std::vector<std::pair<int, int> >&) { return false; }
+  // OptimizationAlgorithmWithHessian::computeMarginals -> Solver::computeMarginals (core/block_solver.hpp:490-499)
+  virtual bool computeMarginals(SparseBlockMatrix<MatrixXd>& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
+    if (blockIndices.empty()) return true;
+    int dims[8];
+    if (b200_get_dims(_ctx, dims) != B200_OK) return false;
+    const int d = dims[6];
+    if (b200_build_system(_ctx) != B200_OK) return false;  // Hpp at the current estimates, no lambda
+    std::vector<int32_t> rows(blockIndices.size()), cols(blockIndices.size());
+    for (size_t q = 0; q < blockIndices.size(); ++q) { rows[q] = blockIndices[q].first; cols[q] = blockIndices[q].second; }
+    std::vector<double> out(blockIndices.size() * d * d);
+    if (b200_compute_marginals(_ctx, static_cast<int>(rows.size()), &rows[0], &cols[0], &out[0]) != B200_OK) {
+      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
+      return false;
+    }
+    // same layout as MarginalCovarianceCholesky::computeCovariance: uniform d x d blocks indexed by Hessian index
+    std::vector<int> blockEnds(dims[0]);
+    for (int i = 0; i < dims[0]; ++i) blockEnds[i] = (i + 1) * d;
+    spinv = SparseBlockMatrix<MatrixXd>(&blockEnds[0], &blockEnds[0], dims[0], dims[0], true);
+    for (size_t q = 0; q < blockIndices.size(); ++q) {
+      MatrixXd* blk = spinv.block(rows[q], cols[q], true);
+      *blk = Eigen::Map<const Eigen::MatrixXd>(&out[q * d * d], d, d);
+    }
+    return true;
+  }
   virtual bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) { return false; }
   virtual void printVerbose(std::ostream& os) const {
     os << "\t schur= " << (_hasLandmarks ? 1 : 0) << "\t lambda= " << FIXED(_lambda) << "\t levenbergIter= " << _levenbergIterations;

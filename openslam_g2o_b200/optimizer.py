@@ -137,6 +137,17 @@ class SolverContext:
             _check(rc, self._h)
         return rc, st
 
+    def compute_marginals(self, pairs):
+        """blocks (row, col) of Hpp^-1 -> array [len(pairs), d, d] (Solver::computeMarginals); after build_system()"""
+        rows = L.as_i32([p[0] for p in pairs])
+        cols = L.as_i32([p[1] for p in pairs])
+        d = self.dims()["poseDim"]
+        out = np.zeros((len(pairs), d, d))
+        rc = _check(lib.b200_compute_marginals(self._h, len(pairs), L.ptr(rows), L.ptr(cols), L.ptr(out)), self._h)
+        if rc != 0:
+            return None
+        return np.ascontiguousarray(np.transpose(out, (0, 2, 1)))  # column-major blocks -> [row, col]
+
     def set_ordering(self, nd_levels=0):
         """0: block AMD (the reference's ordering, default); k > 0: nested dissection with 2^k parts on top of it"""
         _check(lib.b200_set_ordering(self._h, int(nd_levels)), self._h)

@@ -255,6 +255,37 @@ def test_nested_dissection_ordering_matches_oracle(kind, nd):
 
 
 @needs_oracle
+@pytest.mark.parametrize("name", ["intel", "sphere_bignoise"])
+def test_marginals_match_dense_inverse_of_the_oracle_hessian(name):
+    """Solver::computeMarginals: selected blocks of Hpp^-1 from the GPU factor against the dense inverse of the
+    oracle's Hpp (what MarginalCovarianceCholesky evaluates block by block, marginal_covariance_cholesky.cpp:71-100)"""
+    opt, fx = _product_from_fixture(name)
+    o = _oracle_from_fixture(name)
+    opt._ensure_uploaded()
+    ctx = opt.context
+    assert ctx.build_structure() and o.build_structure()
+    ctx.compute_active_errors(); o.compute_active_errors()
+    ctx.build_system(); o.build_system()
+    rows, cols, vals = o.blocks(0)
+    d = vals.shape[1]
+    nb = int(max(cols)) + 1
+    A = np.zeros((nb * d, nb * d))
+    for r, c, v in zip(rows, cols, vals):
+        A[r * d:(r + 1) * d, c * d:(c + 1) * d] = v
+        A[c * d:(c + 1) * d, r * d:(r + 1) * d] = v.T
+    inv = np.linalg.inv(A)
+    rng = np.random.default_rng(4)
+    pairs = [(int(i), int(i)) for i in rng.choice(nb, 4, replace=False)] + \
+            [(int(rng.integers(nb)), int(rng.integers(nb))) for _ in range(3)] + [(0, nb - 1), (nb - 1, nb - 1)]
+    got = ctx.compute_marginals(pairs)
+    assert got is not None
+    scale = np.abs(inv).max()
+    for (r, c), blk in zip(pairs, got):
+        ref = inv[r * d:(r + 1) * d, c * d:(c + 1) * d]
+        assert np.abs(blk - ref).max() <= 1e-8 * scale, (r, c)
+
+
+@needs_oracle
 def test_pose_graph_edge_cases_match_oracle():
     """reversed edges (transposed-block path, block_solver.hpp:221-229), duplicate edges between the same pair,
     a fixed vertex in the middle, edges to the gauge"""
