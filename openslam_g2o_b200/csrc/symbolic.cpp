@@ -471,8 +471,6 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   }
   S.dinv_doubles = S.sn_dinvptr[ns];
   S.level_kind.assign(S.nlevels, 0);
-  S.level_smem.assign(S.nlevels, 0);
-  S.level_tile_ptr.assign(S.nlevels + 1, 0);
   S.level_chunk_ptr.assign(S.nlevels + 1, 0);
   S.level_group_ptr.assign(S.nlevels + 1, 0);
   S.level_rtile_ptr.assign(S.nlevels + 1, 0);
@@ -507,19 +505,15 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   }
   for (int l = 0; l < S.nlevels; ++l) {
     bool singletons = true;
-    int tiles = 0, chunks = 0, ntask = S.level_ptr[l + 1] - S.level_ptr[l], smem = 0;
+    int tiles = 0, chunks = 0, ntask = S.level_ptr[l + 1] - S.level_ptr[l];
     for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
       if (S.task_ptr[t + 1] - S.task_ptr[t] != 1) singletons = false;
       for (int q = S.task_ptr[t]; q < S.task_ptr[t + 1]; ++q) {
         const int J = S.task_sn[q];
         tiles += S.sn_tile_ptr[J + 1] - S.sn_tile_ptr[J];
         chunks += S.sn_chunk_ptr[J + 1] - S.sn_chunk_ptr[J];
-        const int N = S.sn_ncol[J] * d;
-        const int rows = N + std::min(S.sn_nrow[J] - S.sn_ncol[J], chunk_cap(J)) * d;
-        smem = std::max(smem, rows * N * 8);
       }
     }
-    S.level_smem[l] = smem;
     if (singletons && (tiles > ntask || chunks > ntask)) {
       S.level_kind[l] = 1;
       for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
@@ -527,7 +521,6 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         for (int q = S.sn_tile_ptr[J]; q < S.sn_tile_ptr[J + 1]; ++q) {
           const int w0 = S.tile_work_ptr[q], w1 = S.tile_work_ptr[q + 1];
           if (w1 == w0) continue;
-          S.level_tiles.push_back(q);
           const int ng = (w1 - w0 + S.group_items - 1) / S.group_items;
           S.sn_nupd[J]++;
           if (ng == 1) {
@@ -548,7 +541,6 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
       }
     }
     S.max_group_slots = slots;
-    S.level_tile_ptr[l + 1] = (int)S.level_tiles.size();
     S.level_chunk_ptr[l + 1] = (int)S.level_chunks.size();
     S.level_group_ptr[l + 1] = (int)S.group_tile.size();
     S.level_rtile_ptr[l + 1] = (int)S.rtile_tile.size();

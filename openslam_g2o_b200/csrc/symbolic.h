@@ -76,9 +76,10 @@ struct SymbolicFactor {
   int chunk_blocks = 0;
   std::vector<int> sn_chunk_ptr;                   // nsn+1
   std::vector<int> chunk_sn, chunk_b0, chunk_nb;   // supernode, first local block row (>= ncol), #block rows
-  // level plan: kind 0 = fused (one CTA per task does update + factor), 1 = split (tiles kernel, then chunks kernel)
-  std::vector<int> level_kind, level_smem;         // dynamic shared memory (bytes) the level's factor kernel needs
-  std::vector<int> level_tile_ptr, level_tiles, level_chunk_ptr, level_chunks;
+  // level plan (intermediate of the dataflow task list): kind 0 = subtree tasks (one CTA does update + factor of
+  // every supernode of the task), 1 = split (group tasks per tile, chunk tasks per panel)
+  std::vector<int> level_kind;
+  std::vector<int> level_chunk_ptr, level_chunks;
   // split-K groups of the split levels: a tile with many work items is cut into groups of <= group_items items;
   // each group is one CTA.  slot < 0: the tile has a single group and subtracts from the panel directly; otherwise
   // the group writes its partial 48x48 sum to scratch slot `slot` (numbered globally: levels overlap in the dataflow
