@@ -443,6 +443,25 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
       }
     }
   }
+  if (opt.sort_items_by_level) {
+    // inside a tile: items whose source supernode completes early first (ascending task level, then ascending
+    // supernode), so that a group never waits for a late descendant while early ones are ready.  The order is part of
+    // the plan: sums stay deterministic.
+    std::vector<int> idx, tmp;
+    auto lvl = [&](int q) { return tlevel[task_of[S.upd_k[S.work_u[q]]]]; };
+    for (int t = 0; t < ntiles; ++t) {
+      const int w0 = S.tile_work_ptr[t], w1 = S.tile_work_ptr[t + 1];
+      if (w1 - w0 < 2) continue;
+      idx.resize(w1 - w0);
+      for (int q = w0; q < w1; ++q) idx[q - w0] = q;
+      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lvl(x) < lvl(y); });
+      for (std::vector<int>* arr : {&S.work_u, &S.work_a0, &S.work_a1, &S.work_b0, &S.work_b1}) {
+        tmp.resize(w1 - w0);
+        for (int q = 0; q < w1 - w0; ++q) tmp[q] = (*arr)[idx[q]];
+        std::copy(tmp.begin(), tmp.end(), arr->begin() + w0);
+      }
+    }
+  }
   {
     const int nw = (int)S.work_u.size();
     S.work_koff.resize(nw); S.work_reloff.resize(nw); S.work_mk.resize(nw); S.work_nk.resize(nw); S.work_ksn.resize(nw);
