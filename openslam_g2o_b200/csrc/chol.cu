@@ -94,7 +94,7 @@ struct CholFlowDev {
   double* scratch;
 };
 
-constexpr unsigned kSpinLimit = 1u << 24;  // several seconds of polling
+constexpr unsigned kSpinLimit = 1u << 28;  // minutes of polling: far beyond any factorisation that fits the device
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
