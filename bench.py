@@ -320,6 +320,17 @@ def run_b200(args, rank, world):
               "e2e": args.steps / (ms_nd_e2e * 1e-3), "unit": "iterations/s",
               "levels": info_nd["levels"], "factor_doubles": info_nd["factor_doubles"]}
 
+    if rank == 0 and roof is not None and phases.get("chol_factor_flow", (0, 0))[1] > 0:
+        # the kernel that dominates the step by TIME is the sparse factorisation: neither HBM- nor FLOP-bound but
+        # bound by the latency of its dependency chain - reported for completeness
+        f_s = phases["chol_factor_flow"][0] / phases["chol_factor_flow"][1]
+        roof["dominant_by_time"] = {"kernel": "chol_factor_flow_kernel", "avg_launch_ms": 1e3 * f_s,
+                                    "share_of_step": f_s / (ms_total * 1e-3 / args.steps),
+                                    "bound": "latency of the elimination-tree dependency chain (levels: %d)" % info["levels"],
+                                    "fp64_flops_per_launch": info["factor_flops"],
+                                    "achieved_tflops": info["factor_flops"] / f_s / 1e12,
+                                    "fp64_peak_tflops_nominal": 40.0}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.workload, prob)

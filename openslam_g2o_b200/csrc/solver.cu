@@ -1284,6 +1284,7 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
   const SymbolicFactor& S = c->chol.symbolic();
   out[0] = S.nsn; out[1] = (int64_t)S.task_ptr.size() - 1; out[2] = S.nlevels; out[3] = S.max_nrow; out[4] = S.max_ncol; out[5] = S.factor_doubles;
   out[6] = (int64_t)S.flow_kind.size();
+  out[12] = (int64_t)S.flops;
   out[7] = c->sr_n; out[8] = c->sr_nseg; out[9] = c->sr_ncontrib; out[10] = c->n_hpl; out[11] = c->sr_n > 0 ? (int64_t)schur_range_smem(c) : 0;
   return B200_OK;
 }

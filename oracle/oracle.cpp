@@ -27,6 +27,7 @@
 #include <string>
 #include <time.h>
 #include <tr1/unordered_map>
+#include <functional>
 #include <vector>
 
 #ifndef NCOMPLEX
@@ -37,6 +38,7 @@
 // solvers/csparse/csparse_helper.h:41-42 (compiled from the reference into libg2o_csparse_ref.so)
 namespace g2o { namespace csparse_extension {
 int cs_cholsolsymb(const cs* A, double* b, const css* S, double* workspace, int* work);
+csn* cs_chol_workspace(const cs* A, const css* S, int* cin, double* xin);  // csparse_helper.h:37
 } }
 
 namespace {
@@ -747,6 +749,59 @@ struct LinearSolverCSparseO {
     timeNumeric = now() - t;
     return ok != 0;
   }
+
+  // linear_solver_csparse.h:190-225 solvePattern + core/marginal_covariance_cholesky.cpp:55-100, 152-214:
+  // numeric factor through cs_chol_workspace, then the recursive sparse-inverse formula with a memo
+  // (std::map stands in for the reference's unordered_map: same values, no iteration-order dependence)
+  bool solvePattern(const SBM& M, int nblocks, const int* brow, const int* bcol, double* out) {
+    fill(M, S != nullptr);
+    if (!S) computeSymbolic(M);
+    if (!S) return false;
+    const int n = A.n, d = M.cdim;
+    if ((int)work.size() < n) { work.assign(2 * n, 0); iwork.assign(4 * n, 0); }
+    csn* N = g2o::csparse_extension::cs_chol_workspace(&A, S, iwork.data(), work.data());
+    if (!N) return false;
+    const int* Lp = N->L->p; const int* Li = N->L->i; const double* Lx = N->L->x;
+    const int* perm = S->pinv;
+    std::vector<double> diag(n);
+    for (int r = 0; r < n; ++r) diag[r] = 1.0 / Lx[Lp[r]];  // :63-68
+    std::map<long long, double> memo;
+    std::function<double(int, int)> entry = [&](int r, int c) -> double {  // computeEntry :71-100 (r <= c)
+      const long long idx = (long long)r * n + c;
+      auto it = memo.find(idx);
+      if (it != memo.end()) return it->second;
+      double s = 0.;
+      for (int j = Lp[r] + 1; j < Lp[r + 1]; ++j) {
+        const int rr = Li[j];
+        const double val = rr < c ? entry(rr, c) : entry(c, rr);
+        s += val * Lx[j];
+      }
+      const double result = r == c ? diag[r] * (diag[r] - s) : -s * diag[r];
+      memo[idx] = result;
+      return result;
+    };
+    struct Elem { int r, c; };
+    std::vector<Elem> todo;
+    for (int q = 0; q < nblocks; ++q)
+      for (int ir = 0; ir < d; ++ir)
+        for (int ic = 0; ic < d; ++ic) {
+          int r = perm[brow[q] * d + ir], c = perm[bcol[q] * d + ic];
+          if (r > c) std::swap(r, c);
+          todo.push_back({r, c});
+        }
+    // sort the elems to reduce the recursive calls (:39-43: descending column, then descending row)
+    std::sort(todo.begin(), todo.end(), [](const Elem& a2, const Elem& b2) { return a2.c > b2.c || (a2.c == b2.c && a2.r > b2.r); });
+    for (const Elem& e : todo) entry(e.r, e.c);
+    for (int q = 0; q < nblocks; ++q)
+      for (int ir = 0; ir < d; ++ir)
+        for (int ic = 0; ic < d; ++ic) {
+          int r = perm[brow[q] * d + ir], c = perm[bcol[q] * d + ic];
+          if (r > c) std::swap(r, c);
+          out[(size_t)q * d * d + ir + (size_t)ic * d] = memo[(long long)r * n + c];  // column-major block
+        }
+    cs_nfree(N);
+    return true;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1372,6 +1427,10 @@ int oracle_setup_cli(oracle_graph* g, int requires_marginalize) {
   return ret;
 }
 int oracle_initialize(oracle_graph* g) { return initialize_optimization(g) ? 0 : -1; }
+// Solver::computeMarginals (core/block_solver.hpp:490-499): blocks of Hpp^-1, column-major d x d each
+int oracle_compute_marginals(oracle_graph* g, int nblocks, const int* rows, const int* cols, double* out) {
+  return g->linearSolver.solvePattern(g->Hpp, nblocks, rows, cols, out) ? 0 : -1;
+}
 void oracle_robustify(int kind, double delta, double e2, double* rho3) { robustify(kind, delta, e2, rho3); }
 // apps/g2o_cli/g2o.cpp:322-336: one kernel of the given width on every edge
 int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta) {

@@ -64,7 +64,10 @@ void oracle_set_block_ordering(oracle_graph* g, int block_ordering);
 /* one robust kernel on every edge (apps/g2o_cli/g2o.cpp:322-336; core/robust_kernel_impl.cpp:65-126):
  * kind 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS */
 int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta);
-void oracle_robustify(int kind, double delta, double e2, double* rho3);  /* rho, rho', rho'' */
+void oracle_robustify(int kind, double delta, double e2, double* rho3);
+/* Solver::computeMarginals -> LinearSolverCSparse::solvePattern -> MarginalCovarianceCholesky: blocks (rows[q], cols[q])
+ * of Hpp^-1 (after oracle_build_system), column-major d x d each */
+int oracle_compute_marginals(oracle_graph* g, int nblocks, const int* rows, const int* cols, double* out);  /* rho, rho', rho'' */
 
 /* SparseOptimizer::optimize (core/sparse_optimizer.cpp:354-419); returns #iterations done (0 on Fail) */
 int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_stats* stats);

@@ -91,6 +91,16 @@ class Oracle:
     def initialize_optimization(self):
         return self.L.oracle_initialize(self.g) == 0
 
+    def compute_marginals(self, pairs):
+        rows = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int32)
+        cols = np.ascontiguousarray([p[1] for p in pairs], dtype=np.int32)
+        d = self.dims()["poseDim"]
+        out = np.zeros((len(pairs), d, d))
+        self.L.oracle_compute_marginals.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        if self.L.oracle_compute_marginals(self.g, len(pairs), _p(rows), _p(cols), _p(out)) != 0:
+            return None
+        return np.ascontiguousarray(np.transpose(out, (0, 2, 1)))
+
     def set_robust_kernel(self, name, width=1.0):
         kinds = {"none": 0, "Huber": 1, "PseudoHuber": 2, "Cauchy": 3, "Saturated": 4, "DCS": 5}
         self.L.oracle_set_robust_kernel.argtypes = [C.c_void_p, C.c_int, C.c_double]

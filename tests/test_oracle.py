@@ -97,3 +97,30 @@ def test_oracle_jacobians_match_numeric_differences():
         g /= 2 * delta
         assert abs(-0.5 * g - b[k]) <= 1e-5 * max(1.0, abs(b[k])), (k, g, b[k])
     assert chi0 > 0
+
+
+def test_marginal_covariance_recursion_matches_dense_inverse():
+    """oracle restatement of LinearSolverCSparse::solvePattern + MarginalCovarianceCholesky (the reference's sparse
+    inverse recursion on the real CSparse factor) against the dense inverse of the same Hpp"""
+    from helpers import load_fixture, feed_fixture
+    from oracle_binding import Oracle
+    for name in ("intel",):  # the recursion memoises O(nnz(L)) entries: seconds on intel, minutes on the sphere
+        fx = load_fixture(name)
+        o = Oracle()
+        feed_fixture(o, fx)
+        o.setup_cli(True); o.initialize_optimization(); o.algorithm_init()
+        assert o.build_structure()
+        o.compute_active_errors(); o.build_system()
+        rows, cols, vals = o.blocks(0)
+        d = vals.shape[1]
+        nb = int(max(cols)) + 1
+        A = np.zeros((nb * d, nb * d))
+        for r, c, v in zip(rows, cols, vals):
+            A[r * d:(r + 1) * d, c * d:(c + 1) * d] = v
+            A[c * d:(c + 1) * d, r * d:(r + 1) * d] = v.T
+        inv = np.linalg.inv(A)
+        pairs = [(0, 0), (3, 3), (2, 5), (nb - 1, nb - 1), (0, nb - 1), (7, 2)]
+        got = o.compute_marginals(pairs)
+        assert got is not None
+        for (r, c), blk in zip(pairs, got):
+            assert np.abs(blk - inv[r * d:(r + 1) * d, c * d:(c + 1) * d]).max() <= 1e-8 * np.abs(inv).max()
