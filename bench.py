@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 RESTART = 10  # LM iterations per optimisation run (the reference protocol: g2o -i 10)
-ND_LEVELS = {"venice": 5, "ba10k": 7, "sphere2500": 3, "sphere40k": 3}  # dissection depth of the extra measurement
+ND_LEVELS = {"venice": 5, "ba10k": 7, "sphere2500": 7, "sphere40k": 7}  # dissection depth of the extra measurement
 
 
 def parse():
