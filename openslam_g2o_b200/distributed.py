@@ -20,9 +20,13 @@ def make_allreduce(ctx, local_rank):
     device = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
+    views = {}  # (ptr, count) -> tensor view: the library reduces the same few device buffers every iteration
+
     def allreduce(ptr, count, op, _stream, _user):
         try:
-            t = torch.as_tensor(_DevicePointer(ptr, count), device=device)
+            t = views.get((ptr, count))
+            if t is None:
+                t = views[(ptr, count)] = torch.as_tensor(_DevicePointer(ptr, count), device=device)
             with torch.cuda.stream(stream):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
             return 0
