@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--workload", default="venice", choices=["venice", "sphere2500", "venice_small", "ba10k", "sphere40k"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parallel-ordering", action="store_true", help="skip the extra nested-dissection measurement")
     ap.add_argument("--nd-levels", type=int, default=0,
                     help="ordering of the reduced system: 0 = block AMD (reference, default); k = nested dissection, 2^k parts")
     return ap.parse_args()
@@ -308,7 +309,7 @@ def run_b200(args, rank, world):
     # ---- the same workload with the optional ordering for parallelism (nested dissection on top of AMD): reported
     # beside the headline, which keeps the reference's AMD ordering
     nd = None
-    if not args.nd_levels and args.workload in ND_LEVELS:
+    if not args.nd_levels and not args.no_parallel_ordering and args.workload in ND_LEVELS:
         ctx.set_ordering(ND_LEVELS[args.workload])
         assert ctx.build_structure()
         restart()
