@@ -69,3 +69,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in txt and "oracle_binding" not in txt and "oracle/" not in txt.replace("the oracle/", ""), (dirpath, f)
+
+
+def test_committed_bench_line_follows_the_contract():
+    """the bench line committed under profiles/ carries every key the measurement contract names"""
+    import glob
+    import json
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_venice_stage*.json")),
+                   key=lambda f: int(re.search(r"stage(\d+)", f).group(1)))
+    assert files
+    d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["dtype"] == "f64" and d["vs_baseline"] is None and "workload" in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    c = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
