@@ -496,6 +496,7 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_RELAX")) opt.relax = atoi(e) != 0;
   if (const char* e = getenv("G2O_B200_GROUP_ITEMS")) opt.group_items = std::max(1, atoi(e));
   if (const char* e = getenv("G2O_B200_SORT_ITEMS")) opt.sort_items_by_level = atoi(e) != 0;
+  if (const char* e = getenv("G2O_B200_RELAX_FRAC")) opt.relax_frac = atof(e);
   opt.nd_levels = c->nd_levels;
   if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);

@@ -147,7 +147,10 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
       int mc = nc[s] + nc[p];
       double total = (double)mc * (nc[s] + nr[p]) - 0.5 * (double)mc * (mc - 1);
       double frac = z / std::max(total, 1.0);
-      bool ok = (mc * d <= 12) || (mc * d <= 48 && frac < 0.6) || (mc * d <= 96 && frac < 0.25) || frac < 0.05;
+      // amalgamation stops at the panel width: a merged supernode wider than one panel would be cut into equal
+      // pieces again (16 block columns -> 8 + 8), i.e. more and narrower panels on the critical path than 12 + ...
+      const int cap = std::max(1, std::min(opt.max_panel_cols_scalar / d, 12)) * d;
+      bool ok = (mc * d <= 12) || (mc * d <= 48 && mc * d <= cap && frac < 0.6) || (mc * d <= cap && frac < opt.relax_frac) || frac < 0.05;
       if (!ok) continue;
       // merge s into p (p keeps its index; its first column moves down)
       first[p] = first[s];

@@ -19,6 +19,7 @@ struct SymbolicOptions {
   double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
   double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
   bool relax = true;
+  double relax_frac = 0.25;         // relaxed amalgamation: accepted share of explicit zeros up to one panel width
   bool sort_items_by_level = true;  // tile work items ordered by the task level of their source supernode
   int group_items = 16;             // split-K: work items per group task (4 / 8 / 16 measured: 16 best with level-sorted items)
   // 0 (default): the reference's ordering - block AMD, bit-exact with cs_amd.  k > 0: nested dissection with 2^k parts

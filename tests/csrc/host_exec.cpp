@@ -12,7 +12,9 @@
 using namespace g2o_b200;
 
 static int g_nd_levels = 0;
+static double g_relax_frac = 0.25;
 extern "C" void hx_set_nd_levels(int k) { g_nd_levels = k; }
+extern "C" void hx_set_relax_frac(double f) { g_relax_frac = f; }
 extern "C" int hx_block_amd(int n, const int* cp, const int* ri, int* perm) {
   auto p = block_amd(n, cp, ri);
   memcpy(perm, p.data(), n * sizeof(int));
@@ -21,7 +23,7 @@ extern "C" int hx_block_amd(int n, const int* cp, const int* ri, int* perm) {
 
 // info[0]=nsn info[1]=ntasks info[2]=nlevels info[3]=scalar_lnz info[4]=factor_doubles info[5]=max_nrow info[6]=max_ncol
 extern "C" int hx_analyze(int nb, int d, const int* cp, const int* ri, int max_cols, int relax, long long* info, int* perm_out) {
-  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4;
+  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
   info[0] = S.nsn; info[1] = (long long)S.task_ptr.size() - 1; info[2] = S.nlevels; info[3] = S.scalar_lnz;
   info[4] = S.factor_doubles; info[5] = S.max_nrow; info[6] = S.max_ncol; info[7] = (long long)S.flops;
@@ -31,7 +33,7 @@ extern "C" int hx_analyze(int nb, int d, const int* cp, const int* ri, int max_c
 
 extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const double* vals, double lambda,
                         const double* b, double* x, int max_cols, int relax) {
-  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4;
+  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
   std::vector<double> L(S.factor_doubles, 0.0);
   const int nblk = cp[nb];
@@ -165,7 +167,7 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
 // complete (dependencies only point backwards - the no-deadlock argument of chol.cu), every group / chunk must appear
 // exactly once, every split tile must be completed by exactly one last group, and the completion targets (sn_nupd, sn_nchunk) must be reached exactly.
 extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int max_cols, int relax, int group_items) {
-  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.group_items = group_items;
+  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac; o.group_items = group_items;
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
   const int nt = (int)S.task_ptr.size() - 1;
   std::vector<int> upd(S.nsn, 0), chunk(S.nsn, 0), slot(S.rtile_tile.size(), 0);
