@@ -13,7 +13,9 @@
  *                     SE3: [R(3x3 col-major) t(3)] = Isometry3d     (types/slam3d/vertex_se3.h, state is R|t)
  *                     CAM: [t(3) q(x y z w) fx fy cx cy baseline]   (types/sba/sbacam.h:60-98)
  *                     XYZ: [x y z]                                  (types/sba/types_sba.h:136-156)
- *   edge measurement  SE2: [x y theta] of Z; SE3: [R t] of Z (12); P2MC: [u v]
+ *                     SE3_EXPMAP: [t(3) q(x y z w) f f cx cy baseline]  world->camera SE3Quat (types/sba/
+ *                          types_six_dof_expmap.h:87-105) + the CameraParameters its edges name (:45-80)
+ *   edge measurement  SE2: [x y theta] of Z; SE3: [R t] of Z (12); P2MC, XYZ2UV: [u v]
  *   edge information  full D x D column-major (D = 3, 6, 2)
  */
 #ifndef G2O_B200_H
@@ -31,8 +33,11 @@ extern "C" {
 #define B200_ERR_UNSUPPORTED (-4)      /* graph uses types outside {SE2,SE3,CAM,XYZ}: no CPU fallback */
 #define B200_ERR_COLLECTIVE (-5)
 
-enum { B200_VERTEX_SE2 = 0, B200_VERTEX_SE3 = 1, B200_VERTEX_CAM = 2, B200_VERTEX_XYZ = 3 };
-enum { B200_EDGE_SE2 = 0, B200_EDGE_SE3 = 1, B200_EDGE_P2MC = 2 };
+enum { B200_VERTEX_SE2 = 0, B200_VERTEX_SE3 = 1, B200_VERTEX_CAM = 2, B200_VERTEX_XYZ = 3, B200_VERTEX_SE3_EXPMAP = 4 };
+/* XYZ2UV = EdgeProjectXYZ2UV (types/sba/types_six_dof_expmap.h:133-155), the monocular edge of ba_demo / SE3 expmap BA */
+enum { B200_EDGE_SE2 = 0, B200_EDGE_SE3 = 1, B200_EDGE_P2MC = 2, B200_EDGE_XYZ2UV = 3 };
+#define B200_NUM_VERTEX_KINDS 5
+#define B200_NUM_EDGE_KINDS 4
 enum { B200_GAUSS_NEWTON = 0, B200_LEVENBERG = 1 };
 /* OptimizationAlgorithm::SolverResult (core/optimization_algorithm.h:49) */
 enum { B200_RESULT_TERMINATE = 2, B200_RESULT_OK = 1, B200_RESULT_FAIL = -1 };
@@ -71,7 +76,8 @@ const char* b200_version(void);
 int b200_set_vertices(b200_ctx* ctx, int kind, int n, const double* estimates,
                       const int32_t* hessian_index, const uint8_t* marginalized);
 /* vi/vj index into the vertex array of the kind the edge type expects
- * (SE2: SE2,SE2; SE3: SE3,SE3; P2MC: vi = XYZ point, vj = CAM).  Order = active edge order (internalId). */
+ * (SE2: SE2,SE2; SE3: SE3,SE3; P2MC: vi = XYZ point, vj = CAM; XYZ2UV: vi = XYZ point, vj = SE3_EXPMAP).
+ * Order = active edge order (internalId). */
 int b200_set_edges(b200_ctx* ctx, int kind, int n, const int32_t* vi, const int32_t* vj,
                    const double* measurement, const double* information);
 /* landmark sharding: this context owns the landmarks / edges it was given; cameras are
@@ -206,10 +212,14 @@ int b200_graph_add_edge(b200_graph* g, int kind, int id1, int id2, const double*
 int b200_graph_add_vertices(b200_graph* g, int kind, int n, const int32_t* ids, const double* payload, int stride);
 int b200_graph_add_edges(b200_graph* g, int kind, int n, const int32_t* id1, const int32_t* id2, const double* payload, int stride);
 int b200_graph_set_fixed(b200_graph* g, int id, int fixed);
+/* PARAMS_CAMERAPARAMETERS id focal_length cx cy baseline (types/sba/types_six_dof_expmap.h:45-80); has to precede the
+ * XYZ2UV edges that name it (payload of such an edge: paramId u v i00 i01 i11, types_six_dof_expmap.cpp:241-256).
+ * All edges of one pose must name parameters with equal values (the intrinsics ride in the pose's estimate row). */
+int b200_graph_add_camera_parameters(b200_graph* g, int id, double focal_length, double cx, double cy, double baseline);
 /* returns the gauge vertex id fixed (or -1 if none needed) */
 int b200_graph_setup_cli(b200_graph* g, int requires_marginalize);
 int b200_graph_initialize(b200_graph* g);
-/* counts[4] = #vertices by kind; edge_counts[3] */
+/* vertex_counts[B200_NUM_VERTEX_KINDS] = #vertices by kind; edge_counts[B200_NUM_EDGE_KINDS] */
 int b200_graph_counts(b200_graph* g, int32_t* vertex_counts, int32_t* edge_counts);
 /* upload to a context.  shard/num_shards: landmark sharding (0,1 = everything) */
 int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards);

@@ -15,15 +15,16 @@ LIB_PATH = os.environ.get("G2O_B200_LIB", os.path.join(_HERE, "libg2o_b200.so"))
 OK = 0
 NOT_POSITIVE_DEFINITE = 1
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_COLLECTIVE = -1, -2, -3, -4, -5
-VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ = 0, 1, 2, 3
-EDGE_SE2, EDGE_SE3, EDGE_P2MC = 0, 1, 2
+VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP = 0, 1, 2, 3, 4
+EDGE_SE2, EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV = 0, 1, 2, 3
+NUM_VERTEX_KINDS, NUM_EDGE_KINDS = 5, 4
 GAUSS_NEWTON, LEVENBERG = 0, 1
 RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1
 
-VERTEX_EST_LEN = {VERTEX_SE2: 3, VERTEX_SE3: 12, VERTEX_CAM: 12, VERTEX_XYZ: 3}
-VERTEX_DIM = {VERTEX_SE2: 3, VERTEX_SE3: 6, VERTEX_CAM: 6, VERTEX_XYZ: 3}
-EDGE_DIM = {EDGE_SE2: 3, EDGE_SE3: 6, EDGE_P2MC: 2}
-EDGE_MEAS_LEN = {EDGE_SE2: 3, EDGE_SE3: 12, EDGE_P2MC: 2}
+VERTEX_EST_LEN = {VERTEX_SE2: 3, VERTEX_SE3: 12, VERTEX_CAM: 12, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 12}
+VERTEX_DIM = {VERTEX_SE2: 3, VERTEX_SE3: 6, VERTEX_CAM: 6, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 6}
+EDGE_DIM = {EDGE_SE2: 3, EDGE_SE3: 6, EDGE_P2MC: 2, EDGE_XYZ2UV: 2}
+EDGE_MEAS_LEN = {EDGE_SE2: 3, EDGE_SE3: 12, EDGE_P2MC: 2, EDGE_XYZ2UV: 2}
 
 
 class IterStats(C.Structure):
@@ -109,6 +110,7 @@ def _load():
         "b200_graph_add_vertices": (i32, [vp, i32, i32, vp, vp, i32]),
         "b200_graph_add_edges": (i32, [vp, i32, i32, vp, vp, vp, i32]),
         "b200_graph_set_fixed": (i32, [vp, i32, i32]),
+        "b200_graph_add_camera_parameters": (i32, [vp, i32, dbl, dbl, dbl, dbl]),
         "b200_graph_setup_cli": (i32, [vp, i32]),
         "b200_graph_initialize": (i32, [vp]),
         "b200_graph_counts": (i32, [vp, vp, vp]),

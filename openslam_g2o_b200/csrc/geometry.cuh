@@ -376,6 +376,122 @@ G2O_HD void cam_oplus(double* est, const double* u) {
   est[3] = rx / n; est[4] = ry / n; est[5] = rz / n; est[6] = rw / n;
 }
 
+// ------------------------------------------------------------------ expmap camera (types/sba/types_six_dof_expmap, SE3Quat)
+// estimate per pose: t3 | q(xyzw)4 (world -> camera, SE3Quat) | f f cx cy baseline (the CameraParameters of its edges)
+// derived block: [R(q) | t] (3x4 col-major, 12) | f f cx cy - the same shape as the SBACam block (w2n | K), so both
+// camera models run through the same kernels.
+G2O_HD void expmap_derive(const double* est, double* der /*16*/) {
+  quat_to_R(est + 3, der);
+  der[9] = est[0]; der[10] = est[1]; der[11] = est[2];
+  der[12] = est[7]; der[13] = est[8]; der[14] = est[9]; der[15] = est[10];
+}
+// EdgeProjectXYZ2UV::computeError (types_six_dof_expmap.h:143-150): e = obs - cam_map(T.map(X)),
+// cam_map (types_six_dof_expmap.cpp:65-71): proj * focal_length + principle_point
+G2O_HD void xyz2uv_error(const double* der, const double* X, const double* z, double* e) {
+  double p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) p[r] = der[r] * X[0] + der[r + 3] * X[1] + der[r + 6] * X[2] + der[r + 9];
+  e[0] = z[0] - (p[0] / p[2] * der[12] + der[14]);
+  e[1] = z[1] - (p[1] / p[2] * der[13] + der[15]);
+}
+// EdgeProjectXYZ2UV::linearizeOplus (types_six_dof_expmap.cpp:288-326): Jp 2x3 (point), Jc 2x6 (pose: omega, upsilon)
+G2O_HD void xyz2uv_jacobians(const double* der, const double* X, double* Jp, double* Jc) {
+  double p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) p[r] = der[r] * X[0] + der[r + 3] * X[1] + der[r + 6] * X[2] + der[r + 9];
+  const double x = p[0], y = p[1], z = p[2], z_2 = z * z, f = der[12];
+  const double t02 = -x / z * f, t12 = -y / z * f, miz = -1. / z;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // -1/z * tmp * R,  tmp = [f 0 -x/z f ; 0 f -y/z f]
+    Jp[0 + 2 * c] = miz * (f * der[0 + 3 * c] + t02 * der[2 + 3 * c]);
+    Jp[1 + 2 * c] = miz * (f * der[1 + 3 * c] + t12 * der[2 + 3 * c]);
+  }
+  Jc[0] = x * y / z_2 * f;          Jc[1] = (1 + y * y / z_2) * f;
+  Jc[2] = -(1 + (x * x / z_2)) * f; Jc[3] = -x * y / z_2 * f;
+  Jc[4] = y / z * f;                Jc[5] = -x / z * f;
+  Jc[6] = miz * f;                  Jc[7] = 0;
+  Jc[8] = 0;                        Jc[9] = miz * f;
+  Jc[10] = x / z_2 * f;             Jc[11] = y / z_2 * f;
+}
+// Eigen Quaterniond(Matrix3d) (same branches as iso_to_vector_mqt above, without the normalisation)
+G2O_HD void R_to_quat(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[5] - R[7]) * t;
+    q[1] = (R[6] - R[2]) * t;
+    q[2] = (R[1] - R[3]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i + 3 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[i + 3 * i] - R[j + 3 * j] - R[k + 3 * k] + 1.0);
+    double qq[4];
+    qq[i] = 0.5 * t;
+    t = 0.5 / t;
+    qq[3] = (R[k + 3 * j] - R[j + 3 * k]) * t;
+    qq[j] = (R[j + 3 * i] + R[i + 3 * j]) * t;
+    qq[k] = (R[k + 3 * i] + R[i + 3 * k]) * t;
+    q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+  }
+}
+// VertexSE3Expmap::oplusImpl (types_six_dof_expmap.h:101-104): estimate <- SE3Quat::exp(update) * estimate;
+// exp: se3quat.h:216-252 (update = [omega ; upsilon]); product + normalizeRotation: se3quat.h:103-109, 280-285
+G2O_HD void expmap_oplus(double* est, const double* u) {
+  const double ox = u[0], oy = u[1], oz = u[2];
+  const double theta = sqrt(ox * ox + oy * oy + oz * oz);
+  const double Om[9] = {0, oz, -oy, -oz, 0, ox, oy, -ox, 0};  // skew(omega), col-major
+  double Om2[9], R[9], V[9];
+  mm<3, 3, 3>(Om, Om, Om2);
+  double a, b, c;
+  if (theta < 0.00001) { a = 1; b = 1; c = 1; }
+  else {
+    const double sn = sin(theta), cs = cos(theta);
+    a = sn / theta; b = (1 - cs) / (theta * theta); c = (theta - sn) / (theta * theta * theta);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
+    R[i] = I + a * Om[i] + b * Om2[i];
+    V[i] = (theta < 0.00001) ? R[i] : I + b * Om[i] + c * Om2[i];
+  }
+  double qe[4], te[3];
+  R_to_quat(R, qe);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) te[r] = V[r] * u[3] + V[r + 3] * u[4] + V[r + 6] * u[5];
+  if (qe[3] < 0) { qe[0] = -qe[0]; qe[1] = -qe[1]; qe[2] = -qe[2]; qe[3] = -qe[3]; }
+  double n = sqrt(qe[0] * qe[0] + qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3]);
+  qe[0] /= n; qe[1] /= n; qe[2] /= n; qe[3] /= n;
+  // t <- te + qe * t (Eigen quaternion * vector: v + w uv + qv x uv, uv = 2 qv x v)
+  const double vx = est[0], vy = est[1], vz = est[2];
+  double ux = qe[1] * vz - qe[2] * vy, uy = qe[2] * vx - qe[0] * vz, uz = qe[0] * vy - qe[1] * vx;
+  ux += ux; uy += uy; uz += uz;
+  est[0] = te[0] + (vx + qe[3] * ux + (qe[1] * uz - qe[2] * uy));
+  est[1] = te[1] + (vy + qe[3] * uy + (qe[2] * ux - qe[0] * uz));
+  est[2] = te[2] + (vz + qe[3] * uz + (qe[0] * uy - qe[1] * ux));
+  // q <- qe * q, normalizeRotation
+  const double bx = est[3], by = est[4], bz = est[5], bw = est[6];
+  double rw = qe[3] * bw - qe[0] * bx - qe[1] * by - qe[2] * bz;
+  double rx = qe[3] * bx + qe[0] * bw + qe[1] * bz - qe[2] * by;
+  double ry = qe[3] * by + qe[1] * bw + qe[2] * bx - qe[0] * bz;
+  double rz = qe[3] * bz + qe[2] * bw + qe[0] * by - qe[1] * bx;
+  if (rw < 0) { rx = -rx; ry = -ry; rz = -rz; rw = -rw; }
+  n = sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+  est[3] = rx / n; est[4] = ry / n; est[5] = rz / n; est[6] = rw / n;
+}
+// the two camera models behind one call (MODEL 0: SBACam / P2MC, 1: SE3 expmap / XYZ2UV)
+template <int MODEL> G2O_HD void ba_derive(const double* est, double* der) { if (MODEL == 0) cam_derive(est, der); else expmap_derive(est, der); }
+template <int MODEL> G2O_HD void ba_error(const double* der, const double* X, const double* z, double* e) {
+  if (MODEL == 0) p2mc_error(der, X, z, e); else xyz2uv_error(der, X, z, e);
+}
+template <int MODEL> G2O_HD void ba_jacobians(const double* der, const double* cam_t, const double* X, double* Jp, double* Jc) {
+  if (MODEL == 0) p2mc_jacobians(der, cam_t, X, Jp, Jc); else xyz2uv_jacobians(der, X, Jp, Jc);
+}
+template <int MODEL> G2O_HD void ba_oplus(double* est, const double* u) { if (MODEL == 0) cam_oplus(est, u); else expmap_oplus(est, u); }
+
 // Eigen fixed-size 3x3 inverse (cofactors / determinant), used at block_solver.hpp:389
 G2O_HD void inverse3(const double* m, double* r) {
 #define M_(i, j) m[(i) + 3 * (j)]

@@ -10,10 +10,12 @@
 //   OptimizableGraph::save                      core/optimizable_graph.cpp:589-622
 // Host-only, pointer-free after load; everything numeric per iteration happens behind b200_ctx.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <tr1/unordered_map>
 #include <vector>
@@ -32,6 +34,7 @@ struct HVertex {
   double est[12];
 };
 struct HEdge {
+  int param = -1;  // XYZ2UV: id of its CameraParameters
   int kind = 0;
   int v0 = 0, v1 = 0;  // indices into vertices
   bool active = false;
@@ -42,6 +45,18 @@ int vdim(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ)
 int vest(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12; }
 int edim(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
 int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
+bool is_ba(int ekind) { return ekind == B200_EDGE_P2MC || ekind == B200_EDGE_XYZ2UV; }
+// SE3Quat::inverse (types/slam3d/se3quat.h:125-130) on [t3 | q(xyzw)4]: r = conj(q), t = r * (-t) with Eigen's
+// quaternion * vector (v + w uv + qv x uv, uv = 2 qv x v); no normalisation
+void se3quat_inverse(const double* a, double* r) {
+  const double q[4] = {-a[3], -a[4], -a[5], a[6]};
+  const double v[3] = {a[0] * -1., a[1] * -1., a[2] * -1.};
+  double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+  for (double& d : uv) d += d;
+  const double c[3] = {q[1] * uv[2] - q[2] * uv[1], q[2] * uv[0] - q[0] * uv[2], q[0] * uv[1] - q[1] * uv[0]};
+  for (int i = 0; i < 3; ++i) r[i] = v[i] + q[3] * uv[i] + c[i];
+  for (int i = 0; i < 4; ++i) r[3 + i] = q[i];
+}
 
 void quat_normalize(double* q) {
   double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
@@ -71,7 +86,8 @@ struct b200_graph {
   std::vector<HVertex> vertices;
   std::vector<HEdge> edges;
   std::vector<int> active_edges;            // edge indices, internalId order
-  std::vector<int> kind_slots[4];           // per kind: vertex indices handed to the context (ascending id)
+  std::vector<int> kind_slots[B200_NUM_VERTEX_KINDS];  // per kind: vertex indices handed to the context (ascending id)
+  std::map<int, std::array<double, 4>> camera_parameters;  // PARAMS_CAMERAPARAMETERS id -> f cx cy baseline
   std::string err;
   int find(int id) const { auto it = idmap.find(id); return it == idmap.end() ? -1 : it->second; }
 };
@@ -91,6 +107,7 @@ void set_to_origin(HVertex& v) {
   for (double& d : v.est) d = 0;
   if (v.kind == B200_VERTEX_SE3) v.est[0] = v.est[4] = v.est[8] = 1;
   if (v.kind == B200_VERTEX_CAM) { v.est[6] = 1; v.est[7] = 1; v.est[8] = 1; v.est[9] = 0.5; v.est[10] = 0.5; }
+  if (v.kind == B200_VERTEX_SE3_EXPMAP) v.est[6] = 1;  // SE3Quat(); intrinsics arrive with the first edge
 }
 bool vertex_read(HVertex& v, const double* p, int n) {
   switch (v.kind) {
@@ -116,6 +133,12 @@ bool vertex_read(HVertex& v, const double* p, int n) {
       for (int i = 0; i < 4; ++i) v.est[3 + i] = q[i];
       if (n >= 12) for (int i = 0; i < 5; ++i) v.est[7 + i] = p[7 + i];
       else { v.est[7] = 300; v.est[8] = 300; v.est[9] = 320; v.est[10] = 320; v.est[11] = 0.1; }
+      return true;
+    }
+    case B200_VERTEX_SE3_EXPMAP: {  // types_six_dof_expmap.cpp:76-84: the file holds cam2world (fromVector, no
+      if (n < 7) return false;      // normalisation), the estimate is its inverse
+      se3quat_inverse(p, v.est);
+      for (int i = 7; i < 12; ++i) v.est[i] = 0;  // intrinsics: set by the first XYZ2UV edge (f = 0 marks 'unset')
       return true;
     }
   }
@@ -147,6 +170,13 @@ bool edge_read(HEdge& e, const double* p, int n) {
       if (n < 2) return false;
       e.meas[0] = p[0]; e.meas[1] = p[1];
       return true;
+    case B200_EDGE_XYZ2UV: {  // types_six_dof_expmap.cpp:241-256: paramId u v i00 i01 i11
+      if (n < 6) return false;
+      e.param = (int)p[0];
+      e.meas[0] = p[1]; e.meas[1] = p[2];
+      e.info[0] = p[3]; e.info[1] = e.info[2] = p[4]; e.info[3] = p[5];
+      return true;
+    }
   }
   return false;
 }
@@ -168,8 +198,14 @@ void initial_estimate(b200_graph* g, const HEdge& e, bool to_from_from) {
   }
 }
 int add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, int n) {
-  static const int vk0[3] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_XYZ};
-  static const int vk1[3] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_CAM};
+  static const int vk0[4] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_XYZ, B200_VERTEX_XYZ};
+  static const int vk1[4] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_CAM, B200_VERTEX_SE3_EXPMAP};
+  const std::array<double, 4>* cp = nullptr;
+  if (kind == B200_EDGE_XYZ2UV) {  // OptimizableGraph::addEdge -> resolveParameters: unknown parameter id rejects the edge
+    auto it = n >= 1 ? g->camera_parameters.find((int)payload[0]) : g->camera_parameters.end();
+    if (it == g->camera_parameters.end()) { g->err = "XYZ2UV edge names unknown CameraParameters"; return B200_ERR_INVALID; }
+    cp = &it->second;
+  }
   int a = g->find(id1), b = g->find(id2);
   int doInit = 0;
   if (a < 0) { a = add_vertex(g, vk0[kind], id1); set_to_origin(g->vertices[a]); doInit = 2; }
@@ -178,6 +214,12 @@ int add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, i
   HEdge e;
   e.kind = kind; e.v0 = a; e.v1 = b;
   if (!edge_read(e, payload, n)) { g->err = "short edge payload"; return B200_ERR_INVALID; }
+  if (cp) {  // the pose row carries the intrinsics of its edges: f f cx cy baseline
+    HVertex& pv = g->vertices[b];
+    const double want[5] = {(*cp)[0], (*cp)[0], (*cp)[1], (*cp)[2], (*cp)[3]};
+    if (pv.est[7] == 0) for (int i = 0; i < 5; ++i) pv.est[7 + i] = want[i];
+    else for (int i = 0; i < 5; ++i) if (pv.est[7 + i] != want[i]) { g->err = "edges of one pose name different CameraParameters"; return B200_ERR_UNSUPPORTED; }
+  }
   g->edges.push_back(e);
   if (doInit == 1) initial_estimate(g, e, true);
   if (doInit == 2) initial_estimate(g, e, false);
@@ -214,19 +256,19 @@ void b200_graph_destroy(b200_graph* g) { delete g; }
 const char* b200_graph_last_error(const b200_graph* g) { return g ? g->err.c_str() : ""; }
 
 int b200_graph_add_vertex(b200_graph* g, int kind, int id, const double* payload, int n) {
-  if (!g || kind < 0 || kind > 3) return B200_ERR_INVALID;
+  if (!g || kind < 0 || kind >= B200_NUM_VERTEX_KINDS) return B200_ERR_INVALID;
   int v = add_vertex(g, kind, id);
   if (v < 0) { g->err = "duplicate vertex id"; return B200_ERR_INVALID; }
   if (!vertex_read(g->vertices[v], payload, n)) { g->err = "short vertex payload"; return B200_ERR_INVALID; }
   return B200_OK;
 }
 int b200_graph_add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, int n) {
-  if (!g || kind < 0 || kind > 2) return B200_ERR_INVALID;
+  if (!g || kind < 0 || kind >= B200_NUM_EDGE_KINDS) return B200_ERR_INVALID;
   return add_edge(g, kind, id1, id2, payload, n);
 }
 // bulk variants: payload is row-major [n x stride]
 int b200_graph_add_vertices(b200_graph* g, int kind, int n, const int32_t* ids, const double* payload, int stride) {
-  if (!g || kind < 0 || kind > 3 || n < 0 || !ids || !payload) return B200_ERR_INVALID;
+  if (!g || kind < 0 || kind >= B200_NUM_VERTEX_KINDS || n < 0 || !ids || !payload) return B200_ERR_INVALID;
   g->vertices.reserve(g->vertices.size() + n);
   for (int i = 0; i < n; ++i) {
     int rc = b200_graph_add_vertex(g, kind, ids[i], payload + (size_t)i * stride, stride);
@@ -235,12 +277,18 @@ int b200_graph_add_vertices(b200_graph* g, int kind, int n, const int32_t* ids, 
   return B200_OK;
 }
 int b200_graph_add_edges(b200_graph* g, int kind, int n, const int32_t* id1, const int32_t* id2, const double* payload, int stride) {
-  if (!g || kind < 0 || kind > 2 || n < 0 || !id1 || !id2 || !payload) return B200_ERR_INVALID;
+  if (!g || kind < 0 || kind >= B200_NUM_EDGE_KINDS || n < 0 || !id1 || !id2 || !payload) return B200_ERR_INVALID;
   g->edges.reserve(g->edges.size() + n);
   for (int i = 0; i < n; ++i) {
     int rc = add_edge(g, kind, id1[i], id2[i], payload + (size_t)i * stride, stride);
     if (rc) return rc;
   }
+  return B200_OK;
+}
+int b200_graph_add_camera_parameters(b200_graph* g, int id, double focal_length, double cx, double cy, double baseline) {
+  if (!g) return B200_ERR_INVALID;
+  if (g->camera_parameters.count(id)) { g->err = "duplicate parameter id"; return B200_ERR_INVALID; }  // ParameterContainer::addParameter
+  g->camera_parameters[id] = {focal_length, cx, cy, baseline};
   return B200_OK;
 }
 int b200_graph_set_fixed(b200_graph* g, int id, int fixed) {
@@ -286,6 +334,15 @@ int b200_graph_load(b200_graph* g, const char* path) {
     else if (tag == "EDGE_SE2") ekind = B200_EDGE_SE2;
     else if (tag == "EDGE_SE3:QUAT") ekind = B200_EDGE_SE3;
     else if (tag == "EDGE_PROJECT_P2MC") ekind = B200_EDGE_P2MC;
+    else if (tag == "VERTEX_SE3:EXPMAP") vkind = B200_VERTEX_SE3_EXPMAP;
+    else if (tag == "EDGE_PROJECT_XYZ2UV:EXPMAP") ekind = B200_EDGE_XYZ2UV;
+    else if (tag == "PARAMS_CAMERAPARAMETERS") {  // optimizable_graph.cpp:398-415 + CameraParameters::read
+      nums.clear();
+      while (lp.next_token(tb, te)) nums.push_back(strtod(tb, nullptr));
+      lp.skip_line();
+      if (nums.size() >= 5) b200_graph_add_camera_parameters(g, (int)nums[0], nums[1], nums[2], nums[3], nums[4]);
+      continue;
+    }
     else { lp.skip_line(); continue; }  // unknown tags are skipped (optimizable_graph.cpp:417-423)
     nums.clear();
     int ids[2] = {0, 0};
@@ -349,15 +406,15 @@ int b200_graph_initialize(b200_graph* g) {
       HVertex& v = g->vertices[i];
       if (!v.fixed && (int)v.marginalized == k) v.hidx = idx++;
     }
-  for (int k = 0; k < 4; ++k) g->kind_slots[k].clear();
+  for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k) g->kind_slots[k].clear();
   for (int i : act) { HVertex& v = g->vertices[i]; v.slot = (int)g->kind_slots[v.kind].size(); g->kind_slots[v.kind].push_back(i); }
   return B200_OK;
 }
 
 int b200_graph_counts(b200_graph* g, int32_t* vc, int32_t* ec) {
   if (!g) return B200_ERR_INVALID;
-  if (vc) { for (int k = 0; k < 4; ++k) vc[k] = 0; for (const HVertex& v : g->vertices) vc[v.kind]++; }
-  if (ec) { for (int k = 0; k < 3; ++k) ec[k] = 0; for (const HEdge& e : g->edges) ec[e.kind]++; }
+  if (vc) { for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k) vc[k] = 0; for (const HVertex& v : g->vertices) vc[v.kind]++; }
+  if (ec) { for (int k = 0; k < B200_NUM_EDGE_KINDS; ++k) ec[k] = 0; for (const HEdge& e : g->edges) ec[e.kind]++; }
   return B200_OK;
 }
 
@@ -366,7 +423,7 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
   if (g->active_edges.empty()) { g->err = "call b200_graph_initialize first"; return B200_ERR_INVALID; }
   const int ekind = g->edges[g->active_edges[0]].kind;
   for (int k : g->active_edges) if (g->edges[k].kind != ekind) { g->err = "mixed edge types are not supported"; return B200_ERR_UNSUPPORTED; }
-  const bool ba = ekind == B200_EDGE_P2MC;
+  const bool ba = is_ba(ekind);
   if (num_shards > 1 && !ba) { g->err = "only bundle adjustment shards (pose graphs stay single-GPU)"; return B200_ERR_UNSUPPORTED; }
   // numPoses = #free non-marginalized vertices
   int np = 0;
@@ -398,7 +455,7 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
       }
     }
   }
-  for (int kind = 0; kind < 4; ++kind) {
+  for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
     const std::vector<int>& sl = g->kind_slots[kind];
     if (sl.empty()) continue;
     const int ne = vest(kind);
@@ -476,7 +533,7 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
 
 int b200_graph_download(b200_graph* g, b200_ctx* ctx) {
   if (!g || !ctx) return B200_ERR_INVALID;
-  for (int kind = 0; kind < 4; ++kind) {
+  for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
     const std::vector<int>& sl = g->kind_slots[kind];
     if (sl.empty()) continue;
     const int ne = vest(kind);
@@ -513,8 +570,10 @@ int b200_graph_save(b200_graph* g, const char* path) {
   std::vector<int> order(g->vertices.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
   std::sort(order.begin(), order.end(), [&](int a, int b) { return g->vertices[a].id < g->vertices[b].id; });
-  static const char* vtag[4] = {"VERTEX_SE2", "VERTEX_SE3:QUAT", "VERTEX_CAM", "VERTEX_XYZ"};
-  static const char* etag[3] = {"EDGE_SE2", "EDGE_SE3:QUAT", "EDGE_PROJECT_P2MC"};
+  static const char* vtag[B200_NUM_VERTEX_KINDS] = {"VERTEX_SE2", "VERTEX_SE3:QUAT", "VERTEX_CAM", "VERTEX_XYZ", "VERTEX_SE3:EXPMAP"};
+  static const char* etag[B200_NUM_EDGE_KINDS] = {"EDGE_SE2", "EDGE_SE3:QUAT", "EDGE_PROJECT_P2MC", "EDGE_PROJECT_XYZ2UV:EXPMAP"};
+  for (const auto& kv : g->camera_parameters)  // parameters first (optimizable_graph.cpp:591-594)
+    fprintf(f, "PARAMS_CAMERAPARAMETERS %d %.17g %.17g %.17g %.17g\n", kv.first, kv.second[0], kv.second[1], kv.second[2], kv.second[3]);
   for (int i : order) {
     const HVertex& v = g->vertices[i];
     fprintf(f, "%s %d", vtag[v.kind], v.id);
@@ -524,6 +583,10 @@ int b200_graph_save(b200_graph* g, const char* path) {
       R_to_quat(v.est, q);
       quat_normalize(q);
       fprintf(f, " %.17g %.17g %.17g %.17g %.17g %.17g %.17g", v.est[9], v.est[10], v.est[11], q[0], q[1], q[2], q[3]);
+    } else if (v.kind == B200_VERTEX_SE3_EXPMAP) {  // VertexSE3Expmap::write: cam2world = estimate^-1
+      double c2w[7];
+      se3quat_inverse(v.est, c2w);
+      for (int k = 0; k < 7; ++k) fprintf(f, " %.17g", c2w[k]);
     } else {
       for (int k = 0; k < 12; ++k) fprintf(f, " %.17g", v.est[k]);
     }
@@ -532,6 +595,7 @@ int b200_graph_save(b200_graph* g, const char* path) {
   }
   for (const HEdge& e : g->edges) {
     fprintf(f, "%s %d %d", etag[e.kind], g->vertices[e.v0].id, g->vertices[e.v1].id);
+    if (e.kind == B200_EDGE_XYZ2UV) fprintf(f, " %d", e.param);
     const int D = edim(e.kind);
     if (e.kind == B200_EDGE_SE2) fprintf(f, " %.17g %.17g %.17g", e.meas[0], e.meas[1], e.meas[2]);
     else if (e.kind == B200_EDGE_SE3) {

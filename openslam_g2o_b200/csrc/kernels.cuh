@@ -251,14 +251,16 @@ __global__ void gather_segments_kernel(int nseg, const int* __restrict__ src_ptr
   dst[idx] = s;
 }
 
-// ------------------------------------------------------------------ bundle adjustment (CAM + XYZ, P2MC)
+// ------------------------------------------------------------------ bundle adjustment (camera + XYZ)
+// MODEL 0: VertexCam / EdgeProjectP2MC (types_sba), MODEL 1: VertexSE3Expmap / EdgeProjectXYZ2UV (types_six_dof_expmap)
+template <int MODEL>
 __global__ void cam_derive_kernel(int n, const double* __restrict__ est, double* __restrict__ der) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double e[12], d[16];
 #pragma unroll
   for (int k = 0; k < 12; ++k) e[k] = est[12ll * i + k];
-  cam_derive(e, d);
+  ba_derive<MODEL>(e, d);
 #pragma unroll
   for (int k = 0; k < 16; ++k) der[16ll * i + k] = d[k];
 }
@@ -269,6 +271,7 @@ __device__ __forceinline__ void load_der(const double* __restrict__ der, int c, 
   for (int i = 0; i < 8; ++i) { double2 a = __ldg(p + i); d[2 * i] = a.x; d[2 * i + 1] = a.y; }
 }
 
+template <int MODEL>
 __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* __restrict__ e_cam,
                                const double* __restrict__ pt_est, const double* __restrict__ cam_der,
                                const double* __restrict__ meas, const double* __restrict__ info, Robust rk,
@@ -282,7 +285,7 @@ __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* _
     const double X[3] = {X4.x, X4.y, X4.z};
     const double z[2] = {meas[e], meas[(long long)E + e]};
     double err[2];
-    p2mc_error(der, X, z, err);
+    ba_error<MODEL>(der, X, z, err);
     const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
     chi = err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]);
     if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
@@ -292,6 +295,7 @@ __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* _
 }
 
 // one thread per landmark: Hll, b_l and one Hpl block per observation (edges of a landmark are contiguous)
+template <int MODEL>
 __global__ void __launch_bounds__(128)
 ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ lm_order,
                            const int* __restrict__ lm_vertex,
@@ -315,9 +319,9 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
     load_der(cam_der, c, der);
     const double ct[3] = {cam_est[12ll * c], cam_est[12ll * c + 1], cam_est[12ll * c + 2]};
     double Jp[6], Jc[12], err[2];
-    p2mc_jacobians(der, ct, X, Jp, Jc);
+    ba_jacobians<MODEL>(der, ct, X, Jp, Jc);
     const double z[2] = {meas[e], meas[(long long)E + e]};
-    p2mc_error(der, X, z, err);
+    ba_error<MODEL>(der, X, z, err);
     double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
     if (rk.kind) {
       double r0, r1;
@@ -361,6 +365,7 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
 }
 
 // one CTA per free camera: Hpp(i,i) and b_i as an ordered tree-sum over the camera's observations
+template <int MODEL>
 __global__ void __launch_bounds__(128)
 ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict__ cam_eidx,
                          const int* __restrict__ pose_vertex, const int* __restrict__ e_pt,
@@ -381,9 +386,9 @@ ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict
     const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * e_pt[e]);
     const double X[3] = {X4.x, X4.y, X4.z};
     double Jp[6], Jc[12], err[2];
-    p2mc_jacobians(der, ct, X, Jp, Jc);
+    ba_jacobians<MODEL>(der, ct, X, Jp, Jc);
     const double z[2] = {meas[e], meas[(long long)E + e]};
-    p2mc_error(der, X, z, err);
+    ba_error<MODEL>(der, X, z, err);
     double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
     if (rk.kind) {
       double r0, r1;
@@ -744,6 +749,7 @@ __global__ void oplus_se3_kernel(int n, const int* __restrict__ hidx, const doub
 #pragma unroll
   for (int k = 0; k < 12; ++k) est[12ll * v + k] = e[k];
 }
+template <int MODEL>
 __global__ void oplus_cam_kernel(int n, const int* __restrict__ hidx, const double* __restrict__ x, double* __restrict__ est,
                                  double* __restrict__ der) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -753,8 +759,8 @@ __global__ void oplus_cam_kernel(int n, const int* __restrict__ hidx, const doub
   double e[12], d[16];
 #pragma unroll
   for (int k = 0; k < 12; ++k) e[k] = est[12ll * v + k];
-  cam_oplus(e, x + 6ll * h);
-  cam_derive(e, d);
+  ba_oplus<MODEL>(e, x + 6ll * h);
+  ba_derive<MODEL>(e, d);
 #pragma unroll
   for (int k = 3; k < 7; ++k) est[12ll * v + k] = e[k];
 #pragma unroll

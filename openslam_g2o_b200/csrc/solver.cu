@@ -29,6 +29,9 @@ enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE
        PH_LINEARIZE_CAMS = 7, PH_GATHER = 8, PH_SCHUR_INV = 9, PH_SCALE = 10, PH_COLLECTIVE = 11,
        /* 12, 13, 19: inside the Cholesky, see chol.cu */ PH_SCHUR_FINISH = 14, PH_COUNT = 24 };
 
+// camera-model dispatch of the templated BA kernels
+#define BA_MODEL_LAUNCH(c, KERNEL, ...) do { if ((c)->cam_model == 0) k::KERNEL<0> __VA_ARGS__; else k::KERNEL<1> __VA_ARGS__; } while (0)
+
 struct PhaseTimer : ScopedPhase {
   PhaseTimer(b200_ctx* c, int ph) : ScopedPhase(&c->prof, ph) {}
 };
@@ -106,7 +109,8 @@ int build_structure_impl(b200_ctx* c) {
   if (c->edge_kind < 0 || c->nE <= 0) return fail(c, B200_ERR_INVALID, "no edges set");
   const int want_pose = c->edge_kind == B200_EDGE_SE2 ? B200_VERTEX_SE2 : c->edge_kind == B200_EDGE_SE3 ? B200_VERTEX_SE3 : B200_VERTEX_CAM;
   if (want_pose != pose_kind) return fail(c, B200_ERR_UNSUPPORTED, "edge kind does not match the pose vertex kind");
-  if ((c->edge_kind == B200_EDGE_P2MC) != has_lm) return fail(c, B200_ERR_UNSUPPORTED, "P2MC edges need XYZ vertices (and only they do)");
+  if ((c->edge_kind == B200_EDGE_P2MC) != has_lm) return fail(c, B200_ERR_UNSUPPORTED, "P2MC / XYZ2UV edges need XYZ vertices (and only they do)");
+  if (c->edge_kind == B200_EDGE_P2MC && c->edge_model != c->cam_model) return fail(c, B200_ERR_UNSUPPORTED, "P2MC edges go with CAM vertices, XYZ2UV edges with SE3_EXPMAP vertices");
   c->pose_kind = pose_kind;
   c->schur = has_lm;
   b200_ctx::VertexSet& PV = c->vs[pose_kind];
@@ -168,7 +172,7 @@ int build_structure_impl(b200_ctx* c) {
       c->d_cam_der.alloc((size_t)PV.n * 16);
       c->d_cam_der_bak.alloc((size_t)PV.n * 16);
       if (!c->host_only) {
-        k::cam_derive_kernel<<<ceil_div(PV.n, 128), 128, 0, s>>>(PV.n, c->d_pose_est.p, c->d_cam_der.p);
+        BA_MODEL_LAUNCH(c, cam_derive_kernel, <<<ceil_div(PV.n, 128), 128, 0, s>>>(PV.n, c->d_pose_est.p, c->d_cam_der.p));
         c->lc.n++;
       }
     }
@@ -520,7 +524,7 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
   else if (c->edge_kind == B200_EDGE_SE3)
     k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
   else
-    k::ba_chi2_kernel<<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
+    BA_MODEL_LAUNCH(c, ba_chi2_kernel, <<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p));
   k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 0);
   c->lc.n += 2;
   B200_CUDA(cudaGetLastError());
@@ -556,11 +560,11 @@ int enqueue_build_system(b200_ctx* c) {
     double* b_p_stage = c->d_Hpp.p + (size_t)np * 36;
     if (c->nl > 0) {
       PhaseTimer pt(c, PH_LINEARIZE);
-      k::ba_linearize_points_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP);
+      BA_MODEL_LAUNCH(c, ba_linearize_points_kernel, <<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP));
       c->lc.n++;
     }
     { PhaseTimer pt(c, PH_LINEARIZE_CAMS);
-    k::ba_linearize_cams_kernel<<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage); }
+    BA_MODEL_LAUNCH(c, ba_linearize_cams_kernel, <<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage)); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
     int rc = allreduce_dev(c, c->d_Hpp.p, (long long)np * 36 + c->sizeP);  // sharded: partial camera blocks -> full
@@ -649,7 +653,7 @@ void enqueue_update(b200_ctx* c) {
     if (++c->num_oplus_calls > 1000) { c->num_oplus_calls = 0; orth = 1; }  // VertexSE3::orthogonalizeAfter (vertex_se3.h:56,111)
     k::oplus_se3_kernel<<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, orth);
   } else {
-    k::oplus_cam_kernel<<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, c->d_cam_der.p);
+    BA_MODEL_LAUNCH(c, oplus_cam_kernel, <<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, c->d_cam_der.p));
   }
   c->lc.n++;
   if (c->schur && c->n_lm_v > 0) {
@@ -840,7 +844,9 @@ void b200_destroy(b200_ctx* c) {
 const char* b200_last_error(const b200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 int b200_set_vertices(b200_ctx* c, int kind, int n, const double* est, const int32_t* hidx, const uint8_t* marg) {
-  if (!c || kind < 0 || kind > 3 || n < 0 || (n > 0 && (!est || !hidx))) return B200_ERR_INVALID;
+  if (!c || kind < 0 || kind > B200_VERTEX_SE3_EXPMAP || n < 0 || (n > 0 && (!est || !hidx))) return B200_ERR_INVALID;
+  if (kind == B200_VERTEX_CAM) c->cam_model = 0;
+  if (kind == B200_VERTEX_SE3_EXPMAP) { c->cam_model = 1; kind = B200_VERTEX_CAM; }  // same slot, same 12-double rows
   b200_ctx::VertexSet& V = c->vs[kind];
   V.set = true; V.n = n;
   V.est.assign(est, est + (size_t)n * vest(kind));
@@ -851,7 +857,9 @@ int b200_set_vertices(b200_ctx* c, int kind, int n, const double* est, const int
 }
 
 int b200_set_edges(b200_ctx* c, int kind, int n, const int32_t* vi, const int32_t* vj, const double* meas, const double* info) {
-  if (!c || kind < 0 || kind > 2 || n < 0 || (n > 0 && (!vi || !vj || !meas || !info))) return B200_ERR_INVALID;
+  if (!c || kind < 0 || kind > B200_EDGE_XYZ2UV || n < 0 || (n > 0 && (!vi || !vj || !meas || !info))) return B200_ERR_INVALID;
+  if (kind == B200_EDGE_P2MC) c->edge_model = 0;
+  if (kind == B200_EDGE_XYZ2UV) { c->edge_model = 1; kind = B200_EDGE_P2MC; }  // same sizes (2 | 2x2), same structure
   c->edge_kind = kind; c->nE = n;
   c->e_vi.assign(vi, vi + n); c->e_vj.assign(vj, vj + n);
   c->e_meas.assign(meas, meas + (size_t)n * emeas(kind));
@@ -1176,6 +1184,7 @@ int b200_get_bschur(b200_ctx* c, double* out) {
 int b200_get_estimates(b200_ctx* c, int kind, double* out) {
   return guarded(c, [&]() {
     NEED_STRUCTURE(c);
+    if (kind == B200_VERTEX_SE3_EXPMAP || kind == B200_VERTEX_CAM) kind = ((kind == B200_VERTEX_SE3_EXPMAP) == (c->cam_model == 1)) ? B200_VERTEX_CAM : -1;
     const bool lm = kind == B200_VERTEX_XYZ;
     if (!lm && kind != c->pose_kind) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     if (lm && !c->schur) return fail(c, B200_ERR_INVALID, "vertex kind not present");
@@ -1199,6 +1208,7 @@ int b200_set_estimates(b200_ctx* c, int kind, const double* est) {
   return guarded(c, [&]() {
     NEED_DEVICE(c);
     NEED_STRUCTURE(c);
+    if (kind == B200_VERTEX_SE3_EXPMAP || kind == B200_VERTEX_CAM) kind = ((kind == B200_VERTEX_SE3_EXPMAP) == (c->cam_model == 1)) ? B200_VERTEX_CAM : -1;
     const bool lm = kind == B200_VERTEX_XYZ;
     if ((!lm && kind != c->pose_kind) || (lm && !c->schur) || !est) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     B200_CUDA(cudaSetDevice(c->device));
@@ -1213,7 +1223,7 @@ int b200_set_estimates(b200_ctx* c, int kind, const double* est) {
       c->lc.n++;
     }
     if (kind == B200_VERTEX_CAM) {
-      k::cam_derive_kernel<<<ceil_div(n, 128), 128, 0, c->stream>>>(n, c->d_pose_est.p, c->d_cam_der.p);
+      BA_MODEL_LAUNCH(c, cam_derive_kernel, <<<ceil_div(n, 128), 128, 0, c->stream>>>(n, c->d_pose_est.p, c->d_cam_der.p));
       c->lc.n++;
     }
     B200_CUDA(cudaStreamSynchronize(c->stream));

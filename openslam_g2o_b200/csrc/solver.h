@@ -31,6 +31,9 @@ struct b200_ctx {
   } vs[4];
   int edge_kind = -1;
   int nE = 0;
+  // camera model of the BA family: 0 VertexCam / EdgeProjectP2MC, 1 VertexSE3Expmap / EdgeProjectXYZ2UV.  Both live in
+  // the vs[B200_VERTEX_CAM] slot / edge_kind B200_EDGE_P2MC internally (same block sizes 6, 3, 2; same Schur plan)
+  int cam_model = 0, edge_model = 0;
   std::vector<int> e_vi, e_vj;
   std::vector<double> e_meas, e_info;
   std::vector<long long> extra_schur_keys;  // (col<<32|row) blocks other shards contribute to Hschur

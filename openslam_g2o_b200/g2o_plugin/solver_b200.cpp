@@ -23,6 +23,7 @@
 #include "g2o/core/sparse_optimizer.h"
 #include "g2o/stuff/macros.h"
 #include "g2o/types/sba/types_sba.h"
+#include "g2o/types/sba/types_six_dof_expmap.h"
 #include "g2o/types/slam2d/edge_se2.h"
 #include "g2o/types/slam2d/vertex_se2.h"
 #include "g2o/types/slam3d/edge_se3.h"
@@ -109,11 +110,11 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
   bool ingest() {
     const SparseOptimizer::VertexContainer& verts = _optimizer->activeVertices();
     const SparseOptimizer::EdgeContainer& edges = _optimizer->activeEdges();
-    std::vector<double> est[4];
-    std::vector<int32_t> hidx[4];
-    std::vector<uint8_t> marg[4];
+    std::vector<double> est[B200_NUM_VERTEX_KINDS];
+    std::vector<int32_t> hidx[B200_NUM_VERTEX_KINDS];
+    std::vector<uint8_t> marg[B200_NUM_VERTEX_KINDS];
     _slot.clear();
-    for (int k = 0; k < 4; ++k) _verts[k].clear();
+    for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k) _verts[k].clear();
     for (size_t i = 0; i < verts.size(); ++i) {
       OptimizableGraph::Vertex* v = verts[i];
       int kind = -1;
@@ -131,6 +132,11 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
         Eigen::Map<Eigen::Vector3d>(e) = c.translation();
         Eigen::Map<Eigen::Vector4d>(e + 3) = c.rotation().coeffs();  // x y z w
         e[7] = c.Kcam(0, 0); e[8] = c.Kcam(1, 1); e[9] = c.Kcam(0, 2); e[10] = c.Kcam(1, 2); e[11] = c.baseline;
+      } else if (VertexSE3Expmap* p = dynamic_cast<VertexSE3Expmap*>(v)) {
+        kind = B200_VERTEX_SE3_EXPMAP;  // world -> camera SE3Quat; the intrinsics [7..12) come from its edges' CameraParameters
+        Eigen::Map<Eigen::Vector3d>(e) = p->estimate().translation();
+        Eigen::Map<Eigen::Vector4d>(e + 3) = p->estimate().rotation().coeffs();  // x y z w
+        e[7] = e[8] = e[9] = e[10] = e[11] = 0.;
       } else if (VertexSBAPointXYZ* p = dynamic_cast<VertexSBAPointXYZ*>(v)) {
         kind = B200_VERTEX_XYZ;
         Eigen::Map<Eigen::Vector3d>(e) = p->estimate();
@@ -146,9 +152,6 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
       marg[kind].push_back(v->marginalized() ? 1 : 0);
     }
     _hasLandmarks = !hidx[B200_VERTEX_XYZ].empty();
-    for (int k = 0; k < 4; ++k)
-      if (!hidx[k].empty() && b200_set_vertices(_ctx, k, static_cast<int>(hidx[k].size()), &est[k][0], &hidx[k][0], &marg[k][0]) != B200_OK)
-        return false;
     std::vector<int32_t> vi, vj;
     std::vector<double> meas, info;
     int ekind = -1;
@@ -173,6 +176,21 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
         kind = B200_EDGE_P2MC;
         meas.insert(meas.end(), p->measurement().data(), p->measurement().data() + 2);
         info.insert(info.end(), p->information().data(), p->information().data() + 4);
+      } else if (EdgeProjectXYZ2UV* p = dynamic_cast<EdgeProjectXYZ2UV*>(e)) {
+        kind = B200_EDGE_XYZ2UV;
+        meas.insert(meas.end(), p->measurement().data(), p->measurement().data() + 2);
+        info.insert(info.end(), p->information().data(), p->information().data() + 4);
+        // the pose row carries the CameraParameters of its edges (parameter(0), types_six_dof_expmap.h:146-147)
+        const CameraParameters* cam = static_cast<const CameraParameters*>(p->parameter(0));
+        double* row = &est[B200_VERTEX_SE3_EXPMAP][12 * _slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(1))]];
+        const double want[5] = {cam->focal_length, cam->focal_length, cam->principle_point[0], cam->principle_point[1], cam->baseline};
+        for (int i = 0; i < 5; ++i) {
+          if (row[7] != 0. && row[7 + i] != want[i]) {
+            std::cerr << "OptimizationAlgorithmB200: edges of one pose use different CameraParameters" << std::endl;
+            return false;
+          }
+        }
+        for (int i = 0; i < 5; ++i) row[7 + i] = want[i];
       }
       if (kind < 0 || (ekind >= 0 && kind != ekind)) {
         std::cerr << "OptimizationAlgorithmB200: unsupported / mixed edge types" << std::endl;
@@ -200,6 +218,9 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
       vj.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(1))]);
     }
     if (vi.empty()) return false;
+    for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k)
+      if (!hidx[k].empty() && b200_set_vertices(_ctx, k, static_cast<int>(hidx[k].size()), &est[k][0], &hidx[k][0], &marg[k][0]) != B200_OK)
+        return false;
     if (b200_set_edges(_ctx, ekind, static_cast<int>(vi.size()), &vi[0], &vj[0], &meas[0], &info[0]) != B200_OK) return false;
     if (b200_set_robust_kernel(_ctx, robustKind, robustDelta) != B200_OK) return false;
     int rc = b200_build_structure(_ctx);
@@ -210,7 +231,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
   // device estimates -> vertices
   void writeBack() {
     std::vector<double> buf;
-    for (int kind = 0; kind < 4; ++kind) {
+    for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
       const std::vector<OptimizableGraph::Vertex*>& vs = _verts[kind];
       if (vs.empty()) continue;
       const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
@@ -226,6 +247,11 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
           T.linear() = Eigen::Map<const Eigen::Matrix3d>(e);
           T.translation() = Eigen::Map<const Eigen::Vector3d>(e + 9);
           static_cast<VertexSE3*>(vs[i])->setEstimate(T);
+        } else if (kind == B200_VERTEX_SE3_EXPMAP) {
+          SE3Quat T;  // the device keeps q normalised with w >= 0 (SE3Quat::normalizeRotation)
+          T.setRotation(Eigen::Quaterniond(e[6], e[3], e[4], e[5]));
+          T.setTranslation(Eigen::Vector3d(e[0], e[1], e[2]));
+          static_cast<VertexSE3Expmap*>(vs[i])->setEstimate(T);
         } else {
           SBACam cam(Eigen::Quaterniond(e[6], e[3], e[4], e[5]), Eigen::Vector3d(e[0], e[1], e[2]));
           cam.setKcam(e[7], e[8], e[9], e[10], e[11]);
@@ -245,7 +271,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
   Property<double>* _userLambdaInit;
   Property<int>* _maxTrialsAfterFailure;
   std::map<OptimizableGraph::Vertex*, int> _slot;
-  std::vector<OptimizableGraph::Vertex*> _verts[4];
+  std::vector<OptimizableGraph::Vertex*> _verts[B200_NUM_VERTEX_KINDS];
 };
 
 // ----------------------------------------------------------------------------------------------- registration

@@ -313,6 +313,11 @@ class SparseOptimizer:
     def set_fixed(self, vid, fixed=True):
         _check(lib.b200_graph_set_fixed(self._g, vid, int(fixed)), self._g, graph=True)
 
+    def add_camera_parameters(self, pid, focal_length, cx, cy, baseline):
+        """OptimizableGraph::addParameter(CameraParameters) (types/sba/types_six_dof_expmap.h:45-80)"""
+        _check(lib.b200_graph_add_camera_parameters(self._g, int(pid), float(focal_length), float(cx), float(cy),
+                                                     float(baseline)), self._g, graph=True)
+
     def set_robust_kernel(self, name, width=1.0):
         """`g2o -robustKernel name -robustKernelWidth width` (apps/g2o_cli/g2o.cpp:322-336): every edge gets the kernel"""
         self.context.set_robust_kernel(name, width)
@@ -368,8 +373,8 @@ class SparseOptimizer:
         return dict(kind=int(out[0]), hessian_index=int(out[1]), fixed=bool(out[2]), marginalized=bool(out[3]))
 
     def counts(self):
-        vc = np.zeros(4, np.int32)
-        ec = np.zeros(3, np.int32)
+        vc = np.zeros(L.NUM_VERTEX_KINDS, np.int32)
+        ec = np.zeros(L.NUM_EDGE_KINDS, np.int32)
         _check(lib.b200_graph_counts(self._g, L.ptr(vc), L.ptr(ec)), self._g, graph=True)
         return vc, ec
 

@@ -6,10 +6,11 @@ text line), so the same arrays feed the product (SparseOptimizer.add_vertices/ad
 
   sphere(nodes_per_level, laps, ...)   examples/sphere/create_sphere.cpp:95-184 (reference generator)
   venice_like(cams, points, ...)       SURVEY.md section 8d config 3/4: ring of inward-looking cameras, windowed visibility
+  expmap_ba(cams, points, ...)         the same scene as VERTEX_SE3:EXPMAP / EDGE_PROJECT_XYZ2UV:EXPMAP (examples/ba/ba_demo.cpp)
 """
 import numpy as np
 
-from ._lib import EDGE_P2MC, EDGE_SE3, VERTEX_CAM, VERTEX_SE3, VERTEX_XYZ
+from ._lib import EDGE_P2MC, EDGE_SE3, EDGE_XYZ2UV, VERTEX_CAM, VERTEX_SE3, VERTEX_SE3_EXPMAP, VERTEX_XYZ
 
 
 # ---------------------------------------------------------------- quaternion helpers (x y z w), vectorised
@@ -137,6 +138,24 @@ def venice_like(num_cams=871, num_points=530304, mean_extra_obs=1.8, seed=871, p
                 truth_points=X, truth_cams=np.concatenate([C, q], axis=1))
 
 
+def expmap_ba(num_cams=30, num_points=600, seed=7, focal_length=1000.0, principal_point=(320.0, 240.0), **kw):
+    """The same scene in the SE3-expmap formulation of examples/ba/ba_demo.cpp:95-185: VERTEX_SE3:EXPMAP poses (the file
+    holds cam2world: camera centre + camera-to-world quaternion), one PARAMS_CAMERAPARAMETERS (id 0) and
+    EDGE_PROJECT_XYZ2UV:EXPMAP observations `paramId u v i00 i01 i11`."""
+    p = venice_like(num_cams, num_points, seed=seed, **kw)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    cx, cy = principal_point
+    uv = p["edge_payload"] * (focal_length / 1000.0) + np.array([cx, cy])
+    n = len(uv)
+    w = rng.uniform(0.5, 2.0, (n, 2))                     # non-trivial information matrices (upper triangle i00 i01 i11)
+    c = rng.uniform(-0.3, 0.3, n) * np.sqrt(w[:, 0] * w[:, 1])
+    pay = np.concatenate([np.zeros((n, 1)), uv, w[:, :1], c[:, None], w[:, 1:]], axis=1)
+    return dict(kind="ba_expmap", camera_parameters={0: (focal_length, cx, cy, 0.0)}, cam_ids=p["cam_ids"],
+                cam_payload=np.ascontiguousarray(p["cam_payload"][:, :7]), point_ids=p["point_ids"],
+                point_payload=p["point_payload"], edge_v0=p["edge_v0"], edge_v1=p["edge_v1"], edge_payload=pay,
+                truth_points=p["truth_points"], truth_cams=p["truth_cams"])
+
+
 def _rot_to_quat(R):
     """batched rotation matrix -> quaternion (x y z w), w >= 0"""
     m = R
@@ -168,6 +187,12 @@ def feed(problem, target):
     if problem["kind"] == "se3":
         target.add_vertices(VERTEX_SE3, problem["vertex_ids"], problem["vertex_payload"])
         target.add_edges(EDGE_SE3, problem["edge_v0"], problem["edge_v1"], problem["edge_payload"])
+    elif problem["kind"] == "ba_expmap":
+        for pid, par in problem["camera_parameters"].items():
+            target.add_camera_parameters(pid, *par)
+        target.add_vertices(VERTEX_SE3_EXPMAP, problem["cam_ids"], problem["cam_payload"])
+        target.add_vertices(VERTEX_XYZ, problem["point_ids"], problem["point_payload"])
+        target.add_edges(EDGE_XYZ2UV, problem["edge_v0"], problem["edge_v1"], problem["edge_payload"])
     else:
         target.add_vertices(VERTEX_CAM, problem["cam_ids"], problem["cam_payload"])
         target.add_vertices(VERTEX_XYZ, problem["point_ids"], problem["point_payload"])
@@ -182,6 +207,15 @@ def write_g2o(problem, path):
                 f.write("VERTEX_SE3:QUAT %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
             for a, b, p in zip(problem["edge_v0"], problem["edge_v1"], problem["edge_payload"]):
                 f.write("EDGE_SE3:QUAT %d %d %s\n" % (a, b, " ".join(repr(float(x)) for x in p)))
+        elif problem["kind"] == "ba_expmap":
+            for pid, par in problem["camera_parameters"].items():
+                f.write("PARAMS_CAMERAPARAMETERS %d %s\n" % (pid, " ".join(repr(float(x)) for x in par)))
+            for i, p in zip(problem["cam_ids"], problem["cam_payload"]):
+                f.write("VERTEX_SE3:EXPMAP %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
+            for i, p in zip(problem["point_ids"], problem["point_payload"]):
+                f.write("VERTEX_XYZ %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
+            for a, b, p in zip(problem["edge_v0"], problem["edge_v1"], problem["edge_payload"]):
+                f.write("EDGE_PROJECT_XYZ2UV:EXPMAP %d %d %d %s\n" % (a, b, int(p[0]), " ".join(repr(float(x)) for x in p[1:])))
         else:
             for i, p in zip(problem["cam_ids"], problem["cam_payload"]):
                 f.write("VERTEX_CAM %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))

@@ -186,10 +186,12 @@ struct Edge {
   bool transposed = false;  // _hessianRowMajor (base_binary_edge.hpp:207-218)
   int rkKind = 0;           // robustKernel(): 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS
   double rkDelta = 1.0;     // RobustKernel::_delta
+  int paramId = -1;         // EdgeProjectXYZ2UV: id of its CameraParameters (types_six_dof_expmap.cpp:241-256)
+  double camPar[4] = {1, 0, 0, 0.5};  // focal_length, principle_point x y, baseline of that parameter
 };
 
 inline int vertex_dim(int kind) { return kind == ORC_VERTEX_SE2 ? 3 : kind == ORC_VERTEX_XYZ ? 3 : 6; }
-inline int edge_dim(int kind) { return kind == ORC_EDGE_SE2 ? 3 : kind == ORC_EDGE_SE3 ? 6 : 2; }
+inline int edge_dim(int kind) { return kind == ORC_EDGE_SE2 ? 3 : kind == ORC_EDGE_SE3 ? 6 : 2; }  // P2MC, XYZ2UV: 2
 
 // ---- SE2 (types/slam2d/se2.h:41-119) ----
 struct SE2 { double x, y, th; };
@@ -247,6 +249,60 @@ inline void se3quat_normalize_rotation(double* q) {
   quat_normalize(q);
 }
 
+
+// ---- SE3Quat (types/slam3d/se3quat.h:40-300), stored as [t3 | q(xyzw)4] ----
+// Eigen Quaterniond * Vector3d (QuaternionBase::_transformVector): v + w*uv + qv x uv, uv = 2 (qv x v)
+inline void quat_rotate(const double* q, const double* v, double* r) {
+  double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+  for (int i = 0; i < 3; ++i) uv[i] += uv[i];
+  const double c[3] = {q[1] * uv[2] - q[2] * uv[1], q[2] * uv[0] - q[0] * uv[2], q[0] * uv[1] - q[1] * uv[0]};
+  for (int i = 0; i < 3; ++i) r[i] = v[i] + q[3] * uv[i] + c[i];
+}
+// Eigen quaternion product a*b
+inline void quat_mul(const double* a, const double* b, double* r) {
+  r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+// SE3Quat::inverse (se3quat.h:125-130): r = conj(r), t = r * (-t); no normalisation
+inline void se3quat_inverse(const double* a, double* r) {
+  double q[4] = {-a[3], -a[4], -a[5], a[6]};
+  double mt[3] = {a[0] * -1., a[1] * -1., a[2] * -1.};
+  quat_rotate(q, mt, r);
+  for (int i = 0; i < 4; ++i) r[3 + i] = q[i];
+}
+// SE3Quat::operator* (se3quat.h:103-109)
+inline void se3quat_mul(const double* a, const double* b, double* r) {
+  double rt[3];
+  quat_rotate(a + 3, b, rt);
+  for (int i = 0; i < 3; ++i) r[i] = a[i] + rt[i];
+  quat_mul(a + 3, b + 3, r + 3);
+  se3quat_normalize_rotation(r + 3);
+}
+// SE3Quat::exp (se3quat.h:216-252): update = [omega ; upsilon]
+inline void se3quat_exp(const double* u, double* r) {
+  const double om[3] = {u[0], u[1], u[2]}, up[3] = {u[3], u[4], u[5]};
+  const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+  // skew (se3_ops.hpp:27-38), col-major
+  const double Om[9] = {0, om[2], -om[1], -om[2], 0, om[0], om[1], -om[0], 0};
+  double Om2[9], R[9], V[9];
+  mm<3, 3, 3>(Om, Om, Om2);
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; ++i) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + Om[i] + Om2[i]; V[i] = R[i]; }
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3);
+    for (int i = 0; i < 9; ++i) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = I + a * Om[i] + b * Om2[i];
+      V[i] = I + b * Om[i] + c * Om2[i];
+    }
+  }
+  R_to_quat(R, r + 3);
+  mm<3, 3, 1>(V, up, r);
+  se3quat_normalize_rotation(r + 3);  // SE3Quat(Quaterniond, Vector3d) ctor
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-type error / Jacobian / oplus
 // ---------------------------------------------------------------------------------------------
@@ -287,6 +343,15 @@ void compute_error(Edge* e) {
         p[r] = w2i[r] * pt[0] + w2i[r + 3] * pt[1] + w2i[r + 6] * pt[2] + w2i[r + 9] * 1.0;
       e->err[0] = p[0] / p[2] - e->meas[0];
       e->err[1] = p[1] / p[2] - e->meas[1];
+      break;
+    }
+    case ORC_EDGE_XYZ2UV: {  // types/sba/types_six_dof_expmap.h:143-150, cam_map types_six_dof_expmap.cpp:65-71
+      double p[3];
+      quat_rotate(v1->est + 3, v0->est, p);  // SE3Quat::map: _r*xyz + _t
+      for (int i = 0; i < 3; ++i) p[i] += v1->est[i];
+      const double proj[2] = {p[0] / p[2], p[1] / p[2]};
+      e->err[0] = e->meas[0] - (proj[0] * e->camPar[0] + e->camPar[1]);
+      e->err[1] = e->meas[1] - (proj[1] * e->camPar[0] + e->camPar[2]);
       break;
     }
   }
@@ -444,6 +509,25 @@ void linearize(Edge* e) {
       }
       break;
     }
+    case ORC_EDGE_XYZ2UV: {  // types/sba/types_six_dof_expmap.cpp:288-326
+      double p[3];
+      quat_rotate(v1->est + 3, v0->est, p);
+      for (int i = 0; i < 3; ++i) p[i] += v1->est[i];
+      const double x = p[0], y = p[1], z = p[2], z_2 = z * z, f = e->camPar[0];
+      const double tmp[6] = {f, 0, 0, f, -x / z * f, -y / z * f};  // 2x3 col-major
+      double R[9], tR[6];
+      quat_to_R(v1->est + 3, R);
+      mm<2, 3, 3>(tmp, R, tR);
+      for (int i = 0; i < 6; ++i) e->Ji[i] = -1. / z * tR[i];
+      double* J = e->Jj;  // 2x6 col-major
+      J[0] = x * y / z_2 * f;        J[1] = (1 + y * y / z_2) * f;
+      J[2] = -(1 + (x * x / z_2)) * f; J[3] = -x * y / z_2 * f;
+      J[4] = y / z * f;              J[5] = -x / z * f;
+      J[6] = -1. / z * f;            J[7] = 0;
+      J[8] = 0;                      J[9] = -1. / z * f;
+      J[10] = x / z_2 * f;           J[11] = y / z_2 * f;
+      break;
+    }
   }
 }
 
@@ -493,6 +577,13 @@ void oplus(Vertex* v, const double* u) {
       quat_normalize(r);
       for (int i = 0; i < 4; ++i) q[i] = r[i];
       cam_refresh(v->est);
+      break;
+    }
+    case ORC_VERTEX_SE3_EXPMAP: {  // types/sba/types_six_dof_expmap.h:101-104: exp(update) * estimate
+      double inc[7], r[7];
+      se3quat_exp(u, inc);
+      se3quat_mul(inc, v->est, r);
+      for (int i = 0; i < 7; ++i) v->est[i] = r[i];
       break;
     }
     case ORC_VERTEX_XYZ: {  // types/sba/types_sba.h:151-155
@@ -610,6 +701,7 @@ void construct_quadratic_form(Edge* e) {
     case ORC_EDGE_SE2: construct_quadratic_form_t<3, 3, 3>(e); break;
     case ORC_EDGE_SE3: construct_quadratic_form_t<6, 6, 6>(e); break;
     case ORC_EDGE_P2MC: construct_quadratic_form_t<2, 3, 6>(e); break;
+    case ORC_EDGE_XYZ2UV: construct_quadratic_form_t<2, 3, 6>(e); break;
   }
 }
 // ---------------------------------------------------------------------------------------------
@@ -815,6 +907,7 @@ struct oracle_graph {
   std::vector<std::unique_ptr<Vertex>> vstore;
   std::vector<std::unique_ptr<Edge>> edges;  // addEdge order = internalId
   int rkKind = 0;            // robust kernel given to every edge (g2o.cpp:322-336)
+  std::map<int, std::array<double, 4>> cameraParameters;  // PARAMS_CAMERAPARAMETERS id -> f cx cy baseline
   double rkDelta = 1.0;
   // SparseOptimizer
   std::vector<Vertex*> activeVertices, ivMap;
@@ -875,6 +968,13 @@ bool vertex_read(Vertex* v, const double* p, int n) {
       cam_refresh(v->est);
       return true;
     }
+    case ORC_VERTEX_SE3_EXPMAP: {  // types/sba/types_six_dof_expmap.cpp:76-84: file holds cam2world, estimate = inverse
+      if (n < 7) return false;
+      double c2w[7];
+      for (int i = 0; i < 7; ++i) c2w[i] = p[i];  // SE3Quat::fromVector: no normalisation (se3quat.h:157-160)
+      se3quat_inverse(c2w, v->est);
+      return true;
+    }
     case ORC_VERTEX_XYZ:  // types/sba/types_sba.cpp:180-186
       if (n < 3) return false;
       v->est[0] = p[0]; v->est[1] = p[1]; v->est[2] = p[2];
@@ -916,6 +1016,14 @@ bool edge_read(Edge* e, const double* p, int n) {
       e->meas[0] = p[0]; e->meas[1] = p[1];
       return true;
     }
+    case ORC_EDGE_XYZ2UV: {  // types/sba/types_six_dof_expmap.cpp:241-256: paramId u v i00 i01 i11
+      if (n < 6) return false;
+      e->paramId = (int)p[0];
+      e->meas[0] = p[1]; e->meas[1] = p[2];
+      int k = 3;
+      for (int i = 0; i < 2; ++i) for (int j = i; j < 2; ++j) { e->info[i + 2 * j] = p[k]; e->info[j + 2 * i] = p[k]; ++k; }
+      return true;
+    }
   }
   return false;
 }
@@ -944,13 +1052,17 @@ void initial_estimate_from(Edge* e) {  // from = to * meas^-1
 void set_to_origin(Vertex* v) {
   for (int i = 0; i < EST_MAX; ++i) v->est[i] = 0;
   if (v->kind == ORC_VERTEX_SE3) { v->est[0] = v->est[4] = v->est[8] = 1; }
+  if (v->kind == ORC_VERTEX_SE3_EXPMAP) v->est[6] = 1;  // SE3Quat()
   if (v->kind == ORC_VERTEX_CAM) { v->est[6] = 1; v->est[7] = 1; v->est[8] = 1; v->est[9] = 0.5; v->est[10] = 0.5; cam_refresh(v->est); }
 }
 
 int add_edge(G* g, int kind, int id1, int id2, const double* payload, int n) {
   // core/optimizable_graph.cpp:454-520 (binary edges, createEdges = true)
-  static const int vk0[3] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_XYZ};
-  static const int vk1[3] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_CAM};
+  static const int vk0[4] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_XYZ, ORC_VERTEX_XYZ};
+  static const int vk1[4] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_CAM, ORC_VERTEX_SE3_EXPMAP};
+  if (kind == ORC_EDGE_XYZ2UV) {  // OptimizableGraph::addEdge -> resolveParameters: an unknown parameter id rejects the edge
+    if (n < 1 || !g->cameraParameters.count((int)payload[0])) return -1;
+  }
   Vertex* from = g->vertex(id1);
   Vertex* to = g->vertex(id2);
   int doInit = 0;
@@ -965,6 +1077,7 @@ int add_edge(G* g, int kind, int id1, int id2, const double* payload, int n) {
   e->internalId = (int)g->edges.size() - 1;
   for (int i = 0; i < 6; ++i) e->err[i] = 0;
   if (!edge_read(e, payload, n)) { g->edges.pop_back(); return -1; }
+  if (kind == ORC_EDGE_XYZ2UV) { const auto& cp = g->cameraParameters[e->paramId]; for (int i = 0; i < 4; ++i) e->camPar[i] = cp[i]; }
   from->edges.push_back(e);
   if (to != from) to->edges.push_back(e);
   if (doInit == 1) initial_estimate_to(e);
@@ -1374,6 +1487,12 @@ int oracle_set_fixed(oracle_graph* g, int id, int fixed) {
   return 0;
 }
 
+int oracle_add_camera_parameters(oracle_graph* g, int id, double focal_length, double cx, double cy, double baseline) {
+  if (g->cameraParameters.count(id)) return -1;  // ParameterContainer::addParameter refuses duplicate ids
+  g->cameraParameters[id] = {focal_length, cx, cy, baseline};
+  return 0;
+}
+
 int oracle_load(oracle_graph* g, const char* path) {
   std::ifstream is(path);
   if (!is) return -1;
@@ -1393,6 +1512,13 @@ int oracle_load(oracle_graph* g, const char* path) {
     else if (token == "EDGE_SE2") ekind = ORC_EDGE_SE2;
     else if (token == "EDGE_SE3:QUAT") ekind = ORC_EDGE_SE3;
     else if (token == "EDGE_PROJECT_P2MC") ekind = ORC_EDGE_P2MC;
+    else if (token == "VERTEX_SE3:EXPMAP") vkind = ORC_VERTEX_SE3_EXPMAP;
+    else if (token == "EDGE_PROJECT_XYZ2UV:EXPMAP") ekind = ORC_EDGE_XYZ2UV;
+    else if (token == "PARAMS_CAMERAPARAMETERS") {  // optimizable_graph.cpp:398-415 + CameraParameters::read
+      int id; double f, cx, cy, bl;
+      if (ss >> id >> f >> cx >> cy >> bl) oracle_add_camera_parameters(g, id, f, cx, cy, bl);
+      continue;
+    }
     else continue;  // unknown tags are skipped (optimizable_graph.cpp:417-423)
     nums.clear();
     if (vkind >= 0) {
@@ -1516,6 +1642,7 @@ static int canonical_estimate(const Vertex* v, double* out) {
     case ORC_VERTEX_SE3: memcpy(out, v->est, 12 * sizeof(double)); return 12;
     case ORC_VERTEX_CAM: memcpy(out, v->est, 12 * sizeof(double)); return 12;
     case ORC_VERTEX_XYZ: memcpy(out, v->est, 3 * sizeof(double)); return 3;
+    case ORC_VERTEX_SE3_EXPMAP: memcpy(out, v->est, 7 * sizeof(double)); return 7;
   }
   return -1;
 }

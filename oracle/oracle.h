@@ -26,8 +26,8 @@ extern "C" {
 typedef struct oracle_graph oracle_graph;
 
 /* vertex / edge kinds (shared numbering with include/g2o_b200.h) */
-enum { ORC_VERTEX_SE2 = 0, ORC_VERTEX_SE3 = 1, ORC_VERTEX_CAM = 2, ORC_VERTEX_XYZ = 3 };
-enum { ORC_EDGE_SE2 = 0, ORC_EDGE_SE3 = 1, ORC_EDGE_P2MC = 2 };
+enum { ORC_VERTEX_SE2 = 0, ORC_VERTEX_SE3 = 1, ORC_VERTEX_CAM = 2, ORC_VERTEX_XYZ = 3, ORC_VERTEX_SE3_EXPMAP = 4 };
+enum { ORC_EDGE_SE2 = 0, ORC_EDGE_SE3 = 1, ORC_EDGE_P2MC = 2, ORC_EDGE_XYZ2UV = 3 };
 enum { ORC_GN = 0, ORC_LM = 1 };
 
 /* one record per outer iteration; mirrors the fields of G2OBatchStatistics (core/batch_stats.h:40-77) */
@@ -53,6 +53,9 @@ int oracle_add_edge(oracle_graph* g, int kind, int id1, int id2, const double* p
 int oracle_add_vertices(oracle_graph* g, int kind, int n, const int* ids, const double* payload, int stride);
 int oracle_add_edges(oracle_graph* g, int kind, int n, const int* id1, const int* id2, const double* payload, int stride);
 int oracle_set_fixed(oracle_graph* g, int id, int fixed);
+/* PARAMS_CAMERAPARAMETERS (types/sba/types_six_dof_expmap.h:45-80); must precede the XYZ2UV edges that name it.
+ * XYZ2UV edge payload = paramId u v i00 i01 i11 (types_six_dof_expmap.cpp:241-256) */
+int oracle_add_camera_parameters(oracle_graph* g, int id, double focal_length, double cx, double cy, double baseline);
 
 /* apps/g2o_cli/g2o.cpp:272-320: gauge fixing + marginalisation of the low-dimensional vertices.
  * returns the id of the vertex fixed as gauge, -1 if none was needed, -2 on error. */
@@ -97,7 +100,7 @@ int oracle_get_x(oracle_graph* g, double* x);
 int oracle_set_x(oracle_graph* g, const double* x);   /* overwrite solver.x() (numeric-Jacobian checks) */
 int oracle_get_errors(oracle_graph* g, double* err);    /* active edges in order, D doubles each */
 /* canonical estimate layouts: SE2 [x y th]; SE3 [R col-major 9, t 3]; CAM [t3 q(xyzw)4 fx fy cx cy b];
- * XYZ [x y z].  returns #doubles written or -1 */
+ * XYZ [x y z]; SE3_EXPMAP [t3 q(xyzw)4] (world -> camera).  returns #doubles written or -1 */
 int oracle_get_estimate(oracle_graph* g, int id, double* out);
 int oracle_vertex_count(oracle_graph* g);
 /* all vertices ascending id: ids[], kind[], hessianIndex[], flags (1 fixed | 2 marginalized) */

@@ -29,10 +29,18 @@ void gh_p2mc(const double* cam, const double* X, const double* z, double* e, dou
   p2mc_error(der, X, z, e);
   p2mc_jacobians(der, cam, X, Jp, Jc);
 }
+// est: t3 q4 f f cx cy b (world -> camera)
+void gh_xyz2uv(const double* est, const double* X, const double* z, double* e, double* Jp, double* Jc) {
+  double der[16];
+  ba_derive<1>(est, der);
+  ba_error<1>(der, X, z, e);
+  ba_jacobians<1>(der, est, X, Jp, Jc);
+}
 void gh_oplus(int kind, double* est, const double* u) {
   if (kind == 0) se2_oplus(est, u);
   else if (kind == 1) se3_oplus(est, u, false);
   else if (kind == 2) cam_oplus(est, u);
+  else if (kind == 4) expmap_oplus(est, u);
   else { est[0] += u[0]; est[1] += u[1]; est[2] += u[2]; }
 }
 void gh_inverse3(const double* m, double* r) { inverse3(m, r); }

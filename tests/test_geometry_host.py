@@ -186,3 +186,115 @@ def test_inverse3_and_oplus(gh):
     e2 = np.array([0.0, 0.0, 3.0])
     gh.gh_oplus(0, _p(e2), _p(np.array([0.0, 0.0, 1.0, 0, 0, 0])))
     assert -np.pi <= e2[2] < np.pi and abs(e2[2] - (4.0 - 2 * np.pi)) < 1e-12
+
+
+def _expmap_est(rng):
+    """[t3 q4 f f cx cy b] of a world->camera transform that looks at a point cloud around the origin"""
+    iso, q = _rand_iso(rng)
+    t = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(4, 8)])  # the scene sits in front of the camera
+    if q[3] < 0:
+        q = -q
+    return np.concatenate([t, q, [700.0, 700.0, 320.0, 240.0, 0.0]])
+
+
+def test_expmap_analytic_jacobians_vs_numeric(gh):
+    """EdgeProjectXYZ2UV::linearizeOplus against central differences through VertexSE3Expmap::oplusImpl
+    (exp(update) * estimate) - the reference's self-consistency criterion applied to the expmap family"""
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        est = _expmap_est(rng)
+        X = rng.uniform(-1, 1, 3)
+        z = rng.uniform(0, 600, 2)
+
+        def err(ests):
+            e, a, b = np.zeros(2), np.zeros(6), np.zeros(12)
+            gh.gh_xyz2uv(_p(ests[1]), _p(ests[0]), _p(z), _p(e), _p(a), _p(b))
+            return e.copy()
+        e, Jp, Jc = np.zeros(2), np.zeros(6), np.zeros(12)
+        gh.gh_xyz2uv(_p(est), _p(X), _p(z), _p(e), _p(Jp), _p(Jc))
+        Np = _numeric(err, [X, est], [3, 4], 0, 3, 2, gh)
+        Nc = _numeric(err, [X, est], [3, 4], 1, 6, 2, gh)
+        scale = max(1.0, np.abs(Nc).max())
+        assert np.abs(Jp.reshape(3, 2).T - Np).max() < 1e-5 * scale
+        assert np.abs(Jc.reshape(6, 2).T - Nc).max() < 1e-5 * scale
+
+
+def test_expmap_oplus_is_the_se3_exponential(gh):
+    """SE3Quat::exp (se3quat.h:216-252) is the matrix exponential of the twist [omega ; upsilon]: compare the device
+    oplus with scipy.linalg.expm on the homogeneous matrices, incl. the small-angle branch (theta < 1e-5)"""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(6)
+
+    def hom(est):
+        x, y, z, w = est[3:7]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, est[:3]
+        return T
+    for trial in range(60):
+        est = _expmap_est(rng)
+        u = rng.standard_normal(6) * (1e-7 if trial % 3 == 0 else 0.5 if trial % 3 == 1 else 3.0)
+        om, up = u[:3], u[3:]
+        A = np.zeros((4, 4))
+        A[:3, :3] = [[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]]
+        A[:3, 3] = up
+        want = expm(A) @ hom(est)
+        got = est.copy()
+        gh.gh_oplus(4, _p(got), _p(u))
+        assert abs(np.linalg.norm(got[3:7]) - 1) < 1e-14 and got[6] >= 0
+        assert np.abs(hom(got) - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+        assert np.array_equal(got[7:], est[7:])
+
+
+@needs_oracle
+def test_expmap_device_math_matches_oracle(gh):
+    """one XYZ2UV edge with a full information matrix: the oracle's b equals -J^T Omega e of the device math, and the
+    oracle's oplus (quaternion form, as the reference codes it) equals the device oplus"""
+    from oracle_binding import Oracle
+    rng = np.random.default_rng(7)
+    for trial in range(100):
+        c2w_iso, q = _rand_iso(rng)
+        if q[3] < 0:
+            q = -q
+        c2w = np.concatenate([c2w_iso[9:], q])
+        R = c2w_iso[:9].reshape(3, 3).T
+        X = c2w[:3] + R @ np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(2, 6)])
+        zz = rng.uniform(0, 600, 2)
+        w = np.array([rng.uniform(0.5, 2), rng.uniform(-0.3, 0.3), rng.uniform(0.5, 2)])
+        o = Oracle()
+        o.add_camera_parameters(3, 650.0, 300.0, 250.0, 0.1)
+        o.add_vertices(4, [0], c2w[None])
+        o.add_vertices(3, [1], X[None])
+        o.add_edges(3, [1], [0], np.concatenate([[3.0], zz, w])[None])
+        est = np.concatenate([o.vertex_estimate(0), [650.0, 650.0, 300.0, 250.0, 0.1]])
+        # the estimate is the inverse of the file's cam2world: maps the camera centre to the origin
+        assert np.abs(est[:3] + np.array(_rotate(est[3:7], c2w[:3]))).max() < 1e-12
+        e, A, B = np.zeros(2), np.zeros(6), np.zeros(12)
+        gh.gh_xyz2uv(_p(est), _p(X), _p(zz), _p(e), _p(A), _p(B))
+        A, B = A.reshape(3, 2).T, B.reshape(6, 2).T
+        o.initialize_optimization()
+        o.algorithm_init()
+        o.build_structure()
+        W = np.array([[w[0], w[1]], [w[1], w[2]]])
+        assert abs(o.compute_active_errors() - e @ W @ e) <= 1e-11 * max(1.0, e @ W @ e)
+        o.build_system()
+        b = o.b()
+        assert rel_err(b[:6], -B.T @ W @ e) < 1e-10
+        assert rel_err(b[6:9], -A.T @ W @ e) < 1e-10
+        u = rng.standard_normal(9) * 0.05
+        o.set_x(u)
+        o.update()
+        got = est.copy()
+        gh.gh_oplus(4, _p(got), _p(u[:6]))
+        assert rel_err(got[:7], o.vertex_estimate(0)) < 1e-13
+        assert rel_err(X + u[6:], o.vertex_estimate(1)) < 1e-15
+
+
+def _rotate(q, v):
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return R @ np.asarray(v)

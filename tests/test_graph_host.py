@@ -103,7 +103,7 @@ FIX 2
     o = g.SparseOptimizer(device=-1)
     assert o.load(f)
     vc, ec = o.counts()
-    assert list(vc) == [3, 0, 0, 0] and list(ec) == [2, 0, 0]
+    assert list(vc) == [3, 0, 0, 0, 0] and list(ec) == [2, 0, 0, 0]
     # vertex 1 was created by the first edge: estimate = x0 * z; the later VERTEX line is ignored (duplicate id)
     assert np.allclose(o.vertex_estimate(1), [1.0, 0.0, 0.5])
     assert o.setup_cli() == -1  # vertex 2 is already fixed -> no gauge needed
@@ -113,3 +113,69 @@ FIX 2
     e = g.SparseOptimizer(device=-1)
     with pytest.raises(g.B200Error):
         e.initialize_optimization()
+
+
+@needs_oracle
+def test_expmap_ba_setup_text_round_trip_and_structure(tmp_path):
+    """VERTEX_SE3:EXPMAP / PARAMS_CAMERAPARAMETERS / EDGE_PROJECT_XYZ2UV:EXPMAP (types/sba/types_six_dof_expmap.cpp):
+    programmatic ingest == text loader == oracle loader; save() writes cam2world again; the structure phase gives
+    the oracle's index mapping and Hpl / Hschur patterns"""
+    import openslam_g2o_b200 as g
+    from oracle_binding import Oracle
+    from openslam_g2o_b200 import synth
+    p = synth.expmap_ba(9, 60, seed=4)
+    path = tmp_path / "expmap.g2o"
+    synth.write_g2o(p, path)
+    a, b = g.SparseOptimizer(device=-1), g.SparseOptimizer(device=-1)
+    o, o2 = Oracle(), Oracle()
+    synth.feed(p, a)
+    synth.feed(p, o)
+    assert b.load(path) and o2.load(path)
+    vc, ec = b.counts()
+    assert list(vc) == [0, 0, 0, 60, 9] and list(ec) == [0, 0, 0, len(p["edge_v0"])]
+    for vid in list(p["cam_ids"]) + list(p["point_ids"][::7]):
+        ea, eb = a.vertex_estimate(int(vid)), b.vertex_estimate(int(vid))
+        assert np.array_equal(ea, eb)
+        n = len(o.vertex_estimate(int(vid)))
+        assert rel_err(ea[:n], o.vertex_estimate(int(vid))) < 1e-15
+        assert np.array_equal(o.vertex_estimate(int(vid)), o2.vertex_estimate(int(vid)))
+    assert np.array_equal(a.vertex_estimate(0)[7:], [1000.0, 1000.0, 320.0, 240.0, 0.0])
+    # save -> load reproduces the estimates (cam2world is written, inverted again on load) to rounding
+    out = tmp_path / "saved.g2o"
+    assert b.save(out)
+    assert "PARAMS_CAMERAPARAMETERS 0 1000" in out.read_text().splitlines()[0]
+    c = g.SparseOptimizer(device=-1)
+    assert c.load(out)
+    for vid in p["cam_ids"]:
+        assert rel_err(c.vertex_estimate(int(vid)), b.vertex_estimate(int(vid))) < 1e-14
+    # gauge, marginalisation, index mapping, patterns
+    assert a.setup_cli() == o.setup_cli(True) == 0
+    a.initialize_optimization()
+    o.initialize_optimization()
+    ids, kinds, hidx, flags = o.vertices()
+    for i, k, h, f in zip(ids, kinds, hidx, flags):
+        info = a.vertex_info(int(i))
+        assert (info["kind"], info["hessian_index"], info["fixed"], info["marginalized"]) == (int(k), int(h), bool(f & 1), bool(f & 2))
+    a._ensure_uploaded()
+    assert a.context.build_structure()
+    o.algorithm_init()
+    o.build_structure()
+    d, od = a.context.dims(), o.dims()
+    for key in ("numPoses", "numLandmarks", "sizePoses", "sizeLandmarks", "numEdges"):
+        assert d[key] == od[key], key
+    for which in (2, 3):
+        n = g.lib.b200_get_blocks(a.context.handle, which, None, None, None)
+        rows, cols = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        g.lib.b200_get_blocks(a.context.handle, which, rows.ctypes.data, cols.ctypes.data, None)
+        orows, ocols, _ = o.blocks(which)
+        assert np.array_equal(rows, orows) and np.array_equal(cols, ocols), which
+    # an edge that names an unknown parameter is rejected (resolveParameters), as is mixing the two camera models
+    with pytest.raises(g.B200Error):
+        a.add_edges(g.EDGE_XYZ2UV, [int(p["point_ids"][0])], [0], np.array([[5.0, 1, 2, 1, 0, 1]]))
+    with pytest.raises(g.B200Error):
+        a.add_edges(g.EDGE_P2MC, [int(p["point_ids"][0])], [0], np.array([[1.0, 2.0]]))
+    # two parameters with different values on one pose: unsupported, reported
+    a.add_camera_parameters(1, 500.0, 0.0, 0.0, 0.0)
+    with pytest.raises(g.B200Error) as ei:
+        a.add_edges(g.EDGE_XYZ2UV, [int(p["point_ids"][0])], [0], np.array([[1.0, 1, 2, 1, 0, 1]]))
+    assert ei.value.code == g._lib.ERR_UNSUPPORTED

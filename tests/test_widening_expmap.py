@@ -1,0 +1,153 @@
+"""the SE3-expmap bundle-adjustment family (VertexSE3Expmap / EdgeProjectXYZ2UV /
+CameraParameters, types/sba/types_six_dof_expmap.{h,cpp} - the formulation of examples/ba/ba_demo.cpp) behind the
+same kernels as the SBACam family.
+
+CPU part: the oracle restatement pinned by the reference's own criterion (analytic Jacobian vs central differences,
+types/slam3d/test_slam3d_jacobian.cpp:100-149) and by convergence to the noise floor from a perturbed start; the
+context refuses mixed camera models.  GPU part: the CUDA path against the oracle, phase by phase and over a full
+Levenberg run (1e-6 on chi2 and state, north_star)."""
+import numpy as np
+import pytest
+from conftest import needs_oracle
+from helpers import rel_err
+
+EST_TOL = 1e-6
+CHI_TOL = 1e-6
+
+
+@needs_oracle
+def test_oracle_expmap_gradient_and_convergence():
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    p = synth.expmap_ba(6, 40, seed=3)
+    o = Oracle()
+    synth.feed(p, o)
+    assert o.setup_cli(True) == 0
+    o.initialize_optimization()
+    o.algorithm_init()
+    o.build_structure()
+    chi0 = o.compute_active_errors()
+    o.build_system()
+    b = o.b()
+    n = len(b)
+    rng = np.random.default_rng(0)
+    delta = 1e-6
+    # all 6 coordinates (omega, upsilon) of two poses + a sample of the rest
+    for k in list(range(12)) + list(rng.choice(n, 12, replace=False)):
+        g = 0.0
+        for sgn in (+1, -1):
+            o.push()
+            x = np.zeros(n)
+            x[k] = sgn * delta
+            o.set_x(x)
+            o.update()
+            g += sgn * o.compute_active_errors()
+            o.pop()
+        g /= 2 * delta
+        assert abs(-0.5 * g - b[k]) <= 1e-6 * max(1.0, abs(b[k])), (k, g, b[k])
+    nit, st = o.optimize(LM, 8)
+    assert nit == 8
+    chi = [s.chi2 for s in st]
+    # 155 observations x 2, information weights ~ U(0.5, 2), pixel noise 1: the optimum sits at the noise floor
+    assert chi0 > 50 * chi[-1] and chi[-1] < 2.0 * 2 * len(p["edge_v0"])
+    assert abs(chi[-1] - chi[-2]) < 1e-9 * chi[-1]
+    # recovered structure: points close to the truth (gauge: camera 0 fixed at its perturbed pose, so only roughly)
+    pts = np.stack([o.vertex_estimate(int(i)) for i in p["point_ids"]])
+    assert np.abs(pts - p["truth_points"]).max() < 0.5
+
+
+def test_context_refuses_mixed_camera_models():
+    """XYZ2UV edges on VertexCam rows (or P2MC edges on expmap rows) would silently use the wrong projection"""
+    import openslam_g2o_b200 as g
+    L = g._lib
+    for vk, ek in ((g.VERTEX_CAM, g.EDGE_XYZ2UV), (g.VERTEX_SE3_EXPMAP, g.EDGE_P2MC)):
+        ctx = g.SolverContext(device=-1)
+        cams = np.tile(np.array([0, 0, 0, 0, 0, 0, 1.0, 500, 500, 0, 0, 0]), (2, 1)) + np.arange(2)[:, None] * 0.1
+        ctx.set_vertices(vk, cams, np.array([-1, 0], np.int32), np.zeros(2, np.uint8))
+        ctx.set_vertices(g.VERTEX_XYZ, np.array([[0.0, 0, 5]]), np.array([1], np.int32), np.ones(1, np.uint8))
+        ctx.set_edges(ek, np.array([0, 0], np.int32), np.array([0, 1], np.int32), np.zeros((2, 2)),
+                      np.tile(np.eye(2).reshape(-1), (2, 1)))
+        with pytest.raises(g.B200Error) as ei:
+            ctx.build_structure()
+        assert ei.value.code == L.ERR_UNSUPPORTED
+    # the matching pairs pass the structure phase on the host-only context
+    ctx = g.SolverContext(device=-1)
+    ctx.set_vertices(g.VERTEX_SE3_EXPMAP, cams, np.array([-1, 0], np.int32), np.zeros(2, np.uint8))
+    ctx.set_vertices(g.VERTEX_XYZ, np.array([[0.0, 0, 5]]), np.array([1], np.int32), np.ones(1, np.uint8))
+    ctx.set_edges(g.EDGE_XYZ2UV, np.array([0, 0], np.int32), np.array([0, 1], np.int32), np.zeros((2, 2)),
+                  np.tile(np.eye(2).reshape(-1), (2, 1)))
+    assert ctx.build_structure()
+    assert ctx.dims()["numPoses"] == 1 and ctx.dims()["numLandmarks"] == 1
+
+
+@pytest.mark.gpu
+@needs_oracle
+@pytest.mark.parametrize("seed,cams,points,robust", [(1, 8, 120, None), (2, 25, 900, None), (3, 12, 300, "Huber")])
+def test_expmap_bundle_adjustment_matches_oracle(seed, cams, points, robust):
+    import openslam_g2o_b200 as g
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    p = synth.expmap_ba(cams, points, seed=seed)
+    if robust:  # a few gross outliers for the kernel to act on
+        rng = np.random.default_rng(seed)
+        bad = rng.choice(len(p["edge_payload"]), len(p["edge_payload"]) // 25, replace=False)
+        p["edge_payload"][bad, 1:3] += rng.uniform(-60, 60, (len(bad), 2))
+    opt = g.SparseOptimizer(device=0)
+    opt.set_algorithm("lm_fix6_3")
+    o = Oracle()
+    synth.feed(p, opt)
+    synth.feed(p, o)
+    assert opt.setup_cli() == o.setup_cli(True) == 0
+    opt.initialize_optimization()
+    o.initialize_optimization()
+    if robust:
+        opt.set_robust_kernel(robust, 3.0)
+        o.set_robust_kernel(robust, 3.0)
+    o.algorithm_init()
+    opt._ensure_uploaded()
+    ctx = opt.context
+    assert ctx.build_structure() and o.build_structure()
+    assert abs(ctx.compute_active_errors() - o.compute_active_errors()) <= 1e-11 * o.compute_active_errors()
+    ctx.build_system()
+    o.build_system()
+    assert rel_err(ctx.b(), o.b()) < 1e-10
+    for which in (0, 1, 2):
+        gr, gc, gv = ctx.blocks(which)
+        orr, oc, ov = o.blocks(which)
+        assert np.array_equal(gr, orr) and np.array_equal(gc, oc), which
+        assert rel_err(gv, ov) < 1e-10, which
+    lam = o.lambda_init()
+    ctx.set_lambda(lam, True)
+    o.set_lambda(lam, True)
+    assert ctx.solve() and o.solve()
+    gr, gc, gv = ctx.blocks(3)
+    orr, oc, ov = o.blocks(3)
+    assert np.array_equal(gr, orr) and np.array_equal(gc, oc)
+    assert rel_err(gv, ov) < 1e-9
+    assert rel_err(ctx.bschur(), o.bschur()) < 1e-9
+    assert rel_err(ctx.x(), o.x()) < 1e-6
+    # one update through exp(update) * estimate, then the errors again
+    ctx.push()
+    o.push()
+    ctx.update()
+    o.update()
+    assert abs(ctx.compute_active_errors() - o.compute_active_errors()) <= 1e-9 * o.compute_active_errors()
+    ctx.pop()
+    o.pop()
+    ctx.restore_diagonal()
+    o.restore_diagonal()
+    # full LM run
+    n = opt.optimize(8)
+    no, st = o.optimize(LM, 8)
+    assert n == no
+    chi_g = np.array([s.chi2 for s in opt.batch_statistics])
+    chi_o = np.array([s.chi2 for s in st[:no]])
+    assert rel_err(chi_g, chi_o) < CHI_TOL
+    opt.sync_estimates()
+    ids, kinds, _, _ = o.vertices()
+    cam_err = max(rel_err(opt.vertex_estimate(int(i))[:7], o.vertex_estimate(int(i))) for i, k in zip(ids, kinds) if k == 4)
+    pts_g = np.stack([opt.vertex_estimate(int(i)) for i, k in zip(ids, kinds) if k == 3])
+    pts_o = np.stack([o.vertex_estimate(int(i)) for i, k in zip(ids, kinds) if k == 3])
+    assert cam_err < EST_TOL and rel_err(pts_g, pts_o) < EST_TOL
+    # the intrinsics ride along untouched
+    assert np.array_equal(opt.vertex_estimate(int(p["cam_ids"][1]))[7:], [1000.0, 1000.0, 320.0, 240.0, 0.0])
