@@ -1,12 +1,15 @@
 // solver_b200.cpp - g2o plugin "libg2o_solver_b200.so": registers {gn,lm}_{fix3_2,fix6_3}_b200 with g2o's
 // OptimizationAlgorithmFactory (g2o/core/optimization_algorithm_factory.h:153-162), same naming scheme as
-// g2o/solvers/cholmod/solver_cholmod.cpp:41-132.  The `g2o` binary picks it up through its *_solver_*.so glob
+// g2o/solvers/cholmod/solver_cholmod.cpp:41-132 (+ suffix _b200s: Level 2, _b200ls: Level 1).  The `g2o` binary picks it up through its *_solver_*.so glob
 // (apps/g2o_cli/g2o_common.cpp:82,133-167); programmatic users `new OptimizationAlgorithmB200(...)` directly.
 //
 // Level 3 (this file): OptimizationAlgorithmB200 keeps the whole LM / GN iteration on the GPU behind
 // b200_algorithm_solve(); the host only sees a handful of scalars per trial and gets the estimates written back into
 // the vertices at the end of every solve() (what SparseOptimizer::optimize reads when verbose / statistics are on,
 // core/sparse_optimizer.cpp:392-411).
+// Level 2 (this file): SolverB200 is a g2o::Solver (core/solver.h:44-149) for the stock OptimizationAlgorithm
+// {GaussNewton,Levenberg}: buildSystem / setLambda / solve / computeMarginals on the GPU, errors and update stay on the
+// host where those algorithms call them; x, b and the Hessian diagonal are mirrored on the host.
 // Level 1 is linear_solver_b200.h (LinearSolverB200 under the stock BlockSolver).
 //
 // Compiles only inside a g2o source tree (needs Eigen + g2o headers; neither exists in the build container).
@@ -20,6 +23,7 @@
 #include "g2o/core/optimization_algorithm_factory.h"
 #include "g2o/core/optimization_algorithm_gauss_newton.h"
 #include "g2o/core/optimization_algorithm_levenberg.h"
+#include "g2o/core/solver.h"
 #include "g2o/core/sparse_optimizer.h"
 #include "g2o/stuff/macros.h"
 #include "g2o/types/sba/types_sba.h"
@@ -33,114 +37,52 @@
 
 namespace g2o {
 
-class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
- public:
-  explicit OptimizationAlgorithmB200(int algorithm) : OptimizationAlgorithm(), _ctx(0), _algorithm(algorithm) {
-    _device = _properties.makeProperty<Property<int> >("device", 0);
-    _userLambdaInit = _properties.makeProperty<Property<double> >("initialLambda", 0.);
-    _maxTrialsAfterFailure = _properties.makeProperty<Property<int> >("maxTrialsAfterFailure", 10);
-    // 0: block AMD, the reference's ordering; k > 0: nested dissection with 2^k parts on top of it (b200_set_ordering)
-    _ndLevels = _properties.makeProperty<Property<int> >("ndLevels", 0);
+// estimate of one vertex in the C-ABI layout (include/g2o_b200.h); returns its B200_VERTEX_* kind, -1 if unsupported
+static int packEstimate(OptimizableGraph::Vertex* v, double* e) {
+  int kind = -1;
+  if (VertexSE2* p = dynamic_cast<VertexSE2*>(v)) {
+    kind = B200_VERTEX_SE2;
+    e[0] = p->estimate().translation().x(); e[1] = p->estimate().translation().y(); e[2] = p->estimate().rotation().angle();
+  } else if (VertexSE3* p = dynamic_cast<VertexSE3*>(v)) {
+    kind = B200_VERTEX_SE3;  // the state is the Isometry3d itself: R (col-major) | t, never re-quaternionised
+    Eigen::Map<Eigen::Matrix3d>(e) = p->estimate().linear();
+    Eigen::Map<Eigen::Vector3d>(e + 9) = p->estimate().translation();
+  } else if (VertexCam* p = dynamic_cast<VertexCam*>(v)) {
+    kind = B200_VERTEX_CAM;
+    const SBACam& c = p->estimate();
+    Eigen::Map<Eigen::Vector3d>(e) = c.translation();
+    Eigen::Map<Eigen::Vector4d>(e + 3) = c.rotation().coeffs();  // x y z w
+    e[7] = c.Kcam(0, 0); e[8] = c.Kcam(1, 1); e[9] = c.Kcam(0, 2); e[10] = c.Kcam(1, 2); e[11] = c.baseline;
+  } else if (VertexSE3Expmap* p = dynamic_cast<VertexSE3Expmap*>(v)) {
+    kind = B200_VERTEX_SE3_EXPMAP;  // world -> camera SE3Quat; the intrinsics [7..12) come from its edges' CameraParameters
+    Eigen::Map<Eigen::Vector3d>(e) = p->estimate().translation();
+    Eigen::Map<Eigen::Vector4d>(e + 3) = p->estimate().rotation().coeffs();  // x y z w
+    e[7] = e[8] = e[9] = e[10] = e[11] = 0.;
+  } else if (VertexSBAPointXYZ* p = dynamic_cast<VertexSBAPointXYZ*>(v)) {
+    kind = B200_VERTEX_XYZ;
+    Eigen::Map<Eigen::Vector3d>(e) = p->estimate();
   }
-  virtual ~OptimizationAlgorithmB200() { b200_destroy(_ctx); }
+  return kind;
+}
 
-  // OptimizationAlgorithmWithHessian::init (core/optimization_algorithm_with_hessian.cpp:50-73): (re)ingest the graph
-  virtual bool init(bool /*online*/ = false) {
-    if (!_ctx && b200_create(_device->value(), &_ctx) != B200_OK) {
-      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(0) << std::endl;  // no CPU fallback
-      return false;
-    }
-    b200_set_lm_params(_ctx, _userLambdaInit->value(), _maxTrialsAfterFailure->value());
-    b200_set_ordering(_ctx, _ndLevels->value());
-    return ingest();
-  }
-
-  virtual SolverResult solve(int iteration, bool /*online*/ = false) {
-    b200_iter_stats st;
-    int rc = b200_algorithm_solve(_ctx, _algorithm, iteration, &st);
-    if (rc < 0 && rc != B200_RESULT_FAIL) {
-      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
-      return Fail;
-    }
-    G2OBatchStatistics* gs = G2OBatchStatistics::globalStats();
-    if (gs) {  // same fields the CPU path fills (core/batch_stats.h:40-77)
-      gs->levenbergIterations = st.levenberg_iterations;
-      gs->timeIteration = st.time_iteration;
-      gs->timeSymbolicDecomposition = st.time_symbolic;
-      gs->choleskyNNZ = static_cast<size_t>(b200_get_factor_nnz(_ctx));
-    }
-    _lambda = st.lambda;
-    _levenbergIterations = st.levenberg_iterations;
-    writeBack();
-    return static_cast<SolverResult>(st.result);
-  }
-
-  // OptimizationAlgorithmWithHessian::computeMarginals -> Solver::computeMarginals (core/block_solver.hpp:490-499)
-  virtual bool computeMarginals(SparseBlockMatrix<MatrixXd>& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
-    if (blockIndices.empty()) return true;
-    int dims[8];
-    if (b200_get_dims(_ctx, dims) != B200_OK) return false;
-    const int d = dims[6];
-    if (b200_build_system(_ctx) != B200_OK) return false;  // Hpp at the current estimates, no lambda
-    std::vector<int32_t> rows(blockIndices.size()), cols(blockIndices.size());
-    for (size_t q = 0; q < blockIndices.size(); ++q) { rows[q] = blockIndices[q].first; cols[q] = blockIndices[q].second; }
-    std::vector<double> out(blockIndices.size() * d * d);
-    if (b200_compute_marginals(_ctx, static_cast<int>(rows.size()), &rows[0], &cols[0], &out[0]) != B200_OK) {
-      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
-      return false;
-    }
-    // same layout as MarginalCovarianceCholesky::computeCovariance: uniform d x d blocks indexed by Hessian index
-    std::vector<int> blockEnds(dims[0]);
-    for (int i = 0; i < dims[0]; ++i) blockEnds[i] = (i + 1) * d;
-    spinv = SparseBlockMatrix<MatrixXd>(&blockEnds[0], &blockEnds[0], dims[0], dims[0], true);
-    for (size_t q = 0; q < blockIndices.size(); ++q) {
-      MatrixXd* blk = spinv.block(rows[q], cols[q], true);
-      *blk = Eigen::Map<const Eigen::MatrixXd>(&out[q * d * d], d, d);
-    }
-    return true;
-  }
-  virtual bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) { return false; }
-  virtual void printVerbose(std::ostream& os) const {
-    os << "\t schur= " << (_hasLandmarks ? 1 : 0) << "\t lambda= " << FIXED(_lambda) << "\t levenbergIter= " << _levenbergIterations;
-  }
-
- protected:
+// the pointer graph <-> SoA arrays of the C-ABI, shared by the Level-3 algorithm and the Level-2 solver
+struct B200GraphBinding {
   // one-time packing of the pointer graph into SoA arrays (what BlockSolver::buildStructure walks,
   // core/block_solver.hpp:142-295).  Unknown vertex / edge types -> false (no CPU fallback).
-  bool ingest() {
+  bool ingest(b200_ctx* _ctx, SparseOptimizer* _optimizer) {
     const SparseOptimizer::VertexContainer& verts = _optimizer->activeVertices();
     const SparseOptimizer::EdgeContainer& edges = _optimizer->activeEdges();
-    std::vector<double> est[B200_NUM_VERTEX_KINDS];
+    std::vector<double>* est = _est;
+    for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k) _est[k].clear();
     std::vector<int32_t> hidx[B200_NUM_VERTEX_KINDS];
     std::vector<uint8_t> marg[B200_NUM_VERTEX_KINDS];
     _slot.clear();
     for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k) _verts[k].clear();
     for (size_t i = 0; i < verts.size(); ++i) {
       OptimizableGraph::Vertex* v = verts[i];
-      int kind = -1;
       double e[12];
-      if (VertexSE2* p = dynamic_cast<VertexSE2*>(v)) {
-        kind = B200_VERTEX_SE2;
-        e[0] = p->estimate().translation().x(); e[1] = p->estimate().translation().y(); e[2] = p->estimate().rotation().angle();
-      } else if (VertexSE3* p = dynamic_cast<VertexSE3*>(v)) {
-        kind = B200_VERTEX_SE3;  // the state is the Isometry3d itself: R (col-major) | t, never re-quaternionised
-        Eigen::Map<Eigen::Matrix3d>(e) = p->estimate().linear();
-        Eigen::Map<Eigen::Vector3d>(e + 9) = p->estimate().translation();
-      } else if (VertexCam* p = dynamic_cast<VertexCam*>(v)) {
-        kind = B200_VERTEX_CAM;
-        const SBACam& c = p->estimate();
-        Eigen::Map<Eigen::Vector3d>(e) = c.translation();
-        Eigen::Map<Eigen::Vector4d>(e + 3) = c.rotation().coeffs();  // x y z w
-        e[7] = c.Kcam(0, 0); e[8] = c.Kcam(1, 1); e[9] = c.Kcam(0, 2); e[10] = c.Kcam(1, 2); e[11] = c.baseline;
-      } else if (VertexSE3Expmap* p = dynamic_cast<VertexSE3Expmap*>(v)) {
-        kind = B200_VERTEX_SE3_EXPMAP;  // world -> camera SE3Quat; the intrinsics [7..12) come from its edges' CameraParameters
-        Eigen::Map<Eigen::Vector3d>(e) = p->estimate().translation();
-        Eigen::Map<Eigen::Vector4d>(e + 3) = p->estimate().rotation().coeffs();  // x y z w
-        e[7] = e[8] = e[9] = e[10] = e[11] = 0.;
-      } else if (VertexSBAPointXYZ* p = dynamic_cast<VertexSBAPointXYZ*>(v)) {
-        kind = B200_VERTEX_XYZ;
-        Eigen::Map<Eigen::Vector3d>(e) = p->estimate();
-      } else {
+      const int kind = packEstimate(v, e);
+      if (kind < 0) {
         std::cerr << "OptimizationAlgorithmB200: unsupported vertex type (id " << v->id() << ")" << std::endl;
         return false;
       }
@@ -229,7 +171,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
   }
 
   // device estimates -> vertices
-  void writeBack() {
+  void writeBack(b200_ctx* _ctx) {
     std::vector<double> buf;
     for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
       const std::vector<OptimizableGraph::Vertex*>& vs = _verts[kind];
@@ -261,17 +203,195 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     }
   }
 
+  // host vertices -> device estimates (Level 2: SparseOptimizer::update / push / pop run on the host between solves)
+  bool pushEstimates(b200_ctx* ctx) {
+    for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
+      const std::vector<OptimizableGraph::Vertex*>& vs = _verts[kind];
+      if (vs.empty()) continue;
+      const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
+      const int keep = kind == B200_VERTEX_SE3_EXPMAP ? 7 : ne;  // expmap rows keep the intrinsics found at ingest
+      for (size_t i = 0; i < vs.size(); ++i) {
+        double e[12];
+        if (packEstimate(vs[i], e) != kind) return false;
+        for (int k = 0; k < keep; ++k) _est[kind][i * ne + k] = e[k];
+      }
+      if (b200_set_estimates(ctx, kind, &_est[kind][0]) != B200_OK) return false;
+    }
+    return true;
+  }
+
+  bool _hasLandmarks;
+  std::map<OptimizableGraph::Vertex*, int> _slot;
+  std::vector<OptimizableGraph::Vertex*> _verts[B200_NUM_VERTEX_KINDS];
+  std::vector<double> _est[B200_NUM_VERTEX_KINDS];  // rows as handed to b200_set_vertices
+};
+
+// Solver::computeMarginals (core/block_solver.hpp:490-499) -> LinearSolver::solvePattern -> MarginalCovarianceCholesky
+static bool b200Marginals(b200_ctx* _ctx, SparseBlockMatrix<MatrixXd>& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
+  if (blockIndices.empty()) return true;
+  int dims[8];
+  if (b200_get_dims(_ctx, dims) != B200_OK) return false;
+  const int d = dims[6];
+  if (b200_build_system(_ctx) != B200_OK) return false;  // Hpp at the current estimates, no lambda
+  std::vector<int32_t> rows(blockIndices.size()), cols(blockIndices.size());
+  for (size_t q = 0; q < blockIndices.size(); ++q) { rows[q] = blockIndices[q].first; cols[q] = blockIndices[q].second; }
+  std::vector<double> out(blockIndices.size() * d * d);
+  if (b200_compute_marginals(_ctx, static_cast<int>(rows.size()), &rows[0], &cols[0], &out[0]) != B200_OK) {
+    std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
+    return false;
+  }
+  // same layout as MarginalCovarianceCholesky::computeCovariance: uniform d x d blocks indexed by Hessian index
+  std::vector<int> blockEnds(dims[0]);
+  for (int i = 0; i < dims[0]; ++i) blockEnds[i] = (i + 1) * d;
+  spinv = SparseBlockMatrix<MatrixXd>(&blockEnds[0], &blockEnds[0], dims[0], dims[0], true);
+  for (size_t q = 0; q < blockIndices.size(); ++q) {
+    MatrixXd* blk = spinv.block(rows[q], cols[q], true);
+    *blk = Eigen::Map<const Eigen::MatrixXd>(&out[q * d * d], d, d);
+  }
+  return true;
+}
+
+class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
+ public:
+  explicit OptimizationAlgorithmB200(int algorithm) : OptimizationAlgorithm(), _ctx(0), _algorithm(algorithm) {
+    _device = _properties.makeProperty<Property<int> >("device", 0);
+    _userLambdaInit = _properties.makeProperty<Property<double> >("initialLambda", 0.);
+    _maxTrialsAfterFailure = _properties.makeProperty<Property<int> >("maxTrialsAfterFailure", 10);
+    // 0: block AMD, the reference's ordering; k > 0: nested dissection with 2^k parts on top of it (b200_set_ordering)
+    _ndLevels = _properties.makeProperty<Property<int> >("ndLevels", 0);
+  }
+  virtual ~OptimizationAlgorithmB200() { b200_destroy(_ctx); }
+
+  // OptimizationAlgorithmWithHessian::init (core/optimization_algorithm_with_hessian.cpp:50-73): (re)ingest the graph
+  virtual bool init(bool /*online*/ = false) {
+    if (!_ctx && b200_create(_device->value(), &_ctx) != B200_OK) {
+      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(0) << std::endl;  // no CPU fallback
+      return false;
+    }
+    b200_set_lm_params(_ctx, _userLambdaInit->value(), _maxTrialsAfterFailure->value());
+    b200_set_ordering(_ctx, _ndLevels->value());
+    return _graph.ingest(_ctx, _optimizer);
+  }
+
+  virtual SolverResult solve(int iteration, bool /*online*/ = false) {
+    b200_iter_stats st;
+    int rc = b200_algorithm_solve(_ctx, _algorithm, iteration, &st);
+    if (rc < 0 && rc != B200_RESULT_FAIL) {
+      std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
+      return Fail;
+    }
+    G2OBatchStatistics* gs = G2OBatchStatistics::globalStats();
+    if (gs) {  // same fields the CPU path fills (core/batch_stats.h:40-77)
+      gs->levenbergIterations = st.levenberg_iterations;
+      gs->timeIteration = st.time_iteration;
+      gs->timeSymbolicDecomposition = st.time_symbolic;
+      gs->choleskyNNZ = static_cast<size_t>(b200_get_factor_nnz(_ctx));
+    }
+    _lambda = st.lambda;
+    _levenbergIterations = st.levenberg_iterations;
+    _graph.writeBack(_ctx);
+    return static_cast<SolverResult>(st.result);
+  }
+
+  // OptimizationAlgorithmWithHessian::computeMarginals -> Solver::computeMarginals (core/block_solver.hpp:490-499)
+  virtual bool computeMarginals(SparseBlockMatrix<MatrixXd>& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
+    return b200Marginals(_ctx, spinv, blockIndices);
+  }
+  virtual bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) { return false; }
+  virtual void printVerbose(std::ostream& os) const {
+    os << "\t schur= " << (_graph._hasLandmarks ? 1 : 0) << "\t lambda= " << FIXED(_lambda) << "\t levenbergIter= " << _levenbergIterations;
+  }
+
+ protected:
   b200_ctx* _ctx;
   int _algorithm;
-  bool _hasLandmarks;
+  B200GraphBinding _graph;
   double _lambda;
   int _levenbergIterations;
   Property<int>* _device;
   Property<int>* _ndLevels;
   Property<double>* _userLambdaInit;
   Property<int>* _maxTrialsAfterFailure;
-  std::map<OptimizableGraph::Vertex*, int> _slot;
-  std::vector<OptimizableGraph::Vertex*> _verts[B200_NUM_VERTEX_KINDS];
+};
+
+
+// ----------------------------------------------------------------------------------------------- Level 2
+// g2o::Solver (core/solver.h:44-149) under the stock OptimizationAlgorithm{GaussNewton,Levenberg}.  Those algorithms
+// evaluate the errors and apply the update on the host (SparseOptimizer::computeActiveErrors / update / push / pop), so
+// the estimates are re-sent before every buildSystem(); they read x() and b() for computeScale
+// (optimization_algorithm_levenberg.cpp:165-172) and v->hessian(j,j) for computeLambdaInit (:149-163), which is why x, b
+// and the diagonal of every vertex block are mirrored on the host.
+class SolverB200 : public Solver {
+ public:
+  explicit SolverB200(int device = 0, int ndLevels = 0) : Solver(), _ctx(0), _device(device), _ndLevels(ndLevels), _writeDebug(true) {}
+  virtual ~SolverB200() { b200_destroy(_ctx); }
+
+  virtual bool init(SparseOptimizer* optimizer, bool /*online*/ = false) {
+    _optimizer = optimizer;
+    if (!_ctx && b200_create(_device, &_ctx) != B200_OK) {
+      std::cerr << "SolverB200: " << b200_last_error(0) << std::endl;  // no CPU fallback
+      return false;
+    }
+    return b200_set_ordering(_ctx, _ndLevels) == B200_OK;
+  }
+  // BlockSolver::buildStructure (core/block_solver.hpp:142-295): index mapping -> patterns -> symbolic factorisation
+  virtual bool buildStructure(bool /*zeroBlocks*/ = false) {
+    if (!_graph.ingest(_ctx, _optimizer)) return false;
+    int dims[8];
+    if (b200_get_dims(_ctx, dims) != B200_OK) return false;
+    resizeVector(static_cast<size_t>(dims[2] + dims[3]));
+    // host storage of the diagonal blocks, mapped into the vertices like BlockSolver does (block_solver.hpp:181-197)
+    const std::vector<OptimizableGraph::Vertex*>& iv = _optimizer->indexMapping();
+    size_t total = 0;
+    for (size_t i = 0; i < iv.size(); ++i) total += static_cast<size_t>(iv[i]->dimension()) * iv[i]->dimension();
+    _diagBlocks.assign(total, 0.);
+    _diag.resize(_xSize);
+    size_t off = 0;
+    for (size_t i = 0; i < iv.size(); ++i) {
+      iv[i]->mapHessianMemory(&_diagBlocks[off]);
+      off += static_cast<size_t>(iv[i]->dimension()) * iv[i]->dimension();
+    }
+    return true;
+  }
+  virtual bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) { return false; }
+  // BlockSolver::buildSystem (core/block_solver.hpp:501-560) at the estimates the host vertices hold now
+  virtual bool buildSystem() {
+    if (!_graph.pushEstimates(_ctx) || b200_build_system(_ctx) != B200_OK) return report();
+    if (b200_get_b(_ctx, _b) != B200_OK || b200_get_hessian_diagonal(_ctx, &_diag[0]) != B200_OK) return report();
+    const std::vector<OptimizableGraph::Vertex*>& iv = _optimizer->indexMapping();
+    size_t k = 0;
+    for (size_t i = 0; i < iv.size(); ++i)
+      for (int j = 0; j < iv[i]->dimension(); ++j) iv[i]->hessian(j, j) = _diag[k++];
+    return true;
+  }
+  virtual bool solve() {
+    const int rc = b200_solve(_ctx);
+    if (rc < 0) return report();
+    if (rc == B200_NOT_POSITIVE_DEFINITE) return false;  // LM raises lambda and tries again
+    return b200_get_x(_ctx, _x) == B200_OK;
+  }
+  virtual bool computeMarginals(SparseBlockMatrix<MatrixXd>& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
+    return b200Marginals(_ctx, spinv, blockIndices);
+  }
+  virtual bool setLambda(double lambda, bool backup = false) { return b200_set_lambda(_ctx, lambda, backup ? 1 : 0) == B200_OK; }
+  virtual void restoreDiagonal() { b200_restore_diagonal(_ctx); }
+  virtual bool supportsSchur() { return true; }
+  virtual bool schur() { return _graph._hasLandmarks; }
+  virtual void setSchur(bool) {}  // decided by the graph: marginalized XYZ vertices <=> Schur complement
+  virtual void setWriteDebug(bool b) { _writeDebug = b; }
+  virtual bool writeDebug() const { return _writeDebug; }
+  virtual bool saveHessian(const std::string&) const { return false; }
+
+ protected:
+  bool report() {
+    std::cerr << "SolverB200: " << b200_last_error(_ctx) << std::endl;
+    return false;
+  }
+  b200_ctx* _ctx;
+  int _device, _ndLevels;
+  bool _writeDebug;
+  B200GraphBinding _graph;
+  std::vector<double> _diagBlocks, _diag;
 };
 
 // ----------------------------------------------------------------------------------------------- registration
@@ -280,9 +400,11 @@ static OptimizationAlgorithm* createSolverB200(const std::string& fullSolverName
   const std::string rest = fullSolverName.substr(3);
   if (rest == "fix3_2_b200" || rest == "fix6_3_b200")  // Level 3: whole iteration on the GPU
     return new OptimizationAlgorithmB200(method == "gn" ? B200_GAUSS_NEWTON : B200_LEVENBERG);
+  // Level 2: stock LM/GN control, errors and update on the host; system, Schur complement and Cholesky on the GPU
   // Level 1: stock BlockSolver + LM/GN on the host, only the linear solver on the GPU
   Solver* s = 0;
-  if (rest == "fix3_2_b200ls") s = new BlockSolver_3_2(new LinearSolverB200<BlockSolver_3_2::PoseMatrixType>());
+  if (rest == "fix3_2_b200s" || rest == "fix6_3_b200s") s = new SolverB200();
+  else if (rest == "fix3_2_b200ls") s = new BlockSolver_3_2(new LinearSolverB200<BlockSolver_3_2::PoseMatrixType>());
   else if (rest == "fix6_3_b200ls") s = new BlockSolver_6_3(new LinearSolverB200<BlockSolver_6_3::PoseMatrixType>());
   else return 0;
   if (method == "gn") return new OptimizationAlgorithmGaussNewton(s);
@@ -306,6 +428,10 @@ B200_REGISTER(gn_fix3_2_b200, "Gauss-Newton: device-resident solver on B200 (fix
 B200_REGISTER(gn_fix6_3_b200, "Gauss-Newton: device-resident solver on B200 (fixed blocksize)", 6, 3);
 B200_REGISTER(lm_fix3_2_b200, "Levenberg: device-resident solver on B200 (fixed blocksize)", 3, 2);
 B200_REGISTER(lm_fix6_3_b200, "Levenberg: device-resident solver on B200 (fixed blocksize)", 6, 3);
+B200_REGISTER(gn_fix3_2_b200s, "Gauss-Newton: B200 solver (system, Schur, Cholesky) under the stock algorithm", 3, 2);
+B200_REGISTER(gn_fix6_3_b200s, "Gauss-Newton: B200 solver (system, Schur, Cholesky) under the stock algorithm", 6, 3);
+B200_REGISTER(lm_fix3_2_b200s, "Levenberg: B200 solver (system, Schur, Cholesky) under the stock algorithm", 3, 2);
+B200_REGISTER(lm_fix6_3_b200s, "Levenberg: B200 solver (system, Schur, Cholesky) under the stock algorithm", 6, 3);
 B200_REGISTER(gn_fix3_2_b200ls, "Gauss-Newton: BlockSolver + B200 supernodal Cholesky", 3, 2);
 B200_REGISTER(gn_fix6_3_b200ls, "Gauss-Newton: BlockSolver + B200 supernodal Cholesky", 6, 3);
 B200_REGISTER(lm_fix3_2_b200ls, "Levenberg: BlockSolver + B200 supernodal Cholesky", 3, 2);
