@@ -82,8 +82,8 @@ def test_context_refuses_mixed_camera_models():
 
 @pytest.mark.gpu
 @needs_oracle
-@pytest.mark.parametrize("seed,cams,points,robust", [(1, 8, 120, None), (2, 25, 900, None), (3, 12, 300, "Huber")])
-def test_expmap_bundle_adjustment_matches_oracle(seed, cams, points, robust):
+@pytest.mark.parametrize("seed,cams,points,robust,iters", [(1, 8, 120, None, 5), (2, 25, 900, None, 7), (3, 12, 300, "Huber", 6)])
+def test_expmap_bundle_adjustment_matches_oracle(seed, cams, points, robust, iters):
     import openslam_g2o_b200 as g
     from oracle_binding import LM, Oracle
     from openslam_g2o_b200 import synth
@@ -136,10 +136,11 @@ def test_expmap_bundle_adjustment_matches_oracle(seed, cams, points, robust):
     o.pop()
     ctx.restore_diagonal()
     o.restore_diagonal()
-    # full LM run
-    n = opt.optimize(8)
-    no, st = o.optimize(LM, 8)
-    assert n == no
+    # full LM run; the iteration counts stop before the chi2 decrease reaches rounding level, where accepting or
+    # rejecting a step (and with it the 10-failed-trials Terminate) is decided by the last bits
+    n = opt.optimize(iters)
+    no, st = o.optimize(LM, iters)
+    assert n == no == iters
     chi_g = np.array([s.chi2 for s in opt.batch_statistics])
     chi_o = np.array([s.chi2 for s in st[:no]])
     assert rel_err(chi_g, chi_o) < CHI_TOL
