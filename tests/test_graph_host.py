@@ -179,3 +179,41 @@ def test_expmap_ba_setup_text_round_trip_and_structure(tmp_path):
     with pytest.raises(g.B200Error) as ei:
         a.add_edges(g.EDGE_XYZ2UV, [int(p["point_ids"][0])], [0], np.array([[1.0, 1, 2, 1, 0, 1]]))
     assert ei.value.code == g._lib.ERR_UNSUPPORTED
+
+
+def test_parallel_loader_equals_sequential(tmp_path, monkeypatch):
+    """the loader tokenises the text in per-thread chunks and applies the records in file order: any thread count gives
+    the graph a line-by-line reader builds - including a vertex that an EDGE line creates before its VERTEX line and FIX
+    lines that refer to vertices of an earlier chunk"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    p = synth.sphere(40, 30, seed=5)          # 1200 poses / ~4700 edges: > 1 MiB of text, i.e. several chunks
+    path = tmp_path / "s.g2o"
+    synth.write_g2o(p, path)
+    txt = path.read_text().splitlines()
+    nvert = len(p["vertex_ids"])
+    # move one VERTEX line behind the edges (the first edge that touches it creates it), fix two vertices at the end
+    moved = txt.pop(700)
+    txt += [moved, "FIX 3 900", "# trailing comment", ""]
+    path.write_text("\n".join(txt))
+    assert path.stat().st_size > (1 << 20)
+    graphs = []
+    for threads in ("1", "2", "7"):
+        monkeypatch.setenv("G2O_B200_LOADER_THREADS", threads)
+        o = g.SparseOptimizer(device=-1)
+        assert o.load(path)
+        graphs.append(o)
+    vc, ec = graphs[0].counts()
+    assert vc[g.VERTEX_SE3] == nvert and ec[g.EDGE_SE3] == len(p["edge_v0"])
+    for o in graphs[1:]:
+        assert [list(c) for c in o.counts()] == [list(c) for c in graphs[0].counts()]
+        for vid in list(range(0, nvert, 37)) + [3, 700, 900]:
+            assert np.array_equal(o.vertex_estimate(vid), graphs[0].vertex_estimate(vid))
+            assert o.vertex_info(vid) == graphs[0].vertex_info(vid)
+    assert graphs[0].vertex_info(3)["fixed"] and graphs[0].vertex_info(900)["fixed"]
+    # vertex 700 was created by an edge (initialEstimate from its neighbour), the later VERTEX line is a duplicate
+    assert not np.array_equal(graphs[0].vertex_estimate(700)[9:], p["vertex_payload"][700][:3])
+    for o in graphs:
+        assert o.setup_cli() == -1
+        o.initialize_optimization()
+    assert graphs[2].vertex_info(901) == graphs[0].vertex_info(901)
