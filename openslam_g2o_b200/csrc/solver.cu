@@ -94,6 +94,10 @@ static size_t schur_range_smem(const b200_ctx* c) {
 }
 
 int build_structure_impl(b200_ctx* c) {
+  double _t_last = wall();
+  const bool _tv = getenv("G2O_B200_STRUCT_VERBOSE") != nullptr;
+#define STAMP(name) do { if (_tv) { double _n = wall(); fprintf(stderr, "  structure %-28s %.3f s\n", name, _n - _t_last); _t_last = _n; } } while (0)
+
   double t0 = wall();
   drop_graphs(c);
   cudaStream_t s = c->stream;
@@ -186,6 +190,7 @@ int build_structure_impl(b200_ctx* c) {
     }
     if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
   }
+  STAMP("checks + vertex upload");
   const int ntot = c->sizeP + c->sizeL;
   c->d_b.alloc(ntot); c->d_x.alloc(ntot);
   c->d_b.zero(s); c->d_x.zero(s);
@@ -287,6 +292,7 @@ int build_structure_impl(b200_ctx* c) {
       if (la != lb) return la < lb;
       return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
     });
+  STAMP("edge sort by landmark");
     std::vector<int> lm_order(nl), lm_rank(nl);
     {
       std::vector<int> cl_ptr(nl + 1, 0), cl;  // per landmark: ascending distinct free cameras
@@ -313,6 +319,7 @@ int build_structure_impl(b200_ctx* c) {
       });
       for (int i = 0; i < nl; ++i) lm_rank[lm_order[i]] = i;
     }
+  STAMP("landmark ranking");
     // device edge order: by landmark rank (fixed points last), then camera pose index, then input order
     auto rkey = [&](int e) { int l = lm_lidx[c->e_vi[e]]; return l < 0 ? nl : lm_rank[l]; };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
@@ -320,6 +327,7 @@ int build_structure_impl(b200_ctx* c) {
       if (la != lb) return la < lb;
       return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
     });
+  STAMP("edge sort by rank");
     c->e_order = order;
     std::vector<int> e_pt(E), e_cam(E), e_pose(E), e_hpl(E, -1), lm_eptr(nl + 1, 0);
     std::vector<unsigned char> e_first(E, 0);
@@ -343,6 +351,7 @@ int build_structure_impl(b200_ctx* c) {
     }
     for (int l = 0; l < nl; ++l) lm_eptr[l + 1] += lm_eptr[l];
     c->n_hpl = nslot;
+  STAMP("edge arrays + Hpl slots");
     // camera observation lists (ascending device edge index)
     std::vector<int> cam_eptr(np + 1, 0), cam_eidx;
     for (int q = 0; q < E; ++q) if (e_pose[q] >= 0) cam_eptr[e_pose[q] + 1]++;
@@ -357,6 +366,7 @@ int build_structure_impl(b200_ctx* c) {
     c->hpp_colptr.resize(np + 1); c->hpp_rowidx.resize(np); c->hpp_diag_block.resize(np);
     for (int i = 0; i < np; ++i) { c->hpp_colptr[i] = i; c->hpp_rowidx[i] = i; c->hpp_diag_block[i] = i; }
     c->hpp_colptr[np] = np;
+  STAMP("camera lists");
     // Hschur pattern (block_solver.hpp:262-288): Hpp pattern + co-observation pairs (i1<=i2)
     std::vector<long long> keys;
     auto compact = [&]() { std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end()); };
@@ -392,6 +402,7 @@ int build_structure_impl(b200_ctx* c) {
       long long key = ((long long)col << 32) | row;
       return (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
     };
+  STAMP("Hschur pattern");
     // ---- Schur plan (kernels.cuh: schur_range_kernel / schur_finish_kernel)
     std::vector<int> lm_s0(nl + 1, 0);  // distinct Hpl slots per landmark rank (slots are numbered in rank order)
     {
@@ -411,6 +422,7 @@ int build_structure_impl(b200_ctx* c) {
       std::stable_sort(c->hpl_export.begin(), c->hpl_export.end(), [&](int x, int y) { return c->hpl_col[x] < c->hpl_col[y]; });
     }
     {
+  STAMP("hpl export order");
       // shared memory per range CTA (kernels.cuh): 3 CTAs per SM unless one landmark alone needs more slots
       int kmax = 0;
       for (int l : pi) kmax = std::max(kmax, lm_s0[l + 1] - lm_s0[l]);
@@ -479,6 +491,7 @@ int build_structure_impl(b200_ctx* c) {
         B200_CUDA(cudaFuncSetAttribute(k::schur_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_range_smem(c)));
       }
     }
+  STAMP("Schur plan");
     c->d_ev0.upload(e_pt, s); c->d_ev1.upload(e_cam, s); c->d_e_pose.upload(e_pose, s); c->d_e_hpl.upload(e_hpl, s);
     c->d_e_flag.upload(e_first, s);
     c->d_meas.upload(meas, s); c->d_info.upload(info, s);
@@ -492,6 +505,7 @@ int build_structure_impl(b200_ctx* c) {
     if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
     bp_colptr = c->hs_colptr; bp_rowidx = c->hs_rowidx;
   }
+  STAMP("uploads");
   // ---- symbolic phase of the linear solver
   SymbolicOptions opt;
   // tuning knobs (the adapter exposes them as solver properties; the environment overrides are for experiments)
@@ -504,6 +518,7 @@ int build_structure_impl(b200_ctx* c) {
   opt.nd_levels = c->nd_levels;
   if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
+  STAMP("symbolic (ordering + plan)");
   c->structured = true;
   c->backup_depth = 0;
   c->time_symbolic = wall() - t0;
