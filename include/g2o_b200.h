@@ -193,6 +193,11 @@ int b200_ls_get_block_ordering(b200_linear_solver* ls, int32_t* perm);
 int64_t b200_ls_get_factor_nnz(b200_linear_solver* ls);
 const char* b200_ls_last_error(const b200_linear_solver* ls);
 
+/* FNV-1a digest of every array host-only contexts (device -1) of the calling thread have prepared for the device since
+ * the last reset: the complete plan of the structure phase (edge order, gather lists, Schur ranges, Cholesky task
+ * list ...).  Regression aid: host-side changes of b200_build_structure must leave it unchanged. */
+uint64_t b200_debug_upload_digest(int reset);
+
 /* ------------------------------------------------------------------ host-only helpers (no GPU needed)
  * The ordering by itself, for parity checks against cs_amd. */
 int b200_block_amd(int nblocks, const int32_t* colptr, const int32_t* rowidx, int32_t* perm);

@@ -92,6 +92,7 @@ def _load():
         "b200_set_ordering": (i32, [vp, i32]),
         "b200_compute_marginals": (i32, [vp, i32, vp, vp, vp]),
         "b200_get_launch_count": (i64, [vp]),
+        "b200_debug_upload_digest": (C.c_uint64, [i32]),
         "b200_set_profiling": (i32, [vp, i32]),
         "b200_get_phase_time": (i32, [vp, i32, C.POINTER(dbl), C.POINTER(i64)]),
         "b200_ls_create": (i32, [i32, C.POINTER(vp)]),

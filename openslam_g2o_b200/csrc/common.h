@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,22 @@ inline bool& host_only_flag() {
   return f;
 }
 
+// FNV-1a over every array a host-only context "uploads": a digest of the complete device-side plan of the structure
+// phase (b200_debug_upload_digest), used to check that host-side optimisations leave the plan bit-identical
+inline uint64_t& upload_digest() {
+  static thread_local uint64_t h = 1469598103934665603ull;
+  return h;
+}
+inline void digest_bytes(const void* data, size_t bytes) {
+  uint64_t h = upload_digest();
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  // 8 bytes per step: enough for a regression digest, ~1 GB/s
+  size_t i = 0;
+  for (; i + 8 <= bytes; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h = (h ^ w) * 1099511628211ull; }
+  for (; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  upload_digest() = (h ^ bytes) * 1099511628211ull;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -62,12 +79,12 @@ struct DevBuf {
   }
   void upload(const std::vector<T>& h, cudaStream_t s) {
     alloc(h.size());
-    if (host_only_flag()) return;
+    if (host_only_flag()) { digest_bytes(h.data(), h.size() * sizeof(T)); return; }
     if (!h.empty()) B200_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   }
   void upload(const T* h, size_t count, cudaStream_t s) {
     alloc(count);
-    if (host_only_flag()) return;
+    if (host_only_flag()) { digest_bytes(h, count * sizeof(T)); return; }
     if (count) B200_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
   }
   void zero(cudaStream_t s) {

@@ -284,67 +284,106 @@ int build_structure_impl(b200_ctx* c) {
     // landmarks feed the same Hschur blocks and a contiguous range of Hpl is one Schur work unit.  Every
     // landmark-major device structure (edge order, lm_eptr, Hpl slots) follows it; arrays indexed by the landmark's
     // Hessian index (estimates, Hll, b, x, Dinv) are reached through lm_order.
-    std::vector<int> order(E);
-    for (int e = 0; e < E; ++e) order[e] = e;
+    // edges grouped by landmark (fixed points = group nl, last), inside a group ascending camera pose index, ties in
+    // input order: a counting sort over the landmarks + a small stable sort per group (k is 2..10 for most landmarks)
     auto lkey = [&](int e) { int l = lm_lidx[c->e_vi[e]]; return l < 0 ? nl : l; };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      int la = lkey(a), lb = lkey(b);
-      if (la != lb) return la < lb;
-      return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
-    });
+    std::vector<int> order(E), grp_ptr(nl + 2, 0);
+    std::vector<int> e_cam_hidx(E);
+    for (int e = 0; e < E; ++e) { grp_ptr[lkey(e) + 1]++; e_cam_hidx[e] = PV.hidx[c->e_vj[e]]; }
+    for (int l = 0; l <= nl; ++l) grp_ptr[l + 1] += grp_ptr[l];
+    {
+      std::vector<int> fill(grp_ptr.begin(), grp_ptr.end() - 1);
+      for (int e = 0; e < E; ++e) order[fill[lkey(e)]++] = e;
+      for (int l = 0; l <= nl; ++l) {
+        int* b0 = order.data() + grp_ptr[l];
+        const int k2 = grp_ptr[l + 1] - grp_ptr[l];
+        if (k2 <= 24) {  // stable insertion sort
+          for (int i = 1; i < k2; ++i) {
+            const int v = b0[i], kv = e_cam_hidx[v];
+            int j = i - 1;
+            for (; j >= 0 && e_cam_hidx[b0[j]] > kv; --j) b0[j + 1] = b0[j];
+            b0[j + 1] = v;
+          }
+        } else {
+          std::stable_sort(b0, b0 + k2, [&](int a, int b) { return e_cam_hidx[a] < e_cam_hidx[b]; });
+        }
+      }
+    }
   STAMP("edge sort by landmark");
     std::vector<int> lm_order(nl), lm_rank(nl);
     {
       std::vector<int> cl_ptr(nl + 1, 0), cl;  // per landmark: ascending distinct free cameras
       cl.reserve(E);
-      for (int q = 0; q < E;) {
-        const int l = lkey(order[q]);
-        if (l >= nl) break;
+      for (int l = 0; l < nl; ++l) {
         int prev = -1;
-        for (; q < E && lkey(order[q]) == l; ++q) {
-          const int pz = PV.hidx[c->e_vj[order[q]]];
+        for (int q = grp_ptr[l]; q < grp_ptr[l + 1]; ++q) {
+          const int pz = e_cam_hidx[order[q]];
           if (pz >= 0 && pz != prev) { cl.push_back(pz); prev = pz; }
         }
         cl_ptr[l + 1] = (int)cl.size();
       }
-      for (int l = 0; l < nl; ++l) cl_ptr[l + 1] = std::max(cl_ptr[l + 1], cl_ptr[l]);
-      for (int l = 0; l < nl; ++l) lm_order[l] = l;
-      std::stable_sort(lm_order.begin(), lm_order.end(), [&](int x, int y) {
+      // lexicographic order of the camera lists, landmarks without a free camera last, ties by landmark index.  The
+      // first cameras of a list are packed into one integer (as many as fit into 63 bits; a missing entry sorts
+      // first), so most comparisons are one 64-bit compare; only equal prefixes look at the lists.
+      struct RankKey { unsigned long long key; int l; };
+      std::vector<RankKey> rk(nl);
+      int bits = 1;
+      while ((1ll << bits) < (long long)np + 2) ++bits;  // values 0 (missing) .. np
+      const int npack = 63 / bits;
+      for (int l = 0; l < nl; ++l) {
+        const int n = cl_ptr[l + 1] - cl_ptr[l];
+        const int* r = cl.data() + cl_ptr[l];
+        unsigned long long key = ~0ull;
+        if (n > 0) {
+          key = 0;
+          for (int q = 0; q < npack; ++q) key = (key << bits) | (unsigned long long)(q < n ? r[q] + 1 : 0);
+        }
+        rk[l] = RankKey{key, l};
+      }
+      std::sort(rk.begin(), rk.end(), [&](const RankKey& X, const RankKey& Y) {
+        if (X.key != Y.key) return X.key < Y.key;
+        const int x = X.l, y = Y.l;
         const int nx = cl_ptr[x + 1] - cl_ptr[x], ny = cl_ptr[y + 1] - cl_ptr[y];
-        if ((nx == 0) != (ny == 0)) return ny == 0;  // landmarks without a free camera last
         const int* rx = cl.data() + cl_ptr[x];
         const int* ry = cl.data() + cl_ptr[y];
-        for (int q = 0; q < nx && q < ny; ++q) if (rx[q] != ry[q]) return rx[q] < ry[q];
-        return nx < ny;
+        for (int q = npack; q < nx && q < ny; ++q) if (rx[q] != ry[q]) return rx[q] < ry[q];
+        if (nx != ny) return nx < ny;
+        return x < y;
       });
-      for (int i = 0; i < nl; ++i) lm_rank[lm_order[i]] = i;
+      for (int i = 0; i < nl; ++i) { lm_order[i] = rk[i].l; lm_rank[rk[i].l] = i; }
     }
   STAMP("landmark ranking");
     // device edge order: by landmark rank (fixed points last), then camera pose index, then input order
-    auto rkey = [&](int e) { int l = lm_lidx[c->e_vi[e]]; return l < 0 ? nl : lm_rank[l]; };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      int la = rkey(a), lb = rkey(b);
-      if (la != lb) return la < lb;
-      return PV.hidx[c->e_vj[a]] < PV.hidx[c->e_vj[b]];
-    });
+    {
+      std::vector<int> ranked(E);
+      int q = 0;
+      for (int i = 0; i <= nl; ++i) {
+        const int l = i < nl ? lm_order[i] : nl;
+        for (int a = grp_ptr[l]; a < grp_ptr[l + 1]; ++a) ranked[q++] = order[a];
+      }
+      order.swap(ranked);
+    }
   STAMP("edge sort by rank");
     c->e_order = order;
     std::vector<int> e_pt(E), e_cam(E), e_pose(E), e_hpl(E, -1), lm_eptr(nl + 1, 0);
     std::vector<unsigned char> e_first(E, 0);
     std::vector<double> meas((size_t)2 * E), info((size_t)3 * E);
     c->hpl_row.clear(); c->hpl_col.clear();
+    c->hpl_row.reserve(E); c->hpl_col.reserve(E);
     int nslot = 0;
+    int prev_l = -2;  // landmark index of the previous edge
     for (int q = 0; q < E; ++q) {
       int e = order[q];
       e_pt[q] = c->e_vi[e]; e_cam[q] = c->e_vj[e];
-      e_pose[q] = PV.hidx[c->e_vj[e]];
+      e_pose[q] = e_cam_hidx[e];
       int l = lm_lidx[c->e_vi[e]];
       if (l >= 0) lm_eptr[lm_rank[l] + 1]++;
       if (l >= 0 && e_pose[q] >= 0) {
-        bool dup = q > 0 && lm_lidx[e_pt[q - 1]] == l && e_pose[q - 1] == e_pose[q];
+        bool dup = q > 0 && prev_l == l && e_pose[q - 1] == e_pose[q];
         if (dup) e_hpl[q] = e_hpl[q - 1];
         else { e_hpl[q] = nslot++; e_first[q] = 1; c->hpl_row.push_back(e_pose[q]); c->hpl_col.push_back(l); }
       }
+      prev_l = l;
       meas[q] = c->e_meas[(size_t)e * 2]; meas[(size_t)E + q] = c->e_meas[(size_t)e * 2 + 1];
       const double* W = &c->e_info[(size_t)e * 4];
       info[q] = W[0]; info[(size_t)E + q] = W[2]; info[(size_t)2 * E + q] = W[3];
@@ -373,18 +412,28 @@ int build_structure_impl(b200_ctx* c) {
     for (int i = 0; i < np; ++i) keys.push_back(((long long)i << 32) | i);
     for (long long k2 : c->extra_schur_keys) keys.push_back(k2);
     size_t next_compact = std::max<size_t>(keys.size() * 2, (size_t)1 << 24);
-    for (int l = 0; l < nl; ++l) {
-      int prev_a = -1;
-      for (int a = lm_eptr[l]; a < lm_eptr[l + 1]; ++a) {
-        if (e_hpl[a] < 0 || e_hpl[a] == prev_a) continue;
-        prev_a = e_hpl[a];
-        int prev_b = -1;
-        for (int b2 = a; b2 < lm_eptr[l + 1]; ++b2) {
-          if (e_hpl[b2] < 0 || e_hpl[b2] == prev_b) continue;
-          prev_b = e_hpl[b2];
-          keys.push_back(((long long)e_pose[b2] << 32) | e_pose[a]);
-        }
+    // distinct Hpl slots per landmark rank (slots are numbered in rank order; hpl_row[slot] = camera, ascending per landmark)
+    std::vector<int> lm_s0(nl + 1, 0);
+    {
+      int prev = -1;
+      for (int i = 0; i < nl; ++i) {
+        for (int a = lm_eptr[i]; a < lm_eptr[i + 1]; ++a)
+          if (e_hpl[a] >= 0 && e_hpl[a] != prev) { prev = e_hpl[a]; lm_s0[i + 1]++; }
       }
+      for (int i = 0; i < nl; ++i) lm_s0[i + 1] += lm_s0[i];
+    }
+    // neighbours in rank order mostly see the same cameras: a landmark whose camera list equals its predecessor's adds
+    // nothing to the pattern (and reuses its block indices in the Schur plan below)
+    std::vector<unsigned char> same_as_prev(nl, 0);
+    for (int i = 1; i < nl; ++i) {
+      const int k2 = lm_s0[i + 1] - lm_s0[i];
+      same_as_prev[i] = k2 > 0 && k2 == lm_s0[i] - lm_s0[i - 1] &&
+                        std::equal(c->hpl_row.begin() + lm_s0[i], c->hpl_row.begin() + lm_s0[i + 1], c->hpl_row.begin() + lm_s0[i - 1]);
+    }
+    for (int i = 0; i < nl; ++i) {
+      if (same_as_prev[i]) continue;
+      for (int a = lm_s0[i]; a < lm_s0[i + 1]; ++a)
+        for (int b2 = a; b2 < lm_s0[i + 1]; ++b2) keys.push_back(((long long)c->hpl_row[b2] << 32) | c->hpl_row[a]);
       if (keys.size() > next_compact) { compact(); next_compact = std::max<size_t>(keys.size() * 2, (size_t)1 << 24); }
     }
     compact();
@@ -404,22 +453,15 @@ int build_structure_impl(b200_ctx* c) {
     };
   STAMP("Hschur pattern");
     // ---- Schur plan (kernels.cuh: schur_range_kernel / schur_finish_kernel)
-    std::vector<int> lm_s0(nl + 1, 0);  // distinct Hpl slots per landmark rank (slots are numbered in rank order)
-    {
-      int prev = -1;
-      for (int i = 0; i < nl; ++i) {
-        for (int a = lm_eptr[i]; a < lm_eptr[i + 1]; ++a)
-          if (e_hpl[a] >= 0 && e_hpl[a] != prev) { prev = e_hpl[a]; lm_s0[i + 1]++; }
-      }
-      for (int i = 0; i < nl; ++i) lm_s0[i + 1] += lm_s0[i];
-    }
     std::vector<int> pi;  // ranks with at least one slot
     for (int i = 0; i < nl; ++i) if (lm_s0[i + 1] > lm_s0[i]) pi.push_back(i);
     {
       // SparseBlockMatrix (landmark-major, ascending camera) position -> slot, for the exported Hpl pattern
       c->hpl_export.resize(nslot);
-      for (int q = 0; q < nslot; ++q) c->hpl_export[q] = q;
-      std::stable_sort(c->hpl_export.begin(), c->hpl_export.end(), [&](int x, int y) { return c->hpl_col[x] < c->hpl_col[y]; });
+      std::vector<int> colfill(nl + 1, 0);  // stable counting sort by landmark column
+      for (int q = 0; q < nslot; ++q) colfill[c->hpl_col[q] + 1]++;
+      for (int l = 0; l < nl; ++l) colfill[l + 1] += colfill[l];
+      for (int q = 0; q < nslot; ++q) c->hpl_export[colfill[c->hpl_col[q]]++] = q;
     }
     {
   STAMP("hpl export order");
@@ -430,8 +472,16 @@ int build_structure_impl(b200_ctx* c) {
       if (kmax > 1400) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 1400 cameras");
       std::vector<int> r_slot0{0}, r_lm_ptr{0}, r_lm_ids, r_lm_slot, r_seg_ptr{0}, seg_t, seg_cb, seg_ce;
       std::vector<unsigned short> sc_a, sc_b, sc_l;
+      {
+        size_t total = 0;
+        for (int l : pi) { const size_t k2 = lm_s0[l + 1] - lm_s0[l]; total += k2 * (k2 + 1) / 2; }
+        total += 8 * (pi.size() / 16 + 2);  // alignment padding per range
+        sc_a.reserve(total); sc_b.reserve(total); sc_l.reserve(total);
+        r_lm_ids.reserve(pi.size()); r_lm_slot.reserve(pi.size() + pi.size() / 16 + 2);
+      }
       struct Contrib { int t; unsigned short l, a, b; };
       std::vector<Contrib> rc;
+      std::vector<int> pair_t;
       int slot = 0;  // next slot
       long long npairs = 0;
       auto close_range = [&]() {
@@ -459,9 +509,14 @@ int build_structure_impl(b200_ctx* c) {
         const int cur_slots = slot - r_slot0.back(), cur_lms = (int)r_lm_ids.size() - r_lm_ptr.back();
         if (cur_lms > 0 && (cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || (int)rc.size() + pairs > cap_contrib)) close_range();
         const int base = slot - r_slot0.back(), ll = (int)r_lm_ids.size() - r_lm_ptr.back();
-        for (int a = 0; a < k2; ++a)
-          for (int b2 = a; b2 < k2; ++b2)
-            rc.push_back({find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]), (unsigned short)ll, (unsigned short)(base + a), (unsigned short)(base + b2)});
+        if (!same_as_prev[l]) {  // Hschur block of every camera pair of this list (else: the predecessor's, still in pair_t)
+          pair_t.clear();
+          for (int a = 0; a < k2; ++a)
+            for (int b2 = a; b2 < k2; ++b2) pair_t.push_back(find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]));
+        }
+        for (int a = 0, z = 0; a < k2; ++a)
+          for (int b2 = a; b2 < k2; ++b2, ++z)
+            rc.push_back({pair_t[z], (unsigned short)ll, (unsigned short)(base + a), (unsigned short)(base + b2)});
         r_lm_ids.push_back(lm_order[l]);
         r_lm_slot.push_back(base);
         slot += k2;
@@ -1315,6 +1370,11 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
   return B200_OK;
 }
 int64_t b200_get_launch_count(b200_ctx* c) { return c ? c->lc.n : -1; }
+uint64_t b200_debug_upload_digest(int reset) {
+  const uint64_t h = upload_digest();
+  if (reset) upload_digest() = 1469598103934665603ull;
+  return h;
+}
 int b200_set_profiling(b200_ctx* c, int on) {
   if (!c) return B200_ERR_INVALID;
   if (!c->host_only) { cudaSetDevice(c->device); c->prof.stream = c->stream; c->prof.reset(); }

@@ -217,3 +217,28 @@ def test_parallel_loader_equals_sequential(tmp_path, monkeypatch):
         assert o.setup_cli() == -1
         o.initialize_optimization()
     assert graphs[2].vertex_info(901) == graphs[0].vertex_info(901)
+
+
+def test_structure_plan_digest_is_deterministic_and_sensitive():
+    """b200_debug_upload_digest: the digest over everything the structure phase prepares for the device is identical
+    for identical inputs (the plan does not depend on allocation addresses, thread timing or hash-map order) and changes
+    when one observation moves to another camera"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+
+    def digest(p):
+        o = g.SparseOptimizer(device=-1)
+        synth.feed(p, o)
+        o.setup_cli()
+        o.initialize_optimization()
+        o._ensure_uploaded()
+        g.lib.b200_debug_upload_digest(1)
+        assert o.context.build_structure()
+        return g.lib.b200_debug_upload_digest(1)
+    p = synth.venice_like(40, 3000, seed=9)
+    d0 = digest(p)
+    assert d0 == digest(p) and d0 != 1469598103934665603
+    q = dict(p)
+    q["edge_v1"] = p["edge_v1"].copy()
+    q["edge_v1"][17] = (q["edge_v1"][17] + 20) % 40
+    assert digest(q) != d0
