@@ -15,14 +15,19 @@ def _free_port():
     return p
 
 
-def _cpu_worker(rank, world, port, out):
+def _problem(kind):
+    from openslam_g2o_b200 import synth
+    return synth.venice_like(30, 1500, seed=9) if kind == "ba" else synth.expmap_ba(30, 1500, seed=9)
+
+
+def _cpu_worker(rank, world, port, out, kind):
     import torch.distributed as dist
     import openslam_g2o_b200 as g
     from openslam_g2o_b200 import synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    p = synth.venice_like(30, 1500, seed=9)
+    p = _problem(kind)
     opt = g.SparseOptimizer(device=-1, shard=rank, num_shards=world)
     synth.feed(p, opt)
     opt.setup_cli()
@@ -43,7 +48,8 @@ def _cpu_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_landmark_shards_agree_on_the_reduced_system_cpu():
+@pytest.mark.parametrize("kind", ["ba", "ba_expmap"])
+def test_landmark_shards_agree_on_the_reduced_system_cpu(kind):
     """every rank must build the identical Hschur pattern / ordering (the all-reduce adds arrays element-wise),
     the shards must partition landmarks and edges, and the pattern must equal the unsharded one"""
     import torch.multiprocessing as mp
@@ -52,14 +58,14 @@ def test_landmark_shards_agree_on_the_reduced_system_cpu():
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
-    procs = [ctxm.Process(target=_cpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctxm.Process(target=_cpu_worker, args=(r, 2, port, q, kind)) for r in range(2)]
     for p in procs:
         p.start()
     res = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    p = synth.venice_like(30, 1500, seed=9)
+    p = _problem(kind)
     ref = g.SparseOptimizer(device=-1)
     synth.feed(p, ref)
     ref.setup_cli()
