@@ -91,3 +91,36 @@ def test_committed_bench_line_follows_the_contract():
     c = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_header_is_plain_c_and_binds_from_a_c_host(tmp_path):
+    """include/g2o_b200.h compiles as C99 (-pedantic) and a C program drives the standalone host + structure phase
+    through it; the ordering it prints is the one the Python binding sees"""
+    import subprocess
+    import numpy as np
+    import openslam_g2o_b200 as g
+    import openslam_g2o_b200._lib as L
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                           os.path.join(inc, "g2o_b200.h")])
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc,
+                           os.path.join(ROOT, "tests", "csrc", "c_host.c"), "-o", exe, L.LIB_PATH,
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe], text=True).strip().splitlines()
+    assert out[1].startswith("g2o_b200")
+    fields = dict(kv.split("=", 1) for kv in out[0].split(" "))
+    assert fields["poses"] == "5" and fields["edges"] == "6" and fields["nodevice"] == "1"
+    # same graph through the Python mirror
+    opt = g.SparseOptimizer(device=-1)
+    est = np.array([[i, 0.1 * i, 0.05 * i] for i in range(6)], dtype=float)
+    opt.add_vertices(g.VERTEX_SE2, np.arange(6), est)
+    pay = np.tile(np.array([1.0, 0.1, 0.05, 10, 0, 0, 10, 0, 10]), (6, 1))
+    opt.add_edges(g.EDGE_SE2, np.arange(6), (np.arange(6) + 1) % 6, pay)
+    opt.setup_cli()
+    opt.initialize_optimization()
+    opt._ensure_uploaded()
+    assert opt.context.build_structure()
+    assert fields["perm"] == ",".join(str(int(x)) for x in opt.context.block_ordering())
+    assert int(fields["lnz"]) == opt.context.factor_nnz()
