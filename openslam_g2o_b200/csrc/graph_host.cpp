@@ -572,9 +572,13 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     std::vector<int32_t> vi, vj;
     std::vector<double> meas, info;
     std::vector<int32_t> xr, xc;  // Hschur blocks contributed by other shards
+    std::vector<int> vslot(g->vertices.size());  // compact copy: the edge loop gathers two slots per edge
+    for (size_t i = 0; i < vslot.size(); ++i) vslot[i] = g->vertices[i].slot;
+    const size_t na = g->active_edges.size() / (size_t)num_shards + 16;
+    vi.reserve(na); vj.reserve(na); meas.reserve(na * nm); info.reserve(na * D * D);
     for (int k : g->active_edges) {
       const HEdge& e = g->edges[k];
-      int s0 = g->vertices[e.v0].slot, s1 = g->vertices[e.v1].slot;
+      int s0 = vslot[e.v0], s1 = vslot[e.v1];
       if (ba) {
         if (lm_shard[s0] != shard) continue;
         s0 = local_slot[s0];

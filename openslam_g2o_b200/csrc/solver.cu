@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "host_parallel.h"
 #include "kernels.cuh"
 
 using namespace g2o_b200;
@@ -294,7 +295,8 @@ int build_structure_impl(b200_ctx* c) {
     {
       std::vector<int> fill(grp_ptr.begin(), grp_ptr.end() - 1);
       for (int e = 0; e < E; ++e) order[fill[lkey(e)]++] = e;
-      for (int l = 0; l <= nl; ++l) {
+      parallel_ranges((size_t)nl + 1, range_count((size_t)nl + 1, (size_t)1 << 14), [&](int, size_t lb, size_t le) {
+      for (size_t l = lb; l < le; ++l) {
         int* b0 = order.data() + grp_ptr[l];
         const int k2 = grp_ptr[l + 1] - grp_ptr[l];
         if (k2 <= 24) {  // stable insertion sort
@@ -308,6 +310,7 @@ int build_structure_impl(b200_ctx* c) {
           std::stable_sort(b0, b0 + k2, [&](int a, int b) { return e_cam_hidx[a] < e_cam_hidx[b]; });
         }
       }
+      });
     }
   STAMP("edge sort by landmark");
     std::vector<int> lm_order(nl), lm_rank(nl);
@@ -340,7 +343,7 @@ int build_structure_impl(b200_ctx* c) {
         }
         rk[l] = RankKey{key, l};
       }
-      std::sort(rk.begin(), rk.end(), [&](const RankKey& X, const RankKey& Y) {
+      parallel_sort(rk.begin(), rk.end(), [&](const RankKey& X, const RankKey& Y) {
         if (X.key != Y.key) return X.key < Y.key;
         const int x = X.l, y = Y.l;
         const int nx = cl_ptr[x + 1] - cl_ptr[x], ny = cl_ptr[y + 1] - cl_ptr[y];
@@ -368,27 +371,46 @@ int build_structure_impl(b200_ctx* c) {
     std::vector<int> e_pt(E), e_cam(E), e_pose(E), e_hpl(E, -1), lm_eptr(nl + 1, 0);
     std::vector<unsigned char> e_first(E, 0);
     std::vector<double> meas((size_t)2 * E), info((size_t)3 * E);
-    c->hpl_row.clear(); c->hpl_col.clear();
-    c->hpl_row.reserve(E); c->hpl_col.reserve(E);
-    int nslot = 0;
-    int prev_l = -2;  // landmark index of the previous edge
-    for (int q = 0; q < E; ++q) {
-      int e = order[q];
-      e_pt[q] = c->e_vi[e]; e_cam[q] = c->e_vj[e];
-      e_pose[q] = e_cam_hidx[e];
-      int l = lm_lidx[c->e_vi[e]];
-      if (l >= 0) lm_eptr[lm_rank[l] + 1]++;
-      if (l >= 0 && e_pose[q] >= 0) {
-        bool dup = q > 0 && prev_l == l && e_pose[q - 1] == e_pose[q];
-        if (dup) e_hpl[q] = e_hpl[q - 1];
-        else { e_hpl[q] = nslot++; e_first[q] = 1; c->hpl_row.push_back(e_pose[q]); c->hpl_col.push_back(l); }
+    // An observation opens a new Hpl slot unless the previous edge (device order) is the same landmark seen by the same
+    // free camera (duplicate observation: both feed one block).  Slots are numbered in device order, so a slot index
+    // is a prefix count of "opens a slot": counted per contiguous range of edges, offset by a prefix sum, filled
+    // concurrently - identical for any thread count.
+    auto e_l = [&](int q) { return lm_lidx[c->e_vi[order[q]]]; };
+    auto opens_slot = [&](int q, int l, int pose) {
+      if (l < 0 || pose < 0) return false;
+      return !(q > 0 && e_l(q - 1) == l && e_cam_hidx[order[q - 1]] == pose);
+    };
+    const int eparts = range_count((size_t)E, (size_t)1 << 16);
+    std::vector<int> slot_base(eparts + 1, 0);
+    parallel_ranges((size_t)E, eparts, [&](int t, size_t b, size_t e2) {
+      int cnt = 0;
+      for (size_t q = b; q < e2; ++q) {
+        const int e = order[q];
+        cnt += opens_slot((int)q, lm_lidx[c->e_vi[e]], e_cam_hidx[e]);
       }
-      prev_l = l;
-      meas[q] = c->e_meas[(size_t)e * 2]; meas[(size_t)E + q] = c->e_meas[(size_t)e * 2 + 1];
-      const double* W = &c->e_info[(size_t)e * 4];
-      info[q] = W[0]; info[(size_t)E + q] = W[2]; info[(size_t)2 * E + q] = W[3];
-    }
-    for (int l = 0; l < nl; ++l) lm_eptr[l + 1] += lm_eptr[l];
+      slot_base[t + 1] = cnt;
+    });
+    for (int t = 0; t < eparts; ++t) slot_base[t + 1] += slot_base[t];
+    const int nslot = slot_base[eparts];
+    c->hpl_row.assign(nslot, 0); c->hpl_col.assign(nslot, 0);
+    parallel_ranges((size_t)E, eparts, [&](int t, size_t b, size_t e2) {
+      int next = slot_base[t];
+      for (size_t q = b; q < e2; ++q) {
+        const int e = order[q];
+        e_pt[q] = c->e_vi[e]; e_cam[q] = c->e_vj[e];
+        const int pose = e_cam_hidx[e], l = lm_lidx[c->e_vi[e]];
+        e_pose[q] = pose;
+        if (l >= 0 && pose >= 0) {
+          if (opens_slot((int)q, l, pose)) { e_hpl[q] = next; e_first[q] = 1; c->hpl_row[next] = pose; c->hpl_col[next] = l; ++next; }
+          else e_hpl[q] = next - 1;  // duplicate: the slot the run opened (possibly in the previous range)
+        }
+        meas[q] = c->e_meas[(size_t)e * 2]; meas[(size_t)E + q] = c->e_meas[(size_t)e * 2 + 1];
+        const double* W = &c->e_info[(size_t)e * 4];
+        info[q] = W[0]; info[(size_t)E + q] = W[2]; info[(size_t)2 * E + q] = W[3];
+      }
+    });
+    // edges are in rank order: a landmark's edges are its group
+    for (int i = 0; i < nl; ++i) lm_eptr[i + 1] = lm_eptr[i] + (grp_ptr[lm_order[i] + 1] - grp_ptr[lm_order[i]]);
     c->n_hpl = nslot;
   STAMP("edge arrays + Hpl slots");
     // camera observation lists (ascending device edge index)
@@ -470,60 +492,93 @@ int build_structure_impl(b200_ctx* c) {
       for (int l : pi) kmax = std::max(kmax, lm_s0[l + 1] - lm_s0[l]);
       const int cap_slots = std::max(352, kmax), cap_lms = 160, cap_contrib = 1536;
       if (kmax > 1400) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 1400 cameras");
-      std::vector<int> r_slot0{0}, r_lm_ptr{0}, r_lm_ids, r_lm_slot, r_seg_ptr{0}, seg_t, seg_cb, seg_ce;
-      std::vector<unsigned short> sc_a, sc_b, sc_l;
-      {
-        size_t total = 0;
-        for (int l : pi) { const size_t k2 = lm_s0[l + 1] - lm_s0[l]; total += k2 * (k2 + 1) / 2; }
-        total += 8 * (pi.size() / 16 + 2);  // alignment padding per range
-        sc_a.reserve(total); sc_b.reserve(total); sc_l.reserve(total);
-        r_lm_ids.reserve(pi.size()); r_lm_slot.reserve(pi.size() + pi.size() / 16 + 2);
-      }
-      struct Contrib { int t; unsigned short l, a, b; };
-      std::vector<Contrib> rc;
-      std::vector<int> pair_t;
-      int slot = 0;  // next slot
+      // (1) range boundaries: a cheap sequential pass - a range closes when the next landmark would exceed the slot,
+      //     landmark or contribution budget of one CTA
+      std::vector<int> rg_first{0};  // index into pi of the first landmark of each range
+      std::vector<long long> rg_contrib;
       long long npairs = 0;
-      auto close_range = [&]() {
-        if (r_lm_ids.size() == (size_t)r_lm_ptr.back()) return;
-        std::stable_sort(rc.begin(), rc.end(), [](const Contrib& x, const Contrib& y) { return x.t < y.t; });
-        for (size_t q = 0; q < rc.size();) {
-          size_t e2 = q;
-          while (e2 < rc.size() && rc[e2].t == rc[q].t && e2 - q < (size_t)k::kSrSegMax) ++e2;
-          seg_t.push_back(rc[q].t);
-          seg_cb.push_back((int)sc_a.size());
-          for (size_t z = q; z < e2; ++z) { sc_a.push_back(rc[z].a); sc_b.push_back(rc[z].b); sc_l.push_back(rc[z].l); }
-          seg_ce.push_back((int)sc_a.size());
-          q = e2;
+      {
+        int cur_slots = 0, cur_lms = 0;
+        long long cur_contrib = 0;
+        for (size_t j = 0; j < pi.size(); ++j) {
+          const int l = pi[j], k2 = lm_s0[l + 1] - lm_s0[l];
+          if (k2 > 65535) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 65535 cameras");
+          const long long pairs = (long long)k2 * (k2 + 1) / 2;
+          npairs += pairs;
+          if (cur_lms > 0 && (cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || cur_contrib + pairs > cap_contrib)) {
+            rg_first.push_back((int)j); rg_contrib.push_back(cur_contrib);
+            cur_slots = 0; cur_lms = 0; cur_contrib = 0;
+          }
+          cur_slots += k2; cur_lms += 1; cur_contrib += pairs;
         }
-        while (sc_a.size() % 8) { sc_a.push_back(0); sc_b.push_back(0); sc_l.push_back(0); }  // 16-byte aligned ranges (bulk copies)
-        rc.clear();
-        r_lm_slot.push_back(slot - r_slot0.back());  // end entry of the range
-        r_slot0.push_back(slot); r_lm_ptr.push_back((int)r_lm_ids.size()); r_seg_ptr.push_back((int)seg_t.size());
-      };
-      for (int l : pi) {
-        const int k2 = lm_s0[l + 1] - lm_s0[l];
-        const int pairs = k2 * (k2 + 1) / 2;
-        npairs += pairs;
-        if (k2 > 65535) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 65535 cameras");
-        const int cur_slots = slot - r_slot0.back(), cur_lms = (int)r_lm_ids.size() - r_lm_ptr.back();
-        if (cur_lms > 0 && (cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || (int)rc.size() + pairs > cap_contrib)) close_range();
-        const int base = slot - r_slot0.back(), ll = (int)r_lm_ids.size() - r_lm_ptr.back();
-        if (!same_as_prev[l]) {  // Hschur block of every camera pair of this list (else: the predecessor's, still in pair_t)
-          pair_t.clear();
-          for (int a = 0; a < k2; ++a)
-            for (int b2 = a; b2 < k2; ++b2) pair_t.push_back(find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]));
-        }
-        for (int a = 0, z = 0; a < k2; ++a)
-          for (int b2 = a; b2 < k2; ++b2, ++z)
-            rc.push_back({pair_t[z], (unsigned short)ll, (unsigned short)(base + a), (unsigned short)(base + b2)});
-        r_lm_ids.push_back(lm_order[l]);
-        r_lm_slot.push_back(base);
-        slot += k2;
+        if (cur_lms > 0) { rg_first.push_back((int)pi.size()); rg_contrib.push_back(cur_contrib); }
       }
-      close_range();
-      for (int q = 0; q < 8; ++q) { sc_a.push_back(0); sc_b.push_back(0); sc_l.push_back(0); }  // bulk copies round sizes up
-      const int nr = (int)r_slot0.size() - 1, nseg = (int)seg_t.size();
+      const int nr = (int)rg_first.size() - 1;
+      // (2) everything whose position follows from the boundaries
+      std::vector<int> r_slot0(nr + 1, 0), r_lm_ptr(nr + 1, 0), r_lm_ids(pi.size()), r_lm_slot(pi.size() + nr), r_seg_ptr(nr + 1, 0);
+      std::vector<long long> sc_off(nr + 1, 0);  // contributions of a range start 16-byte aligned (bulk copies)
+      for (int r = 0; r < nr; ++r) {
+        r_slot0[r + 1] = lm_s0[pi[rg_first[r + 1] - 1] + 1];
+        r_lm_ptr[r + 1] = rg_first[r + 1];
+        sc_off[r + 1] = sc_off[r] + ((rg_contrib[r] + 7) & ~7ll);
+      }
+      if (sc_off[nr] + 8 > 0x7fffffffll) return fail(c, B200_ERR_UNSUPPORTED, "more than 2^31 Schur contributions on one GPU: shard the landmarks");
+      std::vector<unsigned short> sc_a((size_t)sc_off[nr] + 8, 0), sc_b((size_t)sc_off[nr] + 8, 0), sc_l((size_t)sc_off[nr] + 8, 0);  // + 8: bulk copies round sizes up
+      // (3) contributions and segments of the ranges, a contiguous block of ranges per thread
+      struct Contrib { int t; unsigned short l, a, b; };
+      struct RangeOut { std::vector<int> seg_t, seg_cb, seg_ce; };
+      const int rparts = range_count((size_t)nr, 64);
+      std::vector<RangeOut> outs(rparts);
+      std::vector<int> r_nseg(nr, 0);
+      parallel_ranges((size_t)nr, rparts, [&](int tid, size_t rb, size_t re) {
+        RangeOut& out = outs[tid];
+        std::vector<Contrib> rc;
+        std::vector<int> pair_t;
+        bool have_pairs = false;  // pair_t holds the block indices of the previous landmark's camera list
+        for (size_t r = rb; r < re; ++r) {
+          const int slot0 = r_slot0[r];
+          rc.clear();
+          for (int j = rg_first[r]; j < rg_first[r + 1]; ++j) {
+            const int l = pi[j], k2 = lm_s0[l + 1] - lm_s0[l], slot = lm_s0[l];
+            const int base = slot - slot0, ll = j - rg_first[r];
+            if (!same_as_prev[l] || !have_pairs) {  // Hschur block of every camera pair of this list
+              pair_t.clear();
+              for (int a = 0; a < k2; ++a)
+                for (int b2 = a; b2 < k2; ++b2) pair_t.push_back(find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]));
+              have_pairs = true;
+            }
+            for (int a = 0, z = 0; a < k2; ++a)
+              for (int b2 = a; b2 < k2; ++b2, ++z)
+                rc.push_back({pair_t[z], (unsigned short)ll, (unsigned short)(base + a), (unsigned short)(base + b2)});
+            r_lm_ids[j] = lm_order[l];
+            r_lm_slot[j + r] = base;
+          }
+          r_lm_slot[rg_first[r + 1] + r] = r_slot0[r + 1] - slot0;  // end entry of the range
+          std::stable_sort(rc.begin(), rc.end(), [](const Contrib& x, const Contrib& y) { return x.t < y.t; });
+          size_t pos = (size_t)sc_off[r];
+          int nseg_r = 0;
+          for (size_t q = 0; q < rc.size();) {
+            size_t e2 = q;
+            while (e2 < rc.size() && rc[e2].t == rc[q].t && e2 - q < (size_t)k::kSrSegMax) ++e2;
+            out.seg_t.push_back(rc[q].t);
+            out.seg_cb.push_back((int)pos);
+            for (size_t z = q; z < e2; ++z, ++pos) { sc_a[pos] = rc[z].a; sc_b[pos] = rc[z].b; sc_l[pos] = rc[z].l; }
+            out.seg_ce.push_back((int)pos);
+            ++nseg_r;
+            q = e2;
+          }
+          r_nseg[r] = nseg_r;
+        }
+      });
+      for (int r = 0; r < nr; ++r) r_seg_ptr[r + 1] = r_seg_ptr[r] + r_nseg[r];
+      std::vector<int> seg_t, seg_cb, seg_ce;
+      seg_t.reserve(r_seg_ptr[nr]); seg_cb.reserve(r_seg_ptr[nr]); seg_ce.reserve(r_seg_ptr[nr]);
+      for (const RangeOut& o : outs) {  // thread blocks are contiguous in range order
+        seg_t.insert(seg_t.end(), o.seg_t.begin(), o.seg_t.end());
+        seg_cb.insert(seg_cb.end(), o.seg_cb.begin(), o.seg_cb.end());
+        seg_ce.insert(seg_ce.end(), o.seg_ce.begin(), o.seg_ce.end());
+      }
+      const int nseg = (int)seg_t.size();
       // per block: its segments in ascending order (= fixed summation order of the finish kernel)
       std::vector<int> tseg_ptr(nT + 1, 0), tseg_idx(nseg);
       for (int sg = 0; sg < nseg; ++sg) tseg_ptr[seg_t[sg] + 1]++;

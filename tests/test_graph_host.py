@@ -219,7 +219,7 @@ def test_parallel_loader_equals_sequential(tmp_path, monkeypatch):
     assert graphs[2].vertex_info(901) == graphs[0].vertex_info(901)
 
 
-def test_structure_plan_digest_is_deterministic_and_sensitive():
+def test_structure_plan_digest_is_deterministic_and_sensitive(monkeypatch):
     """b200_debug_upload_digest: the digest over everything the structure phase prepares for the device is identical
     for identical inputs (the plan does not depend on allocation addresses, thread timing or hash-map order) and changes
     when one observation moves to another camera"""
@@ -238,6 +238,18 @@ def test_structure_plan_digest_is_deterministic_and_sensitive():
     p = synth.venice_like(40, 3000, seed=9)
     d0 = digest(p)
     assert d0 == digest(p) and d0 != 1469598103934665603
+    # the host-side fork/join (csrc/host_parallel.h) never changes the plan: many tiny ranges on several threads
+    monkeypatch.setenv("G2O_B200_HOST_GRAIN", "7")
+    for threads in ("2", "5"):
+        monkeypatch.setenv("G2O_B200_HOST_THREADS", threads)
+        assert digest(p) == d0
+    wide = synth.venice_like(30, 200, seed=2, fixed_obs=30)  # ranges grown beyond the default slot budget
+    monkeypatch.setenv("G2O_B200_HOST_THREADS", "1")
+    dw = digest(wide)
+    monkeypatch.setenv("G2O_B200_HOST_THREADS", "4")
+    assert digest(wide) == dw
+    monkeypatch.delenv("G2O_B200_HOST_GRAIN")
+    monkeypatch.delenv("G2O_B200_HOST_THREADS")
     q = dict(p)
     q["edge_v1"] = p["edge_v1"].copy()
     q["edge_v1"][17] = (q["edge_v1"][17] + 20) % 40
