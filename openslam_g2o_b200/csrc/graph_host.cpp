@@ -27,6 +27,7 @@
 
 #include "../../include/g2o_b200.h"
 #include "geometry.cuh"
+#include "host_parallel.h"
 
 using namespace g2o_b200;
 
@@ -574,19 +575,32 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     std::vector<int32_t> xr, xc;  // Hschur blocks contributed by other shards
     std::vector<int> vslot(g->vertices.size());  // compact copy: the edge loop gathers two slots per edge
     for (size_t i = 0; i < vslot.size(); ++i) vslot[i] = g->vertices[i].slot;
-    const size_t na = g->active_edges.size() / (size_t)num_shards + 16;
-    vi.reserve(na); vj.reserve(na); meas.reserve(na * nm); info.reserve(na * D * D);
-    for (int k : g->active_edges) {
-      const HEdge& e = g->edges[k];
-      int s0 = vslot[e.v0], s1 = vslot[e.v1];
-      if (ba) {
-        if (lm_shard[s0] != shard) continue;
-        s0 = local_slot[s0];
+    // this shard's edges in active-edge order: counted per contiguous range, offset by a prefix sum, copied concurrently
+    const size_t nact = g->active_edges.size();
+    auto mine = [&](const HEdge& e) { return !ba || lm_shard[vslot[e.v0]] == shard; };
+    const int parts = g2o_b200::range_count(nact, (size_t)1 << 16);
+    std::vector<size_t> base(parts + 1, 0);
+    g2o_b200::parallel_ranges(nact, parts, [&](int t, size_t b, size_t e2) {
+      size_t cnt = 0;
+      for (size_t q = b; q < e2; ++q) cnt += mine(g->edges[g->active_edges[q]]);
+      base[t + 1] = cnt;
+    });
+    for (int t = 0; t < parts; ++t) base[t + 1] += base[t];
+    const size_t na = base[parts];
+    vi.resize(na); vj.resize(na); meas.resize(na * nm); info.resize(na * D * D);
+    g2o_b200::parallel_ranges(nact, parts, [&](int t, size_t b, size_t e2) {
+      size_t o = base[t];
+      for (size_t q = b; q < e2; ++q) {
+        const HEdge& e = g->edges[g->active_edges[q]];
+        if (!mine(e)) continue;
+        const int s0 = vslot[e.v0];
+        vi[o] = ba ? local_slot[s0] : s0;
+        vj[o] = vslot[e.v1];
+        memcpy(&meas[o * nm], e.meas, nm * sizeof(double));
+        memcpy(&info[o * D * D], e.info, (size_t)D * D * sizeof(double));
+        ++o;
       }
-      vi.push_back(s0); vj.push_back(s1);
-      meas.insert(meas.end(), e.meas, e.meas + nm);
-      info.insert(info.end(), e.info, e.info + D * D);
-    }
+    });
     if (ba && num_shards > 1) {
       // per foreign landmark: the camera pairs it couples
       std::vector<std::vector<int>> cams(g->kind_slots[B200_VERTEX_XYZ].size());
