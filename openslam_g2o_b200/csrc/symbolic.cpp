@@ -7,6 +7,7 @@
 #include <numeric>
 
 #include "block_amd.h"
+#include "host_parallel.h"
 
 namespace g2o_b200 {
 
@@ -409,7 +410,8 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   const int ntiles = (int)S.tile_sn.size();
   S.tile_work_ptr.assign(ntiles + 1, 0);
   {
-    std::vector<int> bound;
+    // the tiles of supernode J are only counted / filled by J: contiguous ranges of supernodes run concurrently
+    // (host_parallel.h), the result does not depend on the number of threads
     for (int pass = 0; pass < 2; ++pass) {
       std::vector<int> fill;
       if (pass == 1) {
@@ -418,7 +420,9 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         S.work_u.assign(nw, 0); S.work_a0.assign(nw, 0); S.work_a1.assign(nw, 0); S.work_b0.assign(nw, 0); S.work_b1.assign(nw, 0);
         fill.assign(S.tile_work_ptr.begin(), S.tile_work_ptr.end() - 1);
       }
-      for (int J = 0; J < ns; ++J) {
+      parallel_ranges((size_t)ns, range_count((size_t)ns, 256), [&](int, size_t Jb, size_t Je) {
+      std::vector<int> bound;
+      for (int J = (int)Jb; J < (int)Je; ++J) {
         const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = sn_nct[J];
         for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
           const int K = S.upd_k[u];
@@ -444,15 +448,17 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
           }
         }
       }
+      });
     }
   }
   if (opt.sort_items_by_level) {
     // inside a tile: items whose source supernode completes early first (ascending task level, then ascending
     // supernode), so that a group never waits for a late descendant while early ones are ready.  The order is part of
     // the plan: sums stay deterministic.
-    std::vector<int> idx, tmp;
     auto lvl = [&](int q) { return tlevel[task_of[S.upd_k[S.work_u[q]]]]; };
-    for (int t = 0; t < ntiles; ++t) {
+    parallel_ranges((size_t)ntiles, range_count((size_t)ntiles, 1024), [&](int, size_t tb, size_t te) {
+    std::vector<int> idx, tmp;
+    for (int t = (int)tb; t < (int)te; ++t) {
       const int w0 = S.tile_work_ptr[t], w1 = S.tile_work_ptr[t + 1];
       if (w1 - w0 < 2) continue;
       idx.resize(w1 - w0);
@@ -464,18 +470,21 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         std::copy(tmp.begin(), tmp.end(), arr->begin() + w0);
       }
     }
+    });
   }
   {
     const int nw = (int)S.work_u.size();
     S.work_koff.resize(nw); S.work_reloff.resize(nw); S.work_mk.resize(nw); S.work_nk.resize(nw); S.work_ksn.resize(nw);
-    for (int q = 0; q < nw; ++q) {
-      const int u = S.work_u[q], K = S.upd_k[u];
-      S.work_koff[q] = S.sn_lptr[K] + (int64_t)S.upd_p0[u] * d;
-      S.work_reloff[q] = S.upd_relptr[u];
-      S.work_mk[q] = S.sn_nrow[K] * d;
-      S.work_nk[q] = S.sn_ncol[K] * d;
-      S.work_ksn[q] = K;
-    }
+    parallel_ranges((size_t)nw, range_count((size_t)nw, (size_t)1 << 16), [&](int, size_t qb, size_t qe) {
+      for (size_t q = qb; q < qe; ++q) {
+        const int u = S.work_u[q], K = S.upd_k[u];
+        S.work_koff[q] = S.sn_lptr[K] + (int64_t)S.upd_p0[u] * d;
+        S.work_reloff[q] = S.upd_relptr[u];
+        S.work_mk[q] = S.sn_nrow[K] * d;
+        S.work_nk[q] = S.sn_ncol[K] * d;
+        S.work_ksn[q] = K;
+      }
+    });
   }
   S.sn_chunk_ptr.assign(ns + 1, 0);
   S.sn_dinvptr.assign(ns + 1, 0);
