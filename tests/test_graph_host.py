@@ -250,6 +250,16 @@ def test_structure_plan_digest_is_deterministic_and_sensitive(monkeypatch):
     assert digest(wide) == dw
     monkeypatch.delenv("G2O_B200_HOST_GRAIN")
     monkeypatch.delenv("G2O_B200_HOST_THREADS")
+    # pose graph: the supernodal Cholesky plan (work items per tile, their order, descriptors) is part of the digest
+    sp = synth.sphere(20, 20, seed=1)
+    ds = digest(sp)
+    monkeypatch.setenv("G2O_B200_HOST_GRAIN", "3")
+    monkeypatch.setenv("G2O_B200_HOST_THREADS", "5")
+    assert digest(sp) == ds
+    monkeypatch.delenv("G2O_B200_HOST_GRAIN")
+    monkeypatch.delenv("G2O_B200_HOST_THREADS")
+    monkeypatch.setenv("G2O_B200_PANEL_COLS", "36")
+    assert digest(sp) != ds
     q = dict(p)
     q["edge_v1"] = p["edge_v1"].copy()
     q["edge_v1"][17] = (q["edge_v1"][17] + 20) % 40
