@@ -124,3 +124,78 @@ def test_marginal_covariance_recursion_matches_dense_inverse():
         assert got is not None
         for (r, c), blk in zip(pairs, got):
             assert np.abs(blk - inv[r * d:(r + 1) * d, c * d:(c + 1) * d]).max() <= 1e-8 * np.abs(inv).max()
+
+
+@needs_oracle
+def test_oracle_optima_match_an_independent_solver():
+    """SE3 pose graph and SBACam bundle adjustment: the oracle's converged chi2 equals the minimum that
+    scipy.optimize.least_squares finds for the same cost written independently in numpy/scipy (rotation-vector
+    parametrisation, numeric Jacobians) - pins error definitions, information weighting and gauge handling"""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+
+    def oracle_chi(p, iters):
+        o = Oracle()
+        synth.feed(p, o)
+        assert o.setup_cli(True) == 0
+        o.initialize_optimization()
+        n, st = o.optimize(LM, iters)
+        return [s.chi2 for s in st[:n]][-1]
+
+    # ---- SE3 pose graph: e = [t ; q_xyz (w >= 0)] of Z^-1 Xi^-1 Xj, Omega = diag blocks (create_sphere.cpp)
+    p = synth.sphere(6, 4, seed=3)
+    nv = len(p["vertex_ids"])
+    t0 = p["vertex_payload"][:, :3]
+    R0 = Rotation.from_quat(p["vertex_payload"][:, 3:7]).as_matrix()
+    zt = p["edge_payload"][:, :3]
+    zq = p["edge_payload"][:, 3:7]
+    zR = Rotation.from_quat(zq / np.linalg.norm(zq, axis=1, keepdims=True)).as_matrix()
+    iu = p["edge_payload"][:, 7:]
+    Om = np.zeros((len(iu), 6, 6))
+    k = 0
+    for i in range(6):
+        for j in range(i, 6):
+            Om[:, i, j] = Om[:, j, i] = iu[:, k]
+            k += 1
+    Lc = np.linalg.cholesky(Om)
+    a, b = p["edge_v0"], p["edge_v1"]
+
+    def res_se3(x):
+        rv = np.concatenate([np.zeros((1, 3)), x[:3 * (nv - 1)].reshape(-1, 3)])
+        dt = np.concatenate([np.zeros((1, 3)), x[3 * (nv - 1):].reshape(-1, 3)])
+        R = np.einsum("nij,njk->nik", R0, Rotation.from_rotvec(rv).as_matrix())
+        t = t0 + dt
+        Rij = np.einsum("eji,ejk->eik", R[a], R[b])                   # Xi^-1 Xj
+        tij = np.einsum("eji,ej->ei", R[a], t[b] - t[a])
+        Rd = np.einsum("eji,ejk->eik", zR, Rij)                       # Z^-1 (Xi^-1 Xj)
+        td = np.einsum("eji,ej->ei", zR, tij - zt)
+        q = Rotation.from_matrix(Rd).as_quat()
+        q = q * np.where(q[:, 3:4] < 0, -1.0, 1.0)
+        e = np.concatenate([td, q[:, :3]], axis=1)
+        return np.einsum("eji,ej->ei", Lc, e).reshape(-1)
+    sol = least_squares(res_se3, np.zeros(6 * (nv - 1)), method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=50000)
+    chi = oracle_chi(p, 15)
+    assert abs(float(np.sum(sol.fun ** 2)) - chi) <= 1e-6 * chi, (float(np.sum(sol.fun ** 2)), chi)
+
+    # ---- SBACam bundle adjustment: e = K [R^T | -R^T c] X projected - z, Omega = I (types_sba.cpp:204-213)
+    p = synth.venice_like(6, 40, seed=3)
+    cam = p["cam_payload"]
+    ncam = len(cam)
+    c0 = cam[:, :3]
+    Rw0 = Rotation.from_quat(cam[:, 3:7]).as_matrix()                   # camera to world
+    fx, fy, cx, cy = cam[0, 7:11]
+    cam_of, pt_of, uv = p["edge_v1"], p["edge_v0"] - ncam, p["edge_payload"]
+
+    def res_ba(x):
+        rv = np.concatenate([np.zeros((1, 3)), x[:3 * (ncam - 1)].reshape(-1, 3)])
+        dc = np.concatenate([np.zeros((1, 3)), x[3 * (ncam - 1):6 * (ncam - 1)].reshape(-1, 3)])
+        X = x[6 * (ncam - 1):].reshape(-1, 3)
+        Rw = np.einsum("nij,njk->nik", Rw0, Rotation.from_rotvec(rv).as_matrix())
+        pc = np.einsum("eji,ej->ei", Rw[cam_of], X[pt_of] - (c0 + dc)[cam_of])
+        return (np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], axis=1) - uv).reshape(-1)
+    x0 = np.concatenate([np.zeros(6 * (ncam - 1)), p["point_payload"].reshape(-1)])
+    sol = least_squares(res_ba, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=50000)
+    chi = oracle_chi(p, 15)
+    assert abs(float(np.sum(sol.fun ** 2)) - chi) <= 1e-6 * chi, (float(np.sum(sol.fun ** 2)), chi)

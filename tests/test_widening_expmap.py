@@ -152,3 +152,58 @@ def test_expmap_bundle_adjustment_matches_oracle(seed, cams, points, robust, ite
     assert cam_err < EST_TOL and rel_err(pts_g, pts_o) < EST_TOL
     # the intrinsics ride along untouched
     assert np.array_equal(opt.vertex_estimate(int(p["cam_ids"][1]))[7:], [1000.0, 1000.0, 320.0, 240.0, 0.0])
+
+
+@needs_oracle
+def test_oracle_expmap_optimum_matches_an_independent_solver():
+    """the converged chi2 of the oracle's Levenberg run equals the minimum scipy.optimize.least_squares finds for the
+    same cost written independently in numpy (rotation-vector parametrisation, numeric Jacobian): error definition,
+    information weighting, gauge handling and the exp-map update all have to be right for the two to agree"""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    p = synth.expmap_ba(6, 40, seed=3)
+    o = Oracle()
+    synth.feed(p, o)
+    assert o.setup_cli(True) == 0  # camera id 0 is the gauge
+    o.initialize_optimization()
+    nit, st = o.optimize(LM, 12)
+    chi_oracle = [s.chi2 for s in st[:nit]][-1]
+
+    f, cx, cy, _ = p["camera_parameters"][0]
+    c2w = p["cam_payload"]                      # t (camera centre), q xyzw (camera to world)
+    Rw = Rotation.from_quat(c2w[:, 3:7]).as_matrix()
+    R0 = np.transpose(Rw, (0, 2, 1))            # world -> camera
+    t0 = -np.einsum("nij,nj->ni", R0, c2w[:, :3])
+    ncam, npt = len(c2w), len(p["point_payload"])
+    cam_of = p["edge_v1"]                        # camera ids are 0..ncam-1
+    pt_of = p["edge_v0"] - ncam                  # point ids follow the cameras
+    uv = p["edge_payload"][:, 1:3]
+    w = p["edge_payload"][:, 3:6]
+    # Omega = L L^T per edge -> whitened residual L^T e has squared norm e^T Omega e
+    L00 = np.sqrt(w[:, 0])
+    L10 = w[:, 1] / L00
+    L11 = np.sqrt(w[:, 2] - L10 ** 2)
+
+    def residuals(x):
+        rv = np.concatenate([np.zeros((1, 3)), x[:3 * (ncam - 1)].reshape(-1, 3)])
+        dt = np.concatenate([np.zeros((1, 3)), x[3 * (ncam - 1):6 * (ncam - 1)].reshape(-1, 3)])
+        X = x[6 * (ncam - 1):].reshape(-1, 3)
+        R = np.einsum("nij,njk->nik", Rotation.from_rotvec(rv).as_matrix(), R0)
+        t = t0 + dt
+        pc = np.einsum("eij,ej->ei", R[cam_of], X[pt_of]) + t[cam_of]
+        e = uv - np.stack([f * pc[:, 0] / pc[:, 2] + cx, f * pc[:, 1] / pc[:, 2] + cy], axis=1)
+        return np.stack([L00 * e[:, 0] + L10 * e[:, 1], L11 * e[:, 1]], axis=1).reshape(-1)
+    x0 = np.concatenate([np.zeros(6 * (ncam - 1)), p["point_payload"].reshape(-1)])
+    sol = least_squares(residuals, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=20000)
+    chi_scipy = float(np.sum(sol.fun ** 2))
+    assert abs(chi_scipy - chi_oracle) <= 1e-6 * chi_oracle, (chi_scipy, chi_oracle)
+    # and the starting cost agrees too (no optimisation involved)
+    o2 = Oracle()
+    synth.feed(p, o2)
+    o2.setup_cli(True)
+    o2.initialize_optimization()
+    o2.algorithm_init()
+    o2.build_structure()
+    assert abs(o2.compute_active_errors() - float(np.sum(residuals(x0) ** 2))) <= 1e-9 * chi_oracle * 100
