@@ -13,7 +13,8 @@
  * pinned by (1) the known-answer table of BASELINE.md section 2 (block-AMD permutation hash, nnz(L)), which was
  * produced by the reference's vendored CSparse and which this oracle reproduces through the same
  * library, and (2) the reference's two self-consistency tests restated in tests/ (analytic vs numeric
- * Jacobian at 1e-6).  The CHOLMOD flavour of the path is unpinned by the reference (SuiteSparse is not
+ * Jacobian at 1e-6), and (3) independent-solver checks in tests/ (converged chi2 of the SE3, SBACam and expmap families
+ * against scipy.optimize.least_squares on the same cost; SE3Quat::exp against expm).  The CHOLMOD flavour of the path is unpinned by the reference (SuiteSparse is not
  * vendored); parity is claimed against the CSparse flavour ({gn,lm}_fix* solvers).
  */
 #ifndef G2O_B200_ORACLE_H
