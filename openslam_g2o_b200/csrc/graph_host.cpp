@@ -394,7 +394,7 @@ int b200_graph_load(b200_graph* g, const char* path) {
   // phase 1 (parallel): the text is cut at line starts into one chunk per thread; every chunk is tokenised into records
   // (tag, ids, numbers).  phase 2 (sequential, file order): the records are applied to the graph - id map inserts,
   // vertices created by an edge that precedes their VERTEX line, duplicates, FIX - exactly like a line-by-line reader.
-  int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+  int nthreads = g2o_b200::host_threads();  // cores this process may use, at most 16
   if (const char* e = getenv("G2O_B200_LOADER_THREADS")) nthreads = std::max(1, atoi(e));
   nthreads = (int)std::max<size_t>(1, std::min<size_t>(nthreads, rd / ((size_t)1 << 20) + 1));  // >= 1 MiB per thread
   std::vector<const char*> cut(nthreads + 1);

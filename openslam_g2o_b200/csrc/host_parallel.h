@@ -4,6 +4,9 @@
 // of the output, offsets come from prefix sums, sorts use total orders.  b200_debug_upload_digest pins that
 // (tests/test_graph_host.py).  G2O_B200_HOST_THREADS overrides the thread count (1 = everything inline).
 #pragma once
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
@@ -14,7 +17,12 @@ namespace g2o_b200 {
 
 inline int host_threads() {
   if (const char* e = getenv("G2O_B200_HOST_THREADS")) return std::max(1, atoi(e));
-  return (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned n = std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;  // the cores this process may run on (taskset, container cpusets), not the cores of the machine
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min<unsigned>(n ? n : 1u, (unsigned)CPU_COUNT(&set));
+#endif
+  return (int)std::min(16u, std::max(1u, n));
 }
 
 // number of ranges [0, n) is cut into: at most host_threads(), at least `grain` items each
