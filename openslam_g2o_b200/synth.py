@@ -6,7 +6,8 @@ text line), so the same arrays feed the product (SparseOptimizer.add_vertices/ad
 
   sphere(nodes_per_level, laps, ...)   examples/sphere/create_sphere.cpp:95-184 (reference generator)
   venice_like(cams, points, ...)       SURVEY.md section 8d config 3/4: ring of inward-looking cameras, windowed visibility
-  expmap_ba(cams, points, ...)         the same scene as VERTEX_SE3:EXPMAP / EDGE_PROJECT_XYZ2UV:EXPMAP (examples/ba/ba_demo.cpp)
+  expmap_ba(cams, points, ...)         the same scene as VERTEX_SE3:EXPMAP / EDGE_PROJECT_XYZ2UV:EXPMAP
+  ba_demo(pixel_noise, outliers, ...)  the scene of the reference's examples/ba/ba_demo.cpp
 """
 import numpy as np
 
@@ -154,6 +155,41 @@ def expmap_ba(num_cams=30, num_points=600, seed=7, focal_length=1000.0, principa
                 cam_payload=np.ascontiguousarray(p["cam_payload"][:, :7]), point_ids=p["point_ids"],
                 point_payload=p["point_payload"], edge_v0=p["edge_v0"], edge_v1=p["edge_v1"], edge_payload=pay,
                 truth_points=p["truth_points"], truth_cams=p["truth_cams"])
+
+
+def ba_demo(pixel_noise=1.0, outlier_ratio=0.0, seed=1):
+    """The scene of the reference's examples/ba/ba_demo.cpp:170-250 in .g2o payload form: 500 points in the box
+    [-1.5, 1.5] x [-0.5, 0.5] x [3, 4], 15 cameras with identity rotation at x = 0.04 i - 1 (world -> camera translation,
+    as ba_demo sets the estimate), focal length 1000, principal point (320, 240); a point is kept when at least two
+    cameras see it inside the 640 x 480 image; pixel noise N(0, pixel_noise), initial points = truth + N(0, 1) per axis;
+    with `outlier_ratio` an observation is replaced by a uniform pixel.  The first two poses are meant to be fixed
+    (`fixed_ids`).  numpy PCG64 stands in for the reference's std::rand."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    truth = np.stack([(rng.uniform(0, 1, 500) - 0.5) * 3, rng.uniform(0, 1, 500) - 0.5, rng.uniform(0, 1, 500) + 3], axis=1)
+    f, cx, cy = 1000.0, 320.0, 240.0
+    trans = np.stack([np.arange(15) * 0.04 - 1.0, np.zeros(15), np.zeros(15)], axis=1)   # world -> camera, R = I
+    # the .g2o vertex line holds cam2world = the inverse: same rotation, translation negated
+    cam_payload = np.concatenate([-trans, np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (15, 1))], axis=1)
+    pc = truth[:, None, :] + trans[None, :, :]                                          # [point, camera, 3]
+    z = np.stack([f * pc[..., 0] / pc[..., 2] + cx, f * pc[..., 1] / pc[..., 2] + cy], axis=-1)
+    vis = (z[..., 0] >= 0) & (z[..., 1] >= 0) & (z[..., 0] < 640) & (z[..., 1] < 480)
+    keep = vis.sum(1) >= 2
+    truth_kept = truth[keep]
+    init = truth_kept + rng.normal(0, 1, truth_kept.shape)
+    pi, ci = np.nonzero(vis[keep])
+    uv = z[keep][pi, ci]
+    outlier = rng.uniform(0, 1, len(uv)) < outlier_ratio
+    uv = np.where(outlier[:, None], np.stack([rng.uniform(0, 640, len(uv)), rng.uniform(0, 480, len(uv))], axis=1), uv)
+    uv = uv + rng.normal(0, pixel_noise, uv.shape)
+    inlier = np.ones(len(truth_kept), bool)
+    inlier[np.unique(pi[outlier])] = False
+    n = len(uv)
+    pay = np.concatenate([np.zeros((n, 1)), uv, np.ones((n, 1)), np.zeros((n, 1)), np.ones((n, 1))], axis=1)
+    cam_ids = np.arange(15, dtype=np.int32)
+    pt_ids = (15 + np.arange(len(truth_kept))).astype(np.int32)
+    return dict(kind="ba_expmap", camera_parameters={0: (f, cx, cy, 0.0)}, cam_ids=cam_ids, cam_payload=cam_payload,
+                point_ids=pt_ids, point_payload=init, edge_v0=pt_ids[pi], edge_v1=cam_ids[ci], edge_payload=pay,
+                truth_points=truth_kept, inlier_points=inlier, fixed_ids=np.array([0, 1], dtype=np.int32))
 
 
 def _rot_to_quat(R):

@@ -207,3 +207,70 @@ def test_oracle_expmap_optimum_matches_an_independent_solver():
     o2.algorithm_init()
     o2.build_structure()
     assert abs(o2.compute_active_errors() - float(np.sum(residuals(x0) ** 2))) <= 1e-9 * chi_oracle * 100
+
+
+def _ba_demo_pair(outliers, device):
+    """the reference's examples/ba/ba_demo.cpp scene in the product (device) and in the oracle; first two poses fixed"""
+    import openslam_g2o_b200 as g
+    from oracle_binding import Oracle
+    from openslam_g2o_b200 import synth
+    p = synth.ba_demo(pixel_noise=1.0, outlier_ratio=0.1 if outliers else 0.0, seed=4)
+    opt = g.SparseOptimizer(device=device)
+    opt.set_algorithm("lm_fix6_3")
+    o = Oracle()
+    for t in (opt, o):
+        synth.feed(p, t)
+        for f in p["fixed_ids"]:
+            t.set_fixed(int(f))
+    assert opt.setup_cli() == o.setup_cli(True) == -1   # two poses are fixed already: no gauge vertex is chosen
+    opt.initialize_optimization()
+    o.initialize_optimization()
+    if outliers:                                         # ba_demo's ROBUST_KERNEL: RobustKernelHuber, default delta 1
+        opt.set_robust_kernel("Huber", 1.0)
+        o.set_robust_kernel("Huber", 1.0)
+    return p, opt, o
+
+
+@needs_oracle
+@pytest.mark.parametrize("outliers", [False, True])
+def test_ba_demo_scene_in_the_oracle(outliers):
+    """what ba_demo prints: the point error (inliers only) shrinks over 10 Levenberg iterations; chi2 never increases"""
+    from oracle_binding import LM
+    p, _, o = _ba_demo_pair(outliers, device=-1)
+    n, st = o.optimize(LM, 10)
+    assert n == 10
+    chi = np.array([s.chi2 for s in st])
+    assert np.all(np.diff(chi) <= 0) and chi[-1] < 0.35 * chi[0]
+    pts = np.stack([o.vertex_estimate(int(i)) for i in p["point_ids"]])
+    m = p["inlier_points"]
+    before = np.sqrt(((p["point_payload"] - p["truth_points"])[m] ** 2).sum(1).mean())
+    after = np.sqrt(((pts - p["truth_points"])[m] ** 2).sum(1).mean())
+    assert before > 1.5 and after < 0.3 * before
+    # the fixed poses did not move
+    for f in p["fixed_ids"]:
+        assert np.allclose(o.vertex_estimate(int(f))[:3], [0.04 * f - 1.0, 0.0, 0.0], atol=0, rtol=0)
+
+
+@pytest.mark.gpu
+@needs_oracle
+@pytest.mark.parametrize("outliers", [False, True])
+def test_ba_demo_scene_matches_oracle(outliers):
+    """the same scene on the B200 path: far-off start (chi2 ~ 1e8 -> 1e4), two fixed poses, Huber kernel with 10 %
+    outliers - the first Levenberg iterations, where every step is a clear decrease, agree with the oracle (1e-5: the
+    run is stopped far from convergence, where rounding differences are still being amplified by the large steps)"""
+    from oracle_binding import LM
+    p, opt, o = _ba_demo_pair(outliers, device=0)
+    iters = 4
+    n = opt.optimize(iters)
+    no, st = o.optimize(LM, iters)
+    assert n == no == iters
+    chi_g = np.array([s.chi2 for s in opt.batch_statistics])
+    chi_o = np.array([s.chi2 for s in st[:no]])
+    assert np.abs(chi_g - chi_o).max() <= CHI_TOL * chi_o.max() and abs(chi_g[-1] - chi_o[-1]) <= 1e-5 * chi_o[-1]
+    opt.sync_estimates()
+    pts_g = np.stack([opt.vertex_estimate(int(i)) for i in p["point_ids"]])
+    pts_o = np.stack([o.vertex_estimate(int(i)) for i in p["point_ids"]])
+    assert rel_err(pts_g, pts_o) < 1e-5
+    cams_g = np.stack([opt.vertex_estimate(int(i))[:7] for i in p["cam_ids"]])
+    cams_o = np.stack([o.vertex_estimate(int(i)) for i in p["cam_ids"]])
+    assert rel_err(cams_g, cams_o) < 1e-5
