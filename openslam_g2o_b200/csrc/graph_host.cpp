@@ -391,6 +391,8 @@ int b200_graph_load(b200_graph* g, const char* path) {
   buf[rd] = '\n';
   const char* const base = buf.data();
   const char* const end = base + rd + 1;
+  // Peak host memory: the file image + the parsed numbers (8 bytes per number) + 32 bytes per record, next to the graph
+  // itself - roughly 3x the file size for bundle-adjustment inputs.
   // phase 1 (parallel): the text is cut at line starts into one chunk per thread; every chunk is tokenised into records
   // (tag, ids, numbers).  phase 2 (sequential, file order): the records are applied to the graph - id map inserts,
   // vertices created by an edge that precedes their VERTEX line, duplicates, FIX - exactly like a line-by-line reader.

@@ -3,6 +3,8 @@
 // Every use is written so that the RESULT does not depend on the number of threads: a thread owns a contiguous range
 // of the output, offsets come from prefix sums, sorts use total orders.  b200_debug_upload_digest pins that
 // (tests/test_graph_host.py).  G2O_B200_HOST_THREADS overrides the thread count (1 = everything inline).
+// Rules for the bodies: plain host memory only - no CUDA calls, no DevBuf (host_only_flag() is thread-local and unset
+// in the workers) - and nothing that throws (an exception escaping a worker terminates the process).
 #pragma once
 #if defined(__linux__)
 #include <sched.h>
