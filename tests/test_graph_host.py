@@ -264,3 +264,41 @@ def test_structure_plan_digest_is_deterministic_and_sensitive(monkeypatch):
     q["edge_v1"] = p["edge_v1"].copy()
     q["edge_v1"][17] = (q["edge_v1"][17] + 20) % 40
     assert digest(q) != d0
+
+
+def test_expmap_poses_may_use_different_camera_parameters(tmp_path):
+    """CameraParameters belong to the edges in g2o; the B200 path carries them in the pose rows, so different poses may
+    name different parameters (a multi-camera rig) as long as each pose is consistent"""
+    import openslam_g2o_b200 as g
+    txt = """PARAMS_CAMERAPARAMETERS 0 1000 320 240 0
+PARAMS_CAMERAPARAMETERS 7 650.5 300 250 0.1
+VERTEX_SE3:EXPMAP 0 0 0 0 0 0 0 1
+VERTEX_SE3:EXPMAP 1 0.5 0 0 0 0 0 1
+VERTEX_XYZ 2 0.1 0.2 4
+VERTEX_XYZ 3 -0.3 0.1 5
+EDGE_PROJECT_XYZ2UV:EXPMAP 2 0 0 345 290 1 0 1
+EDGE_PROJECT_XYZ2UV:EXPMAP 3 0 0 260 260 1 0 1
+EDGE_PROJECT_XYZ2UV:EXPMAP 2 1 7 235 282 2 0.5 3
+EDGE_PROJECT_XYZ2UV:EXPMAP 3 1 7 196 263 2 0.5 3
+EDGE_PROJECT_XYZ2UV:EXPMAP 3 1 9 196 263 2 0.5 3
+"""
+    f = tmp_path / "rig.g2o"
+    f.write_text(txt)
+    o = g.SparseOptimizer(device=-1)
+    assert o.load(f)
+    vc, ec = o.counts()
+    assert ec[g.EDGE_XYZ2UV] == 4          # the edge naming the unknown parameter 9 was dropped (resolveParameters)
+    assert np.array_equal(o.vertex_estimate(0)[7:], [1000, 1000, 320, 240, 0])
+    assert np.array_equal(o.vertex_estimate(1)[7:], [650.5, 650.5, 300, 250, 0.1])
+    # estimate = inverse of the file's cam2world: identity rotation, translation negated
+    assert np.array_equal(o.vertex_estimate(1)[:7], [-0.5, 0, 0, 0, 0, 0, 1])
+    assert o.setup_cli() == 0
+    o.initialize_optimization()
+    o._ensure_uploaded()
+    assert o.context.build_structure()
+    out = tmp_path / "rig_out.g2o"
+    assert o.save(out)
+    lines = out.read_text().splitlines()
+    assert lines[0].startswith("PARAMS_CAMERAPARAMETERS 0 ") and lines[1].startswith("PARAMS_CAMERAPARAMETERS 7 650.5")
+    assert sum(ln.startswith("EDGE_PROJECT_XYZ2UV:EXPMAP") for ln in lines) == 4
+    assert any(ln.startswith("EDGE_PROJECT_XYZ2UV:EXPMAP 3 1 7 ") for ln in lines)
