@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -40,8 +41,16 @@ inline void parallel_ranges(size_t n, int parts, F&& f) {
   if (parts <= 1) { f(0, (size_t)0, n); return; }
   std::vector<std::thread> th;
   th.reserve(parts - 1);
-  for (int t = 1; t < parts; ++t) th.emplace_back([&f, n, parts, t] { f(t, range_begin(n, parts, t), range_begin(n, parts, t + 1)); });
+  int started = 1;  // ranges [1, started) run on their own thread
+  try {
+    for (; started < parts; ++started) {
+      const int t = started;
+      th.emplace_back([&f, n, parts, t] { f(t, range_begin(n, parts, t), range_begin(n, parts, t + 1)); });
+    }
+  } catch (const std::system_error&) {  // no more threads to be had (container limits): the rest runs here
+  }
   f(0, (size_t)0, range_begin(n, parts, 1));
+  for (int t = started; t < parts; ++t) f(t, range_begin(n, parts, t), range_begin(n, parts, t + 1));
   for (std::thread& x : th) x.join();
 }
 
