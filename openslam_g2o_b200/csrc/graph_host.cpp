@@ -412,12 +412,9 @@ int b200_graph_load(b200_graph* g, const char* path) {
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
   std::vector<ParsedChunk> chunks(nthreads);
-  if (nthreads == 1) parse_chunk(cut[0], cut[1], chunks[0]);
-  else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t) th.emplace_back(parse_chunk, cut[t], cut[t + 1], std::ref(chunks[t]));
-    for (std::thread& x : th) x.join();
-  }
+  g2o_b200::parallel_ranges((size_t)nthreads, nthreads, [&](int, size_t tb, size_t te) {
+    for (size_t t = tb; t < te; ++t) parse_chunk(cut[t], cut[t + 1], chunks[t]);
+  });
   const double t1 = now();
   size_t nv = 0, ne = 0;
   for (const ParsedChunk& c : chunks) for (const ParsedRecord& r : c.recs) { if (r.type == REC_VERTEX) ++nv; else if (r.type == REC_EDGE) ++ne; }
