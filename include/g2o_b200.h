@@ -32,6 +32,7 @@ extern "C" {
 #define B200_ERR_CUDA (-3)
 #define B200_ERR_UNSUPPORTED (-4)      /* graph uses types outside {SE2,SE3,CAM,XYZ}: no CPU fallback */
 #define B200_ERR_COLLECTIVE (-5)
+#define B200_ERR_EXCEPTION (-6)        /* a C++ exception other than a CUDA failure (std::bad_alloc, ...) was caught at the ABI */
 
 enum { B200_VERTEX_SE2 = 0, B200_VERTEX_SE3 = 1, B200_VERTEX_CAM = 2, B200_VERTEX_XYZ = 3, B200_VERTEX_SE3_EXPMAP = 4 };
 /* XYZ2UV = EdgeProjectXYZ2UV (types/sba/types_six_dof_expmap.h:133-155), the monocular edge of ba_demo / SE3 expmap BA */
@@ -39,8 +40,11 @@ enum { B200_EDGE_SE2 = 0, B200_EDGE_SE3 = 1, B200_EDGE_P2MC = 2, B200_EDGE_XYZ2U
 #define B200_NUM_VERTEX_KINDS 5
 #define B200_NUM_EDGE_KINDS 4
 enum { B200_GAUSS_NEWTON = 0, B200_LEVENBERG = 1 };
-/* OptimizationAlgorithm::SolverResult (core/optimization_algorithm.h:49) */
+/* OptimizationAlgorithm::SolverResult (core/optimization_algorithm.h:49): the value stored in b200_iter_stats.result.
+ * The RETURN value of b200_algorithm_solve never uses -1 for it (that is B200_ERR_INVALID): a failed linear solve
+ * (GN: not positive definite) is returned as B200_SOLVE_FAIL, hard errors are < 0. */
 enum { B200_RESULT_TERMINATE = 2, B200_RESULT_OK = 1, B200_RESULT_FAIL = -1 };
+#define B200_SOLVE_FAIL 3
 
 typedef struct b200_ctx b200_ctx;
 
@@ -84,7 +88,9 @@ int b200_set_edges(b200_ctx* ctx, int kind, int n, const int32_t* vi, const int3
  * replicated.  After the local Schur reduction [Hschur | bschur | scalars] is all-reduced through fn. */
 int b200_set_allreduce(b200_ctx* ctx, b200_allreduce_fn fn, void* user, int rank, int world_size);
 /* sharded BA: blocks (rows[i] <= cols[i]) that OTHER shards contribute to the reduced camera matrix, so that
- * every rank builds the identical Hschur pattern (core/block_solver.hpp:262-288 over the whole graph) */
+ * every rank builds the identical Hschur pattern (core/block_solver.hpp:262-288 over the whole graph).
+ * Call AFTER b200_set_vertices (which forgets the keys of the previous graph) and before b200_build_structure;
+ * indices are Hessian block indices of free poses (checked against numPoses at b200_build_structure). */
 int b200_add_schur_pattern(b200_ctx* ctx, int n, const int32_t* rows, const int32_t* cols);
 /* the CUDA stream (cudaStream_t) all work of this context is ordered on; b200_synchronize waits for it */
 void* b200_get_stream(b200_ctx* ctx);
@@ -117,7 +123,9 @@ int b200_discard_top(b200_ctx* ctx);
  * core/optimization_algorithm_gauss_newton.cpp:50-93), whole iteration device-resident.
  * stats may be NULL, else room for max_iterations records.  returns #iterations done (0 on Fail), <0 error */
 int b200_optimize(b200_ctx* ctx, int algorithm, int max_iterations, b200_iter_stats* stats);
-/* one OptimizationAlgorithm::solve(iteration) */
+/* one OptimizationAlgorithm::solve(iteration).  returns B200_RESULT_OK (1), B200_RESULT_TERMINATE (2) or
+ * B200_SOLVE_FAIL (3; stats->result = B200_RESULT_FAIL = -1 as in the reference's enum); < 0: hard error (nothing
+ * was solved - missing structure, CUDA failure, out of memory), never an ordinary LM/GN outcome */
 int b200_algorithm_solve(b200_ctx* ctx, int algorithm, int iteration, b200_iter_stats* stats);
 /* fill-reducing ordering of the (reduced) pose system.  nd_levels = 0 (default): block AMD, bit-exact with the
  * reference's cs_amd(1, .) on the block pattern (solvers/csparse/linear_solver_csparse.h:252-294).  nd_levels = k > 0:

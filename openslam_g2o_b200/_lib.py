@@ -14,12 +14,13 @@ LIB_PATH = os.environ.get("G2O_B200_LIB", os.path.join(_HERE, "libg2o_b200.so"))
 
 OK = 0
 NOT_POSITIVE_DEFINITE = 1
-ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_COLLECTIVE = -1, -2, -3, -4, -5
+ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_COLLECTIVE, ERR_EXCEPTION = -1, -2, -3, -4, -5, -6
 VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP = 0, 1, 2, 3, 4
 EDGE_SE2, EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV = 0, 1, 2, 3
 NUM_VERTEX_KINDS, NUM_EDGE_KINDS = 5, 4
 GAUSS_NEWTON, LEVENBERG = 0, 1
-RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1
+RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1   # values of IterStats.result (g2o's SolverResult)
+SOLVE_FAIL = 3                                        # return value of b200_algorithm_solve for a failed solve
 
 VERTEX_EST_LEN = {VERTEX_SE2: 3, VERTEX_SE3: 12, VERTEX_CAM: 12, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 12}
 VERTEX_DIM = {VERTEX_SE2: 3, VERTEX_SE3: 6, VERTEX_CAM: 6, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 6}

@@ -12,6 +12,13 @@
 //   * depth-first post-order of the assembly tree where children are visited youngest first.
 // tests/test_amd.py checks it against the vendored cs_amd on the four in-tree datasets and on random,
 // banded, arrow-head and dense-row patterns.
+//
+// Attribution: because the permutation has to be bit-exact, this file follows the structure of cs_amd.c step by step
+// (same quotient-graph phases in the same order, the same working arrays, the dense-node rule, the in-place garbage
+// collection).  It is a derived work of CSparse: "CSparse: a Concise Sparse matrix package", Copyright (c) 2006-2012,
+// Timothy A. Davis, http://www.suitesparse.com - distributed under the GNU Lesser General Public License, version 2.1
+// or (at your option) any later version (EXTERNAL/csparse/License.txt of the reference tree).  This file is made
+// available under the same terms; CSparse and this file come WITHOUT ANY WARRANTY.
 #include "block_amd.h"
 
 #include <algorithm>

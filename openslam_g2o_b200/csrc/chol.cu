@@ -825,13 +825,13 @@ void up64(DevBuf<long long>& d, const std::vector<T>& v, cudaStream_t s, std::ve
   d.upload(keep.back(), s);
 }
 constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per CTA minus the static shared variables
+// The opt-in is a per-DEVICE (per-context) function attribute: it is set on the device current at every analyze(), not
+// once per process - a second solver context on another GPU of the same process needs it too.  Always the maximum,
+// so that contexts with different panel sizes on one device cannot lower it under each other.
 template <int D>
 void set_smem_attrs() {
-  static bool done = false;
-  if (done) return;
   B200_CUDA(cudaFuncSetAttribute(chol_factor_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_backward_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  done = true;
 }
 // profiler ids of the kernel groups inside the Cholesky (continue the numbering of solver.cu)
 enum { PH_CH_SCATTER = 12, PH_CH_FLOW = 13, PH_CH_BACKWARD = 19 };

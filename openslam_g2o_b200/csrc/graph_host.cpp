@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -110,6 +111,9 @@ struct b200_graph {
   std::vector<int> active_edges;            // edge indices, internalId order
   std::vector<int> kind_slots[B200_NUM_VERTEX_KINDS];  // per kind: vertex indices handed to the context (ascending id)
   std::map<int, std::array<double, 4>> camera_parameters;  // PARAMS_CAMERAPARAMETERS id -> f cx cy baseline
+  // landmark sharding of the last upload: per XYZ slot the row handed to the context (-1: another shard owns it).
+  // Empty = nothing sharded (row i of the context is slot i).  b200_graph_download scatters through it.
+  std::vector<int> uploaded_lm_row;
   std::string err;
   int find(int id) const { auto it = idmap.find(id); return it == idmap.end() ? -1 : it->second; }
 };
@@ -382,12 +386,25 @@ int b200_graph_load(b200_graph* g, const char* path) {
   if (!g || !path) return B200_ERR_INVALID;
   FILE* f = fopen(path, "rb");
   if (!f) { g->err = std::string("cannot open ") + path; return B200_ERR_INVALID; }
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<char> buf((size_t)sz + 1);
+  long sz = -1;
+  if (fseek(f, 0, SEEK_END) == 0) sz = ftell(f);
+  if (sz < 0 || sz == LONG_MAX || fseek(f, 0, SEEK_SET) != 0) {  // a directory, a pipe, ...
+    fclose(f);
+    g->err = std::string("cannot read ") + path + " (not a regular file)";
+    return B200_ERR_INVALID;
+  }
+  std::vector<char> buf;
+  try {
+    buf.resize((size_t)sz + 1);
+  } catch (const std::exception&) {
+    fclose(f);
+    g->err = std::string("out of memory reading ") + path;
+    return B200_ERR_INVALID;
+  }
   size_t rd = fread(buf.data(), 1, (size_t)sz, f);
+  const bool read_error = ferror(f) != 0;
   fclose(f);
+  if (read_error) { g->err = std::string("read error on ") + path; return B200_ERR_INVALID; }
   buf[rd] = '\n';
   const char* const base = buf.data();
   const char* const end = base + rd + 1;
@@ -420,7 +437,9 @@ int b200_graph_load(b200_graph* g, const char* path) {
   for (const ParsedChunk& c : chunks) for (const ParsedRecord& r : c.recs) { if (r.type == REC_VERTEX) ++nv; else if (r.type == REC_EDGE) ++ne; }
   g->vertices.reserve(g->vertices.size() + nv);
   g->edges.reserve(g->edges.size() + ne);
-  g->idmap.rehash((size_t)((g->vertices.size() + nv) / 0.8) + 16);
+  // no idmap.rehash() here: the gauge is the first max-dimension vertex in VertexIDMap ITERATION order
+  // (b200_graph_setup_cli), and that order depends on the bucket count - the map must grow exactly like the
+  // reference's naturally grown tr1::unordered_map (and like this graph's own add_vertices path)
   for (const ParsedChunk& c : chunks)
     for (const ParsedRecord& r : c.recs) {
       const double* nums = c.nums.data() + r.off;
@@ -543,6 +562,7 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     std::vector<double> est;
     std::vector<int32_t> hidx;
     std::vector<uint8_t> marg;
+    if (kind == B200_VERTEX_XYZ) g->uploaded_lm_row.clear();
     if (kind == B200_VERTEX_XYZ && ba) {
       local_slot.assign(sl.size(), -1);
       int nloc = 0, nfree = 0;
@@ -554,8 +574,11 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
         hidx.push_back(v.hidx >= 0 ? np + nfree++ : -1);
         marg.push_back(v.marginalized ? 1 : 0);
       }
-      if (num_shards == 1)  // keep g2o's own numbering when nothing is sharded
+      if (num_shards == 1) {  // keep g2o's own numbering when nothing is sharded
         for (size_t i = 0, q = 0; i < sl.size(); ++i) if (lm_shard[i] == shard) hidx[q++] = g->vertices[sl[i]].hidx;
+      } else {
+        g->uploaded_lm_row = local_slot;
+      }
     } else {
       for (int i : sl) {
         const HVertex& v = g->vertices[i];
@@ -638,6 +661,16 @@ int b200_graph_download(b200_graph* g, b200_ctx* ctx) {
     std::vector<double> est(sl.size() * ne);
     int rc = b200_get_estimates(ctx, kind, est.data());
     if (rc) { g->err = b200_last_error(ctx); return rc; }
+    if (kind == B200_VERTEX_XYZ && !g->uploaded_lm_row.empty()) {
+      // landmark-sharded upload: the context holds only this shard's landmarks, in local row order; the landmarks of
+      // the other shards keep their host estimates (their owners hold the optimised values)
+      if (g->uploaded_lm_row.size() != sl.size()) { g->err = "graph changed since the sharded upload"; return B200_ERR_INVALID; }
+      for (size_t i = 0; i < sl.size(); ++i) {
+        const int row = g->uploaded_lm_row[i];
+        if (row >= 0) memcpy(g->vertices[sl[i]].est, &est[(size_t)row * ne], ne * sizeof(double));
+      }
+      continue;
+    }
     for (size_t i = 0; i < sl.size(); ++i) memcpy(g->vertices[sl[i]].est, &est[i * ne], ne * sizeof(double));
   }
   return B200_OK;

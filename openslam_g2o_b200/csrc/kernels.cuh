@@ -493,6 +493,7 @@ constexpr int kSrThreads = 128;   // 32 groups of 4 lanes; 3 CTAs per SM (shared
 constexpr int kSrLanes = 4;
 constexpr int kSrSegMax = 64;     // products per segment
 constexpr int kSrPartial = 42;    // 36 block entries + 6 right-hand-side entries (diagonal blocks)
+constexpr int kSrMaxDynSmem = 226 * 1024;  // opt-in dynamic shared memory of schur_range_kernel (device maximum)
 
 struct SchurRanges {
   const int* slot0;    // nr+1: first Hpl slot of a range

@@ -48,8 +48,8 @@ int guarded(b200_ctx* c, F&& f) {
     if (e.code == cudaErrorNoDevice || e.code == cudaErrorInsufficientDriver) return B200_ERR_NO_DEVICE;
     return B200_ERR_CUDA;
   } catch (const std::exception& e) {
-    c->err = e.what();
-    return B200_ERR_INVALID;
+    c->err = std::string("exception: ") + e.what();
+    return B200_ERR_EXCEPTION;
   }
 }
 int fail(b200_ctx* c, int code, const std::string& msg) {
@@ -432,7 +432,10 @@ int build_structure_impl(b200_ctx* c) {
     std::vector<long long> keys;
     auto compact = [&]() { std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end()); };
     for (int i = 0; i < np; ++i) keys.push_back(((long long)i << 32) | i);
-    for (long long k2 : c->extra_schur_keys) keys.push_back(k2);
+    for (long long k2 : c->extra_schur_keys) {  // blocks other shards contribute (b200_add_schur_pattern)
+      if ((int)(k2 >> 32) >= np) return fail(c, B200_ERR_INVALID, "b200_add_schur_pattern: block index beyond the number of free poses");
+      keys.push_back(k2);
+    }
     size_t next_compact = std::max<size_t>(keys.size() * 2, (size_t)1 << 24);
     // distinct Hpl slots per landmark rank (slots are numbered in rank order; hpl_row[slot] = camera, ascending per landmark)
     std::vector<int> lm_s0(nl + 1, 0);
@@ -598,7 +601,10 @@ int build_structure_impl(b200_ctx* c) {
       c->d_sr_partial.alloc((size_t)std::max(nseg, 1) * k::kSrPartial);
       if (!c->host_only) {
         B200_CUDA(cudaStreamSynchronize(s));
-        B200_CUDA(cudaFuncSetAttribute(k::schur_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_range_smem(c)));
+        // always the device maximum (not this context's size): a second context on the same device with a smaller
+        // range capacity must not lower the opt-in under this one
+        if (schur_range_smem(c) > (size_t)k::kSrMaxDynSmem) return fail(c, B200_ERR_UNSUPPORTED, "Schur range larger than shared memory");
+        B200_CUDA(cudaFuncSetAttribute(k::schur_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k::kSrMaxDynSmem));
       }
     }
   STAMP("Schur plan");
@@ -978,6 +984,9 @@ int b200_set_vertices(b200_ctx* c, int kind, int n, const double* est, const int
   V.hidx.assign(hidx, hidx + n);
   if (marg) V.marg.assign(marg, marg + n); else V.marg.clear();
   c->structured = false;
+  // a new vertex set renumbers the poses: pattern keys handed over for the previous graph are stale (the uploader
+  // sends vertices first, then the foreign Schur pattern, then the edges)
+  c->extra_schur_keys.clear();
   return B200_OK;
 }
 
@@ -1001,7 +1010,9 @@ int b200_set_allreduce(b200_ctx* c, b200_allreduce_fn fn, void* user, int rank, 
 }
 
 int b200_add_schur_pattern(b200_ctx* c, int n, const int32_t* rows, const int32_t* cols) {
-  if (!c || n < 0) return B200_ERR_INVALID;
+  if (!c || n < 0 || (n > 0 && (!rows || !cols))) return B200_ERR_INVALID;
+  for (int i = 0; i < n; ++i)
+    if (rows[i] < 0 || cols[i] < 0 || rows[i] > cols[i]) return fail(c, B200_ERR_INVALID, "Schur pattern keys must be upper-triangular block indices (0 <= row <= col)");
   for (int i = 0; i < n; ++i) c->extra_schur_keys.push_back(((long long)cols[i] << 32) | (unsigned)rows[i]);
   c->structured = false;
   return B200_OK;
@@ -1208,7 +1219,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       sync_scalars(c);
       st->result = *c->h_status ? B200_RESULT_FAIL : B200_RESULT_OK;
       st->time_iteration = wall() - t_start;
-      return st->result;
+      return st->result == B200_RESULT_FAIL ? B200_SOLVE_FAIL : st->result;
     }
     // ---- Levenberg-Marquardt: core/optimization_algorithm_levenberg.cpp:57-147
     if ((rc = run_prologue(c))) return rc;
@@ -1268,7 +1279,7 @@ int b200_optimize(b200_ctx* c, int algorithm, int max_iterations, b200_iter_stat
     b200_iter_stats local;
     b200_iter_stats* st = stats ? &stats[i] : &local;
     result = b200_algorithm_solve(c, algorithm, i, st);
-    if (result < 0 && result != B200_RESULT_FAIL) return result;  // hard error
+    if (result < 0) return result;  // hard error (never an LM/GN outcome: those are 1, 2, B200_SOLVE_FAIL)
     ok = result == B200_RESULT_OK;
     // what SparseOptimizer::optimize does when statistics are on: chi2 of the state after the iteration
     // (LM already knows it; GN needs one more error pass)
@@ -1280,7 +1291,7 @@ int b200_optimize(b200_ctx* c, int algorithm, int max_iterations, b200_iter_stat
     }
     ++done;
   }
-  if (result == B200_RESULT_FAIL) return 0;
+  if (result == B200_SOLVE_FAIL) return 0;
   return done;
 }
 
@@ -1314,7 +1325,11 @@ int b200_get_estimates(b200_ctx* c, int kind, double* out) {
     if (!lm && kind != c->pose_kind) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     if (lm && !c->schur) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
-    NEED_DEVICE(c);
+    if (c->host_only) {  // no device, nothing was optimised: the estimates as ingested (structure-phase tests on the CPU box)
+      const b200_ctx::VertexSet& V = c->vs[lm ? B200_VERTEX_XYZ : c->pose_kind];
+      std::copy(V.est.begin(), V.est.begin() + (size_t)n * ne, out);
+      return (int)B200_OK;
+    }
     B200_CUDA(cudaSetDevice(c->device));
     const double* dev = lm ? c->d_lm_est.p : c->d_pose_est.p;
     if (st == ne) {

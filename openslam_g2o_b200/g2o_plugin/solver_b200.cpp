@@ -276,7 +276,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
   virtual SolverResult solve(int iteration, bool /*online*/ = false) {
     b200_iter_stats st;
     int rc = b200_algorithm_solve(_ctx, _algorithm, iteration, &st);
-    if (rc < 0 && rc != B200_RESULT_FAIL) {
+    if (rc < 0) {  // hard error (bad structure, CUDA failure, out of memory): st is not meaningful
       std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
       return Fail;
     }

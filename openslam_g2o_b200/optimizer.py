@@ -133,8 +133,7 @@ class SolverContext:
     def algorithm_solve(self, algorithm, iteration):
         st = IterStats()
         rc = lib.b200_algorithm_solve(self._h, algorithm, iteration, C.byref(st))
-        if rc < 0 and rc != L.RESULT_FAIL:
-            _check(rc, self._h)
+        _check(rc, self._h)  # < 0 is always a hard error; OK / Terminate / SOLVE_FAIL are >= 1
         return rc, st
 
     def compute_marginals(self, pairs):

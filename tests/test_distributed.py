@@ -136,3 +136,29 @@ def test_sharded_bundle_adjustment_matches_single_gpu():
         assert np.abs(np.array(r["chi"]) - chi).max() <= 1e-9 * chi.max()
         assert np.abs(np.array(r["cams"]) - cams).max() <= 1e-8 * np.abs(cams).max()
     assert res[0]["chi"] == res[1]["chi"]  # ranks stay in lock-step bit for bit
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_download_scatters_only_the_owned_landmarks(world):
+    """b200_graph_download on a landmark-sharded upload: the context holds only this shard's landmarks in local row
+    order - every owned landmark must land in ITS vertex, the others keep their host estimates (host-only context:
+    the estimates come back as ingested, so any mis-scatter shows up as a changed vertex)"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    p = synth.venice_like(20, 700, seed=4)
+    owned_total = 0
+    for rank in range(world):
+        opt = g.SparseOptimizer(device=-1, shard=rank, num_shards=world)
+        synth.feed(p, opt)
+        opt.setup_cli()
+        opt.initialize_optimization()
+        opt._ensure_uploaded()
+        assert opt.context.build_structure()
+        owned_total += opt.context.dims()["numLandmarks"]
+        before = {int(i): opt.vertex_estimate(int(i)) for i in p["point_ids"]}
+        opt.sync_estimates()
+        for i in p["point_ids"]:
+            assert np.array_equal(opt.vertex_estimate(int(i)), before[int(i)]), (rank, int(i))
+        for i in p["cam_ids"][:5]:
+            assert np.allclose(opt.vertex_estimate(int(i))[:7], p["cam_payload"][int(i)][:7])
+    assert owned_total == len(p["point_ids"])

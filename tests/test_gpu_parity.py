@@ -441,3 +441,57 @@ def test_full_size_sphere2500_properties():
     chi = runs[0]
     assert all(b <= a * (1 + 1e-12) for a, b in zip(chi, chi[1:]))
     assert chi[-1] < 1e-2 * chi[0] or chi[-1] < 3 * (6 * 9799)  # converges towards the noise floor
+
+
+# ----------------------------------------------------------------------------------------------
+# parity gate on the configurations the benchmark numbers are quoted on: the CUDA path against
+# the oracle on the SAME full-size arrays - chi2, lambda and the number of LM trials per iteration, final state
+# ----------------------------------------------------------------------------------------------
+def _headline_parity(p, iters, stride):
+    import openslam_g2o_b200 as g
+    from oracle_binding import LM, Oracle
+    from openslam_g2o_b200 import synth
+    opt = g.SparseOptimizer(device=0)
+    opt.set_algorithm("lm_fix6_3")
+    o = Oracle()
+    synth.feed(p, opt)
+    synth.feed(p, o)
+    assert opt.setup_cli() == o.setup_cli(True) == 0
+    opt.initialize_optimization(); o.initialize_optimization()
+    n = opt.optimize(iters)
+    no, st = o.optimize(LM, iters)
+    assert n == no == iters
+    gs = opt.batch_statistics
+    chi_g, chi_o = np.array([s.chi2 for s in gs]), np.array([s.chi2 for s in st[:no]])
+    assert np.abs(chi_g - chi_o).max() <= CHI_TOL * np.abs(chi_o).min(), (chi_g, chi_o)   # every iteration, not only the largest
+    assert rel_err([s.lambda_ for s in gs], [s.lambda_ for s in st[:no]]) < 1e-5
+    assert [s.levenberg_iterations for s in gs] == [s.levenberg_iterations for s in st[:no]]
+    assert np.array_equal(opt.context.block_ordering(), o.block_perm())                     # AMD bit-exact
+    assert opt.context.factor_nnz() == o.lnz()
+    opt.sync_estimates()
+    ids, kinds, _, _ = o.vertices()
+    pose_ids = [int(i) for i, k in zip(ids, kinds) if k != 3]
+    pt_ids = [int(i) for i, k in zip(ids, kinds) if k == 3][::stride]
+    for group in (pose_ids, pt_ids):
+        if not group:
+            continue
+        eg = np.stack([opt.vertex_estimate(i) for i in group])
+        eo = np.stack([o.vertex_estimate(i) for i in group])
+        assert rel_err(eg, eo) < EST_TOL, rel_err(eg, eo)
+    return chi_g
+
+
+@needs_oracle
+def test_full_size_venice_matches_oracle():
+    """BASELINE.json configs[2] at full size (871 cameras / 530 304 points / ~2.0 M observations): 5 LM iterations"""
+    from openslam_g2o_b200 import synth
+    chi = _headline_parity(synth.venice_like(), 5, stride=3)
+    assert chi[-1] < chi[0]
+
+
+@needs_oracle
+def test_full_size_sphere2500_matches_oracle():
+    """BASELINE.json configs[1] at full size (2500 poses / 9799 edges): 10 LM iterations"""
+    from openslam_g2o_b200 import synth
+    chi = _headline_parity(synth.sphere(), 10, stride=1)
+    assert chi[-1] < chi[0]
