@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py - LM iterations/sec of the g2o hot path on B200 (see BASELINE.json `metric`).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload venice|sphere2500] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload venice|sphere2500|manhattan|ba10k|sphere40k|sphere1m]
+                  [--impl reference] [--no-extras]
 
 A "step" is one Levenberg-Marquardt iteration (OptimizationAlgorithmLevenberg::solve: errors + chi2, linearize +
 accumulate, [Schur], sparse Cholesky, back-substitution, oplus update, re-evaluation, lambda control) over one
-synthetic input graph.  The optimisation is restarted from the initial estimates every RESTART steps (like running
-`g2o -i 10` repeatedly) so that every step does comparable work; the restart copy is outside the per-step timers.
+synthetic input graph (manhattan: one Gauss-Newton iteration, BASELINE.json configs[0]).  The optimisation is restarted
+from the initial estimates every RESTART steps (like running `g2o -i 10` repeatedly) so that every step does comparable
+work; the restart copy is outside the per-step timers.  Both arms follow this protocol.
 
-  value   steps/s with all inputs resident in HBM (CUDA events on the solver's stream, max over ranks)
-  e2e     steps/s through the C-ABI with HOST buffers: per step, H2D of the vertex estimates from pinned memory, one
-          LM iteration, D2H of the updated estimates + chi2 (what a Level-3 g2o adapter does around solve())
-  roofline, cpu_baseline: see DESIGN.md section "Measurement"
+  value    steps/s with all inputs resident in HBM (CUDA events on the solver's stream, max over ranks)
+  e2e      steps/s through the C-ABI with HOST buffers: per step, H2D of the vertex estimates from pinned memory, one
+           LM iteration, D2H of the updated estimates + chi2 (the copies a Level-3 g2o adapter makes around solve();
+           the adapter's per-vertex setEstimate() walk over g2o's heap objects is NOT in it - no g2o binary exists here)
+  parity   the first RESTART iterations of this very process against the oracle on the same arrays (rank 0)
+  roofline the kernel that dominates the step by time first, the HBM-bound kernels beside it
+  cpu_baseline  the oracle on the box's host cores (1 thread: the reference's default build), same iterations
 
-N > 1 (torchrun): venice shards its landmarks over the ranks (cameras replicated, NCCL all-reduce of the reduced
-camera system per LM trial) - strong scaling of the same graph.
+N > 1 (torchrun): bundle adjustment shards its landmarks over the ranks (cameras replicated, two native ncclAllReduce
+per LM trial) - strong scaling of the same graph; pose graphs do not shard ("replicas only").  The default run adds
+short measurements of the other BASELINE.json configurations under `configs` (at N > 1: config 4, the one the
+landmark sharding exists for).
 """
 import argparse
-import ctypes
+import importlib.util
 import json
 import os
 import subprocess
@@ -31,6 +38,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 RESTART = 10  # LM iterations per optimisation run (the reference protocol: g2o -i 10)
 ND_LEVELS = {"venice": 5, "ba10k": 7, "sphere2500": 7, "sphere40k": 7}  # dissection depth of the extra measurement
+WORKLOADS = ["venice", "sphere2500", "manhattan", "venice_small", "ba10k", "sphere40k", "sphere1m"]
+GN, LM = 0, 1
 
 
 def parse():
@@ -38,26 +47,63 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="venice", choices=["venice", "sphere2500", "venice_small", "ba10k", "sphere40k"])
+    ap.add_argument("--workload", default="venice", choices=WORKLOADS)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle (no parity, no cpu_baseline)")
     ap.add_argument("--no-parallel-ordering", action="store_true", help="skip the extra nested-dissection measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations")
     ap.add_argument("--nd-levels", type=int, default=0,
                     help="ordering of the reduced system: 0 = block AMD (reference, default); k = nested dissection, 2^k parts")
     return ap.parse_args()
 
 
-def make_problem(workload):
-    from openslam_g2o_b200 import synth
+def load_synth():
+    """the generators by file path: importing the package would map libg2o_b200.so, which the reference arm must not"""
+    spec = importlib.util.spec_from_file_location("g2o_b200_synth", os.path.join(ROOT, "openslam_g2o_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def manhattan_problem():
+    """BASELINE.json configs[0]: the in-tree manhattanOlson3500 graph as parsed into tests/golden (the GPU box has no
+    /root/reference)"""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "manhattan3500.npz"), allow_pickle=False)
+    return dict(kind="se2", vertex_kind=0, edge_kind=0, vertex_ids=fx["v_ids"], vertex_payload=fx["v_pay"],
+                edge_v0=fx["e_a"], edge_v1=fx["e_b"], edge_payload=fx["e_pay"])
+
+
+def feed(synth, prob, target):
+    if prob["kind"] == "se2":
+        target.add_vertices(0, prob["vertex_ids"], prob["vertex_payload"])
+        target.add_edges(0, prob["edge_v0"], prob["edge_v1"], prob["edge_payload"])
+    else:
+        synth.feed(prob, target)
+
+
+def make_problem(synth, workload):
     if workload == "venice":
         return synth.venice_like(), "Venice-shaped BA (types_sba): 871 cameras / 530304 points / ~2.0M P2MC edges, seed 871"
     if workload == "ba10k":  # BASELINE.json configs[3] shape (one GPU here; shards by landmark under torchrun)
         return synth.venice_like(10000, 2000000, seed=10000, fixed_obs=10), "synthetic BA: 10000 cameras / 2000000 points / 20.0M P2MC edges (k = 10), seed 10000"
     if workload == "sphere40k":  # reduced BASELINE.json configs[4]: same generator, 200 x 200 instead of 1000 x 1000
         return synth.sphere(200, 200, seed=40000), "SE3 pose graph: sphere generator 200 x 200 = 40000 poses / 159399 edges, seed 40000"
+    if workload == "sphere1m":   # BASELINE.json configs[4] at full size
+        return synth.sphere(1000, 1000, seed=1000000), "SE3 pose graph: sphere generator 1000 x 1000 = 1000000 poses / 3995999 edges, seed 1000000"
     if workload == "venice_small":
         return synth.venice_like(100, 20000, seed=7), "small BA: 100 cameras / 20000 points"
+    if workload == "manhattan":
+        return manhattan_problem(), "manhattanOlson3500 (data/2d): 3500 SE2 poses / 5598 edges, Gauss-Newton"
     return synth.sphere(), "sphere2500 SE3 pose graph: 2500 poses / 9799 edges (create_sphere.cpp defaults), seed 2500"
+
+
+def algorithm_of(workload):
+    return GN if workload == "manhattan" else LM
+
+
+def oracle_iterations(workload):
+    """bounded oracle sample per workload (iterations incl. iteration 0); 0 = the reference cannot run it"""
+    return {"ba10k": 2, "sphere40k": 3, "sphere1m": 0}.get(workload, RESTART)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -67,11 +113,12 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.samples, self.proc, self.index = [], None, index
+        self.mark = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -80,13 +127,24 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout=5.0):
+        """the poller needs about a second to deliver its first line: the timed region starts after it"""
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def begin_region(self):
+        self.mark = len(self.samples)
+
     def stop(self):
         if self.proc:
+            time.sleep(0.12)  # one more sample after the region
             self.proc.terminate()
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        region = self.samples[max(self.mark - 1, 0):]
+        sm = [float(s[0]) for s in region if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in region if len(s) > 1 and s[1].replace(".", "").isdigit()]
         reasons = set()
-        for s in self.samples:
+        for s in region:
             if len(s) >= 8:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
                     if v.lower().startswith("active"):
@@ -95,73 +153,104 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
+# ------------------------------------------------------------------------------------------------ oracle (checker / CPU arm)
+def oracle_run(synth, prob, workload, iters, restarts=1, budget_s=1e9):
+    """`restarts` optimisation runs of `iters` iterations each on the oracle, one iteration per call, timed.
+    Returns per-iteration chi2 / lambda / LM trials of the first run, the wall time of every iteration and the oracle."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import Oracle, OracleStats
+    algo = algorithm_of(workload)
+    out = dict(chi2=[], lam=[], lev=[], times=[], iteration0_s=[])
+    t_all = time.time()
+    o = None
+    for r in range(restarts):
+        o = Oracle()
+        feed(synth, prob, o)
+        o.setup_cli(True)
+        o.initialize_optimization()
+        L = o.L
+        L.oracle_iteration.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        for it in range(iters):
+            s = OracleStats()
+            L.oracle_iteration(o.g, algo, it, C.byref(s))
+            dt = s.time_iteration   # the solve() call alone, like G2OBatchStatistics::timeIteration
+            if it == 0:
+                out["iteration0_s"].append(dt)   # carries buildStructure + symbolic analysis
+            else:
+                out["times"].append(dt)
+            if r == 0:
+                out["chi2"].append(s.chi2); out["lam"].append(s.lambda_); out["lev"].append(s.levenberg_iterations)
+        if time.time() - t_all > budget_s:
+            break
+    out["oracle"] = o
+    return out
+
+
 def run_reference(args, rank):
     """The reference's own CPU implementation of the path: the oracle port (Eigen-free restatement of
     SparseOptimizer/BlockSolver/LM) linked against the reference's vendored CSparse compiled in oracle/_ref.
-    Single thread: the reference builds with OpenMP OFF (CMakeLists.txt:137) and CSparse is sequential."""
+    Single thread: the reference builds with OpenMP OFF (CMakeLists.txt:137) and CSparse is sequential.
+    Same protocol as the B200 arm: optimisation runs of RESTART iterations from the initial estimates; iteration 0 of
+    every run additionally carries buildStructure + the symbolic analysis (the B200 arm keeps its structure across
+    restarts), so it is counted as warm-up and the timed steps are iterations 1..RESTART-1 of each run."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_binding import LM, Oracle
-    from openslam_g2o_b200 import synth
-    prob, desc = make_problem(args.workload)
-    o = Oracle()
-    synth.feed(prob, o)
-    o.setup_cli(True)
-    o.initialize_optimization()
-    total = args.warmup + args.steps
-    budget_s = 150.0
-    t_all = time.time()
-    n, st = o.optimize(LM, 1)  # iteration 0: structure + symbolic (not timed)
-    times, done = [], 1
-    L = o.L
-    import ctypes as C
-    from oracle_binding import OracleStats
-    # continue the same optimisation one LM iteration at a time (iteration index > 0: no re-analysis)
-    L.oracle_lm_iteration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-    while done < total + 1 and (time.time() - t_all) < budget_s:
-        s = OracleStats()
-        t0 = time.perf_counter()
-        L.oracle_lm_iteration(o.g, done, C.byref(s))
-        times.append(time.perf_counter() - t0)
-        done += 1
+    synth = load_synth()
+    prob, desc = make_problem(synth, args.workload)
+    want = args.warmup + args.steps
+    iters = RESTART if oracle_iterations(args.workload) else 0
+    if iters == 0:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference's CSparse path indexes the factor with 32-bit ints: nnz(L) of this graph exceeds 2^31"}))
+        return
+    per_run = iters - 1
+    restarts = max(1, -(-want // per_run))
+    res = oracle_run(synth, prob, args.workload, iters, restarts=restarts, budget_s=150.0)
+    times = res["times"]
     timed = times[min(args.warmup, max(len(times) - 1, 0)):] or times
     ms = 1e3 * float(np.mean(timed))
     value = 1e3 / ms
-    sample = "%d LM iterations of the same input after %d warm-up (iteration 0 = structure+symbolic excluded)" % (len(timed), len(times) - len(timed))
+    sample = "%d iterations (iterations 1..%d of %d successive %d-iteration runs from the initial estimates; iteration 0 of each " \
+             "run = structure + symbolic analysis, %.2f s, excluded) after %d warm-up" % (
+                 len(timed), per_run, len(res["iteration0_s"]), iters, float(np.mean(res["iteration0_s"])), len(times) - len(timed))
     print(json.dumps({
         "impl": "reference", "metric": "LM iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
         "steps": len(timed), "warmup": len(times) - len(timed), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "solver": "lm_fix6_3 (CSparse flavour, block AMD)"},
+        "config": {"workload": desc, "solver": "%s_fix%s (CSparse flavour, block AMD)" % ("gn" if algorithm_of(args.workload) == GN else "lm", "3_2" if args.workload == "manhattan" else "6_3"),
+                   "restart_every": RESTART},
+        "chi2_first_run": res["chi2"],
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port", "sample": sample,
-                         "note": "oracle restatement of g2o's LM/BlockSolver + the reference's vendored CSparse compiled from /root/reference (oracle/_ref)"},
+                         "host_cores_available": os.cpu_count(),
+                         "note": "oracle restatement of g2o's LM/BlockSolver + the reference's vendored CSparse compiled from /root/reference (oracle/_ref); "
+                                 "not the CHOLMOD flavour (SuiteSparse and Eigen are absent from this image and from the GPU box: profiles/r02_box_probe.txt)"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def algorithmic_bytes(workload, dims, info, n_hs, n_edges):
-    """per-launch algorithmic bytes of the candidate dominant kernels, read-once/write-once"""
-    if workload.startswith("venice") or workload == "ba10k":
-        nl = dims["numLandmarks"]
-        n_hpl, n_seg, n_contrib = info["hpl_slots"], info["schur_segments"], info["schur_contributions"]
+def algorithmic_bytes(prob_kind, dims, info, n_hs, n_edges):
+    """per-launch ALGORITHMIC bytes of the HBM-bound kernels, exactly SURVEY.md section 8d (read-once / write-once model,
+    f64 = 8 B, int = 4 B); plan indices, padding and partial sums are traffic, not algorithm"""
+    if prob_kind.startswith("ba"):
+        nl, n_hpl = dims["numLandmarks"], info["hpl_slots"]
         return {
-            # ba_linearize_points: per edge cam idx 4 + meas 16 + info 24 + slot 4 + flag 1, write Hpl 144;
-            # per landmark est 32 + eptr 4 + order 4 + vertex 4, write Hll 72 + b 24
-            "linearize": n_edges * (49 + 144) + nl * 140,
-            # schur_range: read every Hpl block once 144 + Wu 80 per landmark + 6 B per contribution index + 12 B per
-            # segment descriptor; write one 36(+6)-double partial sum per segment
-            "schur": n_hpl * 144 + nl * 84 + n_contrib * 6 + n_seg * (12 + 42 * 8),
-            # ba_backsub: read Hpl 144 + slot/pose idx 8 per edge, Dinv 80 + b 24 + eptr/order 8 per landmark, write x 24
-            "backsub": n_hpl * 144 + n_edges * 8 + nl * 136,
+            # P2MC edge: ids 8 + measurement 16 read, Hpl block 144 written; per point: estimate 24 read, Hll 72 + b_l 24 written
+            "linearize": n_edges * 168 + nl * 120,
+            # Schur, per landmark with k observations: 144 k + Hll 72 + b_l 24 read, Dinv 72 written (that part belongs to
+            # schur_landmark_inverse); schur_range reads every Hpl block once + the landmark's transformed 3x3 (+u): 80 B,
+            # and Hschur is written once: 288 B per block
+            "schur": n_hpl * 144 + nl * 80 + n_hs * 288,
+            # back-substitution: Hpl 144 B per block + Dinv 72 + b_l 24 per point read, x_l 24 written
+            "backsub": n_hpl * 144 + nl * 120,
         }
-    # pose graph: pg_linearize reads ids 8 + Zinv 96 + info 168 + 2 poses 192, writes the 120-double staging record
-    return {"linearize": n_edges * (8 + 96 + 168 + 192 + 960)}
+    if prob_kind == "se2":   # SE2 edge: ids 8 + meas 24 + information 48 + 2 poses 48 read; 72-byte off-diagonal block written
+        return {"linearize": n_edges * (128 + 72) + dims["numPoses"] * 96}
+    # SE3 edge: ids 8 + measurement 56 + information 168 + 2 poses 192 = 424 B read, 288 B block written; + 336 B per vertex
+    return {"linearize": n_edges * 712 + dims["numPoses"] * 336}
 
 
-KERNEL_OF = {"linearize": {"ba": "ba_linearize_points_kernel", "pg": "pg_linearize_kernel<SE3>"},
+KERNEL_OF = {"linearize": {"ba": "ba_linearize_points_kernel", "pg": "pg_linearize_kernel"},
              "schur": {"ba": "schur_range_kernel"}, "backsub": {"ba": "ba_backsub_kernel"}}
 
 
@@ -174,117 +263,222 @@ def ncu_traffic(kernel):
         return None
 
 
-def run_b200(args, rank, world):
-    import torch
-    import torch.distributed as dist
-    import openslam_g2o_b200 as g
-    from openslam_g2o_b200 import synth
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    prob, desc = make_problem(args.workload)
-    sharded = world > 1 and prob["kind"] == "ba"
-    opt = g.SparseOptimizer(device=local_rank, shard=rank if sharded else 0, num_shards=world if sharded else 1)
-    opt.set_algorithm("lm_fix6_3")
-    synth.feed(prob, opt)
-    opt.setup_cli()
-    opt.initialize_optimization()
-    opt._ensure_uploaded()
-    ctx = opt.context
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-    if sharded:
-        from openslam_g2o_b200.distributed import make_allreduce
-        ctx.set_allreduce(make_allreduce(ctx, local_rank), rank, world)
-    if args.nd_levels:
-        ctx.set_ordering(args.nd_levels)
-    t_struct = time.perf_counter()
-    assert ctx.build_structure()
-    t_struct = time.perf_counter() - t_struct  # iteration-0 cost, reported beside the steady-state metric
-    dims = ctx.dims()
-    kinds = [g.VERTEX_CAM, g.VERTEX_XYZ] if prob["kind"] == "ba" else [g.VERTEX_SE3]
-    # initial estimates in pinned host memory (source of the e2e H2D copies, destination of the D2H reads)
-    init, host = {}, {}
-    nverts = {}
-    for kd in kinds:
-        n = _vertex_count(ctx, kd, prob, sharded, opt)
-        nverts[kd] = n
-        a = ctx.estimates(kd, n)
-        init[kd] = torch.from_numpy(a.copy()).pin_memory()
-        host[kd] = torch.empty_like(init[kd]).pin_memory()
+def fp64_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+        return float(d["dgemm_8192_sustained_tflops"]), "profiles/fp64_peak.json: cuBLAS DGEMM 8192^3 measured on this pool's B200 (sustained; tcgen05 has no FP64 kind, the FP64 tensor and vector rates are equal)"
+    except Exception:
+        return 37.2, "fallback: 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (no measured DGEMM figure found)"
 
-    def restart():
-        for kd in kinds:
-            ctx.set_estimates(kd, init[kd].numpy())
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        ctx.synchronize()
-        torch.cuda.synchronize()
+class Job:
+    """one workload on this rank: optimizer, context, pinned host mirrors of the estimates"""
 
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda") if args.workload == "sphere2500" else None  # others exceed L2
-    state = {"it": 0}
+    def __init__(self, args, workload, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        import openslam_g2o_b200 as g
+        from openslam_g2o_b200 import synth
+        self.g, self.torch, self.dist, self.synth = g, torch, dist, synth
+        self.workload, self.rank, self.world, self.local_rank = workload, rank, world, local_rank
+        self.algo = algorithm_of(workload)
+        self.prob, self.desc = make_problem(synth, workload)
+        self.sharded = world > 1 and self.prob["kind"] == "ba"
+        opt = g.SparseOptimizer(device=local_rank, shard=rank if self.sharded else 0, num_shards=world if self.sharded else 1)
+        opt.set_algorithm("gn_fix3_2" if self.algo == GN else "lm_fix6_3")
+        feed(synth, self.prob, opt)
+        opt.setup_cli()
+        opt.initialize_optimization()
+        opt._ensure_uploaded()
+        self.opt, self.ctx = opt, opt.context
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", local_rank))
+        if self.sharded:
+            from openslam_g2o_b200.distributed import init_native_comm
+            init_native_comm(self.ctx, rank, world)
+        if args.nd_levels:
+            self.ctx.set_ordering(args.nd_levels)
+        t = time.perf_counter()
+        assert self.ctx.build_structure()
+        self.t_struct = time.perf_counter() - t  # iteration-0 cost, reported beside the steady-state metric (SURVEY 8d)
+        self.dims = self.ctx.dims()
+        kind = self.prob["kind"]
+        self.kinds = [g.VERTEX_CAM, g.VERTEX_XYZ] if kind == "ba" else [g.VERTEX_SE2] if kind == "se2" else [g.VERTEX_SE3]
+        self.init, self.host = {}, {}
+        for kd in self.kinds:
+            n = self._vertex_count(kd)
+            a = self.ctx.estimates(kd, n)
+            self.init[kd] = torch.from_numpy(a.copy()).pin_memory()
+            self.host[kd] = torch.empty_like(self.init[kd]).pin_memory()
+        # pose graphs smaller than the 126 MB L2 are flushed between steps; the others exceed it
+        small = workload in ("sphere2500", "manhattan", "venice_small")
+        self.flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda") if small else None
+        self.it = 0
 
-    def step(e2e):
-        it = state["it"] % RESTART
+    def _vertex_count(self, kind):
+        g = self.g
+        if kind == g.VERTEX_CAM:
+            return len(self.prob["cam_ids"])
+        if kind in (g.VERTEX_SE3, g.VERTEX_SE2):
+            return len(self.prob["vertex_ids"])
+        return self.dims["numVertices"] - len(self.prob["cam_ids"])  # landmarks handed to this rank
+
+    def restart(self):
+        for kd in self.kinds:
+            self.ctx.set_estimates(kd, self.init[kd].numpy())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.ctx.synchronize()
+        self.torch.cuda.synchronize()
+
+    def step(self, e2e):
+        torch, ctx = self.torch, self.ctx
+        it = self.it % RESTART
         if it == 0:
-            restart()
-        if flush is not None:
-            flush.zero_()
+            self.restart()
+        if self.flush is not None:
+            self.flush.zero_()
             torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
+        ev0.record(self.stream)
         if e2e:
-            for kd in kinds:
-                ctx.set_estimates(kd, init[kd].numpy() if it == 0 else host[kd].numpy())
-        rc, st = ctx.algorithm_solve(g.LEVENBERG, it)
+            for kd in self.kinds:
+                ctx.set_estimates(kd, self.init[kd].numpy() if it == 0 else self.host[kd].numpy())
+        rc, st = ctx.algorithm_solve(self.algo, it)
         if e2e:
-            for kd in kinds:
-                ctx.get_estimates_into(kd, host[kd].numpy())
-        ev1.record(stream)
+            for kd in self.kinds:
+                ctx.get_estimates_into(kd, self.host[kd].numpy())
+        ev1.record(self.stream)
         ev1.synchronize()
-        state["it"] += 1
+        self.it += 1
         return ev0.elapsed_time(ev1), st
 
-    def timed_run(e2e, steps, warmup):
-        state["it"] = 0
+    def timed_run(self, e2e, steps, warmup, sampler=None):
+        torch = self.torch
+        self.it = 0
         for _ in range(warmup):
-            step(e2e)
-        # keep the restart phase of the timed region aligned with a fresh optimisation run
-        barrier()
-        t = 0.0
-        trials = 0
+            self.step(e2e)
+        self.barrier()  # the warm-up count is a multiple of nothing in particular: the restart phase just continues
+        if sampler:
+            sampler.begin_region()
+        t, trials = 0.0, 0
         wall0 = time.perf_counter()
         for _ in range(steps):
-            ms, st = step(e2e)
+            ms, st = self.step(e2e)
             t += ms
-            trials += st.levenberg_iterations
-        barrier()
+            trials += max(st.levenberg_iterations, 1)
+        self.barrier()
         wall = time.perf_counter() - wall0
         tt = torch.tensor([t], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if self.world > 1:
+            self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
         return float(tt.item()), trials, wall
 
-    sampler = ClockSampler(local_rank)
-    launches0 = ctx.launch_count()
-    if rank == 0:
+    def first_run(self, iters):
+        """iterations 0..iters-1 from the initial estimates: chi2 / lambda / LM trials + the final state (the parity
+        sample; doubles as warm-up of the CUDA graphs)"""
+        self.restart()
+        chi, lam, lev = [], [], []
+        for it in range(iters):
+            rc, st = self.ctx.algorithm_solve(self.algo, it)
+            if self.algo == GN:
+                chi.append(self.ctx.compute_active_errors())
+            else:
+                chi.append(st.chi2)
+            lam.append(st.lambda_); lev.append(st.levenberg_iterations)
+        self.ctx.synchronize()
+        return dict(chi2=chi, lam=lam, lev=lev)
+
+    def close(self):
+        self.flush = None
+        self.opt.close()
+        self.torch.cuda.empty_cache()
+
+
+def parity_block(job, mine, ora):
+    """GPU trajectory of this process vs the oracle's on the same arrays (tolerance of the path: 1e-6 relative)"""
+    g, o = job.g, ora["oracle"]
+    k = min(len(mine["chi2"]), len(ora["chi2"]))
+    cg, co = np.array(mine["chi2"][:k]), np.array(ora["chi2"][:k])
+    out = {"iterations": k, "chi2_rel": float(np.max(np.abs(cg - co) / np.abs(co))), "chi2_final": float(cg[-1]),
+           "chi2_final_oracle": float(co[-1]), "tolerance": 1e-6}
+    if job.algo == LM:
+        out["lambda_rel"] = float(np.max(np.abs(np.array(mine["lam"][:k]) - np.array(ora["lam"][:k])) / np.abs(ora["lam"][:k])))
+        out["lm_trials_equal"] = list(mine["lev"][:k]) == list(ora["lev"][:k])
+    out["ordering_bit_exact"] = bool(np.array_equal(job.ctx.block_ordering(), o.block_perm()))
+    # final state: every pose + a sample of the landmarks this rank owns
+    job.opt.sync_estimates()
+    ids, kinds, _, _ = o.vertices()
+    pose_ids = [int(i) for i, kd in zip(ids, kinds) if kd != 3]
+    pt_ids = [int(i) for i, kd in zip(ids, kinds) if kd == 3][::16]
+    worst = 0.0
+    for group, is_pt in ((pose_ids[:: max(1, len(pose_ids) // 20000)], False), (pt_ids, True)):
+        if not group:
+            continue
+        eg = np.stack([np.pad(job.opt.vertex_estimate(i), (0, 12))[:12] for i in group])
+        eo = np.stack([np.pad(o.vertex_estimate(i), (0, 12))[:12] for i in group])
+        if is_pt and job.sharded:   # landmarks of other shards keep their initial host estimate on this rank
+            init = {int(i): p for i, p in zip(job.prob["point_ids"], job.prob["point_payload"])}
+            own = np.array([not np.array_equal(e[:3], init[i][:3]) for e, i in zip(eg, group)])
+            eg, eo = eg[own], eo[own]
+        if len(eg):
+            worst = max(worst, float(np.abs(eg - eo).max() / max(np.abs(eo).max(), 1e-300)))
+    out["state_rel"] = worst
+    out["ok"] = bool(out["chi2_rel"] < 1e-6 and out["state_rel"] < 1e-6 and out["ordering_bit_exact"])
+    return out
+
+
+def measure(args, workload, rank, world, local_rank, steps, warmup, full):
+    """one workload: parity sample, value, e2e, roofline; `full` adds the clock sampler, the nested-dissection extra and
+    the long oracle sample"""
+    job = Job(args, workload, rank, world, local_rank)
+    ctx, prob = job.ctx, job.prob
+    n_or = 0 if args.no_cpu_baseline else oracle_iterations(workload)
+    if not full and workload == "ba10k" and world > 1:
+        n_or = 0  # config 4 under torchrun: the chi2 trajectory is printed, the oracle sample is in the N = 1 line
+    k_first = n_or if n_or else min(RESTART, 3 if workload in ("ba10k", "sphere1m", "sphere40k") else RESTART)
+    mine = job.first_run(k_first)
+    parity = cpu = None
+    if rank == 0 and n_or:
+        try:
+            ora = oracle_run(job.synth, prob, workload, n_or)
+            parity = parity_block(job, mine, ora)
+            t = ora["times"]
+            cpu = {"value": 1.0 / float(np.mean(t)), "unit": "iterations/s", "cores": 1, "kind": "port",
+                   "ms_per_iteration": 1e3 * float(np.mean(t)), "iteration0_s": ora["iteration0_s"][0],
+                   "sample": "iterations 1..%d of the same input (iteration 0 = structure + symbolic analysis excluded)" % (n_or - 1),
+                   "host_cores_available": os.cpu_count(),
+                   "note": "oracle = restatement of g2o's LM + BlockSolver linked to the reference's vendored CSparse (oracle/_ref); "
+                           "single thread like the reference's default build (OpenMP OFF)"}
+            ora.pop("oracle")
+        except Exception as e:  # oracle missing or failed: say so, keep the measurement
+            parity = {"unavailable": repr(e)}
+    elif rank == 0 and not args.no_cpu_baseline and oracle_iterations(workload) == 0:
+        parity = {"unavailable": "the reference's CSparse/CHOLMOD-int path indexes nnz(L) with 32-bit ints; this graph's factor has more than 2^31 entries"}
+    if world > 1:
+        job.dist.barrier()
+
+    sampler = ClockSampler(local_rank) if (full and rank == 0) else None
+    if sampler:
         sampler.start()
-    ms_total, trials, wall = timed_run(False, args.steps, max(args.warmup, 3))
+        sampler.wait_first()
+    launches0 = ctx.launch_count()
+    ms_total, trials, wall = job.timed_run(False, steps, max(warmup, 3), sampler)
     launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, _ = timed_run(True, args.steps, 3)
-    value = args.steps / (ms_total * 1e-3)
-    e2e_value = args.steps / (ms_e2e * 1e-3)
-    h2d = sum(int(init[kd].numel()) * 8 for kd in kinds)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, _ = job.timed_run(True, steps, 3)
+    value = steps / (ms_total * 1e-3)
+    e2e_value = steps / (ms_e2e * 1e-3)
+    h2d = sum(int(job.init[kd].numel()) * 8 for kd in job.kinds)
     d2h = h2d + 8
 
-    # ---- roofline of the dominant kernel, CUDA events on the launching stream inside this process
+    # ---- per-kernel-group CUDA events inside this process (profiling pass: individual launches, graphs off)
     ctx.set_profiling(True)
-    state["it"] = 0
-    for _ in range(RESTART):
-        step(False)
+    job.it = 0
+    nprof = RESTART if workload not in ("sphere1m",) else 2
+    for _ in range(nprof):
+        job.step(False)
     phases = ctx.phase_times()
     ctx.set_profiling(False)
     info = ctx.factor_info()
@@ -293,73 +487,83 @@ def run_b200(args, rank, world):
     if rank == 0:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         peak = peaks.get("hbm_gbs", 6650.0)
-        n_hs = lib_blocks(ctx, 3) if prob["kind"] == "ba" else 0
-        ab = algorithmic_bytes(args.workload, dims, info, n_hs, dims["numEdges"])
-        cand = {k: phases[k] for k in ab if phases.get(k, (0, 0))[1] > 0}
-        dom = max(cand, key=lambda k: cand[k][0])
-        sec = cand[dom][0] / cand[dom][1]
-        achieved = ab[dom] / sec / 1e9
-        kname = KERNEL_OF[dom]["ba" if prob["kind"] == "ba" else "pg"]
-        roof = {"bound": "hbm", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": sec * 1e3, "traffic": ncu_traffic(kname),
-                "others": {KERNEL_OF[k]["ba" if prob["kind"] == "ba" else "pg"]:
-                           {"frac": ab[k] / (cand[k][0] / cand[k][1]) / 1e9 / peak, "avg_launch_ms": 1e3 * cand[k][0] / cand[k][1]}
-                           for k in cand if k != dom}}
+        kind = "ba" if prob["kind"].startswith("ba") else "pg"
+        n_hs = lib_blocks(ctx, 3) if kind == "ba" else 0
+        ab = algorithmic_bytes(prob["kind"], job.dims, info, n_hs, job.dims["numEdges"])
+        hbm = {}
+        for k2 in ab:
+            if phases.get(k2, (0, 0))[1] > 0:
+                sec = phases[k2][0] / phases[k2][1]
+                name = KERNEL_OF[k2][kind]
+                hbm[name] = {"achieved": ab[k2] / sec / 1e9, "frac": ab[k2] / sec / 1e9 / peak, "avg_launch_ms": 1e3 * sec,
+                             "algorithmic_bytes_per_launch": ab[k2], "traffic": ncu_traffic(name)}
+        step_s = ms_total * 1e-3 / steps
+        fkeys = [k2 for k2 in ("chol_chain", "chol_factor_flow") if phases.get(k2, (0, 0))[1] > 0]
+        f_s = sum(phases[k2][0] / phases[k2][1] for k2 in fkeys)
+        tpeak, tsrc = fp64_peak()
+        factor_entry = None
+        if f_s > 0:
+            factor_entry = {"bound": "tensor", "kernel": "+".join("%s_kernel" % k2 for k2 in fkeys),
+                            "achieved": info["factor_flops"] / f_s / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                            "frac": info["factor_flops"] / f_s / 1e12 / tpeak, "traffic": ncu_traffic("chol_factor_flow_kernel"),
+                            "avg_launch_ms": 1e3 * f_s, "share_of_step": f_s / step_s, "flops_per_launch": info["factor_flops"],
+                            "peak_source": tsrc,
+                            "note": "FP64 pipe (DFMA) of the sparse supernodal factorisation; on these graphs the kernel is bound by the "
+                                    "latency of the elimination-tree dependency chain (levels: %d), not by the pipe" % info["levels"]}
+        best_hbm = max(hbm, key=lambda n: hbm[n]["avg_launch_ms"]) if hbm else None
+        if factor_entry and (best_hbm is None or factor_entry["avg_launch_ms"] >= hbm[best_hbm]["avg_launch_ms"]):
+            roof = dict(factor_entry)
+        elif best_hbm:
+            e = hbm[best_hbm]
+            roof = {"bound": "hbm", "kernel": best_hbm, "achieved": e["achieved"], "peak": peak, "unit": "GB/s", "frac": e["frac"],
+                    "traffic": e["traffic"], "avg_launch_ms": e["avg_launch_ms"], "share_of_step": e["avg_launch_ms"] * 1e-3 / step_s,
+                    "algorithmic_bytes_per_launch": e["algorithmic_bytes_per_launch"], "fp64_kernel": factor_entry}
+        if roof is not None:
+            roof["hbm_peak"] = peak
+            roof["hbm_peak_source"] = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"
+            roof["hbm_kernels"] = hbm
 
     # ---- the same workload with the optional ordering for parallelism (nested dissection on top of AMD): reported
     # beside the headline, which keeps the reference's AMD ordering
     nd = None
-    if not args.nd_levels and not args.no_parallel_ordering and args.workload in ND_LEVELS:
-        ctx.set_ordering(ND_LEVELS[args.workload])
+    if full and not args.nd_levels and not args.no_parallel_ordering and workload in ND_LEVELS:
+        ctx.set_ordering(ND_LEVELS[workload])
         assert ctx.build_structure()
-        restart()
-        ms_nd, _, _ = timed_run(False, args.steps, max(args.warmup, 3))
-        ms_nd_e2e, _, _ = timed_run(True, args.steps, 3)
+        job.restart()
+        ms_nd, _, _ = job.timed_run(False, steps, max(warmup, 3))
+        ms_nd_e2e, _, _ = job.timed_run(True, steps, 3)
         info_nd = ctx.factor_info()
-        nd = {"ordering": "nested dissection, 2^%d parts, AMD inside (b200_set_ordering)" % ND_LEVELS[args.workload],
-              "value": args.steps / (ms_nd * 1e-3), "ms_per_step": ms_nd / args.steps,
-              "e2e": args.steps / (ms_nd_e2e * 1e-3), "unit": "iterations/s",
+        nd = {"ordering": "nested dissection, 2^%d parts, AMD inside (b200_set_ordering)" % ND_LEVELS[workload],
+              "value": steps / (ms_nd * 1e-3), "ms_per_step": ms_nd / steps,
+              "e2e": steps / (ms_nd_e2e * 1e-3), "unit": "iterations/s",
               "levels": info_nd["levels"], "factor_doubles": info_nd["factor_doubles"]}
 
-    if rank == 0 and roof is not None and phases.get("chol_factor_flow", (0, 0))[1] > 0:
-        # the kernel that dominates the step by TIME is the sparse factorisation: neither HBM- nor FLOP-bound but
-        # bound by the latency of its dependency chain - reported for completeness
-        f_s = phases["chol_factor_flow"][0] / phases["chol_factor_flow"][1]
-        roof["dominant_by_time"] = {"kernel": "chol_factor_flow_kernel", "avg_launch_ms": 1e3 * f_s,
-                                    "share_of_step": f_s / (ms_total * 1e-3 / args.steps),
-                                    "bound": "latency of the elimination-tree dependency chain (levels: %d)" % info["levels"],
-                                    "fp64_flops_per_launch": info["factor_flops"],
-                                    "achieved_tflops": info["factor_flops"] / f_s / 1e12,
-                                    "fp64_peak_tflops_nominal": 40.0}
-
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.workload, prob)
-
+    res = None
     if rank == 0:
-        print(json.dumps({
-            "metric": "LM iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "solver": "lm_fix6_3_b200 (Schur + supernodal Cholesky)" if prob["kind"] == "ba" else "lm_fix6_3_b200 (supernodal Cholesky)",
+        ba = prob["kind"].startswith("ba")
+        res = {
+            "metric": "LM iterations/sec" if job.algo == LM else "GN iterations/sec", "value": value, "unit": "iterations/s",
+            "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_total / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic" if workload != "manhattan" else "in-tree dataset (tests/golden)",
+            "config": {"workload": job.desc,
+                       "solver": ("lm_fix6_3_b200 (Schur + supernodal Cholesky)" if ba else "gn_fix3_2_b200 (supernodal Cholesky)" if job.algo == GN else "lm_fix6_3_b200 (supernodal Cholesky)"),
                        "restart_every": RESTART, "lm_trials_in_timed_region": trials,
                        "ordering": "block AMD (reference)" if not args.nd_levels else "nested dissection, 2^%d parts, AMD inside" % args.nd_levels,
-                       "parallelism": ("landmark-sharded x%d, cameras replicated, NCCL all-reduce of Hschur per trial" % world) if sharded else ("replicas only" if world > 1 else "single GPU"),
-                       "l2": "flushed between steps (256 MiB memset, outside the step timers)" if flush is not None else "working set (Hpl + edge arrays, resp. the factor) larger than the 126 MB L2",
+                       "parallelism": ("landmark-sharded x%d, cameras replicated, 2 native ncclAllReduce per LM trial ([Hschur|bschur|chi2], 2 scalars) in the trial CUDA graph" % world) if job.sharded else ("replicas only" if world > 1 else "single GPU"),
+                       "l2": "flushed between steps (256 MiB memset, outside the step timers)" if job.flush is not None else "working set (Hpl + edge arrays, resp. the factor) larger than the 126 MB L2",
                        "timing": "sum of per-step CUDA-event intervals on the solver stream, max over ranks", "wall_s": wall},
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "kernel_groups_ms_per_%d_iterations" % RESTART: per_phase,
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "chi2_first_run": mine["chi2"],
+            "roofline": roof, "cpu_baseline": cpu,
+            "kernel_groups_ms_per_%d_iterations" % nprof: per_phase,
             "factor": info,
             "parallel_ordering": nd,
-            "iteration0": {"build_structure_s": t_struct, "what": "block patterns, ordering, symbolic factorisation, Schur and "
+            "iteration0": {"build_structure_s": job.t_struct, "what": "block patterns, ordering, symbolic factorisation, Schur and "
                            "Cholesky plans + their upload (host, once per graph)",
                            "cpu_port_iteration0_s": (cpu or {}).get("iteration0_s")},
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+        }
+    job.close()
+    return res
 
 
 def lib_blocks(ctx, which):
@@ -367,50 +571,47 @@ def lib_blocks(ctx, which):
     return int(g.lib.b200_get_blocks(ctx.handle, which, None, None, None))
 
 
-def _vertex_count(ctx, kind, prob, sharded, opt):
-    import openslam_g2o_b200 as g
-    if kind == g.VERTEX_CAM:
-        return len(prob["cam_ids"])
-    if kind == g.VERTEX_SE3:
-        return len(prob["vertex_ids"])
-    # landmarks handed to this rank
-    d = ctx.dims()
-    return d["numVertices"] - len(prob["cam_ids"])
+def slim(r):
+    """short form of a measurement for the `configs` section"""
+    if r is None:
+        return None
+    keep = ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "parity", "chi2_first_run", "cpu_baseline", "factor")
+    out = {k: r.get(k) for k in keep}
+    out["workload"] = r["config"]["workload"]
+    out["parallelism"] = r["config"]["parallelism"]
+    if r.get("roofline"):
+        rf = r["roofline"]
+        out["roofline"] = {k: rf.get(k) for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "avg_launch_ms", "share_of_step")}
+        out["roofline"]["hbm_kernels"] = {n: {"frac": e["frac"], "avg_launch_ms": e["avg_launch_ms"]} for n, e in rf.get("hbm_kernels", {}).items()}
+    return out
 
 
-def cpu_baseline(workload, prob):
-    """the oracle on a bounded sample of the same workload, on this box's host cores (1 thread: reference default)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    try:
-        import ctypes as C
-        from oracle_binding import LM, Oracle, OracleStats
-    except Exception as e:  # oracle missing
-        return {"value": None, "unit": "iterations/s", "cores": 1, "kind": "port", "sample": "unavailable: %s" % e}
-    from openslam_g2o_b200 import synth
-    o = Oracle()
-    synth.feed(prob, o)
-    o.setup_cli(True)
-    o.initialize_optimization()
-    t_it0 = time.perf_counter()
-    o.optimize(LM, 1)
-    t_it0 = time.perf_counter() - t_it0
-    o.L.oracle_lm_iteration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-    times = []
-    t_all = time.time()
-    it = 1
-    min_it = 2 if workload in ("ba10k", "sphere40k") else 4  # bounded sample: the big graphs take seconds per CPU iteration
-    while (it <= min_it or time.time() - t_all < 10.0) and time.time() - t_all < 40.0 and it < 40:
-        s = OracleStats()
-        t0 = time.perf_counter()
-        o.L.oracle_lm_iteration(o.g, it, C.byref(s))
-        times.append(time.perf_counter() - t0)
-        it += 1
-    ms = 1e3 * float(np.mean(times))
-    return {"value": 1e3 / ms, "unit": "iterations/s", "cores": 1, "kind": "port", "ms_per_iteration": ms, "iteration0_s": t_it0,
-            "sample": "LM iterations 1..%d of the same input (iteration 0 = structure + symbolic analysis excluded)" % (it - 1),
-            "host_cores_available": os.cpu_count(),
-            "note": "oracle = restatement of g2o's LM + BlockSolver linked to the reference's vendored CSparse (oracle/_ref); "
-                    "single thread like the reference's default build (OpenMP OFF)"}
+def run_b200(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    main_res = measure(args, args.workload, rank, world, local_rank, args.steps, args.warmup, full=True)
+    extras = {}
+    if args.workload == "venice" and not args.no_extras and not args.nd_levels:
+        # the other BASELINE.json configurations, short runs.  N > 1: only config 4 shards; pose graphs stay single-GPU
+        plan = [("config4_ba10k", "ba10k", 20)] if world > 1 else \
+               [("config1_manhattan_gn", "manhattan", 40), ("config2_sphere2500", "sphere2500", 40),
+                ("config4_ba10k", "ba10k", 20), ("config5_sphere1m", "sphere1m", 3)]
+        for key, wl, st in plan:
+            try:
+                extras[key] = slim(measure(args, wl, rank, world, local_rank, st, 3, full=False))
+            except Exception as e:  # the headline line must survive a failing extra
+                extras[key] = {"error": repr(e)}
+                if world > 1:
+                    raise
+    if rank == 0:
+        main_res["configs"] = extras or None
+        print(json.dumps(main_res))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

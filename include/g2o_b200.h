@@ -48,7 +48,11 @@ enum { B200_RESULT_TERMINATE = 2, B200_RESULT_OK = 1, B200_RESULT_FAIL = -1 };
 
 typedef struct b200_ctx b200_ctx;
 
-/* POD twin of G2OBatchStatistics (core/batch_stats.h:40-77); times in seconds (CUDA events / monotonic) */
+/* POD twin of G2OBatchStatistics (core/batch_stats.h:40-77); times in seconds.  time_iteration (monotonic clock) and
+ * time_symbolic (iteration 0) are always filled.  The per-phase fields (time_residuals, time_quadratic_form,
+ * time_schur, time_numeric, time_linear_solver, time_linear_solution, time_update: CUDA-event intervals on the solver
+ * stream, summed over the trials of the iteration) are filled while b200_set_profiling(ctx, 1) is on - `g2o -stats`
+ * mode: the iteration then runs as individual launches instead of CUDA-graph replays - and are 0 otherwise. */
 typedef struct b200_iter_stats {
   int32_t iteration;
   int32_t levenberg_iterations;
@@ -87,6 +91,17 @@ int b200_set_edges(b200_ctx* ctx, int kind, int n, const int32_t* vi, const int3
 /* landmark sharding: this context owns the landmarks / edges it was given; cameras are
  * replicated.  After the local Schur reduction [Hschur | bschur | scalars] is all-reduced through fn. */
 int b200_set_allreduce(b200_ctx* ctx, b200_allreduce_fn fn, void* user, int rank, int world_size);
+/* Native communicator for the sharded path (preferred over the callback): NCCL, bound at run time (dlopen of
+ * libnccl.so.2), one rank per context / GPU.  Rank 0 calls b200_comm_unique_id and ships the B200_COMM_ID_BYTES bytes
+ * to the other ranks over any out-of-band channel (MPI, a file, torch.distributed's store); every rank then calls
+ * b200_comm_init (collective: ncclCommInitRank on the context's device).  From then on each LM trial issues exactly
+ * two ncclAllReduce(ncclDouble, ncclSum) on the context's stream, captured in its CUDA graph: one over
+ * [Hschur | bschur | chi2 before the trial] and one over 2 doubles after the update (chi2, LM scale). */
+#define B200_COMM_ID_BYTES 128
+int b200_comm_unique_id(void* out, int capacity);
+int b200_comm_init(b200_ctx* ctx, const void* unique_id, int rank, int world_size);
+int b200_comm_destroy(b200_ctx* ctx);
+int b200_comm_version(void);   /* NCCL_VERSION_CODE of the bound library, 0 if none can be loaded */
 /* sharded BA: blocks (rows[i] <= cols[i]) that OTHER shards contribute to the reduced camera matrix, so that
  * every rank builds the identical Hschur pattern (core/block_solver.hpp:262-288 over the whole graph).
  * Call AFTER b200_set_vertices (which forgets the keys of the previous graph) and before b200_build_structure;
@@ -123,6 +138,12 @@ int b200_discard_top(b200_ctx* ctx);
  * core/optimization_algorithm_gauss_newton.cpp:50-93), whole iteration device-resident.
  * stats may be NULL, else room for max_iterations records.  returns #iterations done (0 on Fail), <0 error */
 int b200_optimize(b200_ctx* ctx, int algorithm, int max_iterations, b200_iter_stats* stats);
+/* SparseOptimizer::terminate() / setForceStopFlag (core/sparse_optimizer.h:189, apps/g2o_cli/g2o.cpp:89-99,552): the
+ * host's stop request, polled where the reference polls it - between the trials of one LM iteration
+ * (core/optimization_algorithm_levenberg.cpp:142) and between the iterations of b200_optimize
+ * (core/sparse_optimizer.cpp:376).  fn returns non-zero to stop; NULL removes the hook. */
+typedef int (*b200_terminate_fn)(void* user);
+int b200_set_terminate(b200_ctx* ctx, b200_terminate_fn fn, void* user);
 /* one OptimizationAlgorithm::solve(iteration).  returns B200_RESULT_OK (1), B200_RESULT_TERMINATE (2) or
  * B200_SOLVE_FAIL (3; stats->result = B200_RESULT_FAIL = -1 as in the reference's enum); < 0: hard error (nothing
  * was solved - missing structure, CUDA failure, out of memory), never an ordinary LM/GN outcome */

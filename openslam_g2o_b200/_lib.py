@@ -19,6 +19,7 @@ VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP = 0, 1, 2, 3, 
 EDGE_SE2, EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV = 0, 1, 2, 3
 NUM_VERTEX_KINDS, NUM_EDGE_KINDS = 5, 4
 GAUSS_NEWTON, LEVENBERG = 0, 1
+COMM_ID_BYTES = 128
 RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1   # values of IterStats.result (g2o's SolverResult)
 SOLVE_FAIL = 3                                        # return value of b200_algorithm_solve for a failed solve
 
@@ -38,6 +39,7 @@ class IterStats(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p)
+TERMINATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
 class B200Error(RuntimeError):
@@ -63,6 +65,10 @@ def _load():
         "b200_set_edges": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "b200_set_allreduce": (i32, [vp, ALLREDUCE_FN, vp, i32, i32]),
         "b200_add_schur_pattern": (i32, [vp, i32, vp, vp]),
+        "b200_comm_unique_id": (i32, [vp, i32]),
+        "b200_comm_init": (i32, [vp, vp, i32, i32]),
+        "b200_comm_destroy": (i32, [vp]),
+        "b200_comm_version": (i32, []),
         "b200_get_stream": (vp, [vp]),
         "b200_synchronize": (i32, [vp]),
         "b200_build_structure": (i32, [vp]),
@@ -78,6 +84,7 @@ def _load():
         "b200_optimize": (i32, [vp, i32, i32, vp]),
         "b200_algorithm_solve": (i32, [vp, i32, i32, vp]),
         "b200_set_lm_params": (i32, [vp, dbl, i32]),
+        "b200_set_terminate": (i32, [vp, TERMINATE_FN, vp]),
         "b200_get_dims": (i32, [vp, vp]),
         "b200_get_x": (i32, [vp, vp]),
         "b200_get_b": (i32, [vp, vp]),

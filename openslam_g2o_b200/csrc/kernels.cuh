@@ -476,9 +476,11 @@ __global__ void schur_landmark_inverse_kernel(int nl, const double* __restrict__
   o[8] = w02 * b0 + w12 * b1 + w22 * b2;
 }
 
-// S2: Hschur(i1,i2) = hpp_scale*(Hpp(i1,i2) + [i1==i2] lambda I) - sum_l (Hpl(i1,l) Dinv_l) Hpl(i2,l)^T
+// S2: Hschur(i1,i2) = hpp_scale*Hpp(i1,i2) + [i1==i2] lambda_scale*lambda I - sum_l (Hpl(i1,l) Dinv_l) Hpl(i2,l)^T
 //     bschur_i1     = hpp_scale*b_i1 - sum_l Hpl(i1,l) db_l                      (block_solver.hpp:397-439)
-// hpp_scale is 1 on a single GPU; with landmark sharding only rank 0 adds the (already reduced) Hpp term.
+// Both scales are 1 on a single GPU.  With landmark sharding every rank adds its PARTIAL Hpp / b_p (its own edges'
+// share of the camera blocks) and rank 0 alone the lambda term: the sum over the ranks - the one all-reduce of
+// [Hschur | bschur] - is the reduced system, no separate reduction of Hpp.
 //
 // Two kernels, no atomics, fixed summation order:
 //  schur_range_kernel   one CTA per RANGE of landmarks.  Hpl slots are numbered so that a range is one contiguous
@@ -665,8 +667,8 @@ __global__ void __launch_bounds__(256)
 schur_finish_kernel(int nT, const int* __restrict__ t_row, const int* __restrict__ t_col, const int* __restrict__ t_hpp,
                     const int* __restrict__ tseg_ptr, const int* __restrict__ tseg_idx,
                     const double* __restrict__ partial, const double* __restrict__ Hpp, const double* __restrict__ b_p,
-                    const double* __restrict__ lambda, double hpp_scale, double* __restrict__ Hschur,
-                    double* __restrict__ bschur) {
+                    const double* __restrict__ lambda, double hpp_scale, double lambda_scale,
+                    double* __restrict__ Hschur, double* __restrict__ bschur) {
   const int t = blockIdx.x * 4 + (threadIdx.x >> 6);
   const int e = threadIdx.x & 63;
   if (t >= nT || e >= kSrPartial) return;
@@ -687,7 +689,10 @@ schur_finish_kernel(int nT, const int* __restrict__ t_row, const int* __restrict
   if (e < 36) {
     const int hb = t_hpp[t];
     double base = 0.0;
-    if (hb >= 0 && hpp_scale != 0.0) base = hpp_scale * (Hpp[36ll * hb + e] + ((diag && e % 7 == 0) ? *lambda : 0.0));
+    // landmark-sharded: Hpp holds this rank's partial camera blocks (summed by the all-reduce of Hschur), lambda is
+    // added by rank 0 only (lambda_scale); single GPU: both scales are 1
+    if (hb >= 0) base = hpp_scale * Hpp[36ll * hb + e];
+    if (diag && e % 7 == 0) base += lambda_scale * *lambda;
     Hschur[36ll * t + e] = base - s0;
   } else {
     bschur[6ll * i1 + (e - 36)] = hpp_scale * b_p[6ll * i1 + (e - 36)] - s0;
@@ -841,6 +846,26 @@ __global__ void reduce_max_kernel(const double* __restrict__ partials, int n, do
     r *= scale;
     out[0] = accumulate ? fmax(out[0], r) : r;
   }
+}
+// partial maxima of |v[i]| (sharded lambda init: the reduced Hpp diagonal and the per-rank landmark maxima)
+__global__ void absmax_kernel(int n, const double* __restrict__ v, double* __restrict__ partials) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = idx < n ? fabs(v[idx]) : 0.0;
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  m = warp_max(m);
+  if (lane == 0) sh[wid] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) r = fmax(r, sh[i]);
+    partials[blockIdx.x] = r;
+  }
+}
+// sharded LM scale: the pose part is a partial sum too -> one slot for the all-reduce
+__global__ void fold_scale_kernel(double* __restrict__ scalars) {
+  scalars[1] += scalars[4];
+  scalars[4] = 0.0;
 }
 // gather the diagonal entries of the indexed vertices into a dense vector (host mirror for v->hessian(j,j))
 template <int D>

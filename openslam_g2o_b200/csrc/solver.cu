@@ -58,6 +58,8 @@ int fail(b200_ctx* c, int code, const std::string& msg) {
 }
 
 std::string g_create_error;
+#define NEED_DEVICE_(c) \
+  if ((c)->host_only) return fail((c), B200_ERR_NO_DEVICE, "host-only context: the B200 solve path has no CPU fallback")
 
 // ---- host math for the one-time ingest (same formulas as geometry.cuh; runs where the reference's read() runs)
 void host_se2_inverse(const double* z, double* zi) {
@@ -661,9 +663,18 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
   B200_CUDA(cudaGetLastError());
 }
 
+bool sharded(const b200_ctx* c) { return c->world > 1 && (c->nccl.active() || c->allreduce); }
+
+// in-place all-reduce (op 0 = sum, 1 = max) of device doubles, ordered on the solver stream: ncclAllReduce on the native
+// communicator (b200_comm_init), else the host-supplied callback (b200_set_allreduce)
 int allreduce_dev(b200_ctx* c, double* p, long long count, int op = 0) {
-  if (!c->allreduce || c->world <= 1) return 0;
+  if (!sharded(c)) return 0;
   PhaseTimer pt(c, PH_COLLECTIVE);
+  if (c->nccl.active()) {
+    const int rc = op == 0 ? c->nccl.allreduce_sum(p, count, c->stream, &c->err) : c->nccl.allreduce_max(p, count, c->stream, &c->err);
+    c->lc.n++;  // one NCCL kernel
+    return rc ? B200_ERR_COLLECTIVE : 0;
+  }
   int rc = c->allreduce(p, count, op, (void*)c->stream, c->allreduce_user);
   if (rc != 0) { c->err = "all-reduce callback failed"; return B200_ERR_COLLECTIVE; }
   return 0;
@@ -698,17 +709,41 @@ int enqueue_build_system(b200_ctx* c) {
     BA_MODEL_LAUNCH(c, ba_linearize_cams_kernel, <<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage)); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
-    int rc = allreduce_dev(c, c->d_Hpp.p, (long long)np * 36 + c->sizeP);  // sharded: partial camera blocks -> full
-    if (rc) return rc;
+    // sharded: Hpp and b_p stay this rank's PARTIAL sums (its own observations); they enter the reduced system through
+    // schur_finish_kernel and are summed by the one all-reduce of [Hschur | bschur] (enqueue_solve)
     B200_CUDA(cudaMemcpyAsync(c->d_b.p, b_p_stage, (size_t)c->sizeP * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
   B200_CUDA(cudaGetLastError());
   return 0;
 }
 
-void enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses and landmarks
+int enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses and landmarks
   cudaStream_t s = c->stream;
   const int np = c->np, nl = c->nl;
+  if (sharded(c) && c->schur) {
+    // landmark-sharded: the camera diagonal is a sum over the ranks, the landmark diagonals live on their owners.
+    // One sum all-reduce over [Hpp diagonal partial sums (6 np) | per-rank landmark maximum in slot `rank`], then the
+    // maximum of the reduced vector (iteration 0 only)
+    const int n = c->sizeP + c->world;
+    c->d_comm_diag.alloc((size_t)n);
+    B200_CUDA(cudaMemsetAsync(c->d_comm_diag.p, 0, (size_t)n * sizeof(double), s));
+    k::extract_diag_kernel<6><<<ceil_div((long long)np * 6, 256), 256, 0, s>>>(np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_comm_diag.p);
+    c->lc.n++;
+    if (nl > 0) {
+      const int nb = ceil_div((long long)nl * 3, 256);
+      k::max_diag_kernel<3><<<nb, 256, 0, s>>>(nl, nullptr, c->d_Hll.p, c->d_partials.p);
+      k::reduce_max_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, 1.0, c->d_comm_diag.p + c->sizeP + c->rank, 0);
+      c->lc.n += 2;
+    }
+    B200_CUDA(cudaGetLastError());
+    if (int rc = allreduce_dev(c, c->d_comm_diag.p, n)) return rc;
+    const int nb = ceil_div(n, 256);
+    k::absmax_kernel<<<nb, 256, 0, s>>>(n, c->d_comm_diag.p, c->d_partials.p);
+    k::reduce_max_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, 1.0, c->d_scalars.p + 2, 0);
+    c->lc.n += 2;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
   int nb = ceil_div((long long)np * c->pd, 256);
   if (c->pd == 3) k::max_diag_kernel<3><<<nb, 256, 0, s>>>(np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_partials.p);
   else k::max_diag_kernel<6><<<nb, 256, 0, s>>>(np, c->d_hpp_diag_block.p, c->d_Hpp.p, c->d_partials.p);
@@ -721,7 +756,7 @@ void enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses 
     c->lc.n += 2;
   }
   B200_CUDA(cudaGetLastError());
-  allreduce_dev(c, c->d_scalars.p + 2, 1, /*max*/ 1);  // sharded: landmark diagonals live on different ranks
+  return 0;
 }
 
 
@@ -740,7 +775,7 @@ int enqueue_solve(b200_ctx* c) {
       k::schur_landmark_inverse_kernel<<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_Hll.p, c->d_b.p + c->sizeP, d_lambda, c->d_Dinv.p, c->d_Wu.p);
       c->lc.n++;
     }
-    const double hpp_scale = (c->world > 1 && c->rank != 0) ? 0.0 : 1.0;
+    const double lambda_scale = (sharded(c) && c->rank != 0) ? 0.0 : 1.0;  // the lambda term enters the sum once
     {
       PhaseTimer pt(c, PH_SCHUR);
       if (c->sr_n > 0) {
@@ -753,12 +788,18 @@ int enqueue_solve(b200_ctx* c) {
     {
       PhaseTimer pt(c, PH_SCHUR_FINISH);
       k::schur_finish_kernel<<<ceil_div(c->n_hs, 4), 256, 0, s>>>(c->n_hs, c->d_t_row.p, c->d_t_col.p, c->d_t_hpp.p, c->d_tseg_ptr.p, c->d_tseg_idx.p,
-                                                               c->d_sr_partial.p, c->d_Hpp.p, c->d_b.p, d_lambda, hpp_scale, c->d_Hschur.p, bschur_ptr(c));
+                                                               c->d_sr_partial.p, c->d_Hpp.p, c->d_b.p, d_lambda, 1.0, lambda_scale, c->d_Hschur.p, bschur_ptr(c));
       c->lc.n++;
     }
     B200_CUDA(cudaGetLastError());
-    int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP);
-    if (rc) return rc;
+    if (sharded(c)) {
+      // THE collective of the trial: [Hschur | bschur | chi2 of the state before the trial] in one ncclAllReduce
+      double* tail = bschur_ptr(c) + c->sizeP;
+      B200_CUDA(cudaMemcpyAsync(tail, c->d_scalars.p + 7, sizeof(double), cudaMemcpyDeviceToDevice, s));
+      int rc = allreduce_dev(c, c->d_Hschur.p, (long long)c->n_hs * 36 + c->sizeP + 1);
+      if (rc) return rc;
+      B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 5, tail, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
   }
   { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, bschur_ptr(c), s, &c->lc, &c->prof); }
   { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc, &c->prof); }
@@ -800,7 +841,9 @@ void enqueue_scale(b200_ctx* c) {
   PhaseTimer pt(c, PH_SCALE);
   cudaStream_t s = c->stream;
   int nb = ceil_div(c->sizeP, 256);
-  k::lm_scale_kernel<<<nb, 256, 0, s>>>(c->sizeP, c->d_x.p, c->d_b.p, c->d_scalars.p + 3, c->d_partials.p);
+  // sharded: b_p is this rank's partial sum, so sum_j x_j b_j is partial as well; the lambda x_j^2 term is rank 0's
+  const double* pose_lambda = (sharded(c) && c->rank != 0) ? c->d_scalars.p + 6 /* constant 0 */ : c->d_scalars.p + 3;
+  k::lm_scale_kernel<<<nb, 256, 0, s>>>(c->sizeP, c->d_x.p, c->d_b.p, pose_lambda, c->d_partials.p);
   k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 4);
   c->lc.n += 2;
   if (c->sizeL > 0) {
@@ -811,6 +854,7 @@ void enqueue_scale(b200_ctx* c) {
   } else {
     B200_CUDA(cudaMemsetAsync(c->d_scalars.p + 1, 0, sizeof(double), s));
   }
+  if (sharded(c)) { k::fold_scale_kernel<<<1, 1, 0, s>>>(c->d_scalars.p); c->lc.n++; }  // [1] += [4]: one slot to reduce
   B200_CUDA(cudaGetLastError());
 }
 
@@ -829,14 +873,15 @@ void do_pop(b200_ctx* c) {
 
 // sharded runs: chi2 and the landmark part of the LM scale are partial sums -> one tiny all-reduce
 int reduce_trial_scalars(b200_ctx* c, int count = 1) {
-  if (!c->allreduce || c->world <= 1) return 0;
+  if (!sharded(c)) return 0;
   // [0] chi2 partial, [1] landmark part of the LM scale; the pose part (slot 4) is identical on every rank
   return allreduce_dev(c, c->d_scalars.p + 0, count);
 }
 
 
 // ---- CUDA graph replay of the launch-bound sequences (about 150-250 small kernels each)
-bool graphs_usable(b200_ctx* c) { return c->use_graphs && !c->prof.on && (c->world <= 1 || !c->allreduce); }
+// sharded: the native ncclAllReduce is captured like any kernel; the host callback cannot be
+bool graphs_usable(b200_ctx* c) { return c->use_graphs && !c->prof.on && (!sharded(c) || (c->nccl.active() && c->comm_warm)); }
 
 template <typename F>
 int run_captured(b200_ctx* c, cudaGraphExec_t* exec, long long* launches, F&& enqueue) {
@@ -869,14 +914,11 @@ int run_captured(b200_ctx* c, cudaGraphExec_t* exec, long long* launches, F&& en
 int run_prologue(b200_ctx* c) {
   auto body = [&]() -> int {
     enqueue_chi2(c);
+    // sharded: this rank's part of chi2 rides in the first trial's all-reduce (slot 7 -> tail of [Hschur | bschur])
+    if (sharded(c)) B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 7, c->d_scalars.p + 0, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return enqueue_build_system(c);
   };
-  if (!graphs_usable(c)) {
-    enqueue_chi2(c);
-    int rc = reduce_trial_scalars(c);
-    if (rc) return rc;
-    return enqueue_build_system(c);
-  }
+  if (!graphs_usable(c)) return body();
   return run_captured(c, &c->graph_prologue, &c->graph_prologue_launches, body);
 }
 
@@ -892,7 +934,9 @@ int run_trial(b200_ctx* c) {
     enqueue_update(c);
     enqueue_chi2(c);
     enqueue_scale(c);
-    return reduce_trial_scalars(c, 2);
+    rc = reduce_trial_scalars(c, 2);
+    if (!rc && sharded(c)) c->comm_warm = true;
+    return rc;
   }
   const int saved = c->num_oplus_calls;
   auto body = [&]() -> int {
@@ -902,7 +946,7 @@ int run_trial(b200_ctx* c) {
     enqueue_update(c);
     enqueue_chi2(c);
     enqueue_scale(c);
-    return 0;
+    return reduce_trial_scalars(c, 2);  // sharded: chi2 of the new state + LM scale, 2 doubles
   };
   int rc = run_captured(c, &c->graph_trial, &c->graph_trial_launches, body);
   c->num_oplus_calls = saved + 1;  // the captured enqueue_update only counts once
@@ -965,6 +1009,7 @@ void b200_destroy(b200_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->prof.destroy();
   drop_graphs(c);
+  c->nccl.destroy();
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_status) cudaFreeHost(c->h_status);
   cudaStream_t s = c->stream;
@@ -1008,6 +1053,32 @@ int b200_set_allreduce(b200_ctx* c, b200_allreduce_fn fn, void* user, int rank, 
   c->allreduce = fn; c->allreduce_user = user; c->rank = rank; c->world = world;
   return B200_OK;
 }
+
+int b200_comm_unique_id(void* out, int capacity) {
+  if (!out || capacity < B200_COMM_ID_BYTES) return B200_ERR_INVALID;
+  std::string err;
+  if (NcclComm::unique_id(out, &err)) { g_create_error = err; return B200_ERR_COLLECTIVE; }
+  return B200_OK;
+}
+int b200_comm_init(b200_ctx* c, const void* unique_id, int rank, int world) {
+  if (!c || !unique_id || world < 1 || rank < 0 || rank >= world) return B200_ERR_INVALID;
+  return guarded(c, [&]() -> int {
+    NEED_DEVICE_(c);
+    B200_CUDA(cudaSetDevice(c->device));
+    drop_graphs(c);
+    if (c->nccl.init(unique_id, rank, world, &c->err)) return B200_ERR_COLLECTIVE;
+    c->rank = rank; c->world = world; c->comm_warm = false;
+    return (int)B200_OK;
+  });
+}
+int b200_comm_destroy(b200_ctx* c) {
+  if (!c) return B200_ERR_INVALID;
+  if (!c->host_only) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); drop_graphs(c); }
+  c->nccl.destroy();
+  if (!c->allreduce) { c->rank = 0; c->world = 1; }
+  return B200_OK;
+}
+int b200_comm_version(void) { return NcclComm::version(); }
 
 int b200_add_schur_pattern(b200_ctx* c, int n, const int32_t* rows, const int32_t* cols) {
   if (!c || n < 0 || (n > 0 && (!rows || !cols))) return B200_ERR_INVALID;
@@ -1186,6 +1257,12 @@ int b200_set_robust_kernel(b200_ctx* c, int kind, double delta) {
   return B200_OK;
 }
 
+int b200_set_terminate(b200_ctx* c, b200_terminate_fn fn, void* user) {
+  if (!c) return B200_ERR_INVALID;
+  c->terminate = fn; c->terminate_user = user;
+  return B200_OK;
+}
+
 int b200_set_lm_params(b200_ctx* c, double user_lambda_init, int max_trials) {
   if (!c || max_trials < 1) return B200_ERR_INVALID;
   c->user_lambda_init = user_lambda_init;
@@ -1209,6 +1286,21 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
     }
     NEED_STRUCTURE(c);
     if (iteration == 0) st->time_symbolic = c->time_symbolic;
+    // G2OBatchStatistics phase fields (core/batch_stats.h:49-58) from the CUDA-event profiler, when it is on
+    double ph0[PH_COUNT];
+    if (c->prof.on) { c->prof.flush(); for (int i = 0; i < PH_COUNT; ++i) ph0[i] = c->prof.seconds[i]; }
+    auto fill_phase_stats = [&]() {
+      if (!c->prof.on) return;
+      c->prof.flush();
+      auto d = [&](int ph) { return c->prof.seconds[ph] - ph0[ph]; };
+      st->time_residuals = d(PH_ERRORS);                                             // computeActiveErrors (+ chi2)
+      st->time_quadratic_form = d(PH_LINEARIZE) + d(PH_LINEARIZE_CAMS) + d(PH_GATHER);  // buildSystem
+      st->time_schur = d(PH_SCHUR_INV) + d(PH_SCHUR) + d(PH_SCHUR_FINISH) + d(PH_COLLECTIVE);  // block_solver.hpp:370-441
+      st->time_numeric = d(PH_FACTOR);                                               // numeric decomposition (+ forward substitution)
+      st->time_linear_solution = d(PH_TRISOLVE);                                     // backward substitution
+      st->time_linear_solver = d(PH_FACTOR) + d(PH_TRISOLVE) + d(PH_BACKSUB);        // block_solver.hpp:445-486
+      st->time_update = d(PH_UPDATE);
+    };
     int rc = 0;
     if (algorithm == B200_GAUSS_NEWTON) {
       // core/optimization_algorithm_gauss_newton.cpp:50-93 (computeActiveErrors only caches edge errors there)
@@ -1218,14 +1310,17 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       enqueue_update(c);
       sync_scalars(c);
       st->result = *c->h_status ? B200_RESULT_FAIL : B200_RESULT_OK;
+      fill_phase_stats();
       st->time_iteration = wall() - t_start;
       return st->result == B200_RESULT_FAIL ? B200_SOLVE_FAIL : st->result;
     }
     // ---- Levenberg-Marquardt: core/optimization_algorithm_levenberg.cpp:57-147
+    const bool shard = sharded(c);
     if ((rc = run_prologue(c))) return rc;
-    if (iteration == 0) enqueue_max_diag(c);
-    sync_scalars(c);
-    double currentChi = c->h_scalars[0];
+    if (iteration == 0 && (rc = enqueue_max_diag(c))) return rc;
+    // sharded: chi2 of the current state is a partial sum here; the total arrives with the first trial's all-reduce
+    if (!shard || iteration == 0) sync_scalars(c);
+    double currentChi = shard ? 0.0 : c->h_scalars[0];
     double tempChi = currentChi;
     if (iteration == 0) {
       c->lambda = c->user_lambda_init > 0 ? c->user_lambda_init : 1e-5 * c->h_scalars[2];
@@ -1238,6 +1333,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       do_push(c);
       if ((rc = run_trial(c))) return rc;
       sync_scalars(c);
+      if (shard && qmax == 0) currentChi = c->h_scalars[5];
       const bool ok2 = *c->h_status == 0;
       tempChi = c->h_scalars[0];
       if (!ok2) tempChi = DBL_MAX;
@@ -1258,12 +1354,13 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
         do_pop(c);
       }
       qmax++;
-    } while (rho < 0 && qmax < c->max_trials_after_failure);
+    } while (rho < 0 && qmax < c->max_trials_after_failure && !(c->terminate && c->terminate(c->terminate_user)));
     c->last_chi2 = currentChi;
     st->chi2 = currentChi;
     st->lambda = c->lambda;
     st->levenberg_iterations = qmax;
     st->result = (qmax == c->max_trials_after_failure || rho == 0) ? B200_RESULT_TERMINATE : B200_RESULT_OK;
+    fill_phase_stats();
     st->time_iteration = wall() - t_start;
     return st->result;
   });
@@ -1275,7 +1372,7 @@ int b200_optimize(b200_ctx* c, int algorithm, int max_iterations, b200_iter_stat
   // factor here; the structure is a pure function of the graph handed over, so it is kept until the graph changes
   int done = 0, result = B200_RESULT_OK;
   bool ok = true;
-  for (int i = 0; i < max_iterations && ok; ++i) {
+  for (int i = 0; i < max_iterations && ok && !(c->terminate && c->terminate(c->terminate_user)); ++i) {
     b200_iter_stats local;
     b200_iter_stats* st = stats ? &stats[i] : &local;
     result = b200_algorithm_solve(c, algorithm, i, st);

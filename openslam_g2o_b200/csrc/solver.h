@@ -13,6 +13,7 @@
 #include "../../include/g2o_b200.h"
 #include "chol.h"
 #include "common.h"
+#include "nccl_comm.h"
 
 struct b200_ctx {
   int device = 0;
@@ -72,7 +73,9 @@ struct b200_ctx {
   int sr_n = 0, sr_nseg = 0, sr_cap_slots = 0, sr_cap_lms = 0, sr_cap_contrib = 0;
   long long sr_ncontrib = 0;
   g2o_b200::DevBuf<double> d_stage_est;            // dense staging for host<->device estimate copies
-  g2o_b200::DevBuf<double> d_partials, d_scalars;  // scalars: [0] chi2 [1] scale [2] maxdiag [3] lambda
+  // scalars: [0] chi2 [1] scale (landmark part; sharded: + pose part) [2] maxdiag [3] lambda [4] scale (pose part)
+  //          [5] sharded: chi2 before the trial, summed over the ranks [6] constant 0 [7] sharded: this rank's part of [5]
+  g2o_b200::DevBuf<double> d_partials, d_scalars;
   double* h_scalars = nullptr;                     // pinned mirror of d_scalars (+ status as double)
   int* h_status = nullptr;
   int backup_depth = 0;
@@ -90,15 +93,25 @@ struct b200_ctx {
   int num_oplus_calls = 0;
   double last_chi2 = 0.0;
 
-  // ---------------- sharding
-  b200_allreduce_fn allreduce = nullptr;
+  // ---------------- sharding (landmark shards, cameras replicated).  Two collectives per LM trial:
+  // ONE ncclAllReduce over [Hschur | bschur | chi2 of the state before the trial] (every rank contributes its partial
+  // Hpp / b_p inside Hschur / bschur, rank 0 the lambda term) and a 2-double one after the update (chi2 of the new
+  // state, LM scale); iteration 0 adds one over the Hpp diagonal for the initial lambda.
+  g2o_b200::NcclComm nccl;            // native communicator (b200_comm_init); preferred
+  b200_allreduce_fn allreduce = nullptr;  // host-supplied callback (b200_set_allreduce): same protocol, no CUDA graphs
   void* allreduce_user = nullptr;
   int rank = 0, world = 1;
+  bool comm_warm = false;             // the first sharded trial runs uncaptured (NCCL sets up its channels lazily)
+  g2o_b200::DevBuf<double> d_comm_diag;  // iteration 0: [Hpp diagonal partial sums | per-rank landmark maxima]
 
   // ---------------- CUDA graphs of the two launch-bound sequences of an LM iteration (single GPU, profiling off)
   cudaGraphExec_t graph_prologue = nullptr, graph_trial = nullptr;
   long long graph_prologue_launches = 0, graph_trial_launches = 0;
   bool use_graphs = true;
+
+  // SparseOptimizer::terminate() (core/sparse_optimizer.h:189): polled between LM trials and between iterations
+  b200_terminate_fn terminate = nullptr;
+  void* terminate_user = nullptr;
 
   // ---------------- profiling
   g2o_b200::EventProfiler prof;

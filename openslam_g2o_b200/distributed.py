@@ -1,11 +1,24 @@
-"""torch.distributed plumbing for landmark-sharded bundle adjustment.
+"""Communicator bootstrap for landmark-sharded bundle adjustment.
 
-One process per GPU.  Landmarks (and their observations) are split over the ranks, cameras are replicated; the only
-data-path exchange is the all-reduce of [Hschur | bschur] per LM trial (+ two tiny ones: partial Hpp/b_p after
-linearisation, chi2/scale scalars).  The C library calls back into `make_allreduce()` with a raw device pointer; the
-callback wraps it as a tensor (no copy) and issues the NCCL collective ordered on the solver's CUDA stream.
+One process per GPU.  Landmarks (and their observations) are split over the ranks, cameras are replicated.  The data
+path is native: the C++ host issues ncclAllReduce itself on the solver's stream (csrc/nccl_comm.cpp, captured in the
+trial CUDA graph) - two per LM trial: [Hschur | bschur | chi2] before the factorisation, 2 doubles after the update.
+Python only carries the NCCL unique id from rank 0 to the other ranks (`init_native_comm`, through the already
+initialised torch.distributed process group - any out-of-band channel would do).
+
+`make_allreduce` is the older host-callback route (b200_set_allreduce): the same protocol, every collective a Python
+round trip into torch.distributed and no CUDA graphs - kept for hosts that own their communicator.
 """
 import sys
+
+
+def init_native_comm(ctx, rank, world_size):
+    """collective: rank 0 creates the NCCL id, everybody joins (ncclCommInitRank on ctx's device)"""
+    import torch.distributed as dist
+    from .optimizer import comm_unique_id
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, world_size)
 
 
 class _DevicePointer:
@@ -36,7 +49,7 @@ def make_allreduce(ctx, local_rank):
     return allreduce
 
 
-def sharded_optimizer(problem, rank, world_size, local_rank, algorithm="lm_fix6_3"):
+def sharded_optimizer(problem, rank, world_size, local_rank, algorithm="lm_fix6_3", native=True):
     """SparseOptimizer over this rank's landmark shard, wired to the process group (must be initialised)"""
     from . import SparseOptimizer, synth
     opt = SparseOptimizer(device=local_rank, shard=rank, num_shards=world_size)
@@ -46,5 +59,8 @@ def sharded_optimizer(problem, rank, world_size, local_rank, algorithm="lm_fix6_
     opt.initialize_optimization()
     opt._ensure_uploaded()
     if world_size > 1:
-        opt.context.set_allreduce(make_allreduce(opt.context, local_rank), rank, world_size)
+        if native:
+            init_native_comm(opt.context, rank, world_size)
+        else:
+            opt.context.set_allreduce(make_allreduce(opt.context, local_rank), rank, world_size)
     return opt

@@ -273,8 +273,17 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     return _graph.ingest(_ctx, _optimizer);
   }
 
+  static int terminateHook(void* self) { return static_cast<OptimizationAlgorithmB200*>(self)->_optimizer->terminate() ? 1 : 0; }
+
   virtual SolverResult solve(int iteration, bool /*online*/ = false) {
     b200_iter_stats st;
+    G2OBatchStatistics* gsOn = G2OBatchStatistics::globalStats();
+    // `g2o -stats`: per-phase CUDA-event timing (individual launches instead of graph replays), like the reference's
+    // stats mode costs an extra error pass per iteration (core/sparse_optimizer.cpp:392-397)
+    if (iteration == 0) {
+      b200_set_profiling(_ctx, gsOn ? 1 : 0);
+      b200_set_terminate(_ctx, &OptimizationAlgorithmB200::terminateHook, this);  // forceStopFlag, sparse_optimizer.h:189
+    }
     int rc = b200_algorithm_solve(_ctx, _algorithm, iteration, &st);
     if (rc < 0) {  // hard error (bad structure, CUDA failure, out of memory): st is not meaningful
       std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
@@ -284,6 +293,13 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     if (gs) {  // same fields the CPU path fills (core/batch_stats.h:40-77)
       gs->levenbergIterations = st.levenberg_iterations;
       gs->timeIteration = st.time_iteration;
+      gs->timeResiduals = st.time_residuals;
+      gs->timeQuadraticForm = st.time_quadratic_form;
+      gs->timeSchurComplement = st.time_schur;
+      gs->timeNumericDecomposition = st.time_numeric;
+      gs->timeLinearSolver = st.time_linear_solver;
+      gs->timeLinearSolution = st.time_linear_solution;
+      gs->timeUpdate = st.time_update;
       gs->timeSymbolicDecomposition = st.time_symbolic;
       gs->choleskyNNZ = static_cast<size_t>(b200_get_factor_nnz(_ctx));
     }

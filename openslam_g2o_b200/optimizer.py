@@ -28,6 +28,15 @@ def _check(rc, handle=None, ls=False, graph=False):
     raise B200Error(rc, (msg or b"").decode())
 
 
+def comm_unique_id():
+    """rank 0: the NCCL unique id (bytes) to hand to every rank's SolverContext.comm_init"""
+    buf = C.create_string_buffer(L.COMM_ID_BYTES)
+    rc = lib.b200_comm_unique_id(buf, L.COMM_ID_BYTES)
+    if rc != 0:
+        raise B200Error(rc, (lib.b200_last_error(None) or b"").decode())
+    return buf.raw
+
+
 def block_amd(colptr, rowidx):
     """Block fill-reducing ordering (bit-exact twin of cs_amd(1, .), EXTERNAL/csparse/cs_amd.c). Host only."""
     colptr = L.as_i32(colptr)
@@ -89,6 +98,14 @@ class SolverContext:
         cb = L.ALLREDUCE_FN(fn)
         self._keep.append(cb)
         _check(lib.b200_set_allreduce(self._h, cb, None, rank, world_size), self._h)
+
+    def comm_init(self, unique_id, rank, world_size):
+        """native NCCL communicator of the landmark-sharded path (collective call: every rank, same unique_id)"""
+        buf = C.create_string_buffer(bytes(unique_id), L.COMM_ID_BYTES)
+        _check(lib.b200_comm_init(self._h, buf, rank, world_size), self._h)
+
+    def comm_destroy(self):
+        lib.b200_comm_destroy(self._h)
 
     # ---- g2o::Solver
     def build_structure(self):
@@ -155,6 +172,12 @@ class SolverContext:
         """one robust kernel on every edge (g2o -robustKernel NAME -robustKernelWidth delta)"""
         _check(lib.b200_set_robust_kernel(self._h, ROBUST_KERNELS[kind] if isinstance(kind, str) else int(kind),
                                           float(delta)), self._h)
+
+    def set_terminate(self, fn):
+        """SparseOptimizer::setForceStopFlag / terminate(): fn() -> truthy stops after the current trial / iteration"""
+        cb = L.TERMINATE_FN((lambda _u: 1 if fn() else 0) if fn else 0)
+        self._keep.append(cb)
+        _check(lib.b200_set_terminate(self._h, cb, None), self._h)
 
     def set_lm_params(self, user_lambda_init=0.0, max_trials_after_failure=10):
         _check(lib.b200_set_lm_params(self._h, user_lambda_init, max_trials_after_failure), self._h)

@@ -11,7 +11,10 @@ text line), so the same arrays feed the product (SparseOptimizer.add_vertices/ad
 """
 import numpy as np
 
-from ._lib import EDGE_P2MC, EDGE_SE3, EDGE_XYZ2UV, VERTEX_CAM, VERTEX_SE3, VERTEX_SE3_EXPMAP, VERTEX_XYZ
+# vertex / edge kinds of the C-ABI (include/g2o_b200.h).  Literal copies, so that this module has no import besides numpy:
+# bench.py's reference arm loads it by file path without importing the package (and with it libg2o_b200.so)
+VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP = 1, 2, 3, 4
+EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV = 1, 2, 3
 
 
 # ---------------------------------------------------------------- quaternion helpers (x y z w), vectorised

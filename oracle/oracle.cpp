@@ -1610,6 +1610,29 @@ int oracle_lm_iteration(oracle_graph* g, int iteration, oracle_iter_stats* st) {
   st->levenberg_iterations = g->levenbergIterations;
   return r;
 }
+// one OptimizationAlgorithm{GaussNewton,Levenberg}::solve(iteration) of a continuing optimisation, timed like
+// oracle_optimize times it; the chi2 of the state after the iteration is evaluated outside the timed part (what
+// SparseOptimizer::optimize does for its statistics, core/sparse_optimizer.cpp:392-397).  iteration 0 runs
+// OptimizationAlgorithmWithHessian::init first (sparse_optimizer.cpp:365).
+int oracle_iteration(oracle_graph* g, int algorithm, int iteration, oracle_iter_stats* st) {
+  oracle_iter_stats local;
+  if (!st) st = &local;
+  memset(st, 0, sizeof(*st));
+  if (g->ivMap.empty()) return -1;
+  if (iteration == 0 && !algorithm_init(g)) return -1;
+  st->iteration = iteration;
+  g->linearSolver.timeSymbolic = 0;
+  double ts = now();
+  int r = (algorithm == ORC_GN) ? solve_gn(g, iteration, st) : solve_lm(g, iteration, st);
+  st->time_iteration = now() - ts;
+  st->chi2 = compute_active_errors(g);
+  st->result = r;
+  st->lambda = g->currentLambda;
+  st->levenberg_iterations = g->levenbergIterations;
+  st->time_symbolic = g->linearSolver.timeSymbolic;
+  st->time_numeric = g->linearSolver.timeNumeric;
+  return r;
+}
 int oracle_algorithm_init(oracle_graph* g) { return algorithm_init(g) ? 0 : -1; }
 int oracle_build_structure(oracle_graph* g) { return build_structure(g) ? 0 : -1; }
 double oracle_compute_active_errors(oracle_graph* g) { return compute_active_errors(g); }

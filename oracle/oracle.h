@@ -78,6 +78,8 @@ int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_
 
 /* one OptimizationAlgorithmLevenberg::solve(iteration) of a running optimisation; returns SolverResult */
 int oracle_lm_iteration(oracle_graph* g, int iteration, oracle_iter_stats* stats);
+/* one GN (algorithm 0) / LM (1) iteration incl. OptimizationAlgorithm::init at iteration 0; stats->chi2 = chi2 after it */
+int oracle_iteration(oracle_graph* g, int algorithm, int iteration, oracle_iter_stats* stats);
 
 /* ---- step-wise access to the same objects (for fine-grained parity tests) ---- */
 int oracle_algorithm_init(oracle_graph* g);             /* OptimizationAlgorithmWithHessian::init */

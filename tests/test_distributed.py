@@ -82,7 +82,7 @@ def test_landmark_shards_agree_on_the_reduced_system_cpu(kind):
     assert res[0]["np"] == res[1]["np"] == d["numPoses"]
 
 
-def _gpu_worker(rank, world, port, out):
+def _gpu_worker(rank, world, port, out, native=True):
     import torch
     import torch.distributed as dist
     import openslam_g2o_b200 as g
@@ -93,7 +93,7 @@ def _gpu_worker(rank, world, port, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     p = synth.venice_like(40, 6000, seed=12)
-    opt = sharded_optimizer(p, rank, world, rank)
+    opt = sharded_optimizer(p, rank, world, rank, native=native)
     n = opt.optimize(6)
     chi = [s.chi2 for s in opt.batch_statistics]
     cams = opt.context.estimates(g.VERTEX_CAM, 40)
@@ -105,7 +105,8 @@ def _gpu_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_sharded_bundle_adjustment_matches_single_gpu():
+@pytest.mark.parametrize("native", [True, False], ids=["nccl_native", "host_callback"])
+def test_sharded_bundle_adjustment_matches_single_gpu(native):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -115,7 +116,7 @@ def test_sharded_bundle_adjustment_matches_single_gpu():
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
-    procs = [ctxm.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctxm.Process(target=_gpu_worker, args=(r, 2, port, q, native)) for r in range(2)]
     for p in procs:
         p.start()
     res = q.get(timeout=300)
