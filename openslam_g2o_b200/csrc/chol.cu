@@ -688,6 +688,10 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
   }
 }
 
+}  // namespace g2o_b200
+#include "chol_chain.cuh"
+namespace g2o_b200 {
+
 // ---------------------------------------------------------------------------------------------
 // triangular solves on the permuted vector (in place)
 // ---------------------------------------------------------------------------------------------
@@ -719,7 +723,7 @@ template <int D>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L, const double* __restrict__ Dinv,
                           double* __restrict__ y, int ntasks, const int* __restrict__ task_parent, int* next_task,
-                          int* bdone, int xb_doubles, int stage_doubles) {
+                          int* bdone, int xb_doubles, int stage_doubles, const unsigned char* __restrict__ task_skip) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_task;
   double* xb = smem;                 // x at the rows below the diagonal block
@@ -733,6 +737,10 @@ chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L
     __syncthreads();
     if (s_task >= ntasks) break;
     const int t = ntasks - 1 - s_task;
+    if (task_skip && task_skip[t]) {  // a link of the tail chain: chol_chain_backward_kernel has already solved it
+      cta_signal(bdone + t);
+      continue;
+    }
     const int q_root = P.task_ptr[t + 1] - 1;
     bool staged = false;
     {
@@ -832,9 +840,12 @@ template <int D>
 void set_smem_attrs() {
   B200_CUDA(cudaFuncSetAttribute(chol_factor_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_backward_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_chain_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_chain_dinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChDinvSmem));
 }
 // profiler ids of the kernel groups inside the Cholesky (continue the numbering of solver.cu)
-enum { PH_CH_SCATTER = 12, PH_CH_FLOW = 13, PH_CH_BACKWARD = 19 };
+enum { PH_CH_SCATTER = 12, PH_CH_FLOW = 13, PH_CH_CHAIN = 15, PH_CH_CHAIN_BACKWARD = 16, PH_CH_BACKWARD = 19 };
 }  // namespace
 
 void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, const SymbolicOptions& opt,
@@ -869,6 +880,26 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_flow_kind_.upload(S_.flow_kind, s); d_flow_arg_.upload(S_.flow_arg, s);
   d_sn_nupd_.upload(S_.sn_nupd, s); d_sn_nchunk_.upload(S_.sn_nchunk, s);
   d_task_parent_.upload(S_.task_parent, s);
+  {  // tail chain
+    d_chain_sn_.upload(S_.chain_sn, s); d_chain_mapptr_.upload(S_.chain_mapptr, s); d_chain_map_.upload(S_.chain_map, s);
+    d_chain_new_rows_.upload(S_.chain_new_rows, s); d_chain_colptr_.upload(S_.chain_colptr, s);
+    d_chain_fwd_ptr_.upload(S_.chain_fwd_ptr, s); d_chain_fwd_src_.upload(S_.chain_fwd_src, s);
+    std::vector<unsigned char> skip(S_.task_on_chain.begin(), S_.task_on_chain.end());
+    d_task_skip_.upload(skip, s);
+    chain_smem_ = chain_back_smem_ = 0;
+    if (!S_.chain_sn.empty()) {
+      chain_smem_ = ((size_t)kChFixedDoubles + S_.chain_stage_doubles + S_.chain_remap_blocks * 36 + (size_t)kChR * 42) * sizeof(double);
+      size_t need = 0;
+      for (int J : S_.chain_sn) {
+        const size_t N = (size_t)S_.sn_ncol[J] * d, B = (size_t)(S_.sn_nrow[J] - S_.sn_ncol[J]) * d;
+        need = std::max(need, B * N + N * N);
+      }
+      chain_back_buf_doubles_ = (int)need;
+      const size_t fixed = (192 + kMaxPanelCols) * sizeof(double);
+      chain_back_nbuf_ = (fixed + 2 * need * sizeof(double) <= (size_t)kMaxDynSmem) ? 2 : 1;
+      chain_back_smem_ = fixed + (size_t)chain_back_nbuf_ * need * sizeof(double);
+    }
+  }
   d_L_.alloc((size_t)S_.factor_doubles);
   d_Dinv_.alloc((size_t)S_.dinv_doubles);
   d_Ldiag_.alloc((size_t)S_.dinv_doubles);
@@ -892,6 +923,7 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   if (!host_only_flag()) {
     B200_CUDA(cudaStreamSynchronize(s));  // the temporaries above die here
     if (flow_smem_ > (size_t)kMaxDynSmem || stage_doubles_ < 0) throw CudaError{cudaErrorInvalidValue, "panel too large for shared memory", __FILE__, __LINE__};
+    if (chain_smem_ > (size_t)kMaxDynSmem || chain_back_smem_ > (size_t)kMaxDynSmem) throw CudaError{cudaErrorInvalidValue, "tail chain too large for shared memory (symbolic.cpp budget)", __FILE__, __LINE__};
     if (d == 3) set_smem_attrs<3>(); else set_smem_attrs<6>();
     int dev = 0, sms = 0, occ = 0;
     B200_CUDA(cudaGetDevice(&dev));
@@ -944,9 +976,20 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
                   cnt + cnt_slot_, d_sn_nupd_.p, d_sn_nchunk_.p, d_work_ksn_.p, d_group_rtile_.p, d_group_tile_.p,
                   d_group_w0_.p, d_group_w1_.p, d_group_slot_.p, d_rtile_tile_.p, d_rtile_slot0_.p, d_rtile_nslots_.p,
                   d_gscratch_.p};
-    chol_factor_flow_kernel<D><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2,
-                                                                            d_y_.p, d_z_.p, d_contrib_.p);
-    count();
+    if (!S.flow_kind.empty()) {
+      chol_factor_flow_kernel<D><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2,
+                                                                              d_y_.p, d_z_.p, d_contrib_.p);
+      count();
+    }
+  }
+  if (!S.chain_sn.empty()) {
+    // the tail chain: everything below it is complete (same stream), its panels hold A + the updates from below
+    ScopedPhase ph(prof, PH_CH_CHAIN);
+    ChainDev C{(int)S.chain_sn.size(), d_chain_sn_.p, d_chain_mapptr_.p, d_chain_map_.p, d_chain_new_rows_.p, d_chain_colptr_.p,
+               d_chain_fwd_ptr_.p, d_chain_fwd_src_.p, (int)S.chain_stage_doubles, (int)S.chain_remap_blocks};
+    chol_chain_kernel<<<1, kChThreads, chain_smem_, s>>>(P, C, d_sn_dinvptr_.p, L, d_Ldiag_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
+    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_Dinv_.p);
+    count(2);
   }
   B200_CUDA(cudaGetLastError());
 }
@@ -968,11 +1011,20 @@ void CholeskyGpu::solve_t(double* x, cudaStream_t s, LaunchCounter* lc, EventPro
   int* cnt = d_counters_.p;
   auto count = [&](int k = 1) { if (lc) lc->n += k; };
   double* y = d_z_.p;  // forward result (written by the factorisation) / backward in place
+  if (!S.chain_sn.empty()) {  // top of the tree first: the chain links, one CTA
+    ScopedPhase ph(prof, PH_CH_CHAIN_BACKWARD);
+    chol_chain_backward_kernel<<<1, kChThreads, chain_back_smem_, s>>>(P, (int)S.chain_sn.size(), d_chain_sn_.p, d_sn_dinvptr_.p, d_L_.p,
+                                                                       d_Dinv_.p, y, chain_back_buf_doubles_, chain_back_nbuf_);
+    count();
+  }
   ScopedPhase ph(prof, PH_CH_BACKWARD);
   const size_t bsmem = ((size_t)xb_doubles_ + kMaxPanelCols + stage_doubles_) * sizeof(double);
-  chol_backward_flow_kernel<D><<<back_grid_, kSolveThreads, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, ntask, d_task_parent_.p,
-                                                                        cnt + 1, cnt + cnt_bdone_, xb_doubles_, stage_doubles_);
-  count();
+  if ((int)S.chain_sn.size() < ntask) {
+    chol_backward_flow_kernel<D><<<back_grid_, kSolveThreads, bsmem, s>>>(P, Q, d_L_.p, d_Dinv_.p, y, ntask, d_task_parent_.p,
+                                                                          cnt + 1, cnt + cnt_bdone_, xb_doubles_, stage_doubles_,
+                                                                          S.chain_sn.empty() ? nullptr : d_task_skip_.p);
+    count();
+  }
   chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, cnt + 2);
   count();
   B200_CUDA(cudaGetLastError());

@@ -630,6 +630,7 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_PANEL_COLS")) opt.max_panel_cols_scalar = std::max(pd, std::min(72, atoi(e)));
   if (const char* e = getenv("G2O_B200_SUBTREE_FLOPS")) opt.subtree_min_flops = atof(e);
   if (const char* e = getenv("G2O_B200_RELAX")) opt.relax = atoi(e) != 0;
+  if (const char* e = getenv("G2O_B200_CHAIN")) opt.chain = atoi(e) != 0;   // 0: every supernode through the dataflow kernel
   if (const char* e = getenv("G2O_B200_GROUP_ITEMS")) opt.group_items = std::max(1, atoi(e));
   if (const char* e = getenv("G2O_B200_SORT_ITEMS")) opt.sort_items_by_level = atoi(e) != 0;
   if (const char* e = getenv("G2O_B200_RELAX_FRAC")) opt.relax_frac = atof(e);
@@ -1533,6 +1534,7 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
   out[0] = S.nsn; out[1] = (int64_t)S.task_ptr.size() - 1; out[2] = S.nlevels; out[3] = S.max_nrow; out[4] = S.max_ncol; out[5] = S.factor_doubles;
   out[6] = (int64_t)S.flow_kind.size();
   out[12] = (int64_t)S.flops;
+  out[13] = (int64_t)S.chain_sn.size(); out[14] = (int64_t)S.chain_flops; out[15] = 0;
   out[7] = c->sr_n; out[8] = c->sr_nseg; out[9] = c->sr_ncontrib; out[10] = c->n_hpl; out[11] = c->sr_n > 0 ? (int64_t)schur_range_smem(c) : 0;
   return B200_OK;
 }

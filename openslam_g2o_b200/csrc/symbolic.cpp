@@ -387,6 +387,70 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     S.task_sn.insert(S.task_sn.end(), t.begin(), t.end());
   }
 
+  // ---- 8b. tail chain: from the root down along the heaviest child, as long as the supernode is a task of its own
+  //          (not inside a small-subtree task) and its front fits the chain kernel
+  S.sn_on_chain.assign(ns, 0);
+  if (opt.chain && d == 6 && ns > 0 && S.sn_parent[ns - 1] < 0) {
+    std::vector<int> heavy(ns, -1);
+    for (int s = 0; s < ns; ++s) {  // ascending: the last assignment wins only if heavier
+      const int p = S.sn_parent[s];
+      if (p >= 0 && (heavy[p] < 0 || sub[s] > sub[heavy[p]])) heavy[p] = s;
+    }
+    std::vector<int> path;
+    size_t stage_max = 0, remap_max = 0;
+    for (int cur = ns - 1; cur >= 0; cur = heavy[cur]) {
+      if (root[cur] != -1 || S.sn_nrow[cur] > opt.chain_max_rows || S.sn_ncol[cur] > 12) break;
+      // shared memory of the chain kernel: the staged panel of this link and the re-index buffer of the link below
+      // (its rows below the diagonal block, i.e. at most this link's rows)
+      const size_t stage = (size_t)S.sn_nrow[cur] * d * S.sn_ncol[cur] * d;
+      const size_t below = (size_t)(S.sn_nrow[cur] - S.sn_ncol[cur]);
+      const size_t st2 = std::max(stage_max, stage), rm2 = std::max(remap_max, below * (below + 1) / 2);
+      if ((st2 + rm2 * (d * d + d)) * sizeof(double) > opt.chain_smem_budget) break;
+      stage_max = st2; remap_max = rm2;
+      path.push_back(cur);
+    }
+    if ((int)path.size() >= opt.chain_min_links) {
+      S.chain_sn.assign(path.rbegin(), path.rend());
+      for (int J : S.chain_sn) S.sn_on_chain[J] = 1;
+      // the re-index buffer holds the rows below the diagonal block of the link BELOW: recompute exactly
+      S.chain_stage_doubles = 0; S.chain_remap_blocks = 0;
+      for (int J : S.chain_sn) {
+        S.chain_stage_doubles = std::max(S.chain_stage_doubles, (size_t)S.sn_nrow[J] * d * S.sn_ncol[J] * d);
+        const size_t below = (size_t)(S.sn_nrow[J] - S.sn_ncol[J]);
+        S.chain_remap_blocks = std::max(S.chain_remap_blocks, below * (below + 1) / 2);
+        S.chain_flops += work[J];
+      }
+    }
+  }
+  const int nlinks = (int)S.chain_sn.size();
+  if (nlinks > 0) {
+    // re-index maps (= the relative indices of the update link -> parent) and the rows that enter at each link
+    S.chain_mapptr.assign(nlinks + 1, 0);
+    S.chain_new_rows.assign(nlinks, 0u);
+    S.chain_colptr.assign(nlinks + 1, 0);
+    for (int j = 0; j < nlinks; ++j) {
+      const int J = S.chain_sn[j];
+      S.chain_colptr[j + 1] = S.chain_colptr[j] + S.sn_ncol[J] * d;
+      unsigned fresh = S.sn_nrow[J] >= 32 ? 0xffffffffu : ((1u << S.sn_nrow[J]) - 1u);
+      if (j > 0) {
+        const int K = S.chain_sn[j - 1];
+        // the update K -> J starts at K's first row below its diagonal block (J is K's parent)
+        int u = -1;
+        for (int q = S.upd_ptr[J]; q < S.upd_ptr[J + 1]; ++q) if (S.upd_k[q] == K) { u = q; break; }
+        assert(u >= 0 && S.upd_p0[u] == S.sn_ncol[K]);
+        const int nbelow = S.sn_nrow[K] - S.sn_ncol[K];
+        for (int a = 0; a < nbelow; ++a) {
+          const int r = S.rel[S.upd_relptr[u] + a];
+          S.chain_map.push_back(r);
+          fresh &= ~(1u << r);
+        }
+      }
+      S.chain_mapptr[j + 1] = (int)S.chain_map.size();
+      S.chain_new_rows[j] = fresh;
+    }
+    // (maps are stored with the RECEIVING link: entry j tells where the rows below link j-1's diagonal block go)
+  }
+
   // ---- 9. numeric plan: destination tiles + their work items, row chunks, level kinds
   const int TB = std::max(1, 48 / d);
   // a chunk CTA maps block rows to the 32 lanes of a warp: diagonal block + chunk rows + the right-hand-side row
@@ -426,6 +490,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = sn_nct[J];
         for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
           const int K = S.upd_k[u];
+          if (S.sn_on_chain[K]) continue;  // chain link -> chain link: stays in the chain CTA's registers
           const int h = S.sn_nrow[K] - S.upd_p0[u], w = S.upd_p1[u] - S.upd_p0[u];
           const int* rel = S.rel.data() + S.upd_relptr[u];
           bound.assign(ntr + 1, h);  // bound[t] = first a with rel[a] >= t*TB
@@ -534,10 +599,42 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
             S.fwd_src[fill[kr[p] * d + rr]++] = (int)(S.sn_cptr[K] + (int64_t)(p - S.sn_ncol[K]) * d + rr);
       }
   }
+  if (nlinks > 0) {  // forward substitution of the chain: per scalar column the contributions of sources BELOW the chain
+    S.chain_fwd_ptr.assign(S.chain_colptr[nlinks] + 1, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<int> fill;
+      if (pass == 1) {
+        for (int i = 0; i < S.chain_colptr[nlinks]; ++i) S.chain_fwd_ptr[i + 1] += S.chain_fwd_ptr[i];
+        S.chain_fwd_src.assign(S.chain_fwd_ptr[S.chain_colptr[nlinks]], 0);
+        fill.assign(S.chain_fwd_ptr.begin(), S.chain_fwd_ptr.end() - 1);
+      }
+      for (int j = 0; j < nlinks; ++j) {
+        const int J = S.chain_sn[j];
+        for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
+          const int K = S.upd_k[u];
+          if (S.sn_on_chain[K]) continue;
+          const int* kr = S.sn_rows.data() + S.sn_rowptr[K];
+          for (int p = S.upd_p0[u]; p < S.upd_p1[u]; ++p)
+            for (int rr = 0; rr < d; ++rr) {
+              const int col = S.chain_colptr[j] + (kr[p] - S.sn_col0[J]) * d + rr;
+              if (pass == 0) S.chain_fwd_ptr[col + 1]++;
+              else S.chain_fwd_src[fill[col]++] = (int)(S.sn_cptr[K] + (int64_t)(p - S.sn_ncol[K]) * d + rr);
+            }
+        }
+      }
+    }
+  }
+  S.task_on_chain.assign(nt, 0);
+  for (int t = 0; t < nt; ++t)
+    if (S.task_ptr[t + 1] - S.task_ptr[t] == 1 && S.sn_on_chain[S.task_sn[S.task_ptr[t]]]) S.task_on_chain[t] = 1;
   for (int l = 0; l < S.nlevels; ++l) {
+    // chain links are left to the chain kernel: the level keeps only the GROUP tasks that bring them the updates of
+    // the supernodes below the chain
     bool singletons = true;
-    int tiles = 0, chunks = 0, ntask = S.level_ptr[l + 1] - S.level_ptr[l];
+    int tiles = 0, chunks = 0, ntask = 0;
     for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+      if (S.task_on_chain[t]) continue;
+      ++ntask;
       if (S.task_ptr[t + 1] - S.task_ptr[t] != 1) singletons = false;
       for (int q = S.task_ptr[t]; q < S.task_ptr[t + 1]; ++q) {
         const int J = S.task_sn[q];
@@ -545,9 +642,11 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         chunks += S.sn_chunk_ptr[J + 1] - S.sn_chunk_ptr[J];
       }
     }
-    if (singletons && (tiles > ntask || chunks > ntask)) {
-      S.level_kind[l] = 1;
+    const bool split = singletons && (tiles > ntask || chunks > ntask);
+    if (split) S.level_kind[l] = 1;
+    {
       for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+        if (!split && !S.task_on_chain[t]) continue;  // kind 0: the task's own CTA applies its updates
         const int J = S.task_sn[S.task_ptr[t]];
         for (int q = S.sn_tile_ptr[J]; q < S.sn_tile_ptr[J + 1]; ++q) {
           const int w0 = S.tile_work_ptr[q], w1 = S.tile_work_ptr[q + 1];
@@ -568,7 +667,8 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
             }
           }
         }
-        for (int q = S.sn_chunk_ptr[J]; q < S.sn_chunk_ptr[J + 1]; ++q) S.level_chunks.push_back(q);
+        if (!S.task_on_chain[t])
+          for (int q = S.sn_chunk_ptr[J]; q < S.sn_chunk_ptr[J + 1]; ++q) S.level_chunks.push_back(q);
       }
     }
     S.max_group_slots = slots;
@@ -579,12 +679,12 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   // ---- 10. dataflow task list (level-major; inside a split level: groups, then chunks; the reduction of a split
   //          tile is done by whichever of its groups finishes last)
   for (int l = 0; l < S.nlevels; ++l) {
-    if (S.level_kind[l] == 0) {
-      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) { S.flow_kind.push_back(0); S.flow_arg.push_back(t); }
-    } else {
-      for (int g = S.level_group_ptr[l]; g < S.level_group_ptr[l + 1]; ++g) { S.flow_kind.push_back(1); S.flow_arg.push_back(g); }
-      for (int c = S.level_chunk_ptr[l]; c < S.level_chunk_ptr[l + 1]; ++c) { S.flow_kind.push_back(3); S.flow_arg.push_back(S.level_chunks[c]); }
-    }
+    if (S.level_kind[l] == 0)
+      for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
+        if (!S.task_on_chain[t]) { S.flow_kind.push_back(0); S.flow_arg.push_back(t); }
+    // kind 1: every supernode of the level; kind 0: only the GROUP tasks whose destination is a chain link
+    for (int g = S.level_group_ptr[l]; g < S.level_group_ptr[l + 1]; ++g) { S.flow_kind.push_back(1); S.flow_arg.push_back(g); }
+    for (int c = S.level_chunk_ptr[l]; c < S.level_chunk_ptr[l + 1]; ++c) { S.flow_kind.push_back(3); S.flow_arg.push_back(S.level_chunks[c]); }
   }
   {
     std::vector<int> sn_task(ns, -1);

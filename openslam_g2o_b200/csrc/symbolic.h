@@ -29,6 +29,13 @@ struct SymbolicOptions {
   int nd_min_part = 24;             // parts smaller than this many blocks are not cut further
   // set when the caller already knows the ordering (tests); empty = run block AMD
   std::vector<int> given_perm;
+  // tail chain (chol.cu: chol_chain_kernel): the last stretch of the elimination tree - the path from some supernode up
+  // to the root - is factored by ONE CTA that keeps the whole frontal matrix in registers and never signals through
+  // HBM between links.  Only block dimension 6, fronts of at most chain_max_rows block rows.
+  bool chain = true;
+  int chain_max_rows = 31;
+  int chain_min_links = 3;
+  size_t chain_smem_budget = 190 * 1024;  // staged panel + re-index buffer of the widest link (+ ~31 KB of fixed buffers) must fit
 };
 
 struct SymbolicFactor {
@@ -113,6 +120,23 @@ struct SymbolicFactor {
   // inverses of the triangular diagonal blocks (for the solves)
   std::vector<int64_t> sn_dinvptr;                 // nsn+1
   int64_t dinv_doubles = 0;
+
+  // ---- tail chain (see SymbolicOptions::chain).  chain_sn lists the supernodes of the path bottom -> top (the last one is
+  // the root); they appear in no CHUNK task and no work item has one of them as its SOURCE: what a chain supernode
+  // receives from the supernodes below the chain still arrives through GROUP tasks in its HBM panel, what it receives
+  // from earlier links stays in the chain CTA's registers (multifrontal: the update matrix of link j, re-indexed by
+  // chain_map, is the start of link j+1's front).
+  std::vector<int> chain_sn;
+  std::vector<char> sn_on_chain;                   // nsn
+  std::vector<int> chain_mapptr, chain_map;        // per link: for every block row BELOW its diagonal block, the local row
+                                                   // in the next link's front (empty for the last link)
+  std::vector<unsigned> chain_new_rows;            // per link: bit r = local row r enters the front at this link (zero it)
+  std::vector<int> chain_colptr;                   // nlinks+1: scalar columns before link j (into chain_fwd_ptr)
+  std::vector<int> chain_fwd_ptr, chain_fwd_src;   // per scalar column of the chain: contribution entries of sources
+                                                   // below the chain (forward substitution)
+  std::vector<char> task_on_chain;                 // per task: 1 = its (single) supernode is a chain link
+  size_t chain_stage_doubles = 0, chain_remap_blocks = 0;  // shared-memory needs of the widest link
+  double chain_flops = 0;
 };
 
 // nested_dissection.cpp

@@ -242,11 +242,11 @@ class SolverContext:
         return int(lib.b200_get_factor_nnz(self._h))
 
     def factor_info(self):
-        out = np.zeros(13, np.int64)
+        out = np.zeros(16, np.int64)
         _check(lib.b200_get_factor_info(self._h, L.ptr(out)), self._h)
         return dict(zip(("supernodes", "tasks", "levels", "max_panel_rows", "max_panel_cols", "factor_doubles",
                          "flow_tasks", "schur_ranges", "schur_segments", "schur_contributions", "hpl_slots",
-                         "schur_range_smem", "factor_flops"), (int(v) for v in out)))
+                         "schur_range_smem", "factor_flops", "chain_links", "chain_flops"), (int(v) for v in out)))
 
     def launch_count(self):
         return int(lib.b200_get_launch_count(self._h))
@@ -256,8 +256,8 @@ class SolverContext:
 
     def phase_times(self):
         names = ("errors", "linearize", "schur", "factor", "trisolve", "update", "backsub", "linearize_cams", "gather",
-                 "schur_inv", "scale", "collective", "chol_scatter", "chol_factor_flow", "schur_finish", "unused15",
-                 "unused16", "unused17", "unused18", "chol_backward")
+                 "schur_inv", "scale", "collective", "chol_scatter", "chol_factor_flow", "schur_finish", "chol_chain",
+                 "chol_chain_backward", "unused17", "unused18", "chol_backward")
         out = {}
         for i, nme in enumerate(names):
             s, c = C.c_double(), C.c_int64()

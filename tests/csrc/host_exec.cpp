@@ -2,6 +2,7 @@
 // openslam_g2o_b200/csrc/symbolic.cpp.  It validates the integer plan (row structures, update lists,
 // relative indices, scatter plan, task/level order) on the CPU where there is no GPU; it is never part
 // of libg2o_b200.so and the product never calls it.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -13,6 +14,9 @@ using namespace g2o_b200;
 
 static int g_nd_levels = 0;
 static double g_relax_frac = 0.25;
+static int g_chain = 1, g_chain_min_links = 3, g_chain_max_rows = 31;
+extern "C" void hx_set_chain(int on, int min_links, int max_rows) { g_chain = on; g_chain_min_links = min_links; g_chain_max_rows = max_rows; }
+static void apply_chain_options(SymbolicOptions& o) { o.chain = g_chain != 0; o.chain_min_links = g_chain_min_links; o.chain_max_rows = g_chain_max_rows; }
 extern "C" void hx_set_nd_levels(int k) { g_nd_levels = k; }
 extern "C" void hx_set_relax_frac(double f) { g_relax_frac = f; }
 extern "C" int hx_block_amd(int n, const int* cp, const int* ri, int* perm) {
@@ -24,9 +28,11 @@ extern "C" int hx_block_amd(int n, const int* cp, const int* ri, int* perm) {
 // info[0]=nsn info[1]=ntasks info[2]=nlevels info[3]=scalar_lnz info[4]=factor_doubles info[5]=max_nrow info[6]=max_ncol
 extern "C" int hx_analyze(int nb, int d, const int* cp, const int* ri, int max_cols, int relax, long long* info, int* perm_out) {
   SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
+  apply_chain_options(o);
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
   info[0] = S.nsn; info[1] = (long long)S.task_ptr.size() - 1; info[2] = S.nlevels; info[3] = S.scalar_lnz;
   info[4] = S.factor_doubles; info[5] = S.max_nrow; info[6] = S.max_ncol; info[7] = (long long)S.flops;
+  info[8] = (long long)S.chain_sn.size();
   if (perm_out) memcpy(perm_out, S.perm.data(), nb * sizeof(int));
   return 0;
 }
@@ -34,6 +40,7 @@ extern "C" int hx_analyze(int nb, int d, const int* cp, const int* ri, int max_c
 extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const double* vals, double lambda,
                         const double* b, double* x, int max_cols, int relax) {
   SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
+  apply_chain_options(o);
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
   std::vector<double> L(S.factor_doubles, 0.0);
   const int nblk = cp[nb];
@@ -61,6 +68,7 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
         const int u = S.work_u[wi];
         if (u < S.upd_ptr[J] || u >= S.upd_ptr[J + 1]) return -6;
         const int K = S.upd_k[u], p0 = S.upd_p0[u];
+        if (S.sn_on_chain[K]) return -9;  // chain links never feed GROUP work items
         if (!done[K]) return -2;  // schedule violation
         const double* Kp = L.data() + S.sn_lptr[K];
         const int Mk = S.sn_nrow[K] * d, Nk = S.sn_ncol[K] * d;
@@ -93,6 +101,7 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
       }
       if (expect != S.sn_nrow[J]) return -8;
     }
+    if (S.sn_on_chain[J]) return 0;  // the panel now holds A + the updates of the supernodes below the chain
     for (int j = 0; j < N; ++j) {
       double dj = P[j + (size_t)j * M];
       if (!(dj > 0)) return 1;
@@ -113,6 +122,63 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
         int rc = factor_sn(S.task_sn[q]);
         if (rc) return rc;
       }
+  // the tail chain, the way chol_chain_kernel runs it: ONE frontal matrix in logical (local row) order that moves
+  // up the chain - link j adds its panel, eliminates its columns right-looking, and hands the remaining update
+  // matrix to link j+1 through chain_map; rows flagged in chain_new_rows start from zero
+  if (!S.chain_sn.empty()) {
+    const int nl = (int)S.chain_sn.size();
+    const int RM = 32 * d;
+    std::vector<double> F((size_t)RM * RM, 0.0), G((size_t)RM * RM, 0.0);
+    for (int j = 0; j < nl; ++j) {
+      const int J = S.chain_sn[j];
+      if (j + 1 < nl && S.sn_parent[J] != S.chain_sn[j + 1]) return -100;
+      if (j + 1 == nl && S.sn_parent[J] != -1) return -101;
+      const int nrow = S.sn_nrow[J], ncol = S.sn_ncol[J], M = nrow * d, N = ncol * d;
+      if (nrow > 31) return -102;
+      double* P = L.data() + S.sn_lptr[J];
+      for (int a = 0; a < nrow; ++a)
+        if (S.chain_new_rows[j] >> a & 1u)
+          for (int b = 0; b < nrow; ++b)
+            for (int i = 0; i < d; ++i) for (int jj = 0; jj < d; ++jj) { F[(a * d + i) + (size_t)(b * d + jj) * RM] = 0; F[(b * d + i) + (size_t)(a * d + jj) * RM] = 0; }
+      for (int c = 0; c < N; ++c) for (int r = c; r < M; ++r) F[r + (size_t)c * RM] += P[r + (size_t)c * M];
+      for (int c = 0; c < N; ++c) {
+        double dj = F[c + (size_t)c * RM];
+        if (!(dj > 0)) return 1;
+        dj = std::sqrt(dj);
+        F[c + (size_t)c * RM] = dj;
+        for (int r = c + 1; r < M; ++r) F[r + (size_t)c * RM] /= dj;
+        for (int c2 = c + 1; c2 < M; ++c2) {
+          const double f = F[c2 + (size_t)c * RM];
+          for (int r = c2; r < M; ++r) F[r + (size_t)c2 * RM] -= F[r + (size_t)c * RM] * f;
+        }
+      }
+      for (int c = 0; c < N; ++c) for (int r = c; r < M; ++r) P[r + (size_t)c * M] = F[r + (size_t)c * RM];
+      done[J] = 1;
+      if (j + 1 < nl) {
+        const int nbelow = nrow - ncol;
+        const int* map = S.chain_map.data() + S.chain_mapptr[j + 1];
+        if (S.chain_mapptr[j + 2] - S.chain_mapptr[j + 1] != nbelow) return -103;
+        const int Jn = S.chain_sn[j + 1];
+        const int* jr = S.sn_rows.data() + S.sn_rowptr[J];
+        const int* nr = S.sn_rows.data() + S.sn_rowptr[Jn];
+        std::fill(G.begin(), G.end(), 0.0);
+        for (int a = 0; a < nbelow; ++a) {
+          if (map[a] < 0 || map[a] >= S.sn_nrow[Jn] || nr[map[a]] != jr[ncol + a]) return -104;
+          if (S.chain_new_rows[j + 1] >> map[a] & 1u) return -105;
+          if (a > 0 && map[a] <= map[a - 1]) return -106;
+          for (int b = 0; b <= a; ++b)
+            for (int i = 0; i < d; ++i) for (int jj = 0; jj < d; ++jj)
+              G[(map[a] * d + i) + (size_t)(map[b] * d + jj) * RM] = F[((ncol + a) * d + i) + (size_t)((ncol + b) * d + jj) * RM];
+        }
+        // every row of the next link is either inherited or flagged new
+        unsigned inh = 0;
+        for (int a = 0; a < nbelow; ++a) inh |= 1u << map[a];
+        const unsigned all = (1u << S.sn_nrow[Jn]) - 1u;
+        if ((inh | S.chain_new_rows[j + 1]) != all || (inh & S.chain_new_rows[j + 1])) return -107;
+        F.swap(G);
+      }
+    }
+  }
   for (int s = 0; s < S.nsn; ++s) if (!done[s]) return -4;
   (void)nt;
   // solve: y = P b ; forward (pull) ; backward ; x = P^T y
@@ -168,13 +234,14 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
 // exactly once, every split tile must be completed by exactly one last group, and the completion targets (sn_nupd, sn_nchunk) must be reached exactly.
 extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int max_cols, int relax, int group_items) {
   SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac; o.group_items = group_items;
+  apply_chain_options(o);
   SymbolicFactor S = analyze(nb, d, cp, ri, o);
   const int nt = (int)S.task_ptr.size() - 1;
   std::vector<int> upd(S.nsn, 0), chunk(S.nsn, 0), slot(S.rtile_tile.size(), 0);
   std::vector<char> seen_g(S.group_tile.size(), 0), seen_r(S.rtile_tile.size(), 0), seen_c(S.chunk_sn.size(), 0), seen_t(nt, 0);
   auto ready = [&](int K) { return chunk[K] == S.sn_nchunk[K]; };
   auto items_ready = [&](int w0, int w1) {
-    for (int wi = w0; wi < w1; ++wi) if (!ready(S.work_ksn[wi])) return false;
+    for (int wi = w0; wi < w1; ++wi) if (S.sn_on_chain[S.work_ksn[wi]] || !ready(S.work_ksn[wi])) return false;
     return true;
   };
   for (size_t i = 0; i < S.flow_kind.size(); ++i) {
@@ -213,6 +280,7 @@ extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int ma
         if (a < 0 || a >= (int)seen_c.size() || seen_c[a]) return -40;
         seen_c[a] = 1;
         const int J = S.chunk_sn[a];
+        if (S.sn_on_chain[J]) return -42;
         if (upd[J] != S.sn_nupd[J]) return -41;
         chunk[J]++;
         break;
@@ -220,10 +288,30 @@ extern "C" int hx_check_flow(int nb, int d, const int* cp, const int* ri, int ma
       default: return -50;
     }
   }
-  for (int J = 0; J < S.nsn; ++J) if (!ready(J) || upd[J] != S.sn_nupd[J]) return -60;
+  for (int J = 0; J < S.nsn; ++J) {
+    if (S.sn_on_chain[J]) { if (chunk[J] != 0 || upd[J] != S.sn_nupd[J]) return -64; continue; }
+    if (!ready(J) || upd[J] != S.sn_nupd[J]) return -60;
+  }
+  // forward-substitution lists of the chain = the general lists restricted to sources below the chain, same order
+  if (!S.chain_sn.empty()) {
+    auto source_of = [&](int entry) { return (int)(std::upper_bound(S.sn_cptr.begin(), S.sn_cptr.end(), (int64_t)entry) - S.sn_cptr.begin()) - 1; };
+    for (size_t j = 0; j < S.chain_sn.size(); ++j) {
+      const int J = S.chain_sn[j];
+      for (int c = 0; c < S.sn_ncol[J] * d; ++c) {
+        const int g = S.sn_col0[J] * d + c, cc = S.chain_colptr[j] + c;
+        int q = S.chain_fwd_ptr[cc];
+        for (int e = S.fwd_ptr[g]; e < S.fwd_ptr[g + 1]; ++e) {
+          if (S.sn_on_chain[source_of(S.fwd_src[e])]) continue;
+          if (q >= S.chain_fwd_ptr[cc + 1] || S.chain_fwd_src[q] != S.fwd_src[e]) return -65;
+          ++q;
+        }
+        if (q != S.chain_fwd_ptr[cc + 1]) return -66;
+      }
+    }
+  }
   for (char c : seen_g) if (!c) return -61;
   for (char c : seen_r) if (!c) return -62;
-  for (char c : seen_c) if (!c) return -63;
+  for (size_t c = 0; c < seen_c.size(); ++c) if (!seen_c[c] && !S.sn_on_chain[S.chunk_sn[c]]) return -63;
   // scratch slots must be unique across the whole factorisation (levels overlap in the dataflow kernel)
   {
     std::vector<char> used(std::max(S.max_group_slots, 1), 0);

@@ -495,3 +495,37 @@ def test_full_size_sphere2500_matches_oracle():
     from openslam_g2o_b200 import synth
     chi = _headline_parity(synth.sphere(), 10, stride=1)
     assert chi[-1] < chi[0]
+
+
+def test_tail_chain_kernel_matches_dense_solve():
+    """band / ring systems (the reduced camera matrices of BA): almost every supernode is a link of the tail chain, which
+    one CTA factors with the frontal matrix in registers (chol_chain.cuh).  Against numpy's dense solve, with new values
+    on the same pattern, and with a negative pivot inside the chain (solve() == false)."""
+    import openslam_g2o_b200 as g
+    rng = np.random.default_rng(11)
+    ls = g.LinearSolverB200(0)
+    cases = [(60, [(i, (i + k) % 60) for i in range(60) for k in range(1, 4)]),
+             (200, [(i, (i + k) % 200) for i in range(200) for k in range(1, 9)]),
+             (150, [(i, i + k) for i in range(150) for k in range(1, 10) if i + k < 150]),
+             (90, [(i, i + 1) for i in range(89)] + [(i, i + 9) for i in range(81)])]
+    for nb, edges in cases:
+        cp, ri, vals, A = random_spd_blocks(rng, nb, 6, edges)
+        b = rng.standard_normal(nb * 6)
+        ls.init()
+        x = ls.solve(cp, ri, vals, b)
+        assert x is not None
+        assert rel_err(x, np.linalg.solve(A, b)) < 1e-9, nb
+        vals2 = vals.copy()
+        diag_idx = [q for j in range(nb) for q in range(cp[j], cp[j + 1]) if ri[q] == j]
+        vals2[diag_idx] *= 1.25
+        A2 = A.copy()
+        for j in range(nb):
+            A2[j * 6:(j + 1) * 6, j * 6:(j + 1) * 6] *= 1.25
+        x2 = ls.solve(cp, ri, vals2, b)
+        assert rel_err(x2, np.linalg.solve(A2, b)) < 1e-9, nb
+        # run-to-run bit-identical
+        assert np.array_equal(x2, ls.solve(cp, ri, vals2, b))
+        # a negative pivot in the last block column (the root of the chain)
+        vals3 = vals.copy()
+        vals3[diag_idx[-1]] -= 1e4 * np.eye(6)
+        assert ls.solve(cp, ri, vals3, b) is None

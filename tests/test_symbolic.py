@@ -103,7 +103,7 @@ def test_nested_dissection_option(hx):
                 assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
                 assert hx.hx_check_flow(nb, d, _p(cp), _p(ri), 24, 1, 4) == 0
                 perm = np.zeros(nb, np.int32)
-                info = np.zeros(8, np.int64)
+                info = np.zeros(16, np.int64)
                 hx.hx_analyze(nb, d, _p(cp), _p(ri), 24, 1, _p(info), _p(perm))
                 assert sorted(perm.tolist()) == list(range(nb))
         # ring of 871 cameras, every camera coupled to the next 8: levels of the task schedule, AMD vs dissection
@@ -113,7 +113,7 @@ def test_nested_dissection_option(hx):
         res = {}
         for nd in (0, 4):
             hx.hx_set_nd_levels(nd)
-            info = np.zeros(8, np.int64)
+            info = np.zeros(16, np.int64)
             hx.hx_analyze(871, 6, _p(cp), _p(ri), 72, 1, _p(info), None)
             res[nd] = (int(info[2]), int(info[4]))  # levels, factor doubles
             assert hx.hx_check_flow(871, 6, _p(cp), _p(ri), 72, 1, 8) == 0
@@ -121,3 +121,50 @@ def test_nested_dissection_option(hx):
         assert res[4][1] < 3 * res[0][1], res          # at a bounded price in fill
     finally:
         hx.hx_set_nd_levels(0)
+
+
+def test_tail_chain_plan(hx):
+    """the tail chain (one CTA keeps the frontal matrix in registers along the last path of the elimination tree):
+    the host executor runs the chain the way chol_chain_kernel does (re-index maps, new-row masks, filtered work items)
+    and must still solve the system; on band-like patterns the chain must actually exist"""
+    from helpers import upper_pattern_from_edges
+    rng = np.random.default_rng(3)
+    try:
+        for min_links in (1, 3):
+            hx.hx_set_chain(1, min_links, 31)
+            cases = [(45, [(i, (i + k) % 45) for i in range(45) for k in range(1, 4)], 12),
+                     (120, [(i, (i + k) % 120) for i in range(120) for k in range(1, 6)], 24),
+                     (200, [(i, (i + k) % 200) for i in range(200) for k in range(1, 9)], 72),
+                     (60, [(int(rng.integers(60)), int(rng.integers(60))) for _ in range(150)], 24),
+                     (90, [(i, i + 1) for i in range(89)] + [(i, i + 9) for i in range(81)], 36)]
+            for nb, edges, maxc in cases:
+                cp, ri, vals, A = random_spd_blocks(rng, nb, 6, edges)
+                v = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+                b = rng.standard_normal(nb * 6)
+                x = np.zeros(nb * 6)
+                rc = hx.hx_solve(nb, 6, _p(cp), _p(ri), _p(v), C.c_double(0.5), _p(b), _p(x), maxc, 1)
+                assert rc == 0, (rc, nb, maxc, min_links)
+                xr = np.linalg.solve(A + 0.5 * np.eye(nb * 6), b)
+                assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+                for gi in (1, 4, 16):
+                    assert hx.hx_check_flow(nb, 6, _p(cp), _p(ri), maxc, 1, gi) == 0, (nb, maxc, gi)
+        hx.hx_set_chain(1, 3, 31)
+        # the reduced camera systems of the two BA workloads: almost everything is chain
+        for nb, w in ((871, 8), (2000, 9)):
+            ring = [(i, (i + k) % nb) for i in range(nb) for k in range(1, w + 1)]
+            cp, ri = upper_pattern_from_edges(nb, ring)
+            info = np.zeros(16, np.int64)
+            hx.hx_analyze(nb, 6, _p(cp), _p(ri), 72, 1, _p(info), None)
+            assert info[8] >= 0.5 * info[0] - 8, info   # chain links vs supernodes
+            assert hx.hx_check_flow(nb, 6, _p(cp), _p(ri), 72, 1, 16) == 0
+        # block dimension 3 (SE2) and fronts wider than the chain's register file: no chain, the old path
+        grid = [(r * 50 + c, r * 50 + (c + 1) % 50) for r in range(50) for c in range(50)] + \
+               [(r * 50 + c, (r + 1) * 50 + c) for r in range(49) for c in range(50)]
+        cp, ri = upper_pattern_from_edges(2500, grid)
+        for d in (3, 6):
+            info = np.zeros(16, np.int64)
+            hx.hx_analyze(2500, d, _p(cp), _p(ri), 72, 1, _p(info), None)
+            # d = 3: never; d = 6: at most the last few panels of the top separator (their fronts have shrunk to <= 31 rows)
+            assert info[8] == 0 if d == 3 else info[8] <= 4, info
+    finally:
+        hx.hx_set_chain(1, 3, 31)
