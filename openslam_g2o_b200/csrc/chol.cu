@@ -888,16 +888,32 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
     d_task_skip_.upload(skip, s);
     chain_smem_ = chain_back_smem_ = 0;
     if (!S_.chain_sn.empty()) {
-      chain_smem_ = ((size_t)kChFixedDoubles + S_.chain_stage_doubles + S_.chain_remap_blocks * 36 + (size_t)kChR * 42) * sizeof(double);
+      chain_smem_ = ((size_t)kChFixedDoubles + S_.chain_stage_doubles + 72 + (S_.chain_remap_blocks + kChR) * kChRemapLd) * sizeof(double);
       size_t need = 0;
-      for (int J : S_.chain_sn) {
+      // per-link descriptors (chol_chain.cuh: CD_*)
+      const int nl = (int)S_.chain_sn.size();
+      std::vector<int> desc((size_t)nl * CD_INTS, 0);
+      long long pack_total = 0;  // packed [rows below the diagonal block | inverse diagonal block] per link (backward sweep)
+      for (int j = 0; j < nl; ++j) {
+        const int J = S_.chain_sn[j];
         const size_t N = (size_t)S_.sn_ncol[J] * d, B = (size_t)(S_.sn_nrow[J] - S_.sn_ncol[J]) * d;
-        need = std::max(need, B * N + N * N);
+        need = std::max(need, B * N + N * N + N);
+        int* dj = desc.data() + (size_t)j * CD_INTS;
+        dj[CD_NROW] = S_.sn_nrow[J]; dj[CD_NCOL] = S_.sn_ncol[J]; dj[CD_COL0S] = S_.sn_col0[J] * d;
+        dj[CD_NFWD] = S_.chain_fwd_ptr[S_.chain_colptr[j + 1]] - S_.chain_fwd_ptr[S_.chain_colptr[j]];
+        const long long lp = S_.sn_lptr[J], dp = S_.sn_dinvptr[J];
+        dj[CD_LPTR] = (int)(unsigned)(lp & 0xffffffffll); dj[CD_LPTR + 1] = (int)(lp >> 32);
+        dj[CD_DPTR] = (int)(unsigned)(dp & 0xffffffffll); dj[CD_DPTR + 1] = (int)(dp >> 32);
+        dj[CD_MAPOFF] = S_.chain_mapptr[j]; dj[CD_MAPCNT] = S_.chain_mapptr[j + 1] - S_.chain_mapptr[j];
+        dj[CD_COLPTR] = S_.chain_colptr[j];
+        dj[CD_PACK] = (int)(unsigned)(pack_total & 0xffffffffll); dj[CD_PACK + 1] = (int)(pack_total >> 32);
+        pack_total += (long long)(B * N + N * N);
       }
+      d_chain_pack_.alloc((size_t)pack_total);
+      d_chain_desc_.upload(desc, s);
+      need = (need + 1) & ~(size_t)1;
       chain_back_buf_doubles_ = (int)need;
-      const size_t fixed = (192 + kMaxPanelCols) * sizeof(double);
-      chain_back_nbuf_ = (fixed + 2 * need * sizeof(double) <= (size_t)kMaxDynSmem) ? 2 : 1;
-      chain_back_smem_ = fixed + (size_t)chain_back_nbuf_ * need * sizeof(double);
+      chain_back_smem_ = (2 * 192 + kMaxPanelCols + 2 * need) * sizeof(double);
     }
   }
   d_L_.alloc((size_t)S_.factor_doubles);
@@ -985,10 +1001,10 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
   if (!S.chain_sn.empty()) {
     // the tail chain: everything below it is complete (same stream), its panels hold A + the updates from below
     ScopedPhase ph(prof, PH_CH_CHAIN);
-    ChainDev C{(int)S.chain_sn.size(), d_chain_sn_.p, d_chain_mapptr_.p, d_chain_map_.p, d_chain_new_rows_.p, d_chain_colptr_.p,
-               d_chain_fwd_ptr_.p, d_chain_fwd_src_.p, (int)S.chain_stage_doubles, (int)S.chain_remap_blocks};
-    chol_chain_kernel<<<1, kChThreads, chain_smem_, s>>>(P, C, d_sn_dinvptr_.p, L, d_Ldiag_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
-    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_Dinv_.p);
+    ChainDev C{(int)S.chain_sn.size(), d_chain_desc_.p, d_chain_map_.p, d_chain_fwd_ptr_.p, d_chain_fwd_src_.p,
+               (int)S.chain_stage_doubles, (int)S.chain_remap_blocks};
+    chol_chain_kernel<<<1, kChThreads, chain_smem_, s>>>(C, L, d_Ldiag_.p, d_chain_pack_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
+    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_chain_desc_.p, d_chain_pack_.p);
     count(2);
   }
   B200_CUDA(cudaGetLastError());
@@ -1013,8 +1029,8 @@ void CholeskyGpu::solve_t(double* x, cudaStream_t s, LaunchCounter* lc, EventPro
   double* y = d_z_.p;  // forward result (written by the factorisation) / backward in place
   if (!S.chain_sn.empty()) {  // top of the tree first: the chain links, one CTA
     ScopedPhase ph(prof, PH_CH_CHAIN_BACKWARD);
-    chol_chain_backward_kernel<<<1, kChThreads, chain_back_smem_, s>>>(P, (int)S.chain_sn.size(), d_chain_sn_.p, d_sn_dinvptr_.p, d_L_.p,
-                                                                       d_Dinv_.p, y, chain_back_buf_doubles_, chain_back_nbuf_);
+    chol_chain_backward_kernel<<<1, kChThreads, chain_back_smem_, s>>>((int)S.chain_sn.size(), d_chain_desc_.p, d_chain_map_.p,
+                                                                       d_chain_pack_.p, y, chain_back_buf_doubles_);
     count();
   }
   ScopedPhase ph(prof, PH_CH_BACKWARD);
@@ -1046,6 +1062,10 @@ extern "C" void b200_debug_chol_stamps(unsigned long long* out, int reset) {
     for (int i = 0; i < 6 * 4096; ++i) z[i] = i / 4096 == 3 ? ~0ull : 0ull;
     cudaMemcpyToSymbol(g2o_b200::g_chol_stamp, z, sizeof(z));
   }
+}
+extern "C" void b200_debug_chain_timing(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g2o_b200::g_chain_timing, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g2o_b200::g_chain_timing, z, sizeof(z)); }
 }
 extern "C" void b200_debug_chol_timing(unsigned long long* out, int reset) {
   cudaMemcpyFromSymbol(out, g2o_b200::g_chol_timing, sizeof(unsigned long long) * 32);

@@ -59,11 +59,12 @@ class CholeskyGpu {
   DevBuf<double> d_L_, d_Ldiag_, d_Dinv_, d_y_, d_z_, d_gscratch_, d_contrib_;
   DevBuf<int> d_counters_;  // task counters, status flag, completion counters (zeroed by every factor())
   // tail chain (chol_chain.cuh)
-  DevBuf<int> d_chain_sn_, d_chain_mapptr_, d_chain_map_, d_chain_colptr_, d_chain_fwd_ptr_, d_chain_fwd_src_;
+  DevBuf<int> d_chain_sn_, d_chain_mapptr_, d_chain_map_, d_chain_colptr_, d_chain_fwd_ptr_, d_chain_fwd_src_, d_chain_desc_;
   DevBuf<unsigned> d_chain_new_rows_;
+  DevBuf<double> d_chain_pack_;  // per chain link: rows below the diagonal block (packed) | inverse diagonal block
   DevBuf<unsigned char> d_task_skip_;
   size_t chain_smem_ = 0, chain_back_smem_ = 0;
-  int chain_back_buf_doubles_ = 0, chain_back_nbuf_ = 1;
+  int chain_back_buf_doubles_ = 0;
   int cnt_upd_ = 0, cnt_chunk_ = 0, cnt_slot_ = 0, cnt_bdone_ = 0;
   size_t flow_smem_ = 0;
   int xb_doubles_ = 0, stage_doubles_ = 0, flow_grid_ = 1, back_grid_ = 1;

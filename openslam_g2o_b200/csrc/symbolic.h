@@ -33,7 +33,7 @@ struct SymbolicOptions {
   // to the root - is factored by ONE CTA that keeps the whole frontal matrix in registers and never signals through
   // HBM between links.  Only block dimension 6, fronts of at most chain_max_rows block rows.
   bool chain = true;
-  int chain_max_rows = 31;
+  int chain_max_rows = 29;   // = kChR of chol_chain.cuh
   int chain_min_links = 3;
   size_t chain_smem_budget = 190 * 1024;  // staged panel + re-index buffer of the widest link (+ ~31 KB of fixed buffers) must fit
 };
