@@ -271,12 +271,13 @@ __device__ __forceinline__ void load_der(const double* __restrict__ der, int c, 
   for (int i = 0; i < 8; ++i) { double2 a = __ldg(p + i); d[2 * i] = a.x; d[2 * i + 1] = a.y; }
 }
 
+// edges [e_begin, E) (e_begin > 0: the observations of fixed points, which the fused back-substitution kernel does not visit)
 template <int MODEL>
 __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* __restrict__ e_cam,
                                const double* __restrict__ pt_est, const double* __restrict__ cam_der,
                                const double* __restrict__ meas, const double* __restrict__ info, Robust rk,
-                               double* __restrict__ partials) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+                               double* __restrict__ partials, int e_begin) {
+  const int e = e_begin + blockIdx.x * blockDim.x + threadIdx.x;
   double chi = 0.0;
   if (e < E) {
     double der[16];
@@ -729,6 +730,78 @@ __global__ void ba_backsub_kernel(int nl, const int* __restrict__ lm_eptr, const
   const double* Di = Dinv + kDinvStride * (long long)l;
 #pragma unroll
   for (int r = 0; r < 3; ++r) x_l[3ll * l + r] = Di[r] * c0 + Di[r + 3] * c1 + Di[r + 6] * c2;
+}
+
+// The tail of an LM trial for the landmarks in ONE pass over their observations (one thread per landmark, rank order):
+//   x_l = Dinv (b_l - sum_e Hpl(e)^T x_cam(e))                        back-substitution, block_solver.hpp:461-481
+//   scale_l += x_l . (lambda x_l + b_l)                               computeScale, optimization_algorithm_levenberg.cpp:165-172
+//   X_l <- X_l + x_l                                                  VertexSBAPointXYZ::oplusImpl, types_sba.h:151-155
+//   chi2 += sum_e rho(e_e^T Omega_e e_e) at the NEW state             computeActiveErrors + activeRobustChi2
+// (the cameras have been updated by oplus_cam_kernel before).  Replaces ba_backsub_kernel + oplus_xyz_kernel +
+// ba_chi2_kernel + lm_scale_kernel(landmark part): the observations' indices and the landmark are read once instead of
+// three times.  Block sums are fixed trees: bit-identical from run to run.
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+ba_backsub_update_kernel(int nl, const int* __restrict__ lm_eptr, const int* __restrict__ lm_order,
+                         const int* __restrict__ lm_vertex, const int* __restrict__ e_cam, const int* __restrict__ e_hpl,
+                         const int* __restrict__ e_pose, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+                         const double* __restrict__ b_l, const double* __restrict__ x_p, double* __restrict__ x_l,
+                         const double* __restrict__ lambda, double* __restrict__ pt_est, const double* __restrict__ cam_der,
+                         const double* __restrict__ meas, const double* __restrict__ info, int E, Robust rk,
+                         double* __restrict__ partial_chi2, double* __restrict__ partial_scale) {
+  const int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0, sc = 0.0;
+  if (rank < nl) {
+    const int l = lm_order[rank];
+    const int e0 = lm_eptr[rank], e1 = lm_eptr[rank + 1];
+    const double bl0 = b_l[3ll * l], bl1 = b_l[3ll * l + 1], bl2 = b_l[3ll * l + 2];
+    double c0 = bl0, c1 = bl1, c2 = bl2;
+    int prev = -1;
+    for (int e = e0; e < e1; ++e) {
+      const int slot = e_hpl[e];
+      if (slot < 0 || slot == prev) continue;  // duplicate observations share one block
+      prev = slot;
+      const double2* B2 = reinterpret_cast<const double2*>(Hpl + 18ll * slot);
+      const double2* xp2 = reinterpret_cast<const double2*>(x_p + 6ll * e_pose[e]);
+      double B[18], xv[6];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { const double2 v = __ldg(B2 + k); B[2 * k] = v.x; B[2 * k + 1] = v.y; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double2 v = xp2[k]; xv[2 * k] = -v.x; xv[2 * k + 1] = -v.y; }
+      double t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { t0 += B[r] * xv[r]; t1 += B[r + 6] * xv[r]; t2 += B[r + 12] * xv[r]; }
+      c0 += t0; c1 += t1; c2 += t2;
+    }
+    const double* Di = Dinv + kDinvStride * (long long)l;
+    double x[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) x[r] = Di[r] * c0 + Di[r + 3] * c1 + Di[r + 6] * c2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) x_l[3ll * l + r] = x[r];
+    const double lam = *lambda;
+    sc = x[0] * (lam * x[0] + bl0) + x[1] * (lam * x[1] + bl1) + x[2] * (lam * x[2] + bl2);
+    double4* Xp = reinterpret_cast<double4*>(pt_est + 4ll * lm_vertex[l]);
+    double4 X4 = *Xp;
+    X4.x += x[0]; X4.y += x[1]; X4.z += x[2];
+    *Xp = X4;
+    const double X[3] = {X4.x, X4.y, X4.z};
+    for (int e = e0; e < e1; ++e) {
+      double der[16];
+      load_der(cam_der, e_cam[e], der);
+      const double z[2] = {meas[e], meas[(long long)E + e]};
+      double err[2];
+      ba_error<MODEL>(der, X, z, err);
+      const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+      double ce = err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]);
+      if (rk.kind) { double r1; robustify(rk, ce, ce, r1); }
+      chi += ce;
+    }
+  }
+  chi = block_sum(chi);
+  if (threadIdx.x == 0) partial_chi2[blockIdx.x] = chi;
+  sc = block_sum(sc);
+  if (threadIdx.x == 0) partial_scale[blockIdx.x] = sc;
 }
 
 // ------------------------------------------------------------------ oplus updates

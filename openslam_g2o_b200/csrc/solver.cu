@@ -89,6 +89,7 @@ void set_device_lambda(b200_ctx* c, double lam) {
 void drop_graphs(b200_ctx* c) {
   if (c->graph_prologue) { cudaGraphExecDestroy(c->graph_prologue); c->graph_prologue = nullptr; }
   if (c->graph_trial) { cudaGraphExecDestroy(c->graph_trial); c->graph_trial = nullptr; }
+  if (c->graph_build) { cudaGraphExecDestroy(c->graph_build); c->graph_build = nullptr; }
 }
 
 static size_t schur_range_smem(const b200_ctx* c) {
@@ -199,7 +200,7 @@ int build_structure_impl(b200_ctx* c) {
   c->d_b.zero(s); c->d_x.zero(s);
   c->d_diag.alloc(ntot);
   c->d_scalars.alloc(16); c->d_scalars.zero(s);
-  c->d_partials.alloc((size_t)ceil_div(std::max(E, ntot), 256) + 64);
+  c->d_partials.alloc((size_t)ceil_div(std::max(E, ntot), 256) + (size_t)ceil_div(std::max(nl, 1), 128) + 64);
 
   const int D = edim(c->edge_kind);
   const int pd = c->pd;
@@ -613,6 +614,8 @@ int build_structure_impl(b200_ctx* c) {
     c->d_ev0.upload(e_pt, s); c->d_ev1.upload(e_cam, s); c->d_e_pose.upload(e_pose, s); c->d_e_hpl.upload(e_hpl, s);
     c->d_e_flag.upload(e_first, s);
     c->d_meas.upload(meas, s); c->d_info.upload(info, s);
+    c->n_edges_free_lm = lm_eptr[nl];
+    c->d_partials2.alloc((size_t)ceil_div(std::max(nl, 1), 128) + 8);
     c->d_lm_eptr.upload(lm_eptr, s); c->d_lm_order.upload(lm_order, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
     c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
     c->d_t_row.upload(t_row, s); c->d_t_col.upload(t_col, s); c->d_t_hpp.upload(t_hpp, s);
@@ -639,6 +642,7 @@ int build_structure_impl(b200_ctx* c) {
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
   STAMP("symbolic (ordering + plan)");
   c->structured = true;
+  c->state_chi2_valid = false;  // new graph / new estimates on the device
   c->backup_depth = 0;
   c->time_symbolic = wall() - t0;
   return B200_OK;
@@ -658,7 +662,7 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
   else if (c->edge_kind == B200_EDGE_SE3)
     k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
   else
-    BA_MODEL_LAUNCH(c, ba_chi2_kernel, <<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p));
+    BA_MODEL_LAUNCH(c, ba_chi2_kernel, <<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p, 0));
   k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 0);
   c->lc.n += 2;
   B200_CUDA(cudaGetLastError());
@@ -762,7 +766,7 @@ int enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses a
 
 
 // Solver::solve with the lambda currently stored at d_scalars[3]
-int enqueue_solve(b200_ctx* c) {
+int enqueue_solve(b200_ctx* c, bool skip_backsub = false) {
   cudaStream_t s = c->stream;
   const double* d_lambda = c->d_scalars.p + 3;
   if (!c->schur) {
@@ -804,7 +808,7 @@ int enqueue_solve(b200_ctx* c) {
   }
   { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, bschur_ptr(c), s, &c->lc, &c->prof); }
   { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc, &c->prof); }
-  if (c->nl > 0) {
+  if (c->nl > 0 && !skip_backsub) {
     PhaseTimer pt(c, PH_BACKSUB);
     // on a failed factorisation the reference returns before touching the landmark part of x; the pose part
     // is left untouched by chol.solve, the landmark part is recomputed from the stale pose part (harmless:
@@ -872,6 +876,42 @@ void do_pop(b200_ctx* c) {
   if (c->schur && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_est.p, c->d_lm_bak.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
+// BA trial tail, fused (kernels.cuh: ba_backsub_update_kernel): cameras first, then ONE pass over the landmarks' observations
+// does back-substitution, landmark update, chi2 of the new state and the landmark part of the LM scale
+bool fused_tail(const b200_ctx* c) { return c->fuse_tail && c->schur && c->nl > 0; }
+void enqueue_fused_tail(b200_ctx* c) {
+  cudaStream_t s = c->stream;
+  const int n = c->n_pose_v, E = c->nE;
+  { PhaseTimer pt(c, PH_UPDATE);
+    BA_MODEL_LAUNCH(c, oplus_cam_kernel, <<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, c->d_cam_der.p));
+    c->lc.n++; }
+  const int nb = ceil_div(c->nl, 128);
+  { PhaseTimer pt(c, PH_BACKSUB);
+    BA_MODEL_LAUNCH(c, ba_backsub_update_kernel, <<<nb, 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_pose.p,
+        c->d_Hpl.p, c->d_Dinv.p, c->d_b.p + c->sizeP, c->d_x.p, c->d_x.p + c->sizeP, c->d_scalars.p + 3, c->d_lm_est.p, c->d_cam_der.p,
+        c->d_meas.p, c->d_info.p, E, c->robust, c->d_partials.p, c->d_partials2.p));
+    c->lc.n++; }
+  int nchi = nb;
+  if (c->n_edges_free_lm < E) {  // observations of fixed points: the plain error kernel on the tail of the edge list
+    PhaseTimer pt(c, PH_ERRORS);
+    const int nt = ceil_div(E - c->n_edges_free_lm, 256);
+    BA_MODEL_LAUNCH(c, ba_chi2_kernel, <<<nt, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p + nb, c->n_edges_free_lm));
+    nchi += nt;
+    c->lc.n++;
+  }
+  { PhaseTimer pt(c, PH_SCALE);
+    k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nchi, c->d_scalars.p + 0);
+    k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials2.p, nb, c->d_scalars.p + 1);
+    // pose part of the scale (sharded: partial, see enqueue_scale)
+    const int np = ceil_div(c->sizeP, 256);
+    const double* pose_lambda = (sharded(c) && c->rank != 0) ? c->d_scalars.p + 6 : c->d_scalars.p + 3;
+    k::lm_scale_kernel<<<np, 256, 0, s>>>(c->sizeP, c->d_x.p, c->d_b.p, pose_lambda, c->d_partials.p);
+    k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, np, c->d_scalars.p + 4);
+    c->lc.n += 4;
+    if (sharded(c)) { k::fold_scale_kernel<<<1, 1, 0, s>>>(c->d_scalars.p); c->lc.n++; } }
+  B200_CUDA(cudaGetLastError());
+}
+
 // sharded runs: chi2 and the landmark part of the LM scale are partial sums -> one tiny all-reduce
 int reduce_trial_scalars(b200_ctx* c, int count = 1) {
   if (!sharded(c)) return 0;
@@ -911,16 +951,19 @@ int run_captured(b200_ctx* c, cudaGraphExec_t* exec, long long* launches, F&& en
   return 0;
 }
 
-// errors + chi2 + buildSystem of the current state
-int run_prologue(b200_ctx* c) {
+// errors + chi2 + buildSystem of the current state; the error pass is skipped when the chi2 of this very state is known
+int run_prologue(b200_ctx* c, bool need_chi2) {
   auto body = [&]() -> int {
-    enqueue_chi2(c);
-    // sharded: this rank's part of chi2 rides in the first trial's all-reduce (slot 7 -> tail of [Hschur | bschur])
-    if (sharded(c)) B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 7, c->d_scalars.p + 0, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (need_chi2) {
+      enqueue_chi2(c);
+      // sharded: this rank's part of chi2 rides in the first trial's all-reduce (slot 7 -> tail of [Hschur | bschur])
+      if (sharded(c)) B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 7, c->d_scalars.p + 0, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
     return enqueue_build_system(c);
   };
   if (!graphs_usable(c)) return body();
-  return run_captured(c, &c->graph_prologue, &c->graph_prologue_launches, body);
+  if (need_chi2) return run_captured(c, &c->graph_prologue, &c->graph_prologue_launches, body);
+  return run_captured(c, &c->graph_build, &c->graph_build_launches, body);
 }
 
 // one LM trial: lambda -> solve -> update -> errors + chi2 -> scale
@@ -928,13 +971,13 @@ int run_trial(b200_ctx* c) {
   c->h_scalars[8] = c->lambda;
   bool orth_now = false;
   if (c->pose_kind == B200_VERTEX_SE3 && c->num_oplus_calls + 1 > 1000) orth_now = true;  // rare: take the plain path
+  const bool fuse = fused_tail(c);
   if (!graphs_usable(c) || orth_now) {
     set_device_lambda(c, c->lambda);
-    int rc = enqueue_solve(c);
+    int rc = enqueue_solve(c, fuse);
     if (rc) return rc;
-    enqueue_update(c);
-    enqueue_chi2(c);
-    enqueue_scale(c);
+    if (fuse) enqueue_fused_tail(c);
+    else { enqueue_update(c); enqueue_chi2(c); enqueue_scale(c); }
     rc = reduce_trial_scalars(c, 2);
     if (!rc && sharded(c)) c->comm_warm = true;
     return rc;
@@ -942,11 +985,10 @@ int run_trial(b200_ctx* c) {
   const int saved = c->num_oplus_calls;
   auto body = [&]() -> int {
     B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 3, c->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    int rc = enqueue_solve(c);
+    int rc = enqueue_solve(c, fuse);
     if (rc) return rc;
-    enqueue_update(c);
-    enqueue_chi2(c);
-    enqueue_scale(c);
+    if (fuse) enqueue_fused_tail(c);
+    else { enqueue_update(c); enqueue_chi2(c); enqueue_scale(c); }
     return reduce_trial_scalars(c, 2);  // sharded: chi2 of the new state + LM scale, 2 doubles
   };
   int rc = run_captured(c, &c->graph_trial, &c->graph_trial_launches, body);
@@ -989,6 +1031,7 @@ int b200_create(int device, b200_ctx** out) {
   if (device < 0 || device >= n) { g_create_error = "invalid device index"; return B200_ERR_INVALID; }
   b200_ctx* c = new b200_ctx();
   c->device = device;
+  if (const char* e = getenv("G2O_B200_FUSE")) c->fuse_tail = atoi(e) != 0;  // 0: separate back-substitution / update / chi2 / scale kernels
   try {
     B200_CUDA(cudaSetDevice(device));
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1209,6 +1252,7 @@ int b200_update(b200_ctx* c) {
     NEED_DEVICE(c);
     NEED_STRUCTURE(c);
     B200_CUDA(cudaSetDevice(c->device));
+    c->state_chi2_valid = false;
     enqueue_update(c);
     return (int)B200_OK;
   });
@@ -1229,6 +1273,7 @@ int b200_pop(b200_ctx* c) {
     NEED_STRUCTURE(c);
     if (c->backup_depth < 1) return fail(c, B200_ERR_INVALID, "pop on an empty backup stack");
     B200_CUDA(cudaSetDevice(c->device));
+    c->state_chi2_valid = false;
     do_pop(c);
     c->backup_depth = 0;
     return (int)B200_OK;
@@ -1254,6 +1299,7 @@ int b200_set_robust_kernel(b200_ctx* c, int kind, double delta) {
   if (!c || kind < B200_ROBUST_NONE || kind > B200_ROBUST_DCS || !(delta > 0.0)) return B200_ERR_INVALID;
   c->robust.kind = kind;
   c->robust.delta = delta;
+  c->state_chi2_valid = false;
   if (!c->host_only) { cudaSetDevice(c->device); drop_graphs(c); }  // captured launches carry the kernel by value
   return B200_OK;
 }
@@ -1306,6 +1352,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
     if (algorithm == B200_GAUSS_NEWTON) {
       // core/optimization_algorithm_gauss_newton.cpp:50-93 (computeActiveErrors only caches edge errors there)
       set_device_lambda(c, 0.0);
+      c->state_chi2_valid = false;
       if ((rc = enqueue_build_system(c))) return rc;
       if ((rc = enqueue_solve(c))) return rc;
       enqueue_update(c);
@@ -1317,11 +1364,13 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
     }
     // ---- Levenberg-Marquardt: core/optimization_algorithm_levenberg.cpp:57-147
     const bool shard = sharded(c);
-    if ((rc = run_prologue(c))) return rc;
+    const bool know_chi2 = c->state_chi2_valid && iteration > 0;
+    c->state_chi2_valid = false;
+    if ((rc = run_prologue(c, !know_chi2))) return rc;
     if (iteration == 0 && (rc = enqueue_max_diag(c))) return rc;
     // sharded: chi2 of the current state is a partial sum here; the total arrives with the first trial's all-reduce
-    if (!shard || iteration == 0) sync_scalars(c);
-    double currentChi = shard ? 0.0 : c->h_scalars[0];
+    if (!know_chi2 && (!shard || iteration == 0)) sync_scalars(c);
+    double currentChi = know_chi2 ? c->state_chi2 : shard ? 0.0 : c->h_scalars[0];
     double tempChi = currentChi;
     if (iteration == 0) {
       c->lambda = c->user_lambda_init > 0 ? c->user_lambda_init : 1e-5 * c->h_scalars[2];
@@ -1334,7 +1383,7 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       do_push(c);
       if ((rc = run_trial(c))) return rc;
       sync_scalars(c);
-      if (shard && qmax == 0) currentChi = c->h_scalars[5];
+      if (shard && qmax == 0 && !know_chi2) currentChi = c->h_scalars[5];
       const bool ok2 = *c->h_status == 0;
       tempChi = c->h_scalars[0];
       if (!ok2) tempChi = DBL_MAX;
@@ -1357,6 +1406,8 @@ int b200_algorithm_solve(b200_ctx* c, int algorithm, int iteration, b200_iter_st
       qmax++;
     } while (rho < 0 && qmax < c->max_trials_after_failure && !(c->terminate && c->terminate(c->terminate_user)));
     c->last_chi2 = currentChi;
+    c->state_chi2 = currentChi;      // accepted: the trial's chi2; rejected: the backup was restored
+    c->state_chi2_valid = true;
     st->chi2 = currentChi;
     st->lambda = c->lambda;
     st->levenberg_iterations = qmax;
@@ -1446,6 +1497,7 @@ int b200_set_estimates(b200_ctx* c, int kind, const double* est) {
   return guarded(c, [&]() {
     NEED_DEVICE(c);
     NEED_STRUCTURE(c);
+    c->state_chi2_valid = false;
     if (kind == B200_VERTEX_SE3_EXPMAP || kind == B200_VERTEX_CAM) kind = ((kind == B200_VERTEX_SE3_EXPMAP) == (c->cam_model == 1)) ? B200_VERTEX_CAM : -1;
     const bool lm = kind == B200_VERTEX_XYZ;
     if ((!lm && kind != c->pose_kind) || (lm && !c->schur) || !est) return fail(c, B200_ERR_INVALID, "vertex kind not present");

@@ -75,6 +75,9 @@ struct b200_ctx {
   g2o_b200::DevBuf<double> d_stage_est;            // dense staging for host<->device estimate copies
   // scalars: [0] chi2 [1] scale (landmark part; sharded: + pose part) [2] maxdiag [3] lambda [4] scale (pose part)
   //          [5] sharded: chi2 before the trial, summed over the ranks [6] constant 0 [7] sharded: this rank's part of [5]
+  g2o_b200::DevBuf<double> d_partials2;  // block sums of the fused trial tail (landmark part of the LM scale)
+  int n_edges_free_lm = 0;               // observations of free landmarks (the device edge order lists them first)
+  bool fuse_tail = true;                 // BA trials: back-substitution + landmark update + chi2 + scale in one kernel
   g2o_b200::DevBuf<double> d_partials, d_scalars;
   double* h_scalars = nullptr;                     // pinned mirror of d_scalars (+ status as double)
   int* h_status = nullptr;
@@ -105,8 +108,14 @@ struct b200_ctx {
   g2o_b200::DevBuf<double> d_comm_diag;  // iteration 0: [Hpp diagonal partial sums | per-rank landmark maxima]
 
   // ---------------- CUDA graphs of the two launch-bound sequences of an LM iteration (single GPU, profiling off)
-  cudaGraphExec_t graph_prologue = nullptr, graph_trial = nullptr;
-  long long graph_prologue_launches = 0, graph_trial_launches = 0;
+  cudaGraphExec_t graph_prologue = nullptr, graph_trial = nullptr, graph_build = nullptr;
+  long long graph_prologue_launches = 0, graph_trial_launches = 0, graph_build_launches = 0;
+  // chi2 of the estimates currently on the device, when known: the last LM iteration ended with exactly this state
+  // (accepted trial: its chi2; rejected: the restored backup's), so the next iteration's computeActiveErrors pass
+  // (optimization_algorithm_levenberg.cpp:71-78) would recompute the same number bit for bit and is skipped.  Any
+  // call that changes estimates, edges or the robust kernel from outside invalidates it.
+  bool state_chi2_valid = false;
+  double state_chi2 = 0.0;
   bool use_graphs = true;
 
   // SparseOptimizer::terminate() (core/sparse_optimizer.h:189): polled between LM trials and between iterations
