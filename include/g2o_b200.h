@@ -190,7 +190,9 @@ int b200_get_bschur(b200_ctx* ctx, double* out);
  * factor it implies (css::lnz, linear_solver_csparse.h:292-293) */
 int b200_get_block_ordering(b200_ctx* ctx, int32_t* perm);   /* returns #blocks */
 int64_t b200_get_factor_nnz(b200_ctx* ctx);
-/* schedule facts, out[0..15] (out[12] = flops of one factorisation of the stored structure, out[13] = links of the tail
+/* schedule facts, out[0..23] (out[16] = 1 when the update plan uses the wide 96 x 72 tiles of the FP64 tensor path,
+ * out[17] = update work items, out[18] = flops their rectangular products execute, out[19] = scratch slots of split tiles,
+ * out[20..23] reserved; out[12] = flops of one factorisation of the stored structure, out[13] = links of the tail
  * chain - supernodes factored by the one-CTA chain kernel -, out[14] = their flops, out[15] reserved): #supernodes, #tasks, #levels, max panel rows, max panel cols, stored factor doubles,
  * #dataflow tasks of the factorisation kernel; Schur plan (0 without landmarks): #landmark ranges, #segments
  * (partial sums), #contributions (block products), #Hpl slots, shared-memory bytes of a range CTA */

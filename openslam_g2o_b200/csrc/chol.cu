@@ -275,17 +275,266 @@ __device__ void accumulate_items(const CholPlanDev& Q, const CholFlowDev& F, con
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// wide tiles (SymbolicFactor::wide): 96 rows x 72 columns = the whole width of a panel.  An update item multiplies up
+// to 96 x 72 rows of the source panel by up to 72 x 72 of its rows (10 flops per byte fetched from L2 instead of 6 for
+// the 48 x 48 tiles), and the product runs on the FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA), 12 warps = 4 row
+// groups x 3 column groups, every warp 3 x 3 fragments (24 x 24) in registers, 6 shared-memory fragment loads per 9
+// DMMAs.  The k range of an item is cut into two halves of 36 = one pipeline stage each; the copies (cp.async, 16
+// bytes) of the next stage - the second half, or the first half of the next item when its source supernode is already
+// complete - fly while the current one is multiplied: one CTA barrier per stage.
+// Operand layout in a stage: element (row, k) at k * ld + row with ld = 100 (A side) / 76 (B side), both = 4 mod 16, so
+// the 32 lanes of a fragment load (row = lane / 4, k = lane % 4) hit 32 different 8-byte bank pairs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWR = 96, kWC = 72;          // scalar rows / columns of a wide destination tile
+constexpr int kWLdA = 100, kWLdB = 76;
+constexpr int kWKH = 36;                   // k extent of a stage
+constexpr int kWStage = (kWLdA + kWLdB) * kWKH;
+constexpr int kWAccLd = 100;               // leading dimension of the accumulator tile in shared memory
+constexpr int kWMapInts = 2 * (kWR + kWC); // destination row / column of every product row / column, per item parity
+constexpr int kWideSmemDoubles = kWAccLd * kWC + 2 * kWStage + kWMapInts / 2;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// the cp.async copies of the NEXT stage.  A thread owns up to 9 of them: column k = warp + 12 (c / 3), 16-byte pair
+// j = lane + 32 (c % 3) of the A-side rows followed by the B-side rows.  They are issued one per k-step of the current
+// product: a burst of ~100 LDGSTS per stage ahead of the DMMAs keeps the warps in the LSU queue while the tensor pipe
+// idles (measured, tests/csrc/dmma_tile.cu: 5590 cycles per stage, against 4250 interleaved and a DMMA floor of 3888;
+// cp.async.bulk per column segment is slower still, 6450: 72 copies of 576-768 bytes per stage)
+struct WideCopy {
+  const double *srcA, *srcB;   // first row of the A / B side in column 0 of the stage
+  unsigned dst;                // shared address of the stage buffer
+  int rA, rAB, nk, Mk;         // pairs of the A side, of both sides; columns (0: nothing to copy); source column stride
+};
+__device__ __forceinline__ void wide_copy(const WideCopy& cp, int c, int warp, int lane) {
+  const int kk = c / 3, k = warp + 12 * kk, j = lane + 32 * (c - 3 * kk);
+  if (k < cp.nk && j < cp.rAB) {
+    const bool isA = j < cp.rA;
+    const double* src = (isA ? cp.srcA + 2 * j : cp.srcB + 2 * (j - cp.rA)) + (long long)k * cp.Mk;
+    const unsigned dst = cp.dst + 8u * (unsigned)(isA ? k * kWLdA + 2 * j : kWLdA * kWKH + k * kWLdB + 2 * (j - cp.rA));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  }
+}
+__device__ __forceinline__ void wide_copy_all(const WideCopy& cp, int warp, int lane) {
+#pragma unroll
+  for (int c = 0; c < 9; ++c) wide_copy(cp, c, warp, lane);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// one stage of an item's product: c (3 x 3 fragments of this warp) += A(24 x 4 ks) * B(24 x 4 ks)^T, ks <= 9
+template <bool FULL>
+__device__ __forceinline__ void wide_product(double (&c)[3][3][2], const double* __restrict__ Ap, const double* __restrict__ Bp,
+                                             int ks, unsigned mask, const WideCopy& cp, int warp, int lane) {
+#pragma unroll
+  for (int s = 0; s < 9; ++s) {
+    wide_copy(cp, s, warp, lane);
+    if (s < ks) {
+      const double a0 = Ap[0], a1 = Ap[8], a2 = Ap[16];
+      const double b0 = Bp[0], b1 = Bp[8], b2 = Bp[16];
+      if (FULL || (mask & 1u)) dmma_m8n8k4(c[0][0][0], c[0][0][1], a0, b0);
+      if (FULL || (mask & 8u)) dmma_m8n8k4(c[1][0][0], c[1][0][1], a1, b0);
+      if (FULL || (mask & 64u)) dmma_m8n8k4(c[2][0][0], c[2][0][1], a2, b0);
+      if (FULL || (mask & 2u)) dmma_m8n8k4(c[0][1][0], c[0][1][1], a0, b1);
+      if (FULL || (mask & 16u)) dmma_m8n8k4(c[1][1][0], c[1][1][1], a1, b1);
+      if (FULL || (mask & 128u)) dmma_m8n8k4(c[2][1][0], c[2][1][1], a2, b1);
+      if (FULL || (mask & 4u)) dmma_m8n8k4(c[0][2][0], c[0][2][1], a0, b2);
+      if (FULL || (mask & 32u)) dmma_m8n8k4(c[1][2][0], c[1][2][1], a1, b2);
+      if (FULL || (mask & 256u)) dmma_m8n8k4(c[2][2][0], c[2][2][1], a2, b2);
+      Ap += 4 * kWLdA;
+      Bp += 4 * kWLdB;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+struct WideItem {
+  int a0, nA, b0, nB, Mk, Nk;   // block row offsets (relative to the update's first row), scalar extents
+  const double* Kp;
+  const int* rel;
+};
+
 template <int D>
+__device__ __noinline__ void accumulate_items_wide(const CholPlanDev& Q, const CholFlowDev& F, const double* __restrict__ L, int w0, int w1,
+                                      int R0, int C0, double* __restrict__ acc, double* __restrict__ stg,
+                                      int* __restrict__ maps, int* s_nready /* [3] */) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mg = warp & 3, ng = warp >> 2, g = lane >> 2, q = lane & 3;
+  TCK_INIT;
+  __syncthreads();  // whoever used the shared bytes before (a panel factorisation of the same task) is done
+  for (int i = tid; i < kWAccLd * kWC; i += kCholThreads) acc[i] = 0.0;
+  if (w0 >= w1) { __syncthreads(); return; }
+
+  auto load_item = [&](int wi) {
+    WideItem it;
+    const int a0 = Q.work_a0[wi], a1 = Q.work_a1[wi], b0 = Q.work_b0[wi], b1 = Q.work_b1[wi];
+    it.a0 = a0; it.nA = (a1 - a0) * D; it.b0 = b0; it.nB = (b1 - b0) * D;
+    it.Mk = Q.work_mk[wi]; it.Nk = Q.work_nk[wi];
+    it.Kp = L + Q.work_koff[wi];
+    it.rel = Q.rel + Q.work_reloff[wi];
+    return it;
+  };
+  // warp 0: how many of the items wi, wi+1, ... (up to 32) have a complete source supernode; spin: until at least one
+  auto poll = [&](int wi, bool spin, int* out) {
+    const int idx = wi + lane;
+    const int K = idx < w1 ? F.work_ksn[idx] : -1;
+    const int target = K >= 0 ? F.sn_nchunk[K] : 0;
+    int lead;
+    unsigned spins = 0;
+    do {
+      if (++spins > kSpinLimit) __trap();
+      const bool ok = K < 0 || ld_acquire(F.chunk_done + K) >= target;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      lead = __ffs(~m) - 1;  // leading ready items; -1 when all 32 are
+      if (lead < 0) lead = 32;
+    } while (spin && lead == 0);
+    if (lane == 0) *out = wi + lead;
+  };
+  // copies of one stage: k columns [h * 36, ...) of both operand row blocks, the zero columns that pad k to a multiple
+  // of 4, and (first half) the destination maps of the item
+  // destination of my product row (tid < 96) / column (128 <= tid < 200) of an item: fetched one item ahead of the
+  // issue that stores it into the shared maps (a global load there would stall the issuing warps for an L2 / HBM round trip)
+  auto load_rel = [&](const WideItem& it) -> int {
+    if (tid < kWR) return tid < it.nA ? (it.rel[it.a0 + tid / D] - R0) * D + tid % D : -1;
+    const int cc = tid - 128;
+    if (cc >= 0 && cc < kWC) return cc < it.nB ? (it.rel[it.b0 + cc / D] - C0) * D + cc % D : -1;
+    return -1;
+  };
+  // one stage = k columns [h * 36, ...) of both operand row blocks: the copy descriptor, the zero columns that pad k to a
+  // multiple of 4, and (first half) the destination maps of the item.  The copies themselves: wide_copy
+  auto setup = [&](const WideItem& it, int wi, int h, int buf, int relv) -> WideCopy {
+    double* As = stg + buf * kWStage;
+    double* Bs = As + kWLdA * kWKH;
+    const int k0 = h * kWKH, nk = min(it.Nk - k0, kWKH);
+    WideCopy cp;
+    cp.rA = it.nA >> 1; cp.rAB = cp.rA + (it.nB >> 1);   // 16-byte pairs (D = 6: rows come in multiples of 48 bytes)
+    cp.srcA = it.Kp + (long long)it.a0 * D + (long long)k0 * it.Mk;
+    cp.srcB = it.Kp + (long long)it.b0 * D + (long long)k0 * it.Mk;
+    cp.dst = (unsigned)__cvta_generic_to_shared(As);
+    cp.nk = nk; cp.Mk = it.Mk;
+    if (nk & 3) {
+      const int pad = 4 - (nk & 3);
+      for (int i = tid; i < pad * (kWLdA + kWLdB); i += kCholThreads) {
+        const int kk = i / (kWLdA + kWLdB), r = i - kk * (kWLdA + kWLdB);
+        if (r < kWLdA) As[(nk + kk) * kWLdA + r] = 0.0;
+        else Bs[(nk + kk) * kWLdB + (r - kWLdA)] = 0.0;
+      }
+    }
+    if (h == 0) {
+      int* mp = maps + (wi & 1) * (kWR + kWC);
+      if (tid < kWR) mp[tid] = relv;
+      else if (tid >= 128 && tid < 128 + kWC) mp[kWR + tid - 128] = relv;
+    }
+    return cp;
+  };
+
+  int nready = w0;
+  if (warp == 0) poll(w0, true, s_nready + 2);
+  __syncthreads();
+  nready = s_nready[2];
+  TCK(0);
+  WideItem cur = load_item(w0), nxt = cur;
+  wide_copy_all(setup(cur, w0, 0, 0, load_rel(cur)), warp, lane);
+  int rel_nxt = -1;
+  if (w0 + 1 < w1) { nxt = load_item(w0 + 1); rel_nxt = load_rel(nxt); }
+  double c[3][3][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  int unit = 0;  // stages issued so far minus one: stage `unit` sits in buffer unit & 1
+  bool asked = false;
+  for (int wi = w0; wi < w1; ++wi) {
+    // fragments this warp needs for the item: inside the operands and not entirely above the diagonal of the update
+    unsigned mask = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int r0 = mg * 24 + 8 * i, c0 = ng * 24 + 8 * j;
+        const bool need = r0 < cur.nA && c0 < cur.nB && cur.a0 + min(r0 + 7, cur.nA - 1) / D >= cur.b0 + c0 / D;
+        mask |= (need ? 1u : 0u) << (3 * i + j);
+      }
+    const int nh = cur.Nk > kWKH ? 2 : 1;
+    bool next_issued = false;
+    for (int h = 0; h < nh; ++h, ++unit) {
+      const bool last = h == nh - 1;
+      const bool want_next = last && wi + 1 < w1;
+      TCK(7);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      TCK(13);
+      __syncthreads();  // stage `unit` has landed; every warp is done with stage unit-1 (and the scatter of item wi-1)
+      TCK(14);
+      if (asked) nready = max(nready, s_nready[(unit + 1) & 1]);   // the look taken during the previous stage
+      // one look (no spinning) at the completion counters of the next sources whenever the item after the next is not
+      // known to be complete: by warp 0 ahead of its share of this stage's product - its DMMAs then run while the
+      // other two warps of its sub-partition have finished theirs, the pipe stays busy - and read one stage later
+      asked = nready <= wi + 2 && nready < w1 && wi + 1 < w1;
+      if (asked && warp == 0) poll(max(nready, wi + 1), false, s_nready + (unit & 1));
+      WideCopy cp;
+      cp.nk = 0;  // nothing to copy
+      if (!last) cp = setup(cur, wi, 1, (unit + 1) & 1, -1);
+      else if (want_next && wi + 1 < nready) { cp = setup(nxt, wi + 1, 0, (unit + 1) & 1, rel_nxt); next_issued = true; }
+      TCK(11);
+      {
+        const double* Ap = stg + (unit & 1) * kWStage + q * kWLdA + mg * 24 + g;
+        const double* Bp = stg + (unit & 1) * kWStage + kWLdA * kWKH + q * kWLdB + ng * 24 + g;
+        const int ks = (min(cur.Nk - h * kWKH, kWKH) + 3) >> 2;
+        if (mask == 0x1ffu) wide_product<true>(c, Ap, Bp, ks, mask, cp, warp, lane);   // the common case in large fronts: no predicates
+        else if (mask) wide_product<false>(c, Ap, Bp, ks, mask, cp, warp, lane);
+        else wide_copy_all(cp, warp, lane);
+      }
+      TCK(12);
+    }
+    // the item's product leaves the registers: element (r, c) of it goes to (map[r], map[c]) of the tile
+    if (mask) {
+      const int* mp = maps + (wi & 1) * (kWR + kWC);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int r = mg * 24 + 8 * i + g;
+        const int tr = mp[r];
+        const int ab = cur.a0 + r / D;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (mask & (1u << (3 * i + j))) {
+            const int cc = ng * 24 + 8 * j + 2 * q;
+            const int t0 = mp[kWR + cc], t1 = mp[kWR + cc + 1];
+            if (tr >= 0 && t0 >= 0 && ab >= cur.b0 + cc / D) acc[tr + t0 * kWAccLd] += c[i][j][0];
+            if (tr >= 0 && t1 >= 0 && ab >= cur.b0 + (cc + 1) / D) acc[tr + t1 * kWAccLd] += c[i][j][1];
+          }
+          c[i][j][0] = c[i][j][1] = 0.0;
+        }
+      }
+    }
+    TCK(1);
+    if (wi + 1 < w1) {
+      if (!next_issued) {  // the next source was not complete when this item started: wait for it now
+        if (warp == 0) poll(wi + 1, true, s_nready + 2);
+        __syncthreads();
+        nready = max(nready, s_nready[2]);
+        TCK(0);
+        wide_copy_all(setup(nxt, wi + 1, 0, unit & 1, rel_nxt), warp, lane);
+      }
+      cur = nxt;
+      if (wi + 2 < w1) { nxt = load_item(wi + 2); rel_nxt = load_rel(nxt); }
+    }
+  }
+  __syncthreads();
+}
+
+template <int D, bool WIDE>
 __device__ void subtract_tile(const CholDev& P, const CholPlanDev& Q, double* __restrict__ L, int tile,
                               const double* __restrict__ acc) {
+  constexpr int TR = WIDE ? kWR : kTile, TC = WIDE ? kWC : kTile, LD = WIDE ? kWAccLd : kTile;
   const int J = Q.tile_sn[tile], R0 = Q.tile_r0[tile], C0 = Q.tile_c0[tile];
   const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
   double* Pj = L + P.sn_lptr[J];
-  const int rows = min(kTile, M - R0 * D), cols = min(kTile, N - C0 * D);
+  const int rows = min(TR, M - R0 * D), cols = min(TC, N - C0 * D);
   for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
     const int c = i / rows, r = i - c * rows;
     double* p = Pj + ((long long)(R0 * D + r) + (long long)(C0 * D + c) * M);
-    __stcg(p, __ldcg(p) - acc[r + c * kTile]);
+    __stcg(p, __ldcg(p) - acc[r + c * LD]);
   }
 }
 
@@ -592,18 +841,24 @@ __device__ __noinline__ void factor_chunk(const CholDev& P, const CholPlanDev& Q
   chunk_store<D>(G, Q, Sm, Ldiag, Dinv, first, z, contrib, chunk_done);
 }
 
-template <int D>
+template <int D, bool WIDE>
 __global__ void __launch_bounds__(kCholThreads, 1)
 chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant__ CholPlanDev Q,
                         const __grid_constant__ CholFlowDev F, double* __restrict__ L, double* __restrict__ Ldiag,
                         double* __restrict__ Dinv, int* status, const double* __restrict__ y, double* __restrict__ z,
                         double* contrib) {
   extern __shared__ __align__(16) double smem[];  // update operands and factor staging share the same bytes
-  __shared__ int s_task, s_nready;
+  __shared__ int s_task, s_nready[3];
+  constexpr int TR = WIDE ? kWR : kTile, TC = WIDE ? kWC : kTile, LD = WIDE ? kWAccLd : kTile;
   double* acc = smem;
-  double* As = smem + kTile * kTile;
+  double* As = smem + (WIDE ? kWAccLd * kWC : kTile * kTile);   // wide: the two operand stages
   double* Bs = As + kTile * kMaxPanelCols;
+  int* maps = reinterpret_cast<int*>(As + 2 * kWStage);         // wide only
   const int tid = threadIdx.x;
+  auto accumulate = [&](int w0, int w1, int R0, int C0) {
+    if constexpr (WIDE) accumulate_items_wide<D>(Q, F, L, w0, w1, R0, C0, acc, As, maps, s_nready);
+    else accumulate_items<D>(Q, F, L, w0, w1, R0, C0, acc, As, Bs, s_nready);
+  };
   for (;;) {
     __syncthreads();
     if (tid == 0) s_task = atomicAdd(F.next_task, 1);
@@ -616,13 +871,14 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
       const int slot = F.g_slot[arg];
       const int J = Q.tile_sn[tile], R0 = Q.tile_r0[tile], C0 = Q.tile_c0[tile];
       // this task is the only writer of its tile: the values it will subtract from (A + lambda I, scattered by the
-      // previous kernels) are fetched before the updates are even complete
-      constexpr int kPer = (kTile * kTile + kCholThreads - 1) / kCholThreads;
+      // previous kernels) are fetched before the updates are even complete (narrow tiles: a group is a few
+      // microseconds; a wide group runs for tens of microseconds and reads them at the end)
+      constexpr int kPer = WIDE ? 1 : (kTile * kTile + kCholThreads - 1) / kCholThreads;
       double old[kPer];
       const int M = P.sn_nrow[J] * D, N = P.sn_ncol[J] * D;
-      const int rows = min(kTile, M - R0 * D), cols = min(kTile, N - C0 * D);
+      const int rows = min(TR, M - R0 * D), cols = min(TC, N - C0 * D);
       double* Pt = L + P.sn_lptr[J] + ((long long)R0 * D + (long long)C0 * D * M);
-      if (slot < 0) {
+      if (!WIDE && slot < 0) {
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
           const int i = tid + q * kCholThreads;
@@ -630,39 +886,47 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
           old[q] = i < rows * cols ? __ldcg(Pt + (r + (long long)c * M)) : 0.0;
         }
       }
-      accumulate_items<D>(Q, F, L, F.g_w0[arg], F.g_w1[arg], R0, C0, acc, As, Bs, &s_nready);
+      accumulate(F.g_w0[arg], F.g_w1[arg], R0, C0);
       STAMP_MAX(4, J);
       if (slot < 0) {
+        if constexpr (WIDE) {
+          subtract_tile<D, true>(P, Q, L, tile, acc);
+        } else {
 #pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-          const int i = tid + q * kCholThreads;
-          const int c = i / rows, r = i - c * rows;
-          if (i < rows * cols) __stcg(Pt + (r + (long long)c * M), old[q] - acc[r + c * kTile]);
+          for (int q = 0; q < kPer; ++q) {
+            const int i = tid + q * kCholThreads;
+            const int c = i / rows, r = i - c * rows;
+            if (i < rows * cols) __stcg(Pt + (r + (long long)c * M), old[q] - acc[r + c * kTile]);
+          }
         }
         cta_signal(F.upd_done + J);
         STAMP_MAX(2, J);
       } else {
-        double* out = F.scratch + (long long)slot * kTile * kTile;
-        for (int i = tid; i < kTile * kTile; i += blockDim.x) __stcg(out + i, acc[i]);
+        double* out = F.scratch + (long long)slot * TR * TC;
+        for (int i = tid; i < TR * TC; i += blockDim.x) {
+          const int c = i / TR, r = i - c * TR;
+          __stcg(out + i, acc[r + c * LD]);
+        }
         // split tile: whichever group arrives last adds the partial sums in group order and subtracts once
         const int rt = F.group_rtile[arg];
         const int ns = F.r_nslots[rt];
         __syncthreads();
         if (tid == 0) {
           __threadfence();
-          s_nready = atomicAdd(F.slot_done + rt, 1) == ns - 1;
+          s_nready[0] = atomicAdd(F.slot_done + rt, 1) == ns - 1;
           __threadfence();
         }
         __syncthreads();
-        if (s_nready) {
-          const double* in = F.scratch + (long long)F.r_slot0[rt] * kTile * kTile;
-          for (int i = tid; i < kTile * kTile; i += blockDim.x) {
+        if (s_nready[0]) {
+          const double* in = F.scratch + (long long)F.r_slot0[rt] * TR * TC;
+          for (int i = tid; i < TR * TC; i += blockDim.x) {
             double s = 0.0;
-            for (int g = 0; g < ns; ++g) s += __ldcg(in + ((long long)g * kTile * kTile + i));
-            acc[i] = s;
+            for (int g = 0; g < ns; ++g) s += __ldcg(in + ((long long)g * TR * TC + i));
+            const int c = i / TR, r = i - c * TR;
+            acc[r + c * LD] = s;
           }
           __syncthreads();
-          subtract_tile<D>(P, Q, L, tile, acc);
+          subtract_tile<D, WIDE>(P, Q, L, tile, acc);
           cta_signal(F.upd_done + Q.tile_sn[tile]);
         }
       }
@@ -676,8 +940,8 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
         for (int tile = Q.sn_tile_ptr[J]; tile < Q.sn_tile_ptr[J + 1]; ++tile) {
           const int w0 = Q.tile_work_ptr[tile], w1 = Q.tile_work_ptr[tile + 1];
           if (w0 == w1) continue;
-          accumulate_items<D>(Q, F, L, w0, w1, Q.tile_r0[tile], Q.tile_c0[tile], acc, As, Bs, &s_nready);
-          subtract_tile<D>(P, Q, L, tile, acc);
+          accumulate(w0, w1, Q.tile_r0[tile], Q.tile_c0[tile]);
+          subtract_tile<D, WIDE>(P, Q, L, tile, acc);
           __syncthreads();
         }
         const int c0 = Q.sn_chunk_ptr[J], c1 = Q.sn_chunk_ptr[J + 1];
@@ -838,7 +1102,8 @@ constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per CTA minus the static shar
 // so that contexts with different panel sizes on one device cannot lower it under each other.
 template <int D>
 void set_smem_attrs() {
-  B200_CUDA(cudaFuncSetAttribute(chol_factor_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  B200_CUDA(cudaFuncSetAttribute(chol_factor_flow_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  if (D == 6) B200_CUDA(cudaFuncSetAttribute(chol_factor_flow_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_backward_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   B200_CUDA(cudaFuncSetAttribute(chol_chain_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -919,7 +1184,7 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_L_.alloc((size_t)S_.factor_doubles);
   d_Dinv_.alloc((size_t)S_.dinv_doubles);
   d_Ldiag_.alloc((size_t)S_.dinv_doubles);
-  d_gscratch_.alloc((size_t)std::max(S_.max_group_slots, 1) * kTile * kTile);
+  d_gscratch_.alloc((size_t)std::max(S_.max_group_slots, 1) * (S_.wide ? kWR * kWC : kTile * kTile));
   d_contrib_.alloc((size_t)std::max<int64_t>(S_.sn_cptr[S_.nsn], 1));
   d_y_.alloc((size_t)nb * d);
   d_z_.alloc((size_t)nb * d);
@@ -933,7 +1198,7 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   // shared memory of the two persistent kernels
   const int Nmax = S_.max_ncol * d;
   const size_t factor_doubles = (size_t)Nmax * d * kLds + d * d + d + (size_t)Nmax * Nmax;
-  flow_smem_ = std::max((size_t)kUpdateSmemDoubles, factor_doubles) * sizeof(double);
+  flow_smem_ = std::max((size_t)(S_.wide ? kWideSmemDoubles : kUpdateSmemDoubles), factor_doubles) * sizeof(double);
   xb_doubles_ = (S_.max_nrow * d + 1) & ~1;
   stage_doubles_ = (int)((kMaxDynSmem - 1024) / sizeof(double)) - xb_doubles_ - kMaxPanelCols;
   if (!host_only_flag()) {
@@ -944,8 +1209,9 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
     int dev = 0, sms = 0, occ = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (d == 3) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<3>, kCholThreads, flow_smem_));
-    else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<6>, kCholThreads, flow_smem_));
+    if (d == 3) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<3, false>, kCholThreads, flow_smem_));
+    else if (S_.wide) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<6, true>, kCholThreads, flow_smem_));
+    else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_factor_flow_kernel<6, false>, kCholThreads, flow_smem_));
     flow_grid_ = std::max(1, std::min((int)S_.flow_kind.size(), sms * std::max(occ, 1)));
     back_grid_ = std::max(1, std::min(ntask, sms));
     if (const char* e = getenv("G2O_B200_FLOW_GRID")) flow_grid_ = std::max(1, std::min(flow_grid_, atoi(e)));
@@ -993,8 +1259,12 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
                   d_group_w0_.p, d_group_w1_.p, d_group_slot_.p, d_rtile_tile_.p, d_rtile_slot0_.p, d_rtile_nslots_.p,
                   d_gscratch_.p};
     if (!S.flow_kind.empty()) {
-      chol_factor_flow_kernel<D><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2,
-                                                                              d_y_.p, d_z_.p, d_contrib_.p);
+      if constexpr (D == 6) {
+        if (S.wide) chol_factor_flow_kernel<6, true><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
+        else chol_factor_flow_kernel<6, false><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
+      } else {
+        chol_factor_flow_kernel<D, false><<<flow_grid_, kCholThreads, flow_smem_, s>>>(P, Q, F, L, d_Ldiag_.p, d_Dinv_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
+      }
       count();
     }
   }

@@ -98,6 +98,7 @@ int b200_ls_solve(b200_linear_solver* ls, int nblocks, int block_dim, const int3
       SymbolicOptions opt;
       if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));  // see b200_set_ordering
       if (const char* e = getenv("G2O_B200_CHAIN")) opt.chain = atoi(e) != 0;
+      if (const char* e = getenv("G2O_B200_WIDE_TILES")) opt.wide_tiles = atoi(e);
       ls->chol.analyze(nblocks, block_dim, colptr, rowidx, opt, s);
       ls->nb = nblocks; ls->d = block_dim; ls->nblk = nblk;
     }

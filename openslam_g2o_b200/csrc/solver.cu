@@ -637,6 +637,10 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_GROUP_ITEMS")) opt.group_items = std::max(1, atoi(e));
   if (const char* e = getenv("G2O_B200_SORT_ITEMS")) opt.sort_items_by_level = atoi(e) != 0;
   if (const char* e = getenv("G2O_B200_RELAX_FRAC")) opt.relax_frac = atof(e);
+  if (const char* e = getenv("G2O_B200_WIDE_TILES")) opt.wide_tiles = atoi(e);
+  if (const char* e = getenv("G2O_B200_SUBTREE_MAX_FLOPS")) opt.subtree_max_flops = atof(e);
+  if (const char* e = getenv("G2O_B200_GROUP_SLACK")) opt.group_slack = atoi(e);
+  if (const char* e = getenv("G2O_B200_GROUPS_ASAP")) opt.groups_asap = atoi(e) != 0;   // -1 auto (by flops), 0 off, 1 on
   opt.nd_levels = c->nd_levels;
   if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
@@ -1587,6 +1591,16 @@ int b200_get_factor_info(b200_ctx* c, int64_t* out) {
   out[6] = (int64_t)S.flow_kind.size();
   out[12] = (int64_t)S.flops;
   out[13] = (int64_t)S.chain_sn.size(); out[14] = (int64_t)S.chain_flops; out[15] = 0;
+  // out[16..]: update plan of the factorisation: tile geometry, work items, flops the items execute (incl. the parts
+  // of their rectangular products that fall above the diagonal)
+  out[20] = (int64_t)S.subtree_flops;
+  out[16] = S.wide ? 1 : 0; out[17] = (int64_t)S.work_u.size(); out[19] = S.max_group_slots;
+  {
+    double ex = 0;
+    for (size_t q = 0; q < S.work_u.size(); ++q)
+      ex += 2.0 * (S.work_a1[q] - S.work_a0[q]) * S.d * (double)((S.work_b1[q] - S.work_b0[q]) * S.d) * S.work_nk[q];
+    out[18] = (int64_t)ex;
+  }
   out[7] = c->sr_n; out[8] = c->sr_nseg; out[9] = c->sr_ncontrib; out[10] = c->n_hpl; out[11] = c->sr_n > 0 ? (int64_t)schur_range_smem(c) : 0;
   return B200_OK;
 }

@@ -348,13 +348,17 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     sub[s] += work[s];
     if (S.sn_parent[s] >= 0) sub[S.sn_parent[s]] += sub[s];
   }
-  const double thresh = std::max(S.flops * opt.subtree_work_fraction, opt.subtree_min_flops);
+  // (the cap: one CTA runs a subtree task sequentially at a few tens of GFLOP/s - beyond ~1 ms per task the CTAs that
+  // finish their subtrees early wait for the stragglers; above it the supernodes are split into GROUP / CHUNK tasks)
+  const double thresh = std::min(std::max(S.flops * opt.subtree_work_fraction, opt.subtree_min_flops),
+                                 std::max(opt.subtree_max_flops, opt.subtree_min_flops));
+  S.subtree_flops = 0;
   // task id per supernode: a maximal subtree with sub <= thresh becomes one task (rooted at `root`)
   std::vector<int> root(ns, -1);
   for (int s = ns - 1; s >= 0; --s) {
     int p = S.sn_parent[s];
     if (p >= 0 && root[p] >= 0) root[s] = root[p];                 // inside a subtree task
-    else if (sub[s] <= thresh) root[s] = s;                        // new subtree task rooted here
+    else if (sub[s] <= thresh) { root[s] = s; S.subtree_flops += sub[s]; }   // new subtree task rooted here
     else root[s] = -1;                                             // own task, level-scheduled
   }
   std::vector<int> task_of(ns, -1);
@@ -452,22 +456,28 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   }
 
   // ---- 9. numeric plan: destination tiles + their work items, row chunks, level kinds
-  const int TB = std::max(1, 48 / d);
+  // narrow (default): 48 x 48 scalars, DFMA register tiles.  wide (d = 6, throughput-bound factorisations): 96 rows x
+  // the whole panel width (72 columns) - one column tile per panel, operands of an update item are 96 x 72 and 72 x 72
+  // (10 flops per byte fetched from L2 instead of 6) and the product runs on the FP64 tensor path (chol.cu)
+  S.wide = d == 6 && (opt.wide_tiles > 0 || (opt.wide_tiles < 0 && S.flops >= opt.wide_min_flops));
+  const int TB = S.wide ? 16 : std::max(1, 48 / d);   // block rows of a tile
+  const int TBC = S.wide ? 12 : TB;                   // block columns of a tile
   // a chunk CTA maps block rows to the 32 lanes of a warp: diagonal block + chunk rows + the right-hand-side row
   auto chunk_cap = [&](int J) { return 31 - S.sn_ncol[J]; };
   S.tile_blocks = TB;
+  S.tile_blocks_c = TBC;
   S.chunk_blocks = 30;
   S.sn_tile_ptr.assign(ns + 1, 0);
   std::vector<std::vector<int>> tile_lookup(ns);  // [tr * nct + tc] -> tile id or -1
   std::vector<int> sn_nct(ns, 0);
   for (int J = 0; J < ns; ++J) {
-    const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = (S.sn_ncol[J] + TB - 1) / TB;
+    const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = (S.sn_ncol[J] + TBC - 1) / TBC;
     sn_nct[J] = nct;
     tile_lookup[J].assign((size_t)ntr * nct, -1);
     for (int tr = 0; tr < ntr; ++tr)
-      for (int tc = 0; tc < nct && tc <= tr; ++tc) {
+      for (int tc = 0; tc < nct && tc * TBC <= tr * TB + TB - 1; ++tc) {  // tiles that touch the lower triangle
         tile_lookup[J][(size_t)tr * nct + tc] = (int)S.tile_sn.size();
-        S.tile_sn.push_back(J); S.tile_r0.push_back(tr * TB); S.tile_c0.push_back(tc * TB);
+        S.tile_sn.push_back(J); S.tile_r0.push_back(tr * TB); S.tile_c0.push_back(tc * TBC);
       }
     S.sn_tile_ptr[J + 1] = (int)S.tile_sn.size();
   }
@@ -485,7 +495,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         fill.assign(S.tile_work_ptr.begin(), S.tile_work_ptr.end() - 1);
       }
       parallel_ranges((size_t)ns, range_count((size_t)ns, 256), [&](int, size_t Jb, size_t Je) {
-      std::vector<int> bound;
+      std::vector<int> bound, cbound;
       for (int J = (int)Jb; J < (int)Je; ++J) {
         const int ntr = (S.sn_nrow[J] + TB - 1) / TB, nct = sn_nct[J];
         for (int u = S.upd_ptr[J]; u < S.upd_ptr[J + 1]; ++u) {
@@ -499,14 +509,21 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
             while (a < h && rel[a] < t * TB) ++a;
             bound[t] = a;
           }
+          cbound.assign(nct + 1, h);  // cbound[t] = first a with rel[a] >= t*TBC
+          a = 0;
+          for (int t = 0; t <= nct; ++t) {
+            while (a < h && rel[a] < t * TBC) ++a;
+            cbound[t] = a;
+          }
           for (int tc = 0; tc < nct; ++tc) {
-            const int b0 = std::min(bound[tc], w), b1 = std::min(bound[tc + 1], w);
+            const int b0 = std::min(cbound[tc], w), b1 = std::min(cbound[tc + 1], w);
             if (b0 >= b1) continue;
-            for (int tr = tc; tr < ntr; ++tr) {
+            for (int tr = 0; tr < ntr; ++tr) {
               const int a0 = bound[tr], a1 = bound[tr + 1];
               if (a0 >= a1) continue;
               if (a1 - 1 < b0) continue;  // entirely above the diagonal of the update
               const int t = tile_lookup[J][(size_t)tr * nct + tc];
+              if (t < 0) continue;        // (cannot happen: a row >= column entry lies in a tile touching the lower triangle)
               if (pass == 0) S.tile_work_ptr[t + 1]++;
               else { int q = fill[t]++; S.work_u[q] = u; S.work_a0[q] = a0; S.work_a1[q] = a1; S.work_b0[q] = b0; S.work_b1[q] = b1; }
             }
@@ -627,6 +644,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
   S.task_on_chain.assign(nt, 0);
   for (int t = 0; t < nt; ++t)
     if (S.task_ptr[t + 1] - S.task_ptr[t] == 1 && S.sn_on_chain[S.task_sn[S.task_ptr[t]]]) S.task_on_chain[t] = 1;
+  std::vector<int> group_level;  // per group: the level it is listed at
   for (int l = 0; l < S.nlevels; ++l) {
     // chain links are left to the chain kernel: the level keeps only the GROUP tasks that bring them the updates of
     // the supernodes below the chain
@@ -653,9 +671,24 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
           if (w1 == w0) continue;
           const int ng = (w1 - w0 + S.group_items - 1) / S.group_items;
           S.sn_nupd[J]++;
+          // a group is listed as early as its sources allow: one level above the latest of them (as-soon-as-possible),
+          // not at the level of its destination - when the factorisation reaches the top of the tree, where a level is
+          // one or two panels, only the groups that really depend on the previous level are left
+          // ... plus `group_slack` levels (default 0).  Inside a level the groups whose sources are two or more levels
+          // back come first (ready when taken), then the groups that need the level just below (key 2 l + 1), then the
+          // level's panel factorisations.  Measured on the 90k / 250k-pose spheres: as-soon-as-possible listing is worth
+          // 2 %, one or two levels of slack cost 5 % - what the CTAs really waited for were the SUBTREE tasks (step 8)
+          auto asap = [&](int g0, int g1) {
+            if (!opt.groups_asap) return 2 * l + 1;
+            int m = -1;
+            for (int w = g0; w < g1; ++w) m = std::max(m, tlevel[task_of[S.upd_k[S.work_u[w]]]]);
+            const int lv = std::min(l, m + 1 + std::max(0, opt.group_slack));
+            return 2 * lv + (m == lv - 1 ? 1 : 0);
+          };
           if (ng == 1) {
             S.group_tile.push_back(q); S.group_w0.push_back(w0); S.group_w1.push_back(w1); S.group_slot.push_back(-1);
             S.group_rtile.push_back(-1);
+            group_level.push_back(asap(w0, w1));
           } else {
             S.rtile_tile.push_back(q); S.rtile_slot0.push_back(slots); S.rtile_nslots.push_back(ng);
             for (int gi = 0; gi < ng; ++gi) {
@@ -664,6 +697,7 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
               S.group_w0.push_back(w0 + (int)((long long)(w1 - w0) * gi / ng));
               S.group_w1.push_back(w0 + (int)((long long)(w1 - w0) * (gi + 1) / ng));
               S.group_slot.push_back(slots++);
+              group_level.push_back(asap(S.group_w0.back(), S.group_w1.back()));
             }
           }
         }
@@ -675,6 +709,20 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
     S.level_chunk_ptr[l + 1] = (int)S.level_chunks.size();
     S.level_group_ptr[l + 1] = (int)S.group_tile.size();
     S.level_rtile_ptr[l + 1] = (int)S.rtile_tile.size();
+  }
+  {  // groups bucketed by their listing key 2 * level + (needs the level just below) (stable: creation order inside a bucket)
+    const int ngp = (int)S.group_tile.size();
+    std::vector<int> cnt(2 * S.nlevels + 1, 0), idx(ngp);
+    for (int g = 0; g < ngp; ++g) cnt[group_level[g] + 1]++;
+    for (int l = 0; l < 2 * S.nlevels; ++l) cnt[l + 1] += cnt[l];
+    for (int l = 0; l <= S.nlevels; ++l) S.level_group_ptr[l] = cnt[2 * l];
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int g = 0; g < ngp; ++g) idx[fill[group_level[g]]++] = g;
+    for (std::vector<int>* arr : {&S.group_tile, &S.group_w0, &S.group_w1, &S.group_slot, &S.group_rtile}) {
+      std::vector<int> tmp(ngp);
+      for (int g = 0; g < ngp; ++g) tmp[g] = (*arr)[idx[g]];
+      arr->swap(tmp);
+    }
   }
   // ---- 10. dataflow task list (level-major; inside a split level: groups, then chunks; the reduction of a split
   //          tile is done by whichever of its groups finishes last)

@@ -18,15 +18,22 @@ struct SymbolicOptions {
                                     // and <= 12 blocks: the panel factorisation maps one warp per block column)
   double subtree_work_fraction = 1.0 / 1024;  // subtree tasks: at most this share of the total work
   double subtree_min_flops = 5.0e5;           // ... but never split below what one CTA does in ~10 us
+  double subtree_max_flops = 2.0e7;           // ... and never more than this per task (large graphs; measured: 90k-pose sphere 76.8 -> 59.9 ms)
   bool relax = true;
   double relax_frac = 0.25;         // relaxed amalgamation: accepted share of explicit zeros up to one panel width
   bool sort_items_by_level = true;  // tile work items ordered by the task level of their source supernode
+  bool groups_asap = true;          // a split-K group is listed one level above its latest source, not at its destination's level
+  int group_slack = 0;              // ... plus this many levels (see symbolic.cpp; measured: 1 or 2 levels of slack are 5 % slower)
   int group_items = 16;             // split-K: work items per group task (4 / 8 / 16 measured: 16 best with level-sorted items)
   // 0 (default): the reference's ordering - block AMD, bit-exact with cs_amd.  k > 0: nested dissection with 2^k parts
   // on top of it (nested_dissection.cpp): separators first cut band-like systems, whose AMD elimination tree is one
   // long chain, into independent subtrees; AMD orders the parts and the separators
   int nd_levels = 0;
   int nd_min_part = 24;             // parts smaller than this many blocks are not cut further
+  // destination tiles of the update plan: 0 = 48 x 48 (latency-bound factorisations: Venice, sphere2500), 1 = 96 x 72
+  // with the products on the FP64 tensor path (DMMA), -1 = by the factorisation's flop count (d = 6 only)
+  int wide_tiles = -1;
+  double wide_min_flops = 2.0e10;
   // set when the caller already knows the ordering (tests); empty = run block AMD
   std::vector<int> given_perm;
   // tail chain (chol.cu: chol_chain_kernel): the last stretch of the elimination tree - the path from some supernode up
@@ -68,12 +75,15 @@ struct SymbolicFactor {
   int nlevels = 0;
   int64_t factor_doubles = 0;
   double flops = 0;  // factorisation flops of the stored (relaxed) structure
+  double subtree_flops = 0;  // ... of which inside SUBTREE tasks (one CTA each)
   int max_nrow = 0, max_ncol = 0;
 
   // ---- numeric plan of the GPU kernels (chol.cu)
   // destination tiles: a panel is cut into tile_blocks x tile_blocks block tiles (48 x 48 scalars); only tiles that
   // touch the lower triangle exist.  Each tile owns the list of update pieces (work items) that land in it.
-  int tile_blocks = 0;
+  int tile_blocks = 0;                             // block rows of a tile
+  int tile_blocks_c = 0;                           // block columns of a tile (= tile_blocks unless wide)
+  bool wide = false;                               // 96 x 72 tiles + FP64 tensor-path products (SymbolicOptions::wide_tiles)
   std::vector<int> sn_tile_ptr;                    // nsn+1
   std::vector<int> tile_sn, tile_r0, tile_c0;      // supernode, first local block row / block column
   std::vector<int> tile_work_ptr;                  // ntiles+1

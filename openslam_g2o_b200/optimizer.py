@@ -242,11 +242,12 @@ class SolverContext:
         return int(lib.b200_get_factor_nnz(self._h))
 
     def factor_info(self):
-        out = np.zeros(16, np.int64)
+        out = np.zeros(24, np.int64)
         _check(lib.b200_get_factor_info(self._h, L.ptr(out)), self._h)
         return dict(zip(("supernodes", "tasks", "levels", "max_panel_rows", "max_panel_cols", "factor_doubles",
                          "flow_tasks", "schur_ranges", "schur_segments", "schur_contributions", "hpl_slots",
-                         "schur_range_smem", "factor_flops", "chain_links", "chain_flops"), (int(v) for v in out)))
+                         "schur_range_smem", "factor_flops", "chain_links", "chain_flops", "reserved", "wide_tiles",
+                         "update_items", "update_item_flops", "split_tile_slots", "subtree_flops"), (int(v) for v in out)))
 
     def launch_count(self):
         return int(lib.b200_get_launch_count(self._h))

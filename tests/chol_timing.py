@@ -5,7 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import openslam_g2o_b200 as g
 from openslam_g2o_b200 import synth
 wl = sys.argv[1] if len(sys.argv) > 1 else "venice"
-p = synth.venice_like() if wl == "venice" else synth.sphere()
+if wl.startswith("sphere") and len(wl) > 6:
+    n = int(wl[6:]); p = synth.sphere(n, n, seed=n * n)   # config-5 family: n x n poses
+else:
+    p = synth.venice_like() if wl == "venice" else synth.sphere()
 opt = g.SparseOptimizer(device=0); opt.set_algorithm("lm_fix6_3"); synth.feed(p, opt); opt.setup_cli(); opt.initialize_optimization()
 opt.optimize(2)
 out = (C.c_ulonglong * 32)()
@@ -14,12 +17,15 @@ ctx.build_system(); ctx.set_lambda(1e-3)
 stamps = (C.c_ulonglong * (6 * 4096))()
 ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1); g.lib.b200_debug_chol_stamps(stamps, 1)
 ctx.solve(); ctx.synchronize(); g.lib.b200_debug_chol_timing(out, 1); g.lib.b200_debug_chol_stamps(stamps, 1)
-names = ["item wait", "item compute", "chunk panel load", "chunk factor", "chunk signal", "chunk inverse", "chunk wait", "rtile wait", "chunk rhs gather", "chunk stores", "chunk contrib", "item staging", "item product"]
+names = ["item wait", "item compute", "chunk panel load", "chunk factor", "chunk signal", "chunk inverse", "chunk wait", "wide: poll", "chunk rhs gather", "chunk stores", "chunk contrib", "item staging", "item product", "wide: own copies landed", "wide: stage barrier", "-"]
 print(wl, "one factorisation, thread 0 of every CTA: total cycles, events, cycles/event (us at 1.965 GHz)")
 for i, n in enumerate(names):
     c, k = out[i], out[16 + i]
     print("  %-14s %12d %7d %10.0f  (%.2f us)" % (n, c, k, c / max(k, 1), c / max(k, 1) / 1965.0))
+tot = sum(out[i] for i in (0, 11, 12, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10))
 print(ctx.factor_info())
+ctx.set_profiling(True); ctx.solve(); ctx.synchronize(); ph = ctx.phase_times(); ctx.set_profiling(False)
+print({k: round(1e3 * v[0], 3) for k, v in ph.items() if v[1] > 0})
 
 import numpy as np
 st = np.array(list(stamps), dtype=np.uint64).reshape(6, 4096).astype(np.float64)

@@ -14,9 +14,10 @@ using namespace g2o_b200;
 
 static int g_nd_levels = 0;
 static double g_relax_frac = 0.25;
-static int g_chain = 1, g_chain_min_links = 3, g_chain_max_rows = 31;
+static int g_chain = 1, g_chain_min_links = 3, g_chain_max_rows = 31, g_wide = -1;
+extern "C" void hx_set_wide(int w) { g_wide = w; }
 extern "C" void hx_set_chain(int on, int min_links, int max_rows) { g_chain = on; g_chain_min_links = min_links; g_chain_max_rows = max_rows; }
-static void apply_chain_options(SymbolicOptions& o) { o.chain = g_chain != 0; o.chain_min_links = g_chain_min_links; o.chain_max_rows = g_chain_max_rows; }
+static void apply_chain_options(SymbolicOptions& o) { o.chain = g_chain != 0; o.chain_min_links = g_chain_min_links; o.chain_max_rows = g_chain_max_rows; o.wide_tiles = g_wide; }
 extern "C" void hx_set_nd_levels(int k) { g_nd_levels = k; }
 extern "C" void hx_set_relax_frac(double f) { g_relax_frac = f; }
 extern "C" int hx_block_amd(int n, const int* cp, const int* ri, int* perm) {
@@ -58,12 +59,12 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
     const int M = S.sn_nrow[J] * d, N = S.sn_ncol[J] * d;
     const int* jrows = S.sn_rows.data() + S.sn_rowptr[J];
     // the GPU's update plan: destination tiles, each with its ordered list of work items
-    const int TB = S.tile_blocks;
+    const int TB = S.tile_blocks, TBC = S.tile_blocks_c;
     for (int tile = S.sn_tile_ptr[J]; tile < S.sn_tile_ptr[J + 1]; ++tile) {
       if (S.tile_sn[tile] != J) return -5;
       const int R0 = S.tile_r0[tile], C0 = S.tile_c0[tile];
-      std::vector<double> acc((size_t)TB * d * TB * d, 0.0);
-      const int TS = TB * d;
+      std::vector<double> acc((size_t)TB * d * TBC * d, 0.0);
+      const int TS = TB * d, TSC = TBC * d;
       for (int wi = S.tile_work_ptr[tile]; wi < S.tile_work_ptr[tile + 1]; ++wi) {
         const int u = S.work_u[wi];
         if (u < S.upd_ptr[J] || u >= S.upd_ptr[J + 1]) return -6;
@@ -79,7 +80,7 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
             if (a < b) continue;
             if (jrows[rel[a]] != krows[p0 + a] || jrows[rel[b]] != krows[p0 + b]) return -3;
             const int tr = (rel[a] - R0) * d, tc = (rel[b] - C0) * d;
-            if (tr < 0 || tr + d > TS || tc < 0 || tc + d > TS) return -7;
+            if (tr < 0 || tr + d > TS || tc < 0 || tc + d > TSC) return -7;
             for (int cc = 0; cc < d; ++cc)
               for (int rr = 0; rr < d; ++rr) {
                 double s = 0;
@@ -88,7 +89,7 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
               }
           }
       }
-      const int rows = std::min(TS, M - R0 * d), cols = std::min(TS, N - C0 * d);
+      const int rows = std::min(TS, M - R0 * d), cols = std::min(TSC, N - C0 * d);
       for (int c = 0; c < cols; ++c)
         for (int r = 0; r < rows; ++r) P[R0 * d + r + (size_t)(C0 * d + c) * M] -= acc[r + (size_t)c * TS];
     }

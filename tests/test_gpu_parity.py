@@ -529,3 +529,41 @@ def test_tail_chain_kernel_matches_dense_solve():
         vals3 = vals.copy()
         vals3[diag_idx[-1]] -= 1e4 * np.eye(6)
         assert ls.solve(cp, ri, vals3, b) is None
+
+
+def test_wide_tile_tensor_path_matches_dense_solve(monkeypatch):
+    """96 x 72 destination tiles with the products on the FP64 tensor path (mma.sync.m8n8k4.f64, chol.cu
+    accumulate_items_wide) - the plan large pose graphs get automatically - forced on small systems: wide bands (fronts
+    several tiles tall, two pipeline stages per item), a grid (dense separators, ragged items), a dense matrix, against
+    numpy's dense solve; new values on the same pattern; run-to-run bit-identical; negative pivot reported."""
+    import openslam_g2o_b200 as g
+    monkeypatch.setenv("G2O_B200_WIDE_TILES", "1")
+    monkeypatch.setenv("G2O_B200_CHAIN", "0")
+    rng = np.random.default_rng(12)
+    ls = g.LinearSolverB200(0)
+    grid = [(i * 24 + j, i * 24 + j + 1) for i in range(24) for j in range(23)] + [(i * 24 + j, (i + 1) * 24 + j) for i in range(23) for j in range(24)]
+    cases = [(300, [(i, i + k) for i in range(300) for k in range(1, 41) if i + k < 300]),
+             (576, grid),
+             (70, [(i, j) for i in range(70) for j in range(i + 1, 70)]),
+             (240, [(i, (i + k) % 240) for i in range(240) for k in range(1, 14)])]
+    for nb, edges in cases:
+        cp, ri, vals, A = random_spd_blocks(rng, nb, 6, edges)
+        b = rng.standard_normal(nb * 6)
+        ls.init()
+        x = ls.solve(cp, ri, vals, b)
+        assert x is not None
+        assert rel_err(x, np.linalg.solve(A, b)) < 1e-9, nb
+        assert np.array_equal(x, ls.solve(cp, ri, vals, b))
+        vals3 = vals.copy()
+        diag_idx = [q for j in range(nb) for q in range(cp[j], cp[j + 1]) if ri[q] == j]
+        vals3[diag_idx[-1]] -= 1e4 * np.eye(6)
+        assert ls.solve(cp, ri, vals3, b) is None
+
+
+@needs_oracle
+def test_wide_tile_tensor_path_pose_graph_matches_oracle(monkeypatch):
+    """a 60 x 60 SE3 sphere (3600 poses) through the wide-tile plan, LM iterations against the oracle"""
+    from openslam_g2o_b200 import synth
+    monkeypatch.setenv("G2O_B200_WIDE_TILES", "1")
+    chi = _headline_parity(synth.sphere(60, 60, seed=3600), 4, stride=1)
+    assert chi[-1] < chi[0]

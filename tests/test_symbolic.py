@@ -168,3 +168,38 @@ def test_tail_chain_plan(hx):
             assert info[8] == 0 if d == 3 else info[8] <= 4, info
     finally:
         hx.hx_set_chain(1, 3, 31)
+
+
+def test_wide_tile_plan(hx):
+    """96 x 72 destination tiles (SymbolicOptions::wide_tiles, the FP64 tensor-path plan of large pose graphs): the
+    sequential executor must solve the same systems through the rectangular-tile work lists, incl. dense fronts several
+    tiles tall, panels cut at 12 block columns, and the tail chain receiving its updates through wide tiles."""
+    rng = np.random.default_rng(77)
+    hx.hx_set_wide(1)
+    try:
+        for trial in range(10):
+            nb = int(rng.integers(20, 120))
+            kind = trial % 4
+            if kind == 0:
+                edges = [(int(rng.integers(nb)), int(rng.integers(nb))) for _ in range(4 * nb)]
+            elif kind == 1:
+                s = max(2, int(np.sqrt(nb)))
+                edges = [(i, i + 1) for i in range(nb - 1) if (i + 1) % s] + [(i, i + s) for i in range(nb - s)]
+            elif kind == 2:
+                edges = [(i, j) for i in range(nb) for j in range(i + 1, min(nb, i + 20))]
+            else:
+                nb = min(nb, 60)
+                edges = [(i, j) for i in range(nb) for j in range(i + 1, nb)]
+            cp, ri, vals, A = random_spd_blocks(rng, nb, 6, edges)
+            v = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+            b = rng.standard_normal(nb * 6)
+            x = np.zeros(nb * 6)
+            for maxc, relax in [(72, 1), (72, 0), (24, 1)]:
+                rc = hx.hx_solve(nb, 6, _p(cp), _p(ri), _p(v), C.c_double(0.25), _p(b), _p(x), maxc, relax)
+                assert rc == 0, (rc, trial, nb, maxc, relax)
+                xr = np.linalg.solve(A + 0.25 * np.eye(nb * 6), b)
+                assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+                for gi in (1, 4):
+                    assert hx.hx_check_flow(nb, 6, _p(cp), _p(ri), maxc, relax, gi) == 0, (trial, nb, maxc, relax, gi)
+    finally:
+        hx.hx_set_wide(-1)
