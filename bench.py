@@ -511,8 +511,10 @@ def measure(args, workload, rank, world, local_rank, steps, warmup, full):
                             "frac": info["factor_flops"] / f_s / 1e12 / tpeak, "traffic": ncu_traffic("chol_factor_flow_kernel"),
                             "avg_launch_ms": 1e3 * f_s, "share_of_step": f_s / step_s, "flops_per_launch": info["factor_flops"],
                             "peak_source": tsrc,
-                            "note": "FP64 pipe (DFMA) of the sparse supernodal factorisation; on these graphs the kernel is bound by the "
-                                    "latency of the elimination-tree dependency chain (levels: %d), not by the pipe" % info["levels"]}
+                            "note": ("FP64 tensor path: update products of the supernodal factorisation on mma.sync.m8n8k4.f64 (DMMA), 96 x 72 "
+                                     "destination tiles, cp.async operand pipeline (levels: %d)" % info["levels"]) if info.get("wide_tiles") else
+                                    ("FP64 pipe (DFMA) of the sparse supernodal factorisation; on these graphs the kernel is bound by the "
+                                     "latency of the elimination-tree dependency chain (levels: %d), not by the pipe" % info["levels"])}
         best_hbm = max(hbm, key=lambda n: hbm[n]["avg_launch_ms"]) if hbm else None
         if factor_entry and (best_hbm is None or factor_entry["avg_launch_ms"] >= hbm[best_hbm]["avg_launch_ms"]):
             roof = dict(factor_entry)

@@ -522,13 +522,20 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
   unsigned short* sA = reinterpret_cast<unsigned short*>(sS + ((R.cap_lms + 1 + 3) & ~3));
   unsigned short* sB = sA + R.cap_contrib;
   unsigned short* sL = sB + R.cap_contrib;
+  unsigned short* sLm = sL + R.cap_contrib;              // landmark (range-local) of every slot
   __shared__ __align__(8) unsigned long long sr_bar;
   const int r = blockIdx.x, tid = threadIdx.x;
   const int s0 = R.slot0[r], ns = R.slot0[r + 1] - s0;
   const int l0 = R.lm_ptr[r], nlm = R.lm_ptr[r + 1] - l0;
   const int g0 = R.seg_ptr[r], g1 = R.seg_ptr[r + 1];
   // descriptor of this group's first segment: fetched while the staging copies are in flight
-  int sgm = g0 + tid / kSrLanes;
+  // a segment is shared by 4 lanes that sit 8 apart (lane = 8 * sub + segment): the 8 lanes of a quarter-warp - one
+  // 128-bit shared-memory request - then work on 8 different segments at the SAME position of their contribution lists,
+  // i.e. on the same landmark when the segments are the camera pairs of one camera set (the common case: landmarks are
+  // ranked by camera list).  Their operands are then a handful of neighbouring blocks, most of them shared: broadcasts
+  // instead of the bank conflicts of four lanes walking four landmarks deg * 144 bytes apart
+  const int seg_in_cta = (tid >> 5) * 8 + (tid & 7);
+  int sgm = g0 + seg_in_cta;
   int seg_tt = 0, seg_b = 0, seg_e = 0;
   if (sgm < g1) { seg_tt = R.seg_t[sgm]; seg_b = R.seg_cb[sgm]; seg_e = R.seg_ce[sgm]; }
   const int c0 = R.seg_cb[g0], nc = R.seg_ce[g1 - 1] - c0;  // every range has at least one segment; c0 % 8 == 0
@@ -580,29 +587,38 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
   }
   __syncthreads();
-  // transform in place: every block Hpl(i,l) becomes Hpl(i,l) W_l (one thread per landmark)
-  for (int l = tid; l < nlm; l += kSrThreads) {
-    const double* wl = sW + kDinvStride * l;
+  // transform in place: every block Hpl(i,l) becomes Hpl(i,l) W_l.  One thread per SLOT with 128-bit accesses: the 8
+  // lanes of a quarter-warp touch 8 consecutive 144-byte blocks = 8 different 16-byte bank groups (a thread per
+  // landmark walks its slots with a lane stride of deg * 144 bytes: 8- to 16-way bank conflicts for the common even
+  // degrees - most of the 41 % conflict wavefronts of the round-1 profile)
+  for (int l = tid; l < nlm; l += kSrThreads)
+    for (int q = sS[l]; q < sS[l + 1]; ++q) sLm[q] = (unsigned short)l;
+  __syncthreads();
+  for (int q = tid; q < ns; q += kSrThreads) {
+    const double* wl = sW + kDinvStride * sLm[q];
     const double w00 = wl[0], w01 = wl[1], w02 = wl[2], w11 = wl[3], w12 = wl[4], w22 = wl[5];
-    for (int q = sS[l]; q < sS[l + 1]; ++q) {
-      double* A = sH + 18 * q;
+    double2* A2 = reinterpret_cast<double2*>(sH + 18 * q);
+    double A[18];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double a0 = A[i], a1 = A[i + 6], a2 = A[i + 12];
-        A[i] = a0 * w00;
-        A[i + 6] = fma(a0, w01, a1 * w11);
-        A[i + 12] = fma(a0, w02, fma(a1, w12, a2 * w22));
-      }
+    for (int k = 0; k < 9; ++k) { const double2 v = A2[k]; A[2 * k] = v.x; A[2 * k + 1] = v.y; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double a0 = A[i], a1 = A[i + 6], a2 = A[i + 12];
+      A[i] = a0 * w00;
+      A[i + 6] = fma(a0, w01, a1 * w11);
+      A[i + 12] = fma(a0, w02, fma(a1, w12, a2 * w22));
     }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A2[k] = make_double2(A[2 * k], A[2 * k + 1]);
   }
   __syncthreads();
   const unsigned short* ia = stC ? sA : R.sc_a + c0;
   const unsigned short* ib = stC ? sB : R.sc_b + c0;
   const unsigned short* il = stC ? sL : R.sc_l + c0;
-  const int sub = tid & (kSrLanes - 1);
-  const unsigned gmask = 0xFu << ((tid & 31) & ~3);
+  const int sub = (tid & 31) >> 3;
+  const unsigned gmask = 0x01010101u << (tid & 7);
   for (; sgm < g1; sgm += kSrThreads / kSrLanes) {
-    if (sgm != g0 + tid / kSrLanes) { seg_tt = R.seg_t[sgm]; seg_b = R.seg_cb[sgm]; seg_e = R.seg_ce[sgm]; }
+    if (sgm != g0 + seg_in_cta) { seg_tt = R.seg_t[sgm]; seg_b = R.seg_cb[sgm]; seg_e = R.seg_ce[sgm]; }
     const bool diag = R.t_diag[seg_tt] != 0;
     const int cb = seg_b - c0, ce = seg_e - c0;
     double acc[36], cacc[6];
@@ -647,16 +663,16 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
 #pragma unroll
     for (int k = 0; k < 36; ++k) {
       double v = acc[k];
-      v += __shfl_xor_sync(gmask, v, 1);
-      v += __shfl_xor_sync(gmask, v, 2);
+      v += __shfl_xor_sync(gmask, v, 8);
+      v += __shfl_xor_sync(gmask, v, 16);
       if ((k & 3) == sub) out[k] = v;
     }
     if (diag) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         double v = cacc[k];
-        v += __shfl_xor_sync(gmask, v, 1);
-        v += __shfl_xor_sync(gmask, v, 2);
+        v += __shfl_xor_sync(gmask, v, 8);
+        v += __shfl_xor_sync(gmask, v, 16);
         if ((k & 3) == sub) out[36 + k] = v;
       }
     }

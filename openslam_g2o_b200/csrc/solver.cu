@@ -94,7 +94,8 @@ void drop_graphs(b200_ctx* c) {
 
 static size_t schur_range_smem(const b200_ctx* c) {
   return ((size_t)c->sr_cap_slots * 18 + (size_t)c->sr_cap_lms * k::kDinvStride) * sizeof(double) +
-         (size_t)((c->sr_cap_lms + 1 + 3) & ~3) * sizeof(int) + (size_t)c->sr_cap_contrib * 3 * sizeof(unsigned short);
+         (size_t)((c->sr_cap_lms + 1 + 3) & ~3) * sizeof(int) + (size_t)c->sr_cap_contrib * 3 * sizeof(unsigned short) +
+         (size_t)((c->sr_cap_slots + 7) & ~7) * sizeof(unsigned short);   // + the landmark of every slot
 }
 
 int build_structure_impl(b200_ctx* c) {

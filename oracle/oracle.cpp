@@ -12,6 +12,12 @@
 // nnz(L) for the four in-tree datasets, tests/test_oracle.py); CHOLMOD flavour: "parity unpinned".
 #include "oracle.h"
 
+#include <Eigen/Core>  // oracle/stub/Eigen/Core (shim, see there)
+namespace g2o { namespace internal {   // g2o/types/slam3d/dquat2mat.h:9 - the reference's own object code (oracle/_ref)
+void compute_dq_dR(Eigen::Matrix<double, 3, 9>& dq_dR, const double& r11, const double& r21, const double& r31, const double& r12,
+                   const double& r22, const double& r32, const double& r13, const double& r23, const double& r33);
+} }
+
 #include <algorithm>
 #include <array>
 #include <cassert>
@@ -359,7 +365,15 @@ void compute_error(Edge* e) {
 
 // types/slam3d/dquat2mat.cpp:9-59 + dquat2mat_maxima_generated.cpp:1-165.
 // dq (3x9 col-major), columns ordered r00 r10 r20 r01 r11 r21 r02 r12 r22.
+// The oracle calls the REFERENCE's own function (compiled unmodified into oracle/_ref/libg2o_slam3d_ref.so behind the
+// Eigen::Matrix shim of oracle/stub/Eigen/Core); the restatement below stays as the cross-check of tests/test_oracle.py
+// (bit-equal on all four branches) and as the formula sheet of the device code (csrc/geometry.cuh).
 void compute_dq_dR(double* dq, const double* R) {
+  Eigen::Matrix<double, 3, 9> M;
+  g2o::internal::compute_dq_dR(M, R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8]);
+  for (int i = 0; i < 27; ++i) dq[i] = M.v[i];
+}
+void compute_dq_dR_restated(double* dq, const double* R) {
   const double r00 = R[0], r10 = R[1], r20 = R[2], r01 = R[3], r11 = R[4], r21 = R[5], r02 = R[6],
                r12 = R[7], r22 = R[8];
   for (int i = 0; i < 27; ++i) dq[i] = 0;
@@ -1460,6 +1474,8 @@ int solve_lm(G* g, int iteration, oracle_iter_stats* st) {
 // C interface
 // =============================================================================================
 extern "C" {
+// test hooks: the reference's compute_dq_dR (which = 0) and the restatement (which = 1) on one rotation (col-major 3x3)
+void oracle_dq_dR(const double* R, int which, double* dq27) { if (which == 0) compute_dq_dR(dq27, R); else compute_dq_dR_restated(dq27, R); }
 
 oracle_graph* oracle_new(void) { return new oracle_graph(); }
 void oracle_free(oracle_graph* g) { delete g; }

@@ -199,3 +199,31 @@ def test_oracle_optima_match_an_independent_solver():
     sol = least_squares(res_ba, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=50000)
     chi = oracle_chi(p, 15)
     assert abs(float(np.sum(sol.fun ** 2)) - chi) <= 1e-6 * chi, (float(np.sum(sol.fun ** 2)), chi)
+
+
+@needs_oracle
+def test_dq_dR_is_the_reference_object_code_and_equals_the_restatement():
+    """The SE3 Jacobians of the oracle call the reference's OWN compute_dq_dR (g2o/types/slam3d/dquat2mat.cpp and its
+    maxima-generated tables compiled unmodified into oracle/_ref/libg2o_slam3d_ref.so behind the Eigen shim).  The
+    restatement that the device code follows (csrc/geometry.cuh) must agree with it bit for bit on all four branches of
+    the rotation -> quaternion case split, and with central differences of the quaternion of R."""
+    import ctypes as C
+    from oracle_binding import oracle_lib
+    L = oracle_lib()
+    rng = np.random.default_rng(5)
+    seen = set()
+    for i in range(3000):
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        Rc = R.ravel(order="F").copy()
+        a, b = np.zeros(27), np.zeros(27)
+        L.oracle_dq_dR(Rc.ctypes.data_as(C.c_void_p), 0, a.ctypes.data_as(C.c_void_p))
+        L.oracle_dq_dR(Rc.ctypes.data_as(C.c_void_p), 1, b.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(a, b)
+        tr = np.trace(R)
+        seen.add(0 if tr > 0 else 1 if (R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]) else 2 if R[1, 1] > R[2, 2] else 3)
+    assert seen == {0, 1, 2, 3}
