@@ -640,6 +640,7 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_RELAX_FRAC")) opt.relax_frac = atof(e);
   if (const char* e = getenv("G2O_B200_WIDE_TILES")) opt.wide_tiles = atoi(e);
   if (const char* e = getenv("G2O_B200_SUBTREE_MAX_FLOPS")) opt.subtree_max_flops = atof(e);
+  if (const char* e = getenv("G2O_B200_SPLIT_LATE")) opt.split_late_items = atoi(e) != 0;
   if (const char* e = getenv("G2O_B200_GROUP_SLACK")) opt.group_slack = atoi(e);
   if (const char* e = getenv("G2O_B200_GROUPS_ASAP")) opt.groups_asap = atoi(e) != 0;   // -1 auto (by flops), 0 off, 1 on
   opt.nd_levels = c->nd_levels;

@@ -669,7 +669,23 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
         for (int q = S.sn_tile_ptr[J]; q < S.sn_tile_ptr[J + 1]; ++q) {
           const int w0 = S.tile_work_ptr[q], w1 = S.tile_work_ptr[q + 1];
           if (w1 == w0) continue;
-          const int ng = (w1 - w0 + S.group_items - 1) / S.group_items;
+          // (option split_late_items, off: the items that come from the level just below the destination - they can only
+          // start when that level is complete - in groups of their own, so that no early item waits in a group that is
+          // listed late.  Measured: 3-4 % slower, the early items are not what the levels wait for)
+          std::vector<std::pair<int, int>> cuts;  // [begin, end) of every group
+          {
+            int ws = w1;
+            if (opt.split_late_items && opt.sort_items_by_level)
+              while (ws > w0 && tlevel[task_of[S.upd_k[S.work_u[ws - 1]]]] >= l - 1) --ws;
+            auto chop = [&](int b, int e) {
+              if (b >= e) return;
+              const int n = (e - b + S.group_items - 1) / S.group_items;
+              for (int gi = 0; gi < n; ++gi) cuts.push_back({b + (int)((long long)(e - b) * gi / n), b + (int)((long long)(e - b) * (gi + 1) / n)});
+            };
+            if (ws > w0 && ws < w1) { chop(w0, ws); chop(ws, w1); }
+            else chop(w0, w1);
+          }
+          const int ng = (int)cuts.size();
           S.sn_nupd[J]++;
           // a group is listed as early as its sources allow: one level above the latest of them (as-soon-as-possible),
           // not at the level of its destination - when the factorisation reaches the top of the tree, where a level is
@@ -694,8 +710,8 @@ SymbolicFactor analyze(int nb, int d, const int* colptr, const int* rowidx, cons
             for (int gi = 0; gi < ng; ++gi) {
               S.group_tile.push_back(q);
               S.group_rtile.push_back((int)S.rtile_tile.size() - 1);
-              S.group_w0.push_back(w0 + (int)((long long)(w1 - w0) * gi / ng));
-              S.group_w1.push_back(w0 + (int)((long long)(w1 - w0) * (gi + 1) / ng));
+              S.group_w0.push_back(cuts[gi].first);
+              S.group_w1.push_back(cuts[gi].second);
               S.group_slot.push_back(slots++);
               group_level.push_back(asap(S.group_w0.back(), S.group_w1.back()));
             }

@@ -23,6 +23,8 @@ struct SymbolicOptions {
   double relax_frac = 0.25;         // relaxed amalgamation: accepted share of explicit zeros up to one panel width
   bool sort_items_by_level = true;  // tile work items ordered by the task level of their source supernode
   bool groups_asap = true;          // a split-K group is listed one level above its latest source, not at its destination's level
+  bool split_late_items = false;    // the items fed by the level just below the destination form their own group(s):
+                                    // measured 3-4 % slower on sphere2500 and on the 250k-pose sphere (more split tiles)
   int group_slack = 0;              // ... plus this many levels (see symbolic.cpp; measured: 1 or 2 levels of slack are 5 % slower)
   int group_items = 16;             // split-K: work items per group task (4 / 8 / 16 measured: 16 best with level-sorted items)
   // 0 (default): the reference's ordering - block AMD, bit-exact with cs_amd.  k > 0: nested dissection with 2^k parts
