@@ -26,6 +26,7 @@ struct SymbolicOptions {
   bool split_late_items = false;    // the items fed by the level just below the destination form their own group(s):
                                     // measured 3-4 % slower on sphere2500 and on the 250k-pose sphere (more split tiles)
   int group_slack = 0;              // ... plus this many levels (see symbolic.cpp; measured: 1 or 2 levels of slack are 5 % slower)
+  int wide_group_items = 32;        // ... with wide tiles (unless group_items is set explicitly)
   int group_items = 16;             // split-K: work items per group task (4 / 8 / 16 measured: 16 best with level-sorted items)
   // 0 (default): the reference's ordering - block AMD, bit-exact with cs_amd.  k > 0: nested dissection with 2^k parts
   // on top of it (nested_dissection.cpp): separators first cut band-like systems, whose AMD elimination tree is one
