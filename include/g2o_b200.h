@@ -221,6 +221,16 @@ int b200_ls_init(b200_linear_solver* ls);            /* LinearSolver::init(): dr
  * values: blocks in the same order, block_dim^2 doubles each, column-major.  x,b: HOST buffers. */
 int b200_ls_solve(b200_linear_solver* ls, int nblocks, int block_dim, const int32_t* colptr,
                   const int32_t* rowidx, const double* values, double* x, const double* b);
+/* LinearSolverPCG<MatrixType>::solve (solvers/pcg/linear_solver_pcg.hpp:79-160, linear_solver_pcg.h:47-98): conjugate
+ * gradients with the block-Jacobi preconditioner on the same upper-triangular block CCS matrix.  tolerance /
+ * absolute_tolerance / max_iterations are the reference's setTolerance (1e-6), setAbsoluteTolerance (true) and
+ * setMaxIterations (-1: the number of rows); the absolute residual of one solve carries over to the next until
+ * b200_ls_init(), like _residual.  *iterations = G2OBatchStatistics::iterationsLinearSolver, *residual = _residual.
+ * Returns B200_OK like the reference's unconditional `return true`, B200_NOT_POSITIVE_DEFINITE when a diagonal block
+ * is not positive definite (the reference would invert it silently). */
+int b200_ls_solve_pcg(b200_linear_solver* ls, int nblocks, int block_dim, const int32_t* colptr, const int32_t* rowidx,
+                      const double* values, double* x, const double* b, double tolerance, int absolute_tolerance,
+                      int max_iterations, int32_t* iterations, double* residual);
 int b200_ls_get_block_ordering(b200_linear_solver* ls, int32_t* perm);
 int64_t b200_ls_get_factor_nnz(b200_linear_solver* ls);
 const char* b200_ls_last_error(const b200_linear_solver* ls);

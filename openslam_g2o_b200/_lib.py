@@ -107,6 +107,7 @@ def _load():
         "b200_ls_destroy": (None, [vp]),
         "b200_ls_init": (i32, [vp]),
         "b200_ls_solve": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
+        "b200_ls_solve_pcg": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, C.c_double, i32, i32, vp, vp]),
         "b200_ls_get_block_ordering": (i32, [vp, vp]),
         "b200_ls_get_factor_nnz": (i64, [vp]),
         "b200_ls_last_error": (C.c_char_p, [vp]),

@@ -1046,26 +1046,33 @@ chol_backward_flow_kernel(CholDev P, CholPlanDev Q, const double* __restrict__ L
       const int* jrows = P.sn_rows + P.sn_rowptr[J];
       double* xj = y + (long long)col0 * D;
       __syncthreads();
-      if (q == q_root) {
+      // x at the rows below the diagonal block goes through shared memory in pieces of at most xb_doubles (a top
+      // separator of any height: round 1 refused panels above ~4800 block rows); t_j is accumulated piece by piece in
+      // a fixed order
+      for (int b0 = 0; b0 == 0 || b0 < B; b0 += xb_doubles) {
+        const int Bc = min(xb_doubles, B - b0);
+        if (b0 > 0) __syncthreads();  // the previous piece of xb has been consumed
+        if (q == q_root && b0 == 0) {
 #pragma unroll
-        for (int k = 0; k < kPreIdx; ++k)
-          if (gidx[k] >= 0) xb[tid + k * nt] = __ldcg(y + gidx[k]);
-        for (int i = tid + kPreIdx * nt; i < B; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
-      } else {
-        for (int i = tid; i < B; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
-      }
-      __syncthreads();
-      // t = y_J - L21^T x_below : one warp per column, lanes stride the rows, fixed-order shuffle tree
-      for (int j = wid; j < N; j += nw) {
-        const double* cj = st ? stage + j * B : Pj + ((long long)j * M + N);
-        double s0 = 0.0, s1 = 0.0;
-        int i = lane;
-        for (; i + 32 < B; i += 64) { s0 = fma(cj[i], xb[i], s0); s1 = fma(cj[i + 32], xb[i + 32], s1); }
-        if (i < B) s0 = fma(cj[i], xb[i], s0);
-        double s = s0 + s1;
+          for (int k = 0; k < kPreIdx; ++k)
+            if (gidx[k] >= 0 && tid + k * nt < Bc) xb[tid + k * nt] = __ldcg(y + gidx[k]);
+          for (int i = tid + kPreIdx * nt; i < Bc; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + i / D] * D + (i % D)));
+        } else {
+          for (int i = tid; i < Bc; i += nt) xb[i] = __ldcg(y + ((long long)jrows[nc + (b0 + i) / D] * D + ((b0 + i) % D)));
+        }
+        __syncthreads();
+        // t = y_J - L21^T x_below : one warp per column, lanes stride the rows, fixed-order shuffle tree
+        for (int j = wid; j < N; j += nw) {
+          const double* cj = (st ? stage + j * B : Pj + ((long long)j * M + N)) + b0;
+          double s0 = 0.0, s1 = 0.0;
+          int i = lane;
+          for (; i + 32 < Bc; i += 64) { s0 = fma(cj[i], xb[i], s0); s1 = fma(cj[i + 32], xb[i + 32], s1); }
+          if (i < Bc) s0 = fma(cj[i], xb[i], s0);
+          double s = s0 + s1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) tvec[j] = xj[j] - s;
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) tvec[j] = (b0 == 0 ? xj[j] : tvec[j]) - s;
+        }
       }
       __syncthreads();
       const double* Di = st ? stage + B * N : Dinv + Q.sn_dinvptr[J];
@@ -1199,7 +1206,8 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   const int Nmax = S_.max_ncol * d;
   const size_t factor_doubles = (size_t)Nmax * d * kLds + d * d + d + (size_t)Nmax * Nmax;
   flow_smem_ = std::max((size_t)(S_.wide ? kWideSmemDoubles : kUpdateSmemDoubles), factor_doubles) * sizeof(double);
-  xb_doubles_ = (S_.max_nrow * d + 1) & ~1;
+  xb_doubles_ = std::min((S_.max_nrow * d + 1) & ~1, 12288);   // taller panels go through in pieces (chol_backward_flow_kernel)
+  if (const char* e = getenv("G2O_B200_XB_DOUBLES")) xb_doubles_ = std::max(48, std::min(xb_doubles_, atoi(e) & ~1));  // tests: force pieces
   stage_doubles_ = (int)((kMaxDynSmem - 1024) / sizeof(double)) - xb_doubles_ - kMaxPanelCols;
   if (!host_only_flag()) {
     B200_CUDA(cudaStreamSynchronize(s));  // the temporaries above die here

@@ -78,5 +78,58 @@ class LinearSolverB200 : public LinearSolver<MatrixType> {
   std::vector<double> _values;
 };
 
+// Drop-in for LinearSolverPCG (g2o/solvers/pcg/linear_solver_pcg.h:47-98): same setters, same stopping rule, the
+// iteration on the GPU (csrc/pcg.cuh).  Uncompiled here for the same reason as the class above.
+template <typename MatrixType>
+class LinearSolverB200PCG : public LinearSolverB200<MatrixType> {
+ public:
+  LinearSolverB200PCG() : LinearSolverB200<MatrixType>(), _tolerance(1e-6), _absoluteTolerance(true), _verbose(false), _maxIter(-1) {}
+
+  bool solve(const SparseBlockMatrix<MatrixType>& A, double* x, double* b) {
+    if (!this->_ls && !this->init()) return false;
+    const int nBlocks = static_cast<int>(A.blockCols().size());
+    const int d = A.colsOfBlock(0);
+    for (int i = 0; i < nBlocks; ++i)
+      if (A.colsOfBlock(i) != d) {
+        std::cerr << "LinearSolverB200PCG: only uniform block sizes (3 or 6) are supported" << std::endl;
+        return false;
+      }
+    A.fillBlockStructure(this->_structure);
+    this->_values.resize(static_cast<size_t>(this->_structure.Ap[nBlocks]) * d * d);
+    double* out = &this->_values[0];
+    for (int c = 0; c < nBlocks; ++c) {
+      const typename SparseBlockMatrix<MatrixType>::IntBlockMap& col = A.blockCols()[c];
+      for (typename SparseBlockMatrix<MatrixType>::IntBlockMap::const_iterator it = col.begin(); it != col.end(); ++it) {
+        if (it->first > c) break;
+        memcpy(out, it->second->data(), sizeof(double) * d * d);
+        out += d * d;
+      }
+    }
+    int iterations = 0;
+    double residual = 0.;
+    int rc = b200_ls_solve_pcg(this->_ls, nBlocks, d, this->_structure.Ap, this->_structure.Aii, &this->_values[0], x, b, _tolerance,
+                               _absoluteTolerance ? 1 : 0, _maxIter, &iterations, &residual);
+    if (rc < 0) std::cerr << "LinearSolverB200PCG: " << b200_ls_last_error(this->_ls) << std::endl;
+    if (_verbose) std::cerr << "residual[" << iterations << "]: " << 2. * residual << std::endl;
+    G2OBatchStatistics* globalStats = G2OBatchStatistics::globalStats();
+    if (globalStats) globalStats->iterationsLinearSolver = iterations;
+    return rc == B200_OK;
+  }
+
+  double tolerance() const { return _tolerance; }
+  void setTolerance(double tolerance) { _tolerance = tolerance; }
+  int maxIterations() const { return _maxIter; }
+  void setMaxIterations(int maxIter) { _maxIter = maxIter; }
+  bool absoluteTolerance() const { return _absoluteTolerance; }
+  void setAbsoluteTolerance(bool absoluteTolerance) { _absoluteTolerance = absoluteTolerance; }
+  bool verbose() const { return _verbose; }
+  void setVerbose(bool verbose) { _verbose = verbose; }
+
+ protected:
+  double _tolerance;
+  bool _absoluteTolerance, _verbose;
+  int _maxIter;
+};
+
 }  // namespace g2o
 #endif

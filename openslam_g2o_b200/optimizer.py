@@ -442,6 +442,21 @@ class LinearSolverB200:
                                       L.ptr(x), L.ptr(b)), self._h, ls=True)
         return None if rc == L.NOT_POSITIVE_DEFINITE else x
 
+    def solve_pcg(self, colptr, rowidx, values, b, tolerance=1e-6, absolute_tolerance=True, max_iterations=-1):
+        """LinearSolverPCG::solve (solvers/pcg/linear_solver_pcg.hpp:79-160): returns (x, iterations, residual); x is None
+        when a diagonal block is not positive definite."""
+        colptr, rowidx = L.as_i32(colptr), L.as_i32(rowidx)
+        values = np.asarray(values, dtype=np.float64)
+        d = values.shape[1]
+        vals_cm = np.ascontiguousarray(np.transpose(values, (0, 2, 1)))
+        b = L.as_f64(b)
+        x = np.zeros_like(b)
+        it, res = C.c_int32(0), C.c_double(0.0)
+        rc = _check(lib.b200_ls_solve_pcg(self._h, len(colptr) - 1, d, L.ptr(colptr), L.ptr(rowidx), L.ptr(vals_cm), L.ptr(x),
+                                          L.ptr(b), float(tolerance), int(bool(absolute_tolerance)), int(max_iterations),
+                                          C.byref(it), C.byref(res)), self._h, ls=True)
+        return (None if rc == L.NOT_POSITIVE_DEFINITE else x), int(it.value), float(res.value)
+
     def block_ordering(self):
         n = _check(lib.b200_ls_get_block_ordering(self._h, None), self._h, ls=True)
         p = np.zeros(n, np.int32)

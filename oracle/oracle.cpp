@@ -1473,7 +1473,93 @@ int solve_lm(G* g, int iteration, oracle_iter_stats* st) {
 // =============================================================================================
 // C interface
 // =============================================================================================
+// ---------------------------------------------------------------------------------------------
+// LinearSolverPCG<MatrixType>::solve, solvers/pcg/linear_solver_pcg.hpp:79-197 - restated on plain arrays in the
+// reference's operation order: linear structure of the off-diagonal upper blocks in column order (:86-106), mult() =
+// diagonal part first, then per upper block dest[row] += B src[col]; dest[col] += B^T src[row] (:173-196), the
+// recurrences and the stopping rule of :117-150.  *residual_io carries _residual from one solve to the next.
+// ---------------------------------------------------------------------------------------------
+static void pcg_inverse_spd(const double* B, int d, double* J) {  // it->second->inverse() (:95): Gauss-Jordan, partial pivoting
+  std::vector<double> a((size_t)d * 2 * d, 0.0);
+  for (int r = 0; r < d; ++r) { for (int c = 0; c < d; ++c) a[(size_t)r * 2 * d + c] = B[r + c * d]; a[(size_t)r * 2 * d + d + r] = 1.0; }
+  for (int k = 0; k < d; ++k) {
+    int p = k;
+    for (int r = k + 1; r < d; ++r) if (fabs(a[(size_t)r * 2 * d + k]) > fabs(a[(size_t)p * 2 * d + k])) p = r;
+    if (p != k) for (int c = 0; c < 2 * d; ++c) std::swap(a[(size_t)p * 2 * d + c], a[(size_t)k * 2 * d + c]);
+    const double inv = 1.0 / a[(size_t)k * 2 * d + k];
+    for (int c = 0; c < 2 * d; ++c) a[(size_t)k * 2 * d + c] *= inv;
+    for (int r = 0; r < d; ++r) {
+      if (r == k) continue;
+      const double f = a[(size_t)r * 2 * d + k];
+      if (f != 0.0) for (int c = 0; c < 2 * d; ++c) a[(size_t)r * 2 * d + c] -= f * a[(size_t)k * 2 * d + c];
+    }
+  }
+  for (int r = 0; r < d; ++r) for (int c = 0; c < d; ++c) J[r + c * d] = a[(size_t)r * 2 * d + d + c];
+}
+
+static int pcg_solve(int nb, int d, const int* colptr, const int* rowidx, const double* values, double* x, const double* b,
+                     double tolerance, int absolute_tolerance, int max_iter, double* residual_io) {
+  const int n = nb * d;
+  std::vector<const double*> diag(nb, nullptr), sparse;
+  std::vector<std::pair<int, int>> indices;   // (row offset, column offset) of every off-diagonal upper block
+  std::vector<double> J((size_t)nb * d * d);
+  for (int c = 0; c < nb; ++c)
+    for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
+      const double* B = values + (size_t)q * d * d;
+      if (rowidx[q] == c) { diag[c] = B; pcg_inverse_spd(B, d, &J[(size_t)c * d * d]); break; }
+      indices.push_back({rowidx[q] * d, c * d});
+      sparse.push_back(B);
+    }
+  auto multDiag = [&](const double* const* blocks, const double* Jflat, const double* src, double* dest) {
+    for (int i = 0; i < nb; ++i) {
+      const double* B = blocks ? blocks[i] : Jflat + (size_t)i * d * d;
+      for (int r = 0; r < d; ++r) {
+        double s = 0;
+        for (int c = 0; c < d; ++c) s += B[r + c * d] * src[i * d + c];
+        dest[i * d + r] = s;
+      }
+    }
+  };
+  auto mult = [&](const double* src, double* dest) {
+    multDiag(diag.data(), nullptr, src, dest);
+    for (size_t i = 0; i < sparse.size(); ++i) {
+      const int ro = indices[i].first, co = indices[i].second;
+      const double* B = sparse[i];
+      for (int r = 0; r < d; ++r) { double s = 0; for (int c = 0; c < d; ++c) s += B[r + c * d] * src[co + c]; dest[ro + r] += s; }
+      for (int c = 0; c < d; ++c) { double s = 0; for (int r = 0; r < d; ++r) s += B[r + c * d] * src[ro + r]; dest[co + c] += s; }
+    }
+  };
+  auto dot = [&](const std::vector<double>& u, const std::vector<double>& v) { double s = 0; for (int i = 0; i < n; ++i) s += u[i] * v[i]; return s; };
+  std::vector<double> r(b, b + n), dv(n, 0.0), q(n, 0.0), s(n, 0.0);
+  for (int i = 0; i < n; ++i) x[i] = 0.0;
+  multDiag(nullptr, J.data(), r.data(), dv.data());
+  double dn = dot(r, dv);
+  double d0 = tolerance * dn;
+  if (absolute_tolerance && *residual_io > 0.0 && *residual_io > d0) d0 = *residual_io;
+  const int maxIter = max_iter < 0 ? n : max_iter;
+  int iteration;
+  for (iteration = 0; iteration < maxIter; ++iteration) {
+    if (dn <= d0) break;
+    mult(dv.data(), q.data());
+    const double a = dn / dot(dv, q);
+    for (int i = 0; i < n; ++i) x[i] += a * dv[i];
+    for (int i = 0; i < n; ++i) r[i] -= a * q[i];
+    multDiag(nullptr, J.data(), r.data(), s.data());
+    const double dold = dn;
+    dn = dot(r, s);
+    const double ba = dn / dold;
+    for (int i = 0; i < n; ++i) dv[i] = s[i] + ba * dv[i];
+  }
+  *residual_io = 0.5 * dn;
+  return iteration;
+}
+
 extern "C" {
+// LinearSolverPCG on an upper-triangular block CCS matrix (blocks d*d column-major); returns the iteration count
+int oracle_pcg_solve(int nb, int d, const int* colptr, const int* rowidx, const double* values, double* x, const double* b,
+                     double tolerance, int absolute_tolerance, int max_iter, double* residual_io) {
+  return pcg_solve(nb, d, colptr, rowidx, values, x, b, tolerance, absolute_tolerance, max_iter, residual_io);
+}
 // test hooks: the reference's compute_dq_dR (which = 0) and the restatement (which = 1) on one rotation (col-major 3x3)
 void oracle_dq_dR(const double* R, int which, double* dq27) { if (which == 0) compute_dq_dR(dq27, R); else compute_dq_dR_restated(dq27, R); }
 

@@ -567,3 +567,105 @@ def test_wide_tile_tensor_path_pose_graph_matches_oracle(monkeypatch):
     monkeypatch.setenv("G2O_B200_WIDE_TILES", "1")
     chi = _headline_parity(synth.sphere(60, 60, seed=3600), 4, stride=1)
     assert chi[-1] < chi[0]
+
+
+def test_backward_sweep_in_pieces_matches_dense_solve(monkeypatch):
+    """panels whose rows below the diagonal block exceed the shared-memory piece of the backward sweep (forced down to 96
+    doubles here; 12288 in production, i.e. separators above 2048 block rows) are swept piece by piece"""
+    import openslam_g2o_b200 as g
+    monkeypatch.setenv("G2O_B200_XB_DOUBLES", "96")
+    monkeypatch.setenv("G2O_B200_CHAIN", "0")
+    rng = np.random.default_rng(13)
+    ls = g.LinearSolverB200(0)
+    cases = [(120, [(i, j) for i in range(120) for j in range(i + 1, min(120, i + 60))]),
+             (80, [(i, j) for i in range(80) for j in range(i + 1, 80)])]
+    for d in (3, 6):
+        for nb, edges in cases:
+            cp, ri, vals, A = random_spd_blocks(rng, nb, d, edges)
+            b = rng.standard_normal(nb * d)
+            ls.init()
+            x = ls.solve(cp, ri, vals, b)
+            assert x is not None
+            assert rel_err(x, np.linalg.solve(A, b)) < 1e-9, (nb, d)
+
+
+@needs_oracle
+@pytest.mark.parametrize("d", [3, 6])
+def test_pcg_linear_solver_matches_oracle(d):
+    """LinearSolverPCG on the GPU (csrc/pcg.cuh) against the restated reference iteration (oracle_pcg_solve) on the same
+    block matrix: solution, iteration count (the sums run in another order: +-1 near the threshold), carried-over
+    residual, iteration limit; and against the dense solve."""
+    import ctypes as C
+    import openslam_g2o_b200 as g
+    from oracle_binding import oracle_lib
+    L = oracle_lib()
+    L.oracle_pcg_solve.restype = C.c_int
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(50 + d)
+    ls = g.LinearSolverB200(0)
+    for nb, edges in [(300, [(i, j) for i in range(300) for j in range(i + 1, min(300, i + 6))] + [(i, (11 * i + 5) % 300) for i in range(300)]),
+                      (40, [(i, j) for i in range(40) for j in range(i + 1, 40)]),
+                      (7, [])]:
+        cp, ri, vals, A = random_spd_blocks(rng, nb, d, edges)
+        vcm = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+        b = rng.standard_normal(nb * d)
+        for tol, maxit in [(1e-6, -1), (1e-14, -1), (1e-14, 5)]:
+            ls.init()
+            x, it, res = ls.solve_pcg(cp, ri, vals, b, tolerance=tol, max_iterations=maxit)
+            xo = np.zeros(nb * d)
+            ro = C.c_double(-1.0)
+            ito = L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(xo), p(b), C.c_double(tol), 1, maxit, C.byref(ro))
+            assert abs(it - ito) <= 1, (nb, tol, maxit, it, ito)
+            if it == ito:
+                assert rel_err(x, xo) < 1e-9
+                floor = 1e-25 * float(b @ b)   # converged to rounding noise: only the order of magnitude is comparable
+                assert abs(res - ro.value) <= 1e-6 * ro.value or max(res, ro.value) <= floor or 0.1 < res / ro.value < 10.0
+            if maxit < 0 and tol < 1e-10:
+                assert rel_err(x, np.linalg.solve(A, b)) < 1e-6
+        # the absolute residual carries over (no init() in between) - like _residual of the reference
+        x1, it1, res1 = ls.solve_pcg(cp, ri, vals, b, tolerance=1e-14)
+        xo = np.zeros(nb * d)
+        ito1 = L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(xo), p(b), C.c_double(1e-14), 1, -1, C.byref(ro))
+        assert abs(it1 - ito1) <= 1
+        # run-to-run bit-identical
+        ls.init()
+        xa, ita, _ = ls.solve_pcg(cp, ri, vals, b, tolerance=1e-10)
+        ls.init()
+        xb, itb, _ = ls.solve_pcg(cp, ri, vals, b, tolerance=1e-10)
+        assert ita == itb and np.array_equal(xa, xb)
+    # a Gauss-Newton-shaped matrix (sum of J^T J over the edges of a ring with chords + a weak prior): hundreds of
+    # iterations, where the summation order shows - iteration counts within 3 %, solutions to the tolerance of the rule
+    nb = 200
+    edges = [(i, (i + 1) % nb) for i in range(nb)] + [(i, (i + 37) % nb) for i in range(0, nb, 5)]
+    edges = sorted({(min(a, c), max(a, c)) for a, c in edges if a != c})
+    from helpers import upper_pattern_from_edges
+    cp, ri = upper_pattern_from_edges(nb, edges)
+    pos = {(int(ri[q]), j): q for j in range(nb) for q in range(cp[j], cp[j + 1])}
+    vals = np.zeros((len(ri), d, d))
+    for a, c in edges:
+        Ja, Jc = rng.standard_normal((d, d)), rng.standard_normal((d, d))
+        vals[pos[(a, a)]] += Ja.T @ Ja
+        vals[pos[(c, c)]] += Jc.T @ Jc
+        vals[pos[(a, c)]] += Ja.T @ Jc
+    for j in range(nb):
+        vals[pos[(j, j)]] += 1e-3 * np.eye(d)
+    A = np.zeros((nb * d, nb * d))
+    for (i, j), q in pos.items():
+        A[i * d:(i + 1) * d, j * d:(j + 1) * d] = vals[q]
+        A[j * d:(j + 1) * d, i * d:(i + 1) * d] = vals[q].T
+    vcm = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+    b = rng.standard_normal(nb * d)
+    ls.init()
+    x, it, res = ls.solve_pcg(cp, ri, vals, b, tolerance=1e-10)
+    xo = np.zeros(nb * d)
+    ro = C.c_double(-1.0)
+    ito = L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(xo), p(b), C.c_double(1e-10), 1, -1, C.byref(ro))
+    assert ito > 50 and abs(it - ito) <= max(2, 0.03 * ito), (it, ito)
+    xr = np.linalg.solve(A, b)
+    assert rel_err(x, xr) < 1e-4 and rel_err(xo, xr) < 1e-4
+    # a diagonal block that is not positive definite is reported
+    cp, ri, vals, A = random_spd_blocks(rng, 10, d, [(i, i + 1) for i in range(9)])
+    diag_idx = [q for j in range(10) for q in range(cp[j], cp[j + 1]) if ri[q] == j]
+    vals[diag_idx[3]] -= 1e3 * np.eye(d)
+    ls.init()
+    assert ls.solve_pcg(cp, ri, vals, rng.standard_normal(10 * d))[0] is None

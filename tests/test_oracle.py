@@ -227,3 +227,34 @@ def test_dq_dR_is_the_reference_object_code_and_equals_the_restatement():
         tr = np.trace(R)
         seen.add(0 if tr > 0 else 1 if (R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]) else 2 if R[1, 1] > R[2, 2] else 3)
     assert seen == {0, 1, 2, 3}
+
+
+@needs_oracle
+@pytest.mark.parametrize("d", [3, 6])
+def test_oracle_pcg_matches_dense_solve(d):
+    """the restated LinearSolverPCG (solvers/pcg/linear_solver_pcg.hpp:79-197): converges to the dense solution, stops by
+    the relative rule dn <= tolerance * dn_0, carries the absolute residual to the next solve, honours maxIter"""
+    import ctypes as C
+    from helpers import random_spd_blocks
+    from oracle_binding import oracle_lib
+    L = oracle_lib()
+    L.oracle_pcg_solve.restype = C.c_int
+    rng = np.random.default_rng(40 + d)
+    nb = 60
+    edges = [(i, j) for i in range(nb) for j in range(i + 1, min(nb, i + 5))] + [(i, (7 * i + 3) % nb) for i in range(nb)]
+    cp, ri, vals, A = random_spd_blocks(rng, nb, d, edges)
+    vcm = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+    b = rng.standard_normal(nb * d)
+    x = np.zeros(nb * d)
+    res = C.c_double(-1.0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    it = L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(x), p(b), C.c_double(1e-12), 1, -1, C.byref(res))
+    xr = np.linalg.solve(A, b)
+    assert 2 < it < nb * d
+    assert np.abs(x - xr).max() <= 1e-6 * np.abs(xr).max()
+    assert res.value > 0
+    # second solve with the carried-over absolute residual: stops no later than the first
+    it2 = L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(x), p(b), C.c_double(1e-12), 1, -1, C.byref(res))
+    assert it2 <= it
+    res = C.c_double(-1.0)
+    assert L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(x), p(b), C.c_double(1e-12), 1, 3, C.byref(res)) == 3
