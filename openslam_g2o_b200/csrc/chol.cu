@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace g2o_b200 {
 
@@ -954,6 +955,7 @@ chol_factor_flow_kernel(const __grid_constant__ CholDev P, const __grid_constant
 
 }  // namespace g2o_b200
 #include "chol_chain.cuh"
+#include "sparse_inverse.cuh"
 namespace g2o_b200 {
 
 // ---------------------------------------------------------------------------------------------
@@ -1152,6 +1154,8 @@ void CholeskyGpu::analyze(int nb, int d, const int* colptr, const int* rowidx, c
   d_flow_kind_.upload(S_.flow_kind, s); d_flow_arg_.upload(S_.flow_arg, s);
   d_sn_nupd_.upload(S_.sn_nupd, s); d_sn_nchunk_.upload(S_.sn_nchunk, s);
   d_task_parent_.upload(S_.task_parent, s);
+  d_col2sn_.upload(S_.col2sn, s);
+  spinv_planned_ = false;
   {  // tail chain
     d_chain_sn_.upload(S_.chain_sn, s); d_chain_mapptr_.upload(S_.chain_mapptr, s); d_chain_map_.upload(S_.chain_map, s);
     d_chain_new_rows_.upload(S_.chain_new_rows, s); d_chain_colptr_.upload(S_.chain_colptr, s);
@@ -1282,7 +1286,7 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
     ChainDev C{(int)S.chain_sn.size(), d_chain_desc_.p, d_chain_map_.p, d_chain_fwd_ptr_.p, d_chain_fwd_src_.p,
                (int)S.chain_stage_doubles, (int)S.chain_remap_blocks};
     chol_chain_kernel<<<1, kChThreads, chain_smem_, s>>>(C, L, d_Ldiag_.p, d_chain_pack_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
-    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_chain_desc_.p, d_chain_pack_.p);
+    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_chain_desc_.p, d_chain_pack_.p, d_Dinv_.p);
     count(2);
   }
   B200_CUDA(cudaGetLastError());
@@ -1321,6 +1325,77 @@ void CholeskyGpu::solve_t(double* x, cudaStream_t s, LaunchCounter* lc, EventPro
   }
   chol_permute_out_kernel<D><<<ceil_div(n, 256), 256, 0, s>>>(S.nb, d_perm_.p, y, x, cnt + 2);
   count();
+  B200_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// sparse inverse subset (sparse_inverse.cuh)
+// ---------------------------------------------------------------------------------------------
+void CholeskyGpu::sparse_inverse(cudaStream_t s, LaunchCounter* lc) {
+  const SymbolicFactor& S = S_;
+  if (!spinv_planned_) {
+    // depth levels of the supernodal tree (root = 0); per level its supernodes and its (supernode, block row) items
+    std::vector<int> depth(S.nsn, 0);
+    int nlev = 0;
+    for (int J = S.nsn - 1; J >= 0; --J) {
+      depth[J] = S.sn_parent[J] < 0 ? 0 : depth[S.sn_parent[J]] + 1;
+      nlev = std::max(nlev, depth[J] + 1);
+    }
+    spinv_level_ptr_.assign(nlev + 1, 0);
+    spinv_item_ptr_.assign(nlev + 1, 0);
+    for (int J = 0; J < S.nsn; ++J) {
+      spinv_level_ptr_[depth[J] + 1]++;
+      spinv_item_ptr_[depth[J] + 1] += S.sn_nrow[J] - S.sn_ncol[J];
+    }
+    for (int l = 0; l < nlev; ++l) { spinv_level_ptr_[l + 1] += spinv_level_ptr_[l]; spinv_item_ptr_[l + 1] += spinv_item_ptr_[l]; }
+    std::vector<int> level_sn(S.nsn), item_sn(std::max(spinv_item_ptr_[nlev], 1)), item_p(std::max(spinv_item_ptr_[nlev], 1));
+    std::vector<int> lf(spinv_level_ptr_.begin(), spinv_level_ptr_.end() - 1), itf(spinv_item_ptr_.begin(), spinv_item_ptr_.end() - 1);
+    for (int J = 0; J < S.nsn; ++J) {
+      level_sn[lf[depth[J]]++] = J;
+      for (int p = S.sn_ncol[J]; p < S.sn_nrow[J]; ++p) { item_sn[itf[depth[J]]] = J; item_p[itf[depth[J]]++] = p; }
+    }
+    d_spinv_level_sn_.upload(level_sn, s); d_spinv_item_sn_.upload(item_sn, s); d_spinv_item_p_.upload(item_p, s);
+    d_Zinv_.alloc((size_t)S.factor_doubles); d_Yt_.alloc((size_t)S.factor_doubles);
+    B200_CUDA(cudaStreamSynchronize(s));  // the temporaries above die here
+    spinv_planned_ = true;
+  }
+  const SpinvDev V{dev(), d_sn_dinvptr_.p, d_col2sn_.p};
+  auto count = [&](int k = 1) { if (lc) lc->n += k; };
+  auto run = [&](auto dtag) {
+    constexpr int D = decltype(dtag)::value;
+    spinv_prepare_kernel<D><<<dim3(S.nsn, S.max_nrow > 256 ? 16 : 2), kSpinvThreads, 0, s>>>(V, d_L_.p, d_Dinv_.p, d_Yt_.p, d_Zinv_.p);
+    count();
+    const int nlev = (int)spinv_level_ptr_.size() - 1;
+    for (int l = 0; l < nlev; ++l) {
+      const int ni = spinv_item_ptr_[l + 1] - spinv_item_ptr_[l], ns = spinv_level_ptr_[l + 1] - spinv_level_ptr_[l];
+      if (ni > 0) {
+        spinv_rows_kernel<D><<<ni, kSpinvThreads, 0, s>>>(V, d_spinv_item_sn_.p, d_spinv_item_p_.p, spinv_item_ptr_[l], d_Yt_.p, d_Zinv_.p);
+        spinv_diag_kernel<D><<<ns, kSpinvThreads, 0, s>>>(V, d_spinv_level_sn_.p, spinv_level_ptr_[l], d_Yt_.p, d_Zinv_.p);
+        count(2);
+      }
+    }
+  };
+  if (S.d == 3) run(std::integral_constant<int, 3>{}); else run(std::integral_constant<int, 6>{});
+  B200_CUDA(cudaGetLastError());
+}
+
+bool CholeskyGpu::locate_inverse_block(int r, int c, long long* off, int* ld, bool* transposed) const {
+  const SymbolicFactor& S = S_;
+  int pr = S.pinv[r], pc = S.pinv[c];
+  *transposed = pr < pc;
+  if (pr < pc) std::swap(pr, pc);
+  const long long o = spinv_locate(pr, pc, S.d, S.col2sn.data(), S.sn_col0.data(), S.sn_ncol.data(), S.sn_nrow.data(),
+                                   S.sn_rowptr.data(), S.sn_rows.data(), reinterpret_cast<const long long*>(S.sn_lptr.data()), ld);
+  *off = o;
+  return o >= 0;
+}
+
+void CholeskyGpu::gather_inverse_blocks(int n, const long long* d_off, const int* d_ld, const unsigned char* d_trans,
+                                        double* d_out, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return;
+  if (S_.d == 3) spinv_gather_kernel<3><<<ceil_div((int64_t)n * 9, 256), 256, 0, s>>>(n, d_off, d_ld, d_trans, d_Zinv_.p, d_out);
+  else spinv_gather_kernel<6><<<ceil_div((int64_t)n * 36, 256), 256, 0, s>>>(n, d_off, d_ld, d_trans, d_Zinv_.p, d_out);
+  if (lc) lc->n++;
   B200_CUDA(cudaGetLastError());
 }
 

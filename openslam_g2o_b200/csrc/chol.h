@@ -39,6 +39,16 @@ class CholeskyGpu {
   void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
   int* status_ptr() { return d_counters_.p + 2; }  // device int: 0 ok, 1 not positive definite
   double* factor_values() { return d_L_.p; }
+  // Sparse inverse subset of the matrix of the preceding factor(): every block of A^-1 on the pattern of L + L^T
+  // (Takahashi recursion down the supernodal tree, sparse_inverse.cuh) - what MarginalCovarianceCholesky
+  // (core/marginal_covariance_cholesky.cpp:55-214) evaluates entry by entry.  Asynchronous on s.
+  void sparse_inverse(cudaStream_t s, LaunchCounter* lc);
+  // host: where block (r, c) of A^-1 (ORIGINAL block indices) lives in the array sparse_inverse() filled; false when the
+  // block is outside the pattern of the factor
+  bool locate_inverse_block(int r, int c, long long* off, int* ld, bool* transposed) const;
+  // device gather of n located blocks into d_out (n * d * d doubles, column-major blocks).  Asynchronous on s.
+  void gather_inverse_blocks(int n, const long long* d_off, const int* d_ld, const unsigned char* d_trans, double* d_out,
+                             cudaStream_t s, LaunchCounter* lc);
 
  private:
   bool analyzed_ = false;
@@ -63,6 +73,12 @@ class CholeskyGpu {
   DevBuf<unsigned> d_chain_new_rows_;
   DevBuf<double> d_chain_pack_;  // per chain link: rows below the diagonal block (packed) | inverse diagonal block
   DevBuf<unsigned char> d_task_skip_;
+  // sparse inverse (built at the first sparse_inverse() after analyze()): Z and Y^T with the geometry of L, work items
+  // (supernode, block row) and supernodes per depth level of the supernodal tree
+  DevBuf<double> d_Zinv_, d_Yt_;
+  DevBuf<int> d_col2sn_, d_spinv_item_sn_, d_spinv_item_p_, d_spinv_level_sn_;
+  std::vector<int> spinv_item_ptr_, spinv_level_ptr_;
+  bool spinv_planned_ = false;
   size_t chain_smem_ = 0, chain_back_smem_ = 0;
   int chain_back_buf_doubles_ = 0;
   int cnt_upd_ = 0, cnt_chunk_ = 0, cnt_slot_ = 0, cnt_bdone_ = 0;

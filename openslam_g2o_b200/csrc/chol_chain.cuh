@@ -418,7 +418,8 @@ chol_chain_kernel(const __grid_constant__ ChainDev C, double* __restrict__ L, do
 // thread j builds column j of the inverse - the same recurrence the chunk tasks run after their completion signal
 __global__ void __launch_bounds__(128)
 chol_chain_dinv_kernel(const __grid_constant__ CholDev P, const int* __restrict__ chain_sn, const long long* __restrict__ sn_dinvptr,
-                       const double* __restrict__ Ldiag, const int* __restrict__ desc, double* __restrict__ pack) {
+                       const double* __restrict__ Ldiag, const int* __restrict__ desc, double* __restrict__ pack,
+                       double* __restrict__ Dinv) {
   constexpr int D = 6;
   extern __shared__ __align__(16) double cd_sm[];
   double* Ls = cd_sm;                                       // L(i,k) at Ls[i + k*(N+1)]
@@ -446,9 +447,12 @@ chol_chain_dinv_kernel(const __grid_constant__ CholDev P, const int* __restrict_
   __syncthreads();
   const int* dj = desc + (size_t)blockIdx.x * CD_INTS;  // the inverse goes behind the packed rows of the link
   double* out = pack + cd_i64(dj, CD_PACK) + (size_t)(dj[CD_NROW] - dj[CD_NCOL]) * D * N;
+  double* out2 = Dinv + sn_dinvptr[J];  // ... and where the dataflow kernel keeps its inverses (sparse_inverse.cuh reads it)
   for (int q = threadIdx.x; q < N * N; q += blockDim.x) {
     const int c = q / N, r = q - c * N;  // out(r,c) = inv(r,c) = Zt[c + r*N]
-    out[q] = r >= c ? Zt[c + r * N] : 0.0;
+    const double v = r >= c ? Zt[c + r * N] : 0.0;
+    out[q] = v;
+    out2[q] = v;
   }
 }
 

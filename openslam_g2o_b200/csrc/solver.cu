@@ -1207,9 +1207,10 @@ int b200_solve(b200_ctx* c) {
 
 // Solver::computeMarginals (core/block_solver.hpp:490-499 -> LinearSolver::solvePattern,
 // solvers/csparse/linear_solver_csparse.h:190-225 -> MarginalCovarianceCholesky, core/marginal_covariance_cholesky.cpp):
-// selected blocks of Hpp^-1.  The reference walks the scalar factor with a recursive formula; here every requested
-// block column is d solves with unit right-hand sides on the GPU factor (factorisation and forward substitution are
-// one kernel, so each solve refactors: fine for the handful of blocks a front-end asks for, slow for all of them).
+// selected blocks of Hpp^-1.  The reference walks the scalar factor with a recursive formula and a cache; here ONE
+// factorisation is followed by the same recursion in supernodal form on the GPU (sparse_inverse.cuh), which yields every
+// block on the pattern of L at the cost of one more factorisation; a requested block outside that pattern (no fill
+// between the two poses) falls back to d unit solves for its block column.
 int b200_compute_marginals(b200_ctx* c, int nblocks, const int32_t* rows, const int32_t* cols, double* out) {
   return guarded(c, [&]() -> int {
     NEED_DEVICE(c);
@@ -1220,28 +1221,58 @@ int b200_compute_marginals(b200_ctx* c, int nblocks, const int32_t* rows, const 
     const int d = c->pd, n = c->sizeP;
     for (int q = 0; q < nblocks; ++q)
       if (rows[q] < 0 || rows[q] >= c->np || cols[q] < 0 || cols[q] >= c->np) return fail(c, B200_ERR_INVALID, "block index out of range");
-    std::vector<int> order(nblocks);
-    for (int q = 0; q < nblocks; ++q) order[q] = q;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return cols[a] < cols[b2]; });
+    cudaStream_t s = c->stream;
     DevBuf<double> rhs, xs;
     rhs.alloc(n); xs.alloc(n);
+    // (1) ONE factorisation of Hpp (lambda = 0; the forward substitution that rides along gets a zero right-hand side),
+    //     then the sparse inverse subset on the factor: every requested block on the pattern of L comes out of one
+    //     sweep down the supernodal tree (chol.h: sparse_inverse)
+    {
+      B200_CUDA(cudaMemsetAsync(rhs.p, 0, n * sizeof(double), s));
+      c->chol.factor(c->d_Hpp.p, nullptr, rhs.p, s, &c->lc, nullptr);
+      int status = 0;
+      B200_CUDA(cudaMemcpyAsync(&status, c->chol.status_ptr(), sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      if (status) return (int)B200_NOT_POSITIVE_DEFINITE;
+    }
+    std::vector<int> in_pattern, outside;
+    std::vector<long long> off;
+    std::vector<int> ld;
+    std::vector<unsigned char> trans;
+    for (int q = 0; q < nblocks; ++q) {
+      long long o; int l; bool t;
+      if (c->chol.locate_inverse_block(rows[q], cols[q], &o, &l, &t)) { in_pattern.push_back(q); off.push_back(o); ld.push_back(l); trans.push_back(t); }
+      else outside.push_back(q);
+    }
+    if (!in_pattern.empty()) {
+      c->chol.sparse_inverse(s, &c->lc);
+      const int m = (int)in_pattern.size();
+      DevBuf<long long> d_off; DevBuf<int> d_ld; DevBuf<unsigned char> d_trans; DevBuf<double> d_out;
+      d_off.upload(off, s); d_ld.upload(ld, s); d_trans.upload(trans, s); d_out.alloc((size_t)m * d * d);
+      c->chol.gather_inverse_blocks(m, d_off.p, d_ld.p, d_trans.p, d_out.p, s, &c->lc);
+      std::vector<double> h((size_t)m * d * d);
+      B200_CUDA(cudaMemcpyAsync(h.data(), d_out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      for (int k = 0; k < m; ++k) memcpy(out + (size_t)in_pattern[k] * d * d, &h[(size_t)k * d * d], (size_t)d * d * sizeof(double));
+    }
+    // (2) blocks outside the pattern of L (the reference's recursion reaches them through entries it has to create on the
+    //     way): columns of the inverse by unit solves, one block column at a time
+    const int nout = (int)outside.size();
+    std::vector<int> order(outside);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return cols[a] < cols[b2]; });
     std::vector<double> hx(n);
     const double one = 1.0;
-    cudaStream_t s = c->stream;
-    for (int q0 = 0; q0 < nblocks;) {
+    for (int q0 = 0; q0 < nout;) {
       const int cb = cols[order[q0]];
       int q1 = q0;
-      while (q1 < nblocks && cols[order[q1]] == cb) ++q1;
+      while (q1 < nout && cols[order[q1]] == cb) ++q1;
       for (int k = 0; k < d; ++k) {
         B200_CUDA(cudaMemsetAsync(rhs.p, 0, n * sizeof(double), s));
         B200_CUDA(cudaMemcpyAsync(rhs.p + (size_t)cb * d + k, &one, sizeof(double), cudaMemcpyHostToDevice, s));
         c->chol.factor(c->d_Hpp.p, nullptr, rhs.p, s, &c->lc, nullptr);
         c->chol.solve(rhs.p, xs.p, s, &c->lc, nullptr);
-        int status = 0;
-        B200_CUDA(cudaMemcpyAsync(&status, c->chol.status_ptr(), sizeof(int), cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaMemcpyAsync(hx.data(), xs.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));
-        if (status) return (int)B200_NOT_POSITIVE_DEFINITE;
         for (int q = q0; q < q1; ++q) {
           const int req = order[q];
           for (int i = 0; i < d; ++i) out[(size_t)req * d * d + i + (size_t)k * d] = hx[(size_t)rows[req] * d + i];

@@ -9,6 +9,7 @@
 
 #include "block_amd.h"
 #include "symbolic.h"
+#include "spinv_lookup.h"
 
 using namespace g2o_b200;
 
@@ -38,12 +39,10 @@ extern "C" int hx_analyze(int nb, int d, const int* cp, const int* ri, int max_c
   return 0;
 }
 
-extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const double* vals, double lambda,
-                        const double* b, double* x, int max_cols, int relax) {
-  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
-  apply_chain_options(o);
-  SymbolicFactor S = analyze(nb, d, cp, ri, o);
-  std::vector<double> L(S.factor_doubles, 0.0);
+// numeric factorisation exactly along the plan (tiles / work items / chunks / tail chain); L11 stays in the panel
+static int hx_factor_impl(const SymbolicFactor& S, int nb, int d, const int* cp, const double* vals, double lambda,
+                          std::vector<double>& L) {
+  L.assign(S.factor_doubles, 0.0);
   const int nblk = cp[nb];
   for (int k = 0; k < nblk; ++k)
     for (int c = 0; c < d; ++c)
@@ -182,6 +181,16 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
   }
   for (int s = 0; s < S.nsn; ++s) if (!done[s]) return -4;
   (void)nt;
+  return 0;
+}
+
+extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const double* vals, double lambda,
+                        const double* b, double* x, int max_cols, int relax) {
+  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
+  apply_chain_options(o);
+  SymbolicFactor S = analyze(nb, d, cp, ri, o);
+  std::vector<double> L;
+  if (int rc = hx_factor_impl(S, nb, d, cp, vals, lambda, L)) return rc;
   // solve: y = P b ; forward (pull) ; backward ; x = P^T y
   const int n = nb * d;
   std::vector<double> y(n);
@@ -227,6 +236,74 @@ extern "C" int hx_solve(int nb, int d, const int* cp, const int* ri, const doubl
         }
       }
   for (int k = 0; k < nb; ++k) for (int r = 0; r < d; ++r) x[S.perm[k] * d + r] = y[k * d + r];
+  return 0;
+}
+
+// Sparse inverse subset along the plan of sparse_inverse.cuh (same recursion, same block lookup: spinv_lookup.h), top of
+// the supernodal tree first.  out: the requested blocks (ORIGINAL block indices) of (A + lambda I)^-1, d*d column-major;
+// found[q] = 0 when block q is outside the pattern of the factor (out left untouched).
+extern "C" int hx_sparse_inverse(int nb, int d, const int* cp, const int* ri, const double* vals, double lambda, int nreq,
+                                 const int* rows, const int* cols, double* out, int* found, int max_cols, int relax) {
+  SymbolicOptions o; o.max_panel_cols_scalar = max_cols; o.relax = relax != 0; o.nd_levels = g_nd_levels; o.nd_min_part = 4; o.relax_frac = g_relax_frac;
+  apply_chain_options(o);
+  SymbolicFactor S = analyze(nb, d, cp, ri, o);
+  std::vector<double> L;
+  if (int rc = hx_factor_impl(S, nb, d, cp, vals, lambda, L)) return rc;
+  std::vector<double> Z(S.factor_doubles, 0.0);
+  const long long* lptr = reinterpret_cast<const long long*>(S.sn_lptr.data());
+  auto locate = [&](int gp, int gq, int* ld) {
+    return spinv_locate(gp, gq, d, S.col2sn.data(), S.sn_col0.data(), S.sn_ncol.data(), S.sn_nrow.data(), S.sn_rowptr.data(), S.sn_rows.data(), lptr, ld);
+  };
+  for (int J = S.nsn - 1; J >= 0; --J) {  // parents have larger indices: every ancestor is final
+    if (S.sn_parent[J] >= 0 && S.sn_parent[J] <= J) return -200;
+    const int nr = S.sn_nrow[J], nc = S.sn_ncol[J], M = nr * d, N = nc * d, B = M - N;
+    const double* P = L.data() + S.sn_lptr[J];
+    double* Zp = Z.data() + S.sn_lptr[J];
+    const int* jrows = S.sn_rows.data() + S.sn_rowptr[J];
+    std::vector<double> Di((size_t)N * N, 0.0), Y((size_t)B * N, 0.0);  // Di = L11^-1 (lower), Y = L21 Di
+    for (int j = 0; j < N; ++j)
+      for (int i = j; i < N; ++i) {
+        double s = i == j ? 1.0 : 0.0;
+        for (int k = j; k < i; ++k) s -= P[i + (size_t)k * M] * Di[k + (size_t)j * N];
+        Di[i + (size_t)j * N] = s / P[i + (size_t)i * M];
+      }
+    for (int c = 0; c < N; ++c)
+      for (int r = 0; r < B; ++r) {
+        double s = 0;
+        for (int k = c; k < N; ++k) s += P[N + r + (size_t)k * M] * Di[k + (size_t)c * N];
+        Y[r + (size_t)c * B] = s;
+      }
+    for (int p = nc; p < nr; ++p)
+      for (int q = nc; q < nr; ++q) {
+        const int gp = jrows[p], gq = jrows[q];
+        int ld;
+        const long long off = gp >= gq ? locate(gp, gq, &ld) : locate(gq, gp, &ld);
+        if (off < 0) return -201;  // the pattern of L is closed under this recursion
+        for (int i = 0; i < d; ++i)
+          for (int j = 0; j < d; ++j) {
+            const double g = gp >= gq ? Z[off + i + (size_t)j * ld] : Z[off + j + (size_t)i * ld];
+            for (int c = 0; c < N; ++c) Zp[p * d + i + (size_t)c * M] -= g * Y[(q - nc) * d + j + (size_t)c * B];
+          }
+      }
+    for (int b = 0; b < N; ++b)
+      for (int a = 0; a < N; ++a) {
+        double s = 0;
+        for (int k = std::max(a, b); k < N; ++k) s += Di[k + (size_t)a * N] * Di[k + (size_t)b * N];
+        for (int r = 0; r < B; ++r) s -= Y[r + (size_t)a * B] * Zp[N + r + (size_t)b * M];
+        Zp[a + (size_t)b * M] = s;
+      }
+  }
+  for (int q = 0; q < nreq; ++q) {
+    int pr = S.pinv[rows[q]], pc = S.pinv[cols[q]];
+    const bool tr = pr < pc;
+    if (tr) std::swap(pr, pc);
+    int ld;
+    const long long off = locate(pr, pc, &ld);
+    found[q] = off >= 0;
+    if (off < 0) continue;
+    for (int j = 0; j < d; ++j)
+      for (int i = 0; i < d; ++i) out[(size_t)q * d * d + i + j * d] = tr ? Z[off + j + (size_t)i * ld] : Z[off + i + (size_t)j * ld];
+  }
   return 0;
 }
 

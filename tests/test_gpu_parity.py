@@ -277,6 +277,17 @@ def test_marginals_match_dense_inverse_of_the_oracle_hessian(name):
     rng = np.random.default_rng(4)
     pairs = [(int(i), int(i)) for i in rng.choice(nb, 4, replace=False)] + \
             [(int(rng.integers(nb)), int(rng.integers(nb))) for _ in range(3)] + [(0, nb - 1), (nb - 1, nb - 1)]
+    # ... every block of the Hessian's own pattern, in both orientations: all of them lie on the pattern of the factor and
+    # come out of ONE sweep of the supernodal sparse-inverse recursion (csrc/sparse_inverse.cuh); the random pairs above
+    # mostly do not (unit-solve path)
+    pairs += [(int(r), int(c)) for r, c in zip(rows, cols)] + [(int(c), int(r)) for r, c in zip(rows[:50], cols[:50])]
+    launches0 = ctx.launch_count()
+    got_diag = ctx.compute_marginals([(i, i) for i in range(nb)])
+    sweep_launches = ctx.launch_count() - launches0
+    for i in range(0, nb, max(1, nb // 97)):
+        assert np.abs(got_diag[i] - inv[i * d:(i + 1) * d, i * d:(i + 1) * d]).max() <= 1e-8 * np.abs(inv).max(), i
+    # all nb diagonal blocks cost one factorisation + one sweep (2 launches per tree level), not nb * d factorisations
+    assert sweep_launches < 3 * nb
     got = ctx.compute_marginals(pairs)
     # the reference's recursion on the CSparse factor, restated (minutes on the sphere: intel only)
     ref_o = o.compute_marginals(pairs) if name == "intel" else got

@@ -203,3 +203,45 @@ def test_wide_tile_plan(hx):
                     assert hx.hx_check_flow(nb, 6, _p(cp), _p(ri), maxc, relax, gi) == 0, (trial, nb, maxc, relax, gi)
     finally:
         hx.hx_set_wide(-1)
+
+
+@pytest.mark.parametrize("d", [3, 6])
+def test_sparse_inverse_recursion_matches_dense_inverse(hx, d):
+    """Takahashi recursion in supernodal form (csrc/sparse_inverse.cuh runs the same steps with the same block lookup,
+    csrc/spinv_lookup.h): every block on the pattern of the factor - all diagonal blocks and all blocks of the input
+    pattern among them - equals the block of the dense inverse; blocks outside the pattern are reported as such
+    (core/marginal_covariance_cholesky.cpp:71-100 is the scalar form of this recursion)"""
+    rng = np.random.default_rng(40 + d)
+    for trial in range(16):
+        nb = int(rng.integers(2, 70))
+        kind = trial % 4
+        if kind == 0:
+            edges = [(int(rng.integers(nb)), int(rng.integers(nb))) for _ in range(2 * nb)]
+        elif kind == 1:
+            s = max(2, int(np.sqrt(nb)))
+            edges = [(i, i + 1) for i in range(nb - 1) if (i + 1) % s] + [(i, i + s) for i in range(nb - s)]
+        elif kind == 2:
+            edges = [(i, j) for i in range(nb) for j in range(i + 1, min(nb, i + 5))]
+        else:
+            edges = [(i, i + 1) for i in range(nb - 1)]
+        cp, ri, vals, A = random_spd_blocks(rng, nb, d, edges)
+        v = np.ascontiguousarray(np.transpose(vals, (0, 2, 1)))
+        inv = np.linalg.inv(A + 0.25 * np.eye(nb * d))
+        pairs = [(i, i) for i in range(nb)] + [(int(ri[k]), c) for c in range(nb) for k in range(cp[c], cp[c + 1])]
+        pairs += [(c, int(ri[k])) for c in range(nb) for k in range(cp[c], cp[c + 1])][:20]   # transposed requests
+        pairs += [(int(rng.integers(nb)), int(rng.integers(nb))) for _ in range(20)]         # may be outside
+        rows = np.asarray([p[0] for p in pairs], np.int32)
+        cols = np.asarray([p[1] for p in pairs], np.int32)
+        for maxc, relax in [(96, 1), (12, 1), (6, 0)]:
+            out = np.zeros((len(pairs), d, d))
+            found = np.zeros(len(pairs), np.int32)
+            rc = hx.hx_sparse_inverse(nb, d, _p(cp), _p(ri), _p(v), C.c_double(0.25), len(pairs), _p(rows), _p(cols),
+                                      _p(out), _p(found), maxc, relax)
+            assert rc == 0, (rc, trial, nb, maxc, relax)
+            n_in = nb + int(cp[nb])
+            assert found[:n_in].all()   # diagonal blocks and the input pattern are always on the pattern of L
+            for q, (r, c) in enumerate(pairs):
+                if not found[q]:
+                    continue
+                ref = inv[r * d:(r + 1) * d, c * d:(c + 1) * d]
+                assert np.abs(out[q].T - ref).max() <= 1e-9 * np.abs(inv).max(), (trial, q, r, c)
