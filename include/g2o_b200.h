@@ -15,8 +15,10 @@
  *                     XYZ: [x y z]                                  (types/sba/types_sba.h:136-156)
  *                     SE3_EXPMAP: [t(3) q(x y z w) f f cx cy baseline]  world->camera SE3Quat (types/sba/
  *                          types_six_dof_expmap.h:87-105) + the CameraParameters its edges name (:45-80)
- *   edge measurement  SE2: [x y theta] of Z; SE3: [R t] of Z (12); P2MC, XYZ2UV: [u v]
- *   edge information  full D x D column-major (D = 3, 6, 2)
+ *                     XY:  [x y]                                    (types/slam2d/vertex_point_xy.h)
+ *                     (XYZ also stands for VertexPointXYZ, types/slam3d/vertex_pointxyz.h: same state, same update)
+ *   edge measurement  SE2: [x y theta] of Z; SE3: [R t] of Z (12); P2MC, XYZ2UV: [u v]; SE2_XY: [x y]; SE3_XYZ: [x y z]
+ *   edge information  full D x D column-major (D = 3, 6, 2, 2, 2, 3)
  */
 #ifndef G2O_B200_H
 #define G2O_B200_H
@@ -34,11 +36,21 @@ extern "C" {
 #define B200_ERR_COLLECTIVE (-5)
 #define B200_ERR_EXCEPTION (-6)        /* a C++ exception other than a CUDA failure (std::bad_alloc, ...) was caught at the ABI */
 
-enum { B200_VERTEX_SE2 = 0, B200_VERTEX_SE3 = 1, B200_VERTEX_CAM = 2, B200_VERTEX_XYZ = 3, B200_VERTEX_SE3_EXPMAP = 4 };
-/* XYZ2UV = EdgeProjectXYZ2UV (types/sba/types_six_dof_expmap.h:133-155), the monocular edge of ba_demo / SE3 expmap BA */
-enum { B200_EDGE_SE2 = 0, B200_EDGE_SE3 = 1, B200_EDGE_P2MC = 2, B200_EDGE_XYZ2UV = 3 };
-#define B200_NUM_VERTEX_KINDS 5
-#define B200_NUM_EDGE_KINDS 4
+enum { B200_VERTEX_SE2 = 0, B200_VERTEX_SE3 = 1, B200_VERTEX_CAM = 2, B200_VERTEX_XYZ = 3, B200_VERTEX_SE3_EXPMAP = 4,
+       B200_VERTEX_XY = 5 };
+/* XYZ2UV = EdgeProjectXYZ2UV (types/sba/types_six_dof_expmap.h:133-155), the monocular edge of ba_demo / SE3 expmap BA.
+ * Landmark SLAM: SE2_XY = EdgeSE2PointXY (types/slam2d/edge_se2_pointxy.h:44-51, .cpp:67-95),
+ * SE3_XYZ = EdgeSE3PointXYZ (types/slam3d/edge_se3_pointxyz.cpp:98-135) with its ParameterSE3Offset
+ * (b200_set_sensor_offset).  They go with the pose-pose edges of their pose kind in ONE context, landmarks NOT
+ * marginalized: the reference's variable-block-size path (BlockSolverX, `gn_var` / `lm_var`, solvers/csparse/
+ * solver_csparse.cpp:53-55, the set-up of examples/tutorial_slam2d).  Here the landmark blocks are padded to the pose
+ * dimension (2 -> 3, 3 -> 6; the padding rows / columns are decoupled unit-diagonal unknowns that stay 0), so the
+ * block pattern - and with it the block AMD ordering - is exactly the reference's, and x / b / Hpp blocks / marginals
+ * are reported in the padded layout (poseDim entries per vertex). */
+enum { B200_EDGE_SE2 = 0, B200_EDGE_SE3 = 1, B200_EDGE_P2MC = 2, B200_EDGE_XYZ2UV = 3, B200_EDGE_SE2_XY = 4,
+       B200_EDGE_SE3_XYZ = 5 };
+#define B200_NUM_VERTEX_KINDS 6
+#define B200_NUM_EDGE_KINDS 6
 enum { B200_GAUSS_NEWTON = 0, B200_LEVENBERG = 1 };
 /* OptimizationAlgorithm::SolverResult (core/optimization_algorithm.h:49): the value stored in b200_iter_stats.result.
  * The RETURN value of b200_algorithm_solve never uses -1 for it (that is B200_ERR_INVALID): a failed linear solve
@@ -84,10 +96,16 @@ const char* b200_version(void);
 int b200_set_vertices(b200_ctx* ctx, int kind, int n, const double* estimates,
                       const int32_t* hessian_index, const uint8_t* marginalized);
 /* vi/vj index into the vertex array of the kind the edge type expects
- * (SE2: SE2,SE2; SE3: SE3,SE3; P2MC: vi = XYZ point, vj = CAM; XYZ2UV: vi = XYZ point, vj = SE3_EXPMAP).
- * Order = active edge order (internalId). */
+ * (SE2: SE2,SE2; SE3: SE3,SE3; P2MC: vi = XYZ point, vj = CAM; XYZ2UV: vi = XYZ point, vj = SE3_EXPMAP;
+ * SE2_XY: vi = SE2 pose, vj = XY point; SE3_XYZ: vi = SE3 pose, vj = XYZ point).
+ * Order = active edge order (internalId).  A context holds one pose-pose / projection edge set and, for landmark
+ * SLAM, one pose-landmark edge set (SE2_XY with SE2, SE3_XYZ with SE3): a call replaces the set of its own class;
+ * n = 0 removes it. */
 int b200_set_edges(b200_ctx* ctx, int kind, int n, const int32_t* vi, const int32_t* vj,
                    const double* measurement, const double* information);
+/* ParameterSE3Offset of the SE3_XYZ edges (types/slam3d/parameter_se3_offset.h: sensor pose on the robot), one for
+ * the whole context: isometry [R(3x3 col-major) t(3)].  Default: identity. */
+int b200_set_sensor_offset(b200_ctx* ctx, const double* isometry12);
 /* landmark sharding: this context owns the landmarks / edges it was given; cameras are
  * replicated.  After the local Schur reduction [Hschur | bschur | scalars] is all-reduced through fn. */
 int b200_set_allreduce(b200_ctx* ctx, b200_allreduce_fn fn, void* user, int rank, int world_size);
@@ -263,6 +281,10 @@ int b200_graph_set_fixed(b200_graph* g, int id, int fixed);
  * XYZ2UV edges that name it (payload of such an edge: paramId u v i00 i01 i11, types_six_dof_expmap.cpp:241-256).
  * All edges of one pose must name parameters with equal values (the intrinsics ride in the pose's estimate row). */
 int b200_graph_add_camera_parameters(b200_graph* g, int id, double focal_length, double cx, double cy, double baseline);
+/* PARAMS_SE3OFFSET id x y z qx qy qz qw (types/slam3d/parameter_se3_offset.cpp:47-56); has to precede the SE3_XYZ
+ * edges (EDGE_SE3_TRACKXYZ; payload paramId x y z + upper triangle of the information, edge_se3_pointxyz.cpp:62-84)
+ * that name it.  All SE3_XYZ edges of a graph must name offsets with equal values. */
+int b200_graph_add_se3_offset(b200_graph* g, int id, const double* xyz_qxyzw);
 /* returns the gauge vertex id fixed (or -1 if none needed) */
 int b200_graph_setup_cli(b200_graph* g, int requires_marginalize);
 int b200_graph_initialize(b200_graph* g);

@@ -15,18 +15,18 @@ LIB_PATH = os.environ.get("G2O_B200_LIB", os.path.join(_HERE, "libg2o_b200.so"))
 OK = 0
 NOT_POSITIVE_DEFINITE = 1
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_COLLECTIVE, ERR_EXCEPTION = -1, -2, -3, -4, -5, -6
-VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP = 0, 1, 2, 3, 4
-EDGE_SE2, EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV = 0, 1, 2, 3
-NUM_VERTEX_KINDS, NUM_EDGE_KINDS = 5, 4
+VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP, VERTEX_XY = 0, 1, 2, 3, 4, 5
+EDGE_SE2, EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV, EDGE_SE2_XY, EDGE_SE3_XYZ = 0, 1, 2, 3, 4, 5
+NUM_VERTEX_KINDS, NUM_EDGE_KINDS = 6, 6
 GAUSS_NEWTON, LEVENBERG = 0, 1
 COMM_ID_BYTES = 128
 RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1   # values of IterStats.result (g2o's SolverResult)
 SOLVE_FAIL = 3                                        # return value of b200_algorithm_solve for a failed solve
 
-VERTEX_EST_LEN = {VERTEX_SE2: 3, VERTEX_SE3: 12, VERTEX_CAM: 12, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 12}
-VERTEX_DIM = {VERTEX_SE2: 3, VERTEX_SE3: 6, VERTEX_CAM: 6, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 6}
-EDGE_DIM = {EDGE_SE2: 3, EDGE_SE3: 6, EDGE_P2MC: 2, EDGE_XYZ2UV: 2}
-EDGE_MEAS_LEN = {EDGE_SE2: 3, EDGE_SE3: 12, EDGE_P2MC: 2, EDGE_XYZ2UV: 2}
+VERTEX_EST_LEN = {VERTEX_SE2: 3, VERTEX_SE3: 12, VERTEX_CAM: 12, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 12, VERTEX_XY: 2}
+VERTEX_DIM = {VERTEX_SE2: 3, VERTEX_SE3: 6, VERTEX_CAM: 6, VERTEX_XYZ: 3, VERTEX_SE3_EXPMAP: 6, VERTEX_XY: 2}
+EDGE_DIM = {EDGE_SE2: 3, EDGE_SE3: 6, EDGE_P2MC: 2, EDGE_XYZ2UV: 2, EDGE_SE2_XY: 2, EDGE_SE3_XYZ: 3}
+EDGE_MEAS_LEN = {EDGE_SE2: 3, EDGE_SE3: 12, EDGE_P2MC: 2, EDGE_XYZ2UV: 2, EDGE_SE2_XY: 2, EDGE_SE3_XYZ: 3}
 
 
 class IterStats(C.Structure):
@@ -63,6 +63,7 @@ def _load():
         "b200_version": (C.c_char_p, []),
         "b200_set_vertices": (i32, [vp, i32, i32, vp, vp, vp]),
         "b200_set_edges": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "b200_set_sensor_offset": (i32, [vp, vp]),
         "b200_set_allreduce": (i32, [vp, ALLREDUCE_FN, vp, i32, i32]),
         "b200_add_schur_pattern": (i32, [vp, i32, vp, vp]),
         "b200_comm_unique_id": (i32, [vp, i32]),
@@ -121,6 +122,7 @@ def _load():
         "b200_graph_add_edges": (i32, [vp, i32, i32, vp, vp, vp, i32]),
         "b200_graph_set_fixed": (i32, [vp, i32, i32]),
         "b200_graph_add_camera_parameters": (i32, [vp, i32, dbl, dbl, dbl, dbl]),
+        "b200_graph_add_se3_offset": (i32, [vp, i32, vp]),
         "b200_graph_setup_cli": (i32, [vp, i32]),
         "b200_graph_initialize": (i32, [vp]),
         "b200_graph_counts": (i32, [vp, vp, vp]),

@@ -55,6 +55,16 @@ __global__ void chol_add_lambda_kernel(int nb, const long long* __restrict__ dia
   L[diag_dst[k] + r + (long long)r * diag_ld[k]] += *lambda;
 }
 
+template <int D>
+__global__ void chol_add_diag_extra_kernel(int nb, const long long* __restrict__ diag_dst, const int* __restrict__ diag_ld,
+                                           const int* __restrict__ perm, const double* __restrict__ extra,
+                                           double* __restrict__ L) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb * D) return;
+  const int k = idx / D, r = idx - k * D;   // k = permuted block column, perm[k] = its original index
+  L[diag_dst[k] + r + (long long)r * diag_ld[k]] += extra[(long long)perm[k] * D + r];
+}
+
 // ---------------------------------------------------------------------------------------------
 // numeric factorisation
 //   GROUP  : one CTA per (destination tile of 48 x 48 scalars, split-K group): pulls the update pieces that land in
@@ -1258,6 +1268,10 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
     count();
     if (d_lambda) {
       chol_add_lambda_kernel<D><<<ceil_div((int64_t)S.nb * D, 256), 256, 0, s>>>(S.nb, d_diag_dst_.p, d_diag_ld_.p, d_lambda, L);
+      count();
+    }
+    if (d_diag_extra_) {
+      chol_add_diag_extra_kernel<D><<<ceil_div((int64_t)S.nb * D, 256), 256, 0, s>>>(S.nb, d_diag_dst_.p, d_diag_ld_.p, d_perm_.p, d_diag_extra_, L);
       count();
     }
     // the forward substitution rides along with the factorisation (one more row per panel)

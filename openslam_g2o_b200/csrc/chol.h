@@ -37,6 +37,9 @@ class CholeskyGpu {
   // x = A^-1 b for the b given to the preceding factor() (device, length nb*d, original ordering): the backward
   // sweep (one persistent dataflow kernel) + un-permutation.  One solve() per factor().  Asynchronous on s.
   void solve(const double* d_b, double* d_x, cudaStream_t s, LaunchCounter* lc, EventProfiler* prof = nullptr);
+  // extra[i] (device, length nb*d, ORIGINAL ordering; nullptr = none) is added to diagonal entry i by every factor():
+  // the unit diagonal of padding unknowns (landmark blocks padded to the pose dimension, solver.cu)
+  void set_diagonal_extra(const double* d_extra) { d_diag_extra_ = d_extra; }
   int* status_ptr() { return d_counters_.p + 2; }  // device int: 0 ok, 1 not positive definite
   double* factor_values() { return d_L_.p; }
   // Sparse inverse subset of the matrix of the preceding factor(): every block of A^-1 on the pattern of L + L^T
@@ -52,6 +55,7 @@ class CholeskyGpu {
 
  private:
   bool analyzed_ = false;
+  const double* d_diag_extra_ = nullptr;
   SymbolicFactor S_;
   DevBuf<int> d_sn_col0_, d_sn_ncol_, d_sn_nrow_, d_sn_rowptr_, d_sn_rows_;
   DevBuf<long long> d_sn_lptr_;

@@ -492,6 +492,58 @@ template <int MODEL> G2O_HD void ba_jacobians(const double* der, const double* c
 }
 template <int MODEL> G2O_HD void ba_oplus(double* est, const double* u) { if (MODEL == 0) cam_oplus(est, u); else expmap_oplus(est, u); }
 
+// ------------------------------------------------------------------ landmark SLAM edges
+// EdgeSE2PointXY::computeError (types/slam2d/edge_se2_pointxy.h:46-51): e = x^-1 * l - z, SE2 * Vector2d = R(th) v + t
+G2O_HD void se2_xy_error(const SE2& x, const double* l, const double* z, double* e) {
+  const SE2 xi = se2_inv(x);
+  double s, c;
+  sincos(xi.th, &s, &c);
+  e[0] = (c * l[0] - s * l[1] + xi.x) - z[0];
+  e[1] = (s * l[0] + c * l[1] + xi.y) - z[1];
+}
+// EdgeSE2PointXY::linearizeOplus (types/slam2d/edge_se2_pointxy.cpp:67-95): A 2x3 (pose), B 2x2 (point), col-major
+G2O_HD void se2_xy_jacobians(const SE2& x, const double* l, double* A, double* B) {
+  const double x1 = x.x, y1 = x.y, x2 = l[0], y2 = l[1];
+  double aux_3, aux_1;
+  sincos(x.th, &aux_3, &aux_1);
+  const double aux_2 = -aux_1;
+  A[0] = aux_2; A[2] = -aux_3; A[4] = aux_1 * y2 - aux_1 * y1 - aux_3 * x2 + aux_3 * x1;
+  A[1] = aux_3; A[3] = aux_2;  A[5] = -aux_3 * y2 + aux_3 * y1 - aux_1 * x2 + aux_1 * x1;
+  B[0] = aux_1; B[2] = aux_3;
+  B[1] = -aux_3; B[3] = aux_1;
+}
+// EdgeSE3PointXYZ::computeError (types/slam3d/edge_se3_pointxyz.cpp:98-108): e = w2n * l - z with the cache
+// w2n = (X * offset)^-1 (parameter_se3_offset.cpp:75-80)
+G2O_HD void se3_xyz_error(const Iso& X, const Iso& offset, const double* l, const double* z, double* e) {
+  const Iso w2n = iso_inverse(iso_mul(X, offset));
+#pragma unroll
+  for (int r = 0; r < 3; ++r) e[r] = (w2n.R[r] * l[0] + w2n.R[r + 3] * l[1] + w2n.R[r + 6] * l[2] + w2n.t[r]) - z[r];
+}
+// EdgeSE3PointXYZ::linearizeOplus (types/slam3d/edge_se3_pointxyz.cpp:110-135): J = [-I | 2 [Zcam]x^T-pattern | R(w2l)],
+// Zcam = w2l * l, w2l = X^-1; Jhom = R(offset^-1) * J; A = Jhom(:, 0:6) 3x6, B = Jhom(:, 6:9) 3x3, col-major
+G2O_HD void se3_xyz_jacobians(const Iso& X, const Iso& offset, const double* l, double* A, double* B) {
+  const Iso w2l = iso_inverse(X);
+  double Z[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) Z[r] = w2l.R[r] * l[0] + w2l.R[r + 3] * l[1] + w2l.R[r + 6] * l[2] + w2l.t[r];
+  double J[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) J[i] = 0.0;
+  J[0] = -1.0; J[4] = -1.0; J[8] = -1.0;
+  J[0 + 3 * 4] = -2 * Z[2]; J[0 + 3 * 5] = 2 * Z[1];
+  J[1 + 3 * 3] = 2 * Z[2];  J[1 + 3 * 5] = -2 * Z[0];
+  J[2 + 3 * 3] = -2 * Z[1]; J[2 + 3 * 4] = 2 * Z[0];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) J[18 + i] = w2l.R[i];
+  const Iso oi = iso_inverse(offset);
+  double Jh[27];
+  mm<3, 3, 9>(oi.R, J, Jh);
+#pragma unroll
+  for (int i = 0; i < 18; ++i) A[i] = Jh[i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) B[i] = Jh[18 + i];
+}
+
 // Eigen fixed-size 3x3 inverse (cofactors / determinant), used at block_solver.hpp:389
 G2O_HD void inverse3(const double* m, double* r) {
 #define M_(i, j) m[(i) + 3 * (j)]

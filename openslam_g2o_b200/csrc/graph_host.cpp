@@ -63,11 +63,12 @@ struct DoublePool {
     return r;
   }
 };
-int vdim(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 6; }
-int vest(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12; }
-int edim(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
-int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
+int vdim(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : kind == B200_VERTEX_XY ? 2 : 6; }
+int vest(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : kind == B200_VERTEX_XY ? 2 : 12; }
+int edim(int kind) { return (kind == B200_EDGE_SE2 || kind == B200_EDGE_SE3_XYZ) ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
+int emeas(int kind) { return (kind == B200_EDGE_SE2 || kind == B200_EDGE_SE3_XYZ) ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
 bool is_ba(int ekind) { return ekind == B200_EDGE_P2MC || ekind == B200_EDGE_XYZ2UV; }
+bool is_landmark_edge(int ekind) { return ekind == B200_EDGE_SE2_XY || ekind == B200_EDGE_SE3_XYZ; }
 // SE3Quat::inverse (types/slam3d/se3quat.h:125-130) on [t3 | q(xyzw)4]: r = conj(q), t = r * (-t) with Eigen's
 // quaternion * vector (v + w uv + qv x uv, uv = 2 qv x v); no normalisation
 void se3quat_inverse(const double* a, double* r) {
@@ -111,6 +112,8 @@ struct b200_graph {
   std::vector<int> active_edges;            // edge indices, internalId order
   std::vector<int> kind_slots[B200_NUM_VERTEX_KINDS];  // per kind: vertex indices handed to the context (ascending id)
   std::map<int, std::array<double, 4>> camera_parameters;  // PARAMS_CAMERAPARAMETERS id -> f cx cy baseline
+  std::map<int, std::array<double, 12>> se3_offsets;       // PARAMS_SE3OFFSET id -> isometry [R | t]
+  std::map<int, std::array<double, 7>> se3_offsets_text;   // ... as read (x y z qx qy qz qw), for save()
   // landmark sharding of the last upload: per XYZ slot the row handed to the context (-1: another shard owns it).
   // Empty = nothing sharded (row i of the context is slot i).  b200_graph_download scatters through it.
   std::vector<int> uploaded_lm_row;
@@ -141,6 +144,10 @@ bool vertex_read(HVertex& v, const double* p, int n) {
     case B200_VERTEX_XYZ:
       if (n < 3) return false;
       v.est[0] = p[0]; v.est[1] = p[1]; v.est[2] = p[2];
+      return true;
+    case B200_VERTEX_XY:  // types/slam2d/vertex_point_xy.cpp read
+      if (n < 2) return false;
+      v.est[0] = p[0]; v.est[1] = p[1];
       return true;
     case B200_VERTEX_SE3: {  // fromVectorQT: quaternion used un-normalised (isometry3d_mappings.cpp:131-136)
       if (n < 7) return false;
@@ -203,6 +210,20 @@ bool edge_read(HEdge& e, const double* p, int n) {
       e.info[0] = p[3]; e.info[1] = e.info[2] = p[4]; e.info[3] = p[5];
       return true;
     }
+    case B200_EDGE_SE2_XY: {  // types/slam2d/edge_se2_pointxy.cpp:41-47: x y i00 i01 i11
+      if (n < 5) return false;
+      e.meas[0] = p[0]; e.meas[1] = p[1];
+      e.info[0] = p[2]; e.info[1] = e.info[2] = p[3]; e.info[3] = p[4];
+      return true;
+    }
+    case B200_EDGE_SE3_XYZ: {  // types/slam3d/edge_se3_pointxyz.cpp:62-84: paramId x y z + upper triangle (identity if absent)
+      if (n < 4) return false;
+      e.param = (int)p[0];
+      e.meas[0] = p[1]; e.meas[1] = p[2]; e.meas[2] = p[3];
+      int k = 4;
+      for (int i = 0; i < 3 && k < n; ++i) for (int j = i; j < 3 && k < n; ++j) { e.info[i + 3 * j] = p[k]; e.info[j + 3 * i] = p[k]; ++k; }
+      return true;
+    }
   }
   return false;
 }
@@ -221,12 +242,27 @@ void initial_estimate(b200_graph* g, const HEdge& e, bool to_from_from) {
     memcpy(B.R, b.est, 72); memcpy(B.t, b.est + 9, 24);
     if (to_from_from) { geo::Iso r = geo::iso_mul(A, Z); memcpy(b.est, r.R, 72); memcpy(b.est + 9, r.t, 24); }
     else { geo::Iso r = geo::iso_mul(B, geo::iso_inverse(Z)); memcpy(a.est, r.R, 72); memcpy(a.est + 9, r.t, 24); }
+  } else if (e.kind == B200_EDGE_SE2_XY && to_from_from) {  // edge_se2_pointxy.cpp:55-64: point = pose * measurement
+    double sn, cs;
+    sincos(a.est[2], &sn, &cs);
+    b.est[0] = cs * e.meas[0] - sn * e.meas[1] + a.est[0];
+    b.est[1] = sn * e.meas[0] + cs * e.meas[1] + a.est[1];
+  } else if (e.kind == B200_EDGE_SE3_XYZ && to_from_from) {  // edge_se3_pointxyz.cpp initialEstimate: pose * (offset * z)
+    geo::Iso A, O;
+    memcpy(A.R, a.est, 72); memcpy(A.t, a.est + 9, 24);
+    const std::array<double, 12>& of = g->se3_offsets[e.param];
+    memcpy(O.R, of.data(), 72); memcpy(O.t, of.data() + 9, 24);
+    const geo::Iso n2w = geo::iso_mul(A, O);
+    for (int r = 0; r < 3; ++r) b.est[r] = n2w.R[r] * e.meas[0] + n2w.R[r + 3] * e.meas[1] + n2w.R[r + 6] * e.meas[2] + n2w.t[r];
   }
 }
 int add_edge(b200_graph* g, int kind, int id1, int id2, const double* payload, int n) {
-  static const int vk0[4] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_XYZ, B200_VERTEX_XYZ};
-  static const int vk1[4] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_CAM, B200_VERTEX_SE3_EXPMAP};
+  static const int vk0[B200_NUM_EDGE_KINDS] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_XYZ, B200_VERTEX_XYZ, B200_VERTEX_SE2, B200_VERTEX_SE3};
+  static const int vk1[B200_NUM_EDGE_KINDS] = {B200_VERTEX_SE2, B200_VERTEX_SE3, B200_VERTEX_CAM, B200_VERTEX_SE3_EXPMAP, B200_VERTEX_XY, B200_VERTEX_XYZ};
   const std::array<double, 4>* cp = nullptr;
+  if (kind == B200_EDGE_SE3_XYZ) {  // resolveParameters: unknown ParameterSE3Offset id rejects the edge
+    if (n < 1 || !g->se3_offsets.count((int)payload[0])) { g->err = "SE3_XYZ edge names unknown ParameterSE3Offset"; return B200_ERR_INVALID; }
+  }
   if (kind == B200_EDGE_XYZ2UV) {  // OptimizableGraph::addEdge -> resolveParameters: unknown parameter id rejects the edge
     auto it = n >= 1 ? g->camera_parameters.find((int)payload[0]) : g->camera_parameters.end();
     if (it == g->camera_parameters.end()) { g->err = "XYZ2UV edge names unknown CameraParameters"; return B200_ERR_INVALID; }
@@ -310,8 +346,13 @@ void parse_chunk(const char* begin, const char* end, ParsedChunk& out) {
     else if (tag_is(tb, te, "VERTEX_SE2")) { r.type = REC_VERTEX; r.kind = B200_VERTEX_SE2; }
     else if (tag_is(tb, te, "VERTEX_CAM")) { r.type = REC_VERTEX; r.kind = B200_VERTEX_CAM; }
     else if (tag_is(tb, te, "VERTEX_SE3:EXPMAP")) { r.type = REC_VERTEX; r.kind = B200_VERTEX_SE3_EXPMAP; }
+    else if (tag_is(tb, te, "EDGE_SE2_XY")) { r.type = REC_EDGE; r.kind = B200_EDGE_SE2_XY; }
+    else if (tag_is(tb, te, "EDGE_SE3_TRACKXYZ")) { r.type = REC_EDGE; r.kind = B200_EDGE_SE3_XYZ; }
+    else if (tag_is(tb, te, "VERTEX_XY")) { r.type = REC_VERTEX; r.kind = B200_VERTEX_XY; }
+    else if (tag_is(tb, te, "VERTEX_TRACKXYZ")) { r.type = REC_VERTEX; r.kind = B200_VERTEX_XYZ; }
     else if (tag_is(tb, te, "FIX")) r.type = REC_FIX;
     else if (tag_is(tb, te, "PARAMS_CAMERAPARAMETERS")) r.type = REC_PARAMS;
+    else if (tag_is(tb, te, "PARAMS_SE3OFFSET")) { r.type = REC_PARAMS; r.kind = 1; }
     else { lp.skip_line(); continue; }  // unknown tags are skipped (optimizable_graph.cpp:417-423)
     const int nid = r.type == REC_EDGE ? 2 : r.type == REC_FIX ? 0 : 1;
     bool ok = true;
@@ -372,6 +413,18 @@ int b200_graph_add_camera_parameters(b200_graph* g, int id, double focal_length,
   if (!g) return B200_ERR_INVALID;
   if (g->camera_parameters.count(id)) { g->err = "duplicate parameter id"; return B200_ERR_INVALID; }  // ParameterContainer::addParameter
   g->camera_parameters[id] = {focal_length, cx, cy, baseline};
+  return B200_OK;
+}
+int b200_graph_add_se3_offset(b200_graph* g, int id, const double* o) {
+  if (!g || !o) return B200_ERR_INVALID;
+  if (g->se3_offsets.count(id)) { g->err = "duplicate parameter id"; return B200_ERR_INVALID; }
+  double q[4] = {o[3], o[4], o[5], o[6]};
+  quat_normalize(q);  // parameter_se3_offset.cpp:52-53
+  std::array<double, 12> iso;
+  geo::quat_to_R(q, iso.data());
+  iso[9] = o[0]; iso[10] = o[1]; iso[11] = o[2];
+  g->se3_offsets[id] = iso;
+  g->se3_offsets_text[id] = {o[0], o[1], o[2], q[0], q[1], q[2], q[3]};
   return B200_OK;
 }
 int b200_graph_set_fixed(b200_graph* g, int id, int fixed) {
@@ -448,7 +501,8 @@ int b200_graph_load(b200_graph* g, const char* path) {
           for (int i = 0; i < r.n; ++i) { int v = g->find((int)nums[i]); if (v >= 0) g->vertices[v].fixed = true; }
           break;
         case REC_PARAMS:  // optimizable_graph.cpp:398-415 + CameraParameters::read
-          if (r.n >= 4) b200_graph_add_camera_parameters(g, r.id0, nums[0], nums[1], nums[2], nums[3]);
+          if (r.kind == 1) { if (r.n >= 7) b200_graph_add_se3_offset(g, r.id0, nums); }
+          else if (r.n >= 4) b200_graph_add_camera_parameters(g, r.id0, nums[0], nums[1], nums[2], nums[3]);
           break;
         case REC_VERTEX: {
           int v = add_vertex(g, r.kind, r.id0);
@@ -521,9 +575,16 @@ int b200_graph_counts(b200_graph* g, int32_t* vc, int32_t* ec) {
 int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
   if (!g || !ctx || num_shards < 1 || shard < 0 || shard >= num_shards) return B200_ERR_INVALID;
   if (g->active_edges.empty()) { g->err = "call b200_graph_initialize first"; return B200_ERR_INVALID; }
-  const int ekind = g->edges[g->active_edges[0]].kind;
-  for (int k : g->active_edges) if (g->edges[k].kind != ekind) { g->err = "mixed edge types are not supported"; return B200_ERR_UNSUPPORTED; }
-  const bool ba = is_ba(ekind);
+  // one pose-pose / projection edge kind, and - landmark SLAM - one pose-landmark kind beside it
+  int ekind = -1, lkind = -1;
+  for (int k : g->active_edges) {
+    const int kd = g->edges[k].kind;
+    int& slot = is_landmark_edge(kd) ? lkind : ekind;
+    if (slot < 0) slot = kd;
+    else if (slot != kd) { g->err = "mixed edge types are not supported"; return B200_ERR_UNSUPPORTED; }
+  }
+  if (lkind >= 0 && ekind >= 0 && ekind != (lkind == B200_EDGE_SE2_XY ? B200_EDGE_SE2 : B200_EDGE_SE3)) { g->err = "mixed edge types are not supported"; return B200_ERR_UNSUPPORTED; }
+  const bool ba = ekind >= 0 && is_ba(ekind);
   if (num_shards > 1 && !ba) { g->err = "only bundle adjustment shards (pose graphs stay single-GPU)"; return B200_ERR_UNSUPPORTED; }
   // numPoses = #free non-marginalized vertices
   int np = 0;
@@ -590,7 +651,36 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     int rc = b200_set_vertices(ctx, kind, (int)hidx.size(), est.data(), hidx.data(), marg.data());
     if (rc) { g->err = b200_last_error(ctx); return rc; }
   }
-  {
+  if (lkind >= 0) {
+    // pose-landmark edges of a landmark-SLAM graph, active-edge order; one ParameterSE3Offset value for all of them
+    const int D = edim(lkind), nm = emeas(lkind);
+    std::vector<int32_t> vi, vj;
+    std::vector<double> meas, info;
+    const std::array<double, 12>* off = nullptr;
+    for (int k : g->active_edges) {
+      const HEdge& e = g->edges[k];
+      if (e.kind != lkind) continue;
+      vi.push_back(g->vertices[e.v0].slot); vj.push_back(g->vertices[e.v1].slot);
+      meas.insert(meas.end(), e.meas, e.meas + nm);
+      info.insert(info.end(), e.info, e.info + D * D);
+      if (lkind == B200_EDGE_SE3_XYZ) {
+        const std::array<double, 12>& o = g->se3_offsets[e.param];
+        if (!off) off = &o;
+        else if (o != *off) { g->err = "SE3_XYZ edges name ParameterSE3Offsets with different values"; return B200_ERR_UNSUPPORTED; }
+      }
+    }
+    if (off) { int rc = b200_set_sensor_offset(ctx, off->data()); if (rc) { g->err = b200_last_error(ctx); return rc; } }
+    int rc = b200_set_edges(ctx, lkind, (int)vi.size(), vi.data(), vj.data(), meas.data(), info.data());
+    if (rc) { g->err = b200_last_error(ctx); return rc; }
+    if (ekind < 0) {  // no odometry at all: empty pose-pose set of the matching kind
+      rc = b200_set_edges(ctx, lkind == B200_EDGE_SE2_XY ? B200_EDGE_SE2 : B200_EDGE_SE3, 0, nullptr, nullptr, nullptr, nullptr);
+      if (rc) { g->err = b200_last_error(ctx); return rc; }
+    }
+  } else {
+    int rc = b200_set_edges(ctx, B200_EDGE_SE2_XY, 0, nullptr, nullptr, nullptr, nullptr);  // forget a previous graph's set
+    if (rc) { g->err = b200_last_error(ctx); return rc; }
+  }
+  if (ekind >= 0) {
     const int D = edim(ekind), nm = emeas(ekind);
     std::vector<int32_t> vi, vj;
     std::vector<double> meas, info;
@@ -599,7 +689,7 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     for (size_t i = 0; i < vslot.size(); ++i) vslot[i] = g->vertices[i].slot;
     // this shard's edges in active-edge order: counted per contiguous range, offset by a prefix sum, copied concurrently
     const size_t nact = g->active_edges.size();
-    auto mine = [&](const HEdge& e) { return !ba || lm_shard[vslot[e.v0]] == shard; };
+    auto mine = [&](const HEdge& e) { return e.kind == ekind && (!ba || lm_shard[vslot[e.v0]] == shard); };
     const int parts = g2o_b200::range_count(nact, (size_t)1 << 16);
     std::vector<size_t> base(parts + 1, 0);
     g2o_b200::parallel_ranges(nact, parts, [&](int t, size_t b, size_t e2) {
@@ -701,14 +791,22 @@ int b200_graph_save(b200_graph* g, const char* path) {
   std::vector<int> order(g->vertices.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
   std::sort(order.begin(), order.end(), [&](int a, int b) { return g->vertices[a].id < g->vertices[b].id; });
-  static const char* vtag[B200_NUM_VERTEX_KINDS] = {"VERTEX_SE2", "VERTEX_SE3:QUAT", "VERTEX_CAM", "VERTEX_XYZ", "VERTEX_SE3:EXPMAP"};
-  static const char* etag[B200_NUM_EDGE_KINDS] = {"EDGE_SE2", "EDGE_SE3:QUAT", "EDGE_PROJECT_P2MC", "EDGE_PROJECT_XYZ2UV:EXPMAP"};
+  static const char* vtag[B200_NUM_VERTEX_KINDS] = {"VERTEX_SE2", "VERTEX_SE3:QUAT", "VERTEX_CAM", "VERTEX_XYZ", "VERTEX_SE3:EXPMAP", "VERTEX_XY"};
+  static const char* etag[B200_NUM_EDGE_KINDS] = {"EDGE_SE2", "EDGE_SE3:QUAT", "EDGE_PROJECT_P2MC", "EDGE_PROJECT_XYZ2UV:EXPMAP", "EDGE_SE2_XY", "EDGE_SE3_TRACKXYZ"};
+  bool track = false;  // XYZ points of a landmark-SLAM graph are VertexPointXYZ (VERTEX_TRACKXYZ)
+  for (const HEdge& e : g->edges) if (e.kind == B200_EDGE_SE3_XYZ) { track = true; break; }
+  for (const auto& kv : g->se3_offsets_text) {
+    fprintf(f, "PARAMS_SE3OFFSET %d", kv.first);
+    for (double d : kv.second) fprintf(f, " %.17g", d);
+    fprintf(f, "\n");
+  }
   for (const auto& kv : g->camera_parameters)  // parameters first (optimizable_graph.cpp:591-594)
     fprintf(f, "PARAMS_CAMERAPARAMETERS %d %.17g %.17g %.17g %.17g\n", kv.first, kv.second[0], kv.second[1], kv.second[2], kv.second[3]);
   for (int i : order) {
     const HVertex& v = g->vertices[i];
-    fprintf(f, "%s %d", vtag[v.kind], v.id);
+    fprintf(f, "%s %d", (track && v.kind == B200_VERTEX_XYZ) ? "VERTEX_TRACKXYZ" : vtag[v.kind], v.id);
     if (v.kind == B200_VERTEX_SE2 || v.kind == B200_VERTEX_XYZ) fprintf(f, " %.17g %.17g %.17g", v.est[0], v.est[1], v.est[2]);
+    else if (v.kind == B200_VERTEX_XY) fprintf(f, " %.17g %.17g", v.est[0], v.est[1]);
     else if (v.kind == B200_VERTEX_SE3) {
       double q[4];
       R_to_quat(v.est, q);
@@ -726,9 +824,9 @@ int b200_graph_save(b200_graph* g, const char* path) {
   }
   for (const HEdge& e : g->edges) {
     fprintf(f, "%s %d %d", etag[e.kind], g->vertices[e.v0].id, g->vertices[e.v1].id);
-    if (e.kind == B200_EDGE_XYZ2UV) fprintf(f, " %d", e.param);
+    if (e.kind == B200_EDGE_XYZ2UV || e.kind == B200_EDGE_SE3_XYZ) fprintf(f, " %d", e.param);
     const int D = edim(e.kind);
-    if (e.kind == B200_EDGE_SE2) fprintf(f, " %.17g %.17g %.17g", e.meas[0], e.meas[1], e.meas[2]);
+    if (e.kind == B200_EDGE_SE2 || e.kind == B200_EDGE_SE3_XYZ) fprintf(f, " %.17g %.17g %.17g", e.meas[0], e.meas[1], e.meas[2]);
     else if (e.kind == B200_EDGE_SE3) {
       double q[4];
       R_to_quat(e.meas, q);

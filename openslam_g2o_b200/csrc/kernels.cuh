@@ -251,6 +251,137 @@ __global__ void gather_segments_kernel(int nseg, const int* __restrict__ src_ptr
   dst[idx] = s;
 }
 
+// ------------------------------------------------------------------ landmark SLAM (pose + point, nothing marginalized)
+// FAM 0: EdgeSE2PointXY (pose SE2, D = 3; point 2; error 2), FAM 1: EdgeSE3PointXYZ (pose SE3, D = 6; point 3; error 3).
+// The point's Hessian blocks are padded to the pose dimension D (g2o_b200.h), so these edges write the same staging
+// record as the pose-pose edges and the ordered gather above sums both kinds.  v0 = pose vertex, v1 = point vertex.
+struct SensorOffset { double m[12]; };   // ParameterSE3Offset::offset() as [R col-major | t]
+template <int FAM> struct PlDims { static constexpr int D = FAM == 0 ? 3 : 6, LD = FAM == 0 ? 2 : 3, ED = FAM == 0 ? 2 : 3; };
+
+template <int FAM>
+__device__ __forceinline__ void pl_error(int e, int E, const int* __restrict__ v0, const int* __restrict__ v1,
+                                         const double* __restrict__ pose_est, const double* __restrict__ lm_est,
+                                         const double* __restrict__ meas, const SensorOffset& off, double* err,
+                                         double* A, double* B, bool jac) {
+  const double4 lq = *reinterpret_cast<const double4*>(lm_est + 4ll * v1[e]);
+  const double l[3] = {lq.x, lq.y, lq.z};
+  if (FAM == 0) {
+    const double z[2] = {meas[e], meas[(long long)E + e]};
+    const SE2 x = load_se2(pose_est, v0[e]);
+    se2_xy_error(x, l, z, err);
+    if (jac) se2_xy_jacobians(x, l, A, B);
+  } else {
+    const double z[3] = {meas[e], meas[(long long)E + e], meas[2ll * E + e]};
+    const Iso X = load_iso(pose_est, v0[e]);
+    Iso O;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) O.R[i] = off.m[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) O.t[i] = off.m[9 + i];
+    se3_xyz_error(X, O, l, z, err);
+    if (jac) se3_xyz_jacobians(X, O, l, A, B);
+  }
+}
+
+template <int FAM>
+__global__ void pl_chi2_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v1,
+                               const double* __restrict__ pose_est, const double* __restrict__ lm_est,
+                               const double* __restrict__ meas, const double* __restrict__ info, SensorOffset off,
+                               Robust rk, double* __restrict__ partials) {
+  constexpr int ED = PlDims<FAM>::ED;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0;
+  if (e < E) {
+    double err[ED], W[ED * ED];
+    pl_error<FAM>(e, E, v0, v1, pose_est, lm_est, meas, off, err, nullptr, nullptr, false);
+    load_info<ED>(info, E, e, W);
+    chi = chi2_of<ED>(W, err);
+    if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
+  }
+  chi = block_sum(chi);
+  if (threadIdx.x == 0) partials[blockIdx.x] = chi;
+}
+
+// staging record of edge rec0 + e: [Hii D*D | Hjj D*D (top-left LD x LD) | Hij D*D in destination orientation:
+// D x LD in the first LD columns, transposed: LD x D in the first LD rows | bi D | bj D (first LD)]; padding = 0
+template <int FAM>
+__global__ void __launch_bounds__(128)
+pl_linearize_kernel(int E, int rec0, const int* __restrict__ v0, const int* __restrict__ v1,
+                    const double* __restrict__ pose_est, const double* __restrict__ lm_est,
+                    const double* __restrict__ meas, const double* __restrict__ info,
+                    const unsigned char* __restrict__ transposed, SensorOffset off, Robust rk,
+                    double* __restrict__ stage) {
+  constexpr int D = PlDims<FAM>::D, LD = PlDims<FAM>::LD, ED = PlDims<FAM>::ED;
+  constexpr int STRIDE = 3 * D * D + 2 * D;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double A[ED * D], B[ED * LD], err[ED], W[ED * ED];
+  pl_error<FAM>(e, E, v0, v1, pose_est, lm_est, meas, off, err, A, B, true);
+  load_info<ED>(info, E, e, W);
+  if (rk.kind) {
+    double r0, r1;
+    robustify(rk, chi2_of<ED>(W, err), r0, r1);
+#pragma unroll
+    for (int i = 0; i < ED * ED; ++i) W[i] *= r1;
+  }
+  double omega_r[ED];
+#pragma unroll
+  for (int r = 0; r < ED; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < ED; ++c) s += W[r + ED * c] * err[c];
+    omega_r[r] = -s;
+  }
+  double* out = stage + (long long)(rec0 + e) * STRIDE;
+#pragma unroll 4
+  for (int i = 0; i < STRIDE; ++i) out[i] = 0.0;
+  double AtO[D * ED], BtO[LD * ED];
+  mtm<D, ED, ED>(A, W, AtO);
+  mtm<LD, ED, ED>(B, W, BtO);
+  {
+    double H[D * D];
+    mm<D, ED, D>(AtO, A, H);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) out[i] = H[i];
+  }
+  {
+    double H[LD * LD];
+    mm<LD, ED, LD>(BtO, B, H);
+#pragma unroll
+    for (int c = 0; c < LD; ++c)
+#pragma unroll
+      for (int r = 0; r < LD; ++r) out[D * D + r + D * c] = H[r + LD * c];
+  }
+  {
+    double H[D * LD];
+    mm<D, ED, LD>(AtO, B, H);   // block (pose, point)
+    const bool tr = transposed[rec0 + e];
+#pragma unroll
+    for (int c = 0; c < LD; ++c)
+#pragma unroll
+      for (int r = 0; r < D; ++r) out[2 * D * D + (tr ? c + D * r : r + D * c)] = H[r + D * c];
+  }
+  double bi[D], bj[LD];
+  mtm<D, ED, 1>(A, omega_r, bi);
+  mtm<LD, ED, 1>(B, omega_r, bj);
+#pragma unroll
+  for (int i = 0; i < D; ++i) out[3 * D * D + i] = bi[i];
+#pragma unroll
+  for (int i = 0; i < LD; ++i) out[3 * D * D + D + i] = bj[i];
+}
+
+// VertexPointXY / VertexPointXYZ::oplusImpl (types/slam2d/vertex_point_xy.h:76-80, types/slam3d/vertex_pointxyz.h:49-52)
+// with the point's unknowns at x[hidx * D .. + LD)
+template <int D, int LD>
+__global__ void oplus_point_kernel(int n, const int* __restrict__ hidx, const double* __restrict__ x, double* __restrict__ est) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int h = hidx[v];
+  if (h < 0) return;
+#pragma unroll
+  for (int k = 0; k < LD; ++k) est[4ll * v + k] += x[(long long)D * h + k];
+}
+
 // ------------------------------------------------------------------ bundle adjustment (camera + XYZ)
 // MODEL 0: VertexCam / EdgeProjectP2MC (types_sba), MODEL 1: VertexSE3Expmap / EdgeProjectXYZ2UV (types_six_dof_expmap)
 template <int MODEL>

@@ -19,11 +19,12 @@ double wall() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-int vdim(int kind) { return kind == B200_VERTEX_SE2 ? 3 : kind == B200_VERTEX_XYZ ? 3 : 6; }
-int vest(int kind) { return kind == B200_VERTEX_SE2 ? 3 : kind == B200_VERTEX_XYZ ? 3 : 12; }   // doubles in the ABI layout
-int vstride(int kind) { return kind == B200_VERTEX_SE2 ? 4 : kind == B200_VERTEX_XYZ ? 4 : 12; }  // doubles on the device
-int edim(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
-int emeas(int kind) { return kind == B200_EDGE_SE2 ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
+int vdim(int kind) { return kind == B200_VERTEX_SE2 ? 3 : kind == B200_VERTEX_XYZ ? 3 : kind == B200_VERTEX_XY ? 2 : 6; }
+int vest(int kind) { return kind == B200_VERTEX_SE2 ? 3 : kind == B200_VERTEX_XYZ ? 3 : kind == B200_VERTEX_XY ? 2 : 12; }   // doubles in the ABI layout
+int vstride(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ || kind == B200_VERTEX_XY) ? 4 : 12; }  // doubles on the device
+int edim(int kind) { return (kind == B200_EDGE_SE2 || kind == B200_EDGE_SE3_XYZ) ? 3 : kind == B200_EDGE_SE3 ? 6 : 2; }
+int emeas(int kind) { return (kind == B200_EDGE_SE2 || kind == B200_EDGE_SE3_XYZ) ? 3 : kind == B200_EDGE_SE3 ? 12 : 2; }
+bool is_landmark_kind(int kind) { return kind == B200_VERTEX_XYZ || kind == B200_VERTEX_XY; }
 
 // kernel groups for the profiling counters (b200_get_phase_time ids)
 enum { PH_ERRORS = 0, PH_LINEARIZE = 1, PH_SCHUR = 2, PH_FACTOR = 3, PH_TRISOLVE = 4, PH_UPDATE = 5, PH_BACKSUB = 6,
@@ -114,20 +115,35 @@ int build_structure_impl(b200_ctx* c) {
       pose_kind = k;
     }
   if (pose_kind < 0) return fail(c, B200_ERR_INVALID, "no pose vertices set");
-  const bool has_lm = c->vs[B200_VERTEX_XYZ].set && c->vs[B200_VERTEX_XYZ].n > 0;
-  if (c->edge_kind < 0 || c->nE <= 0) return fail(c, B200_ERR_INVALID, "no edges set");
-  const int want_pose = c->edge_kind == B200_EDGE_SE2 ? B200_VERTEX_SE2 : c->edge_kind == B200_EDGE_SE3 ? B200_VERTEX_SE3 : B200_VERTEX_CAM;
-  if (want_pose != pose_kind) return fail(c, B200_ERR_UNSUPPORTED, "edge kind does not match the pose vertex kind");
-  if ((c->edge_kind == B200_EDGE_P2MC) != has_lm) return fail(c, B200_ERR_UNSUPPORTED, "P2MC / XYZ2UV edges need XYZ vertices (and only they do)");
-  if (c->edge_kind == B200_EDGE_P2MC && c->edge_model != c->cam_model) return fail(c, B200_ERR_UNSUPPORTED, "P2MC edges go with CAM vertices, XYZ2UV edges with SE3_EXPMAP vertices");
+  // landmark SLAM: SE2 + XY / SE3 + XYZ with pose-landmark edges, nothing marginalized (variable-block `*_var` path)
+  const bool var_lm = c->nLE > 0;
+  const int lm_kind = var_lm ? (c->l_edge_kind == B200_EDGE_SE2_XY ? B200_VERTEX_XY : B200_VERTEX_XYZ) : B200_VERTEX_XYZ;
+  if (!var_lm && c->vs[B200_VERTEX_XY].set && c->vs[B200_VERTEX_XY].n > 0) return fail(c, B200_ERR_UNSUPPORTED, "XY vertices need SE2_XY edges");
+  const bool has_lm = !var_lm && c->vs[B200_VERTEX_XYZ].set && c->vs[B200_VERTEX_XYZ].n > 0;
+  if (var_lm) {
+    const int want = c->l_edge_kind == B200_EDGE_SE2_XY ? B200_VERTEX_SE2 : B200_VERTEX_SE3;
+    if (want != pose_kind) return fail(c, B200_ERR_UNSUPPORTED, "SE2_XY edges go with SE2 poses, SE3_XYZ edges with SE3 poses");
+    if (c->nE > 0 && c->edge_kind != (want == B200_VERTEX_SE2 ? B200_EDGE_SE2 : B200_EDGE_SE3)) return fail(c, B200_ERR_UNSUPPORTED, "edge kind does not match the pose vertex kind");
+    if (!c->vs[lm_kind].set || c->vs[lm_kind].n <= 0) return fail(c, B200_ERR_INVALID, "pose-landmark edges without landmark vertices");
+    if (c->world > 1) return fail(c, B200_ERR_UNSUPPORTED, "landmark SLAM graphs are not sharded");
+    if (c->nE <= 0) c->edge_kind = want == B200_VERTEX_SE2 ? B200_EDGE_SE2 : B200_EDGE_SE3;
+  } else {
+    if (c->edge_kind < 0 || c->nE <= 0) return fail(c, B200_ERR_INVALID, "no edges set");
+    const int want_pose = c->edge_kind == B200_EDGE_SE2 ? B200_VERTEX_SE2 : c->edge_kind == B200_EDGE_SE3 ? B200_VERTEX_SE3 : B200_VERTEX_CAM;
+    if (want_pose != pose_kind) return fail(c, B200_ERR_UNSUPPORTED, "edge kind does not match the pose vertex kind");
+    if ((c->edge_kind == B200_EDGE_P2MC) != has_lm) return fail(c, B200_ERR_UNSUPPORTED, "P2MC / XYZ2UV edges need XYZ vertices (and only they do)");
+    if (c->edge_kind == B200_EDGE_P2MC && c->edge_model != c->cam_model) return fail(c, B200_ERR_UNSUPPORTED, "P2MC edges go with CAM vertices, XYZ2UV edges with SE3_EXPMAP vertices");
+  }
   c->pose_kind = pose_kind;
   c->schur = has_lm;
+  c->var_lm = var_lm;
+  c->lm_kind = var_lm ? lm_kind : -1;
   b200_ctx::VertexSet& PV = c->vs[pose_kind];
-  b200_ctx::VertexSet& LV = c->vs[B200_VERTEX_XYZ];
+  b200_ctx::VertexSet& LV = c->vs[lm_kind];
   c->n_pose_v = PV.n;
-  c->n_lm_v = has_lm ? LV.n : 0;
+  c->n_lm_v = (has_lm || var_lm) ? LV.n : 0;
   c->pd = vdim(pose_kind);
-  c->ld = 3;
+  c->ld = var_lm ? vdim(lm_kind) : 3;
   // index mapping as assigned by SparseOptimizer::buildIndexMapping: poses first, then landmarks
   int np = 0, nl = 0;
   for (int v = 0; v < PV.n; ++v) {
@@ -141,6 +157,11 @@ int build_structure_impl(b200_ctx* c) {
         if (LV.marg.empty() || !LV.marg[v]) return fail(c, B200_ERR_UNSUPPORTED, "XYZ vertices must be marginalized (Schur) for this solver");
       }
     }
+  if (var_lm)
+    for (int v = 0; v < LV.n; ++v) {  // the landmarks are numbered with the poses (buildIndexMapping: nothing marginalized)
+      if (LV.hidx[v] >= 0) ++np;
+      if (!LV.marg.empty() && LV.marg[v]) return fail(c, B200_ERR_UNSUPPORTED, "marginalized XY / XYZ landmarks of a landmark-SLAM graph (Schur complement) are not supported: use the variable-block path (nothing marginalized)");
+    }
   if (np == 0) return fail(c, B200_ERR_INVALID, "0 vertices to optimize");
   c->np = np; c->nl = nl;
   c->sizeP = np * c->pd; c->sizeL = nl * c->ld;
@@ -151,6 +172,13 @@ int build_structure_impl(b200_ctx* c) {
     if (h >= np || c->pose_vertex[h] != -1) return fail(c, B200_ERR_INVALID, "pose hessian indices must be a permutation of [0,numPoses)");
     c->pose_vertex[h] = v;
   }
+  if (var_lm)
+    for (int v = 0; v < LV.n; ++v) {
+      const int h = LV.hidx[v];
+      if (h < 0) continue;
+      if (h >= np || c->pose_vertex[h] != -1) return fail(c, B200_ERR_INVALID, "pose hessian indices must be a permutation of [0,numPoses)");
+      c->pose_vertex[h] = -2 - v;  // a landmark
+    }
   c->lm_vertex.assign(nl, -1);
   std::vector<int> lm_lidx(c->n_lm_v, -1);
   if (has_lm)
@@ -167,6 +195,9 @@ int build_structure_impl(b200_ctx* c) {
     const int nvi = has_lm ? LV.n : PV.n;
     if (c->e_vi[e] < 0 || c->e_vi[e] >= nvi || c->e_vj[e] < 0 || c->e_vj[e] >= PV.n) return fail(c, B200_ERR_INVALID, "edge vertex index out of range");
   }
+  const int LE = var_lm ? c->nLE : 0;
+  for (int e = 0; e < LE; ++e)
+    if (c->l_vi[e] < 0 || c->l_vi[e] >= PV.n || c->l_vj[e] < 0 || c->l_vj[e] >= LV.n) return fail(c, B200_ERR_INVALID, "edge vertex index out of range");
 
   // ---- vertex state on the device
   {
@@ -193,6 +224,14 @@ int build_structure_impl(b200_ctx* c) {
       c->d_lm_lidx.upload(lm_lidx, s);
       c->d_lm_vertex.upload(c->lm_vertex, s);
     }
+    if (var_lm) {
+      const int lne = vest(lm_kind);
+      std::vector<double> lb((size_t)LV.n * 4, 0.0);
+      for (int v = 0; v < LV.n; ++v) memcpy(&lb[(size_t)v * 4], &LV.est[(size_t)v * lne], lne * sizeof(double));
+      c->d_lm_est.upload(lb, s);
+      c->d_lm_bak.alloc(lb.size());
+      c->d_lm_lidx.upload(LV.hidx, s);   // index in the common pose / landmark numbering
+    }
     if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
   }
   STAMP("checks + vertex upload");
@@ -201,20 +240,23 @@ int build_structure_impl(b200_ctx* c) {
   c->d_b.zero(s); c->d_x.zero(s);
   c->d_diag.alloc(ntot);
   c->d_scalars.alloc(16); c->d_scalars.zero(s);
-  c->d_partials.alloc((size_t)ceil_div(std::max(E, ntot), 256) + (size_t)ceil_div(std::max(nl, 1), 128) + 64);
+  c->d_partials.alloc((size_t)ceil_div(std::max(E, ntot), 256) + (size_t)ceil_div(std::max(LE, 1), 256) + (size_t)ceil_div(std::max(nl, 1), 128) + 64);
 
   const int D = edim(c->edge_kind);
   const int pd = c->pd;
+  const int ET = E + LE;   // pose graphs: records of the per-edge staging (pose-pose edges first, then pose-landmark)
   std::vector<int> bp_colptr, bp_rowidx;  // pattern handed to the Cholesky
 
   if (!has_lm) {
     // =========================== pose graph ===========================
     // Hpp pattern: diagonal blocks + (min,max) per edge with two free vertices (block_solver.hpp:204-232)
+    auto h_i = [&](int e) { return e < E ? PV.hidx[c->e_vi[e]] : PV.hidx[c->l_vi[e - E]]; };
+    auto h_j = [&](int e) { return e < E ? PV.hidx[c->e_vj[e]] : LV.hidx[c->l_vj[e - E]]; };
     std::vector<long long> keys;
-    keys.reserve((size_t)np + E);
+    keys.reserve((size_t)np + ET);
     for (int i = 0; i < np; ++i) keys.push_back(((long long)i << 32) | i);
-    for (int e = 0; e < E; ++e) {
-      int hi = PV.hidx[c->e_vi[e]], hj = PV.hidx[c->e_vj[e]];
+    for (int e = 0; e < ET; ++e) {
+      int hi = h_i(e), hj = h_j(e);
       if (hi < 0 || hj < 0) continue;
       if (hi == hj) return fail(c, B200_ERR_UNSUPPORTED, "self-loop edge");
       int lo = std::min(hi, hj), hi2 = std::max(hi, hj);
@@ -235,11 +277,11 @@ int build_structure_impl(b200_ctx* c) {
     c->hpp_diag_block.resize(np);
     for (int i = 0; i < np; ++i) c->hpp_diag_block[i] = find_block(i, i);
     // per-edge flags and ordered gather lists
-    std::vector<unsigned char> transposed(E, 0);
+    std::vector<unsigned char> transposed(ET, 0);
     std::vector<int> hcnt(nblk + 1, 0), bcnt(np + 1, 0);
-    std::vector<int> eb_ii(E, -1), eb_jj(E, -1), eb_ij(E, -1);
-    for (int e = 0; e < E; ++e) {
-      int hi = PV.hidx[c->e_vi[e]], hj = PV.hidx[c->e_vj[e]];
+    std::vector<int> eb_ii(ET, -1), eb_jj(ET, -1), eb_ij(ET, -1);
+    for (int e = 0; e < ET; ++e) {
+      int hi = h_i(e), hj = h_j(e);
       if (hi >= 0) { eb_ii[e] = c->hpp_diag_block[hi]; hcnt[eb_ii[e] + 1]++; bcnt[hi + 1]++; }
       if (hj >= 0) { eb_jj[e] = c->hpp_diag_block[hj]; hcnt[eb_jj[e] + 1]++; bcnt[hj + 1]++; }
       if (hi >= 0 && hj >= 0) {
@@ -253,8 +295,9 @@ int build_structure_impl(b200_ctx* c) {
     std::vector<int> hsrc(hcnt[nblk]), bsrc(bcnt[np]);
     {
       std::vector<int> hf(hcnt.begin(), hcnt.end() - 1), bf(bcnt.begin(), bcnt.end() - 1);
-      for (int e = 0; e < E; ++e) {
-        int hi = PV.hidx[c->e_vi[e]], hj = PV.hidx[c->e_vj[e]];
+      if ((long long)ET * 5 > 0x7fffffffll) return fail(c, B200_ERR_UNSUPPORTED, "more than 4e8 edges in one pose graph");
+      for (int e = 0; e < ET; ++e) {
+        int hi = h_i(e), hj = h_j(e);
         if (eb_ii[e] >= 0) { hsrc[hf[eb_ii[e]]++] = e * 5 + 0; bsrc[bf[hi]++] = e * 5 + 3; }
         if (eb_jj[e] >= 0) { hsrc[hf[eb_jj[e]]++] = e * 5 + 1; bsrc[bf[hj]++] = e * 5 + 4; }
         if (eb_ij[e] >= 0) hsrc[hf[eb_ij[e]]++] = e * 5 + 2;
@@ -279,8 +322,25 @@ int build_structure_impl(b200_ctx* c) {
     c->d_hsrc_ptr.upload(hcnt, s); c->d_hsrc_id.upload(hsrc, s);
     c->d_bsrc_ptr.upload(bcnt, s); c->d_bsrc_id.upload(bsrc, s);
     c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
-    c->d_stage.alloc((size_t)E * (3 * D * D + 2 * D));
+    c->d_stage.alloc((size_t)ET * (3 * D * D + 2 * D));
     c->d_Hpp.alloc((size_t)nblk * pd * pd);
+    if (var_lm) {
+      // pose-landmark edges (SoA) and the unit diagonal of the padding unknowns of the landmark blocks
+      const int LDm = edim(c->l_edge_kind), LMS = emeas(c->l_edge_kind), LIS = LDm * (LDm + 1) / 2;
+      std::vector<double> lmeas((size_t)LMS * LE), linfo((size_t)LIS * LE);
+      for (int e = 0; e < LE; ++e) {
+        for (int f = 0; f < LMS; ++f) lmeas[(size_t)f * LE + e] = c->l_meas[(size_t)e * LMS + f];
+        int f = 0;
+        const double* W = &c->l_info[(size_t)e * LDm * LDm];
+        for (int i = 0; i < LDm; ++i) for (int j = i; j < LDm; ++j) linfo[(size_t)(f++) * LE + e] = W[i + LDm * j];
+      }
+      c->d_lev0.upload(c->l_vi, s); c->d_lev1.upload(c->l_vj, s);
+      c->d_lmeas.upload(lmeas, s); c->d_linfo.upload(linfo, s);
+      std::vector<double> pad((size_t)np * pd, 0.0);
+      for (int v = 0; v < LV.n; ++v)
+        if (LV.hidx[v] >= 0) for (int k2 = c->ld; k2 < pd; ++k2) pad[(size_t)LV.hidx[v] * pd + k2] = 1.0;
+      c->d_pad_diag.upload(pad, s);
+    }
     if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
     bp_colptr = c->hpp_colptr; bp_rowidx = c->hpp_rowidx;
   } else {
@@ -646,6 +706,7 @@ int build_structure_impl(b200_ctx* c) {
   opt.nd_levels = c->nd_levels;
   if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
+  c->chol.set_diagonal_extra(var_lm ? c->d_pad_diag.p : nullptr);
   STAMP("symbolic (ordering + plan)");
   c->structured = true;
   c->state_chi2_valid = false;  // new graph / new estimates on the device
@@ -661,16 +722,31 @@ double* bschur_ptr(b200_ctx* c) { return c->d_Hschur.p + (size_t)c->n_hs * 36; }
 // ------------------------------------------------------------------------------------------------
 void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
   PhaseTimer pt(c, PH_ERRORS);
-  const int E = c->nE, nb = ceil_div(E, 256);
+  const int E = c->nE;
+  int nb = ceil_div(E, 256);
   cudaStream_t s = c->stream;
-  if (c->edge_kind == B200_EDGE_SE2)
-    k::pg_chi2_kernel<0><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
-  else if (c->edge_kind == B200_EDGE_SE3)
-    k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
-  else
-    BA_MODEL_LAUNCH(c, ba_chi2_kernel, <<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p, 0));
+  if (E > 0) {
+    if (c->edge_kind == B200_EDGE_SE2)
+      k::pg_chi2_kernel<0><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
+    else if (c->edge_kind == B200_EDGE_SE3)
+      k::pg_chi2_kernel<1><<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p);
+    else
+      BA_MODEL_LAUNCH(c, ba_chi2_kernel, <<<nb, 256, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_lm_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, c->robust, c->d_partials.p, 0));
+    c->lc.n++;
+  }
+  if (c->var_lm) {  // the pose-landmark edges: their block sums follow the pose-pose edges'
+    const int LE = c->nLE, nb2 = ceil_div(LE, 256);
+    k::SensorOffset off;
+    memcpy(off.m, c->sensor_offset, sizeof(off.m));
+    if (c->l_edge_kind == B200_EDGE_SE2_XY)
+      k::pl_chi2_kernel<0><<<nb2, 256, 0, s>>>(LE, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, off, c->robust, c->d_partials.p + nb);
+    else
+      k::pl_chi2_kernel<1><<<nb2, 256, 0, s>>>(LE, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, off, c->robust, c->d_partials.p + nb);
+    nb += nb2;
+    c->lc.n++;
+  }
   k::reduce_partials_kernel<<<1, 1024, 0, s>>>(c->d_partials.p, nb, c->d_scalars.p + 0);
-  c->lc.n += 2;
+  c->lc.n++;
   B200_CUDA(cudaGetLastError());
 }
 
@@ -695,15 +771,19 @@ int enqueue_build_system(b200_ctx* c) {
   cudaStream_t s = c->stream;
   const int E = c->nE, np = c->np;
   if (!c->schur) {
+    k::SensorOffset off;
+    memcpy(off.m, c->sensor_offset, sizeof(off.m));
     if (c->edge_kind == B200_EDGE_SE2) {
       { PhaseTimer pt(c, PH_LINEARIZE);
-      k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p); }
+      if (E > 0) k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p);
+      if (c->var_lm) { k::pl_linearize_kernel<0><<<ceil_div(c->nLE, 128), 128, 0, s>>>(c->nLE, E, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, c->d_e_flag.p, off, c->robust, c->d_stage.p); c->lc.n++; } }
       PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<3, 9><<<ceil_div((long long)c->n_hpp * 9, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<3, 3><<<ceil_div((long long)np * 3, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
     } else {
       { PhaseTimer pt(c, PH_LINEARIZE);
-      k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p); }
+      if (E > 0) k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p);
+      if (c->var_lm) { k::pl_linearize_kernel<1><<<ceil_div(c->nLE, 128), 128, 0, s>>>(c->nLE, E, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, c->d_e_flag.p, off, c->robust, c->d_stage.p); c->lc.n++; } }
       PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<6, 36><<<ceil_div((long long)c->n_hpp * 36, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<6, 6><<<ceil_div((long long)np * 6, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
@@ -839,6 +919,11 @@ void enqueue_update(b200_ctx* c) {
     BA_MODEL_LAUNCH(c, oplus_cam_kernel, <<<ceil_div(n, 128), 128, 0, s>>>(n, c->d_pose_hidx.p, c->d_x.p, c->d_pose_est.p, c->d_cam_der.p));
   }
   c->lc.n++;
+  if (c->var_lm && c->n_lm_v > 0) {
+    if (c->lm_kind == B200_VERTEX_XY) k::oplus_point_kernel<3, 2><<<ceil_div(c->n_lm_v, 128), 128, 0, s>>>(c->n_lm_v, c->d_lm_lidx.p, c->d_x.p, c->d_lm_est.p);
+    else k::oplus_point_kernel<6, 3><<<ceil_div(c->n_lm_v, 128), 128, 0, s>>>(c->n_lm_v, c->d_lm_lidx.p, c->d_x.p, c->d_lm_est.p);
+    c->lc.n++;
+  }
   if (c->schur && c->n_lm_v > 0) {
     k::oplus_xyz_kernel<<<ceil_div(c->n_lm_v, 128), 128, 0, s>>>(c->n_lm_v, c->d_lm_lidx.p, c->d_x.p + c->sizeP, c->d_lm_est.p);
     c->lc.n++;
@@ -873,13 +958,13 @@ void do_push(b200_ctx* c) {
   cudaStream_t s = c->stream;
   B200_CUDA(cudaMemcpyAsync(c->d_pose_bak.p, c->d_pose_est.p, c->d_pose_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (c->pose_kind == B200_VERTEX_CAM) B200_CUDA(cudaMemcpyAsync(c->d_cam_der_bak.p, c->d_cam_der.p, c->d_cam_der.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  if (c->schur && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_bak.p, c->d_lm_est.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if ((c->schur || c->var_lm) && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_bak.p, c->d_lm_est.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 void do_pop(b200_ctx* c) {
   cudaStream_t s = c->stream;
   B200_CUDA(cudaMemcpyAsync(c->d_pose_est.p, c->d_pose_bak.p, c->d_pose_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (c->pose_kind == B200_VERTEX_CAM) B200_CUDA(cudaMemcpyAsync(c->d_cam_der.p, c->d_cam_der_bak.p, c->d_cam_der.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  if (c->schur && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_est.p, c->d_lm_bak.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if ((c->schur || c->var_lm) && c->n_lm_v > 0) B200_CUDA(cudaMemcpyAsync(c->d_lm_est.p, c->d_lm_bak.p, c->d_lm_est.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
 // BA trial tail, fused (kernels.cuh: ba_backsub_update_kernel): cameras first, then ONE pass over the landmarks' observations
@@ -1070,7 +1155,7 @@ void b200_destroy(b200_ctx* c) {
 const char* b200_last_error(const b200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 int b200_set_vertices(b200_ctx* c, int kind, int n, const double* est, const int32_t* hidx, const uint8_t* marg) {
-  if (!c || kind < 0 || kind > B200_VERTEX_SE3_EXPMAP || n < 0 || (n > 0 && (!est || !hidx))) return B200_ERR_INVALID;
+  if (!c || kind < 0 || kind >= B200_NUM_VERTEX_KINDS || n < 0 || (n > 0 && (!est || !hidx))) return B200_ERR_INVALID;
   if (kind == B200_VERTEX_CAM) c->cam_model = 0;
   if (kind == B200_VERTEX_SE3_EXPMAP) { c->cam_model = 1; kind = B200_VERTEX_CAM; }  // same slot, same 12-double rows
   b200_ctx::VertexSet& V = c->vs[kind];
@@ -1086,7 +1171,16 @@ int b200_set_vertices(b200_ctx* c, int kind, int n, const double* est, const int
 }
 
 int b200_set_edges(b200_ctx* c, int kind, int n, const int32_t* vi, const int32_t* vj, const double* meas, const double* info) {
-  if (!c || kind < 0 || kind > B200_EDGE_XYZ2UV || n < 0 || (n > 0 && (!vi || !vj || !meas || !info))) return B200_ERR_INVALID;
+  if (!c || kind < 0 || kind >= B200_NUM_EDGE_KINDS || n < 0 || (n > 0 && (!vi || !vj || !meas || !info))) return B200_ERR_INVALID;
+  if (kind == B200_EDGE_SE2_XY || kind == B200_EDGE_SE3_XYZ) {  // the pose-landmark set of a landmark-SLAM graph
+    c->l_edge_kind = n > 0 ? kind : -1; c->nLE = n;
+    c->l_vi.assign(vi, vi + n); c->l_vj.assign(vj, vj + n);
+    c->l_meas.assign(meas, meas + (size_t)n * emeas(kind));
+    const int D = edim(kind);
+    c->l_info.assign(info, info + (size_t)n * D * D);
+    c->structured = false;
+    return B200_OK;
+  }
   if (kind == B200_EDGE_P2MC) c->edge_model = 0;
   if (kind == B200_EDGE_XYZ2UV) { c->edge_model = 1; kind = B200_EDGE_P2MC; }  // same sizes (2 | 2x2), same structure
   c->edge_kind = kind; c->nE = n;
@@ -1095,6 +1189,14 @@ int b200_set_edges(b200_ctx* c, int kind, int n, const int32_t* vi, const int32_
   const int D = edim(kind);
   c->e_info.assign(info, info + (size_t)n * D * D);
   c->structured = false;
+  return B200_OK;
+}
+
+int b200_set_sensor_offset(b200_ctx* c, const double* iso) {
+  if (!c || !iso) return B200_ERR_INVALID;
+  memcpy(c->sensor_offset, iso, sizeof(c->sensor_offset));
+  c->state_chi2_valid = false;
+  drop_graphs(c);  // the offset is a kernel argument of the captured launches
   return B200_OK;
 }
 
@@ -1484,7 +1586,7 @@ int b200_optimize(b200_ctx* c, int algorithm, int max_iterations, b200_iter_stat
 // ------------------------------------------------------------------------------------------------ read-back
 int b200_get_dims(b200_ctx* c, int32_t* d) {
   if (!c || !d) return B200_ERR_INVALID;
-  d[0] = c->np; d[1] = c->nl; d[2] = c->sizeP; d[3] = c->sizeL; d[4] = c->nE; d[5] = c->n_pose_v + c->n_lm_v; d[6] = c->pd; d[7] = c->schur ? c->ld : 0;
+  d[0] = c->np; d[1] = c->nl; d[2] = c->sizeP; d[3] = c->sizeL; d[4] = c->nE + (c->var_lm ? c->nLE : 0); d[5] = c->n_pose_v + c->n_lm_v; d[6] = c->pd; d[7] = c->schur ? c->ld : 0;
   return B200_OK;
 }
 static int copy_out(b200_ctx* c, const double* dev, double* host, size_t n) {
@@ -1507,12 +1609,12 @@ int b200_get_estimates(b200_ctx* c, int kind, double* out) {
   return guarded(c, [&]() {
     NEED_STRUCTURE(c);
     if (kind == B200_VERTEX_SE3_EXPMAP || kind == B200_VERTEX_CAM) kind = ((kind == B200_VERTEX_SE3_EXPMAP) == (c->cam_model == 1)) ? B200_VERTEX_CAM : -1;
-    const bool lm = kind == B200_VERTEX_XYZ;
+    const bool lm = is_landmark_kind(kind);
     if (!lm && kind != c->pose_kind) return fail(c, B200_ERR_INVALID, "vertex kind not present");
-    if (lm && !c->schur) return fail(c, B200_ERR_INVALID, "vertex kind not present");
+    if (lm && !(c->schur ? kind == B200_VERTEX_XYZ : (c->var_lm && kind == c->lm_kind))) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
     if (c->host_only) {  // no device, nothing was optimised: the estimates as ingested (structure-phase tests on the CPU box)
-      const b200_ctx::VertexSet& V = c->vs[lm ? B200_VERTEX_XYZ : c->pose_kind];
+      const b200_ctx::VertexSet& V = c->vs[lm ? kind : c->pose_kind];
       std::copy(V.est.begin(), V.est.begin() + (size_t)n * ne, out);
       return (int)B200_OK;
     }
@@ -1536,8 +1638,8 @@ int b200_set_estimates(b200_ctx* c, int kind, const double* est) {
     NEED_STRUCTURE(c);
     c->state_chi2_valid = false;
     if (kind == B200_VERTEX_SE3_EXPMAP || kind == B200_VERTEX_CAM) kind = ((kind == B200_VERTEX_SE3_EXPMAP) == (c->cam_model == 1)) ? B200_VERTEX_CAM : -1;
-    const bool lm = kind == B200_VERTEX_XYZ;
-    if ((!lm && kind != c->pose_kind) || (lm && !c->schur) || !est) return fail(c, B200_ERR_INVALID, "vertex kind not present");
+    const bool lm = is_landmark_kind(kind);
+    if ((!lm && kind != c->pose_kind) || (lm && !(c->schur ? kind == B200_VERTEX_XYZ : (c->var_lm && kind == c->lm_kind))) || !est) return fail(c, B200_ERR_INVALID, "vertex kind not present");
     B200_CUDA(cudaSetDevice(c->device));
     const int n = lm ? c->n_lm_v : c->n_pose_v, st = vstride(kind), ne = vest(kind);
     double* dev = lm ? c->d_lm_est.p : c->d_pose_est.p;

@@ -29,9 +29,19 @@ struct b200_ctx {
     std::vector<double> est;
     std::vector<int> hidx;
     std::vector<unsigned char> marg;
-  } vs[4];
+  } vs[B200_NUM_VERTEX_KINDS];   // slot 4 (SE3_EXPMAP) stays empty: that kind lives in the CAM slot
   int edge_kind = -1;
   int nE = 0;
+  // landmark SLAM (SE2 + XY / SE3 + XYZ, nothing marginalized: the reference's variable-block-size `*_var` path): the
+  // pose-landmark edges (B200_EDGE_SE2_XY / B200_EDGE_SE3_XYZ) beside the pose-pose edges above; the landmarks share the
+  // poses' index space, their blocks are padded to the pose dimension (g2o_b200.h)
+  int l_edge_kind = -1;
+  int nLE = 0;
+  std::vector<int> l_vi, l_vj;
+  std::vector<double> l_meas, l_info;
+  double sensor_offset[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // ParameterSE3Offset of the SE3_XYZ edges
+  bool var_lm = false;   // structure: landmarks live in the pose index space (no Schur complement)
+  int lm_kind = -1;      // B200_VERTEX_XY / B200_VERTEX_XYZ of the landmarks of a var_lm structure
   // camera model of the BA family: 0 VertexCam / EdgeProjectP2MC, 1 VertexSE3Expmap / EdgeProjectXYZ2UV.  Both live in
   // the vs[B200_VERTEX_CAM] slot / edge_kind B200_EDGE_P2MC internally (same block sizes 6, 3, 2; same Schur plan)
   int cam_model = 0, edge_model = 0;
@@ -60,6 +70,9 @@ struct b200_ctx {
   g2o_b200::DevBuf<int> d_ev0, d_ev1, d_e_pose, d_e_hpl;
   g2o_b200::DevBuf<unsigned char> d_e_flag;  // pose graphs: transposed; BA: first-occurrence of its Hpl block
   g2o_b200::DevBuf<double> d_meas, d_info, d_stage;
+  g2o_b200::DevBuf<int> d_lev0, d_lev1;          // var_lm: pose / landmark vertex of every pose-landmark edge
+  g2o_b200::DevBuf<double> d_lmeas, d_linfo;     // ... their measurements / information (SoA)
+  g2o_b200::DevBuf<double> d_pad_diag;           // ... 1 at the padding unknowns of the landmark blocks, 0 elsewhere
   g2o_b200::DevBuf<int> d_hsrc_ptr, d_hsrc_id, d_bsrc_ptr, d_bsrc_id;
   g2o_b200::DevBuf<int> d_lm_order;  // landmark rank (processing order) -> Hessian landmark index
   g2o_b200::DevBuf<int> d_lm_eptr, d_cam_eptr, d_cam_eidx, d_hpp_diag_block;

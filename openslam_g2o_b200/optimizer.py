@@ -54,6 +54,10 @@ for _alg, _aid in (("gn", L.GAUSS_NEWTON), ("lm", L.LEVENBERG)):
     for _fix, _pd, _ld in (("fix3_2", 3, 2), ("fix6_3", 6, 3)):
         for _suffix in ("", "_cholmod", "_b200"):
             _SOLVERS["%s_%s%s" % (_alg, _fix, _suffix)] = (_aid, _pd, _ld)
+    # variable block sizes (BlockSolverX; solvers/csparse/solver_csparse.cpp:53-55: requiresMarginalize = false): pose graphs
+    # and landmark SLAM (SE2 + XY, SE3 + XYZ) with every vertex in one system
+    for _suffix in ("", "_cholmod", "_b200"):
+        _SOLVERS["%s_var%s" % (_alg, _suffix)] = (_aid, -1, -1)
 
 
 class SolverContext:
@@ -316,7 +320,7 @@ class SparseOptimizer:
             raise B200Error(L.ERR_UNSUPPORTED, "solver '%s' is not provided by the B200 path (have: %s)"
                             % (name, ", ".join(sorted(_SOLVERS))))
         self._algorithm = _SOLVERS[name][0]
-        self._requires_marginalize = True  # all fix* solvers (solver_cholmod.cpp:115-121)
+        self._requires_marginalize = _SOLVERS[name][1] > 0  # all fix* solvers (solver_cholmod.cpp:115-121); var: false
 
     def load(self, path):
         return _check(lib.b200_graph_load(self._g, str(path).encode()), self._g, graph=True) == 0
@@ -340,6 +344,11 @@ class SparseOptimizer:
         """OptimizableGraph::addParameter(CameraParameters) (types/sba/types_six_dof_expmap.h:45-80)"""
         _check(lib.b200_graph_add_camera_parameters(self._g, int(pid), float(focal_length), float(cx), float(cy),
                                                      float(baseline)), self._g, graph=True)
+
+    def add_se3_offset(self, pid, xyz_qxyzw):
+        """OptimizableGraph::addParameter(ParameterSE3Offset) (types/slam3d/parameter_se3_offset.h): x y z qx qy qz qw"""
+        o = L.as_f64(xyz_qxyzw)
+        _check(lib.b200_graph_add_se3_offset(self._g, int(pid), L.ptr(o)), self._g, graph=True)
 
     def set_robust_kernel(self, name, width=1.0):
         """`g2o -robustKernel name -robustKernelWidth width` (apps/g2o_cli/g2o.cpp:322-336): every edge gets the kernel"""

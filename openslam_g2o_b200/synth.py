@@ -8,13 +8,15 @@ text line), so the same arrays feed the product (SparseOptimizer.add_vertices/ad
   venice_like(cams, points, ...)       SURVEY.md section 8d config 3/4: ring of inward-looking cameras, windowed visibility
   expmap_ba(cams, points, ...)         the same scene as VERTEX_SE3:EXPMAP / EDGE_PROJECT_XYZ2UV:EXPMAP
   ba_demo(pixel_noise, outliers, ...)  the scene of the reference's examples/ba/ba_demo.cpp
+  landmark_slam_2d(poses, landmarks)   SE2 odometry + EdgeSE2PointXY sightings (the set-up of examples/tutorial_slam2d)
+  landmark_slam_3d(poses, landmarks)   SE3 odometry + EdgeSE3PointXYZ sightings through a ParameterSE3Offset
 """
 import numpy as np
 
 # vertex / edge kinds of the C-ABI (include/g2o_b200.h).  Literal copies, so that this module has no import besides numpy:
 # bench.py's reference arm loads it by file path without importing the package (and with it libg2o_b200.so)
-VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP = 1, 2, 3, 4
-EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV = 1, 2, 3
+VERTEX_SE2, VERTEX_SE3, VERTEX_CAM, VERTEX_XYZ, VERTEX_SE3_EXPMAP, VERTEX_XY = 0, 1, 2, 3, 4, 5
+EDGE_SE2, EDGE_SE3, EDGE_P2MC, EDGE_XYZ2UV, EDGE_SE2_XY, EDGE_SE3_XYZ = 0, 1, 2, 3, 4, 5
 
 
 # ---------------------------------------------------------------- quaternion helpers (x y z w), vectorised
@@ -220,12 +222,160 @@ def _rot_to_quat(R):
     return q / np.linalg.norm(q, axis=1, keepdims=True)
 
 
+def _interleaved_ids(n_poses, n_lm):
+    """vertex ids with poses and landmarks interleaved (the index mapping sorts by id: sparse_optimizer.cpp:166-190)"""
+    pose_ids = 3 * np.arange(n_poses)
+    lm_ids = 3 * (np.arange(n_lm) % n_poses) + 1 + (np.arange(n_lm) // n_poses) * 3 * n_poses
+    lm_ids = np.where(np.arange(n_lm) < n_poses, 3 * np.arange(n_lm) + 1, 3 * n_poses + np.arange(n_lm))
+    return pose_ids.astype(np.int32), lm_ids.astype(np.int32)
+
+
+def landmark_slam_2d(n_poses=120, n_landmarks=60, seed=32, max_range=6.0, sigma_odo=(0.02, 0.02, 0.01), sigma_obs=0.05,
+                     odometry=True):
+    """2D landmark SLAM: a robot drives laps on a slowly drifting circle, odometry EdgeSE2 between consecutive poses
+    (+ one loop closure per lap) and EdgeSE2PointXY sightings of the landmarks in range (types/slam2d/edge_se2_pointxy.h).
+    Initial guess: integrated odometry; landmarks from their first sighting."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k = np.arange(n_poses)
+    per_lap = 40
+    ang = 2 * np.pi * k / per_lap
+    rad = 8.0 + 0.5 * np.sin(0.37 * k)
+    x, y = rad * np.cos(ang), rad * np.sin(ang)
+    th = ang + np.pi / 2 + 0.1 * np.sin(0.61 * k)
+    th = (th + np.pi) % (2 * np.pi) - np.pi
+    la = rng.uniform(0, 2 * np.pi, n_landmarks)
+    lr = rng.uniform(3.0, 13.0, n_landmarks)
+    lm = np.stack([lr * np.cos(la), lr * np.sin(la)], axis=1)
+
+    def rel(i, j):  # x_i^-1 * x_j
+        c, s = np.cos(th[i]), np.sin(th[i])
+        dx, dy = x[j] - x[i], y[j] - y[i]
+        dth = (th[j] - th[i] + np.pi) % (2 * np.pi) - np.pi
+        return np.stack([c * dx + s * dy, -s * dx + c * dy, dth], axis=-1)
+    o0 = np.concatenate([k[:-1], k[per_lap:]])
+    o1 = np.concatenate([k[1:], k[:-per_lap]])
+    so = np.asarray(sigma_odo)
+    zo = rel(o0, o1) + rng.normal(0, 1, (len(o0), 3)) * so
+    zo[:, 2] = (zo[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    io = np.diag(1.0 / so ** 2)
+    iu = np.array([io[i, j] for i in range(3) for j in range(i, 3)])
+    odo_payload = np.concatenate([zo, np.tile(iu, (len(o0), 1))], axis=1)
+    # sightings
+    d = lm[None, :, :] - np.stack([x, y], axis=1)[:, None, :]
+    seen = np.linalg.norm(d, axis=2) < max_range
+    pi_, li_ = np.nonzero(seen)
+    c, s = np.cos(th[pi_]), np.sin(th[pi_])
+    dl = d[pi_, li_]
+    zl = np.stack([c * dl[:, 0] + s * dl[:, 1], -s * dl[:, 0] + c * dl[:, 1]], axis=1) + rng.normal(0, sigma_obs, (len(pi_), 2))
+    w = 1.0 / sigma_obs ** 2
+    obs_payload = np.concatenate([zl, np.tile([w, 0.1 * w, 1.3 * w], (len(pi_), 1))], axis=1)
+    used = np.unique(li_)
+    remap = -np.ones(n_landmarks, int)
+    remap[used] = np.arange(len(used))
+    # initial guess
+    pe = np.zeros((n_poses, 3))
+    pe[0] = [x[0], y[0], th[0]]
+    for i in range(1, n_poses):
+        c0, s0 = np.cos(pe[i - 1, 2]), np.sin(pe[i - 1, 2])
+        z = zo[i - 1]
+        pe[i] = [pe[i - 1, 0] + c0 * z[0] - s0 * z[1], pe[i - 1, 1] + s0 * z[0] + c0 * z[1],
+                 (pe[i - 1, 2] + z[2] + np.pi) % (2 * np.pi) - np.pi]
+    le = np.zeros((len(used), 2))
+    first = {}
+    for q, (p, l) in enumerate(zip(pi_, li_)):
+        first.setdefault(int(l), q)
+    for l, q in first.items():
+        p = pi_[q]
+        c0, s0 = np.cos(pe[p, 2]), np.sin(pe[p, 2])
+        le[remap[l]] = [pe[p, 0] + c0 * zl[q, 0] - s0 * zl[q, 1], pe[p, 1] + s0 * zl[q, 0] + c0 * zl[q, 1]]
+    pose_ids, lm_ids = _interleaved_ids(n_poses, len(used))
+    if not odometry:
+        o0, o1, odo_payload = o0[:0], o1[:0], odo_payload[:0]
+    return dict(kind="slam2d", pose_ids=pose_ids, pose_payload=pe, lm_ids=lm_ids, lm_payload=le,
+                odo_v0=pose_ids[o0], odo_v1=pose_ids[o1], odo_payload=odo_payload,
+                obs_v0=pose_ids[pi_], obs_v1=lm_ids[remap[li_]], obs_payload=obs_payload,
+                truth_poses=np.stack([x, y, th], axis=1), truth_landmarks=lm[used])
+
+
+def landmark_slam_3d(n_poses=80, n_landmarks=50, seed=33, max_range=7.0, sigma_t=0.02, sigma_r=0.01, sigma_obs=0.04,
+                     offset=(0.1, -0.05, 0.2, 0.1, 0.2, -0.1, 0.9)):
+    """3D landmark SLAM: SE3 poses on a helix with EdgeSE3 odometry (+ closures to the previous turn) and EdgeSE3PointXYZ
+    sightings (types/slam3d/edge_se3_pointxyz.cpp) through one ParameterSE3Offset (sensor pose on the robot, x y z qx qy qz qw)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k = np.arange(n_poses)
+    per_turn = 20
+    ang = 2 * np.pi * k / per_turn
+    t = np.stack([6.0 * np.cos(ang), 6.0 * np.sin(ang), 0.15 * k], axis=1)
+    qz = np.stack([0 * ang, 0 * ang, np.sin((ang + np.pi / 2) / 2), np.cos((ang + np.pi / 2) / 2)], axis=-1)
+    tilt = 0.2 * np.sin(0.3 * k)
+    qx = np.stack([np.sin(tilt / 2), 0 * tilt, 0 * tilt, np.cos(tilt / 2)], axis=-1)
+    q = _qmul(qz, qx)
+    lm = np.stack([rng.uniform(-9, 9, n_landmarks), rng.uniform(-9, 9, n_landmarks), rng.uniform(-1, 0.15 * n_poses + 1, n_landmarks)], axis=1)
+    o0 = np.concatenate([k[:-1], k[per_turn:]])
+    o1 = np.concatenate([k[1:], k[:-per_turn]])
+    qrel = _qmul(_qconj(q[o0]), q[o1])
+    trel = _qrot(_qconj(q[o0]), t[o1] - t[o0])
+    E = len(o0)
+    v = rng.normal(0.0, sigma_r, (E, 3))
+    qn = np.concatenate([v, np.sqrt(np.maximum(0.0, 1.0 - (v ** 2).sum(1)))[:, None]], axis=1)
+    qmeas = _qmul(qrel, qn)
+    qmeas /= np.linalg.norm(qmeas, axis=1, keepdims=True)
+    tmeas = trel + rng.normal(0.0, sigma_t, (E, 3))
+    info = np.zeros((6, 6))
+    info[:3, :3] = np.eye(3) / sigma_t ** 2
+    info[3:, 3:] = np.eye(3) / sigma_r ** 2
+    iu = np.array([info[i, j] for i in range(6) for j in range(i, 6)])
+    odo_payload = np.concatenate([tmeas, qmeas, np.tile(iu, (E, 1))], axis=1)
+    off = np.asarray(offset, float)
+    oq = off[3:] / np.linalg.norm(off[3:])
+    # sensor frame: n2w = X * offset
+    sq = _qmul(q, np.tile(oq, (n_poses, 1)))
+    st = t + _qrot(q, np.tile(off[:3], (n_poses, 1)))
+    d = lm[None, :, :] - st[:, None, :]
+    seen = np.linalg.norm(d, axis=2) < max_range
+    pi_, li_ = np.nonzero(seen)
+    zl = _qrot(_qconj(sq[pi_]), d[pi_, li_]) + rng.normal(0, sigma_obs, (len(pi_), 3))
+    w = 1.0 / sigma_obs ** 2
+    iw = np.array([w, 0.05 * w, 0.0, 1.2 * w, -0.1 * w, 0.9 * w])
+    obs_payload = np.concatenate([np.zeros((len(pi_), 1)), zl, np.tile(iw, (len(pi_), 1))], axis=1)  # paramId 0
+    used = np.unique(li_)
+    remap = -np.ones(n_landmarks, int)
+    remap[used] = np.arange(len(used))
+    qo = np.concatenate([q[:1], qmeas[:n_poses - 1]], axis=0)
+    to = np.concatenate([t[:1], tmeas[:n_poses - 1]], axis=0)
+    qi, ti = _prefix_compose(qo, to)
+    sqi = _qmul(qi, np.tile(oq, (n_poses, 1)))
+    sti = ti + _qrot(qi, np.tile(off[:3], (n_poses, 1)))
+    le = np.zeros((len(used), 3))
+    first = {}
+    for qq, l in enumerate(li_):
+        first.setdefault(int(l), qq)
+    for l, qq in first.items():
+        p = pi_[qq]
+        le[remap[l]] = sti[p] + _qrot(sqi[p][None, :], zl[qq][None, :])[0]
+    pose_ids, lm_ids = _interleaved_ids(n_poses, len(used))
+    return dict(kind="slam3d", pose_ids=pose_ids, pose_payload=np.concatenate([ti, qi], axis=1), lm_ids=lm_ids, lm_payload=le,
+                odo_v0=pose_ids[o0], odo_v1=pose_ids[o1], odo_payload=odo_payload,
+                obs_v0=pose_ids[pi_], obs_v1=lm_ids[remap[li_]], obs_payload=obs_payload,
+                offsets={0: np.concatenate([off[:3], oq])},
+                truth_poses=np.concatenate([t, q], axis=1), truth_landmarks=lm[used])
+
+
 def feed(problem, target):
     """push a generated problem into anything with add_vertices/add_edges (product SparseOptimizer or the
     tests' oracle wrapper)"""
     if problem["kind"] == "se3":
         target.add_vertices(VERTEX_SE3, problem["vertex_ids"], problem["vertex_payload"])
         target.add_edges(EDGE_SE3, problem["edge_v0"], problem["edge_v1"], problem["edge_payload"])
+    elif problem["kind"] in ("slam2d", "slam3d"):
+        three_d = problem["kind"] == "slam3d"
+        for pid, off in problem.get("offsets", {}).items():
+            target.add_se3_offset(pid, off)
+        target.add_vertices(VERTEX_SE3 if three_d else VERTEX_SE2, problem["pose_ids"], problem["pose_payload"])
+        target.add_vertices(VERTEX_XYZ if three_d else VERTEX_XY, problem["lm_ids"], problem["lm_payload"])
+        if len(problem["odo_v0"]):
+            target.add_edges(EDGE_SE3 if three_d else EDGE_SE2, problem["odo_v0"], problem["odo_v1"], problem["odo_payload"])
+        target.add_edges(EDGE_SE3_XYZ if three_d else EDGE_SE2_XY, problem["obs_v0"], problem["obs_v1"], problem["obs_payload"])
     elif problem["kind"] == "ba_expmap":
         for pid, par in problem["camera_parameters"].items():
             target.add_camera_parameters(pid, *par)
@@ -246,6 +396,22 @@ def write_g2o(problem, path):
                 f.write("VERTEX_SE3:QUAT %d %s\n" % (i, " ".join(repr(float(x)) for x in p)))
             for a, b, p in zip(problem["edge_v0"], problem["edge_v1"], problem["edge_payload"]):
                 f.write("EDGE_SE3:QUAT %d %d %s\n" % (a, b, " ".join(repr(float(x)) for x in p)))
+        elif problem["kind"] in ("slam2d", "slam3d"):
+            three_d = problem["kind"] == "slam3d"
+            num = lambda p: " ".join(repr(float(x)) for x in p)
+            for pid, off in problem.get("offsets", {}).items():
+                f.write("PARAMS_SE3OFFSET %d %s\n" % (pid, num(off)))
+            for i, p in zip(problem["pose_ids"], problem["pose_payload"]):
+                f.write("%s %d %s\n" % ("VERTEX_SE3:QUAT" if three_d else "VERTEX_SE2", i, num(p)))
+            for i, p in zip(problem["lm_ids"], problem["lm_payload"]):
+                f.write("%s %d %s\n" % ("VERTEX_TRACKXYZ" if three_d else "VERTEX_XY", i, num(p)))
+            for a, b, p in zip(problem["odo_v0"], problem["odo_v1"], problem["odo_payload"]):
+                f.write("%s %d %d %s\n" % ("EDGE_SE3:QUAT" if three_d else "EDGE_SE2", a, b, num(p)))
+            for a, b, p in zip(problem["obs_v0"], problem["obs_v1"], problem["obs_payload"]):
+                if three_d:
+                    f.write("EDGE_SE3_TRACKXYZ %d %d %d %s\n" % (a, b, int(p[0]), num(p[1:])))
+                else:
+                    f.write("EDGE_SE2_XY %d %d %s\n" % (a, b, num(p)))
         elif problem["kind"] == "ba_expmap":
             for pid, par in problem["camera_parameters"].items():
                 f.write("PARAMS_CAMERAPARAMETERS %d %s\n" % (pid, " ".join(repr(float(x)) for x in par)))

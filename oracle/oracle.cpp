@@ -194,10 +194,13 @@ struct Edge {
   double rkDelta = 1.0;     // RobustKernel::_delta
   int paramId = -1;         // EdgeProjectXYZ2UV: id of its CameraParameters (types_six_dof_expmap.cpp:241-256)
   double camPar[4] = {1, 0, 0, 0.5};  // focal_length, principle_point x y, baseline of that parameter
+  double offset[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // EdgeSE3PointXYZ: ParameterSE3Offset::offset() as Iso
 };
 
-inline int vertex_dim(int kind) { return kind == ORC_VERTEX_SE2 ? 3 : kind == ORC_VERTEX_XYZ ? 3 : 6; }
-inline int edge_dim(int kind) { return kind == ORC_EDGE_SE2 ? 3 : kind == ORC_EDGE_SE3 ? 6 : 2; }  // P2MC, XYZ2UV: 2
+inline int vertex_dim(int kind) { return kind == ORC_VERTEX_SE2 ? 3 : kind == ORC_VERTEX_XYZ ? 3 : kind == ORC_VERTEX_XY ? 2 : 6; }
+inline int edge_dim(int kind) {  // P2MC, XYZ2UV, SE2_XY: 2
+  return kind == ORC_EDGE_SE2 ? 3 : kind == ORC_EDGE_SE3 ? 6 : kind == ORC_EDGE_SE3_XYZ ? 3 : 2;
+}
 
 // ---- SE2 (types/slam2d/se2.h:41-119) ----
 struct SE2 { double x, y, th; };
@@ -358,6 +361,20 @@ void compute_error(Edge* e) {
       const double proj[2] = {p[0] / p[2], p[1] / p[2]};
       e->err[0] = e->meas[0] - (proj[0] * e->camPar[0] + e->camPar[1]);
       e->err[1] = e->meas[1] - (proj[1] * e->camPar[0] + e->camPar[2]);
+      break;
+    }
+    case ORC_EDGE_SE2_XY: {  // types/slam2d/edge_se2_pointxy.h:46-51: (v1^-1 * l2) - z, SE2 * Vector2d (se2.h:80-83)
+      SE2 xi = se2_inv(SE2{v0->est[0], v0->est[1], v0->est[2]});
+      const double c = cos(xi.th), s = sin(xi.th);
+      e->err[0] = (c * v1->est[0] - s * v1->est[1] + xi.x) - e->meas[0];
+      e->err[1] = (s * v1->est[0] + c * v1->est[1] + xi.y) - e->meas[1];
+      break;
+    }
+    case ORC_EDGE_SE3_XYZ: {  // types/slam3d/edge_se3_pointxyz.cpp:98-108; cache: parameter_se3_offset.cpp:75-80
+      Iso X, O; memcpy(&X, v0->est, sizeof(Iso)); memcpy(&O, e->offset, sizeof(Iso));
+      Iso w2n = iso_inverse(iso_mul(X, O));
+      for (int r = 0; r < 3; ++r)
+        e->err[r] = (w2n.R[r] * v1->est[0] + w2n.R[r + 3] * v1->est[1] + w2n.R[r + 6] * v1->est[2] + w2n.t[r]) - e->meas[r];
       break;
     }
   }
@@ -542,6 +559,48 @@ void linearize(Edge* e) {
       J[10] = x / z_2 * f;           J[11] = y / z_2 * f;
       break;
     }
+    case ORC_EDGE_SE2_XY: {  // types/slam2d/edge_se2_pointxy.cpp:67-95
+      const double x1 = v0->est[0], y1 = v0->est[1], th1 = v0->est[2];
+      const double x2 = v1->est[0], y2 = v1->est[1];
+      double aux_1 = cos(th1);
+      double aux_2 = -aux_1;
+      double aux_3 = sin(th1);
+      double* Ji = e->Ji;  // 2 x 3
+      double* Jj = e->Jj;  // 2 x 2
+      Ji[0 + 2 * 0] = aux_2;
+      Ji[0 + 2 * 1] = -aux_3;
+      Ji[0 + 2 * 2] = aux_1 * y2 - aux_1 * y1 - aux_3 * x2 + aux_3 * x1;
+      Ji[1 + 2 * 0] = aux_3;
+      Ji[1 + 2 * 1] = aux_2;
+      Ji[1 + 2 * 2] = -aux_3 * y2 + aux_3 * y1 - aux_1 * x2 + aux_1 * x1;
+      Jj[0 + 2 * 0] = aux_1;
+      Jj[0 + 2 * 1] = aux_3;
+      Jj[1 + 2 * 0] = -aux_3;
+      Jj[1 + 2 * 1] = aux_1;
+      break;
+    }
+    case ORC_EDGE_SE3_XYZ: {  // types/slam3d/edge_se3_pointxyz.cpp:110-135
+      Iso X, O; memcpy(&X, v0->est, sizeof(Iso)); memcpy(&O, e->offset, sizeof(Iso));
+      Iso w2l = iso_inverse(X);
+      double Zcam[3];
+      for (int r = 0; r < 3; ++r) Zcam[r] = w2l.R[r] * v1->est[0] + w2l.R[r + 3] * v1->est[1] + w2l.R[r + 6] * v1->est[2] + w2l.t[r];
+      double J[27];  // 3 x 9; constructor: fill(0), block(0,0) = -I
+      for (int i = 0; i < 27; ++i) J[i] = 0;
+      J[0 + 3 * 0] = -1; J[1 + 3 * 1] = -1; J[2 + 3 * 2] = -1;
+      J[0 + 3 * 4] = -2 * Zcam[2];
+      J[0 + 3 * 5] = 2 * Zcam[1];
+      J[1 + 3 * 3] = 2 * Zcam[2];
+      J[1 + 3 * 5] = -2 * Zcam[0];
+      J[2 + 3 * 3] = -2 * Zcam[1];
+      J[2 + 3 * 4] = 2 * Zcam[0];
+      for (int i = 0; i < 9; ++i) J[18 + i] = w2l.R[i];
+      Iso Oi = iso_inverse(O);
+      double Jhom[27];
+      mm<3, 3, 9>(Oi.R, J, Jhom);
+      for (int i = 0; i < 18; ++i) e->Ji[i] = Jhom[i];
+      for (int i = 0; i < 9; ++i) e->Jj[i] = Jhom[18 + i];
+      break;
+    }
   }
 }
 
@@ -600,8 +659,12 @@ void oplus(Vertex* v, const double* u) {
       for (int i = 0; i < 7; ++i) v->est[i] = r[i];
       break;
     }
-    case ORC_VERTEX_XYZ: {  // types/sba/types_sba.h:151-155
+    case ORC_VERTEX_XYZ: {  // types/sba/types_sba.h:151-155, types/slam3d/vertex_pointxyz.h:49-52
       v->est[0] += u[0]; v->est[1] += u[1]; v->est[2] += u[2];
+      break;
+    }
+    case ORC_VERTEX_XY: {  // types/slam2d/vertex_point_xy.h:76-80
+      v->est[0] += u[0]; v->est[1] += u[1];
       break;
     }
   }
@@ -716,6 +779,8 @@ void construct_quadratic_form(Edge* e) {
     case ORC_EDGE_SE3: construct_quadratic_form_t<6, 6, 6>(e); break;
     case ORC_EDGE_P2MC: construct_quadratic_form_t<2, 3, 6>(e); break;
     case ORC_EDGE_XYZ2UV: construct_quadratic_form_t<2, 3, 6>(e); break;
+    case ORC_EDGE_SE2_XY: construct_quadratic_form_t<2, 3, 2>(e); break;
+    case ORC_EDGE_SE3_XYZ: construct_quadratic_form_t<3, 6, 3>(e); break;
   }
 }
 // ---------------------------------------------------------------------------------------------
@@ -736,21 +801,34 @@ struct BlockPool {  // bump allocator for the block payloads
   }
 };
 struct SBM {
-  int rdim = 0, cdim = 0, nrows = 0, ncols = 0;  // uniform block dims; #block rows / cols
+  int rdim = 0, cdim = 0, nrows = 0, ncols = 0;  // uniform block dims (fix* solvers); #block rows / cols
+  // ... or, for the variable-size flavour (SparseBlockMatrix<MatrixXd> of BlockSolverX, `*_var` solvers): cumulative
+  // offsets, base[i] = first scalar row / column of block i, base[n] = total (sparse_block_matrix.h:198-204 keeps the
+  // END offsets in _rowBlockIndices; same information)
+  std::vector<int> rbase, cbase;
   std::vector<std::map<int, double*>> cols;
   BlockPool pool;
-  void resize(int nr, int nc, int rd, int cd) { nrows = nr; ncols = nc; rdim = rd; cdim = cd; cols.assign(nc, {}); }
+  int rd(int r) const { return rbase.empty() ? rdim : rbase[r + 1] - rbase[r]; }
+  int cd(int c) const { return cbase.empty() ? cdim : cbase[c + 1] - cbase[c]; }
+  int rb(int r) const { return rbase.empty() ? r * rdim : rbase[r]; }
+  int cb(int c) const { return cbase.empty() ? c * cdim : cbase[c]; }
+  int maxdim() const { int m = cdim; for (int c = 0; c < ncols && !cbase.empty(); ++c) m = std::max(m, cd(c)); return m; }
+  void resize(int nr, int nc, int rd_, int cd_) { nrows = nr; ncols = nc; rdim = rd_; cdim = cd_; rbase.clear(); cbase.clear(); cols.assign(nc, {}); }
+  void resize_var(const std::vector<int>& base) {  // square, block i spans [base[i], base[i+1])
+    nrows = ncols = (int)base.size() - 1; rdim = cdim = 0; rbase = base; cbase = base; cols.assign(ncols, {});
+  }
   double* block(int r, int c, bool alloc) {
     auto it = cols[c].find(r);
     if (it != cols[c].end()) return it->second;
     if (!alloc) return nullptr;
-    double* p = pool.get((size_t)rdim * cdim);
-    for (int i = 0; i < rdim * cdim; ++i) p[i] = 0;
+    const int sz = rd(r) * cd(c);
+    double* p = pool.get((size_t)sz);
+    for (int i = 0; i < sz; ++i) p[i] = 0;
     cols[c][r] = p;
     return p;
   }
   void clear() {  // sparse_block_matrix.hpp:67-83 (zero every block, keep structure)
-    for (auto& c : cols) for (auto& kv : c) memset(kv.second, 0, sizeof(double) * rdim * cdim);
+    for (int c = 0; c < ncols; ++c) for (auto& kv : cols[c]) memset(kv.second, 0, sizeof(double) * rd(kv.first) * cd(c));
   }
   size_t nonZeroBlocks() const { size_t n = 0; for (auto& c : cols) n += c.size(); return n; }
 };
@@ -772,20 +850,22 @@ struct LinearSolverCSparseO {
 
   // core/sparse_block_matrix_ccs.h:143-199 fillCCS(upperTriangle=true)
   void fill(const SBM& M, bool onlyValues) {
-    const int d = M.cdim;
-    const int n = M.ncols * d;
+    const int n = M.cb(M.ncols);
     if (!onlyValues) {
       size_t nz = 0;
-      for (int c = 0; c < M.ncols; ++c) for (auto& kv : M.cols[c]) nz += (kv.first == c) ? d * (d + 1) / 2 : d * d;
+      for (int c = 0; c < M.ncols; ++c)
+        for (auto& kv : M.cols[c]) nz += (kv.first == c) ? M.cd(c) * (M.cd(c) + 1) / 2 : M.rd(kv.first) * M.cd(c);
       Ap.assign(n + 1, 0); Ai.assign(nz, 0); Ax.assign(nz, 0);
     }
     int nz = 0;
     for (int i = 0; i < M.ncols; ++i) {
-      int cstart = i * d;
-      for (int c = 0; c < d; ++c) {
+      int cstart = M.cb(i);
+      const int dc = M.cd(i);
+      for (int c = 0; c < dc; ++c) {
         if (!onlyValues) Ap[cstart + c] = nz;
         for (auto& kv : M.cols[i]) {
-          int rstart = kv.first * d;
+          int rstart = M.rb(kv.first);
+          const int d = M.rd(kv.first);
           int elems = d;
           if (rstart == cstart) elems = c + 1;
           for (int r = 0; r < elems; ++r) {
@@ -822,8 +902,8 @@ struct LinearSolverCSparseO {
       std::vector<int> scalarPerm(n);
       size_t idx = 0;
       for (int i = 0; i < M.ncols; ++i) {
-        int base = P[i] * M.cdim;
-        for (int j = 0; j < M.cdim; ++j) scalarPerm[idx++] = base++;
+        int base = M.cb(P[i]);  // linear_solver_csparse.h:275-283: rowBaseOfBlock / rowsOfBlock of the permuted block
+        for (int j = 0; j < M.cd(P[i]); ++j) scalarPerm[idx++] = base++;
       }
       cs_free(P);
       S = (css*)cs_calloc(1, sizeof(css));
@@ -863,7 +943,7 @@ struct LinearSolverCSparseO {
     fill(M, S != nullptr);
     if (!S) computeSymbolic(M);
     if (!S) return false;
-    const int n = A.n, d = M.cdim;
+    const int n = A.n, d = M.maxdim();  // output blocks are d x d (variable sizes: padded with zeros)
     if ((int)work.size() < n) { work.assign(2 * n, 0); iwork.assign(4 * n, 0); }
     csn* N = g2o::csparse_extension::cs_chol_workspace(&A, S, iwork.data(), work.data());
     if (!N) return false;
@@ -889,9 +969,9 @@ struct LinearSolverCSparseO {
     struct Elem { int r, c; };
     std::vector<Elem> todo;
     for (int q = 0; q < nblocks; ++q)
-      for (int ir = 0; ir < d; ++ir)
-        for (int ic = 0; ic < d; ++ic) {
-          int r = perm[brow[q] * d + ir], c = perm[bcol[q] * d + ic];
+      for (int ir = 0; ir < M.rd(brow[q]); ++ir)
+        for (int ic = 0; ic < M.cd(bcol[q]); ++ic) {
+          int r = perm[M.rb(brow[q]) + ir], c = perm[M.cb(bcol[q]) + ic];
           if (r > c) std::swap(r, c);
           todo.push_back({r, c});
         }
@@ -899,9 +979,9 @@ struct LinearSolverCSparseO {
     std::sort(todo.begin(), todo.end(), [](const Elem& a2, const Elem& b2) { return a2.c > b2.c || (a2.c == b2.c && a2.r > b2.r); });
     for (const Elem& e : todo) entry(e.r, e.c);
     for (int q = 0; q < nblocks; ++q)
-      for (int ir = 0; ir < d; ++ir)
-        for (int ic = 0; ic < d; ++ic) {
-          int r = perm[brow[q] * d + ir], c = perm[bcol[q] * d + ic];
+      for (int ir = 0; ir < M.rd(brow[q]); ++ir)
+        for (int ic = 0; ic < M.cd(bcol[q]); ++ic) {
+          int r = perm[M.rb(brow[q]) + ir], c = perm[M.cb(bcol[q]) + ic];
           if (r > c) std::swap(r, c);
           out[(size_t)q * d * d + ir + (size_t)ic * d] = memo[(long long)r * n + c];  // column-major block
         }
@@ -922,6 +1002,7 @@ struct oracle_graph {
   std::vector<std::unique_ptr<Edge>> edges;  // addEdge order = internalId
   int rkKind = 0;            // robust kernel given to every edge (g2o.cpp:322-336)
   std::map<int, std::array<double, 4>> cameraParameters;  // PARAMS_CAMERAPARAMETERS id -> f cx cy baseline
+  std::map<int, std::array<double, 12>> se3Offsets;       // PARAMS_SE3OFFSET id -> offset as Iso [R col-major | t]
   double rkDelta = 1.0;
   // SparseOptimizer
   std::vector<Vertex*> activeVertices, ivMap;
@@ -989,9 +1070,13 @@ bool vertex_read(Vertex* v, const double* p, int n) {
       se3quat_inverse(c2w, v->est);
       return true;
     }
-    case ORC_VERTEX_XYZ:  // types/sba/types_sba.cpp:180-186
+    case ORC_VERTEX_XYZ:  // types/sba/types_sba.cpp:180-186; VertexPointXYZ: types/slam3d/vertex_pointxyz.cpp read
       if (n < 3) return false;
       v->est[0] = p[0]; v->est[1] = p[1]; v->est[2] = p[2];
+      return true;
+    case ORC_VERTEX_XY:  // types/slam2d/vertex_point_xy.cpp read
+      if (n < 2) return false;
+      v->est[0] = p[0]; v->est[1] = p[1];
       return true;
   }
   return false;
@@ -1038,6 +1123,20 @@ bool edge_read(Edge* e, const double* p, int n) {
       for (int i = 0; i < 2; ++i) for (int j = i; j < 2; ++j) { e->info[i + 2 * j] = p[k]; e->info[j + 2 * i] = p[k]; ++k; }
       return true;
     }
+    case ORC_EDGE_SE2_XY: {  // types/slam2d/edge_se2_pointxy.cpp:41-47: x y i00 i01 i11
+      if (n < 5) return false;
+      e->meas[0] = p[0]; e->meas[1] = p[1];
+      e->info[0] = p[2]; e->info[2] = p[3]; e->info[3] = p[4]; e->info[1] = p[3];
+      return true;
+    }
+    case ORC_EDGE_SE3_XYZ: {  // types/slam3d/edge_se3_pointxyz.cpp:62-84: paramId x y z + upper triangle of the information
+      if (n < 4) return false;
+      e->paramId = (int)p[0];
+      e->meas[0] = p[1]; e->meas[1] = p[2]; e->meas[2] = p[3];
+      int k = 4;
+      for (int i = 0; i < 3 && k < n; ++i) for (int j = i; j < 3 && k < n; ++j) { e->info[i + 3 * j] = p[k]; e->info[j + 3 * i] = p[k]; ++k; }
+      return true;
+    }
   }
   return false;
 }
@@ -1051,9 +1150,17 @@ void initial_estimate_to(Edge* e) {  // to = from * meas
   } else if (e->kind == ORC_EDGE_SE3) {
     Iso f, z; memcpy(&f, e->v[0]->est, sizeof(Iso)); memcpy(&z, e->meas, sizeof(Iso));
     Iso r = iso_mul(f, z); memcpy(e->v[1]->est, &r, sizeof(Iso));
+  } else if (e->kind == ORC_EDGE_SE2_XY) {  // types/slam2d/edge_se2_pointxy.cpp:55-64: vj = vi * measurement
+    const double c = cos(e->v[0]->est[2]), s = sin(e->v[0]->est[2]);
+    e->v[1]->est[0] = c * e->meas[0] - s * e->meas[1] + e->v[0]->est[0];
+    e->v[1]->est[1] = s * e->meas[0] + c * e->meas[1] + e->v[0]->est[1];
+  } else if (e->kind == ORC_EDGE_SE3_XYZ) {  // types/slam3d/edge_se3_pointxyz.cpp initialEstimate: cam->estimate() * (offset * z)
+    Iso X, O; memcpy(&X, e->v[0]->est, sizeof(Iso)); memcpy(&O, e->offset, sizeof(Iso));
+    Iso n2w = iso_mul(X, O);
+    for (int r = 0; r < 3; ++r) e->v[1]->est[r] = n2w.R[r] * e->meas[0] + n2w.R[r + 3] * e->meas[1] + n2w.R[r + 6] * e->meas[2] + n2w.t[r];
   }
 }
-void initial_estimate_from(Edge* e) {  // from = to * meas^-1
+void initial_estimate_from(Edge* e) {  // from = to * meas^-1 (the landmark edges cannot initialise their pose: left at the origin)
   if (e->kind == ORC_EDGE_SE2) {
     SE2 t{e->v[1]->est[0], e->v[1]->est[1], e->v[1]->est[2]};
     SE2 r = se2_mul(t, SE2{e->invMeas[0], e->invMeas[1], e->invMeas[2]});
@@ -1072,10 +1179,13 @@ void set_to_origin(Vertex* v) {
 
 int add_edge(G* g, int kind, int id1, int id2, const double* payload, int n) {
   // core/optimizable_graph.cpp:454-520 (binary edges, createEdges = true)
-  static const int vk0[4] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_XYZ, ORC_VERTEX_XYZ};
-  static const int vk1[4] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_CAM, ORC_VERTEX_SE3_EXPMAP};
+  static const int vk0[6] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_XYZ, ORC_VERTEX_XYZ, ORC_VERTEX_SE2, ORC_VERTEX_SE3};
+  static const int vk1[6] = {ORC_VERTEX_SE2, ORC_VERTEX_SE3, ORC_VERTEX_CAM, ORC_VERTEX_SE3_EXPMAP, ORC_VERTEX_XY, ORC_VERTEX_XYZ};
   if (kind == ORC_EDGE_XYZ2UV) {  // OptimizableGraph::addEdge -> resolveParameters: an unknown parameter id rejects the edge
     if (n < 1 || !g->cameraParameters.count((int)payload[0])) return -1;
+  }
+  if (kind == ORC_EDGE_SE3_XYZ) {
+    if (n < 1 || !g->se3Offsets.count((int)payload[0])) return -1;
   }
   Vertex* from = g->vertex(id1);
   Vertex* to = g->vertex(id2);
@@ -1092,6 +1202,7 @@ int add_edge(G* g, int kind, int id1, int id2, const double* payload, int n) {
   for (int i = 0; i < 6; ++i) e->err[i] = 0;
   if (!edge_read(e, payload, n)) { g->edges.pop_back(); return -1; }
   if (kind == ORC_EDGE_XYZ2UV) { const auto& cp = g->cameraParameters[e->paramId]; for (int i = 0; i < 4; ++i) e->camPar[i] = cp[i]; }
+  if (kind == ORC_EDGE_SE3_XYZ) { const auto& of = g->se3Offsets[e->paramId]; for (int i = 0; i < 12; ++i) e->offset[i] = of[i]; }
   from->edges.push_back(e);
   if (to != from) to->edges.push_back(e);
   if (doInit == 1) initial_estimate_to(e);
@@ -1167,7 +1278,14 @@ bool build_structure(G* g) {
   }
   const int pd = g->poseDim, ld = g->landmarkDim ? g->landmarkDim : 3;
   g->Hpp = SBM(); g->Hll = SBM(); g->Hpl = SBM(); g->Hschur = SBM();
-  g->Hpp.resize(g->numPoses, g->numPoses, pd, pd);
+  // BlockSolverX (`*_var` solvers, nothing marginalized): the blocks of Hpp take the dimension of their vertices
+  // (block_solver.hpp:156-176 collects blockPoseIndices); uniform dimensions stay on the fixed-size layout
+  bool variable = false;
+  std::vector<int> poseBase{0};
+  for (Vertex* v : g->ivMap) if (!v->marginalized) { poseBase.push_back(poseBase.back() + v->dim); variable |= v->dim != pd; }
+  if (variable && g->doSchur) return false;  // mixed pose dimensions under a Schur complement: not restated
+  if (variable) { g->Hpp.resize_var(poseBase); for (Vertex* v : g->ivMap) g->poseDim = std::max(g->poseDim, v->dim); }
+  else g->Hpp.resize(g->numPoses, g->numPoses, pd, pd);
   if (g->doSchur) {
     g->Hschur.resize(g->numPoses, g->numPoses, pd, pd);
     g->Hll.resize(g->numLandmarks, g->numLandmarks, ld, ld);
@@ -1259,11 +1377,12 @@ void build_system(G* g) {
 
 // ---- core/block_solver.hpp:563-604 ----
 void set_lambda(G* g, double lambda, bool backup) {
-  const int pd = g->poseDim, ld = g->landmarkDim;
-  if (backup) { g->diagBackupPose.resize((size_t)g->numPoses * pd); g->diagBackupLandmark.resize((size_t)g->numLandmarks * ld); }
+  const int ld = g->landmarkDim;
+  if (backup) { g->diagBackupPose.resize((size_t)g->sizePoses); g->diagBackupLandmark.resize((size_t)g->numLandmarks * ld); }
   for (int i = 0; i < g->numPoses; ++i) {
     double* blk = g->Hpp.block(i, i, false);
-    for (int k = 0; k < pd; ++k) { if (backup) g->diagBackupPose[(size_t)i * pd + k] = blk[k + pd * k]; blk[k + pd * k] += lambda; }
+    const int pd = g->Hpp.cd(i), b0 = g->Hpp.cb(i);
+    for (int k = 0; k < pd; ++k) { if (backup) g->diagBackupPose[(size_t)b0 + k] = blk[k + pd * k]; blk[k + pd * k] += lambda; }
   }
   for (int i = 0; i < g->numLandmarks; ++i) {
     double* blk = g->Hll.block(i, i, false);
@@ -1271,10 +1390,11 @@ void set_lambda(G* g, double lambda, bool backup) {
   }
 }
 void restore_diagonal(G* g) {
-  const int pd = g->poseDim, ld = g->landmarkDim;
+  const int ld = g->landmarkDim;
   for (int i = 0; i < g->numPoses; ++i) {
     double* blk = g->Hpp.block(i, i, false);
-    for (int k = 0; k < pd; ++k) blk[k + pd * k] = g->diagBackupPose[(size_t)i * pd + k];
+    const int pd = g->Hpp.cd(i), b0 = g->Hpp.cb(i);
+    for (int k = 0; k < pd; ++k) blk[k + pd * k] = g->diagBackupPose[(size_t)b0 + k];
   }
   for (int i = 0; i < g->numLandmarks; ++i) {
     double* blk = g->Hll.block(i, i, false);
@@ -1595,6 +1715,18 @@ int oracle_add_camera_parameters(oracle_graph* g, int id, double focal_length, d
   return 0;
 }
 
+// ParameterSE3Offset::read (types/slam3d/parameter_se3_offset.cpp:47-56): x y z qx qy qz qw, quaternion normalised
+int oracle_add_se3_offset(oracle_graph* g, int id, const double* xyzq) {
+  if (!g || !xyzq || g->se3Offsets.count(id)) return -1;
+  double q[4] = {xyzq[3], xyzq[4], xyzq[5], xyzq[6]};
+  quat_normalize(q);
+  std::array<double, 12> o;
+  quat_to_R(q, o.data());
+  o[9] = xyzq[0]; o[10] = xyzq[1]; o[11] = xyzq[2];
+  g->se3Offsets[id] = o;
+  return 0;
+}
+
 int oracle_load(oracle_graph* g, const char* path) {
   std::ifstream is(path);
   if (!is) return -1;
@@ -1615,6 +1747,15 @@ int oracle_load(oracle_graph* g, const char* path) {
     else if (token == "EDGE_SE3:QUAT") ekind = ORC_EDGE_SE3;
     else if (token == "EDGE_PROJECT_P2MC") ekind = ORC_EDGE_P2MC;
     else if (token == "VERTEX_SE3:EXPMAP") vkind = ORC_VERTEX_SE3_EXPMAP;
+    else if (token == "VERTEX_XY") vkind = ORC_VERTEX_XY;
+    else if (token == "VERTEX_TRACKXYZ") vkind = ORC_VERTEX_XYZ;
+    else if (token == "EDGE_SE2_XY") ekind = ORC_EDGE_SE2_XY;
+    else if (token == "EDGE_SE3_TRACKXYZ") ekind = ORC_EDGE_SE3_XYZ;
+    else if (token == "PARAMS_SE3OFFSET") {  // types/slam3d/parameter_se3_offset.cpp:47-56
+      int id; double o[7];
+      if (ss >> id >> o[0] >> o[1] >> o[2] >> o[3] >> o[4] >> o[5] >> o[6]) oracle_add_se3_offset(g, id, o);
+      continue;
+    }
     else if (token == "EDGE_PROJECT_XYZ2UV:EXPMAP") ekind = ORC_EDGE_XYZ2UV;
     else if (token == "PARAMS_CAMERAPARAMETERS") {  // optimizable_graph.cpp:398-415 + CameraParameters::read
       int id; double f, cx, cy, bl;
@@ -1768,6 +1909,7 @@ static int canonical_estimate(const Vertex* v, double* out) {
     case ORC_VERTEX_CAM: memcpy(out, v->est, 12 * sizeof(double)); return 12;
     case ORC_VERTEX_XYZ: memcpy(out, v->est, 3 * sizeof(double)); return 3;
     case ORC_VERTEX_SE3_EXPMAP: memcpy(out, v->est, 7 * sizeof(double)); return 7;
+    case ORC_VERTEX_XY: memcpy(out, v->est, 2 * sizeof(double)); return 2;
   }
   return -1;
 }
@@ -1792,7 +1934,7 @@ int oracle_get_edge(oracle_graph* g, int k, int* kind, int* id1, int* id2, doubl
   if (k < 0 || k >= (int)g->edges.size()) return -1;
   Edge* e = g->edges[k].get();
   *kind = e->kind; *id1 = e->v[0]->id; *id2 = e->v[1]->id;
-  int nm = e->kind == ORC_EDGE_SE2 ? 3 : e->kind == ORC_EDGE_SE3 ? 12 : 2;
+  int nm = e->kind == ORC_EDGE_SE2 ? 3 : e->kind == ORC_EDGE_SE3 ? 12 : e->kind == ORC_EDGE_SE3_XYZ ? 3 : 2;
   memcpy(meas, e->meas, nm * sizeof(double));
   memcpy(info, e->info, e->D * e->D * sizeof(double));
   return 0;
@@ -1800,6 +1942,21 @@ int oracle_get_edge(oracle_graph* g, int k, int* kind, int* id1, int* id2, doubl
 int oracle_get_blocks(oracle_graph* g, int which, int* rows, int* cols, double* values) {
   SBM* M = which == 0 ? &g->Hpp : which == 1 ? &g->Hll : which == 2 ? &g->Hpl : &g->Hschur;
   int n = 0;
+  if (!M->cbase.empty()) {  // variable block sizes: every block padded with zeros to maxdim x maxdim
+    const int D = M->maxdim();
+    for (int c = 0; c < M->ncols; ++c)
+      for (auto& kv : M->cols[c]) {
+        if (rows) {
+          rows[n] = kv.first; cols[n] = c;
+          double* dst = values + (size_t)n * D * D;
+          for (int i = 0; i < D * D; ++i) dst[i] = 0;
+          const int dr = M->rd(kv.first), dc = M->cd(c);
+          for (int cc = 0; cc < dc; ++cc) for (int rr = 0; rr < dr; ++rr) dst[rr + D * cc] = kv.second[rr + dr * cc];
+        }
+        ++n;
+      }
+    return n;
+  }
   const int sz = M->rdim * M->cdim;
   for (int c = 0; c < M->ncols; ++c)
     for (auto& kv : M->cols[c]) {

@@ -27,8 +27,10 @@ extern "C" {
 typedef struct oracle_graph oracle_graph;
 
 /* vertex / edge kinds (shared numbering with include/g2o_b200.h) */
-enum { ORC_VERTEX_SE2 = 0, ORC_VERTEX_SE3 = 1, ORC_VERTEX_CAM = 2, ORC_VERTEX_XYZ = 3, ORC_VERTEX_SE3_EXPMAP = 4 };
-enum { ORC_EDGE_SE2 = 0, ORC_EDGE_SE3 = 1, ORC_EDGE_P2MC = 2, ORC_EDGE_XYZ2UV = 3 };
+enum { ORC_VERTEX_SE2 = 0, ORC_VERTEX_SE3 = 1, ORC_VERTEX_CAM = 2, ORC_VERTEX_XYZ = 3, ORC_VERTEX_SE3_EXPMAP = 4, ORC_VERTEX_XY = 5 };
+/* SE2_XY = EdgeSE2PointXY (types/slam2d/edge_se2_pointxy.h: VertexSE2 -> VertexPointXY), SE3_XYZ = EdgeSE3PointXYZ
+ * (types/slam3d/edge_se3_pointxyz.h: VertexSE3 -> VertexPointXYZ, stored as ORC_VERTEX_XYZ) */
+enum { ORC_EDGE_SE2 = 0, ORC_EDGE_SE3 = 1, ORC_EDGE_P2MC = 2, ORC_EDGE_XYZ2UV = 3, ORC_EDGE_SE2_XY = 4, ORC_EDGE_SE3_XYZ = 5 };
 enum { ORC_GN = 0, ORC_LM = 1 };
 
 /* one record per outer iteration; mirrors the fields of G2OBatchStatistics (core/batch_stats.h:40-77) */
@@ -57,6 +59,9 @@ int oracle_set_fixed(oracle_graph* g, int id, int fixed);
 /* PARAMS_CAMERAPARAMETERS (types/sba/types_six_dof_expmap.h:45-80); must precede the XYZ2UV edges that name it.
  * XYZ2UV edge payload = paramId u v i00 i01 i11 (types_six_dof_expmap.cpp:241-256) */
 int oracle_add_camera_parameters(oracle_graph* g, int id, double focal_length, double cx, double cy, double baseline);
+/* PARAMS_SE3OFFSET id x y z qx qy qz qw (types/slam3d/parameter_se3_offset.cpp:47-56); must precede the SE3_XYZ edges that
+ * name it.  SE3_XYZ edge payload = paramId x y z + upper triangle of the 3x3 information; SE2_XY: x y i00 i01 i11 */
+int oracle_add_se3_offset(oracle_graph* g, int id, const double* xyz_qxyzw);
 
 /* apps/g2o_cli/g2o.cpp:272-320: gauge fixing + marginalisation of the low-dimensional vertices.
  * returns the id of the vertex fixed as gauge, -1 if none was needed, -2 on error. */

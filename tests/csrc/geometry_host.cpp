@@ -43,6 +43,15 @@ void gh_oplus(int kind, double* est, const double* u) {
   else if (kind == 4) expmap_oplus(est, u);
   else { est[0] += u[0]; est[1] += u[1]; est[2] += u[2]; }
 }
+void gh_se2_xy(const double* x, const double* l, const double* z, double* e, double* A, double* B) {
+  SE2 a{x[0], x[1], x[2]};
+  se2_xy_error(a, l, z, e);
+  se2_xy_jacobians(a, l, A, B);
+}
+void gh_se3_xyz(const double* X, const double* offset, const double* l, const double* z, double* e, double* A, double* B) {
+  se3_xyz_error(to_iso(X), to_iso(offset), l, z, e);
+  se3_xyz_jacobians(to_iso(X), to_iso(offset), l, A, B);
+}
 void gh_inverse3(const double* m, double* r) { inverse3(m, r); }
 void gh_dq_dR(const double* R, double* dq) { dq_dR(R, dq); }
 }

@@ -50,9 +50,9 @@ def fnv1a64(perm):
     return "%016x" % h
 
 
-EST_LEN = {0: 3, 1: 12, 2: 12, 3: 3, 4: 7}
-MEAS_LEN = {0: 3, 1: 12, 2: 2, 3: 2}
-EDGE_DIM = {0: 3, 1: 6, 2: 2, 3: 2}
+EST_LEN = {0: 3, 1: 12, 2: 12, 3: 3, 4: 7, 5: 2}
+MEAS_LEN = {0: 3, 1: 12, 2: 2, 3: 2, 4: 2, 5: 3}
+EDGE_DIM = {0: 3, 1: 6, 2: 2, 3: 2, 4: 2, 5: 3}
 
 
 class Oracle:
@@ -88,6 +88,10 @@ class Oracle:
     def add_camera_parameters(self, pid, focal_length, cx, cy, baseline):
         self.L.oracle_add_camera_parameters.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4
         assert self.L.oracle_add_camera_parameters(self.g, int(pid), focal_length, cx, cy, baseline) == 0
+
+    def add_se3_offset(self, pid, xyz_qxyzw):
+        o = np.ascontiguousarray(xyz_qxyzw, np.float64)
+        assert self.L.oracle_add_se3_offset(self.g, int(pid), _p(o)) == 0
 
     def setup_cli(self, requires_marginalize=True):
         return self.L.oracle_setup_cli(self.g, int(requires_marginalize))

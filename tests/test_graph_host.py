@@ -103,7 +103,7 @@ FIX 2
     o = g.SparseOptimizer(device=-1)
     assert o.load(f)
     vc, ec = o.counts()
-    assert list(vc) == [3, 0, 0, 0, 0] and list(ec) == [2, 0, 0, 0]
+    assert list(vc) == [3, 0, 0, 0, 0, 0] and list(ec) == [2, 0, 0, 0, 0, 0]
     # vertex 1 was created by the first edge: estimate = x0 * z; the later VERTEX line is ignored (duplicate id)
     assert np.allclose(o.vertex_estimate(1), [1.0, 0.0, 0.5])
     assert o.setup_cli() == -1  # vertex 2 is already fixed -> no gauge needed
@@ -132,7 +132,7 @@ def test_expmap_ba_setup_text_round_trip_and_structure(tmp_path):
     synth.feed(p, o)
     assert b.load(path) and o2.load(path)
     vc, ec = b.counts()
-    assert list(vc) == [0, 0, 0, 60, 9] and list(ec) == [0, 0, 0, len(p["edge_v0"])]
+    assert list(vc) == [0, 0, 0, 60, 9, 0] and list(ec) == [0, 0, 0, len(p["edge_v0"]), 0, 0]
     for vid in list(p["cam_ids"]) + list(p["point_ids"][::7]):
         ea, eb = a.vertex_estimate(int(vid)), b.vertex_estimate(int(vid))
         assert np.array_equal(ea, eb)

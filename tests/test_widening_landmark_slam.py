@@ -1,0 +1,398 @@
+"""landmark SLAM - EdgeSE2PointXY / VertexPointXY (types/slam2d/edge_se2_pointxy.{h,cpp}) and
+EdgeSE3PointXYZ / VertexPointXYZ / ParameterSE3Offset (types/slam3d/edge_se3_pointxyz.cpp, parameter_se3_offset.cpp) beside
+the pose-pose edges of their pose kind, nothing marginalized: the reference's variable-block-size path (BlockSolverX,
+`gn_var` / `lm_var`; the set-up of examples/tutorial_slam2d).
+
+CPU: the oracle's restatement is pinned (analytic vs numeric Jacobians as in types/slam3d/test_slam3d_jacobian.cpp, optimum
+against an independent scipy solver of the same cost), the device math (host build of csrc/geometry.cuh) equals the oracle's,
+loader / saver / index mapping of the new tags.  GPU: the CUDA path against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import needs_oracle
+from helpers import ROOT, rel_err
+
+sys.path.insert(0, ROOT)
+
+
+def _problems(small=False):
+    from openslam_g2o_b200 import synth
+    if small:
+        return [synth.landmark_slam_2d(30, 14, seed=5), synth.landmark_slam_3d(24, 12, seed=6)]
+    return [synth.landmark_slam_2d(), synth.landmark_slam_3d()]
+
+
+def _oracle(p, block_ordering=True):
+    from oracle_binding import Oracle
+    from openslam_g2o_b200 import synth
+    o = Oracle()
+    synth.feed(p, o)
+    assert o.setup_cli(False) == int(p["pose_ids"][0])   # gauge: the first max-dimension vertex; nothing marginalized
+    o.set_block_ordering(block_ordering)
+    assert o.initialize_optimization()
+    return o
+
+
+@needs_oracle
+@pytest.mark.parametrize("which", [0, 1])
+def test_oracle_jacobians_match_numeric_differences(which):
+    """b = -J^T Omega e of the restated linearizeOplus (edge_se2_pointxy.cpp:67-95, edge_se3_pointxyz.cpp:110-135) equals the
+    central-difference gradient of chi2 / 2 along every oplus coordinate (poses AND points; variable block sizes)"""
+    p = _problems(small=True)[which]
+    o = _oracle(p)
+    o.algorithm_init()
+    assert o.build_structure()
+    chi0 = o.compute_active_errors()
+    o.build_system()
+    b = o.b()
+    d = o.dims()
+    assert d["numLandmarks"] == 0 and d["sizePoses"] == len(b)
+    n_free_poses = len(p["pose_ids"]) - 1
+    assert len(b) == n_free_poses * (3 if which == 0 else 6) + len(p["lm_ids"]) * (2 if which == 0 else 3)
+    n = len(b)
+    rng = np.random.default_rng(which)
+    delta = 1e-6
+    for k in rng.choice(n, 24, replace=False):
+        g = 0.0
+        for sgn in (+1, -1):
+            o.push()
+            x = np.zeros(n)
+            x[k] = sgn * delta
+            o.set_x(x)
+            o.update()
+            g += sgn * o.compute_active_errors()
+            o.pop()
+        g /= 2 * delta
+        assert abs(-0.5 * g - b[k]) <= 2e-5 * max(1.0, abs(b[k])), (k, g, b[k])
+    assert chi0 > 0
+
+
+@needs_oracle
+def test_oracle_optima_match_an_independent_solver():
+    """converged chi2 of the oracle == minimum scipy.optimize.least_squares finds for the same cost written independently
+    (numeric Jacobians, rotation-vector parametrisation in 3D): pins error definitions, sensor offset, information
+    weighting and the variable-block-size linear system"""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    from oracle_binding import LM
+    p2, p3 = _problems(small=True)
+
+    def chol_info(iu, D):
+        Om = np.zeros((len(iu), D, D))
+        k = 0
+        for i in range(D):
+            for j in range(i, D):
+                Om[:, i, j] = Om[:, j, i] = iu[:, k]
+                k += 1
+        return np.linalg.cholesky(Om)
+
+    def index_of(ids, v):
+        lut = {int(x): i for i, x in enumerate(ids)}
+        return np.asarray([lut[int(x)] for x in v])
+
+    # ---- 2D
+    npz, nl = len(p2["pose_ids"]), len(p2["lm_ids"])
+    a, b = index_of(p2["pose_ids"], p2["odo_v0"]), index_of(p2["pose_ids"], p2["odo_v1"])
+    op, ol = index_of(p2["pose_ids"], p2["obs_v0"]), index_of(p2["lm_ids"], p2["obs_v1"])
+    Lo, Ll = chol_info(p2["odo_payload"][:, 3:], 3), chol_info(p2["obs_payload"][:, 2:], 2)
+    zo, zl = p2["odo_payload"][:, :3], p2["obs_payload"][:, :2]
+    wrap = lambda t: (t + np.pi) % (2 * np.pi) - np.pi
+
+    def res2(x):
+        P = np.concatenate([p2["pose_payload"][:1], x[:3 * (npz - 1)].reshape(-1, 3)])
+        Lm = x[3 * (npz - 1):].reshape(-1, 2)
+        c, s = np.cos(P[a, 2]), np.sin(P[a, 2])
+        dx, dy = P[b, 0] - P[a, 0], P[b, 1] - P[a, 1]
+        rel = np.stack([c * dx + s * dy, -s * dx + c * dy, wrap(P[b, 2] - P[a, 2])], axis=1)  # xi^-1 xj
+        cz, sz = np.cos(zo[:, 2]), np.sin(zo[:, 2])                                             # z^-1 * rel
+        dxe, dye = rel[:, 0] - zo[:, 0], rel[:, 1] - zo[:, 1]
+        e1 = np.stack([cz * dxe + sz * dye, -sz * dxe + cz * dye, wrap(rel[:, 2] - zo[:, 2])], axis=1)
+        c, s = np.cos(P[op, 2]), np.sin(P[op, 2])
+        dx, dy = Lm[ol, 0] - P[op, 0], Lm[ol, 1] - P[op, 1]
+        e2 = np.stack([c * dx + s * dy, -s * dx + c * dy], axis=1) - zl
+        return np.concatenate([np.einsum("eji,ej->ei", Lo, e1).reshape(-1), np.einsum("eji,ej->ei", Ll, e2).reshape(-1)])
+    x0 = np.concatenate([p2["pose_payload"][1:].reshape(-1), p2["lm_payload"].reshape(-1)])
+    sol = least_squares(res2, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=100000)
+    o = _oracle(p2)
+    n, st = o.optimize(LM, 20)
+    chi = st[n - 1].chi2
+    assert abs(float(np.sum(sol.fun ** 2)) - chi) <= 1e-6 * chi, (float(np.sum(sol.fun ** 2)), chi)
+
+    # ---- 3D
+    npz, nl = len(p3["pose_ids"]), len(p3["lm_ids"])
+    a, b = index_of(p3["pose_ids"], p3["odo_v0"]), index_of(p3["pose_ids"], p3["odo_v1"])
+    op, ol = index_of(p3["pose_ids"], p3["obs_v0"]), index_of(p3["lm_ids"], p3["obs_v1"])
+    Lo, Ll = chol_info(p3["odo_payload"][:, 7:], 6), chol_info(p3["obs_payload"][:, 4:], 3)
+    zt, zq = p3["odo_payload"][:, :3], p3["odo_payload"][:, 3:7]
+    zR = Rotation.from_quat(zq / np.linalg.norm(zq, axis=1, keepdims=True)).as_matrix()
+    zl = p3["obs_payload"][:, 1:4]
+    off = p3["offsets"][0]
+    Ro, to = Rotation.from_quat(off[3:]).as_matrix(), off[:3]
+    t0 = p3["pose_payload"][:, :3]
+    R0 = Rotation.from_quat(p3["pose_payload"][:, 3:7]).as_matrix()
+
+    def res3(x):
+        rv = np.concatenate([np.zeros((1, 3)), x[:3 * (npz - 1)].reshape(-1, 3)])
+        dt = np.concatenate([np.zeros((1, 3)), x[3 * (npz - 1):6 * (npz - 1)].reshape(-1, 3)])
+        Lm = x[6 * (npz - 1):].reshape(-1, 3)
+        R = np.einsum("nij,njk->nik", R0, Rotation.from_rotvec(rv).as_matrix())
+        t = t0 + dt
+        Rij = np.einsum("eji,ejk->eik", R[a], R[b])
+        tij = np.einsum("eji,ej->ei", R[a], t[b] - t[a])
+        Rd = np.einsum("eji,ejk->eik", zR, Rij)
+        td = np.einsum("eji,ej->ei", zR, tij - zt)
+        q = Rotation.from_matrix(Rd).as_quat()
+        q = q * np.where(q[:, 3:4] < 0, -1.0, 1.0)
+        e1 = np.concatenate([td, q[:, :3]], axis=1)
+        Rs = np.einsum("nij,jk->nik", R, Ro)                   # sensor in the world: X * offset
+        ts = t + np.einsum("nij,j->ni", R, to)
+        e2 = np.einsum("eji,ej->ei", Rs[op], Lm[ol] - ts[op]) - zl
+        return np.concatenate([np.einsum("eji,ej->ei", Lo, e1).reshape(-1), np.einsum("eji,ej->ei", Ll, e2).reshape(-1)])
+    x0 = np.concatenate([np.zeros(6 * (npz - 1)), p3["lm_payload"].reshape(-1)])
+    sol = least_squares(res3, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=200000)
+    o = _oracle(p3)
+    n, st = o.optimize(LM, 25)
+    chi = st[n - 1].chi2
+    assert abs(float(np.sum(sol.fun ** 2)) - chi) <= 1e-6 * chi, (float(np.sum(sol.fun ** 2)), chi)
+
+
+@needs_oracle
+def test_scalar_and_block_ordering_reach_the_same_optimum():
+    """`*_var` solvers order scalars (solver_csparse.cpp:53-55: blockOrdering = false), the product orders blocks - the same
+    linear systems, so the same iterates to rounding"""
+    from oracle_binding import LM
+    for p in _problems(small=True):
+        chis = []
+        for bo in (False, True):
+            o = _oracle(p, block_ordering=bo)
+            n, st = o.optimize(LM, 6)
+            chis.append([s.chi2 for s in st[:n]])
+        assert len(chis[0]) == len(chis[1])
+        assert np.abs(np.array(chis[0]) - np.array(chis[1])).max() <= 1e-8 * max(chis[0])
+
+
+@needs_oracle
+def test_device_math_equals_the_oracle_edge_by_edge():
+    """host build of the very functions the kernels call (csrc/geometry.cuh: se2_xy_*, se3_xyz_*) against the oracle's
+    errors for every sighting of the synthetic graphs, and analytic vs central-difference Jacobians of the device math"""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "tests", "csrc", "libgeometry_host.so"))
+    from scipy.spatial.transform import Rotation
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(8)
+    # 2D: e, A (2x3), B (2x2) at random states
+    for _ in range(50):
+        x = np.array([rng.normal(0, 3), rng.normal(0, 3), rng.uniform(-np.pi, np.pi)])
+        l, z = rng.normal(0, 4, 2), rng.normal(0, 2, 2)
+        e, A, B = np.zeros(2), np.zeros(6), np.zeros(4)
+        lib.gh_se2_xy(ptr(x), ptr(l), ptr(z), ptr(e), ptr(A), ptr(B))
+        c, s = np.cos(x[2]), np.sin(x[2])
+        d = l - x[:2]
+        assert np.abs(e - (np.array([c * d[0] + s * d[1], -s * d[0] + c * d[1]]) - z)).max() < 1e-12
+        A, B = A.reshape(3, 2).T, B.reshape(2, 2).T
+        num = np.zeros((2, 5))
+        for k in range(5):
+            for sgn in (+1, -1):
+                x2, l2 = x.copy(), l.copy()
+                if k < 3:
+                    x2[k] += sgn * 1e-6
+                else:
+                    l2[k - 3] += sgn * 1e-6
+                e2 = np.zeros(2)
+                lib.gh_se2_xy(ptr(x2), ptr(l2), ptr(z), ptr(e2), ptr(np.zeros(6)), ptr(np.zeros(4)))
+                num[:, k] += sgn * e2 / 2e-6
+        assert np.abs(np.concatenate([A, B], axis=1) - num).max() < 1e-6
+    # 3D: against an independent formula and numeric differences along the VertexSE3 oplus (t, 2 * q_xyz convention)
+    for _ in range(50):
+        Rm = Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        t = rng.normal(0, 3, 3)
+        Ro = Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        to = rng.normal(0, 0.3, 3)
+        X = np.concatenate([Rm.T.reshape(-1), t])       # column-major R | t
+        O = np.concatenate([Ro.T.reshape(-1), to])
+        l, z = rng.normal(0, 4, 3), rng.normal(0, 2, 3)
+        e, A, B = np.zeros(3), np.zeros(18), np.zeros(9)
+        lib.gh_se3_xyz(ptr(X), ptr(O), ptr(l), ptr(z), ptr(e), ptr(A), ptr(B))
+        Rs, ts = Rm @ Ro, t + Rm @ to
+        assert np.abs(e - (Rs.T @ (l - ts) - z)).max() < 1e-12
+        A, B = A.reshape(6, 3).T, B.reshape(3, 3).T
+        num = np.zeros((3, 9))
+        for k in range(9):
+            for sgn in (+1, -1):
+                X2, l2 = X.copy(), l.copy()
+                if k < 6:
+                    u = np.zeros(6)
+                    u[k] = sgn * 1e-6
+                    lib.gh_oplus(1, ptr(X2), ptr(u))
+                else:
+                    l2[k - 6] += sgn * 1e-6
+                e2 = np.zeros(3)
+                lib.gh_se3_xyz(ptr(X2), ptr(O), ptr(l2), ptr(z), ptr(e2), ptr(np.zeros(18)), ptr(np.zeros(9)))
+                num[:, k] += sgn * e2 / 2e-6
+        assert np.abs(np.concatenate([A, B], axis=1) - num).max() < 1e-5
+
+
+def test_loader_saver_and_index_mapping_of_the_new_tags(tmp_path):
+    """VERTEX_XY / EDGE_SE2_XY / VERTEX_TRACKXYZ / EDGE_SE3_TRACKXYZ / PARAMS_SE3OFFSET through load -> setup -> initialize ->
+    host-only structure phase -> save -> load; the landmarks are numbered with the poses (nothing marginalized)"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    for p in _problems(small=True):
+        path = tmp_path / (p["kind"] + ".g2o")
+        synth.write_g2o(p, path)
+        opt = g.SparseOptimizer(device=-1)
+        opt.set_algorithm("lm_var")
+        assert opt.load(path)
+        vc, ec = opt.counts()
+        three_d = p["kind"] == "slam3d"
+        assert vc[g.VERTEX_SE3 if three_d else g.VERTEX_SE2] == len(p["pose_ids"])
+        assert vc[g.VERTEX_XYZ if three_d else g.VERTEX_XY] == len(p["lm_ids"])
+        assert ec[g.EDGE_SE3_XYZ if three_d else g.EDGE_SE2_XY] == len(p["obs_v0"])
+        assert opt.setup_cli() == int(p["pose_ids"][0])
+        assert opt.initialize_optimization()
+        ids = sorted([int(i) for i in p["pose_ids"][1:]] + [int(i) for i in p["lm_ids"]])
+        for h, vid in enumerate(ids):   # buildIndexMapping: ascending id, nobody marginalized
+            info = opt.vertex_info(vid)
+            assert info["hessian_index"] == h and not info["marginalized"]
+        opt._ensure_uploaded()
+        assert opt.context.build_structure()
+        d = opt.context.dims()
+        assert d["numPoses"] == len(ids) and d["numLandmarks"] == 0 and d["poseDim"] == (6 if three_d else 3)
+        assert d["numEdges"] == len(p["odo_v0"]) + len(p["obs_v0"])
+        out = tmp_path / (p["kind"] + "_out.g2o")
+        assert opt.save(out)
+        opt2 = g.SparseOptimizer(device=-1)
+        assert opt2.load(out)
+        for vid in list(p["pose_ids"][:5]) + list(p["lm_ids"][:5]):
+            assert rel_err(opt2.vertex_estimate(int(vid)), opt.vertex_estimate(int(vid))) < 1e-15
+        assert (opt2.counts()[1] == ec).all()
+        # a solver that marginalizes (fix*) is refused for these families: no Schur complement over XY / TRACKXYZ here
+        opt3 = g.SparseOptimizer(device=-1)
+        opt3.set_algorithm("lm_fix6_3" if three_d else "lm_fix3_2")
+        opt3.load(path)
+        opt3.setup_cli()
+        opt3.initialize_optimization()
+        opt3._ensure_uploaded()
+        with pytest.raises(g.B200Error):
+            opt3.context.build_structure()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _padded(o, p):
+    """per Hessian index: dimension of the vertex (oracle order) -> scatter maps from the oracle's dense x / b to the padded
+    layout of the product (poseDim entries per vertex)"""
+    ids, kinds, hidx, flags = o.vertices()
+    D = 6 if p["kind"] == "slam3d" else 3
+    dim = {int(h): (D if k in (0, 1) else (3 if k == 3 else 2)) for h, k in zip(hidx, kinds) if h >= 0}
+    n = len(dim)
+    idx = []
+    for h in range(n):
+        idx += [h * D + k for k in range(dim[h])]
+    return np.asarray(idx), n * D
+
+
+@pytest.mark.gpu
+@needs_oracle
+@pytest.mark.parametrize("which", [0, 1])
+def test_landmark_slam_matches_oracle(which):
+    """structure (block pattern, ordering), chi2, every Hpp block and b, one solve, one update, marginals and the LM
+    trajectory of the CUDA path against the oracle on the synthetic landmark-SLAM graphs"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    from oracle_binding import LM
+    p = _problems()[which]
+    o = _oracle(p)
+    opt = g.SparseOptimizer(device=0)
+    opt.set_algorithm("lm_var")
+    synth.feed(p, opt)
+    assert opt.setup_cli() == int(p["pose_ids"][0])
+    assert opt.initialize_optimization()
+    opt._ensure_uploaded()
+    ctx = opt.context
+    o.algorithm_init()
+    assert ctx.build_structure() and o.build_structure()
+    chi_g, chi_o = ctx.compute_active_errors(), o.compute_active_errors()
+    assert abs(chi_g - chi_o) <= 1e-11 * chi_o
+    ctx.build_system(); o.build_system()
+    idx, npad = _padded(o, p)
+    D = 6 if which else 3
+    b_g = ctx.b()
+    assert len(b_g) == npad
+    assert rel_err(b_g[idx], o.b()) < 1e-10
+    mask = np.ones(npad, bool); mask[idx] = False
+    assert np.all(b_g[mask] == 0)
+    rg, cg, vg = ctx.blocks(0)
+    ro, co, vo = o.blocks(0)       # the oracle pads its variable-size blocks the same way
+    assert np.array_equal(rg, ro) and np.array_equal(cg, co)
+    assert rel_err(vg, vo) < 1e-10
+    lam = o.lambda_init()
+    ctx.set_lambda(lam); o.set_lambda(lam)
+    assert ctx.solve() and o.solve()
+    assert np.array_equal(ctx.block_ordering(), o.block_perm())
+    x_g = ctx.x()
+    assert rel_err(x_g[idx], o.x()) < 1e-7
+    assert np.all(x_g[mask] == 0)
+    ctx.restore_diagonal(); o.restore_diagonal()
+    # marginals of a few poses and landmarks (padded blocks; the padding of a landmark block is the identity's)
+    nb = npad // D
+    pairs = [(int(i), int(i)) for i in np.random.default_rng(1).choice(nb, 6, replace=False)] + [(0, 1), (nb - 1, nb - 2)]
+    mg, mo = ctx.compute_marginals(pairs), o.compute_marginals(pairs)
+    ids_o, kinds_o, hidx_o, _ = o.vertices()
+    dim_of = {int(h): (D if k in (0, 1) else (3 if k == 3 else 2)) for h, k in zip(hidx_o, kinds_o) if h >= 0}
+    scale = max(np.abs(mo).max(), 1e-300)
+    for (r, c), bg, bo in zip(pairs, mg, mo):
+        dr, dc = dim_of[r], dim_of[c]
+        assert np.abs(bg[:dr, :dc] - bo[:dr, :dc]).max() <= 1e-8 * scale, (r, c)
+    ctx.update(); o.update()
+    opt.sync_estimates()
+    ids = [int(i) for i in p["pose_ids"]] + [int(i) for i in p["lm_ids"]]
+    est_g = np.stack([np.pad(opt.vertex_estimate(i), (0, 12))[:12] for i in ids])
+    est_o = np.stack([np.pad(o.vertex_estimate(i), (0, 12))[:12] for i in ids])
+    assert rel_err(est_g, est_o) < 1e-8
+
+    # full LM runs from the initial state
+    o2 = _oracle(p)
+    opt2 = g.SparseOptimizer(device=0)
+    opt2.set_algorithm("lm_var")
+    synth.feed(p, opt2)
+    opt2.setup_cli(); opt2.initialize_optimization()
+    n_g = opt2.optimize(8)
+    n_o, st = o2.optimize(LM, 8)
+    assert n_g == n_o
+    cg2 = np.array([s.chi2 for s in opt2.batch_statistics])
+    co2 = np.array([s.chi2 for s in st[:n_o]])
+    assert np.abs(cg2 - co2).max() <= 1e-6 * co2.max(), (cg2, co2)
+    assert [s.levenberg_iterations for s in opt2.batch_statistics] == [s.levenberg_iterations for s in st[:n_o]]
+    opt2.sync_estimates()
+    est_g = np.stack([np.pad(opt2.vertex_estimate(i), (0, 12))[:12] for i in ids])
+    est_o = np.stack([np.pad(o2.vertex_estimate(i), (0, 12))[:12] for i in ids])
+    assert rel_err(est_g, est_o) < 1e-6
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_landmark_slam_gauss_newton_robust_and_no_odometry():
+    """GN on the 2D graph with a Huber kernel; a 2D graph with sightings only (no pose-pose edges at all)"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    from oracle_binding import GN, LM
+    for p, alg, name, rk in ((synth.landmark_slam_2d(60, 30, seed=9), GN, "gn_var", "Huber"),
+                             (synth.landmark_slam_2d(40, 40, seed=10, odometry=False, max_range=9.0), LM, "lm_var", None),
+                             (synth.landmark_slam_3d(40, 30, seed=11), GN, "gn_var", "Cauchy")):
+        o = _oracle(p)
+        opt = g.SparseOptimizer(device=0)
+        opt.set_algorithm(name)
+        synth.feed(p, opt)
+        opt.setup_cli(); opt.initialize_optimization()
+        if rk:
+            o.set_robust_kernel(rk, 2.0)
+            opt.set_robust_kernel(rk, 2.0)
+        n_g = opt.optimize(5)
+        n_o, st = o.optimize(alg, 5)
+        assert n_g == n_o and n_g > 0
+        cg = np.array([s.chi2 for s in opt.batch_statistics])
+        co = np.array([s.chi2 for s in st[:n_o]])
+        assert np.abs(cg - co).max() <= 1e-6 * co.max(), (cg, co)
