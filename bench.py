@@ -250,7 +250,7 @@ def algorithmic_bytes(prob_kind, dims, info, n_hs, n_edges):
     return {"linearize": n_edges * 712 + dims["numPoses"] * 336}
 
 
-KERNEL_OF = {"linearize": {"ba": "ba_linearize_points_kernel", "pg": "pg_linearize_kernel"},
+KERNEL_OF = {"linearize": {"ba": "ba_linearize_packets_kernel", "pg": "pg_linearize_kernel"},
              "schur": {"ba": "schur_range_kernel"}, "backsub": {"ba": "ba_backsub_kernel"}}
 
 
@@ -591,6 +591,66 @@ def slim(r):
     return out
 
 
+def widening_block(device):
+    """SURVEY 8(f) rows measured beside the headline (N = 1, short; wall clock around synchronised calls): marginal
+    covariances through the supernodal sparse inverse (all diagonal blocks of sphere2500 in one sweep), and the two
+    landmark-SLAM families (`lm_var`) - LM iterations/s and chi2 parity against the oracle on the same arrays."""
+    import openslam_g2o_b200 as g
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import Oracle
+    synth = load_synth()
+    out = {}
+    # ---- marginals
+    opt = g.SparseOptimizer(device=device)
+    opt.set_algorithm("lm_fix6_3")
+    synth.feed(synth.sphere(), opt)
+    opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+    ctx = opt.context
+    assert ctx.build_structure()
+    ctx.compute_active_errors(); ctx.build_system()
+    nb = ctx.dims()["numPoses"]
+    diag = [(i, i) for i in range(nb)]
+    ctx.compute_marginals(diag[:4])  # plan + buffers of the sweep
+    l0 = ctx.launch_count()
+    t = time.perf_counter(); m_all = ctx.compute_marginals(diag); t_all = time.perf_counter() - t
+    launches = ctx.launch_count() - l0
+    t = time.perf_counter(); ctx.compute_marginals(diag[:8]); t_8 = time.perf_counter() - t
+    t = time.perf_counter(); ctx.compute_marginals([(0, nb - 1)]); t_off = time.perf_counter() - t
+    out["marginals_sphere2500"] = {"blocks": nb, "all_diagonal_blocks_ms": t_all * 1e3, "launches": launches, "eight_blocks_ms": t_8 * 1e3,
+                                   "one_block_outside_the_factor_pattern_ms": t_off * 1e3, "trace_sample": float(np.trace(m_all[nb // 2])),
+                                   "method": "one factorisation + supernodal sparse-inverse sweep (csrc/sparse_inverse.cuh); unit solves only outside the pattern of L"}
+    opt.close()
+    # ---- landmark SLAM
+    for key, prob in (("slam2d_lm_var", synth.landmark_slam_2d(2000, 3000, seed=40, growth=0.05)), ("slam3d_lm_var", synth.landmark_slam_3d(1500, 1200, seed=41))):
+        opt = g.SparseOptimizer(device=device)
+        opt.set_algorithm("lm_var")
+        o = Oracle()
+        for tgt in (opt, o):
+            synth.feed(prob, tgt)
+        opt.setup_cli(); o.setup_cli(False); o.set_block_ordering(True)
+        opt.initialize_optimization(); o.initialize_optimization()
+        iters = 10
+        opt.optimize(2)   # structure phase + CUDA graphs; restart from the initial state below
+        opt.close()
+        opt = g.SparseOptimizer(device=device)
+        opt.set_algorithm("lm_var")
+        synth.feed(prob, opt)
+        opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+        assert opt.context.build_structure()
+        opt.context.synchronize()
+        t = time.perf_counter(); n = opt.optimize(iters); opt.context.synchronize(); t_g = time.perf_counter() - t
+        t = time.perf_counter(); no, st = o.optimize(LM, iters); t_o = time.perf_counter() - t
+        cg = np.array([s.chi2 for s in opt.batch_statistics]); co = np.array([s.chi2 for s in st[:no]])
+        k = min(len(cg), len(co))
+        out[key] = {"poses": len(prob["pose_ids"]), "landmarks": len(prob["lm_ids"]), "edges": len(prob["odo_v0"]) + len(prob["obs_v0"]),
+                    "iterations": int(n), "lm_iterations_per_s": n / t_g, "oracle_lm_iterations_per_s": no / t_o,
+                    "chi2_rel": float(np.max(np.abs(cg[:k] - co[:k]) / np.abs(co[:k]))), "chi2_final": float(cg[-1]),
+                    "ordering_bit_exact": bool(np.array_equal(opt.context.block_ordering(), o.block_perm())),
+                    "note": "wall clock incl. the per-trial host round trips; first iteration excludes structure + symbolic analysis (GPU) but includes it for the oracle"}
+        opt.close()
+    return out
+
+
 def run_b200(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -612,6 +672,11 @@ def run_b200(args, rank, world):
                 extras[key] = {"error": repr(e)}
                 if world > 1:
                     raise
+    if rank == 0 and world == 1 and args.workload == "venice" and not args.no_extras and not args.nd_levels:
+        try:
+            main_res["widening"] = widening_block(local_rank)
+        except Exception as e:
+            main_res["widening"] = {"error": repr(e)}
     if rank == 0:
         main_res["configs"] = extras or None
         print(json.dumps(main_res))

@@ -496,6 +496,138 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
   for (int i = 0; i < 3; ++i) b_l[3ll * l + i] = bl[i];
 }
 
+// The same pass with one LANE per observation (round 2).  A warp owns a "packet": consecutive landmark ranks whose
+// observations number at most 32 (a landmark with more gets a packet of its own and is walked in chunks of 32).  Edge
+// arrays are read coalesced (the per-landmark kernel above reads them with a stride of the landmark's degree), all 32
+// lanes do Jacobian work, the 6x3 Hpl blocks of a chunk - consecutive slots - are staged in shared memory and leave as
+// ONE contiguous run of full 16-byte-per-lane stores, and every landmark's Hll / b_l is summed by one lane in ascending
+// edge order from the staged per-edge terms (fixed order: run-to-run bit-identical).
+constexpr int kLinWarps = 4;
+constexpr int kLinWarpDoubles = 32 * 18 + 32 * 12;   // Hpl blocks | per-edge Hll, b_l terms
+template <int MODEL>
+__global__ void __launch_bounds__(32 * kLinWarps, 4)
+ba_linearize_packets_kernel(int npk, const int4* __restrict__ packets, const int* __restrict__ lm_eptr,
+                            const int* __restrict__ lm_order, const int* __restrict__ e_pt,
+                            const int* __restrict__ e_cam, const int* __restrict__ e_hpl,
+                            const unsigned char* __restrict__ e_first, const double* __restrict__ pt_est,
+                            const double* __restrict__ cam_est, const double* __restrict__ cam_der,
+                            const double* __restrict__ meas, const double* __restrict__ info, int E, Robust rk,
+                            double* __restrict__ Hll, double* __restrict__ Hpl, double* __restrict__ b_l) {
+  __shared__ __align__(16) double sm[kLinWarps * kLinWarpDoubles];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int p = blockIdx.x * kLinWarps + wid;
+  if (p >= npk) return;   // whole warps leave: only __syncwarp below
+  double* blk = sm + wid * kLinWarpDoubles;   // [32][18]
+  double* hb = blk + 32 * 18;                 // [32][12]
+  // {first rank, #ranks (<= 32), first edge, end edge}: one load, so that the edge arrays can be requested right away
+  // (the kernel is bound by the latency of its dependent loads, not by bandwidth: measured, long-scoreboard stalls)
+  const int4 pk = __ldg(packets + p);
+  const int r0 = pk.x, nr = pk.y, eb = pk.z, ee = pk.w;
+  // the landmark this lane sums for
+  const bool owner = lane < nr;
+  const int own_a = owner ? lm_eptr[r0 + lane] : 0, own_b = owner ? lm_eptr[r0 + lane + 1] : 0;
+  const int own_l = owner ? lm_order[r0 + lane] : 0;
+  double H[9], bl[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) H[i] = 0.0;
+  bl[0] = bl[1] = bl[2] = 0.0;
+  for (int e0 = eb; e0 < ee; e0 += 32) {
+    const int e = e0 + lane;
+    const bool active = e < ee;
+    const int slot = active ? e_hpl[e] : -1;
+    const bool first = active && e_first[e] != 0;
+    if (active) {
+      const double4 X4 = *reinterpret_cast<const double4*>(pt_est + 4ll * e_pt[e]);
+      const double X[3] = {X4.x, X4.y, X4.z};
+      const int c = e_cam[e];
+      double der[16];
+      load_der(cam_der, c, der);
+      const double ct[3] = {cam_est[12ll * c], cam_est[12ll * c + 1], cam_est[12ll * c + 2]};
+      double Jp[6], Jc[12], err[2];
+      ba_jacobians<MODEL>(der, ct, X, Jp, Jc);
+      const double z[2] = {meas[e], meas[(long long)E + e]};
+      ba_error<MODEL>(der, X, z, err);
+      double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
+      if (rk.kind) {
+        double q0, q1;
+        robustify(rk, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), q0, q1);
+        w0 *= q1; w1 *= q1; w2 *= q1;
+      }
+      double JpW[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        JpW[k] = Jp[2 * k] * w0 + Jp[2 * k + 1] * w1;
+        JpW[k + 3] = Jp[2 * k] * w1 + Jp[2 * k + 1] * w2;
+      }
+      const double or0 = -(w0 * err[0] + w1 * err[1]), or1 = -(w1 * err[0] + w2 * err[1]);
+      double* t = hb + lane * 12;
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) t[r + 3 * c2] = JpW[r] * Jp[2 * c2] + JpW[r + 3] * Jp[2 * c2 + 1];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) t[9 + r] = Jp[2 * r] * or0 + Jp[2 * r + 1] * or1;
+      if (slot >= 0) {  // Hpl(cam, l) (6x3) = Jc^T W Jp into this lane's staging row
+        double2* d = reinterpret_cast<double2*>(blk + 18 * lane);
+#pragma unroll
+        for (int c2 = 0; c2 < 3; ++c2)
+#pragma unroll
+          for (int r = 0; r < 6; r += 2)
+            d[(r + 6 * c2) >> 1] = make_double2(Jc[2 * r] * JpW[c2] + Jc[2 * r + 1] * JpW[c2 + 3],
+                                                Jc[2 * r + 2] * JpW[c2] + Jc[2 * r + 3] * JpW[c2 + 3]);
+      }
+    }
+    __syncwarp();   // the staging rows are visible to the whole warp
+    // Hpl: the slots opened in this chunk are consecutive (slots are numbered in edge order)
+    const unsigned open_mask = __ballot_sync(0xffffffffu, slot >= 0 && first);
+    const int sb = __shfl_sync(0xffffffffu, slot, open_mask ? __ffs(open_mask) - 1 : 0);
+    // duplicate observations (same landmark, same camera) add to the block their run opened, in edge order: the row of
+    // the nearest opener below them in this chunk, or - opened in an earlier chunk - the block in global memory
+    unsigned dup = __ballot_sync(0xffffffffu, slot >= 0 && !first);
+    while (dup) {
+      const int d = __ffs(dup) - 1;
+      if (lane == d) {
+        const unsigned below = open_mask & ((1u << d) - 1u);
+        double* dst = below ? blk + 18 * (31 - __clz(below)) : Hpl + 18ll * slot;
+        const double* src = blk + 18 * d;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) dst[i] += src[i];
+      }
+      __syncwarp();
+      dup &= dup - 1;
+    }
+    {
+      // the opened blocks leave as one contiguous run: element i of the staging area = double2 (i % 9) of row i / 9
+      double2* dst = reinterpret_cast<double2*>(Hpl + 18ll * sb);
+      const double2* src = reinterpret_cast<const double2*>(blk);
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        const int i = lane + 32 * it, row = i / 9, j = i - 9 * row;
+        if (open_mask >> row & 1u) dst[9 * __popc(open_mask & ((1u << row) - 1u)) + j] = src[i];
+      }
+    }
+    // Hll, b_l: the owner adds its landmark's terms of this chunk in ascending edge order
+    if (owner) {
+      const int a = max(own_a, e0), b = min(own_b, e0 + 32);
+      for (int q = a; q < b; ++q) {
+        const double* t = hb + (q - e0) * 12;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] += t[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) bl[i] += t[9 + i];
+      }
+    }
+    __syncwarp();   // the staging buffers are reused by the next chunk; orders the global Hpl stores for later duplicates
+  }
+  if (owner) {
+    const int l = own_l;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Hll[9ll * l + i] = H[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b_l[3ll * l + i] = bl[i];
+  }
+}
+
 // one CTA per free camera: Hpp(i,i) and b_i as an ordered tree-sum over the camera's observations
 template <int MODEL>
 __global__ void __launch_bounds__(128)

@@ -676,6 +676,25 @@ int build_structure_impl(b200_ctx* c) {
     c->d_e_flag.upload(e_first, s);
     c->d_meas.upload(meas, s); c->d_info.upload(info, s);
     c->n_edges_free_lm = lm_eptr[nl];
+    {
+      // packets of the lane-per-observation linearisation (kernels.cuh: ba_linearize_packets_kernel): consecutive ranks
+      // with at most 32 observations (and at most 32 landmarks) in total; a landmark with more is a packet of its own
+      std::vector<int> pk{0};
+      int cur_e = 0, cur_n = 0;
+      for (int i = 0; i < nl; ++i) {
+        const int k2 = lm_eptr[i + 1] - lm_eptr[i];
+        if (cur_n > 0 && (cur_e + k2 > 32 || cur_n + 1 > 32)) { pk.push_back(i); cur_e = 0; cur_n = 0; }
+        cur_e += k2; ++cur_n;
+        if (k2 > 32) { pk.push_back(i + 1); cur_e = 0; cur_n = 0; }
+      }
+      if (cur_n > 0) pk.push_back(nl);
+      c->n_lin_packets = (int)pk.size() - 1;
+      std::vector<int> pk4((size_t)c->n_lin_packets * 4);   // {first rank, #ranks, first edge, end edge}
+      for (int q = 0; q < c->n_lin_packets; ++q) {
+        pk4[4 * q] = pk[q]; pk4[4 * q + 1] = pk[q + 1] - pk[q]; pk4[4 * q + 2] = lm_eptr[pk[q]]; pk4[4 * q + 3] = lm_eptr[pk[q + 1]];
+      }
+      c->d_pk_rank0.upload(pk4, s);
+    }
     c->d_partials2.alloc((size_t)ceil_div(std::max(nl, 1), 128) + 8);
     c->d_lm_eptr.upload(lm_eptr, s); c->d_lm_order.upload(lm_order, s); c->d_cam_eptr.upload(cam_eptr, s); c->d_cam_eidx.upload(cam_eidx, s);
     c->d_hpp_diag_block.upload(c->hpp_diag_block, s);
@@ -791,15 +810,28 @@ int enqueue_build_system(b200_ctx* c) {
     c->lc.n += 3;
   } else {
     double* b_p_stage = c->d_Hpp.p + (size_t)np * 36;
+    // the per-camera pass reads the same estimates and writes disjoint outputs: it runs on the side stream beside the
+    // per-landmark pass (event fork / join; per-phase profiling keeps the serial order so that its intervals stay meaningful)
+    const bool fork = c->overlap_linearize && !c->prof.on && c->nl > 0 && c->stream2;
+    cudaStream_t sc = fork ? c->stream2 : s;
+    if (fork) {
+      B200_CUDA(cudaEventRecord(c->ev_fork, s));
+      B200_CUDA(cudaStreamWaitEvent(sc, c->ev_fork, 0));
+    }
     if (c->nl > 0) {
       PhaseTimer pt(c, PH_LINEARIZE);
-      BA_MODEL_LAUNCH(c, ba_linearize_points_kernel, <<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP));
+      if (c->lin_packets) BA_MODEL_LAUNCH(c, ba_linearize_packets_kernel, <<<ceil_div(c->n_lin_packets, k::kLinWarps), 32 * k::kLinWarps, 0, s>>>(c->n_lin_packets, reinterpret_cast<const int4*>(c->d_pk_rank0.p), c->d_lm_eptr.p, c->d_lm_order.p, c->d_ev0.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP));
+      else BA_MODEL_LAUNCH(c, ba_linearize_points_kernel, <<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP));
       c->lc.n++;
     }
     { PhaseTimer pt(c, PH_LINEARIZE_CAMS);
-    BA_MODEL_LAUNCH(c, ba_linearize_cams_kernel, <<<np, 128, 0, s>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage)); }
+    BA_MODEL_LAUNCH(c, ba_linearize_cams_kernel, <<<np, 128, 0, sc>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage)); }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
+    if (fork) {
+      B200_CUDA(cudaEventRecord(c->ev_join, sc));
+      B200_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    }
     // sharded: Hpp and b_p stay this rank's PARTIAL sums (its own observations); they enter the reduced system through
     // schur_finish_kernel and are summed by the one all-reduce of [Hschur | bschur] (enqueue_solve)
     B200_CUDA(cudaMemcpyAsync(c->d_b.p, b_p_stage, (size_t)c->sizeP * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -1126,6 +1158,11 @@ int b200_create(int device, b200_ctx** out) {
   try {
     B200_CUDA(cudaSetDevice(device));
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (const char* e2 = getenv("G2O_B200_OVERLAP")) c->overlap_linearize = atoi(e2) != 0;
+    if (const char* e2 = getenv("G2O_B200_LIN_PACKETS")) c->lin_packets = atoi(e2) != 0;   // 0: the thread-per-landmark kernel
     B200_CUDA(cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(double)));
     B200_CUDA(cudaMallocHost((void**)&c->h_status, sizeof(int)));
   } catch (const CudaError& err) {
@@ -1147,8 +1184,11 @@ void b200_destroy(b200_ctx* c) {
   c->nccl.destroy();
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_status) cudaFreeHost(c->h_status);
-  cudaStream_t s = c->stream;
+  cudaStream_t s = c->stream, s2 = c->stream2;
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
+  if (s2) cudaStreamDestroy(s2);
   if (s) cudaStreamDestroy(s);
 }
 

@@ -19,6 +19,14 @@ struct b200_ctx {
   int device = 0;
   bool host_only = false;  // created with device -1: structure phase only, no compute
   cudaStream_t stream = nullptr;
+  // side stream of the linearisation: the per-camera pass (Hpp, b_p) runs beside the per-landmark pass (Hll, Hpl, b_l) -
+  // forked from and joined back into `stream` with two events, inside the captured graph as well
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_linearize = false;   // measured: no gain (the per-landmark pass fills every SM's register file), kept for experiments (G2O_B200_OVERLAP=1)
+  bool lin_packets = true;   // BA linearisation with one lane per observation (ba_linearize_packets_kernel)
+  int n_lin_packets = 0;
+  g2o_b200::DevBuf<int> d_pk_rank0;
   std::string err;
   g2o_b200::LaunchCounter lc;
 

@@ -231,20 +231,21 @@ def _interleaved_ids(n_poses, n_lm):
 
 
 def landmark_slam_2d(n_poses=120, n_landmarks=60, seed=32, max_range=6.0, sigma_odo=(0.02, 0.02, 0.01), sigma_obs=0.05,
-                     odometry=True):
+                     odometry=True, growth=0.0):
     """2D landmark SLAM: a robot drives laps on a slowly drifting circle, odometry EdgeSE2 between consecutive poses
     (+ one loop closure per lap) and EdgeSE2PointXY sightings of the landmarks in range (types/slam2d/edge_se2_pointxy.h).
-    Initial guess: integrated odometry; landmarks from their first sighting."""
+    Initial guess: integrated odometry; landmarks from their first sighting.  growth > 0: the circle widens by that much
+    per pose (a spiral: the robot explores, every landmark is seen from a bounded number of poses)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     k = np.arange(n_poses)
     per_lap = 40
     ang = 2 * np.pi * k / per_lap
-    rad = 8.0 + 0.5 * np.sin(0.37 * k)
+    rad = 8.0 + 0.5 * np.sin(0.37 * k) + growth * k
     x, y = rad * np.cos(ang), rad * np.sin(ang)
     th = ang + np.pi / 2 + 0.1 * np.sin(0.61 * k)
     th = (th + np.pi) % (2 * np.pi) - np.pi
     la = rng.uniform(0, 2 * np.pi, n_landmarks)
-    lr = rng.uniform(3.0, 13.0, n_landmarks)
+    lr = rng.uniform(3.0, 13.0, n_landmarks) if growth == 0 else np.sqrt(rng.uniform(0.0, 1.0, n_landmarks)) * (rad.max() + 5.0)
     lm = np.stack([lr * np.cos(la), lr * np.sin(la)], axis=1)
 
     def rel(i, j):  # x_i^-1 * x_j

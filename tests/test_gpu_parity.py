@@ -177,9 +177,12 @@ def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points():
     extra_v1 = np.tile(p["cam_ids"], 3).astype(np.int32)
     extra_uv = rng.normal(0, 30.0, (len(extra_v0), 2))
     dup = np.arange(40)
-    p["edge_v0"] = np.concatenate([p["edge_v0"], extra_v0, p["edge_v0"][dup]]).astype(np.int32)
-    p["edge_v1"] = np.concatenate([p["edge_v1"], extra_v1, p["edge_v1"][dup]]).astype(np.int32)
-    p["edge_payload"] = np.concatenate([p["edge_payload"], extra_uv, p["edge_payload"][dup] + 0.5])
+    # ... and second observations of a wide point by cameras 24..39: the lane-per-observation linearisation walks such a
+    # landmark in chunks of 32 observations, some of these duplicates open in one chunk and repeat in the next
+    wdup = np.arange(24, 40)
+    p["edge_v0"] = np.concatenate([p["edge_v0"], extra_v0, p["edge_v0"][dup], extra_v0[wdup]]).astype(np.int32)
+    p["edge_v1"] = np.concatenate([p["edge_v1"], extra_v1, p["edge_v1"][dup], extra_v1[wdup]]).astype(np.int32)
+    p["edge_payload"] = np.concatenate([p["edge_payload"], extra_uv, p["edge_payload"][dup] + 0.5, extra_uv[wdup] - 0.7])
     opt = g.SparseOptimizer(device=0)
     opt.set_algorithm("lm_fix6_3")
     o = Oracle()
