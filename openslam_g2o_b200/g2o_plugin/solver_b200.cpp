@@ -1,4 +1,4 @@
-// solver_b200.cpp - g2o plugin "libg2o_solver_b200.so": registers {gn,lm}_{fix3_2,fix6_3}_b200 with g2o's
+// solver_b200.cpp - g2o plugin "libg2o_solver_b200.so": registers {gn,lm}_{fix3_2,fix6_3,var}_b200 with g2o's
 // OptimizationAlgorithmFactory (g2o/core/optimization_algorithm_factory.h:153-162), same naming scheme as
 // g2o/solvers/cholmod/solver_cholmod.cpp:41-132 (+ suffix _b200s: Level 2, _b200ls: Level 1).  The `g2o` binary picks it up through its *_solver_*.so glob
 // (apps/g2o_cli/g2o_common.cpp:82,133-167); programmatic users `new OptimizationAlgorithmB200(...)` directly.
@@ -29,8 +29,13 @@
 #include "g2o/types/sba/types_sba.h"
 #include "g2o/types/sba/types_six_dof_expmap.h"
 #include "g2o/types/slam2d/edge_se2.h"
+#include "g2o/types/slam2d/edge_se2_pointxy.h"
+#include "g2o/types/slam2d/vertex_point_xy.h"
 #include "g2o/types/slam2d/vertex_se2.h"
 #include "g2o/types/slam3d/edge_se3.h"
+#include "g2o/types/slam3d/edge_se3_pointxyz.h"
+#include "g2o/types/slam3d/parameter_se3_offset.h"
+#include "g2o/types/slam3d/vertex_pointxyz.h"
 #include "g2o/types/slam3d/vertex_se3.h"
 #include "g2o_b200.h"
 #include "linear_solver_b200.h"
@@ -38,6 +43,7 @@
 namespace g2o {
 
 // estimate of one vertex in the C-ABI layout (include/g2o_b200.h); returns its B200_VERTEX_* kind, -1 if unsupported
+static int estimateLength(int kind) { return (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : kind == B200_VERTEX_XY ? 2 : 12; }
 static int packEstimate(OptimizableGraph::Vertex* v, double* e) {
   int kind = -1;
   if (VertexSE2* p = dynamic_cast<VertexSE2*>(v)) {
@@ -61,6 +67,12 @@ static int packEstimate(OptimizableGraph::Vertex* v, double* e) {
   } else if (VertexSBAPointXYZ* p = dynamic_cast<VertexSBAPointXYZ*>(v)) {
     kind = B200_VERTEX_XYZ;
     Eigen::Map<Eigen::Vector3d>(e) = p->estimate();
+  } else if (VertexPointXYZ* p = dynamic_cast<VertexPointXYZ*>(v)) {  // landmark SLAM in 3D: same state, same update
+    kind = B200_VERTEX_XYZ;
+    Eigen::Map<Eigen::Vector3d>(e) = p->estimate();
+  } else if (VertexPointXY* p = dynamic_cast<VertexPointXY*>(v)) {
+    kind = B200_VERTEX_XY;
+    e[0] = p->estimate()[0]; e[1] = p->estimate()[1];
   }
   return kind;
 }
@@ -86,7 +98,7 @@ struct B200GraphBinding {
         std::cerr << "OptimizationAlgorithmB200: unsupported vertex type (id " << v->id() << ")" << std::endl;
         return false;
       }
-      const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
+      const int ne = estimateLength(kind);
       _slot[v] = static_cast<int>(hidx[kind].size());
       _verts[kind].push_back(v);
       est[kind].insert(est[kind].end(), e, e + ne);
@@ -96,6 +108,11 @@ struct B200GraphBinding {
     _hasLandmarks = !hidx[B200_VERTEX_XYZ].empty();
     std::vector<int32_t> vi, vj;
     std::vector<double> meas, info;
+    // landmark SLAM: the pose-landmark edges form a second edge set beside the pose-pose edges (g2o_b200.h)
+    std::vector<int32_t> lvi, lvj;
+    std::vector<double> lmeas, linfo;
+    int lkind = -1;
+    const ParameterSE3Offset* sensorOffset = 0;
     int ekind = -1;
     int robustKind = B200_ROBUST_NONE;
     double robustDelta = 1.0;
@@ -134,7 +151,23 @@ struct B200GraphBinding {
         }
         for (int i = 0; i < 5; ++i) row[7 + i] = want[i];
       }
-      if (kind < 0 || (ekind >= 0 && kind != ekind)) {
+      else if (EdgeSE2PointXY* p = dynamic_cast<EdgeSE2PointXY*>(e)) {
+        kind = B200_EDGE_SE2_XY;
+        lmeas.insert(lmeas.end(), p->measurement().data(), p->measurement().data() + 2);
+        linfo.insert(linfo.end(), p->information().data(), p->information().data() + 4);
+      } else if (EdgeSE3PointXYZ* p = dynamic_cast<EdgeSE3PointXYZ*>(e)) {
+        kind = B200_EDGE_SE3_XYZ;
+        lmeas.insert(lmeas.end(), p->measurement().data(), p->measurement().data() + 3);
+        linfo.insert(linfo.end(), p->information().data(), p->information().data() + 9);
+        const ParameterSE3Offset* off = static_cast<const ParameterSE3Offset*>(p->parameter(0));
+        if (sensorOffset && !sensorOffset->offset().isApprox(off->offset(), 0.)) {
+          std::cerr << "OptimizationAlgorithmB200: EdgeSE3PointXYZ edges with different ParameterSE3Offset values" << std::endl;
+          return false;
+        }
+        sensorOffset = off;
+      }
+      const bool landmarkEdge = kind == B200_EDGE_SE2_XY || kind == B200_EDGE_SE3_XYZ;
+      if (kind < 0 || (!landmarkEdge && ekind >= 0 && kind != ekind) || (landmarkEdge && lkind >= 0 && kind != lkind)) {
         std::cerr << "OptimizationAlgorithmB200: unsupported / mixed edge types" << std::endl;
         return false;
       }
@@ -155,15 +188,32 @@ struct B200GraphBinding {
         return false;
       }
       robustKind = rk; robustDelta = rkDelta;
+      if (landmarkEdge) {
+        lkind = kind;
+        lvi.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(0))]);
+        lvj.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(1))]);
+        continue;
+      }
       ekind = kind;
       vi.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(0))]);
       vj.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(1))]);
     }
-    if (vi.empty()) return false;
+    if (vi.empty() && lvi.empty()) return false;
+    if (lkind >= 0 && ekind < 0) ekind = lkind == B200_EDGE_SE2_XY ? B200_EDGE_SE2 : B200_EDGE_SE3;  // no odometry at all
+    if (sensorOffset) {
+      double iso[12];
+      Eigen::Map<Eigen::Matrix3d>(iso) = sensorOffset->offset().linear();
+      Eigen::Map<Eigen::Vector3d>(iso + 9) = sensorOffset->offset().translation();
+      if (b200_set_sensor_offset(_ctx, iso) != B200_OK) return false;
+    }
     for (int k = 0; k < B200_NUM_VERTEX_KINDS; ++k)
       if (!hidx[k].empty() && b200_set_vertices(_ctx, k, static_cast<int>(hidx[k].size()), &est[k][0], &hidx[k][0], &marg[k][0]) != B200_OK)
         return false;
-    if (b200_set_edges(_ctx, ekind, static_cast<int>(vi.size()), &vi[0], &vj[0], &meas[0], &info[0]) != B200_OK) return false;
+    if (b200_set_edges(_ctx, ekind, static_cast<int>(vi.size()), vi.empty() ? 0 : &vi[0], vi.empty() ? 0 : &vj[0], vi.empty() ? 0 : &meas[0],
+                       vi.empty() ? 0 : &info[0]) != B200_OK) return false;
+    // the pose-landmark set (n = 0 forgets the set of a previous graph)
+    if (b200_set_edges(_ctx, lkind >= 0 ? lkind : B200_EDGE_SE2_XY, static_cast<int>(lvi.size()), lvi.empty() ? 0 : &lvi[0], lvi.empty() ? 0 : &lvj[0],
+                       lvi.empty() ? 0 : &lmeas[0], lvi.empty() ? 0 : &linfo[0]) != B200_OK) return false;
     if (b200_set_robust_kernel(_ctx, robustKind, robustDelta) != B200_OK) return false;
     int rc = b200_build_structure(_ctx);
     if (rc != B200_OK) std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
@@ -176,14 +226,17 @@ struct B200GraphBinding {
     for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
       const std::vector<OptimizableGraph::Vertex*>& vs = _verts[kind];
       if (vs.empty()) continue;
-      const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
+      const int ne = estimateLength(kind);
       buf.resize(vs.size() * ne);
       if (b200_get_estimates(_ctx, kind, &buf[0]) != B200_OK) continue;
       for (size_t i = 0; i < vs.size(); ++i) {
         const double* e = &buf[i * ne];
         if (vs[i]->fixed()) continue;
         if (kind == B200_VERTEX_SE2) static_cast<VertexSE2*>(vs[i])->setEstimate(SE2(e[0], e[1], e[2]));
-        else if (kind == B200_VERTEX_XYZ) static_cast<VertexSBAPointXYZ*>(vs[i])->setEstimate(Eigen::Vector3d(e[0], e[1], e[2]));
+        else if (kind == B200_VERTEX_XYZ) {
+          if (VertexSBAPointXYZ* q = dynamic_cast<VertexSBAPointXYZ*>(vs[i])) q->setEstimate(Eigen::Vector3d(e[0], e[1], e[2]));
+          else static_cast<VertexPointXYZ*>(vs[i])->setEstimate(Eigen::Vector3d(e[0], e[1], e[2]));
+        } else if (kind == B200_VERTEX_XY) static_cast<VertexPointXY*>(vs[i])->setEstimate(Eigen::Vector2d(e[0], e[1]));
         else if (kind == B200_VERTEX_SE3) {
           Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
           T.linear() = Eigen::Map<const Eigen::Matrix3d>(e);
@@ -208,7 +261,7 @@ struct B200GraphBinding {
     for (int kind = 0; kind < B200_NUM_VERTEX_KINDS; ++kind) {
       const std::vector<OptimizableGraph::Vertex*>& vs = _verts[kind];
       if (vs.empty()) continue;
-      const int ne = (kind == B200_VERTEX_SE2 || kind == B200_VERTEX_XYZ) ? 3 : 12;
+      const int ne = estimateLength(kind);
       const int keep = kind == B200_VERTEX_SE3_EXPMAP ? 7 : ne;  // expmap rows keep the intrinsics found at ingest
       for (size_t i = 0; i < vs.size(); ++i) {
         double e[12];
@@ -414,7 +467,7 @@ class SolverB200 : public Solver {
 static OptimizationAlgorithm* createSolverB200(const std::string& fullSolverName) {
   const std::string method = fullSolverName.substr(0, 2);
   const std::string rest = fullSolverName.substr(3);
-  if (rest == "fix3_2_b200" || rest == "fix6_3_b200")  // Level 3: whole iteration on the GPU
+  if (rest == "fix3_2_b200" || rest == "fix6_3_b200" || rest == "var_b200")  // Level 3: whole iteration on the GPU
     return new OptimizationAlgorithmB200(method == "gn" ? B200_GAUSS_NEWTON : B200_LEVENBERG);
   // Level 2: stock LM/GN control, errors and update on the host; system, Schur complement and Cholesky on the GPU
   // Level 1: stock BlockSolver + LM/GN on the host, only the linear solver on the GPU
@@ -444,6 +497,11 @@ B200_REGISTER(gn_fix3_2_b200, "Gauss-Newton: device-resident solver on B200 (fix
 B200_REGISTER(gn_fix6_3_b200, "Gauss-Newton: device-resident solver on B200 (fixed blocksize)", 6, 3);
 B200_REGISTER(lm_fix3_2_b200, "Levenberg: device-resident solver on B200 (fixed blocksize)", 3, 2);
 B200_REGISTER(lm_fix6_3_b200, "Levenberg: device-resident solver on B200 (fixed blocksize)", 6, 3);
+// variable block sizes (requiresMarginalize = false, like gn_var / lm_var of solvers/csparse/solver_csparse.cpp:53-55,102,108):
+// pose graphs and landmark SLAM (SE2 + XY, SE3 + TRACKXYZ) with every vertex in one system - Level 3 only (the padded
+// landmark blocks of the C-ABI do not map onto a host-side SparseBlockMatrix<MatrixXd>)
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_var_b200, new B200SolverCreator(OptimizationAlgorithmProperty("gn_var_b200", "Gauss-Newton: device-resident solver on B200 (variable blocksize)", "B200", false, Eigen::Dynamic, Eigen::Dynamic)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_var_b200, new B200SolverCreator(OptimizationAlgorithmProperty("lm_var_b200", "Levenberg: device-resident solver on B200 (variable blocksize)", "B200", false, Eigen::Dynamic, Eigen::Dynamic)));
 B200_REGISTER(gn_fix3_2_b200s, "Gauss-Newton: B200 solver (system, Schur, Cholesky) under the stock algorithm", 3, 2);
 B200_REGISTER(gn_fix6_3_b200s, "Gauss-Newton: B200 solver (system, Schur, Cholesky) under the stock algorithm", 6, 3);
 B200_REGISTER(lm_fix3_2_b200s, "Levenberg: B200 solver (system, Schur, Cholesky) under the stock algorithm", 3, 2);
