@@ -762,7 +762,7 @@ constexpr int kSrPartial = 42;    // 36 block entries + 6 right-hand-side entrie
 constexpr int kSrMaxDynSmem = 226 * 1024;  // opt-in dynamic shared memory of schur_range_kernel (device maximum)
 
 struct SchurRanges {
-  const int* slot0;    // nr+1: first Hpl slot of a range
+  const int* slot0;    // 2 nr: [first Hpl slot, end slot) of a range (a wide landmark may sit between two ranges)
   const int* lm_ptr;   // nr+1: into lm_ids / lm_slot
   const int* lm_ids;   // landmark (Wu index) of every landmark of the range
   const int* lm_slot;  // first Hpl slot of that landmark, relative to the range (+ one end entry per range)
@@ -788,7 +788,7 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
   unsigned short* sLm = sL + R.cap_contrib;              // landmark (range-local) of every slot
   __shared__ __align__(8) unsigned long long sr_bar;
   const int r = blockIdx.x, tid = threadIdx.x;
-  const int s0 = R.slot0[r], ns = R.slot0[r + 1] - s0;
+  const int s0 = R.slot0[2 * r], ns = R.slot0[2 * r + 1] - s0;
   const int l0 = R.lm_ptr[r], nlm = R.lm_ptr[r + 1] - l0;
   const int g0 = R.seg_ptr[r], g1 = R.seg_ptr[r + 1];
   // descriptor of this group's first segment: fetched while the staging copies are in flight
@@ -939,6 +939,69 @@ schur_range_kernel(SchurRanges R, const double* __restrict__ Hpl, const double* 
         if ((k & 3) == sub) out[36 + k] = v;
       }
     }
+  }
+}
+
+// Landmarks seen by more cameras than one range CTA can stage (k > 1400: 200 KB of Hpl blocks) take this path instead of
+// being refused (round 1): one THREAD per camera pair (a <= b) of the landmark computes (Hpl_a W)(Hpl_b W)^T (+ the
+// right-hand-side term on the diagonal pairs) straight from global memory - the k blocks of such a landmark (k * 144
+// bytes) stay in L2 - and leaves it as a segment of its own for schur_finish_kernel.  Pairs are enumerated like the
+// range plan does (a ascending, b = a .. k-1), so segment = seg0 + pair index.
+struct SchurWide {
+  int n;                       // wide landmarks
+  const long long* pair0;      // n+1: first pair of every wide landmark
+  const int* lm;               // landmark (Wu index)
+  const int* slot0;            // its first Hpl slot
+  const int* deg;              // its number of slots k
+  const long long* seg0;       // its first segment
+};
+__global__ void __launch_bounds__(128)
+schur_wide_kernel(SchurWide Wd, long long npairs, const double* __restrict__ Hpl, const double* __restrict__ Wu,
+                  double* __restrict__ partial) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  int w = 0;
+  while (w + 1 < Wd.n && Wd.pair0[w + 1] <= p) ++w;   // a handful of wide landmarks at most
+  const long long q = p - Wd.pair0[w];
+  const int k = Wd.deg[w];
+  // invert q = a*k - a*(a-1)/2 + (b - a): largest a with a*k - a*(a-1)/2 <= q
+  int a = (int)(((2.0 * k + 1.0) - sqrt((2.0 * k + 1.0) * (2.0 * k + 1.0) - 8.0 * (double)q)) * 0.5);
+  a = max(0, min(a, k - 1));
+  while (a > 0 && (long long)a * k - (long long)a * (a - 1) / 2 > q) --a;
+  while (a + 1 < k && (long long)(a + 1) * k - (long long)(a + 1) * a / 2 <= q) ++a;
+  const int b = a + (int)(q - ((long long)a * k - (long long)a * (a - 1) / 2));
+  const double* wl = Wu + kDinvStride * (long long)Wd.lm[w];
+  const double w00 = wl[0], w01 = wl[1], w02 = wl[2], w11 = wl[3], w12 = wl[4], w22 = wl[5];
+  double A[18], B[18];
+  {
+    const double2* A2 = reinterpret_cast<const double2*>(Hpl + 18ll * (Wd.slot0[w] + a));
+    const double2* B2 = reinterpret_cast<const double2*>(Hpl + 18ll * (Wd.slot0[w] + b));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const double2 v = A2[i]; A[2 * i] = v.x; A[2 * i + 1] = v.y; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const double2 v = B2[i]; B[2 * i] = v.x; B[2 * i + 1] = v.y; }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {   // the same transform schur_range_kernel applies in place: X <- X W
+    double a0 = A[i], a1 = A[i + 6], a2 = A[i + 12];
+    A[i] = a0 * w00; A[i + 6] = fma(a0, w01, a1 * w11); A[i + 12] = fma(a0, w02, fma(a1, w12, a2 * w22));
+    a0 = B[i]; a1 = B[i + 6]; a2 = B[i + 12];
+    B[i] = a0 * w00; B[i + 6] = fma(a0, w01, a1 * w11); B[i + 12] = fma(a0, w02, fma(a1, w12, a2 * w22));
+  }
+  double* out = partial + (Wd.seg0[w] + q) * kSrPartial;
+#pragma unroll
+  for (int c2 = 0; c2 < 6; ++c2)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v = fma(A[r + 6 * j], B[c2 + 6 * j], v);
+      out[r + 6 * c2] = v;
+    }
+  if (a == b) {
+    const double u0 = wl[6], u1 = wl[7], u2 = wl[8];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) out[36 + r] = A[r] * u0 + A[r + 6] * u1 + A[r + 12] * u2;
   }
 }
 

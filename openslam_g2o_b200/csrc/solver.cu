@@ -542,8 +542,12 @@ int build_structure_impl(b200_ctx* c) {
     };
   STAMP("Hschur pattern");
     // ---- Schur plan (kernels.cuh: schur_range_kernel / schur_finish_kernel)
-    std::vector<int> pi;  // ranks with at least one slot
-    for (int i = 0; i < nl; ++i) if (lm_s0[i + 1] > lm_s0[i]) pi.push_back(i);
+    // landmarks seen by more cameras than a range CTA can stage go through schur_wide_kernel (one thread per camera pair)
+    int wide_thr = 1400;
+    if (const char* e = getenv("G2O_B200_SR_WIDE")) wide_thr = std::max(1, std::min(1400, atoi(e)));   // tests: force the wide path
+    std::vector<int> pi, wide;  // ranks with at least one slot: range landmarks / wide landmarks
+    for (int i = 0; i < nl; ++i)
+      if (lm_s0[i + 1] > lm_s0[i]) (lm_s0[i + 1] - lm_s0[i] > wide_thr ? wide : pi).push_back(i);
     {
       // SparseBlockMatrix (landmark-major, ascending camera) position -> slot, for the exported Hpl pattern
       c->hpl_export.resize(nslot);
@@ -558,21 +562,22 @@ int build_structure_impl(b200_ctx* c) {
       int kmax = 0;
       for (int l : pi) kmax = std::max(kmax, lm_s0[l + 1] - lm_s0[l]);
       const int cap_slots = std::max(352, kmax), cap_lms = 160, cap_contrib = 1536;
-      if (kmax > 1400) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 1400 cameras");
       // (1) range boundaries: a cheap sequential pass - a range closes when the next landmark would exceed the slot,
       //     landmark or contribution budget of one CTA
       std::vector<int> rg_first{0};  // index into pi of the first landmark of each range
       std::vector<long long> rg_contrib;
       long long npairs = 0;
       {
-        int cur_slots = 0, cur_lms = 0;
+        int cur_slots = 0, cur_lms = 0, prev_end = -1;
         long long cur_contrib = 0;
         for (size_t j = 0; j < pi.size(); ++j) {
           const int l = pi[j], k2 = lm_s0[l + 1] - lm_s0[l];
-          if (k2 > 65535) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 65535 cameras");
           const long long pairs = (long long)k2 * (k2 + 1) / 2;
           npairs += pairs;
-          if (cur_lms > 0 && (cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || cur_contrib + pairs > cap_contrib)) {
+          // a range is ONE contiguous run of Hpl slots: a wide landmark between two range landmarks closes the range
+          const bool gap = lm_s0[l] != prev_end;
+          prev_end = lm_s0[l + 1];
+          if (cur_lms > 0 && (gap || cur_slots + k2 > cap_slots || cur_lms + 1 > cap_lms || cur_contrib + pairs > cap_contrib)) {
             rg_first.push_back((int)j); rg_contrib.push_back(cur_contrib);
             cur_slots = 0; cur_lms = 0; cur_contrib = 0;
           }
@@ -582,10 +587,11 @@ int build_structure_impl(b200_ctx* c) {
       }
       const int nr = (int)rg_first.size() - 1;
       // (2) everything whose position follows from the boundaries
-      std::vector<int> r_slot0(nr + 1, 0), r_lm_ptr(nr + 1, 0), r_lm_ids(pi.size()), r_lm_slot(pi.size() + nr), r_seg_ptr(nr + 1, 0);
+      std::vector<int> r_slot0(2 * (size_t)nr + 2, 0), r_lm_ptr(nr + 1, 0), r_lm_ids(pi.size()), r_lm_slot(pi.size() + nr), r_seg_ptr(nr + 1, 0);
       std::vector<long long> sc_off(nr + 1, 0);  // contributions of a range start 16-byte aligned (bulk copies)
       for (int r = 0; r < nr; ++r) {
-        r_slot0[r + 1] = lm_s0[pi[rg_first[r + 1] - 1] + 1];
+        r_slot0[2 * r] = lm_s0[pi[rg_first[r]]];                  // [first slot, end slot) of the range
+        r_slot0[2 * r + 1] = lm_s0[pi[rg_first[r + 1] - 1] + 1];
         r_lm_ptr[r + 1] = rg_first[r + 1];
         sc_off[r + 1] = sc_off[r] + ((rg_contrib[r] + 7) & ~7ll);
       }
@@ -603,7 +609,7 @@ int build_structure_impl(b200_ctx* c) {
         std::vector<int> pair_t;
         bool have_pairs = false;  // pair_t holds the block indices of the previous landmark's camera list
         for (size_t r = rb; r < re; ++r) {
-          const int slot0 = r_slot0[r];
+          const int slot0 = r_slot0[2 * r];
           rc.clear();
           for (int j = rg_first[r]; j < rg_first[r + 1]; ++j) {
             const int l = pi[j], k2 = lm_s0[l + 1] - lm_s0[l], slot = lm_s0[l];
@@ -620,7 +626,7 @@ int build_structure_impl(b200_ctx* c) {
             r_lm_ids[j] = lm_order[l];
             r_lm_slot[j + r] = base;
           }
-          r_lm_slot[rg_first[r + 1] + r] = r_slot0[r + 1] - slot0;  // end entry of the range
+          r_lm_slot[rg_first[r + 1] + r] = r_slot0[2 * r + 1] - slot0;  // end entry of the range
           std::stable_sort(rc.begin(), rc.end(), [](const Contrib& x, const Contrib& y) { return x.t < y.t; });
           size_t pos = (size_t)sc_off[r];
           int nseg_r = 0;
@@ -645,7 +651,26 @@ int build_structure_impl(b200_ctx* c) {
         seg_cb.insert(seg_cb.end(), o.seg_cb.begin(), o.seg_cb.end());
         seg_ce.insert(seg_ce.end(), o.seg_ce.begin(), o.seg_ce.end());
       }
+      const int nseg_ranges = (int)seg_t.size();
+      // wide landmarks: one segment per camera pair, numbered behind the segments of the ranges
+      std::vector<long long> w_pair0{0}, w_seg0;
+      std::vector<int> w_lm, w_slot0, w_deg;
+      for (int l : wide) {
+        const int k2 = lm_s0[l + 1] - lm_s0[l], slot = lm_s0[l];
+        if (k2 > 65535) return fail(c, B200_ERR_UNSUPPORTED, "a landmark observed by more than 65535 cameras");
+        const long long pairs = (long long)k2 * (k2 + 1) / 2;
+        if ((long long)seg_t.size() + pairs > 0x7fffffffll) return fail(c, B200_ERR_UNSUPPORTED, "more than 2^31 Schur segments on one GPU: shard the landmarks");
+        npairs += pairs;
+        w_lm.push_back(lm_order[l]); w_slot0.push_back(slot); w_deg.push_back(k2);
+        w_seg0.push_back((long long)seg_t.size()); w_pair0.push_back(w_pair0.back() + pairs);
+        for (int a = 0; a < k2; ++a)
+          for (int b2 = a; b2 < k2; ++b2) seg_t.push_back(find_t(c->hpl_row[slot + a], c->hpl_row[slot + b2]));
+      }
+      c->sr_nwide = (int)wide.size(); c->sr_wide_pairs = w_pair0.back();
+      c->d_sw_pair0.upload(w_pair0, s); c->d_sw_seg0.upload(w_seg0, s);
+      c->d_sw_lm.upload(w_lm, s); c->d_sw_slot0.upload(w_slot0, s); c->d_sw_deg.upload(w_deg, s);
       const int nseg = (int)seg_t.size();
+      (void)nseg_ranges;
       // per block: its segments in ascending order (= fixed summation order of the finish kernel)
       std::vector<int> tseg_ptr(nT + 1, 0), tseg_idx(nseg);
       for (int sg = 0; sg < nseg; ++sg) tseg_ptr[seg_t[sg] + 1]++;
@@ -905,6 +930,11 @@ int enqueue_solve(b200_ctx* c, bool skip_backsub = false) {
         k::SchurRanges R{c->d_sr_slot0.p, c->d_sr_lm_ptr.p, c->d_sr_lm_ids.p, c->d_sr_lm_slot.p, c->d_sr_seg_ptr.p, c->d_sr_seg_t.p, c->d_sr_seg_cb.p, c->d_sr_seg_ce.p,
                          c->d_sr_a.p, c->d_sr_b.p, c->d_sr_l.p, c->d_t_diag.p, c->sr_cap_slots, c->sr_cap_lms, c->sr_cap_contrib};
         k::schur_range_kernel<<<c->sr_n, k::kSrThreads, schur_range_smem(c), s>>>(R, c->d_Hpl.p, c->d_Wu.p, c->d_sr_partial.p);
+        c->lc.n++;
+      }
+      if (c->sr_nwide > 0) {  // landmarks too wide for a range CTA: one thread per camera pair
+        k::SchurWide Wd{c->sr_nwide, c->d_sw_pair0.p, c->d_sw_lm.p, c->d_sw_slot0.p, c->d_sw_deg.p, c->d_sw_seg0.p};
+        k::schur_wide_kernel<<<ceil_div(c->sr_wide_pairs, 128), 128, 0, s>>>(Wd, c->sr_wide_pairs, c->d_Hpl.p, c->d_Wu.p, c->d_sr_partial.p);
         c->lc.n++;
       }
     }

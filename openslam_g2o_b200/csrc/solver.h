@@ -92,6 +92,11 @@ struct b200_ctx {
   g2o_b200::DevBuf<unsigned char> d_t_diag;
   g2o_b200::DevBuf<double> d_sr_partial;
   int sr_n = 0, sr_nseg = 0, sr_cap_slots = 0, sr_cap_lms = 0, sr_cap_contrib = 0;
+  // landmarks seen by more cameras than a range CTA can stage (schur_wide_kernel): pair / segment offsets, Wu index, slots
+  int sr_nwide = 0;
+  long long sr_wide_pairs = 0;
+  g2o_b200::DevBuf<long long> d_sw_pair0, d_sw_seg0;
+  g2o_b200::DevBuf<int> d_sw_lm, d_sw_slot0, d_sw_deg;
   long long sr_ncontrib = 0;
   g2o_b200::DevBuf<double> d_stage_est;            // dense staging for host<->device estimate copies
   // scalars: [0] chi2 [1] scale (landmark part; sharded: + pose part) [2] maxdiag [3] lambda [4] scale (pose part)

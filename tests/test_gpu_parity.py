@@ -160,13 +160,20 @@ def test_bundle_adjustment_matches_oracle(seed, cams, points):
 
 
 @needs_oracle
-def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points():
+@pytest.mark.parametrize("wide_thr", [None, 40])
+def test_bundle_adjustment_wide_landmarks_duplicates_and_fixed_points(wide_thr, monkeypatch):
     """Schur plan edge cases: landmarks seen by every camera (more Hpl slots / block products than a range's
     shared-memory budget: the range grows, the product indices are read from global memory), several observations
     of one point by the same camera (one shared Hpl block), fixed points, a second fixed camera."""
     import openslam_g2o_b200 as g
     from oracle_binding import LM, Oracle
     from openslam_g2o_b200 import synth
+    # wide_thr = 40: every landmark seen by more than 40 cameras takes the one-thread-per-camera-pair path that
+    # landmarks beyond a range CTA's capacity (1400 cameras) use (kernels.cuh: schur_wide_kernel), wedged between ranges
+    if wide_thr is None:
+        monkeypatch.delenv("G2O_B200_SR_WIDE", raising=False)
+    else:
+        monkeypatch.setenv("G2O_B200_SR_WIDE", str(wide_thr))
     rng = np.random.default_rng(21)
     cams = 600  # more Hpl slots than the default range capacity (512)
     p = dict(synth.venice_like(cams, 300, seed=21))

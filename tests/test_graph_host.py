@@ -302,3 +302,38 @@ EDGE_PROJECT_XYZ2UV:EXPMAP 3 1 9 196 263 2 0.5 3
     assert lines[0].startswith("PARAMS_CAMERAPARAMETERS 0 ") and lines[1].startswith("PARAMS_CAMERAPARAMETERS 7 650.5")
     assert sum(ln.startswith("EDGE_PROJECT_XYZ2UV:EXPMAP") for ln in lines) == 4
     assert any(ln.startswith("EDGE_PROJECT_XYZ2UV:EXPMAP 3 1 7 ") for ln in lines)
+
+
+def test_landmark_seen_by_more_cameras_than_a_range_holds_is_planned_not_refused(monkeypatch):
+    """round 1 refused a landmark observed by more than 1400 cameras (shared-memory capacity of one Schur range); now such
+    landmarks get one segment per camera pair (kernels.cuh: schur_wide_kernel) and the ranges around them stay contiguous
+    runs of Hpl slots.  Host-only structure phase: segments = those of the ranges + k (k + 1) / 2 per wide landmark"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    cams = 1500
+    p = dict(synth.venice_like(cams, 200, seed=3))
+    wide_pt = p["point_ids"][57]
+    p["edge_v0"] = np.concatenate([p["edge_v0"], np.full(cams, wide_pt)]).astype(np.int32)
+    p["edge_v1"] = np.concatenate([p["edge_v1"], p["cam_ids"]]).astype(np.int32)
+    p["edge_payload"] = np.concatenate([p["edge_payload"], np.zeros((cams, 2))])
+
+    def plan(env):
+        if env is None:
+            monkeypatch.delenv("G2O_B200_SR_WIDE", raising=False)
+        else:
+            monkeypatch.setenv("G2O_B200_SR_WIDE", str(env))
+        opt = g.SparseOptimizer(device=-1)
+        opt.set_algorithm("lm_fix6_3")
+        synth.feed(p, opt)
+        opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+        assert opt.context.build_structure()
+        info = opt.context.factor_info()
+        opt.close()
+        return info
+    info = plan(None)
+    k = cams - 1   # the gauge camera is fixed: no Hpl block for it
+    assert info["schur_segments"] >= k * (k + 1) // 2
+    # forcing every landmark with more than 3 cameras through the wide path changes the segments, not the contributions
+    a, b = plan(1400), plan(3)
+    assert a["schur_contributions"] == b["schur_contributions"] and a["hpl_slots"] == b["hpl_slots"]
+    assert b["schur_segments"] > a["schur_segments"]   # (and more, shorter ranges: a wide landmark closes the range before it)
