@@ -504,8 +504,8 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
 // edge order from the staged per-edge terms (fixed order: run-to-run bit-identical).
 constexpr int kLinWarps = 4;
 constexpr int kLinWarpDoubles = 32 * 18 + 32 * 12;   // Hpl blocks | per-edge Hll, b_l terms
-template <int MODEL>
-__global__ void __launch_bounds__(32 * kLinWarps, 4)
+template <int MODEL, int MINB>   // MINB CTAs per SM: the register budget (4: 128, 5: 96, 6: 80 registers per thread)
+__global__ void __launch_bounds__(32 * kLinWarps, MINB)
 ba_linearize_packets_kernel(int npk, const int4* __restrict__ packets, const int* __restrict__ lm_eptr,
                             const int* __restrict__ lm_order, const int* __restrict__ e_pt,
                             const int* __restrict__ e_cam, const int* __restrict__ e_hpl,
@@ -629,8 +629,8 @@ ba_linearize_packets_kernel(int npk, const int4* __restrict__ packets, const int
 }
 
 // one CTA per free camera: Hpp(i,i) and b_i as an ordered tree-sum over the camera's observations
-template <int MODEL>
-__global__ void __launch_bounds__(128)
+template <int MODEL, int MINB>   // MINB CTAs per SM the register allocation is held to
+__global__ void __launch_bounds__(128, MINB)
 ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict__ cam_eidx,
                          const int* __restrict__ pose_vertex, const int* __restrict__ e_pt,
                          const double* __restrict__ pt_est, const double* __restrict__ cam_est,

@@ -845,12 +845,21 @@ int enqueue_build_system(b200_ctx* c) {
     }
     if (c->nl > 0) {
       PhaseTimer pt(c, PH_LINEARIZE);
-      if (c->lin_packets) BA_MODEL_LAUNCH(c, ba_linearize_packets_kernel, <<<ceil_div(c->n_lin_packets, k::kLinWarps), 32 * k::kLinWarps, 0, s>>>(c->n_lin_packets, reinterpret_cast<const int4*>(c->d_pk_rank0.p), c->d_lm_eptr.p, c->d_lm_order.p, c->d_ev0.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP));
+      if (c->lin_packets) {
+#define LIN_PACKETS_LAUNCH(M, B) k::ba_linearize_packets_kernel<M, B><<<ceil_div(c->n_lin_packets, k::kLinWarps), 32 * k::kLinWarps, 0, s>>>(c->n_lin_packets, reinterpret_cast<const int4*>(c->d_pk_rank0.p), c->d_lm_eptr.p, c->d_lm_order.p, c->d_ev0.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP)
+        if (c->cam_model == 0) { if (c->lin_minb == 6) LIN_PACKETS_LAUNCH(0, 6); else if (c->lin_minb == 5) LIN_PACKETS_LAUNCH(0, 5); else LIN_PACKETS_LAUNCH(0, 4); }
+        else { if (c->lin_minb == 6) LIN_PACKETS_LAUNCH(1, 6); else if (c->lin_minb == 5) LIN_PACKETS_LAUNCH(1, 5); else LIN_PACKETS_LAUNCH(1, 4); }
+#undef LIN_PACKETS_LAUNCH
+      }
       else BA_MODEL_LAUNCH(c, ba_linearize_points_kernel, <<<ceil_div(c->nl, 128), 128, 0, s>>>(c->nl, c->d_lm_eptr.p, c->d_lm_order.p, c->d_lm_vertex.p, c->d_ev1.p, c->d_e_hpl.p, c->d_e_flag.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_Hll.p, c->d_Hpl.p, c->d_b.p + c->sizeP));
       c->lc.n++;
     }
     { PhaseTimer pt(c, PH_LINEARIZE_CAMS);
-    BA_MODEL_LAUNCH(c, ba_linearize_cams_kernel, <<<np, 128, 0, sc>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage)); }
+#define LIN_CAMS_LAUNCH(M, B) k::ba_linearize_cams_kernel<M, B><<<np, 128, 0, sc>>>(c->d_cam_eptr.p, c->d_cam_eidx.p, c->d_pose_vertex.p, c->d_ev0.p, c->d_lm_est.p, c->d_pose_est.p, c->d_cam_der.p, c->d_meas.p, c->d_info.p, E, c->robust, c->d_hpp_diag_block.p, c->d_Hpp.p, b_p_stage)
+    if (c->cam_model == 0) { if (c->cams_minb == 6) LIN_CAMS_LAUNCH(0, 6); else if (c->cams_minb == 4) LIN_CAMS_LAUNCH(0, 4); else LIN_CAMS_LAUNCH(0, 3); }
+    else { if (c->cams_minb == 6) LIN_CAMS_LAUNCH(1, 6); else if (c->cams_minb == 4) LIN_CAMS_LAUNCH(1, 4); else LIN_CAMS_LAUNCH(1, 3); }
+#undef LIN_CAMS_LAUNCH
+    }
     c->lc.n++;
     B200_CUDA(cudaGetLastError());
     if (fork) {
@@ -1193,6 +1202,8 @@ int b200_create(int device, b200_ctx** out) {
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* e2 = getenv("G2O_B200_OVERLAP")) c->overlap_linearize = atoi(e2) != 0;
     if (const char* e2 = getenv("G2O_B200_LIN_PACKETS")) c->lin_packets = atoi(e2) != 0;   // 0: the thread-per-landmark kernel
+    if (const char* e2 = getenv("G2O_B200_CAMS_MINB")) c->cams_minb = atoi(e2);            // ... and the per-camera pass (1 / 4 / 6)
+    if (const char* e2 = getenv("G2O_B200_LIN_MINB")) c->lin_minb = atoi(e2);              // CTAs per SM the packets kernel is compiled for
     B200_CUDA(cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(double)));
     B200_CUDA(cudaMallocHost((void**)&c->h_status, sizeof(int)));
   } catch (const CudaError& err) {

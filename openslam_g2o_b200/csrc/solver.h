@@ -26,6 +26,8 @@ struct b200_ctx {
   bool overlap_linearize = false;   // measured: no gain (the per-landmark pass fills every SM's register file), kept for experiments (G2O_B200_OVERLAP=1)
   bool lin_packets = true;   // BA linearisation with one lane per observation (ba_linearize_packets_kernel)
   int n_lin_packets = 0;
+  int cams_minb = 3;         // ba_linearize_cams_kernel: CTAs per SM it is compiled for (3: 168 registers, 4: 128, 6: 80)
+  int lin_minb = 4;          // register budget of that kernel: 4 / 5 / 6 CTAs per SM (128 / 96 / 80 registers)
   g2o_b200::DevBuf<int> d_pk_rank0;
   std::string err;
   g2o_b200::LaunchCounter lc;
