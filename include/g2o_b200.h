@@ -173,6 +173,16 @@ int b200_algorithm_solve(b200_ctx* ctx, int algorithm, int iteration, b200_iter_
  * become 2^k independent subtrees.  Same solution (to rounding), different elimination order; call before
  * b200_build_structure.  b200_get_block_ordering reports the ordering in use. */
 int b200_set_ordering(b200_ctx* ctx, int nd_levels);
+/* linear solver of the (reduced) pose system inside Solver::solve: the supernodal Cholesky (default; LinearSolverCSparse /
+ * LinearSolverCholmod, `*_fix*`, `*_var`) or the block-Jacobi preconditioned conjugate gradients of LinearSolverPCG
+ * (solvers/pcg/linear_solver_pcg.hpp:79-160; solver names `gn_pcg`, `lm_pcg`, `*_pcg3_2`, `*_pcg6_3`,
+ * solvers/pcg/solver_pcg.cpp) with its setTolerance (1e-6) / setAbsoluteTolerance (true) / setMaxIterations (-1: the number
+ * of rows).  Call before b200_build_structure.  PCG trials run as plain launches (the stopping rule reports to the host
+ * every 64 iterations), the Cholesky trials as CUDA-graph replays. */
+enum { B200_LINEAR_SOLVER_CHOLESKY = 0, B200_LINEAR_SOLVER_PCG = 1 };
+int b200_set_linear_solver(b200_ctx* ctx, int kind, double tolerance, int absolute_tolerance, int max_iterations);
+/* G2OBatchStatistics::iterationsLinearSolver (core/batch_stats.h:61): CG iterations of the last PCG solve (0 with the Cholesky) */
+int b200_get_linear_solver_iterations(b200_ctx* ctx);
 /* robust kernel applied to every edge, like `g2o -robustKernel NAME -robustKernelWidth W`
  * (apps/g2o_cli/g2o.cpp:322-336; kernels: core/robust_kernel_impl.cpp:65-126; use sites:
  * core/base_binary_edge.hpp:91-113 first-order weight rho' on information and omega_r,

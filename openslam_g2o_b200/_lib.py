@@ -99,6 +99,8 @@ def _load():
         "b200_get_factor_info": (i32, [vp, vp]),
         "b200_set_robust_kernel": (i32, [vp, i32, C.c_double]),
         "b200_set_ordering": (i32, [vp, i32]),
+        "b200_set_linear_solver": (i32, [vp, i32, C.c_double, i32, i32]),
+        "b200_get_linear_solver_iterations": (i32, [vp]),
         "b200_compute_marginals": (i32, [vp, i32, vp, vp, vp]),
         "b200_get_launch_count": (i64, [vp]),
         "b200_debug_upload_digest": (C.c_uint64, [i32]),

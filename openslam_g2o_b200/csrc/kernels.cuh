@@ -1146,6 +1146,17 @@ ba_backsub_update_kernel(int nl, const int* __restrict__ lm_eptr, const int* __r
   if (threadIdx.x == 0) partial_scale[blockIdx.x] = sc;
 }
 
+// A(i,i) += lambda I (+ extra: the unit diagonal of padding unknowns) on the diagonal blocks of a block matrix: what
+// Solver::setLambda does in place (block_solver.hpp:563-604), applied to the copy the PCG solver reads
+template <int D>
+__global__ void add_block_diagonal_kernel(int np, const int* __restrict__ diag_block, const double* __restrict__ lambda,
+                                          const double* __restrict__ extra, double* __restrict__ A) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= np * D) return;
+  const int i = idx / D, r = idx - i * D;
+  A[(long long)D * D * diag_block[i] + r + D * r] += *lambda + (extra ? extra[idx] : 0.0);
+}
+
 // ------------------------------------------------------------------ oplus updates
 // hidx[v] = hessian index (-1 fixed); x is indexed by colInHessian = hidx*dim (poses) / sizePoses + ... (landmarks)
 __global__ void oplus_se2_kernel(int n, const int* __restrict__ hidx, const double* __restrict__ x, double* __restrict__ est) {

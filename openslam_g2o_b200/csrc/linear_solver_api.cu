@@ -10,7 +10,7 @@
 #include "../../include/g2o_b200.h"
 #include "block_amd.h"
 #include "chol.h"
-#include "pcg.cuh"
+#include "pcg_host.h"
 
 using namespace g2o_b200;
 
@@ -23,13 +23,7 @@ struct b200_linear_solver {
   LaunchCounter lc;
   int nb = 0, d = 0, nblk = 0;
   int* h_status = nullptr;
-  // LinearSolverPCG state (pcg.cuh): symmetric block-row lists of the current pattern, vectors, _residual of the last solve
-  bool pcg_ready = false;
-  int pcg_nb = 0, pcg_d = 0, pcg_nblk = 0;
-  DevBuf<int> p_rowptr, p_ent_blk, p_ent_col, p_diag_blk, p_status;
-  DevBuf<double> p_J, p_x, p_r, p_s, p_q, p_d0, p_d1, p_partial;
-  DevBuf<PcgScalars> p_sc;
-  double pcg_residual = -1.0;
+  PcgGpu pcg;   // LinearSolverPCG state (pcg_host.h): lists of the current pattern, vectors, _residual of the last solve
 };
 
 namespace {
@@ -89,50 +83,9 @@ void b200_ls_destroy(b200_linear_solver* ls) {
 int b200_ls_init(b200_linear_solver* ls) {
   if (!ls) return B200_ERR_INVALID;
   ls->chol.reset();
-  ls->pcg_ready = false;      // LinearSolverPCG::init(): _residual = -1, _indices / _sparseMat cleared (linear_solver_pcg.h:64-71)
-  ls->pcg_residual = -1.0;
+  ls->pcg.init();             // LinearSolverPCG::init(): _residual = -1, _indices / _sparseMat cleared (linear_solver_pcg.h:64-71)
   return B200_OK;
 }
-
-}  // extern "C"
-namespace {
-template <int D>
-int pcg_run(b200_linear_solver* ls, const double* dA, const double* db, double tolerance, int absolute, int max_iter, cudaStream_t s,
-            int* iterations, double* residual) {
-  const int nb = ls->pcg_nb, n = nb * D;
-  PcgDev P{nb, ls->p_rowptr.p, ls->p_ent_blk.p, ls->p_ent_col.p, ls->p_diag_blk.p, dA, ls->p_J.p, ls->p_x.p, ls->p_r.p, ls->p_s.p,
-           ls->p_q.p, ls->p_d0.p, ls->p_d1.p, ls->p_partial.p, ls->p_sc.p};
-  const int grid = (int)ceil_div(n, kPcgThreads);
-  B200_CUDA(cudaMemsetAsync(ls->p_status.p, 0, sizeof(int), s));
-  B200_CUDA(cudaMemsetAsync(ls->p_sc.p, 0, sizeof(PcgScalars), s));
-  pcg_jacobi_kernel<D><<<(int)ceil_div(nb, 128), 128, 0, s>>>(nb, ls->p_diag_blk.p, dA, ls->p_J.p, ls->p_status.p);
-  pcg_init_kernel<D><<<grid, kPcgThreads, 0, s>>>(P, db, tolerance, absolute, ls->pcg_residual, max_iter < 0 ? n : max_iter);
-  ls->lc.n += 2;
-  PcgScalars h;
-  const int limit = max_iter < 0 ? n : max_iter;
-  for (int done_iters = 0;;) {
-    // a batch of iterations without a host round trip; after `done` the kernels return at once
-    const int batch = std::min(64, std::max(1, limit - done_iters));
-    for (int k = 0; k < batch; ++k) {
-      pcg_spmv_kernel<D><<<grid, kPcgThreads, 0, s>>>(P);
-      pcg_update_kernel<D><<<grid, kPcgThreads, 0, s>>>(P);
-    }
-    ls->lc.n += 2 * batch;
-    B200_CUDA(cudaMemcpyAsync(&h, ls->p_sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
-    B200_CUDA(cudaMemcpyAsync(ls->h_status, ls->p_status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    B200_CUDA(cudaStreamSynchronize(s));
-    if (*ls->h_status) return B200_NOT_POSITIVE_DEFINITE;   // a diagonal block that is not positive definite
-    done_iters = h.iteration;
-    if (h.done || done_iters >= limit) break;
-    if (!(h.dn == h.dn)) break;  // NaN: indefinite system, CG broke down
-  }
-  ls->pcg_residual = 0.5 * h.dn;
-  if (iterations) *iterations = h.iteration;
-  if (residual) *residual = ls->pcg_residual;
-  return B200_OK;
-}
-}  // namespace
-extern "C" {
 
 int b200_ls_solve_pcg(b200_linear_solver* ls, int nblocks, int block_dim, const int32_t* colptr, const int32_t* rowidx,
                       const double* values, double* x, const double* b, double tolerance, int absolute_tolerance,
@@ -145,49 +98,19 @@ int b200_ls_solve_pcg(b200_linear_solver* ls, int nblocks, int block_dim, const 
     B200_CUDA(cudaSetDevice(ls->device));
     cudaStream_t s = ls->stream;
     const int nblk = colptr[nblocks], d = block_dim;
-    if (!ls->pcg_ready || ls->pcg_nb != nblocks || ls->pcg_d != d || ls->pcg_nblk != nblk) {
-      // symmetric block-row lists (ascending column inside a row): the "linear structure" of linear_solver_pcg.hpp:86-106
-      std::vector<int> rowptr(nblocks + 1, 0), diag(nblocks, -1);
-      for (int c = 0; c < nblocks; ++c)
-        for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
-          const int r = rowidx[q];
-          if (r < 0 || r > c) { ls->err = "upper-triangular block pattern expected (row <= column)"; return B200_ERR_INVALID; }
-          rowptr[r + 1]++;
-          if (r != c) rowptr[c + 1]++; else diag[c] = q;
-        }
-      for (int c = 0; c < nblocks; ++c) if (diag[c] < 0) { ls->err = "missing diagonal block"; return B200_ERR_INVALID; }
-      for (int i = 0; i < nblocks; ++i) rowptr[i + 1] += rowptr[i];
-      std::vector<int> eb(rowptr[nblocks]), ec(rowptr[nblocks]), fill(rowptr.begin(), rowptr.end() - 1);
-      // row i first meets its transposed entries (columns c' < i come from block column i: rows r < i, ascending), then
-      // its own upper entries in ascending column order: walk the columns in order and append
-      for (int c = 0; c < nblocks; ++c)
-        for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
-          const int r = rowidx[q];
-          if (r != c) { eb[fill[c]] = ~q; ec[fill[c]] = r; fill[c]++; }
-        }
-      for (int c = 0; c < nblocks; ++c)
-        for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
-          const int r = rowidx[q];
-          eb[fill[r]] = q; ec[fill[r]] = c; fill[r]++;
-        }
-      ls->p_rowptr.upload(rowptr, s); ls->p_ent_blk.upload(eb, s); ls->p_ent_col.upload(ec, s); ls->p_diag_blk.upload(diag, s);
-      const size_t n = (size_t)nblocks * d;
-      ls->p_J.alloc((size_t)nblocks * d * d);
-      ls->p_x.alloc(n); ls->p_r.alloc(n); ls->p_s.alloc(n); ls->p_q.alloc(n); ls->p_d0.alloc(n); ls->p_d1.alloc(n);
-      ls->p_partial.alloc(ceil_div(n, (size_t)kPcgThreads) + 1);
-      ls->p_sc.alloc(1); ls->p_status.alloc(1);
-      B200_CUDA(cudaStreamSynchronize(s));
-      ls->pcg_nb = nblocks; ls->pcg_d = d; ls->pcg_nblk = nblk; ls->pcg_ready = true;
+    if (!ls->pcg.matches(nblocks, d, nblk)) {
+      const double carried = ls->pcg.carried_residual();
+      (void)carried;  // a new pattern keeps _residual (only init() resets it): PcgGpu::analyze does not touch it
+      if (!ls->pcg.analyze(nblocks, d, colptr, rowidx, s, &ls->err)) return B200_ERR_INVALID;
     }
     const size_t n = (size_t)nblocks * d;
     ls->dA.upload(values, (size_t)nblk * d * d, s);
     ls->db.upload(b, n, s);
     int it = 0;
     double res = 0.0;
-    const int rc = d == 3 ? pcg_run<3>(ls, ls->dA.p, ls->db.p, tolerance, absolute_tolerance, max_iterations, s, &it, &res)
-                          : pcg_run<6>(ls, ls->dA.p, ls->db.p, tolerance, absolute_tolerance, max_iterations, s, &it, &res);
+    const int rc = ls->pcg.solve(ls->dA.p, ls->db.p, tolerance, absolute_tolerance, max_iterations, s, &ls->lc, &it, &res);
     if (rc != B200_OK) return rc;
-    B200_CUDA(cudaMemcpyAsync(x, ls->p_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(x, ls->pcg.x(), n * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));
     if (iterations) *iterations = it;
     if (residual) *residual = res;

@@ -751,6 +751,11 @@ int build_structure_impl(b200_ctx* c) {
   if (const char* e = getenv("G2O_B200_ND_LEVELS")) opt.nd_levels = std::max(0, atoi(e));
   c->chol.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), opt, s);
   c->chol.set_diagonal_extra(var_lm ? c->d_pad_diag.p : nullptr);
+  c->pcg.init();   // a new structure: LinearSolverPCG::init() (BlockSolver::init -> _linearSolver->init())
+  if (c->linear_solver == 1) {
+    if (!c->pcg.analyze(np, pd, bp_colptr.data(), bp_rowidx.data(), s, &c->err)) return B200_ERR_INVALID;
+    if (!has_lm) c->d_pcg_A.alloc((size_t)c->n_hpp * pd * pd);
+  }
   STAMP("symbolic (ordering + plan)");
   c->structured = true;
   c->state_chi2_valid = false;  // new graph / new estimates on the device
@@ -921,7 +926,20 @@ int enqueue_max_diag(b200_ctx* c) {  // d_scalars[2] = max_j |H_jj| over poses a
 int enqueue_solve(b200_ctx* c, bool skip_backsub = false) {
   cudaStream_t s = c->stream;
   const double* d_lambda = c->d_scalars.p + 3;
-  if (!c->schur) {
+  if (!c->schur && c->linear_solver == 1) {
+    // LinearSolverPCG on Hpp + lambda I: the damped matrix is materialised once (the Cholesky adds lambda while it scatters)
+    PhaseTimer pt(c, PH_FACTOR);
+    B200_CUDA(cudaMemcpyAsync(c->d_pcg_A.p, c->d_Hpp.p, (size_t)c->n_hpp * c->pd * c->pd * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (c->pd == 3) k::add_block_diagonal_kernel<3><<<ceil_div((long long)c->np * 3, 256), 256, 0, s>>>(c->np, c->d_hpp_diag_block.p, d_lambda, c->var_lm ? c->d_pad_diag.p : nullptr, c->d_pcg_A.p);
+    else k::add_block_diagonal_kernel<6><<<ceil_div((long long)c->np * 6, 256), 256, 0, s>>>(c->np, c->d_hpp_diag_block.p, d_lambda, c->var_lm ? c->d_pad_diag.p : nullptr, c->d_pcg_A.p);
+    c->lc.n++;
+    B200_CUDA(cudaMemsetAsync(c->chol.status_ptr(), 0, sizeof(int), s));
+    const int rc = c->pcg.solve(c->d_pcg_A.p, c->d_b.p, c->pcg_tolerance, c->pcg_absolute, c->pcg_max_iterations, s, &c->lc, &c->pcg_last_iterations, nullptr);
+    if (rc) { const int one = 1; B200_CUDA(cudaMemcpyAsync(c->chol.status_ptr(), &one, sizeof(int), cudaMemcpyHostToDevice, s)); }
+    else B200_CUDA(cudaMemcpyAsync(c->d_x.p, c->pcg.x(), (size_t)c->sizeP * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  } else if (!c->schur) {
     { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hpp.p, d_lambda, c->d_b.p, s, &c->lc, &c->prof); }
     { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(c->d_b.p, c->d_x.p, s, &c->lc, &c->prof); }
     return 0;
@@ -963,8 +981,16 @@ int enqueue_solve(b200_ctx* c, bool skip_backsub = false) {
       B200_CUDA(cudaMemcpyAsync(c->d_scalars.p + 5, tail, sizeof(double), cudaMemcpyDeviceToDevice, s));
     }
   }
+  if (c->linear_solver == 1) {  // LinearSolverPCG on the reduced camera system (lambda is already on its diagonal)
+    PhaseTimer pt(c, PH_FACTOR);
+    B200_CUDA(cudaMemsetAsync(c->chol.status_ptr(), 0, sizeof(int), s));
+    const int rc = c->pcg.solve(c->d_Hschur.p, bschur_ptr(c), c->pcg_tolerance, c->pcg_absolute, c->pcg_max_iterations, s, &c->lc, &c->pcg_last_iterations, nullptr);
+    if (rc) { const int one = 1; B200_CUDA(cudaMemcpyAsync(c->chol.status_ptr(), &one, sizeof(int), cudaMemcpyHostToDevice, s)); }
+    else B200_CUDA(cudaMemcpyAsync(c->d_x.p, c->pcg.x(), (size_t)c->sizeP * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  } else {
   { PhaseTimer pt(c, PH_FACTOR); c->chol.factor(c->d_Hschur.p, nullptr, bschur_ptr(c), s, &c->lc, &c->prof); }
   { PhaseTimer pt(c, PH_TRISOLVE); c->chol.solve(bschur_ptr(c), c->d_x.p, s, &c->lc, &c->prof); }
+  }
   if (c->nl > 0 && !skip_backsub) {
     PhaseTimer pt(c, PH_BACKSUB);
     // on a failed factorisation the reference returns before touching the landmark part of x; the pose part
@@ -1084,7 +1110,7 @@ int reduce_trial_scalars(b200_ctx* c, int count = 1) {
 
 // ---- CUDA graph replay of the launch-bound sequences (about 150-250 small kernels each)
 // sharded: the native ncclAllReduce is captured like any kernel; the host callback cannot be
-bool graphs_usable(b200_ctx* c) { return c->use_graphs && !c->prof.on && (!sharded(c) || (c->nccl.active() && c->comm_warm)); }
+bool graphs_usable(b200_ctx* c) { return c->use_graphs && !c->prof.on && c->linear_solver == 0 && (!sharded(c) || (c->nccl.active() && c->comm_warm)); }
 
 template <typename F>
 int run_captured(b200_ctx* c, cudaGraphExec_t* exec, long long* launches, F&& enqueue) {
@@ -1514,6 +1540,18 @@ int b200_set_ordering(b200_ctx* c, int nd_levels) {
   c->structured = false;  // takes effect at the next b200_build_structure
   return B200_OK;
 }
+
+int b200_set_linear_solver(b200_ctx* c, int kind, double tolerance, int absolute_tolerance, int max_iterations) {
+  if (!c || (kind != B200_LINEAR_SOLVER_CHOLESKY && kind != B200_LINEAR_SOLVER_PCG)) return B200_ERR_INVALID;
+  if (kind == B200_LINEAR_SOLVER_PCG && !(tolerance > 0)) return fail(c, B200_ERR_INVALID, "PCG tolerance must be positive");
+  if (kind != c->linear_solver) c->structured = false;   // the PCG lists are built with the structure
+  c->linear_solver = kind;
+  if (kind == B200_LINEAR_SOLVER_PCG) { c->pcg_tolerance = tolerance; c->pcg_absolute = absolute_tolerance != 0; c->pcg_max_iterations = max_iterations; }
+  drop_graphs(c);
+  return B200_OK;
+}
+
+int b200_get_linear_solver_iterations(b200_ctx* c) { return c ? (c->linear_solver == 1 ? c->pcg_last_iterations : 0) : B200_ERR_INVALID; }
 
 int b200_set_robust_kernel(b200_ctx* c, int kind, double delta) {
   if (!c || kind < B200_ROBUST_NONE || kind > B200_ROBUST_DCS || !(delta > 0.0)) return B200_ERR_INVALID;

@@ -14,6 +14,7 @@
 #include "chol.h"
 #include "common.h"
 #include "nccl_comm.h"
+#include "pcg_host.h"
 
 struct b200_ctx {
   int device = 0;
@@ -111,6 +112,15 @@ struct b200_ctx {
   int* h_status = nullptr;
   int backup_depth = 0;
   g2o_b200::CholeskyGpu chol;
+  // linear solver of the (reduced) pose system: 0 = supernodal Cholesky (LinearSolverCSparse / Cholmod), 1 = block-Jacobi
+  // PCG (LinearSolverPCG, solvers/pcg): b200_set_linear_solver.  PCG stops on the device but reports to the host every 64
+  // iterations, so its trials run as plain launches (no CUDA-graph replay)
+  int linear_solver = 0;
+  double pcg_tolerance = 1e-6;
+  int pcg_absolute = 1, pcg_max_iterations = -1;
+  int pcg_last_iterations = 0;
+  g2o_b200::PcgGpu pcg;
+  g2o_b200::DevBuf<double> d_pcg_A;   // pose graphs: Hpp + lambda I (+ the unit diagonal of padding unknowns)
 
   int nd_levels = 0;                           // ordering: 0 = block AMD (reference), k = nested dissection, 2^k parts
   g2o_b200::Robust robust{0, 1.0};                 // robust kernel applied to every edge (b200_set_robust_kernel)

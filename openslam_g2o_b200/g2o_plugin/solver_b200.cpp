@@ -306,12 +306,16 @@ static bool b200Marginals(b200_ctx* _ctx, SparseBlockMatrix<MatrixXd>& spinv, co
 
 class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
  public:
-  explicit OptimizationAlgorithmB200(int algorithm) : OptimizationAlgorithm(), _ctx(0), _algorithm(algorithm) {
+  explicit OptimizationAlgorithmB200(int algorithm, bool pcg = false) : OptimizationAlgorithm(), _ctx(0), _algorithm(algorithm), _pcg(pcg) {
     _device = _properties.makeProperty<Property<int> >("device", 0);
     _userLambdaInit = _properties.makeProperty<Property<double> >("initialLambda", 0.);
     _maxTrialsAfterFailure = _properties.makeProperty<Property<int> >("maxTrialsAfterFailure", 10);
     // 0: block AMD, the reference's ordering; k > 0: nested dissection with 2^k parts on top of it (b200_set_ordering)
     _ndLevels = _properties.makeProperty<Property<int> >("ndLevels", 0);
+    // LinearSolverPCG's setters (solvers/pcg/linear_solver_pcg.h:75-82), used by the *_pcg*_b200 solvers
+    _pcgTolerance = _properties.makeProperty<Property<double> >("pcgTolerance", 1e-6);
+    _pcgAbsoluteTolerance = _properties.makeProperty<Property<bool> >("pcgAbsoluteTolerance", true);
+    _pcgMaxIterations = _properties.makeProperty<Property<int> >("pcgMaxIterations", -1);
   }
   virtual ~OptimizationAlgorithmB200() { b200_destroy(_ctx); }
 
@@ -323,6 +327,8 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
     }
     b200_set_lm_params(_ctx, _userLambdaInit->value(), _maxTrialsAfterFailure->value());
     b200_set_ordering(_ctx, _ndLevels->value());
+    b200_set_linear_solver(_ctx, _pcg ? B200_LINEAR_SOLVER_PCG : B200_LINEAR_SOLVER_CHOLESKY, _pcgTolerance->value(),
+                           _pcgAbsoluteTolerance->value() ? 1 : 0, _pcgMaxIterations->value());
     return _graph.ingest(_ctx, _optimizer);
   }
 
@@ -374,11 +380,15 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm {
  protected:
   b200_ctx* _ctx;
   int _algorithm;
+  bool _pcg;
   B200GraphBinding _graph;
   double _lambda;
   int _levenbergIterations;
   Property<int>* _device;
   Property<int>* _ndLevels;
+  Property<double>* _pcgTolerance;
+  Property<bool>* _pcgAbsoluteTolerance;
+  Property<int>* _pcgMaxIterations;
   Property<double>* _userLambdaInit;
   Property<int>* _maxTrialsAfterFailure;
 };
@@ -469,6 +479,8 @@ static OptimizationAlgorithm* createSolverB200(const std::string& fullSolverName
   const std::string rest = fullSolverName.substr(3);
   if (rest == "fix3_2_b200" || rest == "fix6_3_b200" || rest == "var_b200")  // Level 3: whole iteration on the GPU
     return new OptimizationAlgorithmB200(method == "gn" ? B200_GAUSS_NEWTON : B200_LEVENBERG);
+  if (rest == "pcg_b200" || rest == "pcg3_2_b200" || rest == "pcg6_3_b200")  // ... with LinearSolverPCG as the linear solver
+    return new OptimizationAlgorithmB200(method == "gn" ? B200_GAUSS_NEWTON : B200_LEVENBERG, true);
   // Level 2: stock LM/GN control, errors and update on the host; system, Schur complement and Cholesky on the GPU
   // Level 1: stock BlockSolver + LM/GN on the host, only the linear solver on the GPU
   Solver* s = 0;
@@ -502,6 +514,13 @@ B200_REGISTER(lm_fix6_3_b200, "Levenberg: device-resident solver on B200 (fixed 
 // landmark blocks of the C-ABI do not map onto a host-side SparseBlockMatrix<MatrixXd>)
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_var_b200, new B200SolverCreator(OptimizationAlgorithmProperty("gn_var_b200", "Gauss-Newton: device-resident solver on B200 (variable blocksize)", "B200", false, Eigen::Dynamic, Eigen::Dynamic)));
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_var_b200, new B200SolverCreator(OptimizationAlgorithmProperty("lm_var_b200", "Levenberg: device-resident solver on B200 (variable blocksize)", "B200", false, Eigen::Dynamic, Eigen::Dynamic)));
+// block-Jacobi PCG as the linear solver (solvers/pcg/solver_pcg.cpp: gn_pcg, gn_pcg3_2, gn_pcg6_3, lm_pcg, ...)
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_pcg_b200, new B200SolverCreator(OptimizationAlgorithmProperty("gn_pcg_b200", "Gauss-Newton: device-resident solver on B200, PCG (variable blocksize)", "B200", false, Eigen::Dynamic, Eigen::Dynamic)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_pcg_b200, new B200SolverCreator(OptimizationAlgorithmProperty("lm_pcg_b200", "Levenberg: device-resident solver on B200, PCG (variable blocksize)", "B200", false, Eigen::Dynamic, Eigen::Dynamic)));
+B200_REGISTER(gn_pcg3_2_b200, "Gauss-Newton: device-resident solver on B200, PCG (fixed blocksize)", 3, 2);
+B200_REGISTER(gn_pcg6_3_b200, "Gauss-Newton: device-resident solver on B200, PCG (fixed blocksize)", 6, 3);
+B200_REGISTER(lm_pcg3_2_b200, "Levenberg: device-resident solver on B200, PCG (fixed blocksize)", 3, 2);
+B200_REGISTER(lm_pcg6_3_b200, "Levenberg: device-resident solver on B200, PCG (fixed blocksize)", 6, 3);
 B200_REGISTER(gn_fix3_2_b200s, "Gauss-Newton: B200 solver (system, Schur, Cholesky) under the stock algorithm", 3, 2);
 B200_REGISTER(gn_fix6_3_b200s, "Gauss-Newton: B200 solver (system, Schur, Cholesky) under the stock algorithm", 6, 3);
 B200_REGISTER(lm_fix3_2_b200s, "Levenberg: B200 solver (system, Schur, Cholesky) under the stock algorithm", 3, 2);

@@ -54,6 +54,10 @@ for _alg, _aid in (("gn", L.GAUSS_NEWTON), ("lm", L.LEVENBERG)):
     for _fix, _pd, _ld in (("fix3_2", 3, 2), ("fix6_3", 6, 3)):
         for _suffix in ("", "_cholmod", "_b200"):
             _SOLVERS["%s_%s%s" % (_alg, _fix, _suffix)] = (_aid, _pd, _ld)
+    # LinearSolverPCG as the linear solver (solvers/pcg/solver_pcg.cpp: gn_pcg, gn_pcg3_2, gn_pcg6_3, lm_pcg, ...)
+    for _name, _pd in (("pcg", -1), ("pcg3_2", 3), ("pcg6_3", 6)):
+        for _suffix in ("", "_b200"):
+            _SOLVERS["%s_%s%s" % (_alg, _name, _suffix)] = (_aid, _pd, 3 if _pd == 6 else 2 if _pd == 3 else -1)
     # variable block sizes (BlockSolverX; solvers/csparse/solver_csparse.cpp:53-55: requiresMarginalize = false): pose graphs
     # and landmark SLAM (SE2 + XY, SE3 + XYZ) with every vertex in one system
     for _suffix in ("", "_cholmod", "_b200"):
@@ -167,6 +171,16 @@ class SolverContext:
         if rc != 0:
             return None
         return np.ascontiguousarray(np.transpose(out, (0, 2, 1)))  # column-major blocks -> [row, col]
+
+    def set_linear_solver(self, kind="cholesky", tolerance=1e-6, absolute_tolerance=True, max_iterations=-1):
+        """linear solver of the (reduced) pose system: "cholesky" (default) or "pcg" = LinearSolverPCG (solvers/pcg) with its
+        setTolerance / setAbsoluteTolerance / setMaxIterations; before build_structure()"""
+        _check(lib.b200_set_linear_solver(self._h, {"cholesky": 0, "pcg": 1}[kind], float(tolerance), int(bool(absolute_tolerance)),
+                                          int(max_iterations)), self._h)
+
+    def linear_solver_iterations(self):
+        """G2OBatchStatistics::iterationsLinearSolver of the last solve (PCG)"""
+        return int(lib.b200_get_linear_solver_iterations(self._h))
 
     def set_ordering(self, nd_levels=0):
         """0: block AMD (the reference's ordering, default); k > 0: nested dissection with 2^k parts on top of it"""
@@ -321,6 +335,9 @@ class SparseOptimizer:
                             % (name, ", ".join(sorted(_SOLVERS))))
         self._algorithm = _SOLVERS[name][0]
         self._requires_marginalize = _SOLVERS[name][1] > 0  # all fix* solvers (solver_cholmod.cpp:115-121); var: false
+        self._linear_solver = "pcg" if "_pcg" in name else "cholesky"
+        if self._ctx is not None:
+            self._ctx.set_linear_solver(self._linear_solver)
 
     def load(self, path):
         return _check(lib.b200_graph_load(self._g, str(path).encode()), self._g, graph=True) == 0
@@ -367,6 +384,8 @@ class SparseOptimizer:
     def context(self):
         if self._ctx is None:
             self._ctx = SolverContext(self._device)
+            if getattr(self, "_linear_solver", "cholesky") != "cholesky":
+                self._ctx.set_linear_solver(self._linear_solver)
         return self._ctx
 
     def _ensure_uploaded(self):

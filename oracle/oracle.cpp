@@ -995,8 +995,15 @@ struct LinearSolverCSparseO {
 // ---------------------------------------------------------------------------------------------
 }  // namespace
 
+static int pcg_solve(int nb, int d, const int* colptr, const int* rowidx, const double* values, double* x, const double* b,
+                     double tolerance, int absolute_tolerance, int max_iter, double* residual_io);
+
 struct oracle_graph {
   typedef std::tr1::unordered_map<int, Vertex*> VertexIDMap;  // core/hyper_graph.h VertexIDMap
+  // LinearSolverPCG as the BlockSolver's linear solver (solvers/pcg/solver_pcg.cpp: `*_pcg*`): oracle_set_linear_solver
+  bool usePCG = false;
+  double pcgTolerance = 1e-6, pcgResidual = -1.0;
+  int pcgAbsolute = 1, pcgMaxIter = -1, pcgIterations = 0;
   VertexIDMap vertices;
   std::vector<std::unique_ptr<Vertex>> vstore;
   std::vector<std::unique_ptr<Edge>> edges;  // addEdge order = internalId
@@ -1418,10 +1425,31 @@ inline void inverse3(const double* m, double* r) {
 }
 
 // ---- core/block_solver.hpp:354-486 ----
+// _linearSolver->solve(A, x, b): LinearSolverCSparse, or LinearSolverPCG (solvers/pcg/linear_solver_pcg.hpp:79-160; always true)
+bool linear_solve(G* g, const SBM& M, double* x, const double* b) {
+  if (!g->usePCG) return g->linearSolver.solve(M, x, b);
+  if (!M.cbase.empty()) return false;  // variable block sizes under PCG: not restated
+  std::vector<int> colptr(M.ncols + 1, 0), rowidx;
+  std::vector<double> values;
+  const int sz = M.rdim * M.cdim;
+  for (int c = 0; c < M.ncols; ++c) {
+    for (auto& kv : M.cols[c]) {
+      if (kv.first > c) continue;
+      rowidx.push_back(kv.first);
+      values.insert(values.end(), kv.second, kv.second + sz);
+    }
+    colptr[c + 1] = (int)rowidx.size();
+  }
+  std::vector<double> rhs(b, b + (size_t)M.ncols * M.cdim);  // x and b may alias in the callers
+  g->pcgIterations = pcg_solve(M.ncols, M.cdim, colptr.data(), rowidx.data(), values.data(), x, rhs.data(), g->pcgTolerance,
+                               g->pcgAbsolute, g->pcgMaxIter, &g->pcgResidual);
+  return true;
+}
+
 bool solve(G* g) {
   if (!g->doSchur) {
     double t = now();
-    bool ok = g->linearSolver.solve(g->Hpp, g->x.data(), g->b.data());
+    bool ok = linear_solve(g, g->Hpp, g->x.data(), g->b.data());
     g->timeLinearSolver = now() - t;
     return ok;
   }
@@ -1467,7 +1495,7 @@ bool solve(G* g) {
   for (int i = 0; i < g->sizePoses; ++i) g->bschur[i] -= g->coefficients[i];
   g->timeSchur = now() - t;
   t = now();
-  bool solvedPoses = g->linearSolver.solve(g->Hschur, g->x.data(), g->bschur.data());
+  bool solvedPoses = linear_solve(g, g->Hschur, g->x.data(), g->bschur.data());
   g->timeLinearSolver = now() - t;
   if (!solvedPoses) return false;
   double* xp = g->x.data();
@@ -1505,6 +1533,7 @@ bool algorithm_init(G* g) {  // core/optimization_algorithm_with_hessian.cpp:50-
   for (Vertex* v : g->activeVertices) if (v->marginalized) { useSchur = true; break; }
   g->doSchur = useSchur;
   g->linearSolver.init();
+  g->pcgResidual = -1.0;  // LinearSolverPCG::init (linear_solver_pcg.h:64-71)
   return true;
 }
 
@@ -1809,6 +1838,14 @@ int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta) {
   return 0;
 }
 void oracle_set_block_ordering(oracle_graph* g, int bo) { g->linearSolver.blockOrdering = bo != 0; }
+// kind 0: LinearSolverCSparse, 1: LinearSolverPCG (tolerance / absolute tolerance / max iterations as its setters)
+int oracle_set_linear_solver(oracle_graph* g, int kind, double tolerance, int absolute_tolerance, int max_iterations) {
+  if (!g || kind < 0 || kind > 1) return -1;
+  g->usePCG = kind == 1;
+  g->pcgTolerance = tolerance; g->pcgAbsolute = absolute_tolerance; g->pcgMaxIter = max_iterations; g->pcgResidual = -1.0;
+  return 0;
+}
+int oracle_pcg_iterations(oracle_graph* g) { return g ? g->pcgIterations : -1; }
 
 int oracle_optimize(oracle_graph* g, int algorithm, int iterations, oracle_iter_stats* stats) {
   if (g->ivMap.empty()) return -1;

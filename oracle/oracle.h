@@ -70,6 +70,10 @@ int oracle_setup_cli(oracle_graph* g, int requires_marginalize);
 int oracle_initialize(oracle_graph* g);
 /* LinearSolverCSparse::setBlockOrdering (solver_csparse.cpp: fix* -> 1, var -> 0) */
 void oracle_set_block_ordering(oracle_graph* g, int block_ordering);
+/* the BlockSolver's linear solver: 0 LinearSolverCSparse (default), 1 LinearSolverPCG (solvers/pcg/linear_solver_pcg.hpp:79-160,
+ * the `*_pcg*` solvers of solvers/pcg/solver_pcg.cpp) with setTolerance / setAbsoluteTolerance / setMaxIterations */
+int oracle_set_linear_solver(oracle_graph* g, int kind, double tolerance, int absolute_tolerance, int max_iterations);
+int oracle_pcg_iterations(oracle_graph* g);   /* iterations of the last PCG solve */
 /* one robust kernel on every edge (apps/g2o_cli/g2o.cpp:322-336; core/robust_kernel_impl.cpp:65-126):
  * kind 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS */
 int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta);

@@ -114,6 +114,14 @@ class Oracle:
         self.L.oracle_set_robust_kernel.argtypes = [C.c_void_p, C.c_int, C.c_double]
         assert self.L.oracle_set_robust_kernel(self.g, kinds[name], float(width)) == 0
 
+    def set_linear_solver(self, kind, tolerance=1e-6, absolute_tolerance=True, max_iterations=-1):
+        self.L.oracle_set_linear_solver.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]
+        assert self.L.oracle_set_linear_solver(self.g, {"cholesky": 0, "pcg": 1}[kind], float(tolerance), int(bool(absolute_tolerance)),
+                                               int(max_iterations)) == 0
+
+    def pcg_iterations(self):
+        return int(self.L.oracle_pcg_iterations(self.g))
+
     def set_block_ordering(self, on):
         self.L.oracle_set_block_ordering(self.g, int(on))
 
