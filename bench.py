@@ -648,6 +648,32 @@ def widening_block(device):
                     "ordering_bit_exact": bool(np.array_equal(opt.context.block_ordering(), o.block_perm())),
                     "note": "wall clock incl. the per-trial host round trips; first iteration excludes structure + symbolic analysis (GPU) but includes it for the oracle"}
         opt.close()
+    # ---- LinearSolverPCG as the linear solver of the headline graph (lm_pcg6_3): inexact solves, so a flavour of its own -
+    #      reported beside the Cholesky headline, never instead of it
+    try:
+        prob = synth.venice_like()
+        res = {}
+        for name in ("lm_pcg6_3", "lm_fix6_3"):
+            opt = g.SparseOptimizer(device=device)
+            opt.set_algorithm(name)
+            synth.feed(prob, opt)
+            opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+            assert opt.context.build_structure()
+            opt.optimize(1)                      # warm-up (first launches, lazy module load); a fresh optimizer is timed
+            opt.close()
+            opt = g.SparseOptimizer(device=device)
+            opt.set_algorithm(name)
+            synth.feed(prob, opt)
+            opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+            assert opt.context.build_structure()
+            opt.context.synchronize()
+            t = time.perf_counter(); n = opt.optimize(10); opt.context.synchronize(); dt = time.perf_counter() - t
+            res[name] = {"iterations": int(n), "lm_iterations_per_s_wall": n / dt, "chi2": [float(s_.chi2) for s_ in opt.batch_statistics],
+                         "cg_iterations_last_solve": opt.context.linear_solver_iterations()}
+            opt.close()
+        out["venice_pcg_vs_cholesky"] = res
+    except Exception as e:
+        out["venice_pcg_vs_cholesky"] = {"error": repr(e)}
     return out
 
 
