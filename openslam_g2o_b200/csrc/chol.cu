@@ -1384,7 +1384,7 @@ void CholeskyGpu::sparse_inverse(cudaStream_t s, LaunchCounter* lc) {
       const int ni = spinv_item_ptr_[l + 1] - spinv_item_ptr_[l], ns = spinv_level_ptr_[l + 1] - spinv_level_ptr_[l];
       if (ni > 0) {
         spinv_rows_kernel<D><<<ni, kSpinvThreads, 0, s>>>(V, d_spinv_item_sn_.p, d_spinv_item_p_.p, spinv_item_ptr_[l], d_Yt_.p, d_Zinv_.p);
-        spinv_diag_kernel<D><<<ns, kSpinvThreads, 0, s>>>(V, d_spinv_level_sn_.p, spinv_level_ptr_[l], d_Yt_.p, d_Zinv_.p);
+        spinv_diag_kernel<D><<<dim3(ns, S.max_ncol * D), kSpinvThreads, 0, s>>>(V, d_spinv_level_sn_.p, spinv_level_ptr_[l], d_Yt_.p, d_Zinv_.p);
         count(2);
       }
     }

@@ -8,7 +8,7 @@
 // of Z_RR is final when the supernode is reached):
 //     Y    = L21 L11^-1                      (spinv_prepare_kernel, all supernodes at once)
 //     Z_RJ = - Z_RR Y                        (spinv_rows_kernel, one CTA per block row of a supernode)
-//     Z_JJ = L11^-T L11^-1 - Y^T Z_RJ        (spinv_diag_kernel, one CTA per supernode)
+//     Z_JJ = L11^-T L11^-1 - Y^T Z_RJ        (spinv_diag_kernel, one CTA per column of the diagonal part)
 // One launch pair per depth level of the supernodal tree; cost = the factorisation's flops, once, for EVERY block on the
 // pattern of L (all diagonal blocks, all blocks of edges) - instead of one factorisation + solve per requested scalar
 // column.  Z has the geometry of L (spinv_lookup.h); Z_RR blocks are located by binary search in the ancestor's row list.
@@ -112,26 +112,41 @@ spinv_rows_kernel(const __grid_constant__ SpinvDev V, const int* __restrict__ it
     if (oi[o] >= 0) Zp[p * D + oi[o] + (long long)oc[o] * M] = -acc[o];
 }
 
-// one CTA = one supernode: Z_JJ -= Y^T Z_RJ (the seed L11^-T L11^-1 is already there)
+// one CTA = one COLUMN b of the diagonal part of one supernode: Z_JJ(:, b) -= Y^T Z_RJ(:, b) (the seed L11^-T L11^-1 is
+// already there).  Thread = (row a, one of G interleaved slices of the B rows below), four independent partial sums per
+// thread, slices added in fixed order through shared memory.  (First version: one CTA per supernode, every thread a
+// serial dot product of length B - 0.9 ms for ONE wide supernode near the root, most of the 14 ms sweep on sphere2500.)
 template <int D>
 __global__ void __launch_bounds__(kSpinvThreads)
 spinv_diag_kernel(const __grid_constant__ SpinvDev V, const int* __restrict__ level_sn, int sn0,
                   const double* __restrict__ Yt, double* __restrict__ Z) {
+  __shared__ double part[kSpinvThreads];
   const int J = level_sn[sn0 + blockIdx.x];
   const int M = V.P.sn_nrow[J] * D, N = V.P.sn_ncol[J] * D, B = M - N;
+  const int b = blockIdx.y;
+  if (b >= N) return;   // whole CTA
   const double* Yp = Yt + V.P.sn_lptr[J];
   double* Zp = Z + V.P.sn_lptr[J];
-  for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
-    const int b = i / N, a = i - b * N;
-    const double* zc = Zp + N + (long long)b * M;
-    double s0 = 0.0, s1 = 0.0;
-    int r = 0;
-    for (; r + 1 < B; r += 2) {
+  const int G = kSpinvThreads / N;            // slices (N <= 72: G >= 3)
+  const int a = threadIdx.x % N, g = threadIdx.x / N;
+  const double* zc = Zp + N + (long long)b * M;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (g < G) {
+    int r = g;
+    for (; r + 3 * G < B; r += 4 * G) {
       s0 = fma(Yp[a + (long long)N * r], zc[r], s0);
-      s1 = fma(Yp[a + (long long)N * (r + 1)], zc[r + 1], s1);
+      s1 = fma(Yp[a + (long long)N * (r + G)], zc[r + G], s1);
+      s2 = fma(Yp[a + (long long)N * (r + 2 * G)], zc[r + 2 * G], s2);
+      s3 = fma(Yp[a + (long long)N * (r + 3 * G)], zc[r + 3 * G], s3);
     }
-    if (r < B) s0 = fma(Yp[a + (long long)N * r], zc[r], s0);
-    Zp[a + (long long)b * M] -= s0 + s1;
+    for (; r < B; r += G) s0 = fma(Yp[a + (long long)N * r], zc[r], s0);
+  }
+  part[threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double s = 0.0;
+    for (int q = 0; q < G; ++q) s += part[threadIdx.x + q * N];
+    Zp[threadIdx.x + (long long)b * M] -= s;
   }
 }
 
