@@ -337,3 +337,22 @@ def test_landmark_seen_by_more_cameras_than_a_range_holds_is_planned_not_refused
     a, b = plan(1400), plan(3)
     assert a["schur_contributions"] == b["schur_contributions"] and a["hpl_slots"] == b["hpl_slots"]
     assert b["schur_segments"] > a["schur_segments"]   # (and more, shorter ranges: a wide landmark closes the range before it)
+
+
+def test_pcg_solver_names_plan_on_the_host():
+    """`*_pcg*` solver names (solvers/pcg/solver_pcg.cpp) select LinearSolverPCG inside the solver: the structure phase
+    (incl. the symmetric block-row lists of the CG kernels) runs on a host-only context; compute stays refused without a GPU"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    for p, name in ((synth.venice_like(10, 200, seed=2), "lm_pcg6_3"), (synth.sphere(8, 5, seed=2), "gn_pcg6_3"),
+                    (synth.landmark_slam_2d(20, 10, seed=2), "lm_pcg")):
+        opt = g.SparseOptimizer(device=-1)
+        opt.set_algorithm(name)
+        synth.feed(p, opt)
+        opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+        assert opt.context.build_structure()
+        with pytest.raises(g.B200Error):
+            opt.context.solve()
+        opt.close()
+    with pytest.raises(g.B200Error):
+        g.SparseOptimizer(device=-1).set_algorithm("lm_pcg7_3")   # 7-dimensional poses: not provided
