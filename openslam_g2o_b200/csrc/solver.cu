@@ -1431,7 +1431,8 @@ int b200_compute_marginals(b200_ctx* c, int nblocks, const int32_t* rows, const 
     for (int q = 0; q < nblocks; ++q)
       if (rows[q] < 0 || rows[q] >= c->np || cols[q] < 0 || cols[q] >= c->np) return fail(c, B200_ERR_INVALID, "block index out of range");
     cudaStream_t s = c->stream;
-    DevBuf<double> rhs, xs;
+    DevBuf<double>& rhs = c->d_marg_rhs;
+    DevBuf<double>& xs = c->d_marg_x;
     rhs.alloc(n); xs.alloc(n);
     // (1) ONE factorisation of Hpp (lambda = 0; the forward substitution that rides along gets a zero right-hand side),
     //     then the sparse inverse subset on the factor: every requested block on the pattern of L comes out of one
@@ -1456,7 +1457,7 @@ int b200_compute_marginals(b200_ctx* c, int nblocks, const int32_t* rows, const 
     if (!in_pattern.empty()) {
       c->chol.sparse_inverse(s, &c->lc);
       const int m = (int)in_pattern.size();
-      DevBuf<long long> d_off; DevBuf<int> d_ld; DevBuf<unsigned char> d_trans; DevBuf<double> d_out;
+      DevBuf<long long>& d_off = c->d_marg_off; DevBuf<int>& d_ld = c->d_marg_ld; DevBuf<unsigned char>& d_trans = c->d_marg_trans; DevBuf<double>& d_out = c->d_marg_out;
       d_off.upload(off, s); d_ld.upload(ld, s); d_trans.upload(trans, s); d_out.alloc((size_t)m * d * d);
       c->chol.gather_inverse_blocks(m, d_off.p, d_ld.p, d_trans.p, d_out.p, s, &c->lc);
       std::vector<double> h((size_t)m * d * d);

@@ -120,6 +120,11 @@ struct b200_ctx {
   int pcg_absolute = 1, pcg_max_iterations = -1;
   int pcg_last_iterations = 0;
   g2o_b200::PcgGpu pcg;
+  // b200_compute_marginals: buffers kept between calls (a front end asks for marginals after every optimisation)
+  g2o_b200::DevBuf<double> d_marg_rhs, d_marg_x, d_marg_out;
+  g2o_b200::DevBuf<long long> d_marg_off;
+  g2o_b200::DevBuf<int> d_marg_ld;
+  g2o_b200::DevBuf<unsigned char> d_marg_trans;
   g2o_b200::DevBuf<double> d_pcg_A;   // pose graphs: Hpp + lambda I (+ the unit diagonal of padding unknowns)
 
   int nd_levels = 0;                           // ordering: 0 = block AMD (reference), k = nested dissection, 2^k parts
