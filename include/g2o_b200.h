@@ -190,6 +190,11 @@ int b200_get_linear_solver_iterations(b200_ctx* ctx);
 enum { B200_ROBUST_NONE = 0, B200_ROBUST_HUBER = 1, B200_ROBUST_PSEUDO_HUBER = 2, B200_ROBUST_CAUCHY = 3,
        B200_ROBUST_SATURATED = 4, B200_ROBUST_DCS = 5 };
 int b200_set_robust_kernel(b200_ctx* ctx, int kind, double delta);
+/* per-edge robust kernels - Edge::setRobustKernel on individual edges (core/optimizable_graph.h:446-450), e.g. a kernel on
+ * loop closures / sightings only: kinds[i], deltas[i] for edge i of the set given by b200_set_edges(edge_kind, ...) (same
+ * order, n = its size; B200_ROBUST_NONE = no kernel on that edge).  Call after b200_set_edges; replaces the uniform kernel
+ * for that set until the next b200_set_edges / b200_set_robust_kernel; kinds == NULL returns to the uniform one. */
+int b200_set_edge_robust_kernels(b200_ctx* ctx, int edge_kind, int n, const uint8_t* kinds, const double* deltas);
 /* Solver::computeMarginals (core/solver.h:100-106, core/block_solver.hpp:490-499, LinearSolver::solvePattern
  * solvers/csparse/linear_solver_csparse.h:190-225, core/marginal_covariance_cholesky.cpp): blocks (rows[q], cols[q])
  * of the inverse of the current Hpp (call after b200_build_system; lambda is not added), written to
@@ -287,6 +292,9 @@ int b200_graph_add_edge(b200_graph* g, int kind, int id1, int id2, const double*
 int b200_graph_add_vertices(b200_graph* g, int kind, int n, const int32_t* ids, const double* payload, int stride);
 int b200_graph_add_edges(b200_graph* g, int kind, int n, const int32_t* id1, const int32_t* id2, const double* payload, int stride);
 int b200_graph_set_fixed(b200_graph* g, int id, int fixed);
+/* Edge::setRobustKernel on one edge: edge_index counts the edges in the order they were added / read (internalId);
+ * edges without a kernel of their own stay without one as soon as any edge has one (else the context's uniform kernel) */
+int b200_graph_set_edge_robust_kernel(b200_graph* g, int edge_index, int kind, double delta);
 /* PARAMS_CAMERAPARAMETERS id focal_length cx cy baseline (types/sba/types_six_dof_expmap.h:45-80); has to precede the
  * XYZ2UV edges that name it (payload of such an edge: paramId u v i00 i01 i11, types_six_dof_expmap.cpp:241-256).
  * All edges of one pose must name parameters with equal values (the intrinsics ride in the pose's estimate row). */

@@ -98,6 +98,7 @@ def _load():
         "b200_get_factor_nnz": (i64, [vp]),
         "b200_get_factor_info": (i32, [vp, vp]),
         "b200_set_robust_kernel": (i32, [vp, i32, C.c_double]),
+        "b200_set_edge_robust_kernels": (i32, [vp, i32, i32, vp, vp]),
         "b200_set_ordering": (i32, [vp, i32]),
         "b200_set_linear_solver": (i32, [vp, i32, C.c_double, i32, i32]),
         "b200_get_linear_solver_iterations": (i32, [vp]),
@@ -123,6 +124,7 @@ def _load():
         "b200_graph_add_vertices": (i32, [vp, i32, i32, vp, vp, i32]),
         "b200_graph_add_edges": (i32, [vp, i32, i32, vp, vp, vp, i32]),
         "b200_graph_set_fixed": (i32, [vp, i32, i32]),
+        "b200_graph_set_edge_robust_kernel": (i32, [vp, i32, i32, C.c_double]),
         "b200_graph_add_camera_parameters": (i32, [vp, i32, dbl, dbl, dbl, dbl]),
         "b200_graph_add_se3_offset": (i32, [vp, i32, vp]),
         "b200_graph_setup_cli": (i32, [vp, i32]),

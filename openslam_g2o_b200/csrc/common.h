@@ -144,6 +144,9 @@ struct ScopedPhase {
 struct Robust {
   int kind;      // B200_ROBUST_*: 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS
   double delta;
+  // per-edge kernels (device arrays in device edge order; nullptr: the uniform kernel above)
+  const unsigned char* kinds;
+  const double* deltas;
 };
 
 // counts every kernel launch of this library (reported as bench "gpu_launches")

@@ -117,6 +117,9 @@ struct b200_graph {
   // landmark sharding of the last upload: per XYZ slot the row handed to the context (-1: another shard owns it).
   // Empty = nothing sharded (row i of the context is slot i).  b200_graph_download scatters through it.
   std::vector<int> uploaded_lm_row;
+  // per-edge robust kernels (b200_graph_set_edge_robust_kernel), indexed like `edges`; empty = none set (255 = unset entry)
+  std::vector<unsigned char> edge_rk_kind;
+  std::vector<double> edge_rk_delta;
   std::string err;
   int find(int id) const { auto it = idmap.find(id); return it == idmap.end() ? -1 : it->second; }
 };
@@ -427,6 +430,14 @@ int b200_graph_add_se3_offset(b200_graph* g, int id, const double* o) {
   g->se3_offsets_text[id] = {o[0], o[1], o[2], q[0], q[1], q[2], q[3]};
   return B200_OK;
 }
+int b200_graph_set_edge_robust_kernel(b200_graph* g, int edge_index, int kind, double delta) {
+  if (!g || edge_index < 0 || edge_index >= (int)g->edges.size() || kind < B200_ROBUST_NONE || kind > B200_ROBUST_DCS ||
+      (kind != B200_ROBUST_NONE && !(delta > 0.0))) return B200_ERR_INVALID;
+  if (g->edge_rk_kind.size() != g->edges.size()) { g->edge_rk_kind.resize(g->edges.size(), 255); g->edge_rk_delta.resize(g->edges.size(), 1.0); }
+  g->edge_rk_kind[edge_index] = (unsigned char)kind;
+  g->edge_rk_delta[edge_index] = delta;
+  return B200_OK;
+}
 int b200_graph_set_fixed(b200_graph* g, int id, int fixed) {
   if (!g) return B200_ERR_INVALID;
   int v = g->find(id);
@@ -572,6 +583,26 @@ int b200_graph_counts(b200_graph* g, int32_t* vc, int32_t* ec) {
   return B200_OK;
 }
 
+// per-edge robust kernels of the edges just handed over (`sel`: their indices into g->edges, in hand-over order); edges
+// without an entry of their own carry "no kernel"
+static int upload_edge_kernels(b200_graph* g, b200_ctx* ctx, int ekind, const std::vector<int>& sel) {
+  if (g->edge_rk_kind.empty()) return B200_OK;
+  bool any = false;
+  for (int k : sel) if (k < (int)g->edge_rk_kind.size() && g->edge_rk_kind[k] != 255) { any = true; break; }
+  if (!any) return B200_OK;
+  std::vector<uint8_t> kd(sel.size());
+  std::vector<double> dl(sel.size());
+  for (size_t i = 0; i < sel.size(); ++i) {
+    const int k = sel[i];
+    const bool has = k < (int)g->edge_rk_kind.size() && g->edge_rk_kind[k] != 255;
+    kd[i] = has ? g->edge_rk_kind[k] : (uint8_t)B200_ROBUST_NONE;
+    dl[i] = has ? g->edge_rk_delta[k] : 1.0;
+  }
+  int rc = b200_set_edge_robust_kernels(ctx, ekind, (int)sel.size(), kd.data(), dl.data());
+  if (rc) g->err = b200_last_error(ctx);
+  return rc;
+}
+
 int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
   if (!g || !ctx || num_shards < 1 || shard < 0 || shard >= num_shards) return B200_ERR_INVALID;
   if (g->active_edges.empty()) { g->err = "call b200_graph_initialize first"; return B200_ERR_INVALID; }
@@ -656,10 +687,12 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     const int D = edim(lkind), nm = emeas(lkind);
     std::vector<int32_t> vi, vj;
     std::vector<double> meas, info;
+    std::vector<int> sel;
     const std::array<double, 12>* off = nullptr;
     for (int k : g->active_edges) {
       const HEdge& e = g->edges[k];
       if (e.kind != lkind) continue;
+      sel.push_back(k);
       vi.push_back(g->vertices[e.v0].slot); vj.push_back(g->vertices[e.v1].slot);
       meas.insert(meas.end(), e.meas, e.meas + nm);
       info.insert(info.end(), e.info, e.info + D * D);
@@ -672,6 +705,7 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     if (off) { int rc = b200_set_sensor_offset(ctx, off->data()); if (rc) { g->err = b200_last_error(ctx); return rc; } }
     int rc = b200_set_edges(ctx, lkind, (int)vi.size(), vi.data(), vj.data(), meas.data(), info.data());
     if (rc) { g->err = b200_last_error(ctx); return rc; }
+    if ((rc = upload_edge_kernels(g, ctx, lkind, sel)) != B200_OK) return rc;
     if (ekind < 0) {  // no odometry at all: empty pose-pose set of the matching kind
       rc = b200_set_edges(ctx, lkind == B200_EDGE_SE2_XY ? B200_EDGE_SE2 : B200_EDGE_SE3, 0, nullptr, nullptr, nullptr, nullptr);
       if (rc) { g->err = b200_last_error(ctx); return rc; }
@@ -738,6 +772,12 @@ int b200_graph_upload(b200_graph* g, b200_ctx* ctx, int shard, int num_shards) {
     }
     int rc = b200_set_edges(ctx, ekind, (int)vi.size(), vi.data(), vj.data(), meas.data(), info.data());
     if (rc) { g->err = b200_last_error(ctx); return rc; }
+    if (!g->edge_rk_kind.empty()) {  // this shard's edges of the main set, in hand-over order
+      std::vector<int> sel;
+      sel.reserve(na);
+      for (size_t q = 0; q < nact; ++q) if (mine(g->edges[g->active_edges[q]])) sel.push_back(g->active_edges[q]);
+      if ((rc = upload_edge_kernels(g, ctx, ekind, sel)) != B200_OK) return rc;
+    }
   }
   return B200_OK;
 }

@@ -109,7 +109,12 @@ __device__ __forceinline__ Iso load_iso_soa(const double* __restrict__ meas, int
 // rho(e2) and rho'(e2) as core/robust_kernel_impl.cpp:65-126; the quadratic form uses the first-order weight only:
 // information and omega_r are scaled by rho' (base_edge.h:96-102, base_binary_edge.hpp:91-113), chi2 sums rho
 // (sparse_optimizer.cpp:100-114).
-// struct Robust { int kind; double delta; }: common.h
+// struct Robust { int kind; double delta; kinds, deltas }: common.h.  kinds != nullptr: per-edge kernels
+// (OptimizableGraph::Edge::setRobustKernel on individual edges), indexed by the device edge index
+__device__ __forceinline__ Robust robust_at(const Robust& rk, int e) {
+  if (rk.kinds == nullptr) return rk;
+  return Robust{(int)rk.kinds[e], rk.deltas[e], nullptr, nullptr};
+}
 __device__ __forceinline__ void robustify(const Robust& rk, double e2, double& rho0, double& rho1) {
   const double dsqr = rk.delta * rk.delta;
   switch (rk.kind) {
@@ -158,7 +163,8 @@ __global__ void pg_chi2_kernel(int E, const int* __restrict__ v0, const int* __r
     }
     load_info<D>(info, E, e, W);
     chi = chi2_of<D>(W, err);
-    if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
+    const Robust rke = robust_at(rk, e);
+    if (rke.kind) { double r1; robustify(rke, chi, chi, r1); }
   }
   chi = block_sum(chi);
   if (threadIdx.x == 0) partials[blockIdx.x] = chi;
@@ -185,9 +191,10 @@ pg_linearize_kernel(int E, const int* __restrict__ v0, const int* __restrict__ v
   }
   double W[D * D];
   load_info<D>(info, E, e, W);
-  if (rk.kind) {  // weightedOmega = rho' * information; omega_r = -weightedOmega * error
+  const Robust rke = robust_at(rk, e);
+    if (rke.kind) {  // weightedOmega = rho' * information; omega_r = -weightedOmega * error
     double r0, r1;
-    robustify(rk, chi2_of<D>(W, err), r0, r1);
+    robustify(rke, chi2_of<D>(W, err), r0, r1);
 #pragma unroll
     for (int i = 0; i < D * D; ++i) W[i] *= r1;
   }
@@ -296,7 +303,8 @@ __global__ void pl_chi2_kernel(int E, const int* __restrict__ v0, const int* __r
     pl_error<FAM>(e, E, v0, v1, pose_est, lm_est, meas, off, err, nullptr, nullptr, false);
     load_info<ED>(info, E, e, W);
     chi = chi2_of<ED>(W, err);
-    if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
+    const Robust rke = robust_at(rk, e);
+    if (rke.kind) { double r1; robustify(rke, chi, chi, r1); }
   }
   chi = block_sum(chi);
   if (threadIdx.x == 0) partials[blockIdx.x] = chi;
@@ -318,9 +326,10 @@ pl_linearize_kernel(int E, int rec0, const int* __restrict__ v0, const int* __re
   double A[ED * D], B[ED * LD], err[ED], W[ED * ED];
   pl_error<FAM>(e, E, v0, v1, pose_est, lm_est, meas, off, err, A, B, true);
   load_info<ED>(info, E, e, W);
-  if (rk.kind) {
+  const Robust rke = robust_at(rk, e);
+    if (rke.kind) {
     double r0, r1;
-    robustify(rk, chi2_of<ED>(W, err), r0, r1);
+    robustify(rke, chi2_of<ED>(W, err), r0, r1);
 #pragma unroll
     for (int i = 0; i < ED * ED; ++i) W[i] *= r1;
   }
@@ -420,7 +429,8 @@ __global__ void ba_chi2_kernel(int E, const int* __restrict__ e_pt, const int* _
     ba_error<MODEL>(der, X, z, err);
     const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
     chi = err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]);
-    if (rk.kind) { double r1; robustify(rk, chi, chi, r1); }
+    const Robust rke = robust_at(rk, e);
+    if (rke.kind) { double r1; robustify(rke, chi, chi, r1); }
   }
   chi = block_sum(chi);
   if (threadIdx.x == 0) partials[blockIdx.x] = chi;
@@ -455,9 +465,10 @@ ba_linearize_points_kernel(int nl, const int* __restrict__ lm_eptr, const int* _
     const double z[2] = {meas[e], meas[(long long)E + e]};
     ba_error<MODEL>(der, X, z, err);
     double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
-    if (rk.kind) {
+    const Robust rke = robust_at(rk, e);
+    if (rke.kind) {
       double r0, r1;
-      robustify(rk, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), r0, r1);
+      robustify(rke, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), r0, r1);
       w0 *= r1; w1 *= r1; w2 *= r1;
     }
     // JpW = Jp^T W (3x2), omega_r = -W err
@@ -548,9 +559,10 @@ ba_linearize_packets_kernel(int npk, const int4* __restrict__ packets, const int
       const double z[2] = {meas[e], meas[(long long)E + e]};
       ba_error<MODEL>(der, X, z, err);
       double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
-      if (rk.kind) {
+      const Robust rke = robust_at(rk, e);
+    if (rke.kind) {
         double q0, q1;
-        robustify(rk, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), q0, q1);
+        robustify(rke, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), q0, q1);
         w0 *= q1; w1 *= q1; w2 *= q1;
       }
       double JpW[6];
@@ -654,9 +666,10 @@ ba_linearize_cams_kernel(const int* __restrict__ cam_eptr, const int* __restrict
     const double z[2] = {meas[e], meas[(long long)E + e]};
     ba_error<MODEL>(der, X, z, err);
     double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
-    if (rk.kind) {
+    const Robust rke = robust_at(rk, e);
+    if (rke.kind) {
       double r0, r1;
-      robustify(rk, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), r0, r1);
+      robustify(rke, err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]), r0, r1);
       w0 *= r1; w1 *= r1; w2 *= r1;
     }
     double JW[12];  // Jc^T W : 6x2
@@ -1136,7 +1149,8 @@ ba_backsub_update_kernel(int nl, const int* __restrict__ lm_eptr, const int* __r
       ba_error<MODEL>(der, X, z, err);
       const double w0 = info[e], w1 = info[(long long)E + e], w2 = info[2ll * E + e];
       double ce = err[0] * (w0 * err[0] + w1 * err[1]) + err[1] * (w1 * err[0] + w2 * err[1]);
-      if (rk.kind) { double r1; robustify(rk, ce, ce, r1); }
+      const Robust rke = robust_at(rk, e);
+    if (rke.kind) { double r1; robustify(rke, ce, ce, r1); }
       chi += ce;
     }
   }

@@ -99,6 +99,31 @@ static size_t schur_range_smem(const b200_ctx* c) {
          (size_t)((c->sr_cap_slots + 7) & ~7) * sizeof(unsigned short);   // + the landmark of every slot
 }
 
+// per-edge robust kernels -> device edge order (BA: the landmark-rank order of e_order; pose graphs: input order)
+void upload_robust(b200_ctx* c) {
+  cudaStream_t s = c->stream;
+  c->robust = Robust{c->rk_uniform_kind, c->rk_uniform_delta, nullptr, nullptr};
+  c->robust_l = c->robust;
+  if ((int)c->rk_kinds.size() == c->nE && c->nE > 0) {
+    std::vector<unsigned char> kd(c->nE);
+    std::vector<double> dl(c->nE);
+    for (int q = 0; q < c->nE; ++q) {
+      const int e = c->schur ? c->e_order[q] : q;
+      kd[q] = c->rk_kinds[e]; dl[q] = c->rk_deltas[e];
+    }
+    c->d_rk_kinds.upload(kd, s); c->d_rk_deltas.upload(dl, s);
+    if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
+    c->robust.kinds = c->d_rk_kinds.p; c->robust.deltas = c->d_rk_deltas.p;
+    c->robust.kind = 1;   // "some kernel": the kernels look the edge's own kind up
+  }
+  if (c->var_lm && (int)c->l_rk_kinds.size() == c->nLE && c->nLE > 0) {
+    c->d_lrk_kinds.upload(c->l_rk_kinds, s); c->d_lrk_deltas.upload(c->l_rk_deltas, s);
+    if (!c->host_only) B200_CUDA(cudaStreamSynchronize(s));
+    c->robust_l.kinds = c->d_lrk_kinds.p; c->robust_l.deltas = c->d_lrk_deltas.p;
+    c->robust_l.kind = 1;
+  }
+}
+
 int build_structure_impl(b200_ctx* c) {
   double _t_last = wall();
   const bool _tv = getenv("G2O_B200_STRUCT_VERBOSE") != nullptr;
@@ -758,6 +783,7 @@ int build_structure_impl(b200_ctx* c) {
   }
   STAMP("symbolic (ordering + plan)");
   c->structured = true;
+  upload_robust(c);
   c->state_chi2_valid = false;  // new graph / new estimates on the device
   c->backup_depth = 0;
   c->time_symbolic = wall() - t0;
@@ -788,9 +814,9 @@ void enqueue_chi2(b200_ctx* c) {  // result -> d_scalars[0]
     k::SensorOffset off;
     memcpy(off.m, c->sensor_offset, sizeof(off.m));
     if (c->l_edge_kind == B200_EDGE_SE2_XY)
-      k::pl_chi2_kernel<0><<<nb2, 256, 0, s>>>(LE, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, off, c->robust, c->d_partials.p + nb);
+      k::pl_chi2_kernel<0><<<nb2, 256, 0, s>>>(LE, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, off, c->robust_l, c->d_partials.p + nb);
     else
-      k::pl_chi2_kernel<1><<<nb2, 256, 0, s>>>(LE, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, off, c->robust, c->d_partials.p + nb);
+      k::pl_chi2_kernel<1><<<nb2, 256, 0, s>>>(LE, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, off, c->robust_l, c->d_partials.p + nb);
     nb += nb2;
     c->lc.n++;
   }
@@ -825,14 +851,14 @@ int enqueue_build_system(b200_ctx* c) {
     if (c->edge_kind == B200_EDGE_SE2) {
       { PhaseTimer pt(c, PH_LINEARIZE);
       if (E > 0) k::pg_linearize_kernel<0><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p);
-      if (c->var_lm) { k::pl_linearize_kernel<0><<<ceil_div(c->nLE, 128), 128, 0, s>>>(c->nLE, E, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, c->d_e_flag.p, off, c->robust, c->d_stage.p); c->lc.n++; } }
+      if (c->var_lm) { k::pl_linearize_kernel<0><<<ceil_div(c->nLE, 128), 128, 0, s>>>(c->nLE, E, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, c->d_e_flag.p, off, c->robust_l, c->d_stage.p); c->lc.n++; } }
       PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<3, 9><<<ceil_div((long long)c->n_hpp * 9, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<3, 3><<<ceil_div((long long)np * 3, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
     } else {
       { PhaseTimer pt(c, PH_LINEARIZE);
       if (E > 0) k::pg_linearize_kernel<1><<<ceil_div(E, 128), 128, 0, s>>>(E, c->d_ev0.p, c->d_ev1.p, c->d_pose_est.p, c->d_meas.p, c->d_info.p, c->d_e_flag.p, c->robust, c->d_stage.p);
-      if (c->var_lm) { k::pl_linearize_kernel<1><<<ceil_div(c->nLE, 128), 128, 0, s>>>(c->nLE, E, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, c->d_e_flag.p, off, c->robust, c->d_stage.p); c->lc.n++; } }
+      if (c->var_lm) { k::pl_linearize_kernel<1><<<ceil_div(c->nLE, 128), 128, 0, s>>>(c->nLE, E, c->d_lev0.p, c->d_lev1.p, c->d_pose_est.p, c->d_lm_est.p, c->d_lmeas.p, c->d_linfo.p, c->d_e_flag.p, off, c->robust_l, c->d_stage.p); c->lc.n++; } }
       PhaseTimer pt(c, PH_GATHER);
       k::gather_segments_kernel<6, 36><<<ceil_div((long long)c->n_hpp * 36, 256), 256, 0, s>>>(c->n_hpp, c->d_hsrc_ptr.p, c->d_hsrc_id.p, c->d_stage.p, c->d_Hpp.p);
       k::gather_segments_kernel<6, 6><<<ceil_div((long long)np * 6, 256), 256, 0, s>>>(np, c->d_bsrc_ptr.p, c->d_bsrc_id.p, c->d_stage.p, c->d_b.p);
@@ -1285,6 +1311,7 @@ int b200_set_edges(b200_ctx* c, int kind, int n, const int32_t* vi, const int32_
     c->l_meas.assign(meas, meas + (size_t)n * emeas(kind));
     const int D = edim(kind);
     c->l_info.assign(info, info + (size_t)n * D * D);
+    c->l_rk_kinds.clear(); c->l_rk_deltas.clear();   // per-edge kernels belong to the edge set they were given for
     c->structured = false;
     return B200_OK;
   }
@@ -1295,6 +1322,7 @@ int b200_set_edges(b200_ctx* c, int kind, int n, const int32_t* vi, const int32_
   c->e_meas.assign(meas, meas + (size_t)n * emeas(kind));
   const int D = edim(kind);
   c->e_info.assign(info, info + (size_t)n * D * D);
+  c->rk_kinds.clear(); c->rk_deltas.clear();
   c->structured = false;
   return B200_OK;
 }
@@ -1556,11 +1584,30 @@ int b200_get_linear_solver_iterations(b200_ctx* c) { return c ? (c->linear_solve
 
 int b200_set_robust_kernel(b200_ctx* c, int kind, double delta) {
   if (!c || kind < B200_ROBUST_NONE || kind > B200_ROBUST_DCS || !(delta > 0.0)) return B200_ERR_INVALID;
-  c->robust.kind = kind;
-  c->robust.delta = delta;
+  c->rk_uniform_kind = kind;
+  c->rk_uniform_delta = delta;
+  c->rk_kinds.clear(); c->rk_deltas.clear(); c->l_rk_kinds.clear(); c->l_rk_deltas.clear();   // one kernel for every edge again
   c->state_chi2_valid = false;
   if (!c->host_only) { cudaSetDevice(c->device); drop_graphs(c); }  // captured launches carry the kernel by value
-  return B200_OK;
+  return guarded(c, [&]() { upload_robust(c); return (int)B200_OK; });
+}
+
+int b200_set_edge_robust_kernels(b200_ctx* c, int edge_kind, int n, const uint8_t* kinds, const double* deltas) {
+  if (!c || edge_kind < 0 || edge_kind >= B200_NUM_EDGE_KINDS || n < 0) return B200_ERR_INVALID;
+  const bool lset = edge_kind == B200_EDGE_SE2_XY || edge_kind == B200_EDGE_SE3_XYZ;
+  std::vector<unsigned char>& K = lset ? c->l_rk_kinds : c->rk_kinds;
+  std::vector<double>& D = lset ? c->l_rk_deltas : c->rk_deltas;
+  if (!kinds) { K.clear(); D.clear(); }
+  else {
+    if (!deltas || n != (lset ? c->nLE : c->nE)) return fail(c, B200_ERR_INVALID, "b200_set_edge_robust_kernels: one (kind, width) per edge of the set given to b200_set_edges");
+    for (int i = 0; i < n; ++i)
+      if (kinds[i] > B200_ROBUST_DCS || (kinds[i] != B200_ROBUST_NONE && !(deltas[i] > 0.0))) return fail(c, B200_ERR_INVALID, "b200_set_edge_robust_kernels: unknown kernel or non-positive width");
+    K.assign(kinds, kinds + n); D.assign(deltas, deltas + n);
+  }
+  c->state_chi2_valid = false;
+  if (!c->host_only) { cudaSetDevice(c->device); drop_graphs(c); }
+  if (!c->structured) return B200_OK;   // uploaded (in device edge order) by b200_build_structure
+  return guarded(c, [&]() { upload_robust(c); return (int)B200_OK; });
 }
 
 int b200_set_terminate(b200_ctx* c, b200_terminate_fn fn, void* user) {

@@ -128,7 +128,15 @@ struct b200_ctx {
   g2o_b200::DevBuf<double> d_pcg_A;   // pose graphs: Hpp + lambda I (+ the unit diagonal of padding unknowns)
 
   int nd_levels = 0;                           // ordering: 0 = block AMD (reference), k = nested dissection, 2^k parts
-  g2o_b200::Robust robust{0, 1.0};                 // robust kernel applied to every edge (b200_set_robust_kernel)
+  g2o_b200::Robust robust{0, 1.0, nullptr, nullptr};   // robust kernel applied to every edge (b200_set_robust_kernel) ...
+  g2o_b200::Robust robust_l{0, 1.0, nullptr, nullptr}; // ... the same for the pose-landmark edge set of a landmark-SLAM graph
+  // per-edge kernels (b200_set_edge_robust_kernels): input order on the host, device edge order on the device
+  int rk_uniform_kind = 0;
+  double rk_uniform_delta = 1.0;
+  std::vector<unsigned char> rk_kinds, l_rk_kinds;
+  std::vector<double> rk_deltas, l_rk_deltas;
+  g2o_b200::DevBuf<unsigned char> d_rk_kinds, d_lrk_kinds;
+  g2o_b200::DevBuf<double> d_rk_deltas, d_lrk_deltas;
 
   // ---------------- algorithm state (core/optimization_algorithm_levenberg.h)
   double lambda = -1.0, ni = 2.0;

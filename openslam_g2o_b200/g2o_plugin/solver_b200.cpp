@@ -116,6 +116,10 @@ struct B200GraphBinding {
     int ekind = -1;
     int robustKind = B200_ROBUST_NONE;
     double robustDelta = 1.0;
+    // kernels that differ between edges (Edge::setRobustKernel on individual edges) go over per edge
+    bool uniformKernel = true;
+    std::vector<uint8_t> rkKinds, lrkKinds;
+    std::vector<double> rkDeltas, lrkDeltas;
     for (size_t k = 0; k < edges.size(); ++k) {
       OptimizableGraph::Edge* e = edges[k];
       int kind = -1;
@@ -183,11 +187,14 @@ struct B200GraphBinding {
         else if (dynamic_cast<RobustKernelDCS*>(r)) rk = B200_ROBUST_DCS;
         else rk = -1;
       }
-      if (rk < 0 || (k > 0 && (rk != robustKind || rkDelta != robustDelta))) {
-        std::cerr << "OptimizationAlgorithmB200: unsupported robust kernel, or kernels that differ between edges" << std::endl;
+      if (rk < 0) {
+        std::cerr << "OptimizationAlgorithmB200: unsupported robust kernel type" << std::endl;
         return false;
       }
+      if (k > 0 && (rk != robustKind || rkDelta != robustDelta)) uniformKernel = false;
       robustKind = rk; robustDelta = rkDelta;
+      (landmarkEdge ? lrkKinds : rkKinds).push_back(static_cast<uint8_t>(rk));
+      (landmarkEdge ? lrkDeltas : rkDeltas).push_back(rkDelta);
       if (landmarkEdge) {
         lkind = kind;
         lvi.push_back(_slot[static_cast<OptimizableGraph::Vertex*>(e->vertex(0))]);
@@ -214,7 +221,13 @@ struct B200GraphBinding {
     // the pose-landmark set (n = 0 forgets the set of a previous graph)
     if (b200_set_edges(_ctx, lkind >= 0 ? lkind : B200_EDGE_SE2_XY, static_cast<int>(lvi.size()), lvi.empty() ? 0 : &lvi[0], lvi.empty() ? 0 : &lvj[0],
                        lvi.empty() ? 0 : &lmeas[0], lvi.empty() ? 0 : &linfo[0]) != B200_OK) return false;
-    if (b200_set_robust_kernel(_ctx, robustKind, robustDelta) != B200_OK) return false;
+    if (uniformKernel) {
+      if (b200_set_robust_kernel(_ctx, robustKind, robustDelta) != B200_OK) return false;
+    } else {
+      if (b200_set_robust_kernel(_ctx, B200_ROBUST_NONE, 1.0) != B200_OK) return false;
+      if (!rkKinds.empty() && b200_set_edge_robust_kernels(_ctx, ekind, static_cast<int>(rkKinds.size()), &rkKinds[0], &rkDeltas[0]) != B200_OK) return false;
+      if (!lrkKinds.empty() && b200_set_edge_robust_kernels(_ctx, lkind, static_cast<int>(lrkKinds.size()), &lrkKinds[0], &lrkDeltas[0]) != B200_OK) return false;
+    }
     int rc = b200_build_structure(_ctx);
     if (rc != B200_OK) std::cerr << "OptimizationAlgorithmB200: " << b200_last_error(_ctx) << std::endl;
     return rc == B200_OK;

@@ -371,6 +371,13 @@ class SparseOptimizer:
         """`g2o -robustKernel name -robustKernelWidth width` (apps/g2o_cli/g2o.cpp:322-336): every edge gets the kernel"""
         self.context.set_robust_kernel(name, width)
 
+    def set_edge_robust_kernel(self, edge_indices, name, width=1.0):
+        """Edge::setRobustKernel on individual edges (indices in the order the edges were added / read): e.g. a kernel on the
+        loop closures only.  Edges without one of their own then carry no kernel."""
+        for k in edge_indices:
+            _check(lib.b200_graph_set_edge_robust_kernel(self._g, int(k), ROBUST_KERNELS[name], float(width)), self._g, graph=True)
+        self._uploaded = False
+
     def setup_cli(self):
         """gauge + marginalisation exactly as the g2o binary does (apps/g2o_cli/g2o.cpp:272-320)."""
         return lib.b200_graph_setup_cli(self._g, int(self._requires_marginalize))

@@ -1837,6 +1837,12 @@ int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta) {
   for (auto& e : g->edges) { e->rkKind = kind; e->rkDelta = delta; }
   return 0;
 }
+// Edge::setRobustKernel on one edge (edge k in addEdge order)
+int oracle_set_edge_robust_kernel(oracle_graph* g, int k, int kind, double delta) {
+  if (!g || k < 0 || k >= (int)g->edges.size() || kind < 0 || kind > 5) return -1;
+  g->edges[k]->rkKind = kind; g->edges[k]->rkDelta = delta;
+  return 0;
+}
 void oracle_set_block_ordering(oracle_graph* g, int bo) { g->linearSolver.blockOrdering = bo != 0; }
 // kind 0: LinearSolverCSparse, 1: LinearSolverPCG (tolerance / absolute tolerance / max iterations as its setters)
 int oracle_set_linear_solver(oracle_graph* g, int kind, double tolerance, int absolute_tolerance, int max_iterations) {

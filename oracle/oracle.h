@@ -78,6 +78,8 @@ int oracle_pcg_iterations(oracle_graph* g);   /* iterations of the last PCG solv
  * kind 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS */
 int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta);
 void oracle_robustify(int kind, double delta, double e2, double* rho3);
+/* Edge::setRobustKernel on edge k (addEdge order) only */
+int oracle_set_edge_robust_kernel(oracle_graph* g, int k, int kind, double delta);
 /* Solver::computeMarginals -> LinearSolverCSparse::solvePattern -> MarginalCovarianceCholesky: blocks (rows[q], cols[q])
  * of Hpp^-1 (after oracle_build_system), column-major d x d each */
 int oracle_compute_marginals(oracle_graph* g, int nblocks, const int* rows, const int* cols, double* out);  /* rho, rho', rho'' */

@@ -122,6 +122,12 @@ class Oracle:
     def pcg_iterations(self):
         return int(self.L.oracle_pcg_iterations(self.g))
 
+    def set_edge_robust_kernel(self, edge_indices, name, width=1.0):
+        kinds = {"none": 0, "Huber": 1, "PseudoHuber": 2, "Cauchy": 3, "Saturated": 4, "DCS": 5}
+        self.L.oracle_set_edge_robust_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        for k in edge_indices:
+            assert self.L.oracle_set_edge_robust_kernel(self.g, int(k), kinds[name], float(width)) == 0
+
     def set_block_ordering(self, on):
         self.L.oracle_set_block_ordering(self.g, int(on))
 

@@ -125,3 +125,92 @@ def test_gpu_robust_lm_matches_oracle(kind, kernel, width):
     synth.feed(prob, plain)
     plain.setup_cli(); plain.initialize_optimization()
     assert chi0_g < 0.9 * plain.compute_active_errors()
+
+
+def _per_edge_problem(kind):
+    from openslam_g2o_b200 import synth
+    if kind == "slam2d":
+        p = dict(synth.landmark_slam_2d(60, 30, seed=13))
+        rng = np.random.default_rng(13)
+        pay = p["obs_payload"].copy()
+        bad = rng.choice(len(pay), 25, replace=False)
+        pay[bad, :2] += rng.normal(0, 3.0, (25, 2))
+        p["obs_payload"] = pay
+        n_odo, n_obs = len(p["odo_v0"]), len(p["obs_v0"])
+        # edges are added odometry first, then sightings (synth.feed): kernels on the sightings and the loop closures only
+        sel = {"Huber": list(range(59, n_odo)) + list(range(n_odo, n_odo + n_obs, 2)), "Cauchy": list(range(n_odo + 1, n_odo + n_obs, 4))}
+        return p, "lm_var", False, sel
+    p = _outlier_graph(kind, 17)
+    E = len(p["edge_v0"])
+    sel = {"Huber": list(range(0, E, 3)), "DCS": list(range(1, E, 5))}
+    return p, "lm_fix6_3", True, sel
+
+
+@pytest.mark.gpu
+@needs_oracle
+@pytest.mark.parametrize("kind", ["se3", "ba", "slam2d"])
+def test_gpu_per_edge_robust_kernels_match_oracle(kind):
+    """Edge::setRobustKernel on individual edges (a kernel on loop closures / sightings only, different kernels and widths on
+    different edges; the others carry none): chi2 of the initial state and the LM trajectory against the oracle, whose edges
+    carry their own rkKind / rkDelta like the reference's (core/base_binary_edge.hpp:91-113)"""
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    from oracle_binding import LM, Oracle
+    prob, name, marg, sel = _per_edge_problem(kind)
+    widths = {"Huber": 1.5, "Cauchy": 2.0, "DCS": 2.5}
+
+    def make(cls):
+        t = cls() if cls is Oracle else cls(device=0)
+        if cls is not Oracle:
+            t.set_algorithm(name)
+        synth.feed(prob, t)
+        for kname, idx in sel.items():
+            t.set_edge_robust_kernel(idx, kname, widths[kname])
+        return t
+    opt, o = make(g.SparseOptimizer), make(Oracle)
+    assert opt.setup_cli() == o.setup_cli(marg)
+    o.set_block_ordering(True)
+    opt.initialize_optimization(); o.initialize_optimization()
+    chi0_g = opt.compute_active_errors()
+    o.algorithm_init(); o.build_structure()
+    chi0_o = o.compute_active_errors()
+    assert abs(chi0_g - chi0_o) <= 1e-10 * chi0_o
+    n = opt.optimize(6)
+    o2 = make(Oracle)
+    o2.setup_cli(marg); o2.set_block_ordering(True); o2.initialize_optimization()
+    no, st = o2.optimize(LM, 6)
+    assert n == no
+    chi_g = np.array([s.chi2 for s in opt.batch_statistics]); chi_o = np.array([s.chi2 for s in st[:no]])
+    assert rel_err(chi_g, chi_o) < 1e-6, (chi_g, chi_o)
+    # not the uniform-kernel answer and not the plain one
+    plain = g.SparseOptimizer(device=0)
+    plain.set_algorithm(name)
+    synth.feed(prob, plain)
+    plain.setup_cli(); plain.initialize_optimization()
+    assert chi0_g < 0.98 * plain.compute_active_errors()
+
+
+def test_per_edge_robust_kernels_reach_the_context_in_edge_order():
+    """host side of the same: the graph hands (kind, width) per edge of each edge set to the context in hand-over order;
+    wrong lengths and unknown kernels are refused"""
+    import ctypes as C
+    import openslam_g2o_b200 as g
+    from openslam_g2o_b200 import synth
+    from openslam_g2o_b200._lib import lib, ptr
+    p = synth.landmark_slam_2d(20, 10, seed=3)
+    opt = g.SparseOptimizer(device=-1)
+    opt.set_algorithm("lm_var")
+    synth.feed(p, opt)
+    opt.set_edge_robust_kernel([0, 5, len(p["odo_v0"]) + 2], "Huber", 2.0)
+    opt.setup_cli(); opt.initialize_optimization(); opt._ensure_uploaded()
+    assert opt.context.build_structure()
+    h = opt.context.handle
+    n_obs = len(p["obs_v0"])
+    kinds = np.ones(n_obs, np.uint8); deltas = np.ones(n_obs)
+    assert lib.b200_set_edge_robust_kernels(h, g.EDGE_SE2_XY, n_obs, ptr(kinds), ptr(deltas)) == 0
+    assert lib.b200_set_edge_robust_kernels(h, g.EDGE_SE2_XY, n_obs - 1, ptr(kinds), ptr(deltas)) < 0      # one entry per edge
+    kinds[3] = 9
+    assert lib.b200_set_edge_robust_kernels(h, g.EDGE_SE2_XY, n_obs, ptr(kinds), ptr(deltas)) < 0          # unknown kernel
+    assert lib.b200_set_edge_robust_kernels(h, g.EDGE_SE2_XY, 0, None, None) == 0                          # back to the uniform one
+    with pytest.raises(g.B200Error):
+        opt.set_edge_robust_kernel([10 ** 6], "Huber", 1.0)
