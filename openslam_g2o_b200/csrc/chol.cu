@@ -1300,7 +1300,7 @@ void CholeskyGpu::factor_t(const double* dA, const double* d_lambda, const doubl
     ChainDev C{(int)S.chain_sn.size(), d_chain_desc_.p, d_chain_map_.p, d_chain_fwd_ptr_.p, d_chain_fwd_src_.p,
                (int)S.chain_stage_doubles, (int)S.chain_remap_blocks};
     chol_chain_kernel<<<1, kChThreads, chain_smem_, s>>>(C, L, d_Ldiag_.p, d_chain_pack_.p, cnt + 2, d_y_.p, d_z_.p, d_contrib_.p);
-    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_chain_desc_.p, d_chain_pack_.p, d_Dinv_.p);
+    chol_chain_dinv_kernel<<<(int)S.chain_sn.size(), 128, kChDinvSmem, s>>>(P, d_chain_sn_.p, d_sn_dinvptr_.p, d_Ldiag_.p, d_chain_desc_.p, d_chain_pack_.p, keep_chain_inverses_ ? d_Dinv_.p : nullptr);
     count(2);
   }
   B200_CUDA(cudaGetLastError());

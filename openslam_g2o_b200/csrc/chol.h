@@ -40,6 +40,10 @@ class CholeskyGpu {
   // extra[i] (device, length nb*d, ORIGINAL ordering; nullptr = none) is added to diagonal entry i by every factor():
   // the unit diagonal of padding unknowns (landmark blocks padded to the pose dimension, solver.cu)
   void set_diagonal_extra(const double* d_extra) { d_diag_extra_ = d_extra; }
+  // the next factor() calls also leave the inverse diagonal blocks of the tail-chain links where sparse_inverse() reads
+  // them (the solves take them from the chain's packed records): on for marginals, off on the LM path (measured: the
+  // second copy costs 15 us per factorisation on the Venice-shaped graph)
+  void keep_chain_inverses(bool on) { keep_chain_inverses_ = on; }
   int* status_ptr() { return d_counters_.p + 2; }  // device int: 0 ok, 1 not positive definite
   double* factor_values() { return d_L_.p; }
   // Sparse inverse subset of the matrix of the preceding factor(): every block of A^-1 on the pattern of L + L^T
@@ -56,6 +60,7 @@ class CholeskyGpu {
  private:
   bool analyzed_ = false;
   const double* d_diag_extra_ = nullptr;
+  bool keep_chain_inverses_ = false;
   SymbolicFactor S_;
   DevBuf<int> d_sn_col0_, d_sn_ncol_, d_sn_nrow_, d_sn_rowptr_, d_sn_rows_;
   DevBuf<long long> d_sn_lptr_;

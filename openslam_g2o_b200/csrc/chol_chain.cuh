@@ -447,12 +447,12 @@ chol_chain_dinv_kernel(const __grid_constant__ CholDev P, const int* __restrict_
   __syncthreads();
   const int* dj = desc + (size_t)blockIdx.x * CD_INTS;  // the inverse goes behind the packed rows of the link
   double* out = pack + cd_i64(dj, CD_PACK) + (size_t)(dj[CD_NROW] - dj[CD_NCOL]) * D * N;
-  double* out2 = Dinv + sn_dinvptr[J];  // ... and where the dataflow kernel keeps its inverses (sparse_inverse.cuh reads it)
+  double* out2 = Dinv ? Dinv + sn_dinvptr[J] : nullptr;  // ... and, when the sparse inverse will follow (marginals), where the dataflow kernel keeps its inverses
   for (int q = threadIdx.x; q < N * N; q += blockDim.x) {
     const int c = q / N, r = q - c * N;  // out(r,c) = inv(r,c) = Zt[c + r*N]
     const double v = r >= c ? Zt[c + r * N] : 0.0;
     out[q] = v;
-    out2[q] = v;
+    if (Dinv) out2[q] = v;
   }
 }
 

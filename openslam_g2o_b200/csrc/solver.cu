@@ -1467,7 +1467,9 @@ int b200_compute_marginals(b200_ctx* c, int nblocks, const int32_t* rows, const 
     //     sweep down the supernodal tree (chol.h: sparse_inverse)
     {
       B200_CUDA(cudaMemsetAsync(rhs.p, 0, n * sizeof(double), s));
+      c->chol.keep_chain_inverses(true);
       c->chol.factor(c->d_Hpp.p, nullptr, rhs.p, s, &c->lc, nullptr);
+      c->chol.keep_chain_inverses(false);
       int status = 0;
       B200_CUDA(cudaMemcpyAsync(&status, c->chol.status_ptr(), sizeof(int), cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
