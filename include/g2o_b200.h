@@ -32,7 +32,7 @@ extern "C" {
 #define B200_ERR_INVALID (-1)
 #define B200_ERR_NO_DEVICE (-2)
 #define B200_ERR_CUDA (-3)
-#define B200_ERR_UNSUPPORTED (-4)      /* graph uses types outside {SE2,SE3,CAM,XYZ}: no CPU fallback */
+#define B200_ERR_UNSUPPORTED (-4)      /* graph uses types / combinations outside the families listed below: no CPU fallback */
 #define B200_ERR_COLLECTIVE (-5)
 #define B200_ERR_EXCEPTION (-6)        /* a C++ exception other than a CUDA failure (std::bad_alloc, ...) was caught at the ABI */
 
