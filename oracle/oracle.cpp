@@ -42,6 +42,13 @@ void compute_dq_dR(Eigen::Matrix<double, 3, 9>& dq_dR, const double& r11, const 
 #include <cs.h>  // reference header, found via -I$(REF)/EXTERNAL/csparse at oracle build time
 
 // solvers/csparse/csparse_helper.h:41-42 (compiled from the reference into libg2o_csparse_ref.so)
+// oracle/ref_wrap.cpp -> oracle/_ref/libg2o_ref_wrap.so: the reference's robust kernels (core/robust_kernel_impl.cpp) and
+// SE2 class (types/slam2d/se2.h), compiled from where they lie behind the Eigen shim of oracle/stub
+extern "C" {
+int ref_robustify(int kind, double delta, double e2, double* rho3);
+void ref_edge_se2_error(const double* v1, const double* v2, const double* z, double* e);
+void ref_edge_se2_xy_error(const double* v1, const double* l2, const double* z, double* e);
+}
 namespace g2o { namespace csparse_extension {
 int cs_cholsolsymb(const cs* A, double* b, const css* S, double* workspace, int* work);
 csn* cs_chol_workspace(const cs* A, const css* S, int* cin, double* xin);  // csparse_helper.h:37
@@ -329,11 +336,8 @@ void compute_error(Edge* e) {
   Vertex* v0 = e->v[0];
   Vertex* v1 = e->v[1];
   switch (e->kind) {
-    case ORC_EDGE_SE2: {  // types/slam2d/edge_se2.h:46-52
-      SE2 x1{v0->est[0], v0->est[1], v0->est[2]}, x2{v1->est[0], v1->est[1], v1->est[2]};
-      SE2 zi{e->invMeas[0], e->invMeas[1], e->invMeas[2]};
-      SE2 d = se2_mul(zi, se2_mul(se2_inv(x1), x2));
-      e->err[0] = d.x; e->err[1] = d.y; e->err[2] = d.th;
+    case ORC_EDGE_SE2: {  // types/slam2d/edge_se2.h:46-52, evaluated by the reference's own SE2 class (oracle/ref_wrap.cpp)
+      ref_edge_se2_error(v0->est, v1->est, e->meas, e->err);
       break;
     }
     case ORC_EDGE_SE3: {  // types/slam3d/edge_se3.cpp:48-53
@@ -363,11 +367,8 @@ void compute_error(Edge* e) {
       e->err[1] = e->meas[1] - (proj[1] * e->camPar[0] + e->camPar[2]);
       break;
     }
-    case ORC_EDGE_SE2_XY: {  // types/slam2d/edge_se2_pointxy.h:46-51: (v1^-1 * l2) - z, SE2 * Vector2d (se2.h:80-83)
-      SE2 xi = se2_inv(SE2{v0->est[0], v0->est[1], v0->est[2]});
-      const double c = cos(xi.th), s = sin(xi.th);
-      e->err[0] = (c * v1->est[0] - s * v1->est[1] + xi.x) - e->meas[0];
-      e->err[1] = (s * v1->est[0] + c * v1->est[1] + xi.y) - e->meas[1];
+    case ORC_EDGE_SE2_XY: {  // types/slam2d/edge_se2_pointxy.h:46-51: (v1^-1 * l2) - z, by the reference's own SE2 class
+      ref_edge_se2_xy_error(v0->est, v1->est, e->meas, e->err);
       break;
     }
     case ORC_EDGE_SE3_XYZ: {  // types/slam3d/edge_se3_pointxyz.cpp:98-108; cache: parameter_se3_offset.cpp:75-80
@@ -682,7 +683,15 @@ inline double edge_chi2(const Edge* e) {
   return s;
 }
 // core/robust_kernel_impl.cpp:65-126: rho = [rho(e2), rho'(e2), rho''(e2)]
+// The oracle calls the REFERENCE's own kernels (core/robust_kernel_impl.cpp compiled unmodified into
+// oracle/_ref/libg2o_ref_wrap.so, entered through oracle/ref_wrap.cpp); the restatement below stays as the cross-check of
+// tests/test_oracle.py (bit-equal) and as the formula sheet of the device code (csrc/kernels.cuh: robustify).
+inline void robustify_restated(int kind, double delta, double e2, double rho[3]);
 inline void robustify(int kind, double delta, double e2, double rho[3]) {
+  if (kind >= 1 && kind <= 5) { ref_robustify(kind, delta, e2, rho); return; }
+  robustify_restated(kind, delta, e2, rho);
+}
+inline void robustify_restated(int kind, double delta, double e2, double rho[3]) {
   const double dsqr = delta * delta;
   switch (kind) {
     case 1:  // RobustKernelHuber :65-79
@@ -1830,6 +1839,23 @@ int oracle_compute_marginals(oracle_graph* g, int nblocks, const int* rows, cons
   return g->linearSolver.solvePattern(g->Hpp, nblocks, rows, cols, out) ? 0 : -1;
 }
 void oracle_robustify(int kind, double delta, double e2, double* rho3) { robustify(kind, delta, e2, rho3); }
+void oracle_robustify_restated(int kind, double delta, double e2, double* rho3) { robustify_restated(kind, delta, e2, rho3); }
+// the restated SE2 algebra / 2D edge errors (what compute_error used before it called the reference's SE2 class), for the
+// cross-check against oracle/_ref
+void oracle_se2_restated(int what, const double* a, const double* b, const double* z, double* out) {
+  const SE2 A{a[0], a[1], a[2]};
+  if (what == 0) { const SE2 r = se2_mul(A, SE2{b[0], b[1], b[2]}); out[0] = r.x; out[1] = r.y; out[2] = r.th; }
+  else if (what == 1) { const SE2 r = se2_inv(A); out[0] = r.x; out[1] = r.y; out[2] = r.th; }
+  else if (what == 2) {  // EdgeSE2::computeError
+    const SE2 d = se2_mul(se2_inv(SE2{z[0], z[1], z[2]}), se2_mul(se2_inv(A), SE2{b[0], b[1], b[2]}));
+    out[0] = d.x; out[1] = d.y; out[2] = d.th;
+  } else {               // EdgeSE2PointXY::computeError
+    const SE2 xi = se2_inv(A);
+    const double c = cos(xi.th), s = sin(xi.th);
+    out[0] = (c * b[0] - s * b[1] + xi.x) - z[0];
+    out[1] = (s * b[0] + c * b[1] + xi.y) - z[1];
+  }
+}
 // apps/g2o_cli/g2o.cpp:322-336: one kernel of the given width on every edge
 int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta) {
   if (kind < 0 || kind > 5 || !(delta > 0)) return -1;

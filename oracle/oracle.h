@@ -4,7 +4,9 @@
  * The oracle is a from-scratch, Eigen-free restatement of the reference's CPU hot path
  * (g2o SparseOptimizer -> OptimizationAlgorithm{GaussNewton,Levenberg} -> BlockSolver ->
  * LinearSolverCSparse) that calls the reference's OWN vendored CSparse (compiled in place into
- * oracle/_ref/libg2o_csparse_ref.so) for ordering, symbolic analysis and numeric Cholesky.
+ * oracle/_ref/libg2o_csparse_ref.so) for ordering, symbolic analysis and numeric Cholesky, the reference's own
+ * compute_dq_dR (oracle/_ref/libg2o_slam3d_ref.so), and the reference's own robust kernels and SE2 class
+ * (oracle/_ref/libg2o_ref_wrap.so, entered through oracle/ref_wrap.cpp).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library.  The product (openslam_g2o_b200/) never links, imports or executes it.
@@ -77,7 +79,10 @@ int oracle_pcg_iterations(oracle_graph* g);   /* iterations of the last PCG solv
 /* one robust kernel on every edge (apps/g2o_cli/g2o.cpp:322-336; core/robust_kernel_impl.cpp:65-126):
  * kind 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 Saturated, 5 DCS */
 int oracle_set_robust_kernel(oracle_graph* g, int kind, double delta);
-void oracle_robustify(int kind, double delta, double e2, double* rho3);
+void oracle_robustify(int kind, double delta, double e2, double* rho3);   /* the reference's object code (oracle/_ref) */
+void oracle_robustify_restated(int kind, double delta, double e2, double* rho3);   /* the restatement, for the cross-check */
+/* restated SE2 algebra: what = 0 a*b, 1 a^-1, 2 EdgeSE2 error (a = v1, b = v2, z), 3 EdgeSE2PointXY error (a = pose, b = point, z) */
+void oracle_se2_restated(int what, const double* a, const double* b, const double* z, double* out);
 /* Edge::setRobustKernel on edge k (addEdge order) only */
 int oracle_set_edge_robust_kernel(oracle_graph* g, int k, int kind, double delta);
 /* Solver::computeMarginals -> LinearSolverCSparse::solvePattern -> MarginalCovarianceCholesky: blocks (rows[q], cols[q])

@@ -258,3 +258,55 @@ def test_oracle_pcg_matches_dense_solve(d):
     assert it2 <= it
     res = C.c_double(-1.0)
     assert L.oracle_pcg_solve(nb, d, p(cp), p(ri), p(vcm), p(x), p(b), C.c_double(1e-12), 1, 3, C.byref(res)) == 3
+
+
+@needs_oracle
+def test_robust_kernels_and_se2_are_the_reference_object_code_and_equal_the_restatement():
+    """The oracle's robustify calls the reference's OWN kernels (g2o/core/robust_kernel_impl.cpp with robust_kernel.cpp and
+    robust_kernel_factory.cpp compiled unmodified into oracle/_ref/libg2o_ref_wrap.so), and its 2D edge errors are evaluated
+    by the reference's own SE2 class (g2o/types/slam2d/se2.h instantiated by oracle/ref_wrap.cpp) - both behind the Eigen
+    shim of oracle/stub.  The restatements (the formula sheets of the device code) must agree with them: the kernels bit
+    for bit on both sides of every threshold, the SE2 algebra to the last ulp or two (the two translation units contract
+    products differently), and the device math (host build of csrc/geometry.cuh) with the reference's SE2 errors."""
+    import ctypes as C
+    import os
+    from oracle_binding import oracle_lib
+    L = oracle_lib()
+    from helpers import ROOT
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libg2o_ref_wrap.so"))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for f in (L.oracle_robustify, L.oracle_robustify_restated, R.ref_robustify):
+        f.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p]
+    rng = np.random.default_rng(12)
+    for kind in range(1, 6):
+        for _ in range(400):
+            delta = float(rng.uniform(0.1, 5.0))
+            e2 = float(rng.choice([rng.uniform(0, delta * delta), rng.uniform(delta * delta, 40 * delta * delta), delta * delta]))
+            a, b, c = np.zeros(3), np.zeros(3), np.zeros(3)
+            L.oracle_robustify(kind, delta, e2, p(a)); L.oracle_robustify_restated(kind, delta, e2, p(b)); R.ref_robustify(kind, delta, e2, p(c))
+            assert np.array_equal(a, c)            # the oracle IS the reference here
+            assert np.array_equal(a[:2], b[:2]), (kind, delta, e2, a, b)   # rho and rho' (what the path uses) bit for bit
+            assert np.allclose(a[2], b[2], rtol=1e-14, atol=0)
+    # SE2 algebra and the two 2D edge errors
+    G = C.CDLL(os.path.join(ROOT, "tests", "csrc", "libgeometry_host.so"))
+    worst = 0.0
+    for _ in range(2000):
+        a = np.array([rng.normal(0, 30), rng.normal(0, 30), rng.uniform(-np.pi, np.pi)])
+        b = np.array([rng.normal(0, 30), rng.normal(0, 30), rng.uniform(-np.pi, np.pi)])
+        z = np.array([rng.normal(0, 3), rng.normal(0, 3), rng.uniform(-np.pi, np.pi)])
+        l = rng.normal(0, 30, 2)
+        r_ref, r_res = np.zeros(3), np.zeros(3)
+        R.ref_se2_mul(p(a), p(b), p(r_ref)); L.oracle_se2_restated(0, p(a), p(b), p(z), p(r_res))
+        worst = max(worst, np.abs(r_ref - r_res).max() / 30)
+        R.ref_se2_inverse(p(a), p(r_ref)); L.oracle_se2_restated(1, p(a), p(b), p(z), p(r_res))
+        worst = max(worst, np.abs(r_ref - r_res).max() / 30)
+        R.ref_edge_se2_error(p(a), p(b), p(z), p(r_ref)); L.oracle_se2_restated(2, p(a), p(b), p(z), p(r_res))
+        worst = max(worst, np.abs(r_ref - r_res).max() / 60)
+        e_dev, A, B = np.zeros(3), np.zeros(9), np.zeros(9)
+        G.gh_se2(p(a), p(b), p(z), p(e_dev), p(A), p(B))                 # device math: EdgeSE2 error
+        worst = max(worst, np.abs(r_ref - e_dev).max() / 60)
+        e_ref, e_res, e_dev2 = np.zeros(2), np.zeros(2), np.zeros(2)
+        R.ref_edge_se2_xy_error(p(a), p(l), p(z), p(e_ref)); L.oracle_se2_restated(3, p(a), p(l), p(z), p(e_res))
+        G.gh_se2_xy(p(a), p(l), p(z), p(e_dev2), p(np.zeros(6)), p(np.zeros(4)))   # device math: EdgeSE2PointXY error
+        worst = max(worst, np.abs(e_ref - e_res).max() / 60, np.abs(e_ref - e_dev2).max() / 60)
+    assert worst <= 4 * np.finfo(float).eps, worst
