@@ -280,6 +280,41 @@ def test_loader_saver_and_index_mapping_of_the_new_tags(tmp_path):
             opt3.context.build_structure()
 
 
+def _golden(which):
+    """tests/golden/slam2d.npz / slam3d.npz (tests/golden/make_golden_synth.py): the oracle's 8-iteration LM trajectory on the
+    default synthetic graphs"""
+    from helpers import load_fixture
+    return load_fixture("slam3d" if which else "slam2d")
+
+
+def _check_against_golden(which, chi2, final_ids_est=None, tol=1e-9):
+    gd = _golden(which)
+    n = int(gd["iterations"])
+    assert len(chi2) == n
+    assert np.abs(np.asarray(chi2) - gd["chi2"]).max() <= tol * gd["chi2"].max()
+    if final_ids_est is not None:
+        ids, est = final_ids_est
+        assert np.array_equal(np.asarray(ids, np.int32), gd["final_ids"])
+        assert rel_err(est, gd["final_est"]) < max(tol, 1e-9) * 1e3
+    return gd
+
+
+@needs_oracle
+@pytest.mark.parametrize("which", [0, 1])
+def test_oracle_reproduces_the_committed_golden_trajectories(which):
+    """the committed vectors are what the oracle computes today (drift guard for the checker itself), and the synthetic
+    inputs are the seeded ones the vectors were made from"""
+    from oracle_binding import LM, fnv1a64
+    p = _problems()[which]
+    o = _oracle(p)
+    n, st = o.optimize(LM, 8)
+    ids = [int(i) for i in p["pose_ids"]] + [int(i) for i in p["lm_ids"]]
+    est = np.stack([np.pad(o.vertex_estimate(i), (0, 12))[:12] for i in ids])
+    gd = _check_against_golden(which, [s.chi2 for s in st[:n]], (ids, est), tol=1e-12)
+    assert [s.levenberg_iterations for s in st[:n]] == list(gd["lev"])
+    assert fnv1a64(o.block_perm()) == str(gd["perm_hash"]) and o.lnz() == int(gd["lnz"])
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _padded(o, p):
     """per Hessian index: dimension of the vertex (oracle order) -> scatter maps from the oracle's dense x / b to the padded
@@ -365,6 +400,7 @@ def test_landmark_slam_matches_oracle(which):
     cg2 = np.array([s.chi2 for s in opt2.batch_statistics])
     co2 = np.array([s.chi2 for s in st[:n_o]])
     assert np.abs(cg2 - co2).max() <= 1e-6 * co2.max(), (cg2, co2)
+    _check_against_golden(which, cg2, tol=1e-6)   # ... and against the committed golden vectors of the same graphs
     # LM trials per iteration: equal while chi2 still moves (at the converged state the accept / reject decision of a trial
     # is rounding noise in rho's numerator)
     for i in range(n_o):
