@@ -292,3 +292,35 @@ def test_sparse_inverse_on_an_ill_conditioned_graph_with_a_tail_chain(hx):
     assert found.all()
     err = max(np.abs(out[i].T - inv[i * d:(i + 1) * d, i * d:(i + 1) * d]).max() for i in range(nb))
     assert err <= 1e-6 * np.abs(inv).max()
+
+
+def test_camera_pair_index_of_the_wide_landmark_schur_kernel():
+    """schur_wide_kernel (csrc/kernels.cuh) turns a pair number q into the camera pair (a, b), a <= b, of a landmark seen by
+    k cameras - the enumeration the host plan uses for its segments (a ascending, b = a .. k-1).  The same arithmetic
+    (double sqrt guess + integer correction) here: every q for small k, the edges of every row for k up to the 65535-camera
+    limit"""
+    import math
+
+    def pair_of(q, k):
+        a = int(((2.0 * k + 1.0) - math.sqrt((2.0 * k + 1.0) * (2.0 * k + 1.0) - 8.0 * float(q))) * 0.5)
+        a = max(0, min(a, k - 1))
+        while a > 0 and a * k - a * (a - 1) // 2 > q:
+            a -= 1
+        while a + 1 < k and (a + 1) * k - (a + 1) * a // 2 <= q:
+            a += 1
+        return a, a + (q - (a * k - a * (a - 1) // 2))
+    for k in (1, 2, 3, 7, 64, 257):
+        q = 0
+        for a in range(k):
+            for b in range(a, k):
+                assert pair_of(q, k) == (a, b), (k, q)
+                q += 1
+    for k in (1401, 4096, 20000, 65535):
+        for a in list(range(0, k, max(1, k // 997))) + [k - 2, k - 1]:
+            if a < 0:
+                continue
+            first = a * k - a * (a - 1) // 2
+            assert pair_of(first, k) == (a, a)
+            assert pair_of(first + (k - 1 - a), k) == (a, k - 1)      # last pair of the row
+            if a > 0:
+                assert pair_of(first - 1, k) == (a - 1, k - 1)
